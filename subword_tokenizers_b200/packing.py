@@ -1,0 +1,231 @@
+"""Host-side packing: Python strings <-> the flat integer layouts the C ABI consumes.
+
+Nothing here computes a tokenization; it only changes representation:
+
+* words            -> UTF-8 byte arena + offsets          (north-star subsystem 1)
+* merges_list      -> (left id, right id, merged id) rank table with one id per DISTINCT
+                      string (reference keys are ``(str, str)``, bpe.py:200)
+* vocab (set[str]) -> sorted token list as code points    (reference trie input, utils.py:83-84)
+* word types       -> alphabet-id sequences + frequencies (reference bpe.py:73-81)
+* Python's ``str.isalnum`` / ``str.isspace`` as code-point bitmaps (reference
+  wordpiece.py:285-288 and utils.py:137 use the Python predicates)
+"""
+from __future__ import annotations
+
+from collections import Counter
+from typing import Dict, Iterable, List, Sequence, Tuple
+
+import numpy as np
+
+UNICODE_LIMIT = 0x110000
+
+# token id conventions of the C ABI (include/swt.h)
+BPE_UNKNOWN_CP = 0x40000000      # symbol for a code point no merge mentions
+BPE_EMPTY_TOKEN = 0xFFFFFFFE     # FastBPE.encode_word("") == [""]  (bpe.py:207-208)
+
+_class_cache: Dict[str, np.ndarray] = {}
+
+
+def unicode_class_bitmaps() -> Tuple[np.ndarray, np.ndarray]:
+    """(alnum, space) bitmaps, bit ``cp`` (little-endian within a byte) = ``chr(cp).isX()``."""
+    if "alnum" not in _class_cache:
+        alnum = np.zeros(UNICODE_LIMIT, dtype=np.uint8)
+        space = np.zeros(UNICODE_LIMIT, dtype=np.uint8)
+        for cp in range(UNICODE_LIMIT):
+            ch = chr(cp)
+            if ch.isalnum():
+                alnum[cp] = 1
+            elif ch.isspace():
+                space[cp] = 1
+        _class_cache["alnum"] = np.packbits(alnum, bitorder="little")
+        _class_cache["space"] = np.packbits(space, bitorder="little")
+    return _class_cache["alnum"], _class_cache["space"]
+
+
+def encode_utf8(word: str) -> bytes:
+    # lone surrogates are legal in a Python str; keep them round-trippable
+    return word.encode("utf-8", "surrogatepass")
+
+
+def decode_utf8(b: bytes) -> str:
+    return b.decode("utf-8", "surrogatepass")
+
+
+def pack_words(words: Sequence[str], offset_dtype=np.uint64) -> Tuple[np.ndarray, np.ndarray]:
+    """Byte arena + ``len(words)+1`` offsets."""
+    enc = [encode_utf8(w) for w in words]
+    lens = np.fromiter((len(b) for b in enc), dtype=np.uint64, count=len(enc))
+    off = np.zeros(len(enc) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    arena = np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if enc else np.zeros(0, dtype=np.uint8)
+    return arena, off.astype(offset_dtype, copy=False)
+
+
+def cps_of(s: str) -> np.ndarray:
+    return np.frombuffer(s.encode("utf-32-le", "surrogatepass"), dtype=np.uint32)
+
+
+def pack_strings_as_cps(strings: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
+    """Code-point arena (u32) + offsets (u64) for a list of strings."""
+    off = np.zeros(len(strings) + 1, dtype=np.uint64)
+    if strings:
+        np.cumsum(np.fromiter((len(s) for s in strings), dtype=np.uint64, count=len(strings)), out=off[1:])
+    cps = np.frombuffer("".join(strings).encode("utf-32-le", "surrogatepass"), dtype=np.uint32).copy()
+    return cps, off
+
+
+class BpeTables:
+    """Integer form of ``merges_list`` / ``_bpe_ranks`` (reference bpe.py:196,200,257).
+
+    ``id_to_str[i]`` is the string of symbol ``i``.  Ids are canonical per distinct string, in
+    order of first appearance while scanning merge ``k`` as (left, right, left+right).
+    """
+
+    def __init__(self, merges: Sequence[Tuple[str, str]]):
+        str_to_id: Dict[str, int] = {}
+        id_to_str: List[str] = []
+
+        def intern(s: str) -> int:
+            i = str_to_id.get(s)
+            if i is None:
+                i = len(id_to_str)
+                str_to_id[s] = i
+                id_to_str.append(s)
+            return i
+
+        n = len(merges)
+        left = np.zeros(n, dtype=np.uint32)
+        right = np.zeros(n, dtype=np.uint32)
+        new = np.zeros(n, dtype=np.uint32)
+        for k, pair in enumerate(merges):
+            a, b = pair[0], pair[1]
+            left[k] = intern(a)
+            right[k] = intern(b)
+            new[k] = intern(a + b)
+        self.left, self.right, self.new = left, right, new
+        self.id_to_str = id_to_str
+        self.str_to_id = str_to_id
+        chars = sorted((ord(s), i) for s, i in str_to_id.items() if len(s) == 1)
+        self.char_cp = np.array([c for c, _ in chars], dtype=np.uint32)
+        self.char_id = np.array([i for _, i in chars], dtype=np.uint32)
+
+    @property
+    def n_merges(self) -> int:
+        return int(self.left.shape[0])
+
+    def token_to_str(self, tok: int) -> str:
+        """Inverse of the C-ABI token encoding ``(symbol << 1) | continuation``."""
+        if tok == BPE_EMPTY_TOKEN:
+            return ""
+        sym, cont = tok >> 1, tok & 1
+        s = chr(sym & 0x1FFFFF) if sym & BPE_UNKNOWN_CP else self.id_to_str[sym]
+        return "##" + s if cont else s
+
+    def tokens_to_strs(self, toks: Iterable[int]) -> List[str]:
+        cache: Dict[int, str] = {}
+        out = []
+        for t in toks:
+            t = int(t)
+            s = cache.get(t)
+            if s is None:
+                s = cache[t] = self.token_to_str(t)
+            out.append(s)
+        return out
+
+
+class WpTables:
+    """Sorted vocabulary as code points; token id = index, ``n`` = "['UNK']", ``n+1`` = "[UNK]"."""
+
+    UNK_FAST = "['UNK']"   # reference wordpiece.py:257
+    UNK_NAIVE = "[UNK]"    # reference wordpiece.py:149
+
+    def __init__(self, vocab: Iterable[str]):
+        self.tokens: List[str] = sorted(set(vocab))
+        for t in self.tokens:
+            if any(ch.isspace() for ch in t):
+                # reference wordpiece.py:285 indexes past the end / crosses words for such vocabularies
+                raise NotImplementedError("vocabulary entries containing whitespace are outside the FastWP parity domain")
+        self.cps, self.off = pack_strings_as_cps(self.tokens)
+        self.id_to_str: List[str] = self.tokens + [self.UNK_FAST, self.UNK_NAIVE]
+
+    @property
+    def n_vocab(self) -> int:
+        return len(self.tokens)
+
+    def tokens_to_strs(self, toks: Iterable[int]) -> List[str]:
+        t = self.id_to_str
+        return [t[int(i)] for i in toks]
+
+
+class TrainTypes:
+    """Word types of a pre-tokenized corpus in first-occurrence order (reference bpe.py:73-81)."""
+
+    def __init__(self, words: Sequence[str]):
+        freqs = Counter(words)                        # insertion order == first occurrence
+        self.types: List[str] = list(freqs.keys())
+        self.freq = np.fromiter(freqs.values(), dtype=np.int64, count=len(freqs))
+        alphabet = sorted({ch for w in self.types for ch in w})
+        self.alphabet: List[str] = alphabet
+        cp_to_id = {ord(c): i for i, c in enumerate(alphabet)}
+        cps, off = pack_strings_as_cps(self.types)
+        if len(cps):
+            lut_keys = np.fromiter(cp_to_id.keys(), dtype=np.uint32, count=len(cp_to_id))
+            lut_vals = np.fromiter(cp_to_id.values(), dtype=np.uint32, count=len(cp_to_id))
+            order = np.argsort(lut_keys)
+            lut_keys, lut_vals = lut_keys[order], lut_vals[order]
+            self.syms = lut_vals[np.searchsorted(lut_keys, cps)].astype(np.uint32)
+        else:
+            self.syms = np.zeros(0, dtype=np.uint32)
+        self.off = off
+
+    @property
+    def n_types(self) -> int:
+        return len(self.types)
+
+    @property
+    def n_alpha(self) -> int:
+        return len(self.alphabet)
+
+    def merges_to_strs(self, left, right, new) -> Tuple[List[Tuple[str, str]], List[str]]:
+        """(left,right,new) id triples -> (merges_list, symbol strings)."""
+        strs: List[str] = list(self.alphabet)
+        merges: List[Tuple[str, str]] = []
+        for a, b, z in zip(left.tolist(), right.tolist(), new.tolist()):
+            merges.append((strs[a], strs[b]))
+            if z == len(strs):
+                strs.append(strs[a] + strs[b])
+            elif z > len(strs):
+                raise ValueError("merged id %d skips ahead of the symbol table (%d)" % (z, len(strs)))
+        return merges, strs
+
+
+class WpTrainTypes:
+    """Word types for NaiveWP.train (reference wordpiece.py:49-62): first char bare, the rest
+    prefixed with ``##``; one id per distinct initial symbol string."""
+
+    def __init__(self, words: Sequence[str]):
+        freqs = Counter(words)
+        self.types: List[str] = list(freqs.keys())
+        self.freq = np.fromiter(freqs.values(), dtype=np.int64, count=len(freqs))
+        sym_to_id: Dict[str, int] = {}
+        syms: List[int] = []
+        off = [0]
+        for w in self.types:
+            for k, c in enumerate(w):
+                s = c if k == 0 else "##" + c
+                i = sym_to_id.get(s)
+                if i is None:
+                    i = sym_to_id[s] = len(sym_to_id)
+                syms.append(i)
+            off.append(len(syms))
+        self.init_syms: List[str] = list(sym_to_id.keys())
+        self.syms = np.array(syms, dtype=np.uint32)
+        self.off = np.array(off, dtype=np.uint64)
+        self.init_cps, self.init_off = pack_strings_as_cps(self.init_syms)
+
+    def vocab_from_merges(self, left, right, new) -> List[str]:
+        strs: List[str] = list(self.init_syms)
+        for a, b, z in zip(left.tolist(), right.tolist(), new.tolist()):
+            if z == len(strs):
+                strs.append(strs[a] + strs[b][2:])        # wordpiece.py:95
+        return strs
