@@ -1,0 +1,231 @@
+/*
+ * swt.h -- C ABI of libswt.so, the B200 (sm_100a) implementation of the three hot paths of
+ * phtryll/subword-tokenizers:
+ *
+ *   HP-1  FastBPE.encode_word / tokenize      reference source/bpe.py:205-249
+ *   HP-2  FastWP.tokenize / matchloop         reference source/wordpiece.py:233-316, source/utils.py:66-139
+ *   HP-3  NaiveBPE.train (used by FastBPE)    reference source/bpe.py:50-112, :25-48
+ *
+ * The reference is pure Python and has no FFI of its own; the boundary it offers
+ * is the class surface NaiveBPE/FastBPE/NaiveWP/FastWP.  Each entry point below names the
+ * reference function it replaces.  The Python classes in subword_tokenizers_b200/ bind these
+ * with ctypes (INTEGRATION.md shows the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain C types only; every function returns an int status (SWT_OK == 0) unless stated;
+ *     swt_last_error() gives the message of the last failure on the calling thread.
+ *   - "d_" pointers are device pointers owned by the caller (the Python host owns them as torch
+ *     tensors); "h_" pointers are host pointers.  `stream` is a cudaStream_t passed as void*.
+ *   - hot calls (encode, train_step*) allocate nothing and only enqueue work on `stream`;
+ *     they are asynchronous unless stated.  *_create / *_host calls may allocate and synchronise.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Data layouts
+ *   word arena     UTF-8 bytes of all words back to back (no separators)          uint8
+ *   word offsets   n_words+1 byte offsets into the arena                          uint32  (arena < 4 GiB per call)
+ *   token ids      compact, words in input order                                  uint32
+ *   token offsets  n_words+1 offsets into the token ids (optional, may be NULL)   uint32
+ *
+ * Token id spaces
+ *   BPE:  token = (symbol << 1) | continuation.  continuation=1 is the "##" prefix of
+ *         symbols[1:] (bpe.py:240-241).  symbol is the caller's id for a string mentioned by the
+ *         merge list, or SWT_BPE_UNKNOWN_CP | code point for a character no merge mentions.
+ *         The empty word yields the single token SWT_BPE_EMPTY_TOKEN (bpe.py:207-208).
+ *   WP:   token = index into the caller's (sorted) vocabulary; n_vocab is "['UNK']"
+ *         (wordpiece.py:257) and n_vocab+1 is "[UNK]" (wordpiece.py:149, via the "##" corner :260-261).
+ */
+#ifndef SWT_H
+#define SWT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWT_ABI_VERSION 1
+
+#define SWT_OK 0
+#define SWT_ERR_CUDA 1          /* a CUDA runtime call failed (no device, OOM, launch failure) */
+#define SWT_ERR_ARG 2           /* invalid argument */
+#define SWT_ERR_CAPACITY 3      /* an output or workspace capacity was too small */
+#define SWT_ERR_INTERNAL 4      /* device-side consistency check failed */
+
+#define SWT_BPE_UNKNOWN_CP 0x40000000u
+#define SWT_BPE_EMPTY_TOKEN 0xFFFFFFFEu
+
+/* ---- library ------------------------------------------------------------------------------ */
+int swt_abi_version(void);
+const char *swt_last_error(void);
+int swt_device_count(int *count);
+
+/* ---- HP-1: FastBPE rank table + encode ------------------------------------------------------ */
+/*
+ * swt_bpe_table_create  replaces  FastBPE._bpe_ranks = {pair: i ...}   (bpe.py:200, :257)
+ *   merge k is (left[k], right[k]) -> merged[k]; ids are the caller's, canonical per distinct
+ *   string; a pair listed twice keeps its LAST rank (dict semantics).  char_cp (ascending) /
+ *   char_id map a code point to the id of its one-character symbol.
+ *   The table (open-addressing hash, key = left<<32|right) is built on the host and uploaded to
+ *   `device`.
+ */
+typedef struct swt_bpe_table swt_bpe_table;
+int swt_bpe_table_create(const uint32_t *h_left, const uint32_t *h_right, const uint32_t *h_merged, uint32_t n_merges,
+                         const uint32_t *h_char_cp, const uint32_t *h_char_id, uint32_t n_chars, int device,
+                         swt_bpe_table **out);
+void swt_bpe_table_destroy(swt_bpe_table *t);
+
+/* Words longer than SWT_SHORT_WORD_BYTES leave the shared-memory fast path; `long_word_bytes` is the
+ * total byte length of those words (pass the arena size when unknown).
+ * swt_encode_workspace_bytes: bytes of device workspace an encode call needs (same for BPE and WP). */
+#define SWT_SHORT_WORD_BYTES 32
+size_t swt_encode_workspace_bytes(uint32_t n_words, uint64_t long_word_bytes);
+
+/*
+ * swt_bpe_encode  replaces  [tok for w in words for tok in FastBPE.encode_word(w)]   (bpe.py:205-249)
+ *   d_status (8 x u32): [0] SWT_OK / SWT_ERR_CAPACITY / SWT_ERR_INTERNAL, [1] total tokens (low 32 bits,
+ *   [3] high bits; also written to d_out_tok_off[n_words] when that is not NULL), [2] H6 events (WP).
+ *   Asynchronous on `stream`; returns only argument/launch errors.
+ */
+int swt_bpe_encode(const swt_bpe_table *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
+                   uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off,
+                   void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream);
+
+/* ---- HP-2: WordPiece trie + encode ------------------------------------------------------------ */
+/*
+ * swt_wp_trie_create  replaces  WPTrie_E2E(vocab)   (utils.py:75-139; insert :87-105, precompute :108-139)
+ *   vocab token v is the code points h_vocab_cps[h_vocab_off[v] .. h_vocab_off[v+1]).
+ *   h_alnum_bitmap: 0x110000 bits, bit cp = Python's chr(cp).isalnum() (utils.py:137,
+ *   wordpiece.py:287-288 use the Python predicates; the bitmap is copied to the device).
+ *   The trie, failure links and failure pops are computed on the host and flattened into
+ *   device tables.  n_sharp_special/sharp_special give NaiveWP.encode_word("##")
+ *   (wordpiece.py:260-261), which the caller evaluates once.
+ */
+typedef struct swt_wp_trie swt_wp_trie;
+int swt_wp_trie_create(const uint32_t *h_vocab_cps, const uint64_t *h_vocab_off, uint32_t n_vocab,
+                       const uint8_t *h_alnum_bitmap, const uint32_t *h_sharp_special, uint32_t n_sharp_special,
+                       int device, swt_wp_trie **out);
+void swt_wp_trie_destroy(swt_wp_trie *t);
+/* nodes / edges / pops / nodes whose failure link is root_p (SURVEY.md §8 a7 figures) */
+int swt_wp_trie_stats(const swt_wp_trie *t, uint64_t *n_nodes, uint64_t *n_edges, uint64_t *n_pops, uint64_t *n_rootp);
+
+/*
+ * swt_wp_encode  replaces  FastWP.tokenize   (wordpiece.py:233-270 + matchloop :291-316)
+ *   Each input "word" is a whitespace-free chunk of the lower-cased text (the host splits on
+ *   Python str.isspace); the kernel appends the virtual " " of wordpiece.py:248 itself.
+ *   H6 extension: on a punctuation character that is not a child of the trie root
+ *   the reference never terminates; this implementation emits "['UNK']" and advances one
+ *   character, and counts such events in d_status[2].
+ *   Status / outputs as swt_bpe_encode.
+ */
+int swt_wp_encode(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
+                  uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off,
+                  void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream);
+
+/* ---- host-buffer entry points (what a non-Python integrator binds) ------------------------------- */
+/*
+ * Same results as the device-pointer calls above, but inputs and outputs are HOST buffers:
+ * the call stages the corpus through the GPU in batches (H2D, encode, D2H overlapped on
+ * separate streams) and returns when h_out_ids / h_out_tok_off are complete.
+ * which: 0 = BPE (table is a swt_bpe_table*), 1 = WP (table is a swt_wp_trie*).
+ * h_out_tok_off may be NULL.  n_tokens receives the total; h6_events may be NULL.
+ */
+typedef struct swt_pipeline swt_pipeline;
+int swt_pipeline_create(int device, uint64_t batch_bytes, swt_pipeline **out);
+void swt_pipeline_destroy(swt_pipeline *p);
+/* h_word_off: n_words+1 u32 byte offsets (arena < 4 GiB per call; split larger corpora);
+ * h_out_tok_off: n_words+1 u32 or NULL.  Pinned host buffers (swt_host_alloc) let the copies overlap. */
+int swt_encode_host(swt_pipeline *p, int which, const void *table, const uint8_t *h_arena, const uint32_t *h_word_off,
+                    uint64_t n_words, uint32_t *h_out_ids, uint64_t out_cap, uint32_t *h_out_tok_off,
+                    uint64_t *n_tokens, uint64_t *h6_events);
+/* pinned host allocation helpers so integrators can give the pipeline DMA-able buffers */
+int swt_host_alloc(void **ptr, size_t bytes);
+void swt_host_free(void *ptr);
+
+/* ---- HP-3: BPE training ---------------------------------------------------------------------------- */
+/*
+ * Replaces the merge loop of NaiveBPE.train (bpe.py:88-111): pair-frequency count (:90-95),
+ * argmax with first-inserted tie-break (:102), vocabulary/merge-list update (:103-104) and the
+ * merge-apply over every word (:108-111 -> _replace_pair :25-48).
+ *
+ * Inputs are the word types in first-occurrence order (bpe.py:77-81) as sequences of alphabet
+ * ids 0..n_alpha-1 (one per distinct code point) with their frequencies.  Merged symbols get ids
+ * n_alpha, n_alpha+1, ... in order of first creation of each DISTINCT string (a merge whose
+ * concatenation already exists reuses that id and does not grow the vocabulary, bpe.py:103).
+ *
+ * Multi-GPU: word types are sharded by contiguous ranges; every rank holds `n_types_local`
+ * types starting at global symbol slot `slot_base` and a replica of the pair-count table.
+ * One training step is split in three phases so that the caller can run the two small
+ * collectives (NCCL through torch.distributed) between them on the same stream:
+ *
+ *     swt_bpe_train_select   argmax over the replicated table + local tie-break scan
+ *                            -> candidate record (16 B) at cand_ptr          [all_gather if world>1]
+ *     swt_bpe_train_merge    resolve winner, name the new symbol, mark + apply the merge
+ *                            in place, emit pair-count deltas at delta_ptr   [all_reduce(SUM) if world>1]
+ *     swt_bpe_train_update   fold the deltas into the replicated table
+ *
+ * swt_bpe_train_steps runs `n_steps` whole steps back to back for world == 1.
+ * All phases are asynchronous and self-gating: once the trainer halts (vocabulary reached,
+ * no pairs left, table must grow, record buffer full, error) the remaining launches are no-ops.
+ */
+typedef struct swt_bpe_trainer swt_bpe_trainer;
+
+typedef struct swt_bpe_train_config {
+    uint64_t n_types_local;    /* word types on this rank */
+    uint64_t n_slots_local;    /* total symbols of those types (< 2^32) */
+    uint64_t slot_base;        /* global index of this rank's first symbol slot */
+    uint32_t n_alpha;          /* alphabet size (global) */
+    int64_t  max_vocab;        /* stop when the vocabulary reaches this size (bpe.py:88) */
+    int64_t  initial_vocab;    /* number of distinct code points present globally (bpe.py:75) */
+    uint32_t max_word_len;     /* longest word type in symbols (global) */
+    uint32_t record_cap;       /* merges recorded between two swt_bpe_train_read calls */
+    uint32_t world_size;       /* number of ranks sharing the job */
+    uint32_t rank;
+    uint64_t table_cap;        /* pair-table slots (power of two); 0 = choose */
+} swt_bpe_train_config;
+
+/* host-visible snapshot of the trainer state */
+typedef struct swt_bpe_train_state {
+    uint32_t halt;             /* 0 running, 1 done (vocab reached), 2 done (no pairs), 3 table must grow,
+                                  4 record buffer full, >=16 error */
+    uint32_t n_recorded;       /* merges in the record buffer */
+    uint64_t n_merges_total;   /* merges since create */
+    int64_t  vocab_size;
+    uint64_t n_symbols;        /* distinct symbol strings so far */
+    uint64_t n_table_entries;
+    uint64_t table_cap;
+    uint64_t n_live_slots;     /* live symbols on this rank */
+} swt_bpe_train_state;
+
+size_t swt_bpe_train_workspace_bytes(const swt_bpe_train_config *cfg);
+/* d_syms/d_off/d_freq: this rank's types (u32 symbol ids, u64 offsets n_types_local+1, i64 freqs) */
+int swt_bpe_train_create(const swt_bpe_train_config *cfg, const uint32_t *d_syms, const uint64_t *d_off,
+                         const int64_t *d_freq, void *d_workspace, size_t workspace_bytes, void *stream,
+                         swt_bpe_trainer **out);
+void swt_bpe_train_destroy(swt_bpe_trainer *t);
+/* device addresses/sizes of the exchange buffers, for the caller's collectives */
+int swt_bpe_train_buffers(const swt_bpe_trainer *t, void **init_counts_ptr, uint64_t *init_counts_elems /* i64 */,
+                          void **cand_ptr /* 2 x u64 */, void **cand_gather_ptr /* world x 2 x u64 */,
+                          void **delta_ptr, uint64_t *delta_elems /* i64 */);
+/* initial pair count: local dense count -> [all_reduce(SUM) over init_counts] -> table build */
+int swt_bpe_train_count_local(swt_bpe_trainer *t, void *stream);
+int swt_bpe_train_build_table(swt_bpe_trainer *t, void *stream);
+int swt_bpe_train_select(swt_bpe_trainer *t, void *stream);
+int swt_bpe_train_merge(swt_bpe_trainer *t, void *stream);
+int swt_bpe_train_update(swt_bpe_trainer *t, void *stream);
+int swt_bpe_train_steps(swt_bpe_trainer *t, uint32_t n_steps, void *stream);
+/* synchronises `stream`, copies out the recorded merges (left,right,new ids + chosen pair count)
+   and the state; resets the record buffer and clears halt==4. Arrays need record_cap entries. */
+int swt_bpe_train_read(swt_bpe_trainer *t, uint32_t *h_left, uint32_t *h_right, uint32_t *h_new, int64_t *h_count,
+                       swt_bpe_train_state *state, void *stream);
+/* replaces the pair table by one of `new_cap` slots inside a caller-provided buffer; clears halt==3 */
+size_t swt_bpe_train_table_bytes(uint64_t cap);
+int swt_bpe_train_grow_table(swt_bpe_trainer *t, void *d_new_table, uint64_t new_cap, void *stream);
+/* copies the current segmentation of this rank's types to the host: symbol ids + per-type lengths */
+int swt_bpe_train_read_corpus(swt_bpe_trainer *t, uint32_t *h_syms /* n_slots_local */, uint32_t *h_len /* n_types_local */,
+                              void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWT_H */

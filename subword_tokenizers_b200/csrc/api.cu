@@ -1,0 +1,45 @@
+// api.cu -- library-level entry points of libswt: errors, versioning, workspace layout, pinned memory.
+#include "encode.cuh"
+
+namespace swt {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+size_t encode_workspace_layout(uint32_t n_words, uint64_t long_bytes, void *base, EncodeWorkspace *ws) {
+    Carver cv(base);
+    const uint32_t n_tiles = (n_words + kTileWords - 1) / kTileWords;
+    ws->n_tiles = n_tiles;
+    ws->tile_state = cv.take<uint64_t>(n_tiles + 1);
+    ws->ticket = cv.take<uint32_t>(1);
+    ws->long_cursor = cv.take<uint32_t>(1);
+    ws->long_scratch_elems = 2 * long_bytes;
+    ws->long_scratch = cv.take<uint32_t>(ws->long_scratch_elems + 1);
+    return cv.used();
+}
+
+}  // namespace swt
+
+using namespace swt;
+
+SWT_API int swt_abi_version(void) { return SWT_ABI_VERSION; }
+SWT_API const char *swt_last_error(void) { return g_last_error.c_str(); }
+
+SWT_API int swt_device_count(int *count) {
+    SWT_REQUIRE(count != nullptr, "count is NULL");
+    *count = 0;
+    SWT_CUDA_OK(cudaGetDeviceCount(count));
+    return SWT_OK;
+}
+
+SWT_API size_t swt_encode_workspace_bytes(uint32_t n_words, uint64_t long_word_bytes) {
+    EncodeWorkspace ws;
+    return encode_workspace_layout(n_words, long_word_bytes, nullptr, &ws);
+}
+
+SWT_API int swt_host_alloc(void **ptr, size_t bytes) {
+    SWT_REQUIRE(ptr != nullptr, "ptr is NULL");
+    SWT_CUDA_OK(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SWT_OK;
+}
+SWT_API void swt_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }

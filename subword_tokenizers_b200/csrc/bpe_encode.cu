@@ -1,0 +1,323 @@
+// bpe_encode.cu -- HP-1: FastBPE.encode_word (reference source/bpe.py:205-243) on sm_100a.
+//
+// Rank table: open-addressing hash, 16-byte slots {left, right, rank, merged}; one 128-bit load per
+// probe, key = left<<32|right.  Built on the host from the merge list (last rank wins for a pair that
+// is listed twice, bpe.py:200,257) and uploaded once per table.
+//
+// Kernel: see encode.cuh for the tile skeleton.  Per word (one thread, symbols in a shared-memory
+// column): repeat { min rank over the adjacent pairs (bpe.py:212-217); greedy left-to-right
+// replacement of every occurrence (:221-235) } until no ranked pair is left or one symbol remains.
+// Words longer than kShortBytes are processed by the whole CTA in global scratch.
+#include <vector>
+
+#include "encode.cuh"
+
+namespace swt {
+
+struct BpeTableDev {
+    const uint4 *slots;      // {left, right, rank, merged}; rank == 0xFFFFFFFF marks an empty slot
+    uint32_t mask;           // n_slots - 1
+    const uint32_t *bmp_lut; // 65536 entries: code point -> symbol id or 0xFFFFFFFF
+    const uint32_t *hi_cp;   // sorted code points >= 0x10000 that have a symbol
+    const uint32_t *hi_id;
+    uint32_t n_hi;
+    const uint32_t *m_left, *m_right, *m_new;   // by rank
+    uint32_t n_merges;
+};
+
+}  // namespace swt
+
+struct swt_bpe_table {
+    swt::BpeTableDev dev;
+    int device;
+    void *d_blob;
+};
+
+namespace swt {
+
+constexpr uint32_t kEmptyRank = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t bpe_char_symbol(const BpeTableDev &t, uint32_t cp) {
+    uint32_t id = 0xFFFFFFFFu;
+    if (cp < 0x10000u) id = __ldg(&t.bmp_lut[cp]);
+    else {
+        uint32_t lo = 0, hi = t.n_hi;
+        while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (__ldg(&t.hi_cp[mid]) < cp) lo = mid + 1; else hi = mid; }
+        if (lo < t.n_hi && __ldg(&t.hi_cp[lo]) == cp) id = __ldg(&t.hi_id[lo]);
+    }
+    return id == 0xFFFFFFFFu ? (SWT_BPE_UNKNOWN_CP | cp) : id;
+}
+
+// returns rank (kEmptyRank when the pair is not in the table); merged id in `merged`
+__device__ __forceinline__ uint32_t bpe_probe(const BpeTableDev &t, uint32_t a, uint32_t b, uint32_t &merged) {
+    if ((a | b) & SWT_BPE_UNKNOWN_CP) return kEmptyRank;          // characters no merge mentions
+    uint32_t h = (uint32_t)mix64(((uint64_t)a << 32) | b) & t.mask;
+    for (;;) {
+        uint4 e = __ldg(&t.slots[h]);
+        if (e.z == kEmptyRank) return kEmptyRank;
+        if (e.x == a && e.y == b) { merged = e.w; return e.z; }
+        h = (h + 1) & t.mask;
+    }
+}
+
+// ---- short words: one thread, symbols in a shared-memory column (stride = kTileWords) ------------------
+__device__ __forceinline__ uint32_t bpe_encode_short(const BpeTableDev &t, const uint8_t *p, uint32_t nbytes,
+                                                     uint32_t *col) {
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < nbytes;) {
+        uint32_t adv; uint32_t cp = utf8_decode(p + i, nbytes - i, adv); i += adv;
+        col[n * kTileWords] = bpe_char_symbol(t, cp); ++n;
+    }
+    if (n == 0) { col[0] = SWT_BPE_EMPTY_TOKEN; return 1; }       // bpe.py:207-208
+    while (n >= 2) {
+        uint32_t best = kEmptyRank, ba = 0, bb = 0, bz = 0;
+        uint32_t prev = col[0];
+        for (uint32_t i = 0; i + 1 < n; ++i) {
+            uint32_t cur = col[(i + 1) * kTileWords], z;
+            uint32_t r = bpe_probe(t, prev, cur, z);
+            if (r < best) { best = r; ba = prev; bb = cur; bz = z; }
+            prev = cur;
+        }
+        if (best == kEmptyRank) break;
+        uint32_t r = 0, o = 0;
+        while (r < n) {
+            uint32_t s = col[r * kTileWords];
+            if (r + 1 < n && s == ba && col[(r + 1) * kTileWords] == bb) { col[o * kTileWords] = bz; r += 2; }
+            else { col[o * kTileWords] = s; r += 1; }
+            ++o;
+        }
+        n = o;
+    }
+    for (uint32_t k = 0; k < n; ++k) col[k * kTileWords] = (col[k * kTileWords] << 1) | (k > 0);
+    return n;
+}
+
+// ---- long words: the whole CTA works on one word in global scratch ------------------------------------
+// src/dst are ping-pong symbol buffers of at least nbytes entries. Returns the final symbol count;
+// *result points at the buffer holding the final symbols (already shifted into token form).
+__device__ uint32_t bpe_encode_long(const BpeTableDev &t, const uint8_t *p, uint32_t nbytes, uint32_t *bufA,
+                                    uint32_t *bufB, uint32_t **result, uint32_t *sh_scan /*33*/, uint32_t *sh_misc /*8*/) {
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    // 1. UTF-8 decode in chunks of blockDim bytes: a byte starts a character unless it is 10xxxxxx
+    uint32_t n = 0;
+    for (uint32_t base = 0; base < nbytes; base += nt) {
+        uint32_t i = base + tid;
+        uint32_t is_start = (i < nbytes) && ((p[i] & 0xC0u) != 0x80u);
+        uint32_t total, excl = block_exclusive_scan(is_start, sh_scan, &total);
+        if (is_start) { uint32_t adv; uint32_t cp = utf8_decode(p + i, nbytes - i, adv); bufA[n + excl] = bpe_char_symbol(t, cp); }
+        n += total;
+    }
+    __syncthreads();
+    uint32_t *src = bufA, *dst = bufB;
+    while (n >= 2) {
+        // 2. min rank over all adjacent pairs
+        uint32_t best = kEmptyRank;
+        for (uint32_t i = tid; i + 1 < n; i += nt) { uint32_t z; uint32_t r = bpe_probe(t, src[i], src[i + 1], z); best = min(best, r); }
+        for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+        if ((tid & 31) == 0) sh_scan[tid >> 5] = best;
+        __syncthreads();
+        if (tid == 0) { uint32_t b = kEmptyRank; for (uint32_t w = 0; w < (nt >> 5); ++w) b = min(b, sh_scan[w]); sh_misc[0] = b; }
+        __syncthreads();
+        best = sh_misc[0];
+        __syncthreads();
+        if (best == kEmptyRank) break;
+        const uint32_t a = __ldg(&t.m_left[best]), b = __ldg(&t.m_right[best]), z = __ldg(&t.m_new[best]);
+        // 3. greedy left-to-right replacement; each thread owns one contiguous segment
+        const uint32_t seg = (n + nt - 1) / nt;
+        const uint32_t lo = min(n, tid * seg), hi = min(n, lo + seg);
+        // is element `lo` the right half of a pair selected by an earlier segment?  For a != b
+        // matches cannot overlap; for a == b walk back over the run of a's to get the parity.
+        uint32_t i = lo;
+        if (lo < hi && lo > 0) {
+            if (a != b) { if (src[lo - 1] == a && src[lo] == b) i = lo + 1; }
+            else if (src[lo] == a) {
+                uint32_t k = lo; while (k > 0 && src[k - 1] == a) --k;      // run start
+                if ((lo - k) & 1u) i = lo + 1;                                // lo is consumed as a right half
+            }
+        }
+        const uint32_t first = i;
+        uint32_t cnt = 0;
+        while (i < hi) { if (i + 1 < n && src[i] == a && src[i + 1] == b) i += 2; else i += 1; ++cnt; }
+        uint32_t total, excl = block_exclusive_scan(cnt, sh_scan, &total);
+        i = first; uint32_t o = excl;
+        while (i < hi) {
+            if (i + 1 < n && src[i] == a && src[i + 1] == b) { dst[o++] = z; i += 2; }
+            else { dst[o++] = src[i]; i += 1; }
+        }
+        __syncthreads();
+        n = total;
+        uint32_t *tmp = src; src = dst; dst = tmp;
+    }
+    for (uint32_t k = tid; k < n; k += nt) src[k] = (src[k] << 1) | (k > 0);
+    __syncthreads();
+    *result = src;
+    return n;
+}
+
+__global__ void __launch_bounds__(kTileWords)
+bpe_encode_kernel(BpeTableDev t, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off,
+                  uint32_t n_words, uint32_t *__restrict__ out_ids, uint64_t out_cap, uint32_t *__restrict__ out_tok_off,
+                  uint32_t tok_base, EncodeWorkspace ws, uint32_t *status) {
+    __shared__ uint32_t stage[kShortBytes * kTileWords];   // 32 KB: token/symbol columns
+    __shared__ uint32_t sh_scan[33];
+    __shared__ uint32_t sh_misc[8];
+    __shared__ uint64_t sh_base;
+    __shared__ uint32_t sh_long_list[kTileWords];
+    __shared__ uint32_t *sh_long_ptr[kTileWords];
+    const uint32_t tid = threadIdx.x;
+    for (;;) {
+        if (tid == 0) { sh_misc[4] = atomicAdd(ws.ticket, 1u); sh_misc[5] = 0; }
+        __syncthreads();
+        const uint32_t tile = sh_misc[4];
+        if (tile >= ws.n_tiles) break;
+        const uint32_t w = tile * kTileWords + tid;
+        const bool valid = w < n_words;
+        uint32_t b0 = 0, nbytes = 0, count = 0;
+        if (valid) { b0 = word_off[w]; nbytes = word_off[w + 1] - b0; }
+        const bool is_long = valid && nbytes > kShortBytes;
+        if (valid && !is_long) count = bpe_encode_short(t, arena + b0, nbytes, stage + tid);
+        if (is_long) sh_long_list[atomicAdd(&sh_misc[5], 1u)] = tid;
+        __syncthreads();
+        const uint32_t n_long = sh_misc[5];
+        __syncthreads();
+        for (uint32_t k = 0; k < n_long; ++k) {                     // CTA-uniform loop
+            const uint32_t owner = sh_long_list[k];
+            const uint32_t lw = tile * kTileWords + owner;
+            const uint32_t lb0 = word_off[lw], lnb = word_off[lw + 1] - lb0;
+            if (tid == 0) sh_misc[6] = atomicAdd(ws.long_cursor, 2u * lnb);
+            __syncthreads();
+            const uint64_t so = sh_misc[6];
+            uint32_t *res = nullptr; uint32_t c = 0;
+            if (so + 2ull * lnb <= ws.long_scratch_elems) {
+                c = bpe_encode_long(t, arena + lb0, lnb, ws.long_scratch + so, ws.long_scratch + so + lnb, &res, sh_scan, sh_misc);
+            } else if (tid == 0) atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY);
+            if (tid == owner) { count = c; sh_long_ptr[owner] = res; }
+            __syncthreads();
+        }
+        uint32_t total, excl = block_exclusive_scan(count, sh_scan, &total);
+        if (tid == 0) sh_base = tile_exclusive_prefix(ws.tile_state, tile, total, &status[kStatusCode]);
+        __syncthreads();
+        const uint64_t pos = sh_base + excl;
+        if (valid) {
+            if (out_tok_off) out_tok_off[w] = tok_base + (uint32_t)pos;
+            if (pos + count <= out_cap) {
+                if (!is_long) { for (uint32_t k = 0; k < count; ++k) out_ids[pos + k] = stage[k * kTileWords + tid]; }
+            } else atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY);
+        }
+        for (uint32_t k = 0; k < n_long; ++k) {                     // long results: coalesced CTA copy
+            const uint32_t owner = sh_long_list[k];
+            __syncthreads();
+            if (tid == owner) { sh_misc[6] = count; sh_misc[7] = excl; }
+            __syncthreads();
+            const uint32_t lc = sh_misc[6]; const uint64_t lpos = sh_base + sh_misc[7];
+            const uint32_t *src = sh_long_ptr[owner];
+            if (src && lpos + lc <= out_cap) for (uint32_t i = tid; i < lc; i += blockDim.x) out_ids[lpos + i] = src[i];
+        }
+        if (tile == ws.n_tiles - 1 && tid == 0) {
+            const uint64_t grand = sh_base + total;
+            if (out_tok_off) out_tok_off[n_words] = tok_base + (uint32_t)grand;
+            status[kStatusTokens] = (uint32_t)grand; status[kStatusTokensHi] = (uint32_t)(grand >> 32);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace swt
+
+using namespace swt;
+
+SWT_API int swt_bpe_table_create(const uint32_t *h_left, const uint32_t *h_right, const uint32_t *h_merged, uint32_t n_merges,
+                                 const uint32_t *h_char_cp, const uint32_t *h_char_id, uint32_t n_chars, int device,
+                                 swt_bpe_table **out) {
+    SWT_REQUIRE(out != nullptr, "out is NULL");
+    SWT_REQUIRE(n_merges == 0 || (h_left && h_right && h_merged), "merge arrays are NULL");
+    SWT_REQUIRE(n_chars == 0 || (h_char_cp && h_char_id), "char arrays are NULL");
+    SWT_REQUIRE(n_merges < 0x7FFFFFFFu, "too many merges");
+    SWT_CUDA_OK(cudaSetDevice(device));
+    const uint64_t n_slots = next_pow2((uint64_t)n_merges * 2 + 16);
+    std::vector<uint4> slots(n_slots, make_uint4(0, 0, kEmptyRank, 0));
+    for (uint32_t k = 0; k < n_merges; ++k) {
+        SWT_REQUIRE(!((h_left[k] | h_right[k] | h_merged[k]) & 0xC0000000u), "symbol ids must be < 2^30");
+        uint64_t h = mix64(((uint64_t)h_left[k] << 32) | h_right[k]) & (n_slots - 1);
+        while (slots[h].z != kEmptyRank && !(slots[h].x == h_left[k] && slots[h].y == h_right[k])) h = (h + 1) & (n_slots - 1);
+        slots[h] = make_uint4(h_left[k], h_right[k], k, h_merged[k]);      // last rank wins (dict semantics)
+    }
+    std::vector<uint32_t> lut(65536, 0xFFFFFFFFu), hi_cp, hi_id;
+    for (uint32_t i = 0; i < n_chars; ++i) {
+        SWT_REQUIRE(i == 0 || h_char_cp[i] > h_char_cp[i - 1], "char_cp must be strictly ascending");
+        if (h_char_cp[i] < 0x10000u) lut[h_char_cp[i]] = h_char_id[i];
+        else { hi_cp.push_back(h_char_cp[i]); hi_id.push_back(h_char_id[i]); }
+    }
+    // one device blob: slots | lut | hi_cp | hi_id | m_left | m_right | m_new
+    Carver sz(nullptr);
+    sz.take<uint4>(n_slots); sz.take<uint32_t>(65536); sz.take<uint32_t>(hi_cp.size() + 1); sz.take<uint32_t>(hi_id.size() + 1);
+    sz.take<uint32_t>(n_merges + 1); sz.take<uint32_t>(n_merges + 1); sz.take<uint32_t>(n_merges + 1);
+    void *blob = nullptr;
+    SWT_CUDA_OK(cudaMalloc(&blob, sz.used()));
+    Carver cv(blob);
+    uint4 *d_slots = cv.take<uint4>(n_slots);
+    uint32_t *d_lut = cv.take<uint32_t>(65536);
+    uint32_t *d_hicp = cv.take<uint32_t>(hi_cp.size() + 1), *d_hiid = cv.take<uint32_t>(hi_id.size() + 1);
+    uint32_t *d_l = cv.take<uint32_t>(n_merges + 1), *d_r = cv.take<uint32_t>(n_merges + 1), *d_n = cv.take<uint32_t>(n_merges + 1);
+    cudaError_t e = cudaMemcpy(d_slots, slots.data(), n_slots * sizeof(uint4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_lut, lut.data(), 65536 * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !hi_cp.empty()) e = cudaMemcpy(d_hicp, hi_cp.data(), hi_cp.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !hi_id.empty()) e = cudaMemcpy(d_hiid, hi_id.data(), hi_id.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_merges) e = cudaMemcpy(d_l, h_left, n_merges * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_merges) e = cudaMemcpy(d_r, h_right, n_merges * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_merges) e = cudaMemcpy(d_n, h_merged, n_merges * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(blob); set_error(std::string("table upload: ") + cudaGetErrorString(e)); return SWT_ERR_CUDA; }
+    swt_bpe_table *t = new swt_bpe_table();
+    t->dev = BpeTableDev{d_slots, (uint32_t)(n_slots - 1), d_lut, d_hicp, d_hiid, (uint32_t)hi_cp.size(), d_l, d_r, d_n, n_merges};
+    t->device = device; t->d_blob = blob;
+    *out = t;
+    return SWT_OK;
+}
+
+SWT_API void swt_bpe_table_destroy(swt_bpe_table *t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    cudaFree(t->d_blob);
+    delete t;
+}
+
+namespace swt {
+int encode_grid(const void *kernel, int block) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    int dev = 0, sms = kNumSMs;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms * per_sm;
+}
+}  // namespace swt
+
+namespace swt {
+int bpe_encode_launch(const swt_bpe_table *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
+                      uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off, uint32_t tok_base,
+                      void *d_workspace, size_t workspace_bytes, uint32_t *d_status, cudaStream_t st) {
+    SWT_REQUIRE(t && d_word_off && d_status && d_workspace, "NULL argument");
+    SWT_REQUIRE(n_words == 0 || (d_arena && d_out_ids), "NULL data pointer");
+    EncodeWorkspace ws;
+    size_t need = encode_workspace_layout(n_words, long_word_bytes, d_workspace, &ws);
+    if (need > workspace_bytes) { set_error("encode workspace too small"); return SWT_ERR_CAPACITY; }
+    SWT_CUDA_OK(cudaMemsetAsync(d_workspace, 0, (uint8_t *)ws.long_scratch - (uint8_t *)d_workspace, st));
+    SWT_CUDA_OK(cudaMemsetAsync(d_status, 0, 8 * sizeof(uint32_t), st));
+    if (n_words == 0) {
+        if (d_out_tok_off) SWT_CUDA_OK(cudaMemcpyAsync(d_out_tok_off, &tok_base, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        return SWT_OK;
+    }
+    static int grid = 0;
+    if (!grid) grid = encode_grid((const void *)bpe_encode_kernel, kTileWords);
+    int g = (int)std::min<uint64_t>((uint64_t)grid, ws.n_tiles);
+    bpe_encode_kernel<<<g, kTileWords, 0, st>>>(t->dev, d_arena, d_word_off, n_words, d_out_ids, out_cap, d_out_tok_off, tok_base, ws, d_status);
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}
+}  // namespace swt
+
+SWT_API int swt_bpe_encode(const swt_bpe_table *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
+                           uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off,
+                           void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream) {
+    return bpe_encode_launch(t, d_arena, d_word_off, n_words, long_word_bytes, d_out_ids, out_cap, d_out_tok_off, 0u,
+                             d_workspace, workspace_bytes, d_status, (cudaStream_t)stream);
+}

@@ -1,0 +1,596 @@
+// bpe_train.cu -- HP-3: the merge loop of NaiveBPE.train (reference source/bpe.py:88-111) on sm_100a.
+//
+// HBM layout (all inside one caller-owned workspace):
+//   sym[n_slots]        u32  the word table: symbols of all word types back to back, in first-occurrence
+//                            order.  bit 31 marks the first symbol of a type; 0xFFFFFFFF is a dead slot
+//                            (a merged word is compacted to the front of its own slot range, the tail dies).
+//   word_of[n_slots]    u32  slot -> type index (read only where a merge happens)
+//   start[n_types+1]    u32  type -> first slot;  freq[n_types] i64
+//   table[cap]          16 B {key = left<<32|right, i64 count}: the pair-frequency map of bpe.py:90-95, kept
+//                            INCREMENTALLY instead of being recounted every step
+//   delta[2*vmax+2]     i64  per-step count deltas: L[x] (pairs (x,a)->(x,z)), R[y] ((b,y)->(z,y)), ZZ, M
+//   symbol strings            length / offset / rolling hash per symbol + code arena, so that a merge whose
+//                            concatenation already exists reuses that symbol (bpe.py:103)
+//
+// One step = select (argmax + first-occurrence tie-break) | merge (mark + in-place apply + deltas) |
+// update (fold deltas into the table).  The only full-table passes are streaming reads: the argmax over the
+// pair table, the mark scan over sym[], and -- only on a count tie -- an ascending, early-exit scan that
+// finds the tied pair occurring first (Counter.most_common(1) returns the first-inserted maximum, bpe.py:102).
+//
+// Multi-GPU: types are sharded; L/R/ZZ/M are summed across ranks (NCCL all-reduce by the caller) and every
+// rank folds the same global deltas into its replica of the table, so replicas stay identical.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace swt {
+
+constexpr uint32_t kStart = 0x80000000u;
+constexpr uint32_t kHole = 0xFFFFFFFFu;
+constexpr uint64_t kEmptyKey = ~0ull;
+constexpr uint64_t kNoPos = ~0ull;
+constexpr uint32_t kMaxDenseAlpha = 4096;
+
+enum Halt : uint32_t { kRun = 0, kDoneVocab = 1, kDoneNoPairs = 2, kNeedGrow = 3, kRecordFull = 4,
+                       kErrInternal = 16, kErrCharArena = 17, kErrSymbols = 18, kErrTableFull = 19 };
+
+struct PairEntry { uint64_t key; long long count; };
+
+struct TrainState {                 // device resident, mutable
+    uint32_t halt, n_recorded;
+    uint64_t n_merges_total;
+    long long vocab_size;
+    uint64_t n_symbols, n_entries, table_cap, n_live;
+    // per-step scratch
+    long long max_count;
+    uint32_t n_tied, worklist_n, tie_ticket, step_stamp;
+    uint64_t cand_key, best_pos;
+    uint32_t cur_a, cur_b, cur_z, cur_valid;
+    uint64_t char_used;
+};
+
+struct ArgPart { long long count; uint64_t key; uint32_t n_tied; uint32_t pad; };
+
+struct TrainDev {
+    // sizes
+    uint64_t n_types, n_slots, slot_base;
+    uint32_t n_alpha, vmax, record_cap, world, rank, n_parts;
+    long long max_vocab;
+    uint64_t char_cap, str_ht_cap;
+    // arrays
+    uint32_t *sym, *word_of, *start, *word_mark, *worklist;
+    long long *freq;
+    PairEntry *table;                 // current table (changes on grow)
+    long long *delta;                 // L[vmax] | R[vmax] | ZZ | M
+    long long *dense;                 // n_alpha^2 initial counts
+    uint64_t *cand;                   // 2
+    uint64_t *cand_gather;            // world x 2
+    ArgPart *parts;
+    uint32_t *rec_left, *rec_right, *rec_new; long long *rec_count;
+    uint32_t *sym_len; uint64_t *sym_off, *sym_hash, *sym_pow; uint32_t *chars; uint32_t *str_ht;
+    TrainState *st;
+};
+
+constexpr uint64_t kHashP = 0x9E3779B97F4A7C15ull | 1ull;
+
+// ---- pair table --------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long table_get(const PairEntry *tab, uint64_t cap, uint64_t key) {
+    uint64_t h = mix64(key) & (cap - 1);
+    for (;;) {
+        uint64_t k = tab[h].key;
+        if (k == key) return tab[h].count;
+        if (k == kEmptyKey) return 0;
+        h = (h + 1) & (cap - 1);
+    }
+}
+__device__ __forceinline__ void table_add(PairEntry *tab, uint64_t cap, uint64_t key, long long d, TrainState *st) {
+    uint64_t h = mix64(key) & (cap - 1);
+    for (uint64_t probes = 0; probes <= cap; ++probes) {
+        uint64_t k = *(volatile uint64_t *)&tab[h].key;
+        if (k == kEmptyKey) {
+            uint64_t old = atomicCAS((unsigned long long *)&tab[h].key, (unsigned long long)kEmptyKey, (unsigned long long)key);
+            if (old == kEmptyKey) { atomicAdd((unsigned long long *)&st->n_entries, 1ull); k = key; }
+            else k = old;
+        }
+        if (k == key) { atomicAdd((unsigned long long *)&tab[h].count, (unsigned long long)d); return; }
+        h = (h + 1) & (cap - 1);
+    }
+    atomicExch(&st->halt, (uint32_t)kErrTableFull);
+}
+
+// ---- init -----------------------------------------------------------------------------------------------------
+__global__ void k_init_words(TrainDev d, const uint32_t *__restrict__ syms, const uint64_t *__restrict__ off) {
+    // one thread per type: copies its symbols, flags the first, fills word_of / start
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < d.n_types; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t b = off[t], e = off[t + 1];
+        d.start[t] = (uint32_t)b;
+        for (uint64_t i = b; i < e; ++i) { d.sym[i] = syms[i] | (i == b ? kStart : 0u); d.word_of[i] = (uint32_t)t; }
+        if (t == d.n_types - 1) d.start[d.n_types] = (uint32_t)e;
+    }
+}
+__global__ void k_init_symbols(TrainDev d, long long initial_vocab) {
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < d.n_alpha; c += gridDim.x * blockDim.x) {
+        d.sym_len[c] = 1; d.sym_off[c] = c; d.chars[c] = c; d.sym_hash[c] = (uint64_t)c + 1; d.sym_pow[c] = kHashP;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        TrainState *st = d.st;
+        st->halt = kRun; st->n_recorded = 0; st->n_merges_total = 0; st->vocab_size = initial_vocab;
+        st->n_symbols = d.n_alpha; st->n_entries = 0; st->n_live = d.n_slots; st->step_stamp = 0;
+        st->char_used = d.n_alpha; st->cur_valid = 0; st->worklist_n = 0;
+    }
+}
+__global__ void k_count_dense(TrainDev d) {
+    const uint64_t n = d.n_slots;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i + 1 < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = d.sym[i], nx = d.sym[i + 1];
+        if (nx & kStart) continue;                       // next slot starts another type (or is dead)
+        const uint32_t a = s & ~kStart;
+        atomicAdd((unsigned long long *)&d.dense[(uint64_t)a * d.n_alpha + nx], (unsigned long long)d.freq[d.word_of[i]]);
+    }
+}
+__global__ void k_build_table(TrainDev d, uint64_t cap) {
+    const uint64_t n = (uint64_t)d.n_alpha * d.n_alpha;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const long long c = d.dense[i];
+        if (c != 0) table_add(d.table, cap, ((i / d.n_alpha) << 32) | (i % d.n_alpha), c, d.st);
+    }
+}
+__global__ void k_fill_u64(uint64_t *p, uint64_t n, uint64_t v, uint64_t stride_words) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i * stride_words] = v;
+}
+__global__ void k_rehash(const PairEntry *old_tab, uint64_t old_cap, TrainDev d, uint64_t new_cap) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const PairEntry e = old_tab[i];
+        if (e.key != kEmptyKey && e.count != 0) table_add(d.table, new_cap, e.key, e.count, d.st);
+    }
+}
+
+// ---- select: argmax over the table (bpe.py:102) ---------------------------------------------------------------------
+__device__ __forceinline__ void arg_combine(long long &c, uint64_t &k, uint32_t &n, long long c2, uint64_t k2, uint32_t n2) {
+    if (c2 > c) { c = c2; k = k2; n = n2; }
+    else if (c2 == c) { n += n2; if (k2 < k) k = k2; }
+}
+__global__ void __launch_bounds__(256) k_argmax_partial(TrainDev d) {
+    TrainState *st = d.st;
+    if (st->halt) return;
+    const uint64_t cap = st->table_cap;
+    long long c = 0; uint64_t k = kEmptyKey; uint32_t n = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const PairEntry e = d.table[i];
+        if (e.key != kEmptyKey && e.count > 0) arg_combine(c, k, n, e.count, e.key, 1u);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        long long c2 = __shfl_xor_sync(0xffffffffu, c, o); uint64_t k2 = __shfl_xor_sync(0xffffffffu, k, o);
+        uint32_t n2 = __shfl_xor_sync(0xffffffffu, n, o);
+        arg_combine(c, k, n, c2, k2, n2);
+    }
+    __shared__ long long sc[8]; __shared__ uint64_t sk[8]; __shared__ uint32_t sn[8];
+    if ((threadIdx.x & 31) == 0) { sc[threadIdx.x >> 5] = c; sk[threadIdx.x >> 5] = k; sn[threadIdx.x >> 5] = n; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) arg_combine(c, k, n, sc[w], sk[w], sn[w]);
+        d.parts[blockIdx.x] = ArgPart{c, k, n, 0};
+    }
+}
+__global__ void __launch_bounds__(256) k_select(TrainDev d) {
+    TrainState *st = d.st;
+    if (st->halt) return;
+    long long c = 0; uint64_t k = kEmptyKey; uint32_t n = 0;
+    for (uint32_t i = threadIdx.x; i < d.n_parts; i += blockDim.x) { ArgPart p = d.parts[i]; arg_combine(c, k, n, p.count, p.key, p.n_tied); }
+    for (int o = 16; o > 0; o >>= 1) {
+        long long c2 = __shfl_xor_sync(0xffffffffu, c, o); uint64_t k2 = __shfl_xor_sync(0xffffffffu, k, o);
+        uint32_t n2 = __shfl_xor_sync(0xffffffffu, n, o);
+        arg_combine(c, k, n, c2, k2, n2);
+    }
+    __shared__ long long sc[8]; __shared__ uint64_t sk[8]; __shared__ uint32_t sn[8];
+    if ((threadIdx.x & 31) == 0) { sc[threadIdx.x >> 5] = c; sk[threadIdx.x >> 5] = k; sn[threadIdx.x >> 5] = n; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) arg_combine(c, k, n, sc[w], sk[w], sn[w]);
+        st->max_count = c; st->n_tied = n; st->cand_key = k;
+        st->worklist_n = 0; st->tie_ticket = 0; st->best_pos = kNoPos; st->cur_valid = 0;
+        // loop conditions of bpe.py:88 and :98-99, then the capacity gates (checked before any mutation)
+        if (st->vocab_size >= d.max_vocab) st->halt = kDoneVocab;
+        else if (c <= 0) st->halt = kDoneNoPairs;
+        else if (st->n_recorded >= d.record_cap) st->halt = kRecordFull;
+        else if ((st->n_entries + 2 * st->n_symbols + 2) * 10 > st->table_cap * 7) st->halt = kNeedGrow;
+        else if (st->n_symbols + 1 > d.vmax) st->halt = kErrSymbols;
+    }
+}
+
+// ---- select: tie-break scan.  Among the pairs whose count equals the maximum, the winner is the one whose first
+// occurrence comes first in (type, position) order == ascending slot order.  Chunks are handed out in ascending
+// order; a chunk that starts after an already found position is skipped, so the scan stops early.
+constexpr uint32_t kTieChunk = 4096;
+__global__ void __launch_bounds__(256) k_tie_scan(TrainDev d) {
+    TrainState *st = d.st;
+    if (st->halt || st->n_tied <= 1) return;
+    const long long target = st->max_count;
+    const uint64_t cap = st->table_cap;
+    __shared__ uint32_t s_chunk, s_stop;
+    __shared__ unsigned long long s_best;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            s_chunk = atomicAdd(&st->tie_ticket, 1u); s_best = kNoPos;
+            const uint64_t c = (uint64_t)s_chunk * kTieChunk;
+            // stop when past the end, or when an earlier chunk already holds an occurrence
+            s_stop = (c >= d.n_slots) || (*(volatile uint64_t *)&st->best_pos < d.slot_base + c);
+        }
+        __syncthreads();
+        if (s_stop) break;
+        const uint64_t c0 = (uint64_t)s_chunk * kTieChunk;
+        uint64_t mine = kNoPos;
+        for (uint64_t i = c0 + threadIdx.x; i < c0 + kTieChunk && i + 1 < d.n_slots; i += blockDim.x) {
+            const uint32_t s = d.sym[i], nx = d.sym[i + 1];
+            if (s == kHole || (nx & kStart)) continue;
+            if (table_get(d.table, cap, ((uint64_t)(s & ~kStart) << 32) | nx) == target) { mine = i; break; }
+        }
+        if (mine != kNoPos) atomicMin(&s_best, (unsigned long long)mine);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_best != kNoPos) atomicMin((unsigned long long *)&st->best_pos, (unsigned long long)(d.slot_base + s_best));
+        __syncthreads();
+    }
+}
+__global__ void k_candidate(TrainDev d) {
+    TrainState *st = d.st;
+    uint64_t pos = kNoPos, key = kEmptyKey;
+    if (!st->halt) {
+        if (st->n_tied <= 1) key = st->cand_key;
+        else if (st->best_pos != kNoPos) {
+            pos = st->best_pos;
+            const uint64_t i = pos - d.slot_base;
+            key = ((uint64_t)(d.sym[i] & ~kStart) << 32) | d.sym[i + 1];
+        }
+    }
+    d.cand[0] = pos; d.cand[1] = key;
+    d.cand_gather[2 * d.rank] = pos; d.cand_gather[2 * d.rank + 1] = key;
+}
+
+// ---- merge: name the new symbol (string identity, bpe.py:103), record the merge (bpe.py:104) ---------------------------
+__global__ void __launch_bounds__(32) k_begin_merge(TrainDev d) {
+    TrainState *st = d.st;
+    if (st->halt) return;
+    const uint32_t lane = threadIdx.x;
+    uint64_t key = kEmptyKey;
+    if (st->n_tied <= 1) key = st->cand_key;
+    else {
+        uint64_t best = kNoPos;
+        for (uint32_t r = 0; r < d.world; ++r) if (d.cand_gather[2 * r] < best) { best = d.cand_gather[2 * r]; key = d.cand_gather[2 * r + 1]; }
+        if (best == kNoPos) { if (lane == 0) st->halt = kErrInternal; return; }
+    }
+    const uint32_t a = (uint32_t)(key >> 32), b = (uint32_t)key;
+    const uint32_t la = d.sym_len[a], lb = d.sym_len[b], L = la + lb;
+    const uint32_t *ca = d.chars + d.sym_off[a], *cb = d.chars + d.sym_off[b];
+    const uint64_t h = d.sym_hash[a] * d.sym_pow[b] + d.sym_hash[b];
+    uint64_t slot = mix64(h) & (d.str_ht_cap - 1);
+    uint32_t z = kHole;
+    for (;;) {
+        const uint32_t id1 = d.str_ht[slot];
+        if (id1 == 0) break;
+        const uint32_t cnd = id1 - 1;
+        if (d.sym_hash[cnd] == h && d.sym_len[cnd] == L) {
+            const uint32_t *cc = d.chars + d.sym_off[cnd];
+            bool diff = false;
+            for (uint32_t i = lane; i < L; i += 32) { const uint32_t want = i < la ? ca[i] : cb[i - la]; if (cc[i] != want) diff = true; }
+            if (!__any_sync(0xffffffffu, diff)) { z = cnd; break; }
+        }
+        slot = (slot + 1) & (d.str_ht_cap - 1);
+    }
+    if (z == kHole) {                                   // a string never seen before: the vocabulary grows
+        if (st->char_used + L > d.char_cap) { if (lane == 0) st->halt = kErrCharArena; return; }
+        z = (uint32_t)st->n_symbols;
+        uint32_t *cz = d.chars + st->char_used;
+        for (uint32_t i = lane; i < L; i += 32) cz[i] = i < la ? ca[i] : cb[i - la];
+        __syncwarp();
+        if (lane == 0) {
+            d.sym_len[z] = L; d.sym_off[z] = st->char_used; d.sym_hash[z] = h; d.sym_pow[z] = d.sym_pow[a] * d.sym_pow[b];
+            d.str_ht[slot] = z + 1;
+            st->char_used += L; st->n_symbols += 1; st->vocab_size += 1;
+        }
+    }
+    if (lane == 0) {
+        const uint32_t r = st->n_recorded;
+        d.rec_left[r] = a; d.rec_right[r] = b; d.rec_new[r] = z; d.rec_count[r] = st->max_count;
+        st->n_recorded = r + 1; st->n_merges_total += 1;
+        st->cur_a = a; st->cur_b = b; st->cur_z = z; st->cur_valid = 1; st->step_stamp += 1;
+    }
+}
+
+// ---- merge: mark the types that contain (a,b) -- a pure streaming read of sym[] -----------------------------------------
+__global__ void __launch_bounds__(256) k_mark(TrainDev d) {
+    const TrainState *st = d.st;
+    if (st->halt || !st->cur_valid) return;
+    const uint32_t a = st->cur_a, b = st->cur_b, stamp = st->step_stamp;
+    const uint64_t n = d.n_slots;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i + 1 < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = d.sym[i];
+        if ((s & ~kStart) != a) continue;
+        if (d.sym[i + 1] != b) continue;                 // b carries no flag: same type, live slot
+        const uint32_t w = d.word_of[i];
+        if (atomicExch(&d.word_mark[w], stamp) != stamp) d.worklist[atomicAdd(&d.st->worklist_n, 1u)] = w;
+    }
+}
+
+// ---- merge: greedy left-to-right replacement inside each marked type (bpe.py:25-48), emitting count deltas -------------
+__global__ void __launch_bounds__(128) k_apply(TrainDev d) {
+    TrainState *st = d.st;
+    if (st->halt || !st->cur_valid) return;
+    const uint32_t a = st->cur_a, b = st->cur_b, z = st->cur_z, n_work = st->worklist_n;
+    long long *L = d.delta, *R = d.delta + d.vmax;
+    long long zz = 0, m = 0, removed = 0;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_work; k += gridDim.x * blockDim.x) {
+        const uint32_t w = d.worklist[k];
+        const uint32_t ws = d.start[w], we = d.start[w + 1];
+        const long long f = d.freq[w];
+        uint32_t r = ws, o = ws, prev = 0; bool have_prev = false, last_merge = false;
+        while (r < we) {
+            uint32_t s = d.sym[r];
+            if (s == kHole) break;
+            s &= ~kStart;
+            const uint32_t nx = (r + 1 < we) ? d.sym[r + 1] : kHole;
+            if (s == a && nx == b) {
+                if (have_prev) { if (last_merge) zz += f; else atomicAdd((unsigned long long *)&L[prev], (unsigned long long)f); }
+                m += f;
+                d.sym[o] = z; prev = z; last_merge = true; r += 2;
+            } else {
+                if (have_prev && last_merge) atomicAdd((unsigned long long *)&R[s], (unsigned long long)f);
+                d.sym[o] = s; prev = s; last_merge = false; r += 1;
+            }
+            have_prev = true; ++o;
+        }
+        for (uint32_t q = o; q < r; ++q) d.sym[q] = kHole;
+        d.sym[ws] |= kStart;
+        removed += (long long)(r - o);
+    }
+    if (zz) atomicAdd((unsigned long long *)&d.delta[2 * (uint64_t)d.vmax], (unsigned long long)zz);
+    if (m) atomicAdd((unsigned long long *)&d.delta[2 * (uint64_t)d.vmax + 1], (unsigned long long)m);
+    if (removed) atomicAdd((unsigned long long *)&st->n_live, (unsigned long long)(-removed));
+}
+
+// ---- update: fold the (globally summed) deltas into the replicated table ----------------------------------------------------
+__global__ void __launch_bounds__(256) k_update(TrainDev d) {
+    TrainState *st = d.st;
+    if (st->halt || !st->cur_valid) return;
+    const uint64_t a = st->cur_a, b = st->cur_b, z = st->cur_z;
+    const uint64_t cap = st->table_cap;
+    long long *L = d.delta, *R = d.delta + d.vmax;
+    for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < d.vmax; x += gridDim.x * blockDim.x) {
+        const long long l = L[x], r = R[x];
+        if (l) { table_add(d.table, cap, ((uint64_t)x << 32) | a, -l, st); table_add(d.table, cap, ((uint64_t)x << 32) | z, l, st); L[x] = 0; }
+        if (r) { table_add(d.table, cap, (b << 32) | x, -r, st); table_add(d.table, cap, (z << 32) | x, r, st); R[x] = 0; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const long long zz = d.delta[2 * (uint64_t)d.vmax], m = d.delta[2 * (uint64_t)d.vmax + 1];
+        if (zz) { table_add(d.table, cap, (b << 32) | a, -zz, st); table_add(d.table, cap, (z << 32) | z, zz, st); }
+        if (m) table_add(d.table, cap, (a << 32) | b, -m, st);
+        d.delta[2 * (uint64_t)d.vmax] = 0; d.delta[2 * (uint64_t)d.vmax + 1] = 0;
+    }
+}
+
+__global__ void k_clear_halt(TrainState *st, uint32_t which, uint32_t reset_records) {
+    if (st->halt == which) st->halt = kRun;
+    if (reset_records) st->n_recorded = 0;
+}
+__global__ void k_set_table_cap(TrainState *st, uint64_t cap) { st->table_cap = cap; st->n_entries = 0; }
+
+}  // namespace swt
+
+using namespace swt;
+
+struct swt_bpe_trainer {
+    swt_bpe_train_config cfg;
+    TrainDev dev;
+    int device;
+    uint64_t table_cap;
+    int grid_scan;      // persistent grid for streaming passes
+};
+
+static uint64_t choose_table_cap(const swt_bpe_train_config *cfg) {
+    if (cfg->table_cap) return next_pow2(cfg->table_cap);
+    uint64_t a2 = (uint64_t)cfg->n_alpha * cfg->n_alpha;
+    uint64_t want = std::max<uint64_t>(1ull << 16, 4 * std::min<uint64_t>(a2, 1ull << 24));
+    want = std::max<uint64_t>(want, 8ull * (uint64_t)std::max<int64_t>(cfg->max_vocab, 1));
+    return next_pow2(want);
+}
+static uint32_t vmax_of(const swt_bpe_train_config *cfg) {
+    return (uint32_t)std::max<int64_t>(cfg->max_vocab, (int64_t)cfg->n_alpha) + 2;
+}
+static uint64_t char_cap_of(const swt_bpe_train_config *cfg) {
+    uint64_t want = (uint64_t)vmax_of(cfg) * std::max<uint32_t>(cfg->max_word_len, 1);
+    return std::min<uint64_t>(std::max<uint64_t>(want, 1ull << 20), 1ull << 26) + cfg->n_alpha;
+}
+
+static size_t train_layout(const swt_bpe_train_config *cfg, void *base, TrainDev *d, uint64_t table_cap) {
+    Carver cv(base);
+    const uint32_t vmax = vmax_of(cfg);
+    d->n_types = cfg->n_types_local; d->n_slots = cfg->n_slots_local; d->slot_base = cfg->slot_base;
+    d->n_alpha = cfg->n_alpha; d->vmax = vmax; d->record_cap = cfg->record_cap; d->world = cfg->world_size; d->rank = cfg->rank;
+    d->max_vocab = cfg->max_vocab; d->n_parts = kNumSMs * 4;
+    d->char_cap = char_cap_of(cfg); d->str_ht_cap = next_pow2(4ull * vmax);
+    d->st = cv.take<TrainState>(1);
+    d->sym = cv.take<uint32_t>(d->n_slots + 2);
+    d->word_of = cv.take<uint32_t>(d->n_slots + 1);
+    d->start = cv.take<uint32_t>(d->n_types + 1);
+    d->word_mark = cv.take<uint32_t>(d->n_types + 1);
+    d->worklist = cv.take<uint32_t>(d->n_types + 1);
+    d->freq = cv.take<long long>(d->n_types + 1);
+    d->delta = cv.take<long long>(2ull * vmax + 2);
+    d->dense = cv.take<long long>((uint64_t)cfg->n_alpha * cfg->n_alpha + 1);
+    d->cand = cv.take<uint64_t>(2);
+    d->cand_gather = cv.take<uint64_t>(2ull * cfg->world_size);
+    d->parts = cv.take<ArgPart>(d->n_parts);
+    d->rec_left = cv.take<uint32_t>(cfg->record_cap); d->rec_right = cv.take<uint32_t>(cfg->record_cap);
+    d->rec_new = cv.take<uint32_t>(cfg->record_cap); d->rec_count = cv.take<long long>(cfg->record_cap);
+    d->sym_len = cv.take<uint32_t>(vmax); d->sym_off = cv.take<uint64_t>(vmax); d->sym_hash = cv.take<uint64_t>(vmax);
+    d->sym_pow = cv.take<uint64_t>(vmax); d->chars = cv.take<uint32_t>(d->char_cap); d->str_ht = cv.take<uint32_t>(d->str_ht_cap);
+    d->table = cv.take<PairEntry>(table_cap);
+    return cv.used();
+}
+
+SWT_API size_t swt_bpe_train_workspace_bytes(const swt_bpe_train_config *cfg) {
+    if (!cfg) return 0;
+    TrainDev d;
+    return train_layout(cfg, nullptr, &d, choose_table_cap(cfg));
+}
+SWT_API size_t swt_bpe_train_table_bytes(uint64_t cap) { return next_pow2(cap) * sizeof(PairEntry) + 256; }
+
+SWT_API int swt_bpe_train_create(const swt_bpe_train_config *cfg, const uint32_t *d_syms, const uint64_t *d_off,
+                                 const int64_t *d_freq, void *d_workspace, size_t workspace_bytes, void *stream,
+                                 swt_bpe_trainer **out) {
+    SWT_REQUIRE(cfg && out && d_workspace, "NULL argument");
+    SWT_REQUIRE(cfg->n_slots_local < 0xFFFFFFF0ull, "n_slots_local must be < 2^32");
+    SWT_REQUIRE(cfg->n_types_local < 0xFFFFFFF0ull, "n_types_local must be < 2^32");
+    SWT_REQUIRE(cfg->n_alpha >= 1 && cfg->n_alpha <= kMaxDenseAlpha, "n_alpha must be in [1, 4096]");
+    SWT_REQUIRE(cfg->world_size >= 1 && cfg->rank < cfg->world_size, "bad rank/world_size");
+    SWT_REQUIRE(cfg->record_cap >= 1, "record_cap must be >= 1");
+    SWT_REQUIRE(cfg->max_vocab < (1ll << 30), "max_vocab must be < 2^30");
+    SWT_REQUIRE(cfg->n_types_local == 0 || (d_syms && d_off && d_freq), "NULL corpus pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int device = 0;
+    SWT_CUDA_OK(cudaGetDevice(&device));
+    swt_bpe_trainer *t = new swt_bpe_trainer();
+    t->cfg = *cfg; t->device = device; t->table_cap = choose_table_cap(cfg);
+    size_t need = train_layout(cfg, d_workspace, &t->dev, t->table_cap);
+    if (need > workspace_bytes) { delete t; set_error("train workspace too small"); return SWT_ERR_CAPACITY; }
+    int sms = kNumSMs; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    t->grid_scan = sms * 8;
+    TrainDev &d = t->dev;
+    // zero everything up to the pair table, then mark the table empty
+    cudaError_t e = cudaMemsetAsync(d_workspace, 0, (uint8_t *)d.table - (uint8_t *)d_workspace, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d.table, 0, t->table_cap * sizeof(PairEntry), st);
+    if (e != cudaSuccess) { delete t; set_error(std::string("memset: ") + cudaGetErrorString(e)); return SWT_ERR_CUDA; }
+    k_fill_u64<<<t->grid_scan, 256, 0, st>>>((uint64_t *)d.table, t->table_cap, kEmptyKey, 2);
+    k_init_symbols<<<32, 256, 0, st>>>(d, cfg->initial_vocab);
+    k_set_table_cap<<<1, 1, 0, st>>>(d.st, t->table_cap);
+    if (cfg->n_types_local) {
+        k_init_words<<<t->grid_scan, 256, 0, st>>>(d, d_syms, d_off);
+        e = cudaMemcpyAsync(d.freq, d_freq, cfg->n_types_local * sizeof(long long), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) { delete t; set_error(std::string("freq copy: ") + cudaGetErrorString(e)); return SWT_ERR_CUDA; }
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { delete t; set_error(std::string("init launch: ") + cudaGetErrorString(e)); return SWT_ERR_CUDA; }
+    *out = t;
+    return SWT_OK;
+}
+
+SWT_API void swt_bpe_train_destroy(swt_bpe_trainer *t) { delete t; }
+
+SWT_API int swt_bpe_train_buffers(const swt_bpe_trainer *t, void **init_counts_ptr, uint64_t *init_counts_elems,
+                                  void **cand_ptr, void **cand_gather_ptr, void **delta_ptr, uint64_t *delta_elems) {
+    SWT_REQUIRE(t != nullptr, "NULL trainer");
+    if (init_counts_ptr) *init_counts_ptr = t->dev.dense;
+    if (init_counts_elems) *init_counts_elems = (uint64_t)t->cfg.n_alpha * t->cfg.n_alpha;
+    if (cand_ptr) *cand_ptr = t->dev.cand;
+    if (cand_gather_ptr) *cand_gather_ptr = t->dev.cand_gather;
+    if (delta_ptr) *delta_ptr = t->dev.delta;
+    if (delta_elems) *delta_elems = 2ull * t->dev.vmax + 2;
+    return SWT_OK;
+}
+
+SWT_API int swt_bpe_train_count_local(swt_bpe_trainer *t, void *stream) {
+    SWT_REQUIRE(t != nullptr, "NULL trainer");
+    if (t->dev.n_slots) k_count_dense<<<t->grid_scan, 256, 0, (cudaStream_t)stream>>>(t->dev);
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}
+SWT_API int swt_bpe_train_build_table(swt_bpe_trainer *t, void *stream) {
+    SWT_REQUIRE(t != nullptr, "NULL trainer");
+    k_build_table<<<t->grid_scan, 256, 0, (cudaStream_t)stream>>>(t->dev, t->table_cap);
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}
+
+SWT_API int swt_bpe_train_select(swt_bpe_trainer *t, void *stream) {
+    SWT_REQUIRE(t != nullptr, "NULL trainer");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_argmax_partial<<<t->dev.n_parts, 256, 0, st>>>(t->dev);
+    k_select<<<1, 256, 0, st>>>(t->dev);
+    if (t->dev.n_slots) k_tie_scan<<<t->grid_scan / 2, 256, 0, st>>>(t->dev);
+    k_candidate<<<1, 1, 0, st>>>(t->dev);
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}
+SWT_API int swt_bpe_train_merge(swt_bpe_trainer *t, void *stream) {
+    SWT_REQUIRE(t != nullptr, "NULL trainer");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_begin_merge<<<1, 32, 0, st>>>(t->dev);
+    if (t->dev.n_slots) {
+        k_mark<<<t->grid_scan, 256, 0, st>>>(t->dev);
+        k_apply<<<t->grid_scan / 2, 128, 0, st>>>(t->dev);
+    }
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}
+SWT_API int swt_bpe_train_update(swt_bpe_trainer *t, void *stream) {
+    SWT_REQUIRE(t != nullptr, "NULL trainer");
+    const int blocks = (int)std::min<uint64_t>((t->dev.vmax + 255) / 256, 4096);
+    k_update<<<blocks, 256, 0, (cudaStream_t)stream>>>(t->dev);
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}
+SWT_API int swt_bpe_train_steps(swt_bpe_trainer *t, uint32_t n_steps, void *stream) {
+    SWT_REQUIRE(t != nullptr, "NULL trainer");
+    SWT_REQUIRE(t->cfg.world_size == 1, "swt_bpe_train_steps is the single-rank loop; use select/merge/update with collectives");
+    for (uint32_t s = 0; s < n_steps; ++s) {
+        int rc = swt_bpe_train_select(t, stream); if (rc) return rc;
+        rc = swt_bpe_train_merge(t, stream); if (rc) return rc;
+        rc = swt_bpe_train_update(t, stream); if (rc) return rc;
+    }
+    return SWT_OK;
+}
+
+SWT_API int swt_bpe_train_read(swt_bpe_trainer *t, uint32_t *h_left, uint32_t *h_right, uint32_t *h_new, int64_t *h_count,
+                               swt_bpe_train_state *state, void *stream) {
+    SWT_REQUIRE(t && state, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    TrainState hs;
+    SWT_CUDA_OK(cudaMemcpyAsync(&hs, t->dev.st, sizeof(TrainState), cudaMemcpyDeviceToHost, st));
+    SWT_CUDA_OK(cudaStreamSynchronize(st));
+    const uint32_t n = hs.n_recorded;
+    if (n) {
+        SWT_REQUIRE(h_left && h_right && h_new, "record arrays are NULL");
+        SWT_CUDA_OK(cudaMemcpyAsync(h_left, t->dev.rec_left, n * 4, cudaMemcpyDeviceToHost, st));
+        SWT_CUDA_OK(cudaMemcpyAsync(h_right, t->dev.rec_right, n * 4, cudaMemcpyDeviceToHost, st));
+        SWT_CUDA_OK(cudaMemcpyAsync(h_new, t->dev.rec_new, n * 4, cudaMemcpyDeviceToHost, st));
+        if (h_count) SWT_CUDA_OK(cudaMemcpyAsync(h_count, t->dev.rec_count, n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    k_clear_halt<<<1, 1, 0, st>>>(t->dev.st, kRecordFull, 1u);
+    SWT_CUDA_OK(cudaStreamSynchronize(st));
+    state->halt = hs.halt; state->n_recorded = n; state->n_merges_total = hs.n_merges_total; state->vocab_size = hs.vocab_size;
+    state->n_symbols = hs.n_symbols; state->n_table_entries = hs.n_entries; state->table_cap = hs.table_cap; state->n_live_slots = hs.n_live;
+    return SWT_OK;
+}
+
+SWT_API int swt_bpe_train_grow_table(swt_bpe_trainer *t, void *d_new_table, uint64_t new_cap, void *stream) {
+    SWT_REQUIRE(t && d_new_table, "NULL argument");
+    new_cap = next_pow2(new_cap);
+    SWT_REQUIRE(new_cap > t->table_cap, "new table must be larger");
+    cudaStream_t st = (cudaStream_t)stream;
+    PairEntry *old_tab = t->dev.table; const uint64_t old_cap = t->table_cap;
+    PairEntry *nt = (PairEntry *)(((uintptr_t)d_new_table + 255) / 256 * 256);
+    SWT_CUDA_OK(cudaMemsetAsync(nt, 0, new_cap * sizeof(PairEntry), st));
+    k_fill_u64<<<t->grid_scan, 256, 0, st>>>((uint64_t *)nt, new_cap, kEmptyKey, 2);
+    t->dev.table = nt; t->table_cap = new_cap;
+    k_set_table_cap<<<1, 1, 0, st>>>(t->dev.st, new_cap);
+    k_rehash<<<t->grid_scan, 256, 0, st>>>(old_tab, old_cap, t->dev, new_cap);
+    k_clear_halt<<<1, 1, 0, st>>>(t->dev.st, kNeedGrow, 0u);
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}
+
+SWT_API int swt_bpe_train_read_corpus(swt_bpe_trainer *t, uint32_t *h_syms, uint32_t *h_len, void *stream) {
+    SWT_REQUIRE(t && h_syms && h_len, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t n = t->dev.n_slots, nt = t->dev.n_types;
+    std::vector<uint32_t> start(nt + 1);
+    SWT_CUDA_OK(cudaMemcpyAsync(h_syms, t->dev.sym, n * 4, cudaMemcpyDeviceToHost, st));
+    SWT_CUDA_OK(cudaMemcpyAsync(start.data(), t->dev.start, (nt + 1) * 4, cudaMemcpyDeviceToHost, st));
+    SWT_CUDA_OK(cudaStreamSynchronize(st));
+    for (uint64_t w = 0; w < nt; ++w) {
+        uint32_t len = 0;
+        for (uint32_t i = start[w]; i < start[w + 1] && h_syms[i] != kHole; ++i) { h_syms[i] &= ~kStart; ++len; }
+        h_len[w] = len;
+    }
+    return SWT_OK;
+}

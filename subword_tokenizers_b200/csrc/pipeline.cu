@@ -1,0 +1,158 @@
+// pipeline.cu -- host-buffer entry point: stages a host-resident corpus through the GPU in batches.
+//
+// Three slots, one CUDA stream each; per batch k on slot k%3:  H2D(arena slice, offset slice) -> encode
+// kernel -> D2H(token ids, token offsets).  H2D of batch k+1 and D2H of batch k-1 overlap the kernel of
+// batch k (PCIe is full duplex).  The kernel of batch k is launched once the token total of batch k-1 is
+// known, so that token offsets come out global and ids land compactly in the caller's buffer.
+#include <algorithm>
+#include <vector>
+
+#include "encode.cuh"
+
+struct swt_bpe_table;
+struct swt_wp_trie;
+namespace swt {
+int bpe_encode_launch(const swt_bpe_table *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
+                      uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off, uint32_t tok_base,
+                      void *d_workspace, size_t workspace_bytes, uint32_t *d_status, cudaStream_t st);
+int wp_encode_launch(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
+                     uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off, uint32_t tok_base,
+                     void *d_workspace, size_t workspace_bytes, uint32_t *d_status, cudaStream_t st);
+}
+
+namespace {
+constexpr int kSlots = 3;
+struct Slot {
+    uint8_t *d_arena = nullptr; uint32_t *d_off = nullptr, *d_ids = nullptr, *d_tok_off = nullptr, *d_status = nullptr;
+    void *d_ws = nullptr; size_t ws_bytes = 0;
+    uint32_t *h_status = nullptr;             // pinned
+    cudaStream_t stream = nullptr;
+    cudaEvent_t kernel_done = nullptr, d2h_done = nullptr;
+    bool busy = false;
+};
+}  // namespace
+
+struct swt_pipeline {
+    int device;
+    uint64_t batch_bytes, max_words;
+    Slot slot[kSlots];
+};
+
+using namespace swt;
+
+SWT_API int swt_pipeline_create(int device, uint64_t batch_bytes, swt_pipeline **out) {
+    SWT_REQUIRE(out != nullptr, "out is NULL");
+    SWT_REQUIRE(batch_bytes >= (1u << 16) && batch_bytes <= (1ull << 30), "batch_bytes must be in [64 KiB, 1 GiB]");
+    SWT_CUDA_OK(cudaSetDevice(device));
+    swt_pipeline *p = new swt_pipeline();
+    p->device = device; p->batch_bytes = batch_bytes; p->max_words = batch_bytes / 2;
+    for (int i = 0; i < kSlots; ++i) {
+        Slot &s = p->slot[i];
+        // BPE long-word scratch is sized for the worst case (every word of the batch is long)
+        s.ws_bytes = swt_encode_workspace_bytes((uint32_t)p->max_words, batch_bytes);
+        cudaError_t e = cudaMalloc(&s.d_arena, batch_bytes + 16);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_off, (p->max_words + 1) * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_tok_off, (p->max_words + 1) * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_ids, (batch_bytes + p->max_words + 16) * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_status, 8 * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_ws, s.ws_bytes);
+        if (e == cudaSuccess) e = cudaHostAlloc((void **)&s.h_status, 8 * 4, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.kernel_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            set_error(std::string("pipeline allocation: ") + cudaGetErrorString(e));
+            swt_pipeline_destroy(p);
+            return SWT_ERR_CUDA;
+        }
+    }
+    *out = p;
+    return SWT_OK;
+}
+
+SWT_API void swt_pipeline_destroy(swt_pipeline *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (int i = 0; i < kSlots; ++i) {
+        Slot &s = p->slot[i];
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaFree(s.d_arena); cudaFree(s.d_off); cudaFree(s.d_tok_off); cudaFree(s.d_ids); cudaFree(s.d_status); cudaFree(s.d_ws);
+        if (s.h_status) cudaFreeHost(s.h_status);
+        if (s.kernel_done) cudaEventDestroy(s.kernel_done);
+        if (s.d2h_done) cudaEventDestroy(s.d2h_done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    delete p;
+}
+
+SWT_API int swt_encode_host(swt_pipeline *p, int which, const void *table, const uint8_t *h_arena, const uint32_t *h_word_off,
+                            uint64_t n_words, uint32_t *h_out_ids, uint64_t out_cap, uint32_t *h_out_tok_off,
+                            uint64_t *n_tokens, uint64_t *h6_events) {
+    SWT_REQUIRE(p && table && h_word_off && n_tokens, "NULL argument");
+    SWT_REQUIRE(which == 0 || which == 1, "which must be 0 (BPE) or 1 (WP)");
+    SWT_REQUIRE(n_words < 0xFFFFFFFFull, "n_words must be < 2^32 per call");
+    SWT_REQUIRE(n_words == 0 || (h_arena && h_out_ids), "NULL data pointer");
+    SWT_CUDA_OK(cudaSetDevice(p->device));
+    // batch boundaries: [w0, w1) with at most batch_bytes bytes and max_words words
+    struct Batch { uint64_t w0, w1; };
+    std::vector<Batch> batches;
+    for (uint64_t w0 = 0; w0 < n_words;) {
+        const uint64_t limit = (uint64_t)h_word_off[w0] + p->batch_bytes;
+        const uint64_t hi = std::min<uint64_t>(n_words, w0 + p->max_words);
+        // largest w1 in (w0, hi] with off[w1] <= limit
+        const uint32_t *it = std::upper_bound(h_word_off + w0 + 1, h_word_off + hi + 1, limit,
+                                              [](uint64_t v, uint32_t o) { return v < (uint64_t)o; });
+        uint64_t w1 = (uint64_t)(it - h_word_off) - 1;
+        if (w1 <= w0) { set_error("a single word exceeds the pipeline batch size"); return SWT_ERR_CAPACITY; }
+        batches.push_back({w0, w1});
+        w0 = w1;
+    }
+    auto enqueue_h2d = [&](size_t k) -> int {
+        Slot &s = p->slot[k % kSlots];
+        if (s.busy) { SWT_CUDA_OK(cudaEventSynchronize(s.d2h_done)); s.busy = false; }
+        const Batch &b = batches[k];
+        const uint64_t byte0 = h_word_off[b.w0], nbytes = h_word_off[b.w1] - byte0;
+        if (nbytes) SWT_CUDA_OK(cudaMemcpyAsync(s.d_arena, h_arena + byte0, nbytes, cudaMemcpyHostToDevice, s.stream));
+        SWT_CUDA_OK(cudaMemcpyAsync(s.d_off, h_word_off + b.w0, (b.w1 - b.w0 + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+        return SWT_OK;
+    };
+    uint64_t total = 0, h6 = 0;
+    int rc = SWT_OK;
+    if (!batches.empty()) rc = enqueue_h2d(0);
+    for (size_t k = 0; k < batches.size() && rc == SWT_OK; ++k) {
+        if (k + 1 < batches.size()) { rc = enqueue_h2d(k + 1); if (rc) break; }
+        Slot &s = p->slot[k % kSlots];
+        const Batch &b = batches[k];
+        const uint32_t nw = (uint32_t)(b.w1 - b.w0);
+        const uint64_t byte0 = h_word_off[b.w0], nbytes = h_word_off[b.w1] - byte0;
+        const uint64_t cap = nbytes + nw + 16;
+        if (total > 0xFFFFFFFFull) { set_error("more than 2^32 tokens in one call"); rc = SWT_ERR_CAPACITY; break; }
+        // offsets stay absolute: hand the kernel an arena pointer rebased by the batch's first byte
+        const uint8_t *arena_rebased = s.d_arena - byte0;
+        if (which == 0)
+            rc = bpe_encode_launch((const swt_bpe_table *)table, arena_rebased, s.d_off, nw, nbytes, s.d_ids, cap,
+                                   h_out_tok_off ? s.d_tok_off : nullptr, (uint32_t)total, s.d_ws, s.ws_bytes, s.d_status, s.stream);
+        else
+            rc = wp_encode_launch((const swt_wp_trie *)table, arena_rebased, s.d_off, nw, s.d_ids, cap,
+                                  h_out_tok_off ? s.d_tok_off : nullptr, (uint32_t)total, s.d_ws, s.ws_bytes, s.d_status, s.stream);
+        if (rc) break;
+        SWT_CUDA_OK(cudaMemcpyAsync(s.h_status, s.d_status, 8 * 4, cudaMemcpyDeviceToHost, s.stream));
+        SWT_CUDA_OK(cudaEventRecord(s.kernel_done, s.stream));
+        SWT_CUDA_OK(cudaEventSynchronize(s.kernel_done));
+        if (s.h_status[kStatusCode] != SWT_OK) { set_error("encode kernel reported status " + std::to_string(s.h_status[kStatusCode])); rc = (int)s.h_status[kStatusCode]; break; }
+        const uint64_t nt = ((uint64_t)s.h_status[kStatusTokensHi] << 32) | s.h_status[kStatusTokens];
+        h6 += s.h_status[kStatusH6];
+        if (total + nt > out_cap) { set_error("h_out_ids capacity too small"); rc = SWT_ERR_CAPACITY; break; }
+        if (nt) SWT_CUDA_OK(cudaMemcpyAsync(h_out_ids + total, s.d_ids, nt * 4, cudaMemcpyDeviceToHost, s.stream));
+        if (h_out_tok_off) SWT_CUDA_OK(cudaMemcpyAsync(h_out_tok_off + b.w0, s.d_tok_off, (uint64_t)nw * 4, cudaMemcpyDeviceToHost, s.stream));
+        SWT_CUDA_OK(cudaEventRecord(s.d2h_done, s.stream));
+        s.busy = true;
+        total += nt;
+    }
+    for (int i = 0; i < kSlots; ++i) { cudaStreamSynchronize(p->slot[i].stream); p->slot[i].busy = false; }
+    if (rc != SWT_OK) return rc;
+    if (h_out_tok_off) h_out_tok_off[n_words] = (uint32_t)total;
+    *n_tokens = total;
+    if (h6_events) *h6_events = h6;
+    return SWT_OK;
+}

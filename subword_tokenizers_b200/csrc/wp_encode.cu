@@ -1,0 +1,348 @@
+// wp_encode.cu -- HP-2: FastWP.tokenize / matchloop (reference source/wordpiece.py:233-316) over a
+// flattened WPTrie_E2E (reference source/utils.py:66-139) on sm_100a.
+//
+// Host side (swt_wp_trie_create): builds the trie in index arrays, runs the failure-link / failure-pop
+// precompute of utils.py:108-139 breadth first from [root, root_sharp], and flattens it into
+//   edge table   open-addressing hash, 16-byte slots {node, code point, child, -}  (one 128-bit load/probe)
+//   root_lut     direct child table of the root for code points < kRootLut
+//   node_info    16 bytes per node {failure link, pops offset, pops count, -}
+//   pops         token ids emitted on a failure transition
+//   alnum        Python str.isalnum bitmap (wordpiece.py:287-288, utils.py:137)
+// all small enough to stay L2/L1 resident (about 3 MB for a 20K vocabulary).
+//
+// Device side: one thread walks one whitespace-free chunk (goto + failure transitions), tokens staged
+// in a shared-memory column; chunks longer than kShortBytes are walked twice (count, then write).
+#include <algorithm>
+#include <deque>
+#include <unordered_map>
+#include <vector>
+
+#include "encode.cuh"
+
+namespace swt {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr uint32_t kRootLut = 2048;
+constexpr uint32_t kNodeRoot = 0, kNodeRootP = 1, kNodeRootSharp = 3;   // insert("##") creates nodes 2 and 3
+
+struct WpTrieDev {
+    const uint4 *edges; uint32_t edge_mask;
+    const uint32_t *root_lut;
+    const uint4 *node_info;
+    const uint32_t *pops;
+    const uint32_t *alnum;       // 0x110000 bits
+    uint32_t n_vocab;
+    uint32_t sharp_special[2]; uint32_t n_sharp_special;
+};
+
+}  // namespace swt
+
+struct swt_wp_trie {
+    swt::WpTrieDev dev;
+    int device;
+    void *d_blob;
+    uint64_t n_nodes, n_edges, n_pops, n_rootp;
+};
+
+namespace swt {
+
+__device__ __forceinline__ uint32_t wp_edge(const WpTrieDev &t, uint32_t node, uint32_t cp) {
+    if (node == kNodeRoot && cp < kRootLut) return __ldg(&t.root_lut[cp]);
+    uint32_t h = (uint32_t)mix64(((uint64_t)node << 32) | cp) & t.edge_mask;
+    for (;;) {
+        uint4 e = __ldg(&t.edges[h]);
+        if (e.x == kNone) return kNone;
+        if (e.x == node && e.y == cp) return e.z;
+        h = (h + 1) & t.edge_mask;
+    }
+}
+__device__ __forceinline__ bool wp_alnum(const WpTrieDev &t, uint32_t cp) {
+    return cp < 0x110000u && ((__ldg(&t.alnum[cp >> 5]) >> (cp & 31u)) & 1u);
+}
+
+struct CountEmit {                       // first pass over a long chunk
+    uint32_t n = 0;
+    __device__ __forceinline__ void push(uint32_t) { ++n; }
+    __device__ __forceinline__ uint32_t size() const { return n; }
+    __device__ __forceinline__ void truncate(uint32_t k) { n = k; }
+};
+struct ColumnEmit {                      // shared-memory column, stride kTileWords
+    uint32_t *col; uint32_t n = 0;
+    __device__ __forceinline__ void push(uint32_t tok) { if (n < (uint32_t)kShortBytes) col[n * kTileWords] = tok; ++n; }
+    __device__ __forceinline__ uint32_t size() const { return n; }
+    __device__ __forceinline__ void truncate(uint32_t k) { n = k; }
+};
+struct GlobalEmit {                      // second pass over a long chunk: final position is known
+    uint32_t *out; uint32_t cap; uint32_t n = 0;
+    __device__ __forceinline__ void push(uint32_t tok) { if (n < cap) out[n] = tok; ++n; }
+    __device__ __forceinline__ uint32_t size() const { return n; }
+    __device__ __forceinline__ void truncate(uint32_t k) { n = k; }
+};
+
+// FastWP.tokenize on s = chunk + " " (wordpiece.py:248-269); the chunk holds no whitespace.
+template <class Emit>
+__device__ __forceinline__ void wp_encode_chunk(const WpTrieDev &t, const uint8_t *p, uint32_t nbytes, Emit &emit, uint32_t &h6) {
+    uint32_t i = 0;
+    bool prev_punct = false;                       // ispunc(s[i-1]); false at i == 0
+    while (i < nbytes) {
+        const uint32_t seg = emit.size(), i0 = i;
+        uint32_t node = kNodeRoot, cp = 0, adv = 1;
+        // ---- matchloop (wordpiece.py:291-316)
+        for (;;) {
+            if (i < nbytes) cp = utf8_decode(p + i, nbytes - i, adv); else { cp = 0x20u; adv = 1; }   // the appended " "
+            uint32_t child = (i < nbytes) ? wp_edge(t, node, cp) : kNone;   // no vocabulary entry holds whitespace
+            bool returned = false;
+            while (child == kNone) {                                        // failure transitions :308-312
+                const uint4 info = __ldg(&t.node_info[node]);
+                if (info.x == kNone) { returned = true; break; }
+                for (uint32_t k = 0; k < info.z; ++k) emit.push(__ldg(&t.pops[info.y + k]));
+                node = info.x;
+                child = (i < nbytes) ? wp_edge(t, node, cp) : kNone;
+            }
+            if (returned) break;
+            node = child; i += adv; prev_punct = !wp_alnum(t, cp);          // goto transition :314-315
+        }
+        // ---- accept / reject (wordpiece.py:255-261); cp is s[i]
+        bool bnd = prev_punct || i >= nbytes || !wp_alnum(t, cp);           // iswdbndry :285
+        const bool ok = bnd && (node == kNodeRoot || node == kNodeRootSharp || node == kNodeRootP);
+        if (!ok) { emit.truncate(seg); emit.push(t.n_vocab); }              // "['UNK']"
+        else if (node == kNodeRootSharp && emit.size() == seg) {
+            for (uint32_t k = 0; k < t.n_sharp_special; ++k) emit.push(t.sharp_special[k]);
+        }
+        // ---- advance to the next boundary (:265-266), then skip whitespace (:268-269)
+        while (!bnd) {
+            i += adv; prev_punct = false;                                   // s[i] was alnum here
+            if (i < nbytes) { cp = utf8_decode(p + i, nbytes - i, adv); bnd = !wp_alnum(t, cp); }
+            else bnd = true;
+        }
+        if (i == i0) {
+            // H6: punctuation that is not a child of the root -- the reference spins forever here.
+            // Documented extension: emit "['UNK']" and advance one character.
+            ++h6; emit.push(t.n_vocab);
+            i += adv; prev_punct = !wp_alnum(t, cp);
+        }
+        if (i >= nbytes) break;                                             // the virtual space ends the chunk
+    }
+}
+
+__global__ void __launch_bounds__(kTileWords)
+wp_encode_kernel(WpTrieDev t, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words,
+                 uint32_t *__restrict__ out_ids, uint64_t out_cap, uint32_t *__restrict__ out_tok_off, uint32_t tok_base,
+                 EncodeWorkspace ws, uint32_t *status) {
+    __shared__ uint32_t stage[kShortBytes * kTileWords];
+    __shared__ uint32_t sh_scan[33];
+    __shared__ uint32_t sh_tile;
+    __shared__ uint64_t sh_base;
+    const uint32_t tid = threadIdx.x;
+    uint32_t h6 = 0;
+    for (;;) {
+        if (tid == 0) sh_tile = atomicAdd(ws.ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = sh_tile;
+        if (tile >= ws.n_tiles) break;
+        const uint32_t w = tile * kTileWords + tid;
+        const bool valid = w < n_words;
+        uint32_t b0 = 0, nbytes = 0, count = 0;
+        if (valid) { b0 = word_off[w]; nbytes = word_off[w + 1] - b0; }
+        const bool is_long = valid && nbytes > kShortBytes;
+        if (valid && !is_long) { ColumnEmit e{stage + tid}; wp_encode_chunk(t, arena + b0, nbytes, e, h6); count = e.n; }
+        else if (is_long) { CountEmit e; uint32_t dummy = 0; wp_encode_chunk(t, arena + b0, nbytes, e, dummy); count = e.n; }
+        uint32_t total, excl = block_exclusive_scan(count, sh_scan, &total);
+        if (tid == 0) sh_base = tile_exclusive_prefix(ws.tile_state, tile, total, &status[kStatusCode]);
+        __syncthreads();
+        const uint64_t pos = sh_base + excl;
+        if (valid) {
+            if (out_tok_off) out_tok_off[w] = tok_base + (uint32_t)pos;
+            if (pos + count <= out_cap) {
+                if (!is_long) { for (uint32_t k = 0; k < count; ++k) out_ids[pos + k] = stage[k * kTileWords + tid]; }
+                else { GlobalEmit e{out_ids + pos, count}; wp_encode_chunk(t, arena + b0, nbytes, e, h6); }
+            } else atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY);
+        }
+        if (tile == ws.n_tiles - 1 && tid == 0) {
+            const uint64_t grand = sh_base + total;
+            if (out_tok_off) out_tok_off[n_words] = tok_base + (uint32_t)grand;
+            status[kStatusTokens] = (uint32_t)grand; status[kStatusTokensHi] = (uint32_t)(grand >> 32);
+        }
+        __syncthreads();
+    }
+    if (h6) atomicAdd(&status[kStatusH6], h6);
+}
+
+// ---- host: trie construction + precompute ---------------------------------------------------------------
+struct HostTrie {
+    std::vector<uint32_t> ch, fail, token;         // per node: edge character, failure link, vocab id (or kNone)
+    std::vector<uint8_t> is_end;
+    std::vector<std::vector<uint32_t>> pops;
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> kids;   // (code point, child) in insertion order
+    std::unordered_map<uint64_t, uint32_t> edge;                    // node<<21 | cp -> child
+
+    uint32_t add_node(uint32_t c) {
+        ch.push_back(c); fail.push_back(kNone); token.push_back(kNone); is_end.push_back(0);
+        pops.emplace_back(); kids.emplace_back();
+        return (uint32_t)ch.size() - 1;
+    }
+    uint32_t child(uint32_t node, uint32_t cp) const {
+        auto it = edge.find(((uint64_t)node << 21) | cp);
+        return it == edge.end() ? kNone : it->second;
+    }
+    uint32_t insert(const uint32_t *w, uint32_t len, uint32_t tok) {          // utils.py:87-105
+        uint32_t node = kNodeRoot;
+        for (uint32_t i = 0; i < len; ++i) {
+            uint32_t c = child(node, w[i]);
+            if (c == kNone) {
+                c = add_node(w[i]);
+                edge.emplace(((uint64_t)node << 21) | w[i], c);
+                kids[node].emplace_back(w[i], c);
+            }
+            node = c;
+        }
+        is_end[node] = 1;
+        if (tok != kNone) token[node] = tok;
+        return node;
+    }
+};
+
+}  // namespace swt
+
+using namespace swt;
+
+SWT_API int swt_wp_trie_create(const uint32_t *h_vocab_cps, const uint64_t *h_vocab_off, uint32_t n_vocab,
+                               const uint8_t *h_alnum_bitmap, const uint32_t *h_sharp_special, uint32_t n_sharp_special,
+                               int device, swt_wp_trie **out) {
+    SWT_REQUIRE(out && h_alnum_bitmap && h_vocab_off, "NULL argument");
+    SWT_REQUIRE(n_sharp_special <= 2, "NaiveWP.encode_word('##') longer than 2 tokens is outside the supported domain");
+    SWT_REQUIRE(n_vocab < 0x7FFFFFF0u, "vocabulary too large");
+    SWT_CUDA_OK(cudaSetDevice(device));
+    auto alnum = [&](uint32_t cp) { return cp < 0x110000u && ((h_alnum_bitmap[cp >> 3] >> (cp & 7)) & 1); };
+
+    HostTrie T;
+    T.add_node(0);                                   // root
+    T.add_node(0);                                   // root_p: no children, no failure link (utils.py:79)
+    const uint32_t sharp[2] = {'#', '#'};
+    const uint32_t r_sharp = T.insert(sharp, 2, kNone);                       // utils.py:81
+    if (r_sharp != kNodeRootSharp) { set_error("internal: root_sharp id"); return SWT_ERR_INTERNAL; }
+    for (uint32_t v = 0; v < n_vocab; ++v) {
+        const uint32_t len = (uint32_t)(h_vocab_off[v + 1] - h_vocab_off[v]);
+        for (uint32_t k = 0; k < len; ++k) SWT_REQUIRE(h_vocab_cps[h_vocab_off[v] + k] < 0x110000u, "code point out of range");
+        T.insert(h_vocab_cps + h_vocab_off[v], len, v);                       // utils.py:83-84
+    }
+    // failure links and pops, breadth first from [root, root_sharp] (utils.py:113-139)
+    std::deque<uint32_t> queue{kNodeRoot, kNodeRootSharp};
+    while (!queue.empty()) {
+        const uint32_t cur = queue.front(); queue.pop_front();
+        for (const auto &kc : T.kids[cur]) {
+            const uint32_t c = kc.first, child = kc.second;
+            if (child == kNodeRootSharp) continue;
+            if (T.is_end[child]) {                   // a vocabulary entry ends here: pop it, continue from "##"
+                T.fail[child] = kNodeRootSharp;
+                T.pops[child].assign(1, T.token[child]);
+            } else {
+                uint32_t f = T.fail[cur];
+                std::vector<uint32_t> extra;
+                while (f != kNone && T.child(f, c) == kNone) {
+                    extra.insert(extra.end(), T.pops[f].begin(), T.pops[f].end());
+                    f = T.fail[f];
+                }
+                if (f != kNone) {
+                    T.fail[child] = T.child(f, c);
+                    T.pops[child] = T.pops[cur];
+                    T.pops[child].insert(T.pops[child].end(), extra.begin(), extra.end());
+                }
+            }
+            if (!alnum(T.ch[child])) T.fail[child] = kNodeRootP;              // utils.py:137-138
+            queue.push_back(child);
+        }
+    }
+    // flatten
+    const uint64_t n_nodes = T.ch.size(), n_edges = T.edge.size();
+    const uint64_t n_slots = next_pow2(n_edges * 2 + 16);
+    std::vector<uint4> slots(n_slots, make_uint4(kNone, 0, 0, 0));
+    std::vector<uint32_t> root_lut(kRootLut, kNone);
+    for (uint32_t node = 0; node < n_nodes; ++node)
+        for (const auto &kc : T.kids[node]) {
+            uint64_t h = mix64(((uint64_t)node << 32) | kc.first) & (n_slots - 1);
+            while (slots[h].x != kNone) h = (h + 1) & (n_slots - 1);
+            slots[h] = make_uint4(node, kc.first, kc.second, 0);
+            if (node == kNodeRoot && kc.first < kRootLut) root_lut[kc.first] = kc.second;
+        }
+    std::vector<uint4> info(n_nodes);
+    std::vector<uint32_t> pops;
+    uint64_t n_rootp = 0;
+    for (uint32_t node = 0; node < n_nodes; ++node) {
+        info[node] = make_uint4(T.fail[node], (uint32_t)pops.size(), (uint32_t)T.pops[node].size(), 0);
+        pops.insert(pops.end(), T.pops[node].begin(), T.pops[node].end());
+        n_rootp += (T.fail[node] == kNodeRootP);
+    }
+    Carver sz(nullptr);
+    sz.take<uint4>(n_slots); sz.take<uint4>(n_nodes); sz.take<uint32_t>(kRootLut); sz.take<uint32_t>(pops.size() + 1); sz.take<uint32_t>(0x110000 / 32);
+    void *blob = nullptr;
+    SWT_CUDA_OK(cudaMalloc(&blob, sz.used()));
+    Carver cv(blob);
+    uint4 *d_slots = cv.take<uint4>(n_slots); uint4 *d_info = cv.take<uint4>(n_nodes);
+    uint32_t *d_lut = cv.take<uint32_t>(kRootLut); uint32_t *d_pops = cv.take<uint32_t>(pops.size() + 1);
+    uint32_t *d_alnum = cv.take<uint32_t>(0x110000 / 32);
+    cudaError_t e = cudaMemcpy(d_slots, slots.data(), n_slots * sizeof(uint4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_info, info.data(), n_nodes * sizeof(uint4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_lut, root_lut.data(), kRootLut * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !pops.empty()) e = cudaMemcpy(d_pops, pops.data(), pops.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_alnum, h_alnum_bitmap, 0x110000 / 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(blob); set_error(std::string("trie upload: ") + cudaGetErrorString(e)); return SWT_ERR_CUDA; }
+    swt_wp_trie *t = new swt_wp_trie();
+    t->dev.edges = d_slots; t->dev.edge_mask = (uint32_t)(n_slots - 1); t->dev.root_lut = d_lut; t->dev.node_info = d_info;
+    t->dev.pops = d_pops; t->dev.alnum = d_alnum; t->dev.n_vocab = n_vocab; t->dev.n_sharp_special = n_sharp_special;
+    for (uint32_t k = 0; k < 2; ++k) t->dev.sharp_special[k] = k < n_sharp_special ? h_sharp_special[k] : 0;
+    t->device = device; t->d_blob = blob;
+    t->n_nodes = n_nodes; t->n_edges = n_edges; t->n_pops = pops.size(); t->n_rootp = n_rootp;
+    *out = t;
+    return SWT_OK;
+}
+
+SWT_API void swt_wp_trie_destroy(swt_wp_trie *t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    cudaFree(t->d_blob);
+    delete t;
+}
+
+SWT_API int swt_wp_trie_stats(const swt_wp_trie *t, uint64_t *n_nodes, uint64_t *n_edges, uint64_t *n_pops, uint64_t *n_rootp) {
+    SWT_REQUIRE(t != nullptr, "NULL trie");
+    if (n_nodes) *n_nodes = t->n_nodes;
+    if (n_edges) *n_edges = t->n_edges;
+    if (n_pops) *n_pops = t->n_pops;
+    if (n_rootp) *n_rootp = t->n_rootp;
+    return SWT_OK;
+}
+
+namespace swt { int encode_grid(const void *kernel, int block); }
+
+namespace swt {
+int wp_encode_launch(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
+                     uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off, uint32_t tok_base,
+                     void *d_workspace, size_t workspace_bytes, uint32_t *d_status, cudaStream_t st) {
+    SWT_REQUIRE(t && d_word_off && d_status && d_workspace, "NULL argument");
+    SWT_REQUIRE(n_words == 0 || (d_arena && d_out_ids), "NULL data pointer");
+    EncodeWorkspace ws;
+    size_t need = encode_workspace_layout(n_words, 0, d_workspace, &ws);
+    if (need > workspace_bytes) { set_error("encode workspace too small"); return SWT_ERR_CAPACITY; }
+    SWT_CUDA_OK(cudaMemsetAsync(d_workspace, 0, need, st));
+    SWT_CUDA_OK(cudaMemsetAsync(d_status, 0, 8 * sizeof(uint32_t), st));
+    if (n_words == 0) {
+        if (d_out_tok_off) SWT_CUDA_OK(cudaMemcpyAsync(d_out_tok_off, &tok_base, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        return SWT_OK;
+    }
+    static int grid = 0;
+    if (!grid) grid = encode_grid((const void *)wp_encode_kernel, kTileWords);
+    int g = (int)std::min<uint64_t>((uint64_t)grid, ws.n_tiles);
+    wp_encode_kernel<<<g, kTileWords, 0, st>>>(t->dev, d_arena, d_word_off, n_words, d_out_ids, out_cap, d_out_tok_off, tok_base, ws, d_status);
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}
+}  // namespace swt
+
+SWT_API int swt_wp_encode(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
+                          uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off,
+                          void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream) {
+    (void)long_word_bytes;   // long chunks are walked twice instead of using scratch
+    return wp_encode_launch(t, d_arena, d_word_off, n_words, d_out_ids, out_cap, d_out_tok_off, 0u, d_workspace, workspace_bytes,
+                            d_status, (cudaStream_t)stream);
+}

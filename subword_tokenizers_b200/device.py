@@ -1,0 +1,333 @@
+"""Device-side objects: rank table / trie handles, encode calls and the BPE trainer loop.
+
+PyTorch is used only to own device buffers and streams (and ``torch.distributed`` for the two small
+collectives of multi-GPU training); every computation is a call into libswt.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SHORT_WORD_BYTES, SwtError, TrainConfig, TrainState, check, c_u8p, c_u32p, c_u64p, c_i64p, c_vp
+from . import packing as P
+
+
+def _np_ptr(a: np.ndarray, typ):
+    return a.ctypes.data_as(typ)
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def current_device() -> int:
+    return torch.cuda.current_device()
+
+
+class _Encoder:
+    """Shared encode plumbing: words -> arena on device -> libswt encode -> token ids (+ offsets)."""
+
+    _which = -1
+
+    def __init__(self):
+        self._handle = c_vp(None)
+        self._pipeline = c_vp(None)
+        self._pipeline_batch = 0
+
+    # -- device-resident call ---------------------------------------------------------------------------
+    def encode_device(self, d_arena: torch.Tensor, d_off: torch.Tensor, n_words: int, long_word_bytes: int,
+                      out_cap: Optional[int] = None, want_offsets: bool = True):
+        """d_arena: uint8 CUDA tensor, d_off: int32/uint32-compatible CUDA tensor of n_words+1 offsets.
+        Returns (d_ids[out_cap] int32 tensor, d_tok_off or None, d_status); asynchronous."""
+        lib = _lib.load()
+        dev = d_arena.device
+        if out_cap is None:
+            out_cap = int(d_arena.numel()) + n_words + 16
+        ws_bytes = lib.swt_encode_workspace_bytes(n_words, long_word_bytes)
+        d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        d_ids = torch.empty(max(out_cap, 1), dtype=torch.int32, device=dev)
+        d_tok_off = torch.empty(n_words + 1, dtype=torch.int32, device=dev) if want_offsets else None
+        d_status = torch.empty(8, dtype=torch.int32, device=dev)
+        self.encode_into(d_arena, d_off, n_words, long_word_bytes, d_ids, out_cap, d_tok_off, d_ws, d_status)
+        return d_ids, d_tok_off, d_status
+
+    def encode_into(self, d_arena, d_off, n_words, long_word_bytes, d_ids, out_cap, d_tok_off, d_ws, d_status):
+        lib = _lib.load()
+        fn = lib.swt_bpe_encode if self._which == 0 else lib.swt_wp_encode
+        check(fn(self._handle, d_arena.data_ptr(), d_off.data_ptr(), n_words, long_word_bytes, d_ids.data_ptr(), out_cap,
+                 d_tok_off.data_ptr() if d_tok_off is not None else None, d_ws.data_ptr(), d_ws.numel(),
+                 d_status.data_ptr(), _stream_ptr()), "swt_encode")
+
+    @staticmethod
+    def check_status(d_status: torch.Tensor) -> Tuple[int, int]:
+        """Synchronises; returns (n_tokens, h6_events) or raises."""
+        st = d_status.cpu().numpy().astype(np.uint32)
+        if st[0] != 0:
+            raise SwtError("encode kernel status %d" % int(st[0]))
+        return int(st[1]) | (int(st[3]) << 32), int(st[2])
+
+    # -- convenience: Python words in, numpy out ---------------------------------------------------------------
+    def encode_words(self, words: Sequence[str]) -> Tuple[np.ndarray, np.ndarray, int]:
+        """-> (token ids u32, token offsets u32[n_words+1], h6_events)."""
+        _lib.require_cuda()
+        arena, off = P.pack_words(words, offset_dtype=np.uint64)
+        if len(arena) >= (1 << 32) - 64:
+            raise SwtError("arena >= 4 GiB: split the batch")
+        return self.encode_packed(arena, off.astype(np.uint32))
+
+    def encode_packed(self, arena: np.ndarray, off: np.ndarray) -> Tuple[np.ndarray, np.ndarray, int]:
+        n_words = len(off) - 1
+        lens = np.diff(off.astype(np.int64))
+        long_bytes = int(lens[lens > SHORT_WORD_BYTES].sum()) if n_words else 0
+        dev = torch.device("cuda", current_device())
+        d_arena = torch.from_numpy(arena).to(dev) if len(arena) else torch.zeros(1, dtype=torch.uint8, device=dev)
+        d_off = torch.from_numpy(off.view(np.int32)).to(dev)
+        d_ids, d_tok_off, d_status = self.encode_device(d_arena, d_off, n_words, long_bytes)
+        n_tok, h6 = self.check_status(d_status)
+        ids = d_ids[:n_tok].cpu().numpy().view(np.uint32)
+        tok_off = d_tok_off.cpu().numpy().view(np.uint32)
+        return ids, tok_off, h6
+
+    # -- host-buffer pipeline (the e2e path) --------------------------------------------------------------------
+    def pipeline(self, batch_bytes: int = 64 << 20):
+        lib = _lib.load()
+        if not self._pipeline or self._pipeline_batch != batch_bytes:
+            if self._pipeline:
+                lib.swt_pipeline_destroy(self._pipeline)
+            h = c_vp(None)
+            check(lib.swt_pipeline_create(current_device(), batch_bytes, ctypes.byref(h)), "swt_pipeline_create")
+            self._pipeline, self._pipeline_batch = h, batch_bytes
+        return self._pipeline
+
+    def encode_host(self, h_arena: torch.Tensor, h_off: torch.Tensor, h_out_ids: torch.Tensor,
+                    h_out_tok_off: Optional[torch.Tensor], batch_bytes: int = 64 << 20) -> Tuple[int, int]:
+        """Host (ideally pinned) tensors in and out, through swt_encode_host. -> (n_tokens, h6_events)."""
+        lib = _lib.load()
+        n_words = h_off.numel() - 1
+        nt, h6 = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        check(lib.swt_encode_host(self.pipeline(batch_bytes), self._which, self._handle, h_arena.data_ptr(), h_off.data_ptr(),
+                                  n_words, h_out_ids.data_ptr(), h_out_ids.numel(),
+                                  h_out_tok_off.data_ptr() if h_out_tok_off is not None else None,
+                                  ctypes.byref(nt), ctypes.byref(h6)), "swt_encode_host")
+        return int(nt.value), int(h6.value)
+
+    def close(self):
+        lib = _lib.load()
+        if self._pipeline:
+            lib.swt_pipeline_destroy(self._pipeline)
+            self._pipeline = c_vp(None)
+        self._destroy()
+
+    def _destroy(self):
+        raise NotImplementedError
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BpeEncoder(_Encoder):
+    """Device rank table of a merge list (reference FastBPE._bpe_ranks, bpe.py:200,257)."""
+
+    _which = 0
+
+    def __init__(self, tables: P.BpeTables, device: Optional[int] = None):
+        super().__init__()
+        _lib.require_cuda()
+        lib = _lib.load()
+        self.tables = tables
+        left, right, new = (np.ascontiguousarray(x, dtype=np.uint32) for x in (tables.left, tables.right, tables.new))
+        ccp, cid = np.ascontiguousarray(tables.char_cp, np.uint32), np.ascontiguousarray(tables.char_id, np.uint32)
+        check(lib.swt_bpe_table_create(_np_ptr(left, c_u32p), _np_ptr(right, c_u32p), _np_ptr(new, c_u32p), len(left),
+                                       _np_ptr(ccp, c_u32p), _np_ptr(cid, c_u32p), len(ccp),
+                                       current_device() if device is None else device, ctypes.byref(self._handle)),
+              "swt_bpe_table_create")
+
+    def _destroy(self):
+        if self._handle:
+            _lib.load().swt_bpe_table_destroy(self._handle)
+            self._handle = c_vp(None)
+
+
+class WpEncoder(_Encoder):
+    """Device trie + failure links of a vocabulary (reference WPTrie_E2E, utils.py:66-139)."""
+
+    _which = 1
+
+    def __init__(self, tables: P.WpTables, sharp_special: Sequence[int], device: Optional[int] = None):
+        super().__init__()
+        _lib.require_cuda()
+        lib = _lib.load()
+        self.tables = tables
+        alnum, _ = P.unicode_class_bitmaps()
+        cps, off = np.ascontiguousarray(tables.cps, np.uint32), np.ascontiguousarray(tables.off, np.uint64)
+        ss = np.ascontiguousarray(list(sharp_special) + [0, 0], dtype=np.uint32)
+        if len(sharp_special) > 2:
+            raise NotImplementedError("NaiveWP.encode_word('##') longer than 2 tokens is outside the supported domain")
+        check(lib.swt_wp_trie_create(_np_ptr(cps, c_u32p), _np_ptr(off, c_u64p), tables.n_vocab, _np_ptr(alnum, c_u8p),
+                                     _np_ptr(ss, c_u32p), len(sharp_special),
+                                     current_device() if device is None else device, ctypes.byref(self._handle)),
+              "swt_wp_trie_create")
+
+    def stats(self):
+        n, e, p, r = (ctypes.c_uint64(0) for _ in range(4))
+        check(_lib.load().swt_wp_trie_stats(self._handle, ctypes.byref(n), ctypes.byref(e), ctypes.byref(p), ctypes.byref(r)))
+        return {"nodes": n.value, "edges": e.value, "pops": p.value, "root_p_links": r.value}
+
+    def _destroy(self):
+        if self._handle:
+            _lib.load().swt_wp_trie_destroy(self._handle)
+            self._handle = c_vp(None)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# HP-3 trainer
+# ------------------------------------------------------------------------------------------------------------
+
+HALT_RUN, HALT_DONE_VOCAB, HALT_DONE_NOPAIRS, HALT_GROW, HALT_RECORD_FULL = 0, 1, 2, 3, 4
+
+
+def shard_types(off: np.ndarray, world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous type ranges [t0, t1) per rank, balanced by symbol count (global first-occurrence
+    order is preserved inside and across shards, which the tie-break needs)."""
+    n_types = len(off) - 1
+    total = int(off[-1])
+    bounds = [0]
+    for r in range(1, world_size):
+        target = total * r // world_size
+        t = int(np.searchsorted(off, target, side="left"))
+        bounds.append(min(max(t, bounds[-1]), n_types))
+    bounds.append(n_types)
+    return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
+
+
+class CudaTrainEngine:
+    """One rank's share of the word table + its replica of the pair table, on the GPU (libswt)."""
+
+    def __init__(self, syms: np.ndarray, off: np.ndarray, freq: np.ndarray, n_alpha: int, max_vocab: int,
+                 initial_vocab: int, max_word_len: int, slot_base: int, rank: int, world_size: int,
+                 record_cap: int = 4096, table_cap: int = 0):
+        _lib.require_cuda()
+        lib = _lib.load()
+        self.lib = lib
+        self.dev = torch.device("cuda", current_device())
+        n_types = len(off) - 1
+        self.cfg = TrainConfig(n_types, int(off[-1]) if n_types else 0, slot_base, n_alpha, max_vocab, initial_vocab,
+                               max(1, max_word_len), record_cap, world_size, rank, table_cap)
+        ws_bytes = lib.swt_bpe_train_workspace_bytes(ctypes.byref(self.cfg))
+        self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=self.dev)
+        self._keep = [
+            torch.from_numpy(np.ascontiguousarray(syms, dtype=np.uint32).view(np.int32)).to(self.dev),
+            torch.from_numpy(np.ascontiguousarray(off, dtype=np.uint64).view(np.int64)).to(self.dev),
+            torch.from_numpy(np.ascontiguousarray(freq, dtype=np.int64)).to(self.dev),
+        ]
+        self.handle = c_vp(None)
+        check(lib.swt_bpe_train_create(ctypes.byref(self.cfg), self._keep[0].data_ptr(), self._keep[1].data_ptr(),
+                                       self._keep[2].data_ptr(), self.workspace.data_ptr(), ws_bytes, _stream_ptr(),
+                                       ctypes.byref(self.handle)), "swt_bpe_train_create")
+        ic, ice, cp, cgp, dp, de = c_vp(), ctypes.c_uint64(), c_vp(), c_vp(), c_vp(), ctypes.c_uint64()
+        check(lib.swt_bpe_train_buffers(self.handle, ctypes.byref(ic), ctypes.byref(ice), ctypes.byref(cp), ctypes.byref(cgp),
+                                        ctypes.byref(dp), ctypes.byref(de)))
+        base = self.workspace.data_ptr()
+        w64 = self.workspace.view(torch.int64)           # workspace regions are 256-byte aligned
+
+        def view(ptr, n):
+            o = (ptr.value - base) // 8
+            return w64[o:o + n]
+        self.init_counts = view(ic, ice.value)
+        self.cand = view(cp, 2)
+        self.cand_gather = view(cgp, 2 * world_size)
+        self.delta = view(dp, de.value)
+        self.record_cap = record_cap
+        self._rec = [np.zeros(record_cap, dtype=np.uint32) for _ in range(3)] + [np.zeros(record_cap, dtype=np.int64)]
+        self._tables: List[torch.Tensor] = []
+        self.n_types, self.n_slots = n_types, int(off[-1]) if n_types else 0
+
+    # phases (all asynchronous on the current stream)
+    def count_local(self): check(self.lib.swt_bpe_train_count_local(self.handle, _stream_ptr()))
+    def build_table(self): check(self.lib.swt_bpe_train_build_table(self.handle, _stream_ptr()))
+    def select(self): check(self.lib.swt_bpe_train_select(self.handle, _stream_ptr()))
+    def merge(self): check(self.lib.swt_bpe_train_merge(self.handle, _stream_ptr()))
+    def update(self): check(self.lib.swt_bpe_train_update(self.handle, _stream_ptr()))
+    def steps(self, n: int): check(self.lib.swt_bpe_train_steps(self.handle, n, _stream_ptr()))
+
+    def read(self):
+        """Synchronises. -> (state dict, left, right, new, count) for the merges recorded since the last read."""
+        st = TrainState()
+        check(self.lib.swt_bpe_train_read(self.handle, _np_ptr(self._rec[0], c_u32p), _np_ptr(self._rec[1], c_u32p),
+                                          _np_ptr(self._rec[2], c_u32p), _np_ptr(self._rec[3], c_i64p), ctypes.byref(st),
+                                          _stream_ptr()), "swt_bpe_train_read")
+        n = st.n_recorded
+        state = {f[0]: getattr(st, f[0]) for f in TrainState._fields_}
+        return state, self._rec[0][:n].copy(), self._rec[1][:n].copy(), self._rec[2][:n].copy(), self._rec[3][:n].copy()
+
+    def grow_table(self, cur_cap: int):
+        new_cap = cur_cap * 4
+        buf = torch.empty(self.lib.swt_bpe_train_table_bytes(new_cap), dtype=torch.uint8, device=self.dev)
+        self._tables.append(buf)                       # keep alive; older tables are released after the rehash ran
+        check(self.lib.swt_bpe_train_grow_table(self.handle, buf.data_ptr(), new_cap, _stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+        self._tables = self._tables[-1:]
+
+    def read_corpus(self):
+        syms = np.zeros(max(self.n_slots, 1), dtype=np.uint32)
+        lens = np.zeros(max(self.n_types, 1), dtype=np.uint32)
+        check(self.lib.swt_bpe_train_read_corpus(self.handle, _np_ptr(syms, c_u32p), _np_ptr(lens, c_u32p), _stream_ptr()))
+        return syms[:self.n_slots], lens[:self.n_types]
+
+    def close(self):
+        if self.handle:
+            torch.cuda.synchronize()
+            self.lib.swt_bpe_train_destroy(self.handle)
+            self.handle = c_vp(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def run_training_loop(engine, world_size: int = 1, group=None, steps_per_sync: int = 256, progress=None):
+    """Drives one rank's engine until the trainer halts; returns (left, right, new, count, state).
+
+    ``engine`` exposes count_local/build_table/select/merge/update/steps/read/grow_table and the exchange
+    tensors init_counts / cand / cand_gather / delta.  With world_size > 1 the two collectives per step are
+    issued through torch.distributed on those tensors (NCCL on GPUs; the CPU tests drive a numpy engine
+    over gloo through this same function).
+    """
+    import torch.distributed as dist
+    lefts, rights, news, counts = [], [], [], []
+    engine.count_local()
+    if world_size > 1:
+        dist.all_reduce(engine.init_counts, op=dist.ReduceOp.SUM, group=group)
+    engine.build_table()
+    while True:
+        if world_size == 1:
+            engine.steps(steps_per_sync)
+        else:
+            for _ in range(steps_per_sync):
+                engine.select()
+                dist.all_gather_into_tensor(engine.cand_gather, engine.cand, group=group)
+                engine.merge()
+                dist.all_reduce(engine.delta, op=dist.ReduceOp.SUM, group=group)
+                engine.update()
+        state, l, r, n, c = engine.read()
+        lefts.append(l); rights.append(r); news.append(n); counts.append(c)
+        if progress is not None and len(l):
+            progress(len(l))
+        halt = state["halt"]
+        if halt in (HALT_DONE_VOCAB, HALT_DONE_NOPAIRS):
+            break
+        if halt == HALT_GROW:
+            engine.grow_table(state["table_cap"])
+        elif halt >= 16:
+            raise SwtError("BPE trainer halted with device error %d" % halt)
+    cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dtype=dt)
+    return cat(lefts, np.uint32), cat(rights, np.uint32), cat(news, np.uint32), cat(counts, np.int64), state

@@ -1,0 +1,332 @@
+"""GPU parity tests proper: every call goes through the C ABI (libswt.so) on cuda:0 and is compared with
+the CPU oracle on the same inputs and with the committed golden vectors produced by the reference."""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    from subword_tokenizers_b200 import packing
+    return packing
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    assert torch.cuda.is_available(), "the gpu tests need a CUDA device"
+    from subword_tokenizers_b200 import device
+    return device
+
+
+def _split(strs, tok_off, counts):
+    out, wi = [], 0
+    for n in counts:
+        out.append(strs[int(tok_off[wi]):int(tok_off[wi + n])])
+        wi += n
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ HP-1
+def test_fastbpe_pan_tadeusz_golden(P, dev, pre_tokenize):
+    import oracle
+    lines = load_golden("pan_tadeusz.json.gz")
+    gold = load_golden("pan_tadeusz.tokens.json.gz")["FastBPE"]
+    tab = P.BpeTables([tuple(p) for p in load_golden("pretrained_bpe_merges.json.gz")])
+    enc = dev.BpeEncoder(tab)
+    words = [pre_tokenize(l) for l in lines]
+    flat = [w for ws in words for w in ws]
+    ids, tok_off, _ = enc.encode_words(flat)
+    assert _split(tab.tokens_to_strs(ids), tok_off, [len(ws) for ws in words]) == gold
+    o_ids, o_off = oracle.bpe_encode(tab, *P.pack_words(flat))
+    assert np.array_equal(ids, o_ids) and np.array_equal(tok_off.astype(np.uint64), o_off)
+
+
+def test_fastbpe_random_cases(P, dev, random_cases):
+    import oracle
+    for case in random_cases["bpe_encode"]:
+        tab = P.BpeTables([tuple(p) for p in case["merges"]])
+        enc = dev.BpeEncoder(tab)
+        ids, tok_off, _ = enc.encode_words(case["words"])
+        strs = tab.tokens_to_strs(ids)
+        assert [strs[int(tok_off[i]):int(tok_off[i + 1])] for i in range(len(case["words"]))] == case["fast"]
+        o_ids, o_off = oracle.bpe_encode(tab, *P.pack_words(case["words"]))
+        assert np.array_equal(ids, o_ids) and np.array_equal(tok_off.astype(np.uint64), o_off)
+        enc.close()
+
+
+def _adversarial_words(rng, alphabet):
+    words = ["", "a", "ab"]
+    for n in (31, 32, 33, 255, 256, 257, 4096, 65536):
+        words.append("a" * n)                                                   # runs: overlap semantics (H2)
+        words.append("".join(rng.choice(list(alphabet), size=n)))               # long random words
+    words += ["".join(rng.choice(list(alphabet), size=int(rng.integers(1, 40)))) for _ in range(3000)]
+    words += ["ż" * 17, "€uro", "\U0001F600ab", "ab\U0001F600", "q" * 40]          # non-ASCII, unknown chars
+    return words
+
+
+def test_fastbpe_adversarial_vs_oracle(P, dev):
+    import oracle
+    rng = np.random.default_rng(5)
+    merges = [tuple(p) for p in load_golden("pretrained_bpe_merges.json.gz")]
+    merges += [("a", "a"), ("aa", "aa"), ("aaaa", "aaaa"), ("aaaaaaaa", "aaaaaaaa"), ("b", "a"), ("a", "b")]
+    tab = P.BpeTables(merges)
+    enc = dev.BpeEncoder(tab)
+    words = _adversarial_words(rng, "abcdeiknorstwyzł")
+    ids, tok_off, _ = enc.encode_words(words)
+    o_ids, o_off = oracle.bpe_encode(tab, *P.pack_words(words))
+    assert np.array_equal(tok_off.astype(np.uint64), o_off)
+    assert np.array_equal(ids, o_ids)
+    # untrainable-order list: FastBPE semantics, not NaiveBPE's
+    tab2 = P.BpeTables([("ab", "c"), ("a", "b")])
+    enc2 = dev.BpeEncoder(tab2)
+    ids2, _, _ = enc2.encode_words(["abc"])
+    assert tab2.tokens_to_strs(ids2) == ["abc"]
+
+
+def test_bpe_empty_inputs(P, dev):
+    tab = P.BpeTables([("a", "b")])
+    enc = dev.BpeEncoder(tab)
+    ids, tok_off, _ = enc.encode_words([])
+    assert len(ids) == 0 and list(tok_off) == [0]
+    ids, tok_off, _ = enc.encode_words(["", "ab", ""])
+    assert tab.tokens_to_strs(ids) == ["", "ab", ""] and list(tok_off) == [0, 1, 2, 3]
+
+
+# ------------------------------------------------------------------------------------------------ HP-2
+def _wp_encoder(P, dev, vocab):
+    from subword_tokenizers_b200.utils import naive_wp_encode_ids
+    tab = P.WpTables(vocab)
+    return tab, dev.WpEncoder(tab, naive_wp_encode_ids("##", tab))
+
+
+def test_fastwp_pan_tadeusz_golden(P, dev):
+    import oracle
+    lines = load_golden("pan_tadeusz.json.gz")
+    gold = load_golden("pan_tadeusz.tokens.json.gz")["FastWordPiece"]
+    tab, enc = _wp_encoder(P, dev, load_golden("pretrained_wp_vocab.json.gz"))
+    st = enc.stats()
+    assert (st["nodes"], st["edges"], st["pops"], st["root_p_links"]) == (50173, 50171, 50277, 122)
+    chunks = [l.lower().split() for l in lines]
+    flat = [c for cs in chunks for c in cs]
+    ids, tok_off, h6 = enc.encode_words(flat)
+    assert h6 == 0
+    assert _split(tab.tokens_to_strs(ids), tok_off, [len(cs) for cs in chunks]) == gold
+    alnum, space = P.unicode_class_bitmaps()
+    o_ids, o_off, _ = oracle.WpTrie(tab, alnum).encode(*P.pack_words(flat), space)
+    assert np.array_equal(ids, o_ids) and np.array_equal(tok_off.astype(np.uint64), o_off)
+
+
+def test_fastwp_random_cases(P, dev, random_cases):
+    import oracle
+    alnum, space = P.unicode_class_bitmaps()
+    n_ref = 0
+    for case in random_cases["wp_encode"]:
+        try:
+            tab, enc = _wp_encoder(P, dev, case["vocab"])
+        except NotImplementedError:
+            continue
+        trie = oracle.WpTrie(tab, alnum)
+        for text, fast in zip(case["texts"], case["fast"]):
+            chunks = text.lower().split()
+            ids, tok_off, h6 = enc.encode_words(chunks)
+            o_ids, o_off, o_h6 = trie.encode(*P.pack_words(chunks), space)
+            assert np.array_equal(ids, o_ids) and np.array_equal(tok_off.astype(np.uint64), o_off) and h6 == o_h6
+            if fast is not None:                      # the reference terminated on this text
+                assert h6 == 0 and tab.tokens_to_strs(ids) == fast
+                n_ref += 1
+        enc.close()
+    assert n_ref > 500
+
+
+def test_fastwp_adversarial_vs_oracle(P, dev):
+    import oracle
+    rng = np.random.default_rng(7)
+    vocab = load_golden("pretrained_wp_vocab.json.gz")
+    tab, enc = _wp_encoder(P, dev, vocab)
+    alnum, space = P.unicode_class_bitmaps()
+    trie = oracle.WpTrie(tab, alnum)
+    alphabet = list("abcdeiknorstwyzł.,-!")
+    chunks = ["", "a", "##", "##a", "a##", ".", "...", "a.b", "€", "a€b", "\U0001F600", "x" * 33]
+    for n in (31, 32, 33, 255, 256, 257, 4096, 65536):
+        chunks.append("a" * n)
+        chunks.append("".join(rng.choice(alphabet, size=n)))
+    chunks += ["".join(rng.choice(alphabet, size=int(rng.integers(1, 40)))) for _ in range(5000)]
+    ids, tok_off, h6 = enc.encode_words(chunks)
+    o_ids, o_off, o_h6 = trie.encode(*P.pack_words(chunks), space)
+    assert np.array_equal(tok_off.astype(np.uint64), o_off)
+    assert np.array_equal(ids, o_ids) and h6 == o_h6 and h6 > 0
+
+
+# ------------------------------------------------------------------------------------------------ HP-3
+def _train_gpu(dev, P, words, max_vocab, **kw):
+    tt = P.TrainTypes(words)
+    max_len = int(np.diff(tt.off.astype(np.int64)).max()) if tt.n_types else 1
+    eng = dev.CudaTrainEngine(tt.syms, tt.off, tt.freq, tt.n_alpha, max_vocab, tt.n_alpha, max_len, 0, 0, 1, **kw)
+    l, r, n, c, state = dev.run_training_loop(eng, 1, steps_per_sync=kw.get("record_cap", 64))
+    return tt, l, r, n, c, state, eng
+
+
+def _train_oracle(P, words, max_vocab):
+    import oracle
+    tt = P.TrainTypes(words)
+    return oracle.bpe_train(tt.syms, tt.off, tt.freq, tt.n_alpha, max_vocab)
+
+
+def test_bpe_train_kats(P, dev, pre_tokenize):
+    kat = load_golden("kat_tests_resources.json")
+    words = [w for s in kat["corpus"] for w in pre_tokenize(s)]
+    tt, l, r, n, c, state, _ = _train_gpu(dev, P, words, kat["max_vocab"])
+    merges, _ = tt.merges_to_strs(l, r, n)
+    assert merges == [tuple(p) for p in kat["FastBPE"]]
+    assert state["vocab_size"] == 25 and state["halt"] == 1
+    tt, l, r, n, c, state, _ = _train_gpu(dev, P, pre_tokenize("aaa aaa b"), 10)
+    assert tt.merges_to_strs(l, r, n)[0] == [("a", "a"), ("aa", "a")]
+    assert state["halt"] == 2                                     # no pairs left (bpe.py:98-99)
+
+
+def test_bpe_train_random_cases(P, dev, random_cases, pre_tokenize):
+    for case in random_cases["bpe_train"]:
+        words = [w for s in case["corpus"] for w in pre_tokenize(s)]
+        tt, l, r, n, c, state, _ = _train_gpu(dev, P, words, case["max_vocab"], record_cap=7)
+        merges, _ = tt.merges_to_strs(l, r, n)
+        assert merges == [tuple(p) for p in case["merges"]], case["corpus"]
+        assert state["vocab_size"] == case["vocab_size"]
+        ol, orr, on, oc, ovs = _train_oracle(P, words, case["max_vocab"])
+        assert np.array_equal(l, ol) and np.array_equal(r, orr) and np.array_equal(n, on) and np.array_equal(c, oc)
+
+
+def test_bpe_train_5k_config1(P, dev, pre_tokenize):
+    corpus = load_golden("train-5K.json.gz")
+    words = [w for s in corpus for w in pre_tokenize(s)]
+    tt, l, r, n, c, state, eng = _train_gpu(dev, P, words, 1000, record_cap=256)
+    merges, strs = tt.merges_to_strs(l, r, n)
+    assert len(merges) == 922 and state["vocab_size"] == 1000
+    assert merges == [tuple(p) for p in load_golden("ref_bpe_train5k_v1000_merges.json.gz")]
+    h = hashlib.sha256(json.dumps(merges, ensure_ascii=False).encode()).hexdigest()
+    assert h == "f5f4451432124d34d4b1803a7482deebb3ac78d88e891cd6e8f10f5ad8967a44"
+    ol, orr, on, oc, _ = _train_oracle(P, words, 1000)
+    assert np.array_equal(c, oc)                                  # chosen pair counts agree step by step
+    # the device word table equals a replay of the merges (merge-apply parity)
+    syms, lens = eng.read_corpus()
+    total = 0
+    for k in range(0, tt.n_types, 997):
+        word = list(tt.types[k])
+        for a, b in merges:
+            out, i = [], 0
+            while i < len(word):
+                if i + 1 < len(word) and word[i] == a and word[i + 1] == b:
+                    out.append(a + b); i += 2
+                else:
+                    out.append(word[i]); i += 1
+            word = out
+        s = int(tt.off[k])
+        assert [strs[j] for j in syms[s:s + int(lens[k])]] == word
+        total += 1
+    assert total > 20
+
+
+def test_bpe_train_table_growth_and_ties(P, dev):
+    """Tiny pair table -> several rehashes; heavy ties (every type has freq 1)."""
+    rng = np.random.default_rng(11)
+    alphabet = list("abcdefghijklmnopqrstuvwxyz")
+    words = ["".join(rng.choice(alphabet, size=int(rng.integers(2, 12)))) for _ in range(4000)]
+    tt, l, r, n, c, state, _ = _train_gpu(dev, P, words, 600, record_cap=64, table_cap=1024)
+    ol, orr, on, oc, ovs = _train_oracle(P, words, 600)
+    assert np.array_equal(l, ol) and np.array_equal(r, orr) and np.array_equal(n, on) and np.array_equal(c, oc)
+    assert state["vocab_size"] == ovs
+
+
+def test_bpe_train_long_word_runs(P, dev):
+    words = ["a" * 5000, "ab" * 3000, "a" * 17, "b", "aab" * 1000] * 2 + ["ba" * 7]
+    tt, l, r, n, c, state, _ = _train_gpu(dev, P, words, 40, record_cap=16)
+    ol, orr, on, oc, ovs = _train_oracle(P, words, 40)
+    assert np.array_equal(l, ol) and np.array_equal(r, orr) and np.array_equal(n, on) and np.array_equal(c, oc)
+
+
+# ------------------------------------------------------------------------------------------------ classes
+def test_classes_end_to_end(hf_tokenizer, tmp_path):
+    from subword_tokenizers_b200 import FastBPE, FastWP, NaiveBPE
+    kat = load_golden("kat_tests_resources.json")
+    fb = FastBPE(hf_tokenizer)
+    fb.train(kat["corpus"], kat["max_vocab"])
+    assert fb.merges_list == [tuple(p) for p in kat["FastBPE"]] and len(fb.vocab) == 25
+    assert fb.tokenize(kat["readme_sentence"]) == kat["readme_tokens"]["FastBPE"]
+    assert fb.corpus_as_symbols[0] == (["this"], 1)
+    fb.save_resources(str(tmp_path / "FastBPE"))
+    assert json.load(open(tmp_path / "FastBPE" / "merges.json")) == kat["FastBPE"]
+    fb2 = FastBPE(hf_tokenizer)
+    fb2.load_resources(str(tmp_path / "FastBPE"))
+    assert fb2.tokenize(kat["readme_sentence"]) == kat["readme_tokens"]["FastBPE"]
+    assert fb2.encode_word("") == [""] and fb2.encode_word("x") == ["x"]
+    nb = NaiveBPE(hf_tokenizer)
+    nb.train(kat["corpus"], kat["max_vocab"])
+    assert nb.merges_list == fb.merges_list
+    assert nb.tokenize(kat["readme_sentence"]) == kat["readme_tokens"]["NaiveBPE"]
+    fw = FastWP(hf_tokenizer)
+    with pytest.raises(AttributeError):
+        fw.tokenize("no trie yet")
+    fw.train(kat["corpus"], kat["max_vocab"])
+    assert fw.vocab == set(kat["FastWordPiece"])
+    assert fw.tokenize(kat["readme_sentence"]) == kat["readme_tokens"]["FastWordPiece"]
+    assert fw.tokenize_batch([kat["readme_sentence"], ""]) == [kat["readme_tokens"]["FastWordPiece"], []]
+
+
+# ------------------------------------------------------------------------------------------------ host-buffer ABI
+def test_encode_host_pipeline_matches_device_call(P, dev):
+    import torch
+    rng = np.random.default_rng(3)
+    tab = P.BpeTables([tuple(p) for p in load_golden("pretrained_bpe_merges.json.gz")])
+    wtab, wenc = _wp_encoder(P, dev, load_golden("pretrained_wp_vocab.json.gz"))
+    benc = dev.BpeEncoder(tab)
+    types = load_golden("pan_tadeusz.json.gz")
+    words = [w for l in types for w in l.lower().split()]
+    words = [words[i] for i in rng.integers(0, len(words), size=200_000)] + ["x" * 5000]
+    arena, off = P.pack_words(words)
+    off32 = off.astype(np.uint32)
+    for enc in (benc, wenc):
+        ids, tok_off, h6 = enc.encode_packed(arena, off32)
+        h_arena = torch.from_numpy(arena).pin_memory()
+        h_off = torch.from_numpy(off32.view(np.int32)).pin_memory()
+        h_ids = torch.empty(len(arena) + len(words) + 16, dtype=torch.int32).pin_memory()
+        h_tok = torch.empty(len(words) + 1, dtype=torch.int32).pin_memory()
+        nt, h6b = enc.encode_host(h_arena, h_off, h_ids, h_tok, batch_bytes=1 << 17)    # many small batches
+        assert nt == len(ids) and h6b == h6
+        assert np.array_equal(h_ids.numpy()[:nt].view(np.uint32), ids)
+        assert np.array_equal(h_tok.numpy().view(np.uint32), tok_off)
+
+
+# ------------------------------------------------------------------------------------------------ scale properties
+def test_large_stream_properties(P, dev):
+    """At sizes the oracle cannot replay in seconds: size-independent properties.
+    (1) the token stream of a word stream drawn from a type list equals the gather of the per-type
+    encodings (each word is encoded independently); (2) token offsets are sorted and end at n_tokens;
+    (3) decoding the ids reproduces the input bytes for BPE (tokens concatenate to the word)."""
+    rng = np.random.default_rng(1)
+    tab = P.BpeTables([tuple(p) for p in load_golden("pretrained_bpe_merges.json.gz")])
+    wtab, wenc = _wp_encoder(P, dev, load_golden("pretrained_wp_vocab.json.gz"))
+    benc = dev.BpeEncoder(tab)
+    types = sorted({w for l in load_golden("train-5K.json.gz")[:2000] for w in l.lower().split()})
+    n = 3_000_000
+    zipf = 1.0 / np.arange(1, len(types) + 1)
+    draw = rng.choice(len(types), size=n, p=zipf / zipf.sum())
+    t_arena, t_off = P.pack_words(types)
+    lens = np.diff(t_off.astype(np.int64))
+    w_len = lens[draw]
+    off = np.zeros(n + 1, dtype=np.int64); np.cumsum(w_len, out=off[1:])
+    idx = np.repeat(t_off[:-1].astype(np.int64)[draw] - off[:-1], w_len) + np.arange(off[-1])
+    arena = t_arena[idx]
+    for enc in (benc, wenc):
+        t_ids, t_tok_off, _ = enc.encode_packed(t_arena, t_off.astype(np.uint32))
+        ids, tok_off, _ = enc.encode_packed(arena, off.astype(np.uint32))
+        tl = np.diff(t_tok_off.astype(np.int64))
+        assert np.array_equal(np.diff(tok_off.astype(np.int64)), tl[draw])
+        assert int(tok_off[-1]) == len(ids)
+        gidx = np.repeat(t_tok_off[:-1].astype(np.int64)[draw] - tok_off[:-1].astype(np.int64), tl[draw]) + np.arange(len(ids))
+        assert np.array_equal(ids, t_ids[gidx])
