@@ -1,4 +1,6 @@
 // api.cu -- library-level entry points of libswt: errors, versioning, workspace layout, pinned memory.
+#include <algorithm>
+
 #include "encode.cuh"
 
 namespace swt {
@@ -12,7 +14,13 @@ size_t encode_workspace_layout(uint32_t n_words, uint64_t long_bytes, void *base
     ws->n_tiles = n_tiles;
     ws->tile_state = cv.take<uint64_t>(n_tiles + 1);
     ws->ticket = cv.take<uint32_t>(1);
-    ws->long_cursor = cv.take<uint32_t>(1);
+    ws->long_cursor = cv.take<unsigned long long>(1);
+    // word-type memo: rebuilt from empty by every launch; sized with the batch, at most 2^20 entries (256 MB)
+    uint64_t slots = next_pow2(std::max<uint64_t>(n_words / 4, 1024));
+    slots = std::min<uint64_t>(slots, 1ull << 20);
+    ws->memo = cv.take<MemoEntry>(slots);
+    ws->memo_mask = (uint32_t)(slots - 1);
+    ws->zero_bytes = cv.used();
     ws->long_scratch_elems = 2 * long_bytes;
     ws->long_scratch = cv.take<uint32_t>(ws->long_scratch_elems + 1);
     return cv.used();

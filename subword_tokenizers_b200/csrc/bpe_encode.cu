@@ -4,8 +4,8 @@
 // probe, key = left<<32|right.  Built on the host from the merge list (last rank wins for a pair that
 // is listed twice, bpe.py:200,257) and uploaded once per table.
 //
-// Kernel: see encode.cuh for the tile skeleton.  Per word (one thread, symbols in a shared-memory
-// column): repeat { min rank over the adjacent pairs (bpe.py:212-217); greedy left-to-right
+// Kernel: see encode.cuh for the tile kernel and the word-type memo.  Per directly encoded word (one thread,
+// symbols in a thread-local buffer): repeat { min rank over the adjacent pairs (bpe.py:212-217); greedy left-to-right
 // replacement of every occurrence (:221-235) } until no ranked pair is left or one symbol remains.
 // Words longer than kShortBytes are processed by the whole CTA in global scratch.
 #include <vector>
@@ -60,35 +60,34 @@ __device__ __forceinline__ uint32_t bpe_probe(const BpeTableDev &t, uint32_t a, 
     }
 }
 
-// ---- short words: one thread, symbols in a shared-memory column (stride = kTileWords) ------------------
-__device__ __forceinline__ uint32_t bpe_encode_short(const BpeTableDev &t, const uint8_t *p, uint32_t nbytes,
-                                                     uint32_t *col) {
+// ---- short words: one thread, symbols in a thread-local buffer ----------------------------------------------------
+__device__ __forceinline__ uint32_t bpe_encode_short(const BpeTableDev &t, const uint8_t *p, uint32_t nbytes, uint32_t *s) {
     uint32_t n = 0;
     for (uint32_t i = 0; i < nbytes;) {
         uint32_t adv; uint32_t cp = utf8_decode(p + i, nbytes - i, adv); i += adv;
-        col[n * kTileWords] = bpe_char_symbol(t, cp); ++n;
+        s[n++] = bpe_char_symbol(t, cp);
     }
-    if (n == 0) { col[0] = SWT_BPE_EMPTY_TOKEN; return 1; }       // bpe.py:207-208
+    if (n == 0) { s[0] = SWT_BPE_EMPTY_TOKEN; return 1; }         // bpe.py:207-208
     while (n >= 2) {
         uint32_t best = kEmptyRank, ba = 0, bb = 0, bz = 0;
-        uint32_t prev = col[0];
-        for (uint32_t i = 0; i + 1 < n; ++i) {
-            uint32_t cur = col[(i + 1) * kTileWords], z;
+        uint32_t prev = s[0];
+        for (uint32_t i = 0; i + 1 < n; ++i) {                      // min rank over the adjacent pairs (bpe.py:212-217)
+            uint32_t cur = s[i + 1], z;
             uint32_t r = bpe_probe(t, prev, cur, z);
             if (r < best) { best = r; ba = prev; bb = cur; bz = z; }
             prev = cur;
         }
         if (best == kEmptyRank) break;
-        uint32_t r = 0, o = 0;
+        uint32_t r = 0, o = 0;                                      // greedy left-to-right replacement (bpe.py:221-235)
         while (r < n) {
-            uint32_t s = col[r * kTileWords];
-            if (r + 1 < n && s == ba && col[(r + 1) * kTileWords] == bb) { col[o * kTileWords] = bz; r += 2; }
-            else { col[o * kTileWords] = s; r += 1; }
+            uint32_t v = s[r];
+            if (r + 1 < n && v == ba && s[r + 1] == bb) { s[o] = bz; r += 2; }
+            else { s[o] = v; r += 1; }
             ++o;
         }
         n = o;
     }
-    for (uint32_t k = 0; k < n; ++k) col[k * kTileWords] = (col[k * kTileWords] << 1) | (k > 0);
+    for (uint32_t k = 0; k < n; ++k) s[k] = (s[k] << 1) | (k > 0);   // '##' prefix of symbols[1:] (bpe.py:240-241)
     return n;
 }
 
@@ -154,73 +153,18 @@ __device__ uint32_t bpe_encode_long(const BpeTableDev &t, const uint8_t *p, uint
     return n;
 }
 
-__global__ void __launch_bounds__(kTileWords)
-bpe_encode_kernel(BpeTableDev t, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off,
-                  uint32_t n_words, uint32_t *__restrict__ out_ids, uint64_t out_cap, uint32_t *__restrict__ out_tok_off,
-                  uint32_t tok_base, EncodeWorkspace ws, uint32_t *status) {
-    __shared__ uint32_t stage[kShortBytes * kTileWords];   // 32 KB: token/symbol columns
-    __shared__ uint32_t sh_scan[33];
-    __shared__ uint32_t sh_misc[8];
-    __shared__ uint64_t sh_base;
-    __shared__ uint32_t sh_long_list[kTileWords];
-    __shared__ uint32_t *sh_long_ptr[kTileWords];
-    const uint32_t tid = threadIdx.x;
-    for (;;) {
-        if (tid == 0) { sh_misc[4] = atomicAdd(ws.ticket, 1u); sh_misc[5] = 0; }
-        __syncthreads();
-        const uint32_t tile = sh_misc[4];
-        if (tile >= ws.n_tiles) break;
-        const uint32_t w = tile * kTileWords + tid;
-        const bool valid = w < n_words;
-        uint32_t b0 = 0, nbytes = 0, count = 0;
-        if (valid) { b0 = word_off[w]; nbytes = word_off[w + 1] - b0; }
-        const bool is_long = valid && nbytes > kShortBytes;
-        if (valid && !is_long) count = bpe_encode_short(t, arena + b0, nbytes, stage + tid);
-        if (is_long) sh_long_list[atomicAdd(&sh_misc[5], 1u)] = tid;
-        __syncthreads();
-        const uint32_t n_long = sh_misc[5];
-        __syncthreads();
-        for (uint32_t k = 0; k < n_long; ++k) {                     // CTA-uniform loop
-            const uint32_t owner = sh_long_list[k];
-            const uint32_t lw = tile * kTileWords + owner;
-            const uint32_t lb0 = word_off[lw], lnb = word_off[lw + 1] - lb0;
-            if (tid == 0) sh_misc[6] = atomicAdd(ws.long_cursor, 2u * lnb);
-            __syncthreads();
-            const uint64_t so = sh_misc[6];
-            uint32_t *res = nullptr; uint32_t c = 0;
-            if (so + 2ull * lnb <= ws.long_scratch_elems) {
-                c = bpe_encode_long(t, arena + lb0, lnb, ws.long_scratch + so, ws.long_scratch + so + lnb, &res, sh_scan, sh_misc);
-            } else if (tid == 0) atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY);
-            if (tid == owner) { count = c; sh_long_ptr[owner] = res; }
-            __syncthreads();
-        }
-        uint32_t total, excl = block_exclusive_scan(count, sh_scan, &total);
-        if (tid == 0) sh_base = tile_exclusive_prefix(ws.tile_state, tile, total, &status[kStatusCode]);
-        __syncthreads();
-        const uint64_t pos = sh_base + excl;
-        if (valid) {
-            if (out_tok_off) out_tok_off[w] = tok_base + (uint32_t)pos;
-            if (pos + count <= out_cap) {
-                if (!is_long) { for (uint32_t k = 0; k < count; ++k) out_ids[pos + k] = stage[k * kTileWords + tid]; }
-            } else atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY);
-        }
-        for (uint32_t k = 0; k < n_long; ++k) {                     // long results: coalesced CTA copy
-            const uint32_t owner = sh_long_list[k];
-            __syncthreads();
-            if (tid == owner) { sh_misc[6] = count; sh_misc[7] = excl; }
-            __syncthreads();
-            const uint32_t lc = sh_misc[6]; const uint64_t lpos = sh_base + sh_misc[7];
-            const uint32_t *src = sh_long_ptr[owner];
-            if (src && lpos + lc <= out_cap) for (uint32_t i = tid; i < lc; i += blockDim.x) out_ids[lpos + i] = src[i];
-        }
-        if (tile == ws.n_tiles - 1 && tid == 0) {
-            const uint64_t grand = sh_base + total;
-            if (out_tok_off) out_tok_off[n_words] = tok_base + (uint32_t)grand;
-            status[kStatusTokens] = (uint32_t)grand; status[kStatusTokensHi] = (uint32_t)(grand >> 32);
-        }
-        __syncthreads();
+struct BpeEnc {
+    BpeTableDev t;
+    static constexpr bool kCoopLong = true;
+    __device__ __forceinline__ uint32_t encode_short(const uint8_t *p, uint32_t nbytes, uint32_t *buf, uint32_t &h6) const {
+        (void)h6;
+        return bpe_encode_short(t, p, nbytes, buf);
     }
-}
+    __device__ __forceinline__ uint32_t encode_long_coop(const uint8_t *p, uint32_t nbytes, uint32_t *bufA, uint32_t *bufB,
+                                                         uint32_t **result, uint32_t *sh_scan, uint32_t *sh_misc) const {
+        return bpe_encode_long(t, p, nbytes, bufA, bufB, result, sh_scan, sh_misc);
+    }
+};
 
 }  // namespace swt
 
@@ -289,29 +233,13 @@ int encode_grid(const void *kernel, int block) {
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return sms * per_sm;
 }
-}  // namespace swt
 
-namespace swt {
 int bpe_encode_launch(const swt_bpe_table *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
                       uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off, uint32_t tok_base,
                       void *d_workspace, size_t workspace_bytes, uint32_t *d_status, cudaStream_t st) {
-    SWT_REQUIRE(t && d_word_off && d_status && d_workspace, "NULL argument");
-    SWT_REQUIRE(n_words == 0 || (d_arena && d_out_ids), "NULL data pointer");
-    EncodeWorkspace ws;
-    size_t need = encode_workspace_layout(n_words, long_word_bytes, d_workspace, &ws);
-    if (need > workspace_bytes) { set_error("encode workspace too small"); return SWT_ERR_CAPACITY; }
-    SWT_CUDA_OK(cudaMemsetAsync(d_workspace, 0, (uint8_t *)ws.long_scratch - (uint8_t *)d_workspace, st));
-    SWT_CUDA_OK(cudaMemsetAsync(d_status, 0, 8 * sizeof(uint32_t), st));
-    if (n_words == 0) {
-        if (d_out_tok_off) SWT_CUDA_OK(cudaMemcpyAsync(d_out_tok_off, &tok_base, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        return SWT_OK;
-    }
-    static int grid = 0;
-    if (!grid) grid = encode_grid((const void *)bpe_encode_kernel, kTileWords);
-    int g = (int)std::min<uint64_t>((uint64_t)grid, ws.n_tiles);
-    bpe_encode_kernel<<<g, kTileWords, 0, st>>>(t->dev, d_arena, d_word_off, n_words, d_out_ids, out_cap, d_out_tok_off, tok_base, ws, d_status);
-    SWT_CUDA_OK(cudaGetLastError());
-    return SWT_OK;
+    SWT_REQUIRE(t != nullptr, "NULL table");
+    return launch_encode_tiles(BpeEnc{t->dev}, d_arena, d_word_off, n_words, long_word_bytes, d_out_ids, out_cap, d_out_tok_off,
+                               tok_base, d_workspace, workspace_bytes, d_status, st);
 }
 }  // namespace swt
 

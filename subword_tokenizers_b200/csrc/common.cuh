@@ -74,6 +74,15 @@ __device__ __forceinline__ uint32_t utf8_decode(const uint8_t *p, uint32_t avail
 constexpr uint64_t kTileInvalid = 0ull, kTileAggregate = 1ull, kTilePrefix = 2ull;
 constexpr uint64_t kTileValueMask = (1ull << 62) - 1;
 
+// tile states carry status and value in ONE 64-bit word, so relaxed (L2-served) accesses are enough
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t *p) {
     uint64_t v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

@@ -10,8 +10,8 @@
 //   alnum        Python str.isalnum bitmap (wordpiece.py:287-288, utils.py:137)
 // all small enough to stay L2/L1 resident (about 3 MB for a 20K vocabulary).
 //
-// Device side: one thread walks one whitespace-free chunk (goto + failure transitions), tokens staged
-// in a shared-memory column; chunks longer than kShortBytes are walked twice (count, then write).
+// Device side (tile kernel and word-type memo: encode.cuh): one thread walks one whitespace-free chunk (goto +
+// failure transitions); chunks longer than kShortBytes are walked twice (count, then write).
 #include <algorithm>
 #include <deque>
 #include <unordered_map>
@@ -60,19 +60,13 @@ __device__ __forceinline__ bool wp_alnum(const WpTrieDev &t, uint32_t cp) {
     return cp < 0x110000u && ((__ldg(&t.alnum[cp >> 5]) >> (cp & 31u)) & 1u);
 }
 
-struct CountEmit {                       // first pass over a long chunk
+struct CountEmit {                       // counting pass over a long chunk
     uint32_t n = 0;
     __device__ __forceinline__ void push(uint32_t) { ++n; }
     __device__ __forceinline__ uint32_t size() const { return n; }
     __device__ __forceinline__ void truncate(uint32_t k) { n = k; }
 };
-struct ColumnEmit {                      // shared-memory column, stride kTileWords
-    uint32_t *col; uint32_t n = 0;
-    __device__ __forceinline__ void push(uint32_t tok) { if (n < (uint32_t)kShortBytes) col[n * kTileWords] = tok; ++n; }
-    __device__ __forceinline__ uint32_t size() const { return n; }
-    __device__ __forceinline__ void truncate(uint32_t k) { n = k; }
-};
-struct GlobalEmit {                      // second pass over a long chunk: final position is known
+struct ArrayEmit {                       // ids into a buffer of `cap` entries (thread-local, shared or global)
     uint32_t *out; uint32_t cap; uint32_t n = 0;
     __device__ __forceinline__ void push(uint32_t tok) { if (n < cap) out[n] = tok; ++n; }
     __device__ __forceinline__ uint32_t size() const { return n; }
@@ -125,48 +119,25 @@ __device__ __forceinline__ void wp_encode_chunk(const WpTrieDev &t, const uint8_
     }
 }
 
-__global__ void __launch_bounds__(kTileWords)
-wp_encode_kernel(WpTrieDev t, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words,
-                 uint32_t *__restrict__ out_ids, uint64_t out_cap, uint32_t *__restrict__ out_tok_off, uint32_t tok_base,
-                 EncodeWorkspace ws, uint32_t *status) {
-    __shared__ uint32_t stage[kShortBytes * kTileWords];
-    __shared__ uint32_t sh_scan[33];
-    __shared__ uint32_t sh_tile;
-    __shared__ uint64_t sh_base;
-    const uint32_t tid = threadIdx.x;
-    uint32_t h6 = 0;
-    for (;;) {
-        if (tid == 0) sh_tile = atomicAdd(ws.ticket, 1u);
-        __syncthreads();
-        const uint32_t tile = sh_tile;
-        if (tile >= ws.n_tiles) break;
-        const uint32_t w = tile * kTileWords + tid;
-        const bool valid = w < n_words;
-        uint32_t b0 = 0, nbytes = 0, count = 0;
-        if (valid) { b0 = word_off[w]; nbytes = word_off[w + 1] - b0; }
-        const bool is_long = valid && nbytes > kShortBytes;
-        if (valid && !is_long) { ColumnEmit e{stage + tid}; wp_encode_chunk(t, arena + b0, nbytes, e, h6); count = e.n; }
-        else if (is_long) { CountEmit e; uint32_t dummy = 0; wp_encode_chunk(t, arena + b0, nbytes, e, dummy); count = e.n; }
-        uint32_t total, excl = block_exclusive_scan(count, sh_scan, &total);
-        if (tid == 0) sh_base = tile_exclusive_prefix(ws.tile_state, tile, total, &status[kStatusCode]);
-        __syncthreads();
-        const uint64_t pos = sh_base + excl;
-        if (valid) {
-            if (out_tok_off) out_tok_off[w] = tok_base + (uint32_t)pos;
-            if (pos + count <= out_cap) {
-                if (!is_long) { for (uint32_t k = 0; k < count; ++k) out_ids[pos + k] = stage[k * kTileWords + tid]; }
-                else { GlobalEmit e{out_ids + pos, count}; wp_encode_chunk(t, arena + b0, nbytes, e, h6); }
-            } else atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY);
-        }
-        if (tile == ws.n_tiles - 1 && tid == 0) {
-            const uint64_t grand = sh_base + total;
-            if (out_tok_off) out_tok_off[n_words] = tok_base + (uint32_t)grand;
-            status[kStatusTokens] = (uint32_t)grand; status[kStatusTokensHi] = (uint32_t)(grand >> 32);
-        }
-        __syncthreads();
+struct WpEnc {
+    WpTrieDev t;
+    static constexpr bool kCoopLong = false;
+    __device__ __forceinline__ uint32_t encode_short(const uint8_t *p, uint32_t nbytes, uint32_t *buf, uint32_t &h6) const {
+        ArrayEmit e{buf, (uint32_t)kShortBytes};
+        wp_encode_chunk(t, p, nbytes, e, h6);
+        return e.n;
     }
-    if (h6) atomicAdd(&status[kStatusH6], h6);
-}
+    // chunks longer than kShortBytes are walked twice: count, then write at the final position
+    __device__ __forceinline__ uint32_t long_count(const uint8_t *p, uint32_t nbytes) const {
+        CountEmit e; uint32_t dummy = 0;
+        wp_encode_chunk(t, p, nbytes, e, dummy);
+        return e.n;
+    }
+    __device__ __forceinline__ void long_emit(const uint8_t *p, uint32_t nbytes, uint32_t *dst, uint32_t cap, uint32_t &h6) const {
+        ArrayEmit e{dst, cap};
+        wp_encode_chunk(t, p, nbytes, e, h6);
+    }
+};
 
 // ---- host: trie construction + precompute ---------------------------------------------------------------
 struct HostTrie {
@@ -313,29 +284,13 @@ SWT_API int swt_wp_trie_stats(const swt_wp_trie *t, uint64_t *n_nodes, uint64_t 
     return SWT_OK;
 }
 
-namespace swt { int encode_grid(const void *kernel, int block); }
-
 namespace swt {
 int wp_encode_launch(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
                      uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off, uint32_t tok_base,
                      void *d_workspace, size_t workspace_bytes, uint32_t *d_status, cudaStream_t st) {
-    SWT_REQUIRE(t && d_word_off && d_status && d_workspace, "NULL argument");
-    SWT_REQUIRE(n_words == 0 || (d_arena && d_out_ids), "NULL data pointer");
-    EncodeWorkspace ws;
-    size_t need = encode_workspace_layout(n_words, 0, d_workspace, &ws);
-    if (need > workspace_bytes) { set_error("encode workspace too small"); return SWT_ERR_CAPACITY; }
-    SWT_CUDA_OK(cudaMemsetAsync(d_workspace, 0, need, st));
-    SWT_CUDA_OK(cudaMemsetAsync(d_status, 0, 8 * sizeof(uint32_t), st));
-    if (n_words == 0) {
-        if (d_out_tok_off) SWT_CUDA_OK(cudaMemcpyAsync(d_out_tok_off, &tok_base, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        return SWT_OK;
-    }
-    static int grid = 0;
-    if (!grid) grid = encode_grid((const void *)wp_encode_kernel, kTileWords);
-    int g = (int)std::min<uint64_t>((uint64_t)grid, ws.n_tiles);
-    wp_encode_kernel<<<g, kTileWords, 0, st>>>(t->dev, d_arena, d_word_off, n_words, d_out_ids, out_cap, d_out_tok_off, tok_base, ws, d_status);
-    SWT_CUDA_OK(cudaGetLastError());
-    return SWT_OK;
+    SWT_REQUIRE(t != nullptr, "NULL trie");
+    return launch_encode_tiles(WpEnc{t->dev}, d_arena, d_word_off, n_words, 0, d_out_ids, out_cap, d_out_tok_off, tok_base,
+                               d_workspace, workspace_bytes, d_status, st);
 }
 }  // namespace swt
 

@@ -1,0 +1,121 @@
+"""Host-side logic that needs no GPU: packing, the Naive* host classes against the reference's golden
+outputs, error behaviour and the on-disk layout."""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from subword_tokenizers_b200 import FastBPE, FastWP, NaiveBPE, NaiveWP, packing as P
+from subword_tokenizers_b200.device import shard_types
+
+
+def test_pack_words_roundtrip():
+    words = ["", "zażółć", "a", "\U0001F600x", "ab" * 40]
+    arena, off = P.pack_words(words)
+    assert off[0] == 0 and off[-1] == len(arena)
+    back = [P.decode_utf8(arena[int(off[i]):int(off[i + 1])].tobytes()) for i in range(len(words))]
+    assert back == words
+
+
+def test_bpe_tables_canonical_ids_and_last_rank():
+    tab = P.BpeTables([("a", "b"), ("ab", "c"), ("a", "bc"), ("a", "b")])
+    assert tab.id_to_str[tab.new[1]] == "abc" and tab.new[1] == tab.new[2]        # one id per distinct string (H3)
+    assert tab.new[0] == tab.new[3]
+    assert tab.token_to_str(P.BPE_EMPTY_TOKEN) == ""
+    assert tab.token_to_str(((P.BPE_UNKNOWN_CP | ord("ż")) << 1) | 1) == "##ż"
+
+
+def test_unicode_class_bitmaps_match_python():
+    alnum, space = P.unicode_class_bitmaps()
+    for cp in list(range(0, 0x300)) + [0x1C, 0x1F, 0x85, 0xA0, 0x2028, 0x3000, 0x20AC, 0x1F600, 0x10FFFF]:
+        ch = chr(cp)
+        assert bool((alnum[cp >> 3] >> (cp & 7)) & 1) == ch.isalnum()
+        assert bool((space[cp >> 3] >> (cp & 7)) & 1) == ch.isspace()
+
+
+def test_train_types_first_occurrence_order():
+    tt = P.TrainTypes(["b", "a", "b", "ca", "a", "b"])
+    assert tt.types == ["b", "a", "ca"] and tt.freq.tolist() == [3, 2, 1]
+    assert tt.alphabet == ["a", "b", "c"] and tt.syms.tolist() == [1, 0, 2, 0] and tt.off.tolist() == [0, 1, 2, 4]
+    merges, strs = tt.merges_to_strs(np.array([2]), np.array([0]), np.array([3]))
+    assert merges == [("c", "a")] and strs[3] == "ca"
+
+
+def test_shard_types_contiguous_and_complete():
+    off = np.array([0, 5, 6, 20, 21, 22, 40], dtype=np.uint64)
+    for world in (1, 2, 3, 4, 8):
+        shards = shard_types(off, world)
+        assert shards[0][0] == 0 and shards[-1][1] == 6
+        assert all(shards[i][1] == shards[i + 1][0] for i in range(world - 1))
+
+
+def test_type_errors_match_reference_messages(hf_tokenizer):
+    for cls in (NaiveBPE, FastBPE):
+        t = cls(hf_tokenizer)
+        with pytest.raises(TypeError, match="Corpus must be a list of strings."):
+            t.train("not a list", 10)
+        with pytest.raises(TypeError, match="Maximum vocabulary size must be an integer."):
+            t.train(["a"], 10.5)
+        with pytest.raises(TypeError):
+            t.tokenize(3)
+    for cls in (NaiveWP, FastWP):
+        t = cls(hf_tokenizer)
+        with pytest.raises(TypeError, match="corpus must be a list of strings."):
+            t.train(["a", 3], 10)
+        with pytest.raises(TypeError, match="max_vocab must be an int."):
+            t.train(["a"], "10")
+        with pytest.raises(TypeError):
+            t.tokenize(None)
+    with pytest.raises(AttributeError):
+        FastWP(hf_tokenizer).tokenize("trie not built yet")
+
+
+def test_resources_layout_and_missing_file(hf_tokenizer, tmp_path):
+    nb = NaiveBPE(hf_tokenizer)
+    nb.merges_list = [("a", "ł"), ("ał", "b")]
+    nb.save_resources(str(tmp_path / "NaiveBPE"))
+    raw = open(tmp_path / "NaiveBPE" / "merges.json", encoding="utf-8").read()
+    assert raw == '[["a", "ł"], ["ał", "b"]]'                       # json.dump(..., ensure_ascii=False), no indent
+    nb2 = NaiveBPE(hf_tokenizer)
+    nb2.load_resources(str(tmp_path / "NaiveBPE"))
+    assert nb2.merges_list == [("a", "ł"), ("ał", "b")]
+    nb2.load_resources(str(tmp_path / "does-not-exist"))             # silently ignored
+    assert nb2.merges_list == [("a", "ł"), ("ał", "b")]
+    nw = NaiveWP(hf_tokenizer)
+    nw.vocab = {"a", "##b", "ł"}
+    nw.save_resources(str(tmp_path / "NaiveWordPiece"))
+    assert sorted(json.load(open(tmp_path / "NaiveWordPiece" / "vocab.json", encoding="utf-8"))) == ["##b", "a", "ł"]
+    nw2 = NaiveWP(hf_tokenizer)
+    nw2.load_resources(str(tmp_path / "NaiveWordPiece"))
+    assert nw2.vocab == {"a", "##b", "ł"}
+
+
+def test_naive_bpe_host_encoder_matches_reference(hf_tokenizer, random_cases):
+    nb = NaiveBPE(hf_tokenizer)
+    for case in random_cases["bpe_encode"]:
+        nb.merges_list = [tuple(p) for p in case["merges"]]
+        assert [nb.encode_word(w) for w in case["words"]] == case["naive"]
+    gold = load_golden("pan_tadeusz.tokens.json.gz")["NaiveBPE"]
+    nb.merges_list = [tuple(p) for p in load_golden("pretrained_bpe_merges.json.gz")]
+    lines = load_golden("pan_tadeusz.json.gz")
+    assert [nb.tokenize(l) for l in lines[:3]] == gold[:3]
+    assert nb.encode_word("") == []
+
+
+def test_naive_wp_host_class_matches_reference(hf_tokenizer, random_cases):
+    nw = NaiveWP(hf_tokenizer)
+    for case in random_cases["wp_train"]:
+        nw.train(case["corpus"], case["max_vocab"])
+        assert sorted(nw.vocab) == case["vocab"]
+    for case in random_cases["wp_encode"]:
+        nw.vocab = set(case["vocab"])
+        for text, naive in zip(case["texts"], case["naive"]):
+            if naive is not None:
+                assert nw.tokenize(text) == naive
+    nw.vocab = set(load_golden("pretrained_wp_vocab.json.gz"))
+    lines = load_golden("pan_tadeusz.json.gz")
+    assert [nw.tokenize(l) for l in lines] == load_golden("pan_tadeusz.tokens.json.gz")["NaiveWordPiece"]
+    kat = load_golden("kat_tests_resources.json")
+    nw.train(kat["corpus"], kat["max_vocab"])
+    assert nw.vocab == set(kat["NaiveWordPiece"])
