@@ -226,9 +226,9 @@ SWT_API void swt_bpe_table_destroy(swt_bpe_table *t) {
 }
 
 namespace swt {
-int encode_grid(const void *kernel, int block) {
+int encode_grid(const void *kernel, int block, size_t dyn_smem) {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     int dev = 0, sms = kNumSMs;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return sms * per_sm;

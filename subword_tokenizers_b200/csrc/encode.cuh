@@ -10,8 +10,8 @@
 //   phase B  per word: copy the ids (memo entry -> shared memory) at their tile-local position
 //   store    the tile's ids leave shared memory with fully coalesced writes; u32 token offsets go out as 16 B stores
 //
-// Tiles are handed out by an atomic ticket so the grid is persistent
-// (kNumSMs x resident CTAs) and the look-back never waits on a CTA that has not started.
+// The grid is persistent (kNumSMs x resident CTAs); tiles are handed out by an atomic ticket, so the look-back
+// never waits on a tile that has not started.
 //
 // Word-type memo: encode_word is a pure function of the word and word streams are
 // Zipf-distributed, so every launch keeps a hash table  word bytes -> token ids  in its workspace.  The first
@@ -34,22 +34,20 @@ constexpr int kWordsPerThread = 4;
 constexpr int kTileWords = kThreads * kWordsPerThread;   // 1024 words per tile
 constexpr int kShortBytes = 32;        // words up to this many bytes are encoded by one thread (and memoised)
 constexpr int kCompactTokens = 8192;   // tile token totals up to this are assembled in smem before the store
-constexpr int kMemoTokens = 52;        // >= kShortBytes: every word of up to 32 bytes fits (ids <= bytes)
+constexpr int kMemoTokens = 54;        // >= kShortBytes: every word of up to 32 bytes fits (ids <= bytes)
 constexpr int kMemoProbes = 8;
 
 // status words written by the encode kernels
 enum { kStatusCode = 0, kStatusTokens = 1, kStatusH6 = 2, kStatusTokensHi = 3, kStatusMemoTypes = 4 };
 
-struct alignas(256) MemoEntry {         // 256 bytes; a typical hit touches the first 64-96 bytes only
+struct alignas(256) MemoEntry {         // 256 bytes; a typical hit touches the first 32-96 bytes only
     unsigned long long lo, hi;          // CAS key: word bytes 0..7 | bytes 8..14 + (length << 56); 0/0 == empty
-    unsigned long long tail_a, tail_b;  // bytes 15..22 | 23..30 (words longer than 15 bytes; verified after the key)
     uint32_t meta;                      // 0 = claimed, not published; else (n_tokens + 1) | (h6 << 8); ~0 = not cacheable
     uint32_t tail_last;                 // byte 31
-    uint32_t pad[2];
-    uint32_t tok[kMemoTokens];          // at byte 48
+    uint32_t tok01[2];                  // ids 0 and 1: a word of up to two ids is served by the first 32-byte sector
+    unsigned long long tail_a, tail_b;  // bytes 15..22 | 23..30 (words longer than 15 bytes; verified after the key)
+    uint32_t tok[kMemoTokens - 2];      // ids 2.. at byte 48
 };
-static_assert(sizeof(MemoEntry) == 256, "MemoEntry must be 256 bytes");
-
 struct MemoKey { unsigned long long lo, hi, tail_a, tail_b; uint32_t tail_last; uint32_t nbytes; };
 
 struct EncodeWorkspace {
@@ -64,7 +62,7 @@ struct EncodeWorkspace {
 };
 
 size_t encode_workspace_layout(uint32_t n_words, uint64_t long_bytes, void *base, EncodeWorkspace *ws);
-int encode_grid(const void *kernel, int block);
+int encode_grid(const void *kernel, int block, size_t dyn_smem);
 
 #ifdef __CUDACC__
 enum { kMemoHit = 0, kMemoClaimed = 1, kMemoMiss = 2 };
@@ -132,43 +130,32 @@ __device__ __forceinline__ void memo_key(const uint8_t *arena, uint32_t b0, uint
     k.nbytes = nbytes;
 }
 
-// Probes the memo.  kMemoHit: slot/meta describe a published entry for exactly this word.  kMemoClaimed: this
-// thread now owns `slot` and must call memo_publish after encoding.  kMemoMiss: encode directly, publish nothing.
-__device__ __forceinline__ int memo_probe(const EncodeWorkspace &ws, const MemoKey &key, uint32_t &slot, uint32_t &meta_out) {
+// Probes the memo.  kMemoHit: slot/meta describe a published entry for exactly this word, t01 holds its first two
+// ids.  kMemoClaimed: this thread now owns `slot` and must call memo_publish after encoding.  kMemoMiss: encode
+// directly, publish nothing.  `first` is the probe index to start from (the caller may have checked probe 0 itself).
+static __device__ __noinline__ int memo_probe(const EncodeWorkspace &ws, const MemoKey &key, uint32_t &slot, uint32_t &meta_out, uint2 &t01) {
     uint32_t h = (uint32_t)mix64(key.lo ^ (key.hi * 0x9E3779B97F4A7C15ull)) & ws.memo_mask;
     for (int probe = 0; probe < kMemoProbes; ++probe, h = (h + 1) & ws.memo_mask) {
         MemoEntry *e = ws.memo + h;
         unsigned long long klo, khi;
         ld_cg_u64x2(e, klo, khi);
-        uint32_t meta = ld_relaxed_u32(&e->meta);                        // issued together with the key load
+        uint4 m = ld_cg_u32x4(&e->meta);                                 // meta, tail_last, id0, id1 (same sector as the key)
         if (klo == 0 && khi == 0) {
             cas128(e, key.lo, key.hi, klo, khi);
             if (klo == 0 && khi == 0) { slot = h; return kMemoClaimed; }
-            meta = 0;                                                    // lost the race: the winner has not published yet
+            m.x = 0;                                                     // lost the race: the winner has not published yet
         }
         if (klo != key.lo || khi != key.hi) continue;
-        if (meta == 0 || meta == 0xFFFFFFFFu) return kMemoMiss;          // not published yet / not cacheable
+        if (m.x == 0 || m.x == 0xFFFFFFFFu) return kMemoMiss;            // not published yet / not cacheable
         if (key.nbytes > 15) {                                           // same 15-byte prefix and length: check the rest
             unsigned long long ta, tb;
             ld_cg_u64x2(&e->tail_a, ta, tb);
-            const uint4 m = ld_cg_u32x4(&e->meta);
             if (ta != key.tail_a || tb != key.tail_b || m.y != key.tail_last) continue;
         }
-        slot = h; meta_out = meta;
+        slot = h; meta_out = m.x; t01 = make_uint2(m.z, m.w);
         return kMemoHit;
     }
     return kMemoMiss;
-}
-// copies the ids of a published entry to dst[0..ntok)
-__device__ __forceinline__ void memo_copy(const EncodeWorkspace &ws, uint32_t slot, uint32_t ntok, uint32_t *dst) {
-    const MemoEntry *e = ws.memo + slot;
-    for (uint32_t k0 = 0; k0 < ntok; k0 += 4) {
-        const uint4 v = ld_cg_u32x4(&e->tok[k0]);
-        dst[k0] = v.x;
-        if (k0 + 1 < ntok) dst[k0 + 1] = v.y;
-        if (k0 + 2 < ntok) dst[k0 + 2] = v.z;
-        if (k0 + 3 < ntok) dst[k0 + 3] = v.w;
-    }
 }
 // returns true when the entry now holds the ids (false: too many ids, marked not cacheable)
 __device__ __forceinline__ bool memo_publish(const EncodeWorkspace &ws, uint32_t slot, const MemoKey &key, const uint32_t *buf,
@@ -176,7 +163,8 @@ __device__ __forceinline__ bool memo_publish(const EncodeWorkspace &ws, uint32_t
     MemoEntry *e = ws.memo + slot;
     if (ntok > (uint32_t)kMemoTokens || h6 > 0xFFFFFFu) { st_release_u32(&e->meta, 0xFFFFFFFFu); return false; }
     e->tail_a = key.tail_a; e->tail_b = key.tail_b; e->tail_last = key.tail_last;
-    for (uint32_t k = 0; k < ntok; ++k) e->tok[k] = buf[k];
+    e->tok01[0] = ntok > 0 ? buf[0] : 0u; e->tok01[1] = ntok > 1 ? buf[1] : 0u;
+    for (uint32_t k = 2; k < ntok; ++k) e->tok[k - 2] = buf[k];
     st_release_u32(&e->meta, (ntok + 1) | (h6 << 8));
     atomicAdd(&status[kStatusMemoTypes], 1u);
     return true;
@@ -222,6 +210,48 @@ __device__ __forceinline__ uint64_t tile_prefix_warp(uint64_t *tile_state, uint3
 // per-word bookkeeping between phase A and phase B
 enum : uint32_t { kWordNone = 0u, kWordHit = 1u, kWordRecompute = 2u, kWordLong = 3u, kWordLongB = 4u };
 
+struct TileSmem {                         // dynamic shared memory of the tile kernel (37 KB)
+    uint32_t compact[kCompactTokens];     // the tile's ids in output order
+    uint32_t off[kTileWords + 4];         // the tile's word offsets
+    uint32_t scan[36];
+    uint32_t misc[8];
+    uint64_t base;
+};
+
+// phase A slow path (first probe did not hit): full probe, then direct encode + publish.  Kept out of line so
+// that the 4x unrolled fast path stays small.
+struct SlowResult { uint32_t kind, ntok, slot, h6; uint2 t01; };
+template <class Enc>
+__device__ __noinline__ SlowResult resolve_slow(const Enc &enc, const EncodeWorkspace &ws, const uint8_t *arena, uint32_t b0,
+                                                uint32_t nbytes, uint32_t arena_end, uint32_t *buf, uint32_t *status) {
+    SlowResult r; r.kind = kWordRecompute; r.ntok = 0; r.slot = 0; r.h6 = 0; r.t01 = make_uint2(0, 0);
+    int m = kMemoMiss; uint32_t meta = 0; MemoKey key;
+    if (ws.memo_mask && nbytes >= 1) { memo_key(arena, b0, nbytes, arena_end, key); m = memo_probe(ws, key, r.slot, meta, r.t01); }
+    if (m == kMemoHit) { r.kind = kWordHit; r.ntok = (meta & 0xFFu) - 1; r.h6 = meta >> 8; return r; }
+    r.ntok = enc.encode_short(arena + b0, nbytes, buf, r.h6);
+    if (m == kMemoClaimed && memo_publish(ws, r.slot, key, buf, r.ntok, r.h6, status)) {
+        r.kind = kWordHit; r.t01 = make_uint2(r.ntok > 0 ? buf[0] : 0u, r.ntok > 1 ? buf[1] : 0u);
+    }
+    return r;
+}
+// phase B slow paths: re-encode a word whose ids were not kept, or emit a long word
+template <class Enc>
+__device__ __noinline__ uint32_t emit_slow(const Enc &enc, const EncodeWorkspace &ws, const uint8_t *word, uint32_t nbytes,
+                                           uint32_t kind, uint32_t ntok, uint32_t slot, uint32_t *buf, uint32_t *dst) {
+    uint32_t h6 = 0;
+    if (kind == kWordRecompute) {
+        uint32_t dummy = 0;
+        const uint32_t n = enc.encode_short(word, nbytes, buf, dummy);
+        for (uint32_t k = 0; k < n; ++k) dst[k] = buf[k];
+    } else if constexpr (!Enc::kCoopLong) {
+        enc.long_emit(word, nbytes, dst, ntok, h6);
+    } else {
+        const uint32_t *src = ws.long_scratch + ((unsigned long long)slot << 1) + (kind == kWordLongB ? nbytes : 0u);
+        for (uint32_t k = 0; k < ntok; ++k) dst[k] = src[k];
+    }
+    return h6;
+}
+
 // ---- the tile kernel ---------------------------------------------------------------------------------------------------
 // Enc provides
 //   uint32_t encode_short(const uint8_t *p, uint32_t nbytes, uint32_t *buf /*thread-local, kShortBytes*/, uint32_t &h6) const
@@ -229,55 +259,92 @@ enum : uint32_t { kWordNone = 0u, kWordHit = 1u, kWordRecompute = 2u, kWordLong 
 //   kCoopLong == false:  uint32_t long_count(p, nbytes) const;  void long_emit(p, nbytes, uint32_t *dst, uint32_t cap, uint32_t &h6) const
 //   kCoopLong == true :  uint32_t encode_long_coop(p, nbytes, bufA, bufB, uint32_t **result, uint32_t *sh_scan, uint32_t *sh_misc) const
 template <class Enc>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 encode_tiles_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words,
                     uint32_t *__restrict__ out_ids, uint64_t out_cap, uint32_t *__restrict__ out_tok_off, uint32_t tok_base,
                     EncodeWorkspace ws, uint32_t *status) {
-    __shared__ uint32_t compact[kCompactTokens];            // 32 KB: the tile's ids in output order
-    __shared__ uint32_t s_off[kTileWords + 1];              // the tile's word offsets
-    __shared__ uint32_t sh_scan[33];
-    __shared__ uint32_t sh_misc[8];
-    __shared__ uint64_t sh_base;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x;
     const uint32_t arena_end = word_off[n_words];
     const bool tok_off_vec = out_tok_off && (((uintptr_t)out_tok_off & 15) == 0);
+    const bool use_memo = ws.memo_mask != 0;
     uint32_t h6 = 0;
-    uint32_t next_ticket = 0;
-    if (tid == 0) next_ticket = atomicAdd(ws.ticket, 1u);
     uint32_t buf[kShortBytes];                              // thread-local scratch for one directly encoded word
 
+    // Tiles are handed out by an atomic ticket: a tile only starts once a CTA is free to run it, so every predecessor
+    // of a running tile is itself running or finished and the look-back cannot deadlock.
+    uint32_t next_ticket = 0;
+    if (tid == 0) next_ticket = atomicAdd(ws.ticket, 1u);
     for (;;) {
-        if (tid == 0) sh_misc[4] = next_ticket;
+        if (tid == 0) sm.misc[4] = next_ticket;
         __syncthreads();
-        const uint32_t tile = sh_misc[4];
+        const uint32_t tile = sm.misc[4];
         if (tile >= ws.n_tiles) break;
         const uint32_t w_tile = tile * kTileWords;
         const uint32_t tile_words = min((uint32_t)kTileWords, n_words - w_tile);
-        for (uint32_t i = tid; i <= tile_words; i += kThreads) s_off[i] = word_off[w_tile + i];
+        for (uint32_t i = tid; i <= tile_words; i += kThreads) sm.off[i] = word_off[w_tile + i];
         __syncthreads();
 
-        // ---- phase A: counts
+        // ---- phase A: counts.  Fast path = first memo probe hits; everything else goes through resolve_slow.
         uint32_t kind[kWordsPerThread], ntok[kWordsPerThread], slot[kWordsPerThread];
+        uint2 t01[kWordsPerThread];
+        unsigned long long klo[kWordsPerThread], khi[kWordsPerThread];      // word key, then (after the xor) key difference
+        uint32_t nb[kWordsPerThread], b0s[kWordsPerThread];
+        uint4 mt[kWordsPerThread];
         uint32_t count = 0; bool has_long = false;
 #pragma unroll
         for (int j = 0; j < kWordsPerThread; ++j) {
             const uint32_t i = tid * kWordsPerThread + j;
-            kind[j] = kWordNone; ntok[j] = 0; slot[j] = 0;
-            if (i >= tile_words) continue;
-            const uint32_t b0 = s_off[i], nbytes = s_off[i + 1] - b0;
-            if (nbytes > (uint32_t)kShortBytes) {
-                kind[j] = kWordLong; has_long = true;
-                if constexpr (!Enc::kCoopLong) ntok[j] = enc.long_count(arena + b0, nbytes);
-            } else {
-                int m = kMemoMiss; uint32_t meta = 0; MemoKey key;
-                if (ws.memo_mask && nbytes >= 1) { memo_key(arena, b0, nbytes, arena_end, key); m = memo_probe(ws, key, slot[j], meta); }
-                if (m == kMemoHit) { kind[j] = kWordHit; ntok[j] = (meta & 0xFFu) - 1; h6 += meta >> 8; }
-                else {
-                    uint32_t my_h6 = 0;
-                    ntok[j] = enc.encode_short(arena + b0, nbytes, buf, my_h6);
-                    h6 += my_h6;
-                    kind[j] = (m == kMemoClaimed && memo_publish(ws, slot[j], key, buf, ntok[j], my_h6, status)) ? kWordHit : kWordRecompute;
+            kind[j] = kWordNone; ntok[j] = 0; slot[j] = 0; t01[j] = make_uint2(0, 0);
+            b0s[j] = i < tile_words ? sm.off[i] : 0u;
+            nb[j] = i < tile_words ? sm.off[i + 1] - b0s[j] : 0xFFFFFFFFu;          // 0xFFFFFFFF: no word
+            klo[j] = khi[j] = ~0ull; mt[j] = make_uint4(0, 0, 0, 0);
+        }
+        if (use_memo) {
+            // words of 1..15 bytes: request the (up to three) aligned 8-byte words of all four words, then the first memo
+            // probe of all four, before looking at any result
+            unsigned long long r0[kWordsPerThread], r1[kWordsPerThread], r2[kWordsPerThread];
+            bool fastj[kWordsPerThread];
+#pragma unroll
+            for (int j = 0; j < kWordsPerThread; ++j) {
+                fastj[j] = nb[j] >= 1 && nb[j] <= 15 && (uint64_t)b0s[j] + 24 <= arena_end;
+                r0[j] = r1[j] = r2[j] = 0;
+                if (fastj[j]) {
+                    const uintptr_t a = (uintptr_t)(arena + b0s[j]);
+                    const unsigned long long *q = (const unsigned long long *)(a & ~(uintptr_t)7);
+                    r0[j] = __ldg(q); r1[j] = __ldg(q + 1);
+                    if (nb[j] + (uint32_t)(a & 7) > 16) r2[j] = __ldg(q + 2);
                 }
+            }
+#pragma unroll
+            for (int j = 0; j < kWordsPerThread; ++j) {
+                if (fastj[j]) {
+                    const uint32_t sh = (uint32_t)((uintptr_t)(arena + b0s[j]) & 7) * 8;
+                    unsigned long long lo = r0[j], hi = r1[j], elo, ehi;
+                    if (sh) { lo = (r0[j] >> sh) | (r1[j] << (64 - sh)); hi = (r1[j] >> sh) | (r2[j] << (64 - sh)); }
+                    if (nb[j] < 8) { lo &= (1ull << (8 * nb[j])) - 1; hi = 0; }
+                    else hi = nb[j] == 8 ? 0ull : hi & ((1ull << (8 * (nb[j] - 8))) - 1);
+                    hi |= (unsigned long long)nb[j] << 56;
+                    slot[j] = (uint32_t)mix64(lo ^ (hi * 0x9E3779B97F4A7C15ull)) & ws.memo_mask;
+                    const MemoEntry *e = ws.memo + slot[j];
+                    ld_cg_u64x2(e, elo, ehi);
+                    mt[j] = ld_cg_u32x4(&e->meta);
+                    klo[j] = lo ^ elo; khi[j] = hi ^ ehi;                            // zero iff the entry holds this word
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kWordsPerThread; ++j) {
+            if (nb[j] == 0xFFFFFFFFu) continue;
+            if (nb[j] > (uint32_t)kShortBytes) {
+                kind[j] = kWordLong; has_long = true;
+                if constexpr (!Enc::kCoopLong) ntok[j] = enc.long_count(arena + b0s[j], nb[j]);
+            } else if ((klo[j] | khi[j]) == 0 && mt[j].x != 0 && mt[j].x != 0xFFFFFFFFu) {
+                kind[j] = kWordHit; ntok[j] = (mt[j].x & 0xFFu) - 1; h6 += mt[j].x >> 8; t01[j] = make_uint2(mt[j].z, mt[j].w);
+            } else {
+                const SlowResult r = resolve_slow(enc, ws, arena, b0s[j], nb[j], arena_end, buf, status);
+                kind[j] = r.kind; ntok[j] = r.ntok; slot[j] = r.slot; t01[j] = r.t01; h6 += r.h6;
             }
             count += ntok[j];
         }
@@ -285,18 +352,18 @@ encode_tiles_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
             // long words: the whole CTA works on one word at a time in global scratch (rare)
             if (__syncthreads_or(has_long)) {
                 for (uint32_t i = 0; i < tile_words; ++i) {
-                    const uint32_t b0 = s_off[i], nbytes = s_off[i + 1] - b0;
+                    const uint32_t b0 = sm.off[i], nbytes = sm.off[i + 1] - b0;
                     if (nbytes <= (uint32_t)kShortBytes) continue;                      // CTA-uniform
                     if (tid == 0) {
                         const unsigned long long so = atomicAdd(ws.long_cursor, 2ull * nbytes);
-                        sh_misc[6] = (uint32_t)(so >> 1); sh_misc[7] = (so + 2ull * nbytes <= ws.long_scratch_elems) ? 1u : 0u;
+                        sm.misc[6] = (uint32_t)(so >> 1); sm.misc[7] = (so + 2ull * nbytes <= ws.long_scratch_elems) ? 1u : 0u;
                     }
                     __syncthreads();
-                    const unsigned long long so = (unsigned long long)sh_misc[6] << 1;
-                    const bool fits = sh_misc[7] != 0;
+                    const unsigned long long so = (unsigned long long)sm.misc[6] << 1;
+                    const bool fits = sm.misc[7] != 0;
                     __syncthreads();
                     uint32_t *res = nullptr; uint32_t c = 0;
-                    if (fits) c = enc.encode_long_coop(arena + b0, nbytes, ws.long_scratch + so, ws.long_scratch + so + nbytes, &res, sh_scan, sh_misc);
+                    if (fits) c = enc.encode_long_coop(arena + b0, nbytes, ws.long_scratch + so, ws.long_scratch + so + nbytes, &res, sm.scan, sm.misc);
                     else if (tid == 0) atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY);
                     if (tid == i / kWordsPerThread) {
 #pragma unroll
@@ -311,54 +378,93 @@ encode_tiles_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
             }
         }
 
-        // ---- scan + look-back
-        uint32_t total, excl = block_exclusive_scan(count, sh_scan, &total);
-        if (tid < 32) { const uint64_t b = tile_prefix_warp(ws.tile_state, tile, total, &status[kStatusCode]); if (tid == 0) sh_base = b; }
-        __syncthreads();
-        const uint64_t base = sh_base;
+        // ---- scan; warp 0 then runs the look-back while the other warps already assemble the tile's ids in smem
+        uint32_t total, excl = block_exclusive_scan(count, sm.scan, &total);
+        if (tid < 32) { const uint64_t b = tile_prefix_warp(ws.tile_state, tile, total, &status[kStatusCode]); if (tid == 0) sm.base = b; }
         const bool use_compact = total <= (uint32_t)kCompactTokens;
-        const bool fits_out = base + total <= out_cap;
-        if (!fits_out && tid == 0) atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY);
+        uint64_t base = 0; bool fits_out = true;
+        if (!use_compact) {                       // oversized tile (rare): ids go straight to global memory, base needed now
+            __syncthreads();
+            base = sm.base; fits_out = base + total <= out_cap;
+        }
 
-        // ---- phase B: ids to their tile-local position
-        uint32_t run = excl;
-        uint32_t offs[kWordsPerThread];
+        // ---- phase B: ids to their tile-local position.  Ids 0-1 came with the probe; ids 2-9 of all four words are
+        // requested before any is stored; the rest (rare) in a loop.
+        uint32_t run[kWordsPerThread];
+        {
+            uint32_t r = excl;
 #pragma unroll
-        for (int j = 0; j < kWordsPerThread; ++j) {
-            const uint32_t i = tid * kWordsPerThread + j;
-            offs[j] = tok_base + (uint32_t)(base + run);
-            if (kind[j] == kWordNone || !fits_out) { run += ntok[j]; continue; }
-            uint32_t *dst = use_compact ? compact + run : out_ids + base + run;
-            if (kind[j] == kWordHit) memo_copy(ws, slot[j], ntok[j], dst);
-            else if (kind[j] == kWordRecompute) {
-                uint32_t dummy = 0;
-                const uint32_t b0 = s_off[i];
-                const uint32_t n = enc.encode_short(arena + b0, s_off[i + 1] - b0, buf, dummy);
-                for (uint32_t k = 0; k < n; ++k) dst[k] = buf[k];
-            } else {
-                const uint32_t b0 = s_off[i], nbytes = s_off[i + 1] - b0;
-                if constexpr (!Enc::kCoopLong) enc.long_emit(arena + b0, nbytes, dst, ntok[j], h6);
-                else {
-                    const uint32_t *src = ws.long_scratch + ((unsigned long long)slot[j] << 1) + (kind[j] == kWordLongB ? nbytes : 0u);
-                    for (uint32_t k = 0; k < ntok[j]; ++k) dst[k] = src[k];
+            for (int j = 0; j < kWordsPerThread; ++j) { run[j] = r; r += ntok[j]; }
+        }
+        if (fits_out) {
+            uint4 c0[kWordsPerThread], c1[kWordsPerThread];
+#pragma unroll
+            for (int j = 0; j < kWordsPerThread; ++j) {
+                c0[j] = c1[j] = make_uint4(0, 0, 0, 0);
+                if (kind[j] == kWordHit && ntok[j] > 2) {
+                    const MemoEntry *e = ws.memo + slot[j];
+                    c0[j] = ld_cg_u32x4(&e->tok[0]);
+                    if (ntok[j] > 6) c1[j] = ld_cg_u32x4(&e->tok[4]);
                 }
             }
-            run += ntok[j];
-        }
-        if (out_tok_off) {
-            const uint32_t i0 = tid * kWordsPerThread;
-            if (tok_off_vec && i0 + kWordsPerThread <= tile_words)
-                *reinterpret_cast<uint4 *>(out_tok_off + w_tile + i0) = make_uint4(offs[0], offs[1], offs[2], offs[3]);
-            else {
 #pragma unroll
-                for (int j = 0; j < kWordsPerThread; ++j) if (i0 + j < tile_words) out_tok_off[w_tile + i0 + j] = offs[j];
+            for (int j = 0; j < kWordsPerThread; ++j) {
+                if (kind[j] == kWordNone) continue;
+                uint32_t *dst = use_compact ? sm.compact + run[j] : out_ids + base + run[j];
+                if (kind[j] == kWordHit) {
+                    const uint32_t n = ntok[j];
+                    if (n > 0) dst[0] = t01[j].x;
+                    if (n > 1) dst[1] = t01[j].y;
+                    if (n > 2) dst[2] = c0[j].x;
+                    if (n > 3) dst[3] = c0[j].y;
+                    if (n > 4) dst[4] = c0[j].z;
+                    if (n > 5) dst[5] = c0[j].w;
+                    if (n > 6) dst[6] = c1[j].x;
+                    if (n > 7) dst[7] = c1[j].y;
+                    if (n > 8) dst[8] = c1[j].z;
+                    if (n > 9) dst[9] = c1[j].w;
+                    if (n > 10) {
+                        const MemoEntry *e = ws.memo + slot[j];
+                        for (uint32_t k0 = 8; k0 + 2 < n; k0 += 4) {
+                            const uint4 v = ld_cg_u32x4(&e->tok[k0]);
+                            dst[k0 + 2] = v.x;
+                            if (k0 + 3 < n) dst[k0 + 3] = v.y;
+                            if (k0 + 4 < n) dst[k0 + 4] = v.z;
+                            if (k0 + 5 < n) dst[k0 + 5] = v.w;
+                        }
+                    }
+                } else h6 += emit_slow(enc, ws, arena + b0s[j], nb[j], kind[j], ntok[j], slot[j], buf, dst);
             }
         }
         __syncthreads();
+        if (use_compact) { base = sm.base; fits_out = base + total <= out_cap; }
+        if (!fits_out && tid == 0) atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY);
+        if (out_tok_off) {
+            const uint32_t i0 = tid * kWordsPerThread;
+            const uint32_t o0 = tok_base + (uint32_t)base;
+            if (tok_off_vec && i0 + kWordsPerThread <= tile_words)
+                *reinterpret_cast<uint4 *>(out_tok_off + w_tile + i0) = make_uint4(o0 + run[0], o0 + run[1], o0 + run[2], o0 + run[3]);
+            else {
+#pragma unroll
+                for (int j = 0; j < kWordsPerThread; ++j) if (i0 + j < tile_words) out_tok_off[w_tile + i0 + j] = o0 + run[j];
+            }
+        }
         // take the next ticket now so that its latency hides behind the store of this tile.  (It must not be taken any
         // earlier: a tile that holds a ticket without running delays the look-back of every later tile.)
         if (tid == 0) next_ticket = atomicAdd(ws.ticket, 1u);
-        if (use_compact && fits_out) for (uint32_t i = tid; i < total; i += kThreads) out_ids[base + i] = compact[i];
+        if (use_compact && fits_out) {
+            // coalesced store: scalar head up to 16-byte alignment of the destination, then 128-bit stores
+            uint32_t *dst = out_ids + base;
+            const uint32_t head = min(total, (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15) >> 2);
+            if (tid < head) dst[tid] = sm.compact[tid];
+            const uint32_t nvec = (total - head) >> 2;
+            for (uint32_t v = tid; v < nvec; v += kThreads) {
+                const uint32_t c = head + 4 * v;
+                *reinterpret_cast<uint4 *>(dst + c) = make_uint4(sm.compact[c], sm.compact[c + 1], sm.compact[c + 2], sm.compact[c + 3]);
+            }
+            const uint32_t tail0 = head + 4 * nvec;
+            if (tail0 + tid < total) dst[tail0 + tid] = sm.compact[tail0 + tid];
+        }
         if (tile == ws.n_tiles - 1 && tid == 0) {
             const uint64_t grand = base + total;
             if (out_tok_off) out_tok_off[n_words] = tok_base + (uint32_t)grand;
@@ -385,9 +491,12 @@ int launch_encode_tiles(const Enc &enc, const uint8_t *d_arena, const uint32_t *
         return SWT_OK;
     }
     static int grid = 0;
-    if (!grid) grid = encode_grid((const void *)encode_tiles_kernel<Enc>, kThreads);
+    if (!grid) {
+        SWT_CUDA_OK(cudaFuncSetAttribute(encode_tiles_kernel<Enc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+        grid = encode_grid((const void *)encode_tiles_kernel<Enc>, kThreads, sizeof(TileSmem));
+    }
     const int g = (int)std::min<uint64_t>((uint64_t)grid, ws.n_tiles);
-    encode_tiles_kernel<Enc><<<g, kThreads, 0, st>>>(enc, d_arena, d_word_off, n_words, d_out_ids, out_cap, d_out_tok_off, tok_base, ws, d_status);
+    encode_tiles_kernel<Enc><<<g, kThreads, sizeof(TileSmem), st>>>(enc, d_arena, d_word_off, n_words, d_out_ids, out_cap, d_out_tok_off, tok_base, ws, d_status);
     SWT_CUDA_OK(cudaGetLastError());
     return SWT_OK;
 }
