@@ -120,40 +120,50 @@ class ZipfStream:
 
 
 # ------------------------------------------------------------------------------------------------------------
-def clocks_sampler(gpu_index: int):
-    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    try:
-        return subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-    except Exception:
-        return None
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML from a background thread (every ~2 ms),
+    so that even a timed region of a few tens of milliseconds gets samples DURING the region."""
 
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-def clocks_summary(proc):
-    if proc is None:
-        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-    proc.terminate()
-    try:
-        out, _ = proc.communicate(timeout=5)
-    except Exception:
-        proc.kill()
-        out = ""
-    sm, mx, reasons = [], [], set()
-    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    for line in out.strip().splitlines():
-        f = [x.strip() for x in line.split(",")]
-        if len(f) < 7:
-            continue
+    def __init__(self, gpu_index: int):
+        import threading
+        self.ok = False
+        self.sm, self.reasons, self.max_sm = [], set(), None
+        self._stop = threading.Event()
         try:
-            sm.append(float(f[0])); mx.append(float(f[1]))
-        except ValueError:
-            continue
-        for name, v in zip(names, f[3:7]):
-            if v.lower().startswith("active"):
-                reasons.add(name)
-    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-            "samples": len(sm), "reasons": sorted(reasons)}
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:                       # noqa: BLE001
+            self.err = repr(e)
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:                        # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def summary(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self._stop.set()
+        self.t.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "samples": len(self.sm), "reasons": sorted(self.reasons)}
 
 
 def hbm_peak():
@@ -198,7 +208,7 @@ def cpu_oracle_wp(stream: "ZipfStream", vocab, sample_words: int, threads: int, 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bytes", type=int, default=1_000_000_000, help="stream bytes per GPU")
@@ -267,7 +277,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = clocks_sampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     torch.cuda.synchronize()
     ev[0].record()
@@ -279,7 +289,7 @@ def main():
         dist.barrier()
     step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     total_ms = ev[0].elapsed_time(ev[args.steps])
-    clocks = clocks_summary(sampler) if rank == 0 else None
+    clocks = sampler.summary() if rank == 0 else None
     enc.check_status(d_status)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     tot_bytes = torch.tensor([float(n_bytes)], dtype=torch.float64, device=dev)
@@ -325,7 +335,7 @@ def main():
         "warmup": max(3, args.warmup), "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "wp_encode_kernel",
+                     "traffic": None, "peak_source": peak_src, "kernel": "encode_tiles_kernel<WpEnc>",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms},
         "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": n_bytes + 4 * (n_words + 1),
                 "d2h_bytes_per_step": 4 * n_tokens + 4 * n_words + 32 * ((n_bytes >> 26) + 1), "steps": e2e_steps,
