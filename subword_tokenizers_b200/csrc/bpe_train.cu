@@ -31,6 +31,8 @@ constexpr uint32_t kHole = 0xFFFFFFFFu;
 constexpr uint64_t kEmptyKey = ~0ull;
 constexpr uint64_t kNoPos = ~0ull;
 constexpr uint32_t kMaxDenseAlpha = 4096;
+constexpr uint32_t kChunkShift = 14;            // mark scan granularity: 16384 slots per chunk
+constexpr uint32_t kBlkShift = 12;              // argmax cache granularity: 4096 table slots per block
 
 enum Halt : uint32_t { kRun = 0, kDoneVocab = 1, kDoneNoPairs = 2, kNeedGrow = 3, kRecordFull = 4,
                        kErrInternal = 16, kErrCharArena = 17, kErrSymbols = 18, kErrTableFull = 19 };
@@ -60,8 +62,11 @@ struct TrainDev {
     uint64_t char_cap, str_ht_cap;
     // arrays
     uint32_t *sym, *word_of, *start, *word_mark, *worklist;
+    uint32_t *pres; uint32_t pres_words, n_chunks;   // per chunk: bitmap of the symbols that (may) occur in it
     long long *freq;
     PairEntry *table;                 // current table (changes on grow)
+    ArgPart *blk;                     // per 4096-slot block: cached (max count, a key attaining it, how many attain it)
+    uint32_t *dirty;                  // block touched since its cache entry was computed
     long long *delta;                 // L[vmax] | R[vmax] | ZZ | M
     long long *dense;                 // n_alpha^2 initial counts
     uint64_t *cand;                   // 2
@@ -84,7 +89,7 @@ __device__ __forceinline__ long long table_get(const PairEntry *tab, uint64_t ca
         h = (h + 1) & (cap - 1);
     }
 }
-__device__ __forceinline__ void table_add(PairEntry *tab, uint64_t cap, uint64_t key, long long d, TrainState *st) {
+__device__ __forceinline__ void table_add(PairEntry *tab, uint64_t cap, uint64_t key, long long d, TrainState *st, uint32_t *dirty) {
     uint64_t h = mix64(key) & (cap - 1);
     for (uint64_t probes = 0; probes <= cap; ++probes) {
         uint64_t k = *(volatile uint64_t *)&tab[h].key;
@@ -93,10 +98,20 @@ __device__ __forceinline__ void table_add(PairEntry *tab, uint64_t cap, uint64_t
             if (old == kEmptyKey) { atomicAdd((unsigned long long *)&st->n_entries, 1ull); k = key; }
             else k = old;
         }
-        if (k == key) { atomicAdd((unsigned long long *)&tab[h].count, (unsigned long long)d); return; }
+        if (k == key) { atomicAdd((unsigned long long *)&tab[h].count, (unsigned long long)d); dirty[h >> kBlkShift] = 1u; return; }
         h = (h + 1) & (cap - 1);
     }
     atomicExch(&st->halt, (uint32_t)kErrTableFull);
+}
+
+// ---- per-chunk symbol presence: lets the mark scan skip chunks that cannot contain the pair -----------------------
+__device__ __forceinline__ bool pres_has(const TrainDev &d, uint32_t chunk, uint32_t sym) {
+    return (d.pres[(uint64_t)chunk * d.pres_words + (sym >> 5)] >> (sym & 31u)) & 1u;
+}
+__device__ __forceinline__ void pres_set(const TrainDev &d, uint64_t slot, uint32_t sym) {
+    uint32_t *w = &d.pres[(slot >> kChunkShift) * d.pres_words + (sym >> 5)];
+    const uint32_t bit = 1u << (sym & 31u);
+    if (!(*(volatile uint32_t *)w & bit)) atomicOr(w, bit);
 }
 
 // ---- init -----------------------------------------------------------------------------------------------------
@@ -105,7 +120,7 @@ __global__ void k_init_words(TrainDev d, const uint32_t *__restrict__ syms, cons
     for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < d.n_types; t += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t b = off[t], e = off[t + 1];
         d.start[t] = (uint32_t)b;
-        for (uint64_t i = b; i < e; ++i) { d.sym[i] = syms[i] | (i == b ? kStart : 0u); d.word_of[i] = (uint32_t)t; }
+        for (uint64_t i = b; i < e; ++i) { d.sym[i] = syms[i] | (i == b ? kStart : 0u); d.word_of[i] = (uint32_t)t; pres_set(d, i, syms[i]); }
         if (t == d.n_types - 1) d.start[d.n_types] = (uint32_t)e;
     }
 }
@@ -133,16 +148,19 @@ __global__ void k_build_table(TrainDev d, uint64_t cap) {
     const uint64_t n = (uint64_t)d.n_alpha * d.n_alpha;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const long long c = d.dense[i];
-        if (c != 0) table_add(d.table, cap, ((i / d.n_alpha) << 32) | (i % d.n_alpha), c, d.st);
+        if (c != 0) table_add(d.table, cap, ((i / d.n_alpha) << 32) | (i % d.n_alpha), c, d.st, d.dirty);
     }
 }
 __global__ void k_fill_u64(uint64_t *p, uint64_t n, uint64_t v, uint64_t stride_words) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i * stride_words] = v;
 }
+__global__ void k_fill_u32(uint32_t *p, uint64_t n, uint32_t v) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
 __global__ void k_rehash(const PairEntry *old_tab, uint64_t old_cap, TrainDev d, uint64_t new_cap) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_cap; i += (uint64_t)gridDim.x * blockDim.x) {
         const PairEntry e = old_tab[i];
-        if (e.key != kEmptyKey && e.count != 0) table_add(d.table, new_cap, e.key, e.count, d.st);
+        if (e.key != kEmptyKey && e.count != 0) table_add(d.table, new_cap, e.key, e.count, d.st, d.dirty);
     }
 }
 
@@ -151,33 +169,43 @@ __device__ __forceinline__ void arg_combine(long long &c, uint64_t &k, uint32_t 
     if (c2 > c) { c = c2; k = k2; n = n2; }
     else if (c2 == c) { n += n2; if (k2 < k) k = k2; }
 }
+// Refreshes the cached maximum of every table block that was touched since the last step (usually a few
+// hundred of the thousands of blocks), so that select does not have to stream the whole table every merge.
 __global__ void __launch_bounds__(256) k_argmax_partial(TrainDev d) {
     TrainState *st = d.st;
     if (st->halt) return;
     const uint64_t cap = st->table_cap;
-    long long c = 0; uint64_t k = kEmptyKey; uint32_t n = 0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
-        const PairEntry e = d.table[i];
-        if (e.key != kEmptyKey && e.count > 0) arg_combine(c, k, n, e.count, e.key, 1u);
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        long long c2 = __shfl_xor_sync(0xffffffffu, c, o); uint64_t k2 = __shfl_xor_sync(0xffffffffu, k, o);
-        uint32_t n2 = __shfl_xor_sync(0xffffffffu, n, o);
-        arg_combine(c, k, n, c2, k2, n2);
-    }
+    const uint32_t n_blk = (uint32_t)(cap >> kBlkShift);
     __shared__ long long sc[8]; __shared__ uint64_t sk[8]; __shared__ uint32_t sn[8];
-    if ((threadIdx.x & 31) == 0) { sc[threadIdx.x >> 5] = c; sk[threadIdx.x >> 5] = k; sn[threadIdx.x >> 5] = n; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) arg_combine(c, k, n, sc[w], sk[w], sn[w]);
-        d.parts[blockIdx.x] = ArgPart{c, k, n, 0};
+    for (uint32_t b = blockIdx.x; b < n_blk; b += gridDim.x) {
+        if (!d.dirty[b]) continue;                                   // CTA-uniform
+        long long c = 0; uint64_t k = kEmptyKey; uint32_t n = 0;
+        const uint64_t s0 = (uint64_t)b << kBlkShift;
+        for (uint32_t i = threadIdx.x; i < (1u << kBlkShift); i += blockDim.x) {
+            const PairEntry e = d.table[s0 + i];
+            if (e.key != kEmptyKey && e.count > 0) arg_combine(c, k, n, e.count, e.key, 1u);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            long long c2 = __shfl_xor_sync(0xffffffffu, c, o); uint64_t k2 = __shfl_xor_sync(0xffffffffu, k, o);
+            uint32_t n2 = __shfl_xor_sync(0xffffffffu, n, o);
+            arg_combine(c, k, n, c2, k2, n2);
+        }
+        if ((threadIdx.x & 31) == 0) { sc[threadIdx.x >> 5] = c; sk[threadIdx.x >> 5] = k; sn[threadIdx.x >> 5] = n; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) arg_combine(c, k, n, sc[w], sk[w], sn[w]);
+            d.blk[b] = ArgPart{c, k, n, 0};
+            d.dirty[b] = 0;
+        }
+        __syncthreads();
     }
 }
 __global__ void __launch_bounds__(256) k_select(TrainDev d) {
     TrainState *st = d.st;
     if (st->halt) return;
     long long c = 0; uint64_t k = kEmptyKey; uint32_t n = 0;
-    for (uint32_t i = threadIdx.x; i < d.n_parts; i += blockDim.x) { ArgPart p = d.parts[i]; arg_combine(c, k, n, p.count, p.key, p.n_tied); }
+    const uint32_t n_blk = (uint32_t)(st->table_cap >> kBlkShift);
+    for (uint32_t i = threadIdx.x; i < n_blk; i += blockDim.x) { ArgPart p = d.blk[i]; arg_combine(c, k, n, p.count, p.key, p.n_tied); }
     for (int o = 16; o > 0; o >>= 1) {
         long long c2 = __shfl_xor_sync(0xffffffffu, c, o); uint64_t k2 = __shfl_xor_sync(0xffffffffu, k, o);
         uint32_t n2 = __shfl_xor_sync(0xffffffffu, n, o);
@@ -303,12 +331,30 @@ __global__ void __launch_bounds__(256) k_mark(TrainDev d) {
     if (st->halt || !st->cur_valid) return;
     const uint32_t a = st->cur_a, b = st->cur_b, stamp = st->step_stamp;
     const uint64_t n = d.n_slots;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i + 1 < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t s = d.sym[i];
-        if ((s & ~kStart) != a) continue;
-        if (d.sym[i + 1] != b) continue;                 // b carries no flag: same type, live slot
-        const uint32_t w = d.word_of[i];
-        if (atomicExch(&d.word_mark[w], stamp) != stamp) d.worklist[atomicAdd(&d.st->worklist_n, 1u)] = w;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t chunk = blockIdx.x; chunk < d.n_chunks; chunk += gridDim.x) {
+        // a chunk can hold an occurrence only if `a` occurs in it and `b` occurs in it or at the start of the next one
+        if (!pres_has(d, chunk, a)) continue;                                        // CTA-uniform
+        if (!pres_has(d, chunk, b) && !(chunk + 1 < d.n_chunks && pres_has(d, chunk + 1, b))) continue;
+        const uint64_t c0 = (uint64_t)chunk << kChunkShift;
+        for (uint32_t it = 0; it < (1u << kChunkShift) / (256 * 4); ++it) {
+            const uint64_t i = c0 + ((uint64_t)it * 256 + threadIdx.x) * 4;           // 4 slots per thread, 128-bit load
+            uint4 v = make_uint4(kHole, kHole, kHole, kHole);
+            if (i < n) v = *reinterpret_cast<const uint4 *>(d.sym + i);              // sym[] is padded with dead slots
+            uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x, 1);
+            if (lane == 31) nxt = (i + 4 < n) ? d.sym[i + 4] : kHole;
+            const bool m0 = (v.x & ~kStart) == a && v.y == b, m1 = (v.y & ~kStart) == a && v.z == b;
+            const bool m2 = (v.z & ~kStart) == a && v.w == b, m3 = (v.w & ~kStart) == a && nxt == b;
+            if (m0 | m1 | m2 | m3) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool m = k == 0 ? m0 : k == 1 ? m1 : k == 2 ? m2 : m3;
+                    if (!m) continue;
+                    const uint32_t w = d.word_of[i + k];
+                    if (atomicExch(&d.word_mark[w], stamp) != stamp) d.worklist[atomicAdd(&d.st->worklist_n, 1u)] = w;
+                }
+            }
+        }
     }
 }
 
@@ -332,10 +378,10 @@ __global__ void __launch_bounds__(128) k_apply(TrainDev d) {
             if (s == a && nx == b) {
                 if (have_prev) { if (last_merge) zz += f; else atomicAdd((unsigned long long *)&L[prev], (unsigned long long)f); }
                 m += f;
-                d.sym[o] = z; prev = z; last_merge = true; r += 2;
+                d.sym[o] = z; pres_set(d, o, z); prev = z; last_merge = true; r += 2;
             } else {
                 if (have_prev && last_merge) atomicAdd((unsigned long long *)&R[s], (unsigned long long)f);
-                d.sym[o] = s; prev = s; last_merge = false; r += 1;
+                d.sym[o] = s; if (o != r) pres_set(d, o, s); prev = s; last_merge = false; r += 1;
             }
             have_prev = true; ++o;
         }
@@ -357,13 +403,13 @@ __global__ void __launch_bounds__(256) k_update(TrainDev d) {
     long long *L = d.delta, *R = d.delta + d.vmax;
     for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < d.vmax; x += gridDim.x * blockDim.x) {
         const long long l = L[x], r = R[x];
-        if (l) { table_add(d.table, cap, ((uint64_t)x << 32) | a, -l, st); table_add(d.table, cap, ((uint64_t)x << 32) | z, l, st); L[x] = 0; }
-        if (r) { table_add(d.table, cap, (b << 32) | x, -r, st); table_add(d.table, cap, (z << 32) | x, r, st); R[x] = 0; }
+        if (l) { table_add(d.table, cap, ((uint64_t)x << 32) | a, -l, st, d.dirty); table_add(d.table, cap, ((uint64_t)x << 32) | z, l, st, d.dirty); L[x] = 0; }
+        if (r) { table_add(d.table, cap, (b << 32) | x, -r, st, d.dirty); table_add(d.table, cap, (z << 32) | x, r, st, d.dirty); R[x] = 0; }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const long long zz = d.delta[2 * (uint64_t)d.vmax], m = d.delta[2 * (uint64_t)d.vmax + 1];
-        if (zz) { table_add(d.table, cap, (b << 32) | a, -zz, st); table_add(d.table, cap, (z << 32) | z, zz, st); }
-        if (m) table_add(d.table, cap, (a << 32) | b, -m, st);
+        if (zz) { table_add(d.table, cap, (b << 32) | a, -zz, st, d.dirty); table_add(d.table, cap, (z << 32) | z, zz, st, d.dirty); }
+        if (m) table_add(d.table, cap, (a << 32) | b, -m, st, d.dirty);
         d.delta[2 * (uint64_t)d.vmax] = 0; d.delta[2 * (uint64_t)d.vmax + 1] = 0;
     }
 }
@@ -384,10 +430,12 @@ struct swt_bpe_trainer {
     int device;
     uint64_t table_cap;
     int grid_scan;      // persistent grid for streaming passes
+    cudaGraphExec_t step_graph = nullptr;   // kStepsPerGraph whole steps, captured once (re-captured after a table grow)
 };
+static constexpr uint32_t kStepsPerGraph = 32;
 
 static uint64_t choose_table_cap(const swt_bpe_train_config *cfg) {
-    if (cfg->table_cap) return next_pow2(cfg->table_cap);
+    if (cfg->table_cap) return std::max<uint64_t>(next_pow2(cfg->table_cap), 1ull << kBlkShift);
     uint64_t a2 = (uint64_t)cfg->n_alpha * cfg->n_alpha;
     uint64_t want = std::max<uint64_t>(1ull << 16, 4 * std::min<uint64_t>(a2, 1ull << 24));
     want = std::max<uint64_t>(want, 8ull * (uint64_t)std::max<int64_t>(cfg->max_vocab, 1));
@@ -401,6 +449,17 @@ static uint64_t char_cap_of(const swt_bpe_train_config *cfg) {
     return std::min<uint64_t>(std::max<uint64_t>(want, 1ull << 20), 1ull << 26) + cfg->n_alpha;
 }
 
+static size_t table_region_bytes(uint64_t cap) {
+    const uint64_t n_blk = cap >> kBlkShift;
+    return align_up(cap * sizeof(PairEntry), 256) + align_up(n_blk * sizeof(ArgPart), 256) + align_up(n_blk * sizeof(uint32_t), 256);
+}
+static void table_region_carve(void *base, uint64_t cap, TrainDev *d) {
+    uint8_t *p = (uint8_t *)base;
+    const uint64_t n_blk = cap >> kBlkShift;
+    d->table = (PairEntry *)p; p += align_up(cap * sizeof(PairEntry), 256);
+    d->blk = (ArgPart *)p; p += align_up(n_blk * sizeof(ArgPart), 256);
+    d->dirty = (uint32_t *)p;
+}
 static size_t train_layout(const swt_bpe_train_config *cfg, void *base, TrainDev *d, uint64_t table_cap) {
     Carver cv(base);
     const uint32_t vmax = vmax_of(cfg);
@@ -409,7 +468,10 @@ static size_t train_layout(const swt_bpe_train_config *cfg, void *base, TrainDev
     d->max_vocab = cfg->max_vocab; d->n_parts = kNumSMs * 4;
     d->char_cap = char_cap_of(cfg); d->str_ht_cap = next_pow2(4ull * vmax);
     d->st = cv.take<TrainState>(1);
-    d->sym = cv.take<uint32_t>(d->n_slots + 2);
+    d->sym = cv.take<uint32_t>(d->n_slots + 8);
+    d->n_chunks = (uint32_t)((d->n_slots + (1ull << kChunkShift) - 1) >> kChunkShift);
+    d->pres_words = (vmax + 31) / 32;
+    d->pres = cv.take<uint32_t>((uint64_t)d->n_chunks * d->pres_words + 1);
     d->word_of = cv.take<uint32_t>(d->n_slots + 1);
     d->start = cv.take<uint32_t>(d->n_types + 1);
     d->word_mark = cv.take<uint32_t>(d->n_types + 1);
@@ -424,7 +486,8 @@ static size_t train_layout(const swt_bpe_train_config *cfg, void *base, TrainDev
     d->rec_new = cv.take<uint32_t>(cfg->record_cap); d->rec_count = cv.take<long long>(cfg->record_cap);
     d->sym_len = cv.take<uint32_t>(vmax); d->sym_off = cv.take<uint64_t>(vmax); d->sym_hash = cv.take<uint64_t>(vmax);
     d->sym_pow = cv.take<uint64_t>(vmax); d->chars = cv.take<uint32_t>(d->char_cap); d->str_ht = cv.take<uint32_t>(d->str_ht_cap);
-    d->table = cv.take<PairEntry>(table_cap);
+    uint8_t *region = cv.take<uint8_t>(table_region_bytes(table_cap));
+    table_region_carve(region, table_cap, d);
     return cv.used();
 }
 
@@ -433,7 +496,7 @@ SWT_API size_t swt_bpe_train_workspace_bytes(const swt_bpe_train_config *cfg) {
     TrainDev d;
     return train_layout(cfg, nullptr, &d, choose_table_cap(cfg));
 }
-SWT_API size_t swt_bpe_train_table_bytes(uint64_t cap) { return next_pow2(cap) * sizeof(PairEntry) + 256; }
+SWT_API size_t swt_bpe_train_table_bytes(uint64_t cap) { return table_region_bytes(next_pow2(cap)) + 256; }
 
 SWT_API int swt_bpe_train_create(const swt_bpe_train_config *cfg, const uint32_t *d_syms, const uint64_t *d_off,
                                  const int64_t *d_freq, void *d_workspace, size_t workspace_bytes, void *stream,
@@ -458,11 +521,13 @@ SWT_API int swt_bpe_train_create(const swt_bpe_train_config *cfg, const uint32_t
     TrainDev &d = t->dev;
     // zero everything up to the pair table, then mark the table empty
     cudaError_t e = cudaMemsetAsync(d_workspace, 0, (uint8_t *)d.table - (uint8_t *)d_workspace, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d.table, 0, t->table_cap * sizeof(PairEntry), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d.table, 0, table_region_bytes(t->table_cap), st);
     if (e != cudaSuccess) { delete t; set_error(std::string("memset: ") + cudaGetErrorString(e)); return SWT_ERR_CUDA; }
     k_fill_u64<<<t->grid_scan, 256, 0, st>>>((uint64_t *)d.table, t->table_cap, kEmptyKey, 2);
+    k_fill_u32<<<64, 256, 0, st>>>(d.dirty, t->table_cap >> kBlkShift, 1u);
     k_init_symbols<<<32, 256, 0, st>>>(d, cfg->initial_vocab);
     k_set_table_cap<<<1, 1, 0, st>>>(d.st, t->table_cap);
+    k_fill_u32<<<1, 32, 0, st>>>(d.sym + d.n_slots, 8, kHole);
     if (cfg->n_types_local) {
         k_init_words<<<t->grid_scan, 256, 0, st>>>(d, d_syms, d_off);
         e = cudaMemcpyAsync(d.freq, d_freq, cfg->n_types_local * sizeof(long long), cudaMemcpyDeviceToDevice, st);
@@ -474,7 +539,11 @@ SWT_API int swt_bpe_train_create(const swt_bpe_train_config *cfg, const uint32_t
     return SWT_OK;
 }
 
-SWT_API void swt_bpe_train_destroy(swt_bpe_trainer *t) { delete t; }
+SWT_API void swt_bpe_train_destroy(swt_bpe_trainer *t) {
+    if (!t) return;
+    if (t->step_graph) cudaGraphExecDestroy(t->step_graph);
+    delete t;
+}
 
 SWT_API int swt_bpe_train_buffers(const swt_bpe_trainer *t, void **init_counts_ptr, uint64_t *init_counts_elems,
                                   void **cand_ptr, void **cand_gather_ptr, void **delta_ptr, uint64_t *delta_elems) {
@@ -516,7 +585,7 @@ SWT_API int swt_bpe_train_merge(swt_bpe_trainer *t, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     k_begin_merge<<<1, 32, 0, st>>>(t->dev);
     if (t->dev.n_slots) {
-        k_mark<<<t->grid_scan, 256, 0, st>>>(t->dev);
+        k_mark<<<(int)std::min<uint32_t>((uint32_t)t->grid_scan, t->dev.n_chunks), 256, 0, st>>>(t->dev);
         k_apply<<<t->grid_scan / 2, 128, 0, st>>>(t->dev);
     }
     SWT_CUDA_OK(cudaGetLastError());
@@ -529,14 +598,36 @@ SWT_API int swt_bpe_train_update(swt_bpe_trainer *t, void *stream) {
     SWT_CUDA_OK(cudaGetLastError());
     return SWT_OK;
 }
+static int enqueue_step(swt_bpe_trainer *t, void *stream) {
+    int rc = swt_bpe_train_select(t, stream); if (rc) return rc;
+    rc = swt_bpe_train_merge(t, stream); if (rc) return rc;
+    return swt_bpe_train_update(t, stream);
+}
+
 SWT_API int swt_bpe_train_steps(swt_bpe_trainer *t, uint32_t n_steps, void *stream) {
     SWT_REQUIRE(t != nullptr, "NULL trainer");
     SWT_REQUIRE(t->cfg.world_size == 1, "swt_bpe_train_steps is the single-rank loop; use select/merge/update with collectives");
-    for (uint32_t s = 0; s < n_steps; ++s) {
-        int rc = swt_bpe_train_select(t, stream); if (rc) return rc;
-        rc = swt_bpe_train_merge(t, stream); if (rc) return rc;
-        rc = swt_bpe_train_update(t, stream); if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    // The step is launch-bound on small corpora (9 short kernels), so kStepsPerGraph steps are captured into one CUDA
+    // graph and replayed; every kernel is self-gating on the halt flag, so replaying past the end is harmless.
+    if (!t->step_graph && n_steps >= kStepsPerGraph && st != nullptr) {
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            int rc = SWT_OK;
+            for (uint32_t s = 0; s < kStepsPerGraph && rc == SWT_OK; ++s) rc = enqueue_step(t, stream);
+            cudaError_t e = cudaStreamEndCapture(st, &g);
+            if (rc == SWT_OK && e == cudaSuccess && g) {
+                if (cudaGraphInstantiate(&t->step_graph, g, 0) != cudaSuccess) t->step_graph = nullptr;
+            }
+            if (g) cudaGraphDestroy(g);
+            (void)cudaGetLastError();
+        } else (void)cudaGetLastError();
     }
+    uint32_t done = 0;
+    if (t->step_graph) {
+        for (; done + kStepsPerGraph <= n_steps; done += kStepsPerGraph) SWT_CUDA_OK(cudaGraphLaunch(t->step_graph, st));
+    }
+    for (; done < n_steps; ++done) { int rc = enqueue_step(t, stream); if (rc) return rc; }
     return SWT_OK;
 }
 
@@ -568,10 +659,13 @@ SWT_API int swt_bpe_train_grow_table(swt_bpe_trainer *t, void *d_new_table, uint
     SWT_REQUIRE(new_cap > t->table_cap, "new table must be larger");
     cudaStream_t st = (cudaStream_t)stream;
     PairEntry *old_tab = t->dev.table; const uint64_t old_cap = t->table_cap;
-    PairEntry *nt = (PairEntry *)(((uintptr_t)d_new_table + 255) / 256 * 256);
-    SWT_CUDA_OK(cudaMemsetAsync(nt, 0, new_cap * sizeof(PairEntry), st));
-    k_fill_u64<<<t->grid_scan, 256, 0, st>>>((uint64_t *)nt, new_cap, kEmptyKey, 2);
-    t->dev.table = nt; t->table_cap = new_cap;
+    void *region = (void *)(((uintptr_t)d_new_table + 255) / 256 * 256);
+    SWT_CUDA_OK(cudaMemsetAsync(region, 0, table_region_bytes(new_cap), st));
+    table_region_carve(region, new_cap, &t->dev);
+    t->table_cap = new_cap;
+    if (t->step_graph) { cudaGraphExecDestroy(t->step_graph); t->step_graph = nullptr; }   // kernels captured the old table pointer
+    k_fill_u64<<<t->grid_scan, 256, 0, st>>>((uint64_t *)t->dev.table, new_cap, kEmptyKey, 2);
+    k_fill_u32<<<64, 256, 0, st>>>(t->dev.dirty, new_cap >> kBlkShift, 1u);
     k_set_table_cap<<<1, 1, 0, st>>>(t->dev.st, new_cap);
     k_rehash<<<t->grid_scan, 256, 0, st>>>(old_tab, old_cap, t->dev, new_cap);
     k_clear_halt<<<1, 1, 0, st>>>(t->dev.st, kNeedGrow, 0u);

@@ -228,8 +228,12 @@ class CudaTrainEngine:
             torch.from_numpy(np.ascontiguousarray(freq, dtype=np.int64)).to(self.dev),
         ]
         self.handle = c_vp(None)
+        # the trainer runs on its own (non-default) stream: the single-rank loop is replayed as a CUDA graph, and
+        # stream capture is not possible on the legacy default stream
+        torch.cuda.synchronize()
+        self.stream = torch.cuda.Stream(device=self.dev)
         check(lib.swt_bpe_train_create(ctypes.byref(self.cfg), self._keep[0].data_ptr(), self._keep[1].data_ptr(),
-                                       self._keep[2].data_ptr(), self.workspace.data_ptr(), ws_bytes, _stream_ptr(),
+                                       self._keep[2].data_ptr(), self.workspace.data_ptr(), ws_bytes, self._sp(),
                                        ctypes.byref(self.handle)), "swt_bpe_train_create")
         ic, ice, cp, cgp, dp, de = c_vp(), ctypes.c_uint64(), c_vp(), c_vp(), c_vp(), ctypes.c_uint64()
         check(lib.swt_bpe_train_buffers(self.handle, ctypes.byref(ic), ctypes.byref(ice), ctypes.byref(cp), ctypes.byref(cgp),
@@ -249,20 +253,23 @@ class CudaTrainEngine:
         self._tables: List[torch.Tensor] = []
         self.n_types, self.n_slots = n_types, int(off[-1]) if n_types else 0
 
-    # phases (all asynchronous on the current stream)
-    def count_local(self): check(self.lib.swt_bpe_train_count_local(self.handle, _stream_ptr()))
-    def build_table(self): check(self.lib.swt_bpe_train_build_table(self.handle, _stream_ptr()))
-    def select(self): check(self.lib.swt_bpe_train_select(self.handle, _stream_ptr()))
-    def merge(self): check(self.lib.swt_bpe_train_merge(self.handle, _stream_ptr()))
-    def update(self): check(self.lib.swt_bpe_train_update(self.handle, _stream_ptr()))
-    def steps(self, n: int): check(self.lib.swt_bpe_train_steps(self.handle, n, _stream_ptr()))
+    def _sp(self) -> int:
+        return self.stream.cuda_stream
+
+    # phases (all asynchronous on the trainer's stream)
+    def count_local(self): check(self.lib.swt_bpe_train_count_local(self.handle, self._sp()))
+    def build_table(self): check(self.lib.swt_bpe_train_build_table(self.handle, self._sp()))
+    def select(self): check(self.lib.swt_bpe_train_select(self.handle, self._sp()))
+    def merge(self): check(self.lib.swt_bpe_train_merge(self.handle, self._sp()))
+    def update(self): check(self.lib.swt_bpe_train_update(self.handle, self._sp()))
+    def steps(self, n: int): check(self.lib.swt_bpe_train_steps(self.handle, n, self._sp()))
 
     def read(self):
         """Synchronises. -> (state dict, left, right, new, count) for the merges recorded since the last read."""
         st = TrainState()
         check(self.lib.swt_bpe_train_read(self.handle, _np_ptr(self._rec[0], c_u32p), _np_ptr(self._rec[1], c_u32p),
                                           _np_ptr(self._rec[2], c_u32p), _np_ptr(self._rec[3], c_i64p), ctypes.byref(st),
-                                          _stream_ptr()), "swt_bpe_train_read")
+                                          self._sp()), "swt_bpe_train_read")
         n = st.n_recorded
         state = {f[0]: getattr(st, f[0]) for f in TrainState._fields_}
         return state, self._rec[0][:n].copy(), self._rec[1][:n].copy(), self._rec[2][:n].copy(), self._rec[3][:n].copy()
@@ -271,14 +278,14 @@ class CudaTrainEngine:
         new_cap = cur_cap * 4
         buf = torch.empty(self.lib.swt_bpe_train_table_bytes(new_cap), dtype=torch.uint8, device=self.dev)
         self._tables.append(buf)                       # keep alive; older tables are released after the rehash ran
-        check(self.lib.swt_bpe_train_grow_table(self.handle, buf.data_ptr(), new_cap, _stream_ptr()))
-        torch.cuda.current_stream().synchronize()
+        check(self.lib.swt_bpe_train_grow_table(self.handle, buf.data_ptr(), new_cap, self._sp()))
+        self.stream.synchronize()
         self._tables = self._tables[-1:]
 
     def read_corpus(self):
         syms = np.zeros(max(self.n_slots, 1), dtype=np.uint32)
         lens = np.zeros(max(self.n_types, 1), dtype=np.uint32)
-        check(self.lib.swt_bpe_train_read_corpus(self.handle, _np_ptr(syms, c_u32p), _np_ptr(lens, c_u32p), _stream_ptr()))
+        check(self.lib.swt_bpe_train_read_corpus(self.handle, _np_ptr(syms, c_u32p), _np_ptr(lens, c_u32p), self._sp()))
         return syms[:self.n_slots], lens[:self.n_types]
 
     def close(self):
@@ -302,7 +309,15 @@ def run_training_loop(engine, world_size: int = 1, group=None, steps_per_sync: i
     issued through torch.distributed on those tensors (NCCL on GPUs; the CPU tests drive a numpy engine
     over gloo through this same function).
     """
+    import contextlib
     import torch.distributed as dist
+    stream = getattr(engine, "stream", None)
+    ctx = torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+    with ctx:                                   # the collectives must be ordered with the kernels: same stream
+        return _training_loop(engine, world_size, group, steps_per_sync, progress, dist)
+
+
+def _training_loop(engine, world_size, group, steps_per_sync, progress, dist):
     lefts, rights, news, counts = [], [], [], []
     engine.count_local()
     if world_size > 1:
