@@ -31,7 +31,7 @@ constexpr uint32_t kHole = 0xFFFFFFFFu;
 constexpr uint64_t kEmptyKey = ~0ull;
 constexpr uint64_t kNoPos = ~0ull;
 constexpr uint32_t kMaxDenseAlpha = 4096;
-constexpr uint32_t kChunkShift = 14;            // mark scan granularity: 16384 slots per chunk
+constexpr uint32_t kChunkShift = 12;            // mark scan granularity: 4096 slots per chunk
 constexpr uint32_t kBlkShift = 12;              // argmax cache granularity: 4096 table slots per block
 
 enum Halt : uint32_t { kRun = 0, kDoneVocab = 1, kDoneNoPairs = 2, kNeedGrow = 3, kRecordFull = 4,
@@ -50,6 +50,7 @@ struct TrainState {                 // device resident, mutable
     uint64_t cand_key, best_pos;
     uint32_t cur_a, cur_b, cur_z, cur_valid;
     uint64_t char_used;
+    uint32_t n_dirty, n_touch_l, n_touch_r, pad0;   // lengths of the dirty-block list and of the touched-symbol lists
 };
 
 struct ArgPart { long long count; uint64_t key; uint32_t n_tied; uint32_t pad; };
@@ -67,6 +68,8 @@ struct TrainDev {
     PairEntry *table;                 // current table (changes on grow)
     ArgPart *blk;                     // per 4096-slot block: cached (max count, a key attaining it, how many attain it)
     uint32_t *dirty;                  // block touched since its cache entry was computed
+    uint32_t *dirty_list;             // the blocks whose flag went 0 -> 1 (what the next select has to refresh)
+    uint32_t *touch_l, *touch_r;      // symbols x / y whose L[x] / R[y] became non-zero in this step
     long long *delta;                 // L[vmax] | R[vmax] | ZZ | M
     long long *dense;                 // n_alpha^2 initial counts
     uint64_t *cand;                   // 2
@@ -89,7 +92,8 @@ __device__ __forceinline__ long long table_get(const PairEntry *tab, uint64_t ca
         h = (h + 1) & (cap - 1);
     }
 }
-__device__ __forceinline__ void table_add(PairEntry *tab, uint64_t cap, uint64_t key, long long d, TrainState *st, uint32_t *dirty) {
+__device__ __forceinline__ void table_add(PairEntry *tab, uint64_t cap, uint64_t key, long long d, TrainState *st, uint32_t *dirty,
+                                          uint32_t *dirty_list) {
     uint64_t h = mix64(key) & (cap - 1);
     for (uint64_t probes = 0; probes <= cap; ++probes) {
         uint64_t k = *(volatile uint64_t *)&tab[h].key;
@@ -98,7 +102,12 @@ __device__ __forceinline__ void table_add(PairEntry *tab, uint64_t cap, uint64_t
             if (old == kEmptyKey) { atomicAdd((unsigned long long *)&st->n_entries, 1ull); k = key; }
             else k = old;
         }
-        if (k == key) { atomicAdd((unsigned long long *)&tab[h].count, (unsigned long long)d); dirty[h >> kBlkShift] = 1u; return; }
+        if (k == key) {
+            atomicAdd((unsigned long long *)&tab[h].count, (unsigned long long)d);
+            const uint32_t b = (uint32_t)(h >> kBlkShift);
+            if (*(volatile uint32_t *)&dirty[b] == 0u && atomicExch(&dirty[b], 1u) == 0u) dirty_list[atomicAdd(&st->n_dirty, 1u)] = b;
+            return;
+        }
         h = (h + 1) & (cap - 1);
     }
     atomicExch(&st->halt, (uint32_t)kErrTableFull);
@@ -132,7 +141,7 @@ __global__ void k_init_symbols(TrainDev d, long long initial_vocab) {
         TrainState *st = d.st;
         st->halt = kRun; st->n_recorded = 0; st->n_merges_total = 0; st->vocab_size = initial_vocab;
         st->n_symbols = d.n_alpha; st->n_entries = 0; st->n_live = d.n_slots; st->step_stamp = 0;
-        st->char_used = d.n_alpha; st->cur_valid = 0; st->worklist_n = 0;
+        st->char_used = d.n_alpha; st->cur_valid = 0; st->worklist_n = 0; st->n_dirty = 0; st->n_touch_l = 0; st->n_touch_r = 0;
     }
 }
 __global__ void k_count_dense(TrainDev d) {
@@ -148,7 +157,7 @@ __global__ void k_build_table(TrainDev d, uint64_t cap) {
     const uint64_t n = (uint64_t)d.n_alpha * d.n_alpha;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const long long c = d.dense[i];
-        if (c != 0) table_add(d.table, cap, ((i / d.n_alpha) << 32) | (i % d.n_alpha), c, d.st, d.dirty);
+        if (c != 0) table_add(d.table, cap, ((i / d.n_alpha) << 32) | (i % d.n_alpha), c, d.st, d.dirty, d.dirty_list);
     }
 }
 __global__ void k_fill_u64(uint64_t *p, uint64_t n, uint64_t v, uint64_t stride_words) {
@@ -160,7 +169,7 @@ __global__ void k_fill_u32(uint32_t *p, uint64_t n, uint32_t v) {
 __global__ void k_rehash(const PairEntry *old_tab, uint64_t old_cap, TrainDev d, uint64_t new_cap) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_cap; i += (uint64_t)gridDim.x * blockDim.x) {
         const PairEntry e = old_tab[i];
-        if (e.key != kEmptyKey && e.count != 0) table_add(d.table, new_cap, e.key, e.count, d.st, d.dirty);
+        if (e.key != kEmptyKey && e.count != 0) table_add(d.table, new_cap, e.key, e.count, d.st, d.dirty, d.dirty_list);
     }
 }
 
@@ -174,11 +183,10 @@ __device__ __forceinline__ void arg_combine(long long &c, uint64_t &k, uint32_t 
 __global__ void __launch_bounds__(256) k_argmax_partial(TrainDev d) {
     TrainState *st = d.st;
     if (st->halt) return;
-    const uint64_t cap = st->table_cap;
-    const uint32_t n_blk = (uint32_t)(cap >> kBlkShift);
+    const uint32_t n_dirty = st->n_dirty;
     __shared__ long long sc[8]; __shared__ uint64_t sk[8]; __shared__ uint32_t sn[8];
-    for (uint32_t b = blockIdx.x; b < n_blk; b += gridDim.x) {
-        if (!d.dirty[b]) continue;                                   // CTA-uniform
+    for (uint32_t q = blockIdx.x; q < n_dirty; q += gridDim.x) {
+        const uint32_t b = d.dirty_list[q];
         long long c = 0; uint64_t k = kEmptyKey; uint32_t n = 0;
         const uint64_t s0 = (uint64_t)b << kBlkShift;
         for (uint32_t i = threadIdx.x; i < (1u << kBlkShift); i += blockDim.x) {
@@ -200,7 +208,7 @@ __global__ void __launch_bounds__(256) k_argmax_partial(TrainDev d) {
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(256) k_select(TrainDev d) {
+__global__ void __launch_bounds__(1024) k_select(TrainDev d) {
     TrainState *st = d.st;
     if (st->halt) return;
     long long c = 0; uint64_t k = kEmptyKey; uint32_t n = 0;
@@ -211,11 +219,13 @@ __global__ void __launch_bounds__(256) k_select(TrainDev d) {
         uint32_t n2 = __shfl_xor_sync(0xffffffffu, n, o);
         arg_combine(c, k, n, c2, k2, n2);
     }
-    __shared__ long long sc[8]; __shared__ uint64_t sk[8]; __shared__ uint32_t sn[8];
+    __shared__ long long sc[32]; __shared__ uint64_t sk[32]; __shared__ uint32_t sn[32];
     if ((threadIdx.x & 31) == 0) { sc[threadIdx.x >> 5] = c; sk[threadIdx.x >> 5] = k; sn[threadIdx.x >> 5] = n; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) arg_combine(c, k, n, sc[w], sk[w], sn[w]);
+        for (int w = 1; w < 32; ++w) arg_combine(c, k, n, sc[w], sk[w], sn[w]);
+        st->n_dirty = 0;                                    // every listed block was refreshed by k_argmax_partial
+        st->n_touch_l = 0; st->n_touch_r = 0;               // consumed by the previous step's k_update
         st->max_count = c; st->n_tied = n; st->cand_key = k;
         st->worklist_n = 0; st->tie_ticket = 0; st->best_pos = kNoPos; st->cur_valid = 0;
         // loop conditions of bpe.py:88 and :98-99, then the capacity gates (checked before any mutation)
@@ -376,11 +386,14 @@ __global__ void __launch_bounds__(128) k_apply(TrainDev d) {
             s &= ~kStart;
             const uint32_t nx = (r + 1 < we) ? d.sym[r + 1] : kHole;
             if (s == a && nx == b) {
-                if (have_prev) { if (last_merge) zz += f; else atomicAdd((unsigned long long *)&L[prev], (unsigned long long)f); }
+                if (have_prev) {
+                    if (last_merge) zz += f;
+                    else if (atomicAdd((unsigned long long *)&L[prev], (unsigned long long)f) == 0ull) d.touch_l[atomicAdd(&st->n_touch_l, 1u)] = prev;
+                }
                 m += f;
                 d.sym[o] = z; pres_set(d, o, z); prev = z; last_merge = true; r += 2;
             } else {
-                if (have_prev && last_merge) atomicAdd((unsigned long long *)&R[s], (unsigned long long)f);
+                if (have_prev && last_merge && atomicAdd((unsigned long long *)&R[s], (unsigned long long)f) == 0ull) d.touch_r[atomicAdd(&st->n_touch_r, 1u)] = s;
                 d.sym[o] = s; if (o != r) pres_set(d, o, s); prev = s; last_merge = false; r += 1;
             }
             have_prev = true; ++o;
@@ -401,15 +414,32 @@ __global__ void __launch_bounds__(256) k_update(TrainDev d) {
     const uint64_t a = st->cur_a, b = st->cur_b, z = st->cur_z;
     const uint64_t cap = st->table_cap;
     long long *L = d.delta, *R = d.delta + d.vmax;
-    for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < d.vmax; x += gridDim.x * blockDim.x) {
-        const long long l = L[x], r = R[x];
-        if (l) { table_add(d.table, cap, ((uint64_t)x << 32) | a, -l, st, d.dirty); table_add(d.table, cap, ((uint64_t)x << 32) | z, l, st, d.dirty); L[x] = 0; }
-        if (r) { table_add(d.table, cap, (b << 32) | x, -r, st, d.dirty); table_add(d.table, cap, (z << 32) | x, r, st, d.dirty); R[x] = 0; }
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    if (d.world == 1) {
+        // single rank: only the symbols whose delta became non-zero (listed by k_apply) have to be visited
+        const uint32_t nl = st->n_touch_l, nr = st->n_touch_r;
+        for (uint32_t i = gtid; i < nl; i += gsz) {
+            const uint64_t x = d.touch_l[i]; const long long l = L[x];
+            table_add(d.table, cap, (x << 32) | a, -l, st, d.dirty, d.dirty_list); table_add(d.table, cap, (x << 32) | z, l, st, d.dirty, d.dirty_list);
+            L[x] = 0;
+        }
+        for (uint32_t i = gtid; i < nr; i += gsz) {
+            const uint64_t y = d.touch_r[i]; const long long r = R[y];
+            table_add(d.table, cap, (b << 32) | y, -r, st, d.dirty, d.dirty_list); table_add(d.table, cap, (z << 32) | y, r, st, d.dirty, d.dirty_list);
+            R[y] = 0;
+        }
+    } else {
+        // sharded: the deltas were summed over ranks, the lists are rank-local -> visit every symbol
+        for (uint32_t x = gtid; x < d.vmax; x += gsz) {
+            const long long l = L[x], r = R[x];
+            if (l) { table_add(d.table, cap, ((uint64_t)x << 32) | a, -l, st, d.dirty, d.dirty_list); table_add(d.table, cap, ((uint64_t)x << 32) | z, l, st, d.dirty, d.dirty_list); L[x] = 0; }
+            if (r) { table_add(d.table, cap, (b << 32) | x, -r, st, d.dirty, d.dirty_list); table_add(d.table, cap, (z << 32) | x, r, st, d.dirty, d.dirty_list); R[x] = 0; }
+        }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (gtid == 0) {
         const long long zz = d.delta[2 * (uint64_t)d.vmax], m = d.delta[2 * (uint64_t)d.vmax + 1];
-        if (zz) { table_add(d.table, cap, (b << 32) | a, -zz, st, d.dirty); table_add(d.table, cap, (z << 32) | z, zz, st, d.dirty); }
-        if (m) table_add(d.table, cap, (a << 32) | b, -m, st, d.dirty);
+        if (zz) { table_add(d.table, cap, (b << 32) | a, -zz, st, d.dirty, d.dirty_list); table_add(d.table, cap, (z << 32) | z, zz, st, d.dirty, d.dirty_list); }
+        if (m) table_add(d.table, cap, (a << 32) | b, -m, st, d.dirty, d.dirty_list);
         d.delta[2 * (uint64_t)d.vmax] = 0; d.delta[2 * (uint64_t)d.vmax + 1] = 0;
     }
 }
@@ -418,7 +448,7 @@ __global__ void k_clear_halt(TrainState *st, uint32_t which, uint32_t reset_reco
     if (st->halt == which) st->halt = kRun;
     if (reset_records) st->n_recorded = 0;
 }
-__global__ void k_set_table_cap(TrainState *st, uint64_t cap) { st->table_cap = cap; st->n_entries = 0; }
+__global__ void k_set_table_cap(TrainState *st, uint64_t cap) { st->table_cap = cap; st->n_entries = 0; st->n_dirty = 0; }
 
 }  // namespace swt
 
@@ -451,14 +481,15 @@ static uint64_t char_cap_of(const swt_bpe_train_config *cfg) {
 
 static size_t table_region_bytes(uint64_t cap) {
     const uint64_t n_blk = cap >> kBlkShift;
-    return align_up(cap * sizeof(PairEntry), 256) + align_up(n_blk * sizeof(ArgPart), 256) + align_up(n_blk * sizeof(uint32_t), 256);
+    return align_up(cap * sizeof(PairEntry), 256) + align_up(n_blk * sizeof(ArgPart), 256) + 2 * align_up(n_blk * sizeof(uint32_t), 256);
 }
 static void table_region_carve(void *base, uint64_t cap, TrainDev *d) {
     uint8_t *p = (uint8_t *)base;
     const uint64_t n_blk = cap >> kBlkShift;
     d->table = (PairEntry *)p; p += align_up(cap * sizeof(PairEntry), 256);
     d->blk = (ArgPart *)p; p += align_up(n_blk * sizeof(ArgPart), 256);
-    d->dirty = (uint32_t *)p;
+    d->dirty = (uint32_t *)p; p += align_up(n_blk * sizeof(uint32_t), 256);
+    d->dirty_list = (uint32_t *)p;
 }
 static size_t train_layout(const swt_bpe_train_config *cfg, void *base, TrainDev *d, uint64_t table_cap) {
     Carver cv(base);
@@ -478,6 +509,7 @@ static size_t train_layout(const swt_bpe_train_config *cfg, void *base, TrainDev
     d->worklist = cv.take<uint32_t>(d->n_types + 1);
     d->freq = cv.take<long long>(d->n_types + 1);
     d->delta = cv.take<long long>(2ull * vmax + 2);
+    d->touch_l = cv.take<uint32_t>(vmax); d->touch_r = cv.take<uint32_t>(vmax);
     d->dense = cv.take<long long>((uint64_t)cfg->n_alpha * cfg->n_alpha + 1);
     d->cand = cv.take<uint64_t>(2);
     d->cand_gather = cv.take<uint64_t>(2ull * cfg->world_size);
@@ -524,7 +556,6 @@ SWT_API int swt_bpe_train_create(const swt_bpe_train_config *cfg, const uint32_t
     if (e == cudaSuccess) e = cudaMemsetAsync(d.table, 0, table_region_bytes(t->table_cap), st);
     if (e != cudaSuccess) { delete t; set_error(std::string("memset: ") + cudaGetErrorString(e)); return SWT_ERR_CUDA; }
     k_fill_u64<<<t->grid_scan, 256, 0, st>>>((uint64_t *)d.table, t->table_cap, kEmptyKey, 2);
-    k_fill_u32<<<64, 256, 0, st>>>(d.dirty, t->table_cap >> kBlkShift, 1u);
     k_init_symbols<<<32, 256, 0, st>>>(d, cfg->initial_vocab);
     k_set_table_cap<<<1, 1, 0, st>>>(d.st, t->table_cap);
     k_fill_u32<<<1, 32, 0, st>>>(d.sym + d.n_slots, 8, kHole);
@@ -574,7 +605,7 @@ SWT_API int swt_bpe_train_select(swt_bpe_trainer *t, void *stream) {
     SWT_REQUIRE(t != nullptr, "NULL trainer");
     cudaStream_t st = (cudaStream_t)stream;
     k_argmax_partial<<<t->dev.n_parts, 256, 0, st>>>(t->dev);
-    k_select<<<1, 256, 0, st>>>(t->dev);
+    k_select<<<1, 1024, 0, st>>>(t->dev);
     if (t->dev.n_slots) k_tie_scan<<<t->grid_scan / 2, 256, 0, st>>>(t->dev);
     k_candidate<<<1, 1, 0, st>>>(t->dev);
     SWT_CUDA_OK(cudaGetLastError());
@@ -593,7 +624,7 @@ SWT_API int swt_bpe_train_merge(swt_bpe_trainer *t, void *stream) {
 }
 SWT_API int swt_bpe_train_update(swt_bpe_trainer *t, void *stream) {
     SWT_REQUIRE(t != nullptr, "NULL trainer");
-    const int blocks = (int)std::min<uint64_t>((t->dev.vmax + 255) / 256, 4096);
+    const int blocks = t->cfg.world_size == 1 ? 32 : (int)std::min<uint64_t>((t->dev.vmax + 255) / 256, 4096);
     k_update<<<blocks, 256, 0, (cudaStream_t)stream>>>(t->dev);
     SWT_CUDA_OK(cudaGetLastError());
     return SWT_OK;
@@ -665,7 +696,6 @@ SWT_API int swt_bpe_train_grow_table(swt_bpe_trainer *t, void *d_new_table, uint
     t->table_cap = new_cap;
     if (t->step_graph) { cudaGraphExecDestroy(t->step_graph); t->step_graph = nullptr; }   // kernels captured the old table pointer
     k_fill_u64<<<t->grid_scan, 256, 0, st>>>((uint64_t *)t->dev.table, new_cap, kEmptyKey, 2);
-    k_fill_u32<<<64, 256, 0, st>>>(t->dev.dirty, new_cap >> kBlkShift, 1u);
     k_set_table_cap<<<1, 1, 0, st>>>(t->dev.st, new_cap);
     k_rehash<<<t->grid_scan, 256, 0, st>>>(old_tab, old_cap, t->dev, new_cap);
     k_clear_halt<<<1, 1, 0, st>>>(t->dev.st, kNeedGrow, 0u);

@@ -317,22 +317,54 @@ def run_training_loop(engine, world_size: int = 1, group=None, steps_per_sync: i
         return _training_loop(engine, world_size, group, steps_per_sync, progress, dist)
 
 
+def _one_step_with_collectives(engine, group, dist):
+    engine.select()
+    dist.all_gather_into_tensor(engine.cand_gather, engine.cand, group=group)      # 16-byte tie-break candidates
+    engine.merge()
+    dist.all_reduce(engine.delta, op=dist.ReduceOp.SUM, group=group)               # pair-count deltas L | R | ZZ | M
+    engine.update()
+
+
+STEPS_PER_GRAPH = 16
+
+
+def _capture_steps(engine, group, dist):
+    """Multi-GPU steps are latency-bound by five host calls each; capture a run of steps (kernels + both NCCL
+    collectives) into one CUDA graph so that a replay costs one launch.  Returns None when capture is unavailable."""
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=engine.stream, capture_error_mode="thread_local"):
+            for _ in range(STEPS_PER_GRAPH):
+                _one_step_with_collectives(engine, group, dist)
+        return g
+    except Exception:                                   # noqa: BLE001 - fall back to eager stepping
+        torch.cuda.synchronize()
+        return None
+
+
 def _training_loop(engine, world_size, group, steps_per_sync, progress, dist):
     lefts, rights, news, counts = [], [], [], []
     engine.count_local()
     if world_size > 1:
         dist.all_reduce(engine.init_counts, op=dist.ReduceOp.SUM, group=group)
     engine.build_table()
+    graph = None
+    use_graph = world_size > 1 and getattr(engine, "stream", None) is not None and steps_per_sync >= STEPS_PER_GRAPH
+    if use_graph:
+        _one_step_with_collectives(engine, group, dist)             # eager once: communicators and kernels are warm
+        engine.stream.synchronize()
+        graph = _capture_steps(engine, group, dist)
     while True:
         if world_size == 1:
             engine.steps(steps_per_sync)
         else:
-            for _ in range(steps_per_sync):
-                engine.select()
-                dist.all_gather_into_tensor(engine.cand_gather, engine.cand, group=group)
-                engine.merge()
-                dist.all_reduce(engine.delta, op=dist.ReduceOp.SUM, group=group)
-                engine.update()
+            done = 0
+            if graph is not None:
+                for _ in range(steps_per_sync // STEPS_PER_GRAPH):
+                    graph.replay()
+                    done += STEPS_PER_GRAPH
+            for _ in range(steps_per_sync - done):
+                _one_step_with_collectives(engine, group, dist)
         state, l, r, n, c = engine.read()
         lefts.append(l); rights.append(r); news.append(n); counts.append(c)
         if progress is not None and len(l):
@@ -342,6 +374,8 @@ def _training_loop(engine, world_size, group, steps_per_sync, progress, dist):
             break
         if halt == HALT_GROW:
             engine.grow_table(state["table_cap"])
+            if graph is not None:                                    # the captured kernels hold the old table pointer
+                graph = _capture_steps(engine, group, dist)
         elif halt >= 16:
             raise SwtError("BPE trainer halted with device error %d" % halt)
     cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dtype=dt)
