@@ -2,7 +2,7 @@
 //
 // Data flow of one launch (north-star subsystem 1: packed word-offset/byte arena):
 //
-//   arena bytes + u32 word offsets --(tile = 1024 consecutive words per CTA, 4 consecutive words per thread)-->
+//   arena bytes + u32 word offsets --(tile = 1024 consecutive words per CTA, 2 consecutive words per thread)-->
 //   phase A  per word: look the word up in the word-type memo; on a miss encode it (rank table / trie walk)
 //            and publish the ids; only the token COUNT is kept
 //   scan     CTA exclusive scan of the per-thread counts, then a warp-parallel decoupled look-back over a
@@ -29,8 +29,8 @@
 
 namespace swt {
 
-constexpr int kThreads = 256;
-constexpr int kWordsPerThread = 4;
+constexpr int kThreads = 512;
+constexpr int kWordsPerThread = 2;
 constexpr int kTileWords = kThreads * kWordsPerThread;   // 1024 words per tile
 constexpr int kShortBytes = 32;        // words up to this many bytes are encoded by one thread (and memoised)
 constexpr int kCompactTokens = 8192;   // tile token totals up to this are assembled in smem before the store
@@ -80,6 +80,19 @@ __device__ __forceinline__ void ld_cg_u64x2(const void *p, unsigned long long &a
 __device__ __forceinline__ uint4 ld_cg_u32x4(const void *p) {
     uint4 v;
     asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// L1-cached variants for the FAST path.  Hot word types (Zipf) then hit the 100+ KB L1 instead of going to L2.  This is
+// safe although the memo is written during the launch: a key never changes once set and meta goes 0 -> final exactly
+// once, after the ids of the same sector were written (release); L1 fills are whole 32-byte sectors.  A stale L1 sector can
+// therefore only show "empty" or "not published yet", which sends the word to the slow path, and the slow path re-probes
+// at L2 (ld.cg).  Id sectors beyond the first are only ever read after a valid meta was seen, i.e. after publication.
+__device__ __forceinline__ void ld_ca_u64x2(const void *p, unsigned long long &a, unsigned long long &b) {
+    asm volatile("ld.global.ca.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ uint4 ld_ca_u32x4(const void *p) {
+    uint4 v;
+    asm volatile("ld.global.ca.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 // meta is read with a STRONG RELAXED load served at L2, not an acquire: ld.acquire.gpu compiles to LDG + CCTL.IVALL
@@ -171,15 +184,16 @@ __device__ __forceinline__ bool memo_publish(const EncodeWorkspace &ws, uint32_t
 }
 
 // ---- warp-parallel decoupled look-back: all 32 lanes of one warp call this -----------------------------------------
-// Publishes the tile's aggregate, then inspects 32 predecessors per step until a tile with a published inclusive
-// prefix is found.  Returns (in every lane) the exclusive prefix of `tile`.
+// The aggregate is published first; later one warp inspects 32 predecessors per step until a tile with a published
+// inclusive prefix is found and returns (in every lane) the exclusive prefix of `tile`.
+// step 1 (one thread, right after the CTA scan): make the tile's aggregate visible to later tiles at once
+__device__ __forceinline__ void tile_publish_aggregate(uint64_t *tile_state, uint32_t tile, uint64_t aggregate) {
+    st_relaxed_u64(&tile_state[tile], ((tile == 0 ? kTilePrefix : kTileAggregate) << 62) | aggregate);
+}
+// step 2 (all 32 lanes of one warp, any time later): look back, publish the inclusive prefix, return the exclusive one
 __device__ __forceinline__ uint64_t tile_prefix_warp(uint64_t *tile_state, uint32_t tile, uint64_t aggregate, uint32_t *err) {
     const uint32_t lane = threadIdx.x & 31;
-    if (tile == 0) {
-        if (lane == 0) st_relaxed_u64(&tile_state[0], (kTilePrefix << 62) | aggregate);
-        return 0;
-    }
-    if (lane == 0) st_relaxed_u64(&tile_state[tile], (kTileAggregate << 62) | aggregate);
+    if (tile == 0) return 0;
     uint64_t running = 0;
     int64_t p = (int64_t)tile - 1;                  // lane l looks at tile p - l
     uint32_t spins = 0;
@@ -252,6 +266,27 @@ __device__ __noinline__ uint32_t emit_slow(const Enc &enc, const EncodeWorkspace
     return h6;
 }
 
+// ids of a memo hit -> dst (ids 0-1 arrived with the probe, 2-9 were prefetched, the rest is fetched here)
+__device__ __forceinline__ void store_hit_ids(uint32_t *dst, uint32_t n, uint2 t01, uint4 c0, uint4 c1, const MemoEntry *e) {
+    if (n > 0) dst[0] = t01.x;
+    if (n > 1) dst[1] = t01.y;
+    if (n > 2) dst[2] = c0.x;
+    if (n > 3) dst[3] = c0.y;
+    if (n > 4) dst[4] = c0.z;
+    if (n > 5) dst[5] = c0.w;
+    if (n > 6) dst[6] = c1.x;
+    if (n > 7) dst[7] = c1.y;
+    if (n > 8) dst[8] = c1.z;
+    if (n > 9) dst[9] = c1.w;
+    for (uint32_t k0 = 8; k0 + 2 < n; k0 += 4) {
+        const uint4 v = ld_ca_u32x4(&e->tok[k0]);
+        dst[k0 + 2] = v.x;
+        if (k0 + 3 < n) dst[k0 + 3] = v.y;
+        if (k0 + 4 < n) dst[k0 + 4] = v.z;
+        if (k0 + 5 < n) dst[k0 + 5] = v.w;
+    }
+}
+
 // ---- the tile kernel ---------------------------------------------------------------------------------------------------
 // Enc provides
 //   uint32_t encode_short(const uint8_t *p, uint32_t nbytes, uint32_t *buf /*thread-local, kShortBytes*/, uint32_t &h6) const
@@ -259,7 +294,7 @@ __device__ __noinline__ uint32_t emit_slow(const Enc &enc, const EncodeWorkspace
 //   kCoopLong == false:  uint32_t long_count(p, nbytes) const;  void long_emit(p, nbytes, uint32_t *dst, uint32_t cap, uint32_t &h6) const
 //   kCoopLong == true :  uint32_t encode_long_coop(p, nbytes, bufA, bufB, uint32_t **result, uint32_t *sh_scan, uint32_t *sh_misc) const
 template <class Enc>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 2)
 encode_tiles_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words,
                     uint32_t *__restrict__ out_ids, uint64_t out_cap, uint32_t *__restrict__ out_tok_off, uint32_t tok_base,
                     EncodeWorkspace ws, uint32_t *status) {
@@ -272,6 +307,8 @@ encode_tiles_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
     uint32_t h6 = 0;
     uint32_t buf[kShortBytes];                              // thread-local scratch for one directly encoded word
 
+    // Tiles are handed out by an atomic ticket: a tile only starts once a CTA is free to run it, so every predecessor
+    // of a running tile is itself running or finished and the look-back cannot deadlock.
     // Tiles are handed out by an atomic ticket: a tile only starts once a CTA is free to run it, so every predecessor
     // of a running tile is itself running or finished and the look-back cannot deadlock.
     uint32_t next_ticket = 0;
@@ -328,8 +365,8 @@ encode_tiles_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
                     hi |= (unsigned long long)nb[j] << 56;
                     slot[j] = (uint32_t)mix64(lo ^ (hi * 0x9E3779B97F4A7C15ull)) & ws.memo_mask;
                     const MemoEntry *e = ws.memo + slot[j];
-                    ld_cg_u64x2(e, elo, ehi);
-                    mt[j] = ld_cg_u32x4(&e->meta);
+                    ld_ca_u64x2(e, elo, ehi);
+                    mt[j] = ld_ca_u32x4(&e->meta);
                     klo[j] = lo ^ elo; khi[j] = hi ^ ehi;                            // zero iff the entry holds this word
                 }
             }
@@ -378,12 +415,14 @@ encode_tiles_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
             }
         }
 
-        // ---- scan; warp 0 then runs the look-back while the other warps already assemble the tile's ids in smem
+        // ---- scan.  The look-back (warp 0) mostly WAITS for earlier tiles, so it runs after warp 0 has assembled its
+        // own share of the tile's ids in shared memory; only an oversized tile (rare) needs the base first.
         uint32_t total, excl = block_exclusive_scan(count, sm.scan, &total);
-        if (tid < 32) { const uint64_t b = tile_prefix_warp(ws.tile_state, tile, total, &status[kStatusCode]); if (tid == 0) sm.base = b; }
+        if (tid == 0) tile_publish_aggregate(ws.tile_state, tile, total);
         const bool use_compact = total <= (uint32_t)kCompactTokens;
         uint64_t base = 0; bool fits_out = true;
-        if (!use_compact) {                       // oversized tile (rare): ids go straight to global memory, base needed now
+        if (!use_compact) {
+            if (tid < 32) { const uint64_t b = tile_prefix_warp(ws.tile_state, tile, total, &status[kStatusCode]); if (tid == 0) sm.base = b; }
             __syncthreads();
             base = sm.base; fits_out = base + total <= out_cap;
         }
@@ -403,54 +442,42 @@ encode_tiles_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
                 c0[j] = c1[j] = make_uint4(0, 0, 0, 0);
                 if (kind[j] == kWordHit && ntok[j] > 2) {
                     const MemoEntry *e = ws.memo + slot[j];
-                    c0[j] = ld_cg_u32x4(&e->tok[0]);
-                    if (ntok[j] > 6) c1[j] = ld_cg_u32x4(&e->tok[4]);
+                    c0[j] = ld_ca_u32x4(&e->tok[0]);
+                    if (ntok[j] > 6) c1[j] = ld_ca_u32x4(&e->tok[4]);
                 }
             }
 #pragma unroll
             for (int j = 0; j < kWordsPerThread; ++j) {
                 if (kind[j] == kWordNone) continue;
-                uint32_t *dst = use_compact ? sm.compact + run[j] : out_ids + base + run[j];
                 if (kind[j] == kWordHit) {
-                    const uint32_t n = ntok[j];
-                    if (n > 0) dst[0] = t01[j].x;
-                    if (n > 1) dst[1] = t01[j].y;
-                    if (n > 2) dst[2] = c0[j].x;
-                    if (n > 3) dst[3] = c0[j].y;
-                    if (n > 4) dst[4] = c0[j].z;
-                    if (n > 5) dst[5] = c0[j].w;
-                    if (n > 6) dst[6] = c1[j].x;
-                    if (n > 7) dst[7] = c1[j].y;
-                    if (n > 8) dst[8] = c1[j].z;
-                    if (n > 9) dst[9] = c1[j].w;
-                    if (n > 10) {
-                        const MemoEntry *e = ws.memo + slot[j];
-                        for (uint32_t k0 = 8; k0 + 2 < n; k0 += 4) {
-                            const uint4 v = ld_cg_u32x4(&e->tok[k0]);
-                            dst[k0 + 2] = v.x;
-                            if (k0 + 3 < n) dst[k0 + 3] = v.y;
-                            if (k0 + 4 < n) dst[k0 + 4] = v.z;
-                            if (k0 + 5 < n) dst[k0 + 5] = v.w;
-                        }
-                    }
-                } else h6 += emit_slow(enc, ws, arena + b0s[j], nb[j], kind[j], ntok[j], slot[j], buf, dst);
+                    // two copies of the same code so that the common case compiles to shared-memory stores (STS)
+                    if (use_compact) store_hit_ids(sm.compact + run[j], ntok[j], t01[j], c0[j], c1[j], ws.memo + slot[j]);
+                    else store_hit_ids(out_ids + base + run[j], ntok[j], t01[j], c0[j], c1[j], ws.memo + slot[j]);
+                } else {
+                    uint32_t *dst = use_compact ? sm.compact + run[j] : out_ids + base + run[j];
+                    h6 += emit_slow(enc, ws, arena + b0s[j], nb[j], kind[j], ntok[j], slot[j], buf, dst);
+                }
             }
         }
+        if (use_compact && tid < 32) { const uint64_t b = tile_prefix_warp(ws.tile_state, tile, total, &status[kStatusCode]); if (tid == 0) sm.base = b; }
         __syncthreads();
         if (use_compact) { base = sm.base; fits_out = base + total <= out_cap; }
         if (!fits_out && tid == 0) atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY);
         if (out_tok_off) {
             const uint32_t i0 = tid * kWordsPerThread;
             const uint32_t o0 = tok_base + (uint32_t)base;
-            if (tok_off_vec && i0 + kWordsPerThread <= tile_words)
-                *reinterpret_cast<uint4 *>(out_tok_off + w_tile + i0) = make_uint4(o0 + run[0], o0 + run[1], o0 + run[2], o0 + run[3]);
-            else {
+            if (tok_off_vec && i0 + kWordsPerThread <= tile_words) {
+                if constexpr (kWordsPerThread == 4)
+                    *reinterpret_cast<uint4 *>(out_tok_off + w_tile + i0) = make_uint4(o0 + run[0], o0 + run[1], o0 + run[2 % kWordsPerThread], o0 + run[3 % kWordsPerThread]);
+                else
+                    *reinterpret_cast<uint2 *>(out_tok_off + w_tile + i0) = make_uint2(o0 + run[0], o0 + run[1]);
+            } else {
 #pragma unroll
                 for (int j = 0; j < kWordsPerThread; ++j) if (i0 + j < tile_words) out_tok_off[w_tile + i0 + j] = o0 + run[j];
             }
         }
         // take the next ticket now so that its latency hides behind the store of this tile.  (It must not be taken any
-        // earlier: a tile that holds a ticket without running delays the look-back of every later tile.)
+        // earlier: a tile that holds a ticket without running delays the look-back of every later tile -- measured.)
         if (tid == 0) next_ticket = atomicAdd(ws.ticket, 1u);
         if (use_compact && fits_out) {
             // coalesced store: scalar head up to 16-byte alignment of the destination, then 128-bit stores
