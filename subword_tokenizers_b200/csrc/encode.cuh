@@ -36,6 +36,7 @@ constexpr int kShortBytes = 32;        // words up to this many bytes are encode
 constexpr int kCompactTokens = 8192;   // tile token totals up to this are assembled in smem before the store
 constexpr int kMemoTokens = 54;        // >= kShortBytes: every word of up to 32 bytes fits (ids <= bytes)
 constexpr int kMemoProbes = 8;
+constexpr int kSlowCap = 512;          // per tile: words resolved by the dense slow pass (more are resolved inline)
 
 // status words written by the encode kernels
 enum { kStatusCode = 0, kStatusTokens = 1, kStatusH6 = 2, kStatusTokensHi = 3, kStatusMemoTypes = 4 };
@@ -222,7 +223,7 @@ __device__ __forceinline__ uint64_t tile_prefix_warp(uint64_t *tile_state, uint3
 }
 
 // per-word bookkeeping between phase A and phase B
-enum : uint32_t { kWordNone = 0u, kWordHit = 1u, kWordRecompute = 2u, kWordLong = 3u, kWordLongB = 4u };
+enum : uint32_t { kWordNone = 0u, kWordHit = 1u, kWordRecompute = 2u, kWordLong = 3u, kWordLongB = 4u, kWordPending = 5u };
 
 struct TileSmem {                         // dynamic shared memory of the tile kernel (37 KB)
     uint32_t compact[kCompactTokens];     // the tile's ids in output order
@@ -230,6 +231,9 @@ struct TileSmem {                         // dynamic shared memory of the tile k
     uint32_t scan[36];
     uint32_t misc[8];
     uint64_t base;
+    uint32_t n_slow;                      // words of this tile that missed the fast path ...
+    uint32_t slow_list[kSlowCap];         // ... their tile-local index ...
+    uint32_t slow_res[kSlowCap][4];       // ... and, once resolved by a dense pass, {kind | ntok << 8, slot, id0, id1}
 };
 
 // phase A slow path (first probe did not hit): full probe, then direct encode + publish.  Kept out of line so
@@ -314,7 +318,7 @@ encode_tiles_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
     uint32_t next_ticket = 0;
     if (tid == 0) next_ticket = atomicAdd(ws.ticket, 1u);
     for (;;) {
-        if (tid == 0) sm.misc[4] = next_ticket;
+        if (tid == 0) { sm.misc[4] = next_ticket; sm.n_slow = 0; }
         __syncthreads();
         const uint32_t tile = sm.misc[4];
         if (tile >= ws.n_tiles) break;
@@ -380,8 +384,34 @@ encode_tiles_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
             } else if ((klo[j] | khi[j]) == 0 && mt[j].x != 0 && mt[j].x != 0xFFFFFFFFu) {
                 kind[j] = kWordHit; ntok[j] = (mt[j].x & 0xFFu) - 1; h6 += mt[j].x >> 8; t01[j] = make_uint2(mt[j].z, mt[j].w);
             } else {
-                const SlowResult r = resolve_slow(enc, ws, arena, b0s[j], nb[j], arena_end, buf, status);
-                kind[j] = r.kind; ntok[j] = r.ntok; slot[j] = r.slot; t01[j] = r.t01; h6 += r.h6;
+                // not served by the first probe (longer than 15 bytes, hash collision, first occurrence): defer to the
+                // dense pass below so that these few words do not serialise whole warps one lane at a time
+                const uint32_t q = atomicAdd(&sm.n_slow, 1u);
+                if (q < (uint32_t)kSlowCap) { sm.slow_list[q] = tid * kWordsPerThread + j; kind[j] = kWordPending; slot[j] = q; }
+                else {
+                    const SlowResult r = resolve_slow(enc, ws, arena, b0s[j], nb[j], arena_end, buf, status);
+                    kind[j] = r.kind; ntok[j] = r.ntok; slot[j] = r.slot; t01[j] = r.t01; h6 += r.h6;
+                }
+            }
+        }
+        __syncthreads();
+        {
+            const uint32_t n_slow = min(sm.n_slow, (uint32_t)kSlowCap);
+            for (uint32_t q = tid; q < n_slow; q += kThreads) {                      // one deferred word per thread, lanes dense
+                const uint32_t i = sm.slow_list[q];
+                const uint32_t b0 = sm.off[i];
+                const SlowResult r = resolve_slow(enc, ws, arena, b0, sm.off[i + 1] - b0, arena_end, buf, status);
+                h6 += r.h6;
+                sm.slow_res[q][0] = r.kind | (r.ntok << 8); sm.slow_res[q][1] = r.slot; sm.slow_res[q][2] = r.t01.x; sm.slow_res[q][3] = r.t01.y;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kWordsPerThread; ++j) {
+            if (kind[j] == kWordPending) {
+                const uint32_t q = slot[j];
+                const uint32_t kn = sm.slow_res[q][0];
+                kind[j] = kn & 0xFFu; ntok[j] = kn >> 8; slot[j] = sm.slow_res[q][1]; t01[j] = make_uint2(sm.slow_res[q][2], sm.slow_res[q][3]);
             }
             count += ntok[j];
         }
