@@ -12,8 +12,6 @@ size_t encode_workspace_layout(uint32_t n_words, uint64_t long_bytes, void *base
     Carver cv(base);
     const uint32_t n_tiles = (n_words + kTileWords - 1) / kTileWords;
     ws->n_tiles = n_tiles;
-    ws->tile_state = cv.take<uint64_t>(n_tiles + 1);
-    ws->ticket = cv.take<uint32_t>(1);
     ws->long_cursor = cv.take<unsigned long long>(1);
     // word-type memo: rebuilt from empty by every launch; sized with the batch, at most 2^20 entries (256 MB)
     uint64_t slots = next_pow2(std::max<uint64_t>(n_words / 4, 1024));
@@ -21,7 +19,11 @@ size_t encode_workspace_layout(uint32_t n_words, uint64_t long_bytes, void *base
     ws->memo = cv.take<MemoEntry>(slots);
     ws->memo_mask = (uint32_t)(slots - 1);
     ws->zero_bytes = cv.used();
-    ws->long_scratch_elems = 2 * long_bytes;
+    ws->packed = cv.take<uint32_t>((size_t)n_words + 2);
+    ws->tile_total = cv.take<uint32_t>((size_t)n_tiles + 1);
+    ws->group_base = cv.take<unsigned long long>((size_t)n_tiles / 1024 + 2);
+    // BPE long words: 16-word header + two symbol buffers each, allocated in 16-word granules
+    ws->long_scratch_elems = long_bytes ? 2 * long_bytes + 32 * (long_bytes / 33 + 1) : 0;
     ws->long_scratch = cv.take<uint32_t>(ws->long_scratch_elems + 1);
     return cv.used();
 }

@@ -7,7 +7,7 @@
 // Kernel: see encode.cuh for the tile kernel and the word-type memo.  Per directly encoded word (one thread,
 // symbols in a thread-local buffer): repeat { min rank over the adjacent pairs (bpe.py:212-217); greedy left-to-right
 // replacement of every occurrence (:221-235) } until no ranked pair is left or one symbol remains.
-// Words longer than kShortBytes are processed by the whole CTA in global scratch.
+// Words longer than kShortBytes are processed by a whole warp in global scratch.
 #include <vector>
 
 #include "encode.cuh"
@@ -91,41 +91,43 @@ __device__ __forceinline__ uint32_t bpe_encode_short(const BpeTableDev &t, const
     return n;
 }
 
-// ---- long words: the whole CTA works on one word in global scratch ------------------------------------
-// src/dst are ping-pong symbol buffers of at least nbytes entries. Returns the final symbol count;
-// *result points at the buffer holding the final symbols (already shifted into token form).
-__device__ uint32_t bpe_encode_long(const BpeTableDev &t, const uint8_t *p, uint32_t nbytes, uint32_t *bufA,
-                                    uint32_t *bufB, uint32_t **result, uint32_t *sh_scan /*33*/, uint32_t *sh_misc /*8*/) {
-    const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    // 1. UTF-8 decode in chunks of blockDim bytes: a byte starts a character unless it is 10xxxxxx
+// ---- long words: one WARP works on the word in global scratch ----------------------------------------------------------
+// bufA/bufB are ping-pong symbol buffers of at least nbytes entries.  Returns the final symbol count; *result points
+// at the buffer holding the final symbols (already in token form).  All 32 lanes must call this.
+__device__ __noinline__ uint32_t bpe_encode_long_warp(const BpeTableDev &t, const uint8_t *p, uint32_t nbytes, uint32_t *bufA,
+                                                      uint32_t *bufB, uint32_t **result) {
+    const uint32_t lane = threadIdx.x & 31;
+    auto warp_excl_scan = [&](uint32_t v, uint32_t &total) {
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += u; }
+        total = __shfl_sync(0xffffffffu, incl, 31);
+        return incl - v;
+    };
+    // 1. UTF-8 decode, 32 bytes at a time: a byte starts a character unless it is 10xxxxxx
     uint32_t n = 0;
-    for (uint32_t base = 0; base < nbytes; base += nt) {
-        uint32_t i = base + tid;
-        uint32_t is_start = (i < nbytes) && ((p[i] & 0xC0u) != 0x80u);
-        uint32_t total, excl = block_exclusive_scan(is_start, sh_scan, &total);
-        if (is_start) { uint32_t adv; uint32_t cp = utf8_decode(p + i, nbytes - i, adv); bufA[n + excl] = bpe_char_symbol(t, cp); }
+    for (uint32_t base = 0; base < nbytes; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t is_start = (i < nbytes) && ((p[i] & 0xC0u) != 0x80u);
+        uint32_t total; const uint32_t excl = warp_excl_scan(is_start, total);
+        if (is_start) { uint32_t adv; const uint32_t cp = utf8_decode(p + i, nbytes - i, adv); bufA[n + excl] = bpe_char_symbol(t, cp); }
         n += total;
     }
-    __syncthreads();
+    __syncwarp();
     uint32_t *src = bufA, *dst = bufB;
     while (n >= 2) {
-        // 2. min rank over all adjacent pairs
+        // 2. min rank over all adjacent pairs (bpe.py:212-217)
         uint32_t best = kEmptyRank;
-        for (uint32_t i = tid; i + 1 < n; i += nt) { uint32_t z; uint32_t r = bpe_probe(t, src[i], src[i + 1], z); best = min(best, r); }
+        for (uint32_t i = lane; i + 1 < n; i += 32) { uint32_t z; const uint32_t r = bpe_probe(t, src[i], src[i + 1], z); best = min(best, r); }
+#pragma unroll
         for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
-        if ((tid & 31) == 0) sh_scan[tid >> 5] = best;
-        __syncthreads();
-        if (tid == 0) { uint32_t b = kEmptyRank; for (uint32_t w = 0; w < (nt >> 5); ++w) b = min(b, sh_scan[w]); sh_misc[0] = b; }
-        __syncthreads();
-        best = sh_misc[0];
-        __syncthreads();
         if (best == kEmptyRank) break;
         const uint32_t a = __ldg(&t.m_left[best]), b = __ldg(&t.m_right[best]), z = __ldg(&t.m_new[best]);
-        // 3. greedy left-to-right replacement; each thread owns one contiguous segment
-        const uint32_t seg = (n + nt - 1) / nt;
-        const uint32_t lo = min(n, tid * seg), hi = min(n, lo + seg);
-        // is element `lo` the right half of a pair selected by an earlier segment?  For a != b
-        // matches cannot overlap; for a == b walk back over the run of a's to get the parity.
+        // 3. greedy left-to-right replacement (bpe.py:221-235); each lane owns one contiguous segment
+        const uint32_t seg = (n + 31) / 32;
+        const uint32_t lo = min(n, lane * seg), hi = min(n, lo + seg);
+        // is element `lo` the right half of a pair selected by an earlier segment?  For a != b matches cannot overlap;
+        // for a == b walk back over the run of a's to get the parity.
         uint32_t i = lo;
         if (lo < hi && lo > 0) {
             if (a != b) { if (src[lo - 1] == a && src[lo] == b) i = lo + 1; }
@@ -137,32 +139,32 @@ __device__ uint32_t bpe_encode_long(const BpeTableDev &t, const uint8_t *p, uint
         const uint32_t first = i;
         uint32_t cnt = 0;
         while (i < hi) { if (i + 1 < n && src[i] == a && src[i + 1] == b) i += 2; else i += 1; ++cnt; }
-        uint32_t total, excl = block_exclusive_scan(cnt, sh_scan, &total);
+        uint32_t total; const uint32_t excl = warp_excl_scan(cnt, total);
         i = first; uint32_t o = excl;
         while (i < hi) {
             if (i + 1 < n && src[i] == a && src[i + 1] == b) { dst[o++] = z; i += 2; }
             else { dst[o++] = src[i]; i += 1; }
         }
-        __syncthreads();
+        __syncwarp();
         n = total;
         uint32_t *tmp = src; src = dst; dst = tmp;
     }
-    for (uint32_t k = tid; k < n; k += nt) src[k] = (src[k] << 1) | (k > 0);
-    __syncthreads();
+    for (uint32_t k = lane; k < n; k += 32) src[k] = (src[k] << 1) | (k > 0);
+    __syncwarp();
     *result = src;
     return n;
 }
 
 struct BpeEnc {
     BpeTableDev t;
-    static constexpr bool kCoopLong = true;
+    static constexpr bool kScratchLong = true;
     __device__ __forceinline__ uint32_t encode_short(const uint8_t *p, uint32_t nbytes, uint32_t *buf, uint32_t &h6) const {
         (void)h6;
         return bpe_encode_short(t, p, nbytes, buf);
     }
-    __device__ __forceinline__ uint32_t encode_long_coop(const uint8_t *p, uint32_t nbytes, uint32_t *bufA, uint32_t *bufB,
-                                                         uint32_t **result, uint32_t *sh_scan, uint32_t *sh_misc) const {
-        return bpe_encode_long(t, p, nbytes, bufA, bufB, result, sh_scan, sh_misc);
+    __device__ __forceinline__ uint32_t encode_long_warp(const uint8_t *p, uint32_t nbytes, uint32_t *bufA, uint32_t *bufB,
+                                                         uint32_t **result) const {
+        return bpe_encode_long_warp(t, p, nbytes, bufA, bufB, result);
     }
 };
 

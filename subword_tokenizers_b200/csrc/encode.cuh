@@ -1,17 +1,19 @@
 // encode.cuh -- the tile kernel shared by the two tokenize paths (HP-1 FastBPE, HP-2 FastWP).
 //
-// Data flow of one launch (north-star subsystem 1: packed word-offset/byte arena):
+// Data flow of one encode call (north-star subsystem 1: packed word-offset/byte arena).  Tile = 64 consecutive words per
+// WARP (2 per lane), tiles assigned round-robin to a persistent grid; warps never synchronise with each other.
 //
-//   arena bytes + u32 word offsets --(tile = 1024 consecutive words per CTA, 2 consecutive words per thread)-->
-//   phase A  per word: look the word up in the word-type memo; on a miss encode it (rank table / trie walk)
-//            and publish the ids; only the token COUNT is kept
-//   scan     CTA exclusive scan of the per-thread counts, then a warp-parallel decoupled look-back over a
-//            64-bit tile-state array gives the tile's global token offset (single pass, no second kernel)
-//   phase B  per word: copy the ids (memo entry -> shared memory) at their tile-local position
-//   store    the tile's ids leave shared memory with fully coalesced writes; u32 token offsets go out as 16 B stores
+//   pass 1  encode_count_kernel   per word: look the word up in the word-type memo; on a miss encode it (rank table /
+//                                 trie walk) and publish the ids.  Writes one packed u32 record per word (kind, token
+//                                 count, memo slot) and the tile's token total.
+//   scan    two tiny kernels      exclusive scan of the tile totals (in-group prefixes + group bases)
+//   pass 2  encode_emit_kernel    per word: copy the ids memo entry -> the warp's shared-memory buffer at their tile-local
+//                                 position; the tile's ids leave shared memory as 128-bit coalesced stores at their final
+//                                 position, u32 token offsets as 8-byte stores.
 //
-// The grid is persistent (kNumSMs x resident CTAs); tiles are handed out by an atomic ticket, so the look-back
-// never waits on a tile that has not started.
+// An earlier single-pass version (decoupled look-back over tile states) was measured slower: with warp-sized tiles
+// the look-back walked hundreds of in-flight predecessors, with CTA-sized tiles the CTA barriers serialised the L2
+// latencies.  The two passes cost 8 extra bytes of HBM traffic per word and have no inter-tile dependency at all.
 //
 // Word-type memo: encode_word is a pure function of the word and word streams are
 // Zipf-distributed, so every launch keeps a hash table  word bytes -> token ids  in its workspace.  The first
@@ -29,14 +31,15 @@
 
 namespace swt {
 
-constexpr int kThreads = 512;
+constexpr int kWarps = 8;              // warps per CTA; every warp owns its own tile
+constexpr int kThreads = kWarps * 32;
+constexpr int kCtasPerSm = 4;
 constexpr int kWordsPerThread = 2;
-constexpr int kTileWords = kThreads * kWordsPerThread;   // 1024 words per tile
+constexpr int kTileWords = 32 * kWordsPerThread;         // 64 words per (warp) tile
 constexpr int kShortBytes = 32;        // words up to this many bytes are encoded by one thread (and memoised)
-constexpr int kCompactTokens = 8192;   // tile token totals up to this are assembled in smem before the store
+constexpr int kCompactTokens = 1024;   // tile token totals up to this are assembled in smem before the store
 constexpr int kMemoTokens = 54;        // >= kShortBytes: every word of up to 32 bytes fits (ids <= bytes)
 constexpr int kMemoProbes = 8;
-constexpr int kSlowCap = 512;          // per tile: words resolved by the dense slow pass (more are resolved inline)
 
 // status words written by the encode kernels
 enum { kStatusCode = 0, kStatusTokens = 1, kStatusH6 = 2, kStatusTokensHi = 3, kStatusMemoTypes = 4 };
@@ -52,11 +55,12 @@ struct alignas(256) MemoEntry {         // 256 bytes; a typical hit touches the 
 struct MemoKey { unsigned long long lo, hi, tail_a, tail_b; uint32_t tail_last; uint32_t nbytes; };
 
 struct EncodeWorkspace {
-    uint64_t *tile_state;            // n_tiles
-    uint32_t *ticket;                // 1
     unsigned long long *long_cursor; // 1 (BPE: allocation cursor into long_scratch, in u32 units)
     MemoEntry *memo; uint32_t memo_mask;   // memo_mask == 0: memo disabled
-    uint32_t *long_scratch;          // 2 x long bytes (BPE symbol ping-pong buffers for long words)
+    uint32_t *packed;                // n_words: per-word record handed from the count pass to the emit pass
+    uint32_t *tile_total;            // n_tiles: tokens per tile, then (after the scan) the in-group exclusive prefix
+    unsigned long long *group_base;  // n_groups: tokens per group of 1024 tiles, then the group's global token offset
+    uint32_t *long_scratch;          // BPE symbol ping-pong buffers for long words
     uint64_t long_scratch_elems;
     uint32_t n_tiles;
     size_t zero_bytes;               // prefix of the workspace that must be zeroed before a launch
@@ -94,6 +98,11 @@ __device__ __forceinline__ void ld_ca_u64x2(const void *p, unsigned long long &a
 __device__ __forceinline__ uint4 ld_ca_u32x4(const void *p) {
     uint4 v;
     asm volatile("ld.global.ca.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_ca_u32(const void *p) {
+    uint32_t v;
+    asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 // meta is read with a STRONG RELAXED load served at L2, not an acquire: ld.acquire.gpu compiles to LDG + CCTL.IVALL
@@ -184,96 +193,46 @@ __device__ __forceinline__ bool memo_publish(const EncodeWorkspace &ws, uint32_t
     return true;
 }
 
-// ---- warp-parallel decoupled look-back: all 32 lanes of one warp call this -----------------------------------------
-// The aggregate is published first; later one warp inspects 32 predecessors per step until a tile with a published
-// inclusive prefix is found and returns (in every lane) the exclusive prefix of `tile`.
-// step 1 (one thread, right after the CTA scan): make the tile's aggregate visible to later tiles at once
-__device__ __forceinline__ void tile_publish_aggregate(uint64_t *tile_state, uint32_t tile, uint64_t aggregate) {
-    st_relaxed_u64(&tile_state[tile], ((tile == 0 ? kTilePrefix : kTileAggregate) << 62) | aggregate);
-}
-// step 2 (all 32 lanes of one warp, any time later): look back, publish the inclusive prefix, return the exclusive one
-__device__ __forceinline__ uint64_t tile_prefix_warp(uint64_t *tile_state, uint32_t tile, uint64_t aggregate, uint32_t *err) {
-    const uint32_t lane = threadIdx.x & 31;
-    if (tile == 0) return 0;
-    uint64_t running = 0;
-    int64_t p = (int64_t)tile - 1;                  // lane l looks at tile p - l
-    uint32_t spins = 0;
-    for (;;) {
-        const int64_t idx = p - (int64_t)lane;
-        const uint64_t s = idx >= 0 ? ld_relaxed_u64(&tile_state[idx]) : (kTilePrefix << 62);   // before tile 0: prefix 0
-        const uint64_t st = s >> 62;
-        const uint32_t inv = __ballot_sync(0xffffffffu, st == kTileInvalid);
-        const uint32_t pre = __ballot_sync(0xffffffffu, st == kTilePrefix);
-        const uint32_t first_pre = pre ? (uint32_t)__ffs(pre) - 1 : 32u;
-        const uint32_t first_inv = inv ? (uint32_t)__ffs(inv) - 1 : 32u;
-        if (first_inv < first_pre) {                                        // a needed predecessor is not there yet
-            if (++spins > (1u << 24)) { if (lane == 0) atomicExch(err, (uint32_t)SWT_ERR_INTERNAL); break; }   // never hang
-            __nanosleep(40);
-            continue;
-        }
-        uint64_t v = lane <= first_pre ? (s & kTileValueMask) : 0ull;      // aggregates up to and including the prefix tile
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        running += v;
-        if (first_pre < 32u) break;
-        p -= 32;
-    }
-    if (lane == 0) st_relaxed_u64(&tile_state[tile], (kTilePrefix << 62) | ((running + aggregate) & kTileValueMask));
-    return running;
-}
+// per-word record between the two passes, packed into 32 bits:
+//   [31:29] kind; Hit: [28:23] n_tokens, [19:0] memo slot; Recompute: [28:23] n_tokens;
+//   WP long: [28:0] n_tokens; BPE long: [28:0] scratch granule (16 u32) -- header word 0 holds n_tokens
+enum : uint32_t { kWordNone = 0u, kWordHit = 1u, kWordRecompute = 2u, kWordLong = 3u, kWordLongB = 4u };
+constexpr uint32_t kLongHeader = 16;      // u32 words reserved in front of the two scratch buffers of a long BPE word
+constexpr uint32_t kGroupTiles = 1024;    // tiles per scan group
 
-// per-word bookkeeping between phase A and phase B
-enum : uint32_t { kWordNone = 0u, kWordHit = 1u, kWordRecompute = 2u, kWordLong = 3u, kWordLongB = 4u, kWordPending = 5u };
+struct SlowResult { uint32_t kind, ntok, slot, h6; };
 
-struct TileSmem {                         // dynamic shared memory of the tile kernel (37 KB)
-    uint32_t compact[kCompactTokens];     // the tile's ids in output order
-    uint32_t off[kTileWords + 4];         // the tile's word offsets
-    uint32_t scan[36];
-    uint32_t misc[8];
-    uint64_t base;
-    uint32_t n_slow;                      // words of this tile that missed the fast path ...
-    uint32_t slow_list[kSlowCap];         // ... their tile-local index ...
-    uint32_t slow_res[kSlowCap][4];       // ... and, once resolved by a dense pass, {kind | ntok << 8, slot, id0, id1}
-};
-
-// phase A slow path (first probe did not hit): full probe, then direct encode + publish.  Kept out of line so
-// that the 4x unrolled fast path stays small.
-struct SlowResult { uint32_t kind, ntok, slot, h6; uint2 t01; };
+// pass 1 slow path (first probe did not hit): full probe at L2, then direct encode + publish.  Out of line so that
+// the unrolled fast path stays small.
 template <class Enc>
 __device__ __noinline__ SlowResult resolve_slow(const Enc &enc, const EncodeWorkspace &ws, const uint8_t *arena, uint32_t b0,
                                                 uint32_t nbytes, uint32_t arena_end, uint32_t *buf, uint32_t *status) {
-    SlowResult r; r.kind = kWordRecompute; r.ntok = 0; r.slot = 0; r.h6 = 0; r.t01 = make_uint2(0, 0);
-    int m = kMemoMiss; uint32_t meta = 0; MemoKey key;
-    if (ws.memo_mask && nbytes >= 1) { memo_key(arena, b0, nbytes, arena_end, key); m = memo_probe(ws, key, r.slot, meta, r.t01); }
+    SlowResult r; r.kind = kWordRecompute; r.ntok = 0; r.slot = 0; r.h6 = 0;
+    int m = kMemoMiss; uint32_t meta = 0; MemoKey key; uint2 t01;
+    if (ws.memo_mask && nbytes >= 1) { memo_key(arena, b0, nbytes, arena_end, key); m = memo_probe(ws, key, r.slot, meta, t01); }
     if (m == kMemoHit) { r.kind = kWordHit; r.ntok = (meta & 0xFFu) - 1; r.h6 = meta >> 8; return r; }
     r.ntok = enc.encode_short(arena + b0, nbytes, buf, r.h6);
-    if (m == kMemoClaimed && memo_publish(ws, r.slot, key, buf, r.ntok, r.h6, status)) {
-        r.kind = kWordHit; r.t01 = make_uint2(r.ntok > 0 ? buf[0] : 0u, r.ntok > 1 ? buf[1] : 0u);
-    }
+    if (m == kMemoClaimed && memo_publish(ws, r.slot, key, buf, r.ntok, r.h6, status)) r.kind = kWordHit;
     return r;
 }
-// phase B slow paths: re-encode a word whose ids were not kept, or emit a long word
+// pass 2 slow paths: re-encode a word whose ids were not kept, or emit a long word (Enc without scratch)
 template <class Enc>
-__device__ __noinline__ uint32_t emit_slow(const Enc &enc, const EncodeWorkspace &ws, const uint8_t *word, uint32_t nbytes,
-                                           uint32_t kind, uint32_t ntok, uint32_t slot, uint32_t *buf, uint32_t *dst) {
-    uint32_t h6 = 0;
+__device__ __noinline__ void emit_slow(const Enc &enc, const uint8_t *word, uint32_t nbytes, uint32_t kind, uint32_t ntok,
+                                       uint32_t *buf, uint32_t *dst) {
     if (kind == kWordRecompute) {
         uint32_t dummy = 0;
         const uint32_t n = enc.encode_short(word, nbytes, buf, dummy);
         for (uint32_t k = 0; k < n; ++k) dst[k] = buf[k];
-    } else if constexpr (!Enc::kCoopLong) {
-        enc.long_emit(word, nbytes, dst, ntok, h6);
-    } else {
-        const uint32_t *src = ws.long_scratch + ((unsigned long long)slot << 1) + (kind == kWordLongB ? nbytes : 0u);
-        for (uint32_t k = 0; k < ntok; ++k) dst[k] = src[k];
+    } else if constexpr (!Enc::kScratchLong) {
+        uint32_t dummy = 0;
+        enc.long_emit(word, nbytes, dst, ntok, dummy);
     }
-    return h6;
 }
 
-// ids of a memo hit -> dst (ids 0-1 arrived with the probe, 2-9 were prefetched, the rest is fetched here)
-__device__ __forceinline__ void store_hit_ids(uint32_t *dst, uint32_t n, uint2 t01, uint4 c0, uint4 c1, const MemoEntry *e) {
-    if (n > 0) dst[0] = t01.x;
-    if (n > 1) dst[1] = t01.y;
+// ids of a memo hit -> dst (ids 0-9 were prefetched, the rest is fetched here)
+__device__ __forceinline__ void store_hit_ids(uint32_t *dst, uint32_t n, uint4 m, uint4 c0, uint4 c1, const MemoEntry *e) {
+    if (n > 0) dst[0] = m.z;
+    if (n > 1) dst[1] = m.w;
     if (n > 2) dst[2] = c0.x;
     if (n > 3) dst[3] = c0.y;
     if (n > 4) dst[4] = c0.z;
@@ -291,60 +250,47 @@ __device__ __forceinline__ void store_hit_ids(uint32_t *dst, uint32_t n, uint2 t
     }
 }
 
-// ---- the tile kernel ---------------------------------------------------------------------------------------------------
+// ---- pass 1: count ---------------------------------------------------------------------------------------------------
 // Enc provides
 //   uint32_t encode_short(const uint8_t *p, uint32_t nbytes, uint32_t *buf /*thread-local, kShortBytes*/, uint32_t &h6) const
-//   static constexpr bool kCoopLong
-//   kCoopLong == false:  uint32_t long_count(p, nbytes) const;  void long_emit(p, nbytes, uint32_t *dst, uint32_t cap, uint32_t &h6) const
-//   kCoopLong == true :  uint32_t encode_long_coop(p, nbytes, bufA, bufB, uint32_t **result, uint32_t *sh_scan, uint32_t *sh_misc) const
+//   static constexpr bool kScratchLong
+//   kScratchLong == false: uint32_t long_count(p, nbytes, h6) const;  void long_emit(p, nbytes, uint32_t *dst, uint32_t cap, uint32_t &h6) const
+//   kScratchLong == true : uint32_t encode_long_warp(p, nbytes, bufA, bufB, uint32_t **result) const   (all 32 lanes)
+//
+// Every warp owns tiles of kTileWords = 64 consecutive words (2 per lane), assigned round-robin; warps never wait for
+// each other, so the L2 latencies of one warp's probes are covered by the other warps of the SM.
 template <class Enc>
-__global__ void __launch_bounds__(kThreads, 2)
-encode_tiles_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words,
-                    uint32_t *__restrict__ out_ids, uint64_t out_cap, uint32_t *__restrict__ out_tok_off, uint32_t tok_base,
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words,
                     EncodeWorkspace ws, uint32_t *status) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
-    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * kThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kThreads) >> 5;
     const uint32_t arena_end = word_off[n_words];
-    const bool tok_off_vec = out_tok_off && (((uintptr_t)out_tok_off & 15) == 0);
     const bool use_memo = ws.memo_mask != 0;
     uint32_t h6 = 0;
-    uint32_t buf[kShortBytes];                              // thread-local scratch for one directly encoded word
+    uint32_t buf[kShortBytes];                                   // thread-local scratch for one directly encoded word
 
-    // Tiles are handed out by an atomic ticket: a tile only starts once a CTA is free to run it, so every predecessor
-    // of a running tile is itself running or finished and the look-back cannot deadlock.
-    // Tiles are handed out by an atomic ticket: a tile only starts once a CTA is free to run it, so every predecessor
-    // of a running tile is itself running or finished and the look-back cannot deadlock.
-    uint32_t next_ticket = 0;
-    if (tid == 0) next_ticket = atomicAdd(ws.ticket, 1u);
-    for (;;) {
-        if (tid == 0) { sm.misc[4] = next_ticket; sm.n_slow = 0; }
-        __syncthreads();
-        const uint32_t tile = sm.misc[4];
-        if (tile >= ws.n_tiles) break;
+    for (uint32_t tile = warp_global; tile < ws.n_tiles; tile += n_warps) {
         const uint32_t w_tile = tile * kTileWords;
         const uint32_t tile_words = min((uint32_t)kTileWords, n_words - w_tile);
-        for (uint32_t i = tid; i <= tile_words; i += kThreads) sm.off[i] = word_off[w_tile + i];
-        __syncthreads();
-
-        // ---- phase A: counts.  Fast path = first memo probe hits; everything else goes through resolve_slow.
-        uint32_t kind[kWordsPerThread], ntok[kWordsPerThread], slot[kWordsPerThread];
-        uint2 t01[kWordsPerThread];
-        unsigned long long klo[kWordsPerThread], khi[kWordsPerThread];      // word key, then (after the xor) key difference
+        // ---- offsets of this lane's two words
         uint32_t nb[kWordsPerThread], b0s[kWordsPerThread];
-        uint4 mt[kWordsPerThread];
-        uint32_t count = 0; bool has_long = false;
-#pragma unroll
-        for (int j = 0; j < kWordsPerThread; ++j) {
-            const uint32_t i = tid * kWordsPerThread + j;
-            kind[j] = kWordNone; ntok[j] = 0; slot[j] = 0; t01[j] = make_uint2(0, 0);
-            b0s[j] = i < tile_words ? sm.off[i] : 0u;
-            nb[j] = i < tile_words ? sm.off[i + 1] - b0s[j] : 0xFFFFFFFFu;          // 0xFFFFFFFF: no word
-            klo[j] = khi[j] = ~0ull; mt[j] = make_uint4(0, 0, 0, 0);
+        {
+            const uint32_t i0 = lane * kWordsPerThread;
+            const uint32_t o0 = i0 <= tile_words ? __ldg(word_off + w_tile + i0) : 0u;
+            const uint32_t o1 = i0 + 1 <= tile_words ? __ldg(word_off + w_tile + i0 + 1) : 0u;
+            const uint32_t o2 = i0 + 2 <= tile_words ? __ldg(word_off + w_tile + i0 + 2) : 0u;
+            b0s[0] = o0; nb[0] = i0 < tile_words ? o1 - o0 : 0xFFFFFFFFu;       // 0xFFFFFFFF: no word
+            b0s[1] = o1; nb[1] = i0 + 1 < tile_words ? o2 - o1 : 0xFFFFFFFFu;
         }
+        // ---- fast path = the first memo probe (L1-cached) hits
+        uint32_t kind[kWordsPerThread], ntok[kWordsPerThread], slot[kWordsPerThread];
+        unsigned long long klo[kWordsPerThread], khi[kWordsPerThread];
+        uint32_t meta[kWordsPerThread];
+#pragma unroll
+        for (int j = 0; j < kWordsPerThread; ++j) { kind[j] = kWordNone; ntok[j] = 0; slot[j] = 0; klo[j] = khi[j] = ~0ull; meta[j] = 0; }
         if (use_memo) {
-            // words of 1..15 bytes: request the (up to three) aligned 8-byte words of all four words, then the first memo
-            // probe of all four, before looking at any result
+            // words of 1..15 bytes: request the (up to three) aligned 8-byte words of both words, then both probes
             unsigned long long r0[kWordsPerThread], r1[kWordsPerThread], r2[kWordsPerThread];
             bool fastj[kWordsPerThread];
 #pragma unroll
@@ -370,166 +316,235 @@ encode_tiles_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
                     slot[j] = (uint32_t)mix64(lo ^ (hi * 0x9E3779B97F4A7C15ull)) & ws.memo_mask;
                     const MemoEntry *e = ws.memo + slot[j];
                     ld_ca_u64x2(e, elo, ehi);
-                    mt[j] = ld_ca_u32x4(&e->meta);
+                    meta[j] = ld_ca_u32(&e->meta);
                     klo[j] = lo ^ elo; khi[j] = hi ^ ehi;                            // zero iff the entry holds this word
                 }
             }
         }
+        bool slow[kWordsPerThread], is_long[kWordsPerThread];
 #pragma unroll
         for (int j = 0; j < kWordsPerThread; ++j) {
+            slow[j] = false; is_long[j] = false;
             if (nb[j] == 0xFFFFFFFFu) continue;
-            if (nb[j] > (uint32_t)kShortBytes) {
-                kind[j] = kWordLong; has_long = true;
-                if constexpr (!Enc::kCoopLong) ntok[j] = enc.long_count(arena + b0s[j], nb[j]);
-            } else if ((klo[j] | khi[j]) == 0 && mt[j].x != 0 && mt[j].x != 0xFFFFFFFFu) {
-                kind[j] = kWordHit; ntok[j] = (mt[j].x & 0xFFu) - 1; h6 += mt[j].x >> 8; t01[j] = make_uint2(mt[j].z, mt[j].w);
-            } else {
-                // not served by the first probe (longer than 15 bytes, hash collision, first occurrence): defer to the
-                // dense pass below so that these few words do not serialise whole warps one lane at a time
-                const uint32_t q = atomicAdd(&sm.n_slow, 1u);
-                if (q < (uint32_t)kSlowCap) { sm.slow_list[q] = tid * kWordsPerThread + j; kind[j] = kWordPending; slot[j] = q; }
-                else {
-                    const SlowResult r = resolve_slow(enc, ws, arena, b0s[j], nb[j], arena_end, buf, status);
-                    kind[j] = r.kind; ntok[j] = r.ntok; slot[j] = r.slot; t01[j] = r.t01; h6 += r.h6;
-                }
-            }
+            if (nb[j] > (uint32_t)kShortBytes) { kind[j] = kWordLong; is_long[j] = true; }
+            else if ((klo[j] | khi[j]) == 0 && meta[j] != 0 && meta[j] != 0xFFFFFFFFu) {
+                kind[j] = kWordHit; ntok[j] = (meta[j] & 0xFFu) - 1; h6 += meta[j] >> 8;
+            } else slow[j] = true;
         }
-        __syncthreads();
-        {
-            const uint32_t n_slow = min(sm.n_slow, (uint32_t)kSlowCap);
-            for (uint32_t q = tid; q < n_slow; q += kThreads) {                      // one deferred word per thread, lanes dense
-                const uint32_t i = sm.slow_list[q];
-                const uint32_t b0 = sm.off[i];
-                const SlowResult r = resolve_slow(enc, ws, arena, b0, sm.off[i + 1] - b0, arena_end, buf, status);
-                h6 += r.h6;
-                sm.slow_res[q][0] = r.kind | (r.ntok << 8); sm.slow_res[q][1] = r.slot; sm.slow_res[q][2] = r.t01.x; sm.slow_res[q][3] = r.t01.y;
-            }
-        }
-        __syncthreads();
+        // words not served by the first probe (longer than 15 bytes, hash collision, first occurrence) are spread over the
+        // lanes of the warp so that they are resolved side by side instead of one lane at a time
 #pragma unroll
         for (int j = 0; j < kWordsPerThread; ++j) {
-            if (kind[j] == kWordPending) {
-                const uint32_t q = slot[j];
-                const uint32_t kn = sm.slow_res[q][0];
-                kind[j] = kn & 0xFFu; ntok[j] = kn >> 8; slot[j] = sm.slow_res[q][1]; t01[j] = make_uint2(sm.slow_res[q][2], sm.slow_res[q][3]);
-            }
-            count += ntok[j];
+            const uint32_t m = __ballot_sync(0xffffffffu, slow[j]);
+            if (m == 0) continue;                                                   // warp-uniform
+            const uint32_t n_slow = __popc(m);
+            const uint32_t src = __fns(m, 0, lane + 1);                             // lane -> owner of the lane-th slow word
+            const uint32_t sb0 = __shfl_sync(0xffffffffu, b0s[j], src & 31), snb = __shfl_sync(0xffffffffu, nb[j], src & 31);
+            SlowResult r; r.kind = kWordNone; r.ntok = 0; r.slot = 0; r.h6 = 0;
+            if (lane < n_slow) r = resolve_slow(enc, ws, arena, sb0, snb, arena_end, buf, status);
+            h6 += r.h6;
+            const uint32_t rank = __popc(m & ((1u << lane) - 1u));                 // this lane's word was resolved by lane `rank`
+            const uint32_t k_ = __shfl_sync(0xffffffffu, r.kind, rank), n_ = __shfl_sync(0xffffffffu, r.ntok, rank);
+            const uint32_t s_ = __shfl_sync(0xffffffffu, r.slot, rank);
+            if (slow[j]) { kind[j] = k_; ntok[j] = n_; slot[j] = s_; }
         }
-        if constexpr (Enc::kCoopLong) {
-            // long words: the whole CTA works on one word at a time in global scratch (rare)
-            if (__syncthreads_or(has_long)) {
-                for (uint32_t i = 0; i < tile_words; ++i) {
-                    const uint32_t b0 = sm.off[i], nbytes = sm.off[i + 1] - b0;
-                    if (nbytes <= (uint32_t)kShortBytes) continue;                      // CTA-uniform
-                    if (tid == 0) {
-                        const unsigned long long so = atomicAdd(ws.long_cursor, 2ull * nbytes);
-                        sm.misc[6] = (uint32_t)(so >> 1); sm.misc[7] = (so + 2ull * nbytes <= ws.long_scratch_elems) ? 1u : 0u;
-                    }
-                    __syncthreads();
-                    const unsigned long long so = (unsigned long long)sm.misc[6] << 1;
-                    const bool fits = sm.misc[7] != 0;
-                    __syncthreads();
-                    uint32_t *res = nullptr; uint32_t c = 0;
-                    if (fits) c = enc.encode_long_coop(arena + b0, nbytes, ws.long_scratch + so, ws.long_scratch + so + nbytes, &res, sm.scan, sm.misc);
-                    else if (tid == 0) atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY);
-                    if (tid == i / kWordsPerThread) {
+        // long words (rare)
+        uint32_t packed[kWordsPerThread];
 #pragma unroll
-                        for (int j = 0; j < kWordsPerThread; ++j) if ((uint32_t)j == i % kWordsPerThread) {
-                            ntok[j] = c; count += c; slot[j] = (uint32_t)(so >> 1);
-                            kind[j] = (res == ws.long_scratch + so) ? kWordLong : kWordLongB;
-                            if (!fits) kind[j] = kWordNone;
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
-        }
-
-        // ---- scan.  The look-back (warp 0) mostly WAITS for earlier tiles, so it runs after warp 0 has assembled its
-        // own share of the tile's ids in shared memory; only an oversized tile (rare) needs the base first.
-        uint32_t total, excl = block_exclusive_scan(count, sm.scan, &total);
-        if (tid == 0) tile_publish_aggregate(ws.tile_state, tile, total);
-        const bool use_compact = total <= (uint32_t)kCompactTokens;
-        uint64_t base = 0; bool fits_out = true;
-        if (!use_compact) {
-            if (tid < 32) { const uint64_t b = tile_prefix_warp(ws.tile_state, tile, total, &status[kStatusCode]); if (tid == 0) sm.base = b; }
-            __syncthreads();
-            base = sm.base; fits_out = base + total <= out_cap;
-        }
-
-        // ---- phase B: ids to their tile-local position.  Ids 0-1 came with the probe; ids 2-9 of all four words are
-        // requested before any is stored; the rest (rare) in a loop.
-        uint32_t run[kWordsPerThread];
-        {
-            uint32_t r = excl;
-#pragma unroll
-            for (int j = 0; j < kWordsPerThread; ++j) { run[j] = r; r += ntok[j]; }
-        }
-        if (fits_out) {
-            uint4 c0[kWordsPerThread], c1[kWordsPerThread];
-#pragma unroll
-            for (int j = 0; j < kWordsPerThread; ++j) {
-                c0[j] = c1[j] = make_uint4(0, 0, 0, 0);
-                if (kind[j] == kWordHit && ntok[j] > 2) {
-                    const MemoEntry *e = ws.memo + slot[j];
-                    c0[j] = ld_ca_u32x4(&e->tok[0]);
-                    if (ntok[j] > 6) c1[j] = ld_ca_u32x4(&e->tok[4]);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < kWordsPerThread; ++j) {
-                if (kind[j] == kWordNone) continue;
-                if (kind[j] == kWordHit) {
-                    // two copies of the same code so that the common case compiles to shared-memory stores (STS)
-                    if (use_compact) store_hit_ids(sm.compact + run[j], ntok[j], t01[j], c0[j], c1[j], ws.memo + slot[j]);
-                    else store_hit_ids(out_ids + base + run[j], ntok[j], t01[j], c0[j], c1[j], ws.memo + slot[j]);
-                } else {
-                    uint32_t *dst = use_compact ? sm.compact + run[j] : out_ids + base + run[j];
-                    h6 += emit_slow(enc, ws, arena + b0s[j], nb[j], kind[j], ntok[j], slot[j], buf, dst);
-                }
-            }
-        }
-        if (use_compact && tid < 32) { const uint64_t b = tile_prefix_warp(ws.tile_state, tile, total, &status[kStatusCode]); if (tid == 0) sm.base = b; }
-        __syncthreads();
-        if (use_compact) { base = sm.base; fits_out = base + total <= out_cap; }
-        if (!fits_out && tid == 0) atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY);
-        if (out_tok_off) {
-            const uint32_t i0 = tid * kWordsPerThread;
-            const uint32_t o0 = tok_base + (uint32_t)base;
-            if (tok_off_vec && i0 + kWordsPerThread <= tile_words) {
-                if constexpr (kWordsPerThread == 4)
-                    *reinterpret_cast<uint4 *>(out_tok_off + w_tile + i0) = make_uint4(o0 + run[0], o0 + run[1], o0 + run[2 % kWordsPerThread], o0 + run[3 % kWordsPerThread]);
-                else
-                    *reinterpret_cast<uint2 *>(out_tok_off + w_tile + i0) = make_uint2(o0 + run[0], o0 + run[1]);
+        for (int j = 0; j < kWordsPerThread; ++j) {
+            packed[j] = (kind[j] << 29) | (ntok[j] << 23) | (kind[j] == kWordHit ? slot[j] : 0u);
+            if constexpr (!Enc::kScratchLong) {
+                if (is_long[j]) { ntok[j] = enc.long_count(arena + b0s[j], nb[j], h6); packed[j] = (kWordLong << 29) | ntok[j]; }
             } else {
+                uint32_t m = __ballot_sync(0xffffffffu, is_long[j]);
+                while (m) {                                                         // the whole warp works on one long word
+                    const uint32_t owner = __ffs(m) - 1; m &= m - 1;
+                    const uint32_t lb0 = __shfl_sync(0xffffffffu, b0s[j], owner), lnb = __shfl_sync(0xffffffffu, nb[j], owner);
+                    const unsigned long long need = (kLongHeader + 2ull * lnb + 15ull) & ~15ull;
+                    unsigned long long so = 0;
+                    if (lane == 0) so = atomicAdd(ws.long_cursor, need);
+                    so = __shfl_sync(0xffffffffu, so, 0);
+                    uint32_t c = 0; uint32_t *res = nullptr;
+                    const bool fits = so + need <= ws.long_scratch_elems && (so >> 4) < (1ull << 29);
+                    uint32_t *bufA = ws.long_scratch + so + kLongHeader;
+                    if (fits) c = enc.encode_long_warp(arena + lb0, lnb, bufA, bufA + lnb, &res);
+                    else if (lane == 0) atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY);
+                    if (lane == owner) {
+                        ntok[j] = c;
+                        if (fits) { ws.long_scratch[so] = c; packed[j] = ((res == bufA ? kWordLong : kWordLongB) << 29) | (uint32_t)(so >> 4); }
+                        else packed[j] = 0;
+                    }
+                }
+            }
+        }
+        // ---- per-word records and the tile total
+        {
+            const uint32_t i0 = lane * kWordsPerThread;
+            if (i0 + 1 < tile_words) *reinterpret_cast<uint2 *>(ws.packed + w_tile + i0) = make_uint2(packed[0], packed[1]);
+            else if (i0 < tile_words) ws.packed[w_tile + i0] = packed[0];
+        }
+        uint32_t total = ntok[0] + ntok[1];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+        if (lane == 0) ws.tile_total[tile] = total;
+    }
+    if (h6) atomicAdd(&status[kStatusH6], h6);
+}
+
+// ---- scan of the tile totals: in-group exclusive prefixes (in place) + group sums, then the group bases ------------------
+static __global__ void __launch_bounds__(256) encode_scan_groups_kernel(EncodeWorkspace ws) {
+    __shared__ uint32_t sh_scan[36];
+    const uint32_t g = blockIdx.x, t0 = g * kGroupTiles + threadIdx.x * 4;
+    uint32_t v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = t0 + k < ws.n_tiles ? ws.tile_total[t0 + k] : 0u; s += v[k]; }
+    uint32_t total, excl = block_exclusive_scan(s, sh_scan, &total);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { if (t0 + k < ws.n_tiles) ws.tile_total[t0 + k] = excl; excl += v[k]; }
+    if (threadIdx.x == 0) ws.group_base[g] = total;
+}
+static __global__ void __launch_bounds__(1024) encode_scan_top_kernel(EncodeWorkspace ws, uint32_t n_words, uint32_t *out_tok_off, uint32_t tok_base,
+                                                               uint64_t out_cap, uint32_t *status) {
+    __shared__ unsigned long long sh[33];
+    __shared__ unsigned long long carry;
+    const uint32_t n_groups = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t g0 = 0; g0 < n_groups; g0 += 1024) {
+        const uint32_t g = g0 + threadIdx.x;
+        const unsigned long long v = g < n_groups ? ws.group_base[g] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += u; }
+        if (lane == 31) sh[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long w = sh[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned long long u = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= (uint32_t)d) wi += u; }
+            sh[lane] = wi - w;
+            if (lane == 31) sh[32] = wi;
+        }
+        __syncthreads();
+        const unsigned long long c = carry;
+        if (g < n_groups) ws.group_base[g] = c + sh[wid] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + sh[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long grand = carry;
+        if (out_tok_off) out_tok_off[n_words] = tok_base + (uint32_t)grand;
+        status[kStatusTokens] = (uint32_t)grand; status[kStatusTokensHi] = (uint32_t)(grand >> 32);
+        if (grand > out_cap) atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY);
+    }
+}
+
+// ---- pass 2: emit ------------------------------------------------------------------------------------------------------
+template <class Enc>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words,
+                   uint32_t *__restrict__ out_ids, uint64_t out_cap, uint32_t *__restrict__ out_tok_off, uint32_t tok_base,
+                   EncodeWorkspace ws) {
+    __shared__ uint32_t s_compact[kWarps][kCompactTokens];       // per warp: the tile's ids in output order
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * kThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kThreads) >> 5;
+    const bool tok_off_vec = out_tok_off && (((uintptr_t)out_tok_off & 7) == 0);
+    uint32_t *compact = s_compact[threadIdx.x >> 5];
+    uint32_t buf[kShortBytes];
+
+    for (uint32_t tile = warp_global; tile < ws.n_tiles; tile += n_warps) {
+        const uint32_t w_tile = tile * kTileWords;
+        const uint32_t tile_words = min((uint32_t)kTileWords, n_words - w_tile);
+        const uint32_t i0 = lane * kWordsPerThread;
+        uint32_t packed[kWordsPerThread] = {0u, 0u};
+        if (i0 + 1 < tile_words) { const uint2 p = *reinterpret_cast<const uint2 *>(ws.packed + w_tile + i0); packed[0] = p.x; packed[1] = p.y; }
+        else if (i0 < tile_words) packed[0] = ws.packed[w_tile + i0];
+        const uint64_t base = ws.group_base[tile / kGroupTiles] + ws.tile_total[tile];
+        uint32_t kind[kWordsPerThread], ntok[kWordsPerThread], arg[kWordsPerThread];
+        uint4 m[kWordsPerThread], c0[kWordsPerThread], c1[kWordsPerThread];
+#pragma unroll
+        for (int j = 0; j < kWordsPerThread; ++j) {
+            kind[j] = packed[j] >> 29;
+            arg[j] = packed[j] & 0x1FFFFFFFu;
+            ntok[j] = (kind[j] == kWordHit || kind[j] == kWordRecompute) ? (arg[j] >> 23) : (kind[j] == kWordLong && !Enc::kScratchLong) ? arg[j] : 0u;
+            m[j] = c0[j] = c1[j] = make_uint4(0, 0, 0, 0);
+            if (kind[j] == kWordHit) {                              // all id loads of both words are in flight together
+                const MemoEntry *e = ws.memo + (arg[j] & 0xFFFFFu);
+                m[j] = ld_ca_u32x4(&e->meta);
+                if (ntok[j] > 2) c0[j] = ld_ca_u32x4(&e->tok[0]);
+                if (ntok[j] > 6) c1[j] = ld_ca_u32x4(&e->tok[4]);
+            }
+            if constexpr (Enc::kScratchLong) {
+                if (kind[j] == kWordLong || kind[j] == kWordLongB) ntok[j] = ws.long_scratch[(unsigned long long)arg[j] << 4];
+            }
+        }
+        uint32_t count = 0, run[kWordsPerThread];
+#pragma unroll
+        for (int j = 0; j < kWordsPerThread; ++j) { run[j] = count; count += ntok[j]; }
+        uint32_t incl = count;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += v; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), excl = incl - count;
+#pragma unroll
+        for (int j = 0; j < kWordsPerThread; ++j) run[j] += excl;
+        const bool fits_out = base + total <= out_cap;
+        const bool use_compact = total <= (uint32_t)kCompactTokens;
+        if (out_tok_off) {
+            const uint32_t o0 = tok_base + (uint32_t)base;
+            if (tok_off_vec && i0 + kWordsPerThread <= tile_words)
+                *reinterpret_cast<uint2 *>(out_tok_off + w_tile + i0) = make_uint2(o0 + run[0], o0 + run[1]);
+            else {
 #pragma unroll
                 for (int j = 0; j < kWordsPerThread; ++j) if (i0 + j < tile_words) out_tok_off[w_tile + i0 + j] = o0 + run[j];
             }
         }
-        // take the next ticket now so that its latency hides behind the store of this tile.  (It must not be taken any
-        // earlier: a tile that holds a ticket without running delays the look-back of every later tile -- measured.)
-        if (tid == 0) next_ticket = atomicAdd(ws.ticket, 1u);
-        if (use_compact && fits_out) {
+        if (!fits_out) continue;                                                    // warp-uniform (status set by the scan)
+#pragma unroll
+        for (int j = 0; j < kWordsPerThread; ++j) {
+            if (kind[j] == kWordHit) {
+                // two copies of the same code so that the common case compiles to shared-memory stores (STS)
+                if (use_compact) store_hit_ids(compact + run[j], ntok[j], m[j], c0[j], c1[j], ws.memo + (arg[j] & 0xFFFFFu));
+                else store_hit_ids(out_ids + base + run[j], ntok[j], m[j], c0[j], c1[j], ws.memo + (arg[j] & 0xFFFFFu));
+            } else if (kind[j] == kWordRecompute || (!Enc::kScratchLong && kind[j] == kWordLong)) {
+                uint32_t *dst = use_compact ? compact + run[j] : out_ids + base + run[j];
+                const uint32_t b0 = __ldg(word_off + w_tile + i0 + j), b1 = __ldg(word_off + w_tile + i0 + j + 1);
+                emit_slow(enc, arena + b0, b1 - b0, kind[j], ntok[j], buf, dst);
+            }
+        }
+        if constexpr (Enc::kScratchLong) {                                          // long results: the warp copies them together
+#pragma unroll
+            for (int j = 0; j < kWordsPerThread; ++j) {
+                uint32_t lm = __ballot_sync(0xffffffffu, kind[j] == kWordLong || kind[j] == kWordLongB);
+                while (lm) {
+                    const uint32_t owner = __ffs(lm) - 1; lm &= lm - 1;
+                    const uint32_t ln = __shfl_sync(0xffffffffu, ntok[j], owner), lrun = __shfl_sync(0xffffffffu, run[j], owner);
+                    const uint32_t larg = __shfl_sync(0xffffffffu, arg[j], owner), lkind = __shfl_sync(0xffffffffu, kind[j], owner);
+                    const uint32_t lb0 = __ldg(word_off + w_tile + owner * kWordsPerThread + j);
+                    const uint32_t lnb = __ldg(word_off + w_tile + owner * kWordsPerThread + j + 1) - lb0;
+                    const uint32_t *src = ws.long_scratch + ((unsigned long long)larg << 4) + kLongHeader + (lkind == kWordLongB ? lnb : 0u);
+                    uint32_t *dst = use_compact ? compact + lrun : out_ids + base + lrun;
+                    for (uint32_t k = lane; k < ln; k += 32) dst[k] = src[k];
+                }
+            }
+        }
+        __syncwarp();
+        if (use_compact) {
             // coalesced store: scalar head up to 16-byte alignment of the destination, then 128-bit stores
             uint32_t *dst = out_ids + base;
             const uint32_t head = min(total, (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15) >> 2);
-            if (tid < head) dst[tid] = sm.compact[tid];
+            if (lane < head) dst[lane] = compact[lane];
             const uint32_t nvec = (total - head) >> 2;
-            for (uint32_t v = tid; v < nvec; v += kThreads) {
+            for (uint32_t v = lane; v < nvec; v += 32) {
                 const uint32_t c = head + 4 * v;
-                *reinterpret_cast<uint4 *>(dst + c) = make_uint4(sm.compact[c], sm.compact[c + 1], sm.compact[c + 2], sm.compact[c + 3]);
+                *reinterpret_cast<uint4 *>(dst + c) = make_uint4(compact[c], compact[c + 1], compact[c + 2], compact[c + 3]);
             }
             const uint32_t tail0 = head + 4 * nvec;
-            if (tail0 + tid < total) dst[tail0 + tid] = sm.compact[tail0 + tid];
+            if (tail0 + lane < total) dst[tail0 + lane] = compact[tail0 + lane];
         }
-        if (tile == ws.n_tiles - 1 && tid == 0) {
-            const uint64_t grand = base + total;
-            if (out_tok_off) out_tok_off[n_words] = tok_base + (uint32_t)grand;
-            status[kStatusTokens] = (uint32_t)grand; status[kStatusTokensHi] = (uint32_t)(grand >> 32);
-        }
-        __syncthreads();
+        __syncwarp();                                            // the compact buffer is reused by the next tile
     }
-    if (h6) atomicAdd(&status[kStatusH6], h6);
 }
 
 template <class Enc>
@@ -547,13 +562,17 @@ int launch_encode_tiles(const Enc &enc, const uint8_t *d_arena, const uint32_t *
         if (d_out_tok_off) SWT_CUDA_OK(cudaMemcpyAsync(d_out_tok_off, &tok_base, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         return SWT_OK;
     }
-    static int grid = 0;
-    if (!grid) {
-        SWT_CUDA_OK(cudaFuncSetAttribute(encode_tiles_kernel<Enc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
-        grid = encode_grid((const void *)encode_tiles_kernel<Enc>, kThreads, sizeof(TileSmem));
+    static int grid1 = 0, grid2 = 0;
+    if (!grid1) {
+        grid1 = encode_grid((const void *)encode_count_kernel<Enc>, kThreads, 0);
+        grid2 = encode_grid((const void *)encode_emit_kernel<Enc>, kThreads, 0);
     }
-    const int g = (int)std::min<uint64_t>((uint64_t)grid, ws.n_tiles);
-    encode_tiles_kernel<Enc><<<g, kThreads, sizeof(TileSmem), st>>>(enc, d_arena, d_word_off, n_words, d_out_ids, out_cap, d_out_tok_off, tok_base, ws, d_status);
+    const uint32_t n_ctas = (ws.n_tiles + kWarps - 1) / kWarps, n_groups = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
+    encode_count_kernel<Enc><<<(int)std::min<uint32_t>((uint32_t)grid1, n_ctas), kThreads, 0, st>>>(enc, d_arena, d_word_off, n_words, ws, d_status);
+    encode_scan_groups_kernel<<<n_groups, 256, 0, st>>>(ws);
+    encode_scan_top_kernel<<<1, 1024, 0, st>>>(ws, n_words, d_out_tok_off, tok_base, out_cap, d_status);
+    encode_emit_kernel<Enc><<<(int)std::min<uint32_t>((uint32_t)grid2, n_ctas), kThreads, 0, st>>>(enc, d_arena, d_word_off, n_words, d_out_ids, out_cap,
+                                                                                                   d_out_tok_off, tok_base, ws);
     SWT_CUDA_OK(cudaGetLastError());
     return SWT_OK;
 }

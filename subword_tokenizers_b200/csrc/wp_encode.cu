@@ -121,16 +121,16 @@ __device__ __forceinline__ void wp_encode_chunk(const WpTrieDev &t, const uint8_
 
 struct WpEnc {
     WpTrieDev t;
-    static constexpr bool kCoopLong = false;
+    static constexpr bool kScratchLong = false;
     __device__ __forceinline__ uint32_t encode_short(const uint8_t *p, uint32_t nbytes, uint32_t *buf, uint32_t &h6) const {
         ArrayEmit e{buf, (uint32_t)kShortBytes};
         wp_encode_chunk(t, p, nbytes, e, h6);
         return e.n;
     }
     // chunks longer than kShortBytes are walked twice: count, then write at the final position
-    __device__ __forceinline__ uint32_t long_count(const uint8_t *p, uint32_t nbytes) const {
-        CountEmit e; uint32_t dummy = 0;
-        wp_encode_chunk(t, p, nbytes, e, dummy);
+    __device__ __forceinline__ uint32_t long_count(const uint8_t *p, uint32_t nbytes, uint32_t &h6) const {
+        CountEmit e;
+        wp_encode_chunk(t, p, nbytes, e, h6);
         return e.n;
     }
     __device__ __forceinline__ void long_emit(const uint8_t *p, uint32_t nbytes, uint32_t *dst, uint32_t cap, uint32_t &h6) const {
