@@ -47,6 +47,10 @@ def load_golden(name):
 # The draw sequence comes from numpy PCG64 in fixed chunks, so any prefix is reproducible on the CPU.
 # ------------------------------------------------------------------------------------------------------------
 ZIPF_C = 200_000
+# dram__bytes_read.sum + dram__bytes_write.sum of the kernels of ONE FastWP encode call over the 1 GB bench stream
+# (ncu --set full, see profiles/r01_final_ncu_wp_1GB.txt); None until measured
+TRAFFIC_1GB_WP = 5_916_539_000
+TRAFFIC_SOURCE = "profiles/r01_final_ncu_wp_1GB.txt"
 DRAW_CHUNK = 1 << 24
 
 
@@ -335,12 +339,13 @@ def main():
         "warmup": max(3, args.warmup), "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "encode_tiles_kernel<WpEnc>",
+                     "traffic": TRAFFIC_1GB_WP if args.bytes == 1_000_000_000 else None, "traffic_source": TRAFFIC_SOURCE,
+                     "peak_source": peak_src, "kernel": "encode_count_kernel<WpEnc> + scan + encode_emit_kernel<WpEnc> (one encode call)",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms},
         "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": n_bytes + 4 * (n_words + 1),
                 "d2h_bytes_per_step": 4 * n_tokens + 4 * n_words + 32 * ((n_bytes >> 26) + 1), "steps": e2e_steps,
                 "matches_resident_run": e2e_ok},
-        "gpu_launches": args.steps, "clocks": clocks,
+        "gpu_launches": 5 * args.steps, "clocks": clocks,
         "stream": {"n_words": n_words, "n_bytes": n_bytes, "n_tokens": n_tokens, "h6_events": h6},
     }
     # ---- CPU baseline: oracle port on the host cores, bounded sample (N=1 only)

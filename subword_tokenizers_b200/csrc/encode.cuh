@@ -26,6 +26,7 @@
 // Every input byte is still read and every output id still written by every launch.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -98,6 +99,11 @@ __device__ __forceinline__ void ld_ca_u64x2(const void *p, unsigned long long &a
 __device__ __forceinline__ uint4 ld_ca_u32x4(const void *p) {
     uint4 v;
     asm volatile("ld.global.ca.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 ld_ca_u32x2(const void *p) {
+    uint2 v;
+    asm volatile("ld.global.ca.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ uint32_t ld_ca_u32(const void *p) {
@@ -206,7 +212,8 @@ struct SlowResult { uint32_t kind, ntok, slot, h6; };
 // the unrolled fast path stays small.
 template <class Enc>
 __device__ __noinline__ SlowResult resolve_slow(const Enc &enc, const EncodeWorkspace &ws, const uint8_t *arena, uint32_t b0,
-                                                uint32_t nbytes, uint32_t arena_end, uint32_t *buf, uint32_t *status) {
+                                                uint32_t nbytes, uint32_t arena_end, uint32_t *status) {
+    uint32_t buf[kShortBytes];                                   // scratch for one directly encoded word
     SlowResult r; r.kind = kWordRecompute; r.ntok = 0; r.slot = 0; r.h6 = 0;
     int m = kMemoMiss; uint32_t meta = 0; MemoKey key; uint2 t01;
     if (ws.memo_mask && nbytes >= 1) { memo_key(arena, b0, nbytes, arena_end, key); m = memo_probe(ws, key, r.slot, meta, t01); }
@@ -218,8 +225,9 @@ __device__ __noinline__ SlowResult resolve_slow(const Enc &enc, const EncodeWork
 // pass 2 slow paths: re-encode a word whose ids were not kept, or emit a long word (Enc without scratch)
 template <class Enc>
 __device__ __noinline__ void emit_slow(const Enc &enc, const uint8_t *word, uint32_t nbytes, uint32_t kind, uint32_t ntok,
-                                       uint32_t *buf, uint32_t *dst) {
+                                       uint32_t *dst) {
     if (kind == kWordRecompute) {
+        uint32_t buf[kShortBytes];
         uint32_t dummy = 0;
         const uint32_t n = enc.encode_short(word, nbytes, buf, dummy);
         for (uint32_t k = 0; k < n; ++k) dst[k] = buf[k];
@@ -250,6 +258,16 @@ __device__ __forceinline__ void store_hit_ids(uint32_t *dst, uint32_t n, uint4 m
     }
 }
 
+// clears the key/meta sector of every memo entry (the rest of an entry is only read after its meta was published)
+static __global__ void __launch_bounds__(256) memo_clear_kernel(MemoEntry *memo, uint32_t n_slots, unsigned long long *long_cursor) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) {
+        uint4 *e = reinterpret_cast<uint4 *>(memo + i);
+        e[0] = z; e[1] = z;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *long_cursor = 0ull;
+}
+
 // ---- pass 1: count ---------------------------------------------------------------------------------------------------
 // Enc provides
 //   uint32_t encode_short(const uint8_t *p, uint32_t nbytes, uint32_t *buf /*thread-local, kShortBytes*/, uint32_t &h6) const
@@ -268,7 +286,6 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
     const uint32_t arena_end = word_off[n_words];
     const bool use_memo = ws.memo_mask != 0;
     uint32_t h6 = 0;
-    uint32_t buf[kShortBytes];                                   // thread-local scratch for one directly encoded word
 
     for (uint32_t tile = warp_global; tile < ws.n_tiles; tile += n_warps) {
         const uint32_t w_tile = tile * kTileWords;
@@ -283,53 +300,53 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
             b0s[0] = o0; nb[0] = i0 < tile_words ? o1 - o0 : 0xFFFFFFFFu;       // 0xFFFFFFFF: no word
             b0s[1] = o1; nb[1] = i0 + 1 < tile_words ? o2 - o1 : 0xFFFFFFFFu;
         }
-        // ---- fast path = the first memo probe (L1-cached) hits
+        // ---- fast path: key from aligned 8-byte loads, then up to two L1-cached memo probes.  Both words' loads are in
+        // flight together.
         uint32_t kind[kWordsPerThread], ntok[kWordsPerThread], slot[kWordsPerThread];
-        unsigned long long klo[kWordsPerThread], khi[kWordsPerThread];
-        uint32_t meta[kWordsPerThread];
-#pragma unroll
-        for (int j = 0; j < kWordsPerThread; ++j) { kind[j] = kWordNone; ntok[j] = 0; slot[j] = 0; klo[j] = khi[j] = ~0ull; meta[j] = 0; }
-        if (use_memo) {
-            // words of 1..15 bytes: request the (up to three) aligned 8-byte words of both words, then both probes
-            unsigned long long r0[kWordsPerThread], r1[kWordsPerThread], r2[kWordsPerThread];
-            bool fastj[kWordsPerThread];
-#pragma unroll
-            for (int j = 0; j < kWordsPerThread; ++j) {
-                fastj[j] = nb[j] >= 1 && nb[j] <= 15 && (uint64_t)b0s[j] + 24 <= arena_end;
-                r0[j] = r1[j] = r2[j] = 0;
-                if (fastj[j]) {
-                    const uintptr_t a = (uintptr_t)(arena + b0s[j]);
-                    const unsigned long long *q = (const unsigned long long *)(a & ~(uintptr_t)7);
-                    r0[j] = __ldg(q); r1[j] = __ldg(q + 1);
-                    if (nb[j] + (uint32_t)(a & 7) > 16) r2[j] = __ldg(q + 2);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < kWordsPerThread; ++j) {
-                if (fastj[j]) {
-                    const uint32_t sh = (uint32_t)((uintptr_t)(arena + b0s[j]) & 7) * 8;
-                    unsigned long long lo = r0[j], hi = r1[j], elo, ehi;
-                    if (sh) { lo = (r0[j] >> sh) | (r1[j] << (64 - sh)); hi = (r1[j] >> sh) | (r2[j] << (64 - sh)); }
-                    if (nb[j] < 8) { lo &= (1ull << (8 * nb[j])) - 1; hi = 0; }
-                    else hi = nb[j] == 8 ? 0ull : hi & ((1ull << (8 * (nb[j] - 8))) - 1);
-                    hi |= (unsigned long long)nb[j] << 56;
-                    slot[j] = (uint32_t)mix64(lo ^ (hi * 0x9E3779B97F4A7C15ull)) & ws.memo_mask;
-                    const MemoEntry *e = ws.memo + slot[j];
-                    ld_ca_u64x2(e, elo, ehi);
-                    meta[j] = ld_ca_u32(&e->meta);
-                    klo[j] = lo ^ elo; khi[j] = hi ^ ehi;                            // zero iff the entry holds this word
-                }
-            }
-        }
-        bool slow[kWordsPerThread], is_long[kWordsPerThread];
+        MemoKey key[kWordsPerThread];
+        bool fastj[kWordsPerThread], slow[kWordsPerThread], is_long[kWordsPerThread];
 #pragma unroll
         for (int j = 0; j < kWordsPerThread; ++j) {
-            slow[j] = false; is_long[j] = false;
+            kind[j] = kWordNone; ntok[j] = 0; slot[j] = 0; slow[j] = false;
+            is_long[j] = nb[j] != 0xFFFFFFFFu && nb[j] > (uint32_t)kShortBytes;
+            fastj[j] = use_memo && nb[j] >= 1 && nb[j] <= (uint32_t)kShortBytes && (uint64_t)b0s[j] + 40 <= arena_end;
+            if (fastj[j]) memo_key(arena, b0s[j], nb[j], arena_end, key[j]);
+        }
+        unsigned long long elo[kWordsPerThread], ehi[kWordsPerThread], eta[kWordsPerThread], etb[kWordsPerThread];
+        uint2 mt[kWordsPerThread];
+#pragma unroll
+        for (int j = 0; j < kWordsPerThread; ++j) {
+            elo[j] = ehi[j] = eta[j] = etb[j] = 0; mt[j] = make_uint2(0, 0);
+            if (fastj[j]) {
+                slot[j] = (uint32_t)mix64(key[j].lo ^ (key[j].hi * 0x9E3779B97F4A7C15ull)) & ws.memo_mask;
+                const MemoEntry *e = ws.memo + slot[j];
+                ld_ca_u64x2(e, elo[j], ehi[j]);
+                mt[j] = ld_ca_u32x2(&e->meta);
+                if (nb[j] > 15) ld_ca_u64x2(&e->tail_a, eta[j], etb[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kWordsPerThread; ++j) {
             if (nb[j] == 0xFFFFFFFFu) continue;
-            if (nb[j] > (uint32_t)kShortBytes) { kind[j] = kWordLong; is_long[j] = true; }
-            else if ((klo[j] | khi[j]) == 0 && meta[j] != 0 && meta[j] != 0xFFFFFFFFu) {
-                kind[j] = kWordHit; ntok[j] = (meta[j] & 0xFFu) - 1; h6 += meta[j] >> 8;
-            } else slow[j] = true;
+            if (is_long[j]) { kind[j] = kWordLong; continue; }
+            bool hit = false;
+            if (fastj[j]) {
+                bool same = elo[j] == key[j].lo && ehi[j] == key[j].hi;
+                bool full = same && (nb[j] <= 15 || (eta[j] == key[j].tail_a && etb[j] == key[j].tail_b && mt[j].y == key[j].tail_last));
+                if (!full && (elo[j] | ehi[j]) != 0 && !(same && (mt[j].x == 0 || mt[j].x == 0xFFFFFFFFu))) {
+                    // the slot holds another word (hash collision, or the same 15-byte prefix): look at the next slot
+                    slot[j] = (slot[j] + 1) & ws.memo_mask;
+                    const MemoEntry *e = ws.memo + slot[j];
+                    ld_ca_u64x2(e, elo[j], ehi[j]);
+                    mt[j] = ld_ca_u32x2(&e->meta);
+                    same = elo[j] == key[j].lo && ehi[j] == key[j].hi;
+                    full = same;
+                    if (same && nb[j] > 15) { ld_ca_u64x2(&e->tail_a, eta[j], etb[j]); full = eta[j] == key[j].tail_a && etb[j] == key[j].tail_b && mt[j].y == key[j].tail_last; }
+                }
+                hit = full && mt[j].x != 0 && mt[j].x != 0xFFFFFFFFu;
+            }
+            if (hit) { kind[j] = kWordHit; ntok[j] = (mt[j].x & 0xFFu) - 1; h6 += mt[j].x >> 8; }
+            else slow[j] = true;
         }
         // words not served by the first probe (longer than 15 bytes, hash collision, first occurrence) are spread over the
         // lanes of the warp so that they are resolved side by side instead of one lane at a time
@@ -341,7 +358,7 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
             const uint32_t src = __fns(m, 0, lane + 1);                             // lane -> owner of the lane-th slow word
             const uint32_t sb0 = __shfl_sync(0xffffffffu, b0s[j], src & 31), snb = __shfl_sync(0xffffffffu, nb[j], src & 31);
             SlowResult r; r.kind = kWordNone; r.ntok = 0; r.slot = 0; r.h6 = 0;
-            if (lane < n_slow) r = resolve_slow(enc, ws, arena, sb0, snb, arena_end, buf, status);
+            if (lane < n_slow) r = resolve_slow(enc, ws, arena, sb0, snb, arena_end, status);
             h6 += r.h6;
             const uint32_t rank = __popc(m & ((1u << lane) - 1u));                 // this lane's word was resolved by lane `rank`
             const uint32_t k_ = __shfl_sync(0xffffffffu, r.kind, rank), n_ = __shfl_sync(0xffffffffu, r.ntok, rank);
@@ -452,7 +469,6 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
     const uint32_t warp_global = (blockIdx.x * kThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kThreads) >> 5;
     const bool tok_off_vec = out_tok_off && (((uintptr_t)out_tok_off & 7) == 0);
     uint32_t *compact = s_compact[threadIdx.x >> 5];
-    uint32_t buf[kShortBytes];
 
     for (uint32_t tile = warp_global; tile < ws.n_tiles; tile += n_warps) {
         const uint32_t w_tile = tile * kTileWords;
@@ -510,7 +526,7 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
             } else if (kind[j] == kWordRecompute || (!Enc::kScratchLong && kind[j] == kWordLong)) {
                 uint32_t *dst = use_compact ? compact + run[j] : out_ids + base + run[j];
                 const uint32_t b0 = __ldg(word_off + w_tile + i0 + j), b1 = __ldg(word_off + w_tile + i0 + j + 1);
-                emit_slow(enc, arena + b0, b1 - b0, kind[j], ntok[j], buf, dst);
+                emit_slow(enc, arena + b0, b1 - b0, kind[j], ntok[j], dst);
             }
         }
         if constexpr (Enc::kScratchLong) {                                          // long results: the warp copies them together
@@ -556,7 +572,6 @@ int launch_encode_tiles(const Enc &enc, const uint8_t *d_arena, const uint32_t *
     EncodeWorkspace ws;
     size_t need = encode_workspace_layout(n_words, long_word_bytes, d_workspace, &ws);
     if (need > workspace_bytes) { set_error("encode workspace too small"); return SWT_ERR_CAPACITY; }
-    SWT_CUDA_OK(cudaMemsetAsync(d_workspace, 0, ws.zero_bytes, st));
     SWT_CUDA_OK(cudaMemsetAsync(d_status, 0, 8 * sizeof(uint32_t), st));
     if (n_words == 0) {
         if (d_out_tok_off) SWT_CUDA_OK(cudaMemcpyAsync(d_out_tok_off, &tok_base, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
@@ -568,11 +583,28 @@ int launch_encode_tiles(const Enc &enc, const uint8_t *d_arena, const uint32_t *
         grid2 = encode_grid((const void *)encode_emit_kernel<Enc>, kThreads, 0);
     }
     const uint32_t n_ctas = (ws.n_tiles + kWarps - 1) / kWarps, n_groups = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
+    // SWT_TIMING=1: per-kernel CUDA-event times of this call on stderr (diagnostic; synchronises)
+    static const bool timing = getenv("SWT_TIMING") != nullptr;
+    cudaEvent_t ev[6];
+    if (timing) for (auto &e : ev) cudaEventCreate(&e);
+    if (timing) cudaEventRecord(ev[0], st);
+    memo_clear_kernel<<<kNumSMs * 8, 256, 0, st>>>(ws.memo, ws.memo_mask + 1, ws.long_cursor);
+    if (timing) cudaEventRecord(ev[1], st);
     encode_count_kernel<Enc><<<(int)std::min<uint32_t>((uint32_t)grid1, n_ctas), kThreads, 0, st>>>(enc, d_arena, d_word_off, n_words, ws, d_status);
+    if (timing) cudaEventRecord(ev[2], st);
     encode_scan_groups_kernel<<<n_groups, 256, 0, st>>>(ws);
+    if (timing) cudaEventRecord(ev[3], st);
     encode_scan_top_kernel<<<1, 1024, 0, st>>>(ws, n_words, d_out_tok_off, tok_base, out_cap, d_status);
+    if (timing) cudaEventRecord(ev[4], st);
     encode_emit_kernel<Enc><<<(int)std::min<uint32_t>((uint32_t)grid2, n_ctas), kThreads, 0, st>>>(enc, d_arena, d_word_off, n_words, d_out_ids, out_cap,
                                                                                                    d_out_tok_off, tok_base, ws);
+    if (timing) {
+        cudaEventRecord(ev[5], st); cudaEventSynchronize(ev[5]);
+        float t[5];
+        for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+        fprintf(stderr, "[swt timing] clear %.3f count %.3f scan %.3f+%.3f emit %.3f ms (grid %d/%d, %u tiles)\n", t[0], t[1], t[2], t[3], t[4], grid1, grid2, ws.n_tiles);
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
     SWT_CUDA_OK(cudaGetLastError());
     return SWT_OK;
 }
