@@ -330,3 +330,63 @@ def test_large_stream_properties(P, dev):
         assert int(tok_off[-1]) == len(ids)
         gidx = np.repeat(t_tok_off[:-1].astype(np.int64)[draw] - tok_off[:-1].astype(np.int64), tl[draw]) + np.arange(len(ids))
         assert np.array_equal(ids, t_ids[gidx])
+
+
+# ------------------------------------------------------------------------------------------------ memo / capacity edge cases
+def test_all_distinct_words_overflow_the_memo(P, dev):
+    """No repetition at all: the memo (n_words/4 slots) fills up, later words take the direct / recompute path."""
+    import oracle
+    rng = np.random.default_rng(21)
+    alphabet = list("abcdeiknorstwyzłąę.,")
+    words = list({"".join(rng.choice(alphabet, size=int(rng.integers(1, 30)))) for _ in range(120_000)})
+    tab = P.BpeTables([tuple(p) for p in load_golden("pretrained_bpe_merges.json.gz")])
+    wtab, wenc = _wp_encoder(P, dev, load_golden("pretrained_wp_vocab.json.gz"))
+    benc = dev.BpeEncoder(tab)
+    arena, off = P.pack_words(words)
+    alnum, space = P.unicode_class_bitmaps()
+    ids, tok_off, _ = benc.encode_packed(arena, off.astype(np.uint32))
+    o_ids, o_off = oracle.bpe_encode(tab, arena, off)
+    assert np.array_equal(ids, o_ids) and np.array_equal(tok_off.astype(np.uint64), o_off)
+    ids, tok_off, h6 = wenc.encode_packed(arena, off.astype(np.uint32))
+    o_ids, o_off, o_h6 = oracle.WpTrie(wtab, alnum).encode(arena, off, space)
+    assert np.array_equal(ids, o_ids) and np.array_equal(tok_off.astype(np.uint64), o_off) and h6 == o_h6
+
+
+def test_words_sharing_a_15_byte_prefix(P, dev):
+    """The 128-bit memo key is the first 15 bytes + length; longer words with equal prefix and length must not alias."""
+    import oracle
+    base = "abcdefghijklmno"                                    # 15 bytes
+    words = [base + s for s in ("p", "q", "pq", "qp", "pqrstuvwxyzabcdef"[:17], "pqrstuvwxyzabcdeg"[:17])] * 50
+    words += [base, base + "p"] * 50
+    tab = P.BpeTables([("a", "b"), ("ab", "c"), ("o", "p"), ("o", "q"), ("p", "q")])
+    benc = dev.BpeEncoder(tab)
+    arena, off = P.pack_words(words)
+    ids, tok_off, _ = benc.encode_packed(arena, off.astype(np.uint32))
+    o_ids, o_off = oracle.bpe_encode(tab, arena, off)
+    assert np.array_equal(ids, o_ids) and np.array_equal(tok_off.astype(np.uint64), o_off)
+
+
+def test_output_capacity_is_checked(P, dev):
+    import torch
+    from subword_tokenizers_b200._lib import SwtError
+    tab = P.BpeTables([("a", "b")])
+    benc = dev.BpeEncoder(tab)
+    arena, off = P.pack_words(["xyz"] * 1000)
+    d_arena = torch.from_numpy(arena).cuda()
+    d_off = torch.from_numpy(off.astype(np.uint32).view(np.int32)).cuda()
+    d_ids, d_tok, d_status = benc.encode_device(d_arena, d_off, 1000, 0, out_cap=100)
+    with pytest.raises(SwtError):
+        benc.check_status(d_status)
+
+
+def test_encode_host_without_token_offsets(P, dev):
+    import torch
+    tab = P.BpeTables([tuple(p) for p in load_golden("pretrained_bpe_merges.json.gz")])
+    benc = dev.BpeEncoder(tab)
+    words = [w for l in load_golden("pan_tadeusz.json.gz") for w in l.lower().split()]
+    arena, off = P.pack_words(words)
+    ids, _, _ = benc.encode_packed(arena, off.astype(np.uint32))
+    h_ids = torch.empty(len(arena) + len(words) + 16, dtype=torch.int32).pin_memory()
+    nt, _ = benc.encode_host(torch.from_numpy(arena).pin_memory(), torch.from_numpy(off.astype(np.uint32).view(np.int32)).pin_memory(),
+                             h_ids, None, batch_bytes=1 << 16)
+    assert nt == len(ids) and np.array_equal(h_ids.numpy()[:nt].view(np.uint32), ids)
