@@ -35,6 +35,7 @@ namespace swt {
 constexpr int kWarps = 8;              // warps per CTA; every warp owns its own tile
 constexpr int kThreads = kWarps * 32;
 constexpr int kCtasPerSm = 4;
+constexpr int kEmitCtasPerSm = 4;
 constexpr int kWordsPerThread = 2;
 constexpr int kTileWords = 32 * kWordsPerThread;         // 64 words per (warp) tile
 constexpr int kShortBytes = 32;        // words up to this many bytes are encoded by one thread (and memoised)
@@ -159,11 +160,23 @@ __device__ __forceinline__ void memo_key(const uint8_t *arena, uint32_t b0, uint
     k.nbytes = nbytes;
 }
 
+// slot hash of a key, in 32-bit operations (the 64-bit mixer costs ~4x the instructions on the fast path)
+__device__ __forceinline__ uint32_t memo_hash4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    uint32_t h = (w0 ^ 0x9E3779B9u) * 0x85EBCA6Bu;
+    h = (h ^ (h >> 15) ^ w1) * 0xC2B2AE35u;
+    h = (h ^ (h >> 13) ^ w2) * 0x27D4EB2Fu;
+    h = (h ^ (h >> 16) ^ w3) * 0x165667B1u;
+    return h ^ (h >> 15);
+}
+__device__ __forceinline__ uint32_t memo_hash(unsigned long long lo, unsigned long long hi) {
+    return memo_hash4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+}
+
 // Probes the memo.  kMemoHit: slot/meta describe a published entry for exactly this word, t01 holds its first two
 // ids.  kMemoClaimed: this thread now owns `slot` and must call memo_publish after encoding.  kMemoMiss: encode
 // directly, publish nothing.  `first` is the probe index to start from (the caller may have checked probe 0 itself).
 static __device__ __noinline__ int memo_probe(const EncodeWorkspace &ws, const MemoKey &key, uint32_t &slot, uint32_t &meta_out, uint2 &t01) {
-    uint32_t h = (uint32_t)mix64(key.lo ^ (key.hi * 0x9E3779B97F4A7C15ull)) & ws.memo_mask;
+    uint32_t h = memo_hash(key.lo, key.hi) & ws.memo_mask;
     for (int probe = 0; probe < kMemoProbes; ++probe, h = (h + 1) & ws.memo_mask) {
         MemoEntry *e = ws.memo + h;
         unsigned long long klo, khi;
@@ -237,8 +250,8 @@ __device__ __noinline__ void emit_slow(const Enc &enc, const uint8_t *word, uint
     }
 }
 
-// ids of a memo hit -> dst (ids 0-9 were prefetched, the rest is fetched here)
-__device__ __forceinline__ void store_hit_ids(uint32_t *dst, uint32_t n, uint4 m, uint4 c0, uint4 c1, const MemoEntry *e) {
+// ids of a memo hit -> dst (ids 0-13 were prefetched, the rest is fetched here)
+__device__ __forceinline__ void store_hit_ids(uint32_t *dst, uint32_t n, uint4 m, uint4 c0, uint4 c1, uint4 c2, const MemoEntry *e) {
     if (n > 0) dst[0] = m.z;
     if (n > 1) dst[1] = m.w;
     if (n > 2) dst[2] = c0.x;
@@ -249,7 +262,11 @@ __device__ __forceinline__ void store_hit_ids(uint32_t *dst, uint32_t n, uint4 m
     if (n > 7) dst[7] = c1.y;
     if (n > 8) dst[8] = c1.z;
     if (n > 9) dst[9] = c1.w;
-    for (uint32_t k0 = 8; k0 + 2 < n; k0 += 4) {
+    if (n > 10) dst[10] = c2.x;
+    if (n > 11) dst[11] = c2.y;
+    if (n > 12) dst[12] = c2.z;
+    if (n > 13) dst[13] = c2.w;
+    for (uint32_t k0 = 12; k0 + 2 < n; k0 += 4) {
         const uint4 v = ld_ca_u32x4(&e->tok[k0]);
         dst[k0 + 2] = v.x;
         if (k0 + 3 < n) dst[k0 + 3] = v.y;
@@ -300,29 +317,49 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
             b0s[0] = o0; nb[0] = i0 < tile_words ? o1 - o0 : 0xFFFFFFFFu;       // 0xFFFFFFFF: no word
             b0s[1] = o1; nb[1] = i0 + 1 < tile_words ? o2 - o1 : 0xFFFFFFFFu;
         }
-        // ---- fast path: key from aligned 8-byte loads, then up to two L1-cached memo probes.  Both words' loads are in
-        // flight together.
+        // ---- fast path (words of 1..15 bytes): 128-bit key from aligned 8-byte loads, then up to two L1-cached memo
+        // probes.  Both words' loads are in flight together.
         uint32_t kind[kWordsPerThread], ntok[kWordsPerThread], slot[kWordsPerThread];
-        MemoKey key[kWordsPerThread];
+        uint4 kw[kWordsPerThread], ew[kWordsPerThread];           // key of the word / key found in the probed entry
+        uint32_t meta[kWordsPerThread];
         bool fastj[kWordsPerThread], slow[kWordsPerThread], is_long[kWordsPerThread];
+        {
+            uint32_t a0[kWordsPerThread], a1[kWordsPerThread], a2[kWordsPerThread], a3[kWordsPerThread], a4[kWordsPerThread];
 #pragma unroll
-        for (int j = 0; j < kWordsPerThread; ++j) {
-            kind[j] = kWordNone; ntok[j] = 0; slot[j] = 0; slow[j] = false;
-            is_long[j] = nb[j] != 0xFFFFFFFFu && nb[j] > (uint32_t)kShortBytes;
-            fastj[j] = use_memo && nb[j] >= 1 && nb[j] <= (uint32_t)kShortBytes && (uint64_t)b0s[j] + 40 <= arena_end;
-            if (fastj[j]) memo_key(arena, b0s[j], nb[j], arena_end, key[j]);
-        }
-        unsigned long long elo[kWordsPerThread], ehi[kWordsPerThread], eta[kWordsPerThread], etb[kWordsPerThread];
-        uint2 mt[kWordsPerThread];
+            for (int j = 0; j < kWordsPerThread; ++j) {
+                kind[j] = kWordNone; ntok[j] = 0; slot[j] = 0; slow[j] = false; meta[j] = 0;
+                kw[j] = ew[j] = make_uint4(0, 0, 0, 0);
+                is_long[j] = nb[j] != 0xFFFFFFFFu && nb[j] > (uint32_t)kShortBytes;
+                fastj[j] = use_memo && nb[j] >= 1 && nb[j] <= 15 && (uint64_t)b0s[j] + 24 <= arena_end;
+                a0[j] = a1[j] = a2[j] = a3[j] = a4[j] = 0;
+                if (fastj[j]) {                                   // the (up to five) aligned 32-bit words that hold the word
+                    const uintptr_t a = (uintptr_t)(arena + b0s[j]);
+                    const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
+                    const uint32_t span = nb[j] + (uint32_t)(a & 3);
+                    a0[j] = __ldg(q);
+                    if (span > 4) a1[j] = __ldg(q + 1);
+                    if (span > 8) a2[j] = __ldg(q + 2);
+                    if (span > 12) a3[j] = __ldg(q + 3);
+                    if (span > 16) a4[j] = __ldg(q + 4);
+                }
+            }
 #pragma unroll
-        for (int j = 0; j < kWordsPerThread; ++j) {
-            elo[j] = ehi[j] = eta[j] = etb[j] = 0; mt[j] = make_uint2(0, 0);
-            if (fastj[j]) {
-                slot[j] = (uint32_t)mix64(key[j].lo ^ (key[j].hi * 0x9E3779B97F4A7C15ull)) & ws.memo_mask;
-                const MemoEntry *e = ws.memo + slot[j];
-                ld_ca_u64x2(e, elo[j], ehi[j]);
-                mt[j] = ld_ca_u32x2(&e->meta);
-                if (nb[j] > 15) ld_ca_u64x2(&e->tail_a, eta[j], etb[j]);
+            for (int j = 0; j < kWordsPerThread; ++j) {
+                if (fastj[j]) {
+                    const uint32_t sh = (uint32_t)((uintptr_t)(arena + b0s[j]) & 3) * 8, n = nb[j];
+                    uint32_t w0 = __funnelshift_r(a0[j], a1[j], sh), w1 = __funnelshift_r(a1[j], a2[j], sh);
+                    uint32_t w2 = __funnelshift_r(a2[j], a3[j], sh), w3 = __funnelshift_r(a3[j], a4[j], sh);
+                    // zero the bytes at and beyond n, put the length into the top byte (layout of MemoEntry::lo/hi)
+                    w0 = n >= 4 ? w0 : w0 & ((1u << (8 * n)) - 1u);
+                    w1 = n >= 8 ? w1 : (n > 4 ? w1 & ((1u << (8 * (n - 4))) - 1u) : 0u);
+                    w2 = n >= 12 ? w2 : (n > 8 ? w2 & ((1u << (8 * (n - 8))) - 1u) : 0u);
+                    w3 = (n > 12 ? w3 & ((1u << (8 * (n - 12))) - 1u) : 0u) | (n << 24);
+                    kw[j] = make_uint4(w0, w1, w2, w3);
+                    slot[j] = memo_hash4(w0, w1, w2, w3) & ws.memo_mask;
+                    const MemoEntry *e = ws.memo + slot[j];
+                    ew[j] = ld_ca_u32x4(e);
+                    meta[j] = ld_ca_u32(&e->meta);
+                }
             }
         }
 #pragma unroll
@@ -331,21 +368,18 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
             if (is_long[j]) { kind[j] = kWordLong; continue; }
             bool hit = false;
             if (fastj[j]) {
-                bool same = elo[j] == key[j].lo && ehi[j] == key[j].hi;
-                bool full = same && (nb[j] <= 15 || (eta[j] == key[j].tail_a && etb[j] == key[j].tail_b && mt[j].y == key[j].tail_last));
-                if (!full && (elo[j] | ehi[j]) != 0 && !(same && (mt[j].x == 0 || mt[j].x == 0xFFFFFFFFu))) {
-                    // the slot holds another word (hash collision, or the same 15-byte prefix): look at the next slot
+                bool same = ew[j].x == kw[j].x && ew[j].y == kw[j].y && ew[j].z == kw[j].z && ew[j].w == kw[j].w;
+                if (!same && (ew[j].x | ew[j].y | ew[j].z | ew[j].w) != 0) {
+                    // the slot holds another word (hash collision): look at the next slot
                     slot[j] = (slot[j] + 1) & ws.memo_mask;
                     const MemoEntry *e = ws.memo + slot[j];
-                    ld_ca_u64x2(e, elo[j], ehi[j]);
-                    mt[j] = ld_ca_u32x2(&e->meta);
-                    same = elo[j] == key[j].lo && ehi[j] == key[j].hi;
-                    full = same;
-                    if (same && nb[j] > 15) { ld_ca_u64x2(&e->tail_a, eta[j], etb[j]); full = eta[j] == key[j].tail_a && etb[j] == key[j].tail_b && mt[j].y == key[j].tail_last; }
+                    ew[j] = ld_ca_u32x4(e);
+                    meta[j] = ld_ca_u32(&e->meta);
+                    same = ew[j].x == kw[j].x && ew[j].y == kw[j].y && ew[j].z == kw[j].z && ew[j].w == kw[j].w;
                 }
-                hit = full && mt[j].x != 0 && mt[j].x != 0xFFFFFFFFu;
+                hit = same && meta[j] != 0 && meta[j] != 0xFFFFFFFFu;
             }
-            if (hit) { kind[j] = kWordHit; ntok[j] = (mt[j].x & 0xFFu) - 1; h6 += mt[j].x >> 8; }
+            if (hit) { kind[j] = kWordHit; ntok[j] = (meta[j] & 0xFFu) - 1; h6 += meta[j] >> 8; }
             else slow[j] = true;
         }
         // words not served by the first probe (longer than 15 bytes, hash collision, first occurrence) are spread over the
@@ -460,7 +494,7 @@ static __global__ void __launch_bounds__(1024) encode_scan_top_kernel(EncodeWork
 
 // ---- pass 2: emit ------------------------------------------------------------------------------------------------------
 template <class Enc>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+__global__ void __launch_bounds__(kThreads, kEmitCtasPerSm)
 encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words,
                    uint32_t *__restrict__ out_ids, uint64_t out_cap, uint32_t *__restrict__ out_tok_off, uint32_t tok_base,
                    EncodeWorkspace ws) {
@@ -479,18 +513,19 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
         else if (i0 < tile_words) packed[0] = ws.packed[w_tile + i0];
         const uint64_t base = ws.group_base[tile / kGroupTiles] + ws.tile_total[tile];
         uint32_t kind[kWordsPerThread], ntok[kWordsPerThread], arg[kWordsPerThread];
-        uint4 m[kWordsPerThread], c0[kWordsPerThread], c1[kWordsPerThread];
+        uint4 m[kWordsPerThread], c0[kWordsPerThread], c1[kWordsPerThread], c2[kWordsPerThread];
 #pragma unroll
         for (int j = 0; j < kWordsPerThread; ++j) {
             kind[j] = packed[j] >> 29;
             arg[j] = packed[j] & 0x1FFFFFFFu;
             ntok[j] = (kind[j] == kWordHit || kind[j] == kWordRecompute) ? (arg[j] >> 23) : (kind[j] == kWordLong && !Enc::kScratchLong) ? arg[j] : 0u;
-            m[j] = c0[j] = c1[j] = make_uint4(0, 0, 0, 0);
+            m[j] = c0[j] = c1[j] = c2[j] = make_uint4(0, 0, 0, 0);
             if (kind[j] == kWordHit) {                              // all id loads of both words are in flight together
                 const MemoEntry *e = ws.memo + (arg[j] & 0xFFFFFu);
                 m[j] = ld_ca_u32x4(&e->meta);
                 if (ntok[j] > 2) c0[j] = ld_ca_u32x4(&e->tok[0]);
                 if (ntok[j] > 6) c1[j] = ld_ca_u32x4(&e->tok[4]);
+                if (ntok[j] > 10) c2[j] = ld_ca_u32x4(&e->tok[8]);
             }
             if constexpr (Enc::kScratchLong) {
                 if (kind[j] == kWordLong || kind[j] == kWordLongB) ntok[j] = ws.long_scratch[(unsigned long long)arg[j] << 4];
@@ -521,8 +556,8 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
         for (int j = 0; j < kWordsPerThread; ++j) {
             if (kind[j] == kWordHit) {
                 // two copies of the same code so that the common case compiles to shared-memory stores (STS)
-                if (use_compact) store_hit_ids(compact + run[j], ntok[j], m[j], c0[j], c1[j], ws.memo + (arg[j] & 0xFFFFFu));
-                else store_hit_ids(out_ids + base + run[j], ntok[j], m[j], c0[j], c1[j], ws.memo + (arg[j] & 0xFFFFFu));
+                if (use_compact) store_hit_ids(compact + run[j], ntok[j], m[j], c0[j], c1[j], c2[j], ws.memo + (arg[j] & 0xFFFFFu));
+                else store_hit_ids(out_ids + base + run[j], ntok[j], m[j], c0[j], c1[j], c2[j], ws.memo + (arg[j] & 0xFFFFFu));
             } else if (kind[j] == kWordRecompute || (!Enc::kScratchLong && kind[j] == kWordLong)) {
                 uint32_t *dst = use_compact ? compact + run[j] : out_ids + base + run[j];
                 const uint32_t b0 = __ldg(word_off + w_tile + i0 + j), b1 = __ldg(word_off + w_tile + i0 + j + 1);
