@@ -40,20 +40,25 @@ constexpr int kWordsPerThread = 2;
 constexpr int kTileWords = 32 * kWordsPerThread;         // 64 words per (warp) tile
 constexpr int kShortBytes = 32;        // words up to this many bytes are encoded by one thread (and memoised)
 constexpr int kCompactTokens = 1024;   // tile token totals up to this are assembled in smem before the store
-constexpr int kMemoTokens = 54;        // >= kShortBytes: every word of up to 32 bytes fits (ids <= bytes)
+constexpr int kMemoTokens = 44;        // >= kShortBytes: every word of up to 32 bytes fits (ids <= bytes)
 constexpr int kMemoProbes = 8;
 
 // status words written by the encode kernels
 enum { kStatusCode = 0, kStatusTokens = 1, kStatusH6 = 2, kStatusTokensHi = 3, kStatusMemoTypes = 4 };
 
-struct alignas(256) MemoEntry {         // 256 bytes; a typical hit touches the first 32-96 bytes only
-    unsigned long long lo, hi;          // CAS key: word bytes 0..7 | bytes 8..14 + (length << 56); 0/0 == empty
+struct alignas(256) MemoEntry {         // 256 bytes; a fast-path hit touches the first 16 (count pass) + 16..32 (emit pass) bytes
+    unsigned long long lo, hi;          // CAS key: word bytes 0..7 | bytes 8..14, bits 56-59 = length (0 for words > 15 bytes),
+                                        // bits 60-63 = "pub": 0, or n_tokens + 1 once ids16[] is valid (set after the CAS claim)
+    uint16_t ids16[16];                 // ids 0..15 as 16-bit values (only when every id of the word is < 65536)
     uint32_t meta;                      // 0 = claimed, not published; else (n_tokens + 1) | (h6 << 8); ~0 = not cacheable
-    uint32_t tail_last;                 // byte 31
-    uint32_t tok01[2];                  // ids 0 and 1: a word of up to two ids is served by the first 32-byte sector
-    unsigned long long tail_a, tail_b;  // bytes 15..22 | 23..30 (words longer than 15 bytes; verified after the key)
-    uint32_t tok[kMemoTokens - 2];      // ids 2.. at byte 48
+    uint32_t tail_last;                 // words > 15 bytes: byte 31 | length << 8
+    uint32_t pad[2];
+    unsigned long long tail_a, tail_b;  // at byte 64; words > 15 bytes: bytes 15..22 | 23..30 (verified after the key)
+    uint32_t tok[kMemoTokens];          // all ids as 32-bit values, at byte 80
 };
+static_assert(sizeof(MemoEntry) == 256, "MemoEntry must be 256 bytes");
+constexpr unsigned long long kPubMask = 0xFull << 60;
+
 struct MemoKey { unsigned long long lo, hi, tail_a, tail_b; uint32_t tail_last; uint32_t nbytes; };
 
 struct EncodeWorkspace {
@@ -83,6 +88,11 @@ __device__ __forceinline__ void cas128(MemoEntry *e, unsigned long long lo, unsi
 // the memo is written during the launch: read it at L2 (never through the non-coherent L1)
 __device__ __forceinline__ void ld_cg_u64x2(const void *p, unsigned long long &a, unsigned long long &b) {
     asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ uint2 ld_cg_u32x2(const void *p) {
+    uint2 v;
+    asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ uint4 ld_cg_u32x4(const void *p) {
     uint4 v;
@@ -153,10 +163,10 @@ __device__ __forceinline__ void memo_key(const uint8_t *arena, uint32_t b0, uint
     else if (nbytes < 24) { w2 = nbytes == 16 ? 0ull : w2 & ((1ull << (8 * (nbytes - 16))) - 1); w3 = 0; }
     else if (nbytes < 32) { w3 = nbytes == 24 ? 0ull : w3 & ((1ull << (8 * (nbytes - 24))) - 1); }
     k.lo = w0;
-    k.hi = (w1 & ((1ull << 56) - 1)) | ((unsigned long long)nbytes << 56);
+    k.hi = (w1 & ((1ull << 56) - 1)) | ((unsigned long long)(nbytes <= 15 ? nbytes : 0u) << 56);
     k.tail_a = (w1 >> 56) | (w2 << 8);
     k.tail_b = (w2 >> 56) | (w3 << 8);
-    k.tail_last = (uint32_t)(w3 >> 56);
+    k.tail_last = (uint32_t)(w3 >> 56) | (nbytes << 8);
     k.nbytes = nbytes;
 }
 
@@ -172,29 +182,29 @@ __device__ __forceinline__ uint32_t memo_hash(unsigned long long lo, unsigned lo
     return memo_hash4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
 }
 
-// Probes the memo.  kMemoHit: slot/meta describe a published entry for exactly this word, t01 holds its first two
-// ids.  kMemoClaimed: this thread now owns `slot` and must call memo_publish after encoding.  kMemoMiss: encode
-// directly, publish nothing.  `first` is the probe index to start from (the caller may have checked probe 0 itself).
-static __device__ __noinline__ int memo_probe(const EncodeWorkspace &ws, const MemoKey &key, uint32_t &slot, uint32_t &meta_out, uint2 &t01) {
+// Probes the memo at L2 (slow path).  kMemoHit: slot/meta describe a published entry for exactly this word.
+// kMemoClaimed: this thread now owns `slot` and must call memo_publish after encoding.  kMemoMiss: encode directly,
+// publish nothing.
+static __device__ __noinline__ int memo_probe(const EncodeWorkspace &ws, const MemoKey &key, uint32_t &slot, uint32_t &meta_out) {
     uint32_t h = memo_hash(key.lo, key.hi) & ws.memo_mask;
     for (int probe = 0; probe < kMemoProbes; ++probe, h = (h + 1) & ws.memo_mask) {
         MemoEntry *e = ws.memo + h;
         unsigned long long klo, khi;
         ld_cg_u64x2(e, klo, khi);
-        uint4 m = ld_cg_u32x4(&e->meta);                                 // meta, tail_last, id0, id1 (same sector as the key)
+        uint2 m = ld_cg_u32x2(&e->meta);                                 // meta, tail_last
         if (klo == 0 && khi == 0) {
             cas128(e, key.lo, key.hi, klo, khi);
             if (klo == 0 && khi == 0) { slot = h; return kMemoClaimed; }
             m.x = 0;                                                     // lost the race: the winner has not published yet
         }
-        if (klo != key.lo || khi != key.hi) continue;
+        if (klo != key.lo || (khi & ~kPubMask) != key.hi) continue;
         if (m.x == 0 || m.x == 0xFFFFFFFFu) return kMemoMiss;            // not published yet / not cacheable
-        if (key.nbytes > 15) {                                           // same 15-byte prefix and length: check the rest
+        if (key.nbytes > 15) {                                           // same 15-byte prefix: check the rest and the length
             unsigned long long ta, tb;
             ld_cg_u64x2(&e->tail_a, ta, tb);
             if (ta != key.tail_a || tb != key.tail_b || m.y != key.tail_last) continue;
         }
-        slot = h; meta_out = m.x; t01 = make_uint2(m.z, m.w);
+        slot = h; meta_out = m.x;
         return kMemoHit;
     }
     return kMemoMiss;
@@ -205,17 +215,19 @@ __device__ __forceinline__ bool memo_publish(const EncodeWorkspace &ws, uint32_t
     MemoEntry *e = ws.memo + slot;
     if (ntok > (uint32_t)kMemoTokens || h6 > 0xFFFFFFu) { st_release_u32(&e->meta, 0xFFFFFFFFu); return false; }
     e->tail_a = key.tail_a; e->tail_b = key.tail_b; e->tail_last = key.tail_last;
-    e->tok01[0] = ntok > 0 ? buf[0] : 0u; e->tok01[1] = ntok > 1 ? buf[1] : 0u;
-    for (uint32_t k = 2; k < ntok; ++k) e->tok[k - 2] = buf[k];
-    st_release_u32(&e->meta, (ntok + 1) | (h6 << 8));
+    bool narrow = ntok <= 14 && h6 == 0 && key.nbytes <= 15;            // servable by the one-load fast path?
+    for (uint32_t k = 0; k < ntok; ++k) { e->tok[k] = buf[k]; narrow = narrow && buf[k] < 65536u; }
+    if (narrow) for (uint32_t k = 0; k < ntok; ++k) e->ids16[k] = (uint16_t)buf[k];
+    st_release_u32(&e->meta, (ntok + 1) | (h6 << 8));                   // release: everything above is visible first
+    if (narrow) atomicOr(reinterpret_cast<uint32_t *>(&e->hi) + 1, (ntok + 1) << 28);   // pub nibble, after the release
     atomicAdd(&status[kStatusMemoTypes], 1u);
     return true;
 }
 
 // per-word record between the two passes, packed into 32 bits:
-//   [31:29] kind; Hit: [28:23] n_tokens, [19:0] memo slot; Recompute: [28:23] n_tokens;
+//   [31:29] kind; Hit / Hit16 (ids16[] valid): [28:23] n_tokens, [19:0] memo slot; Recompute: [28:23] n_tokens;
 //   WP long: [28:0] n_tokens; BPE long: [28:0] scratch granule (16 u32) -- header word 0 holds n_tokens
-enum : uint32_t { kWordNone = 0u, kWordHit = 1u, kWordRecompute = 2u, kWordLong = 3u, kWordLongB = 4u };
+enum : uint32_t { kWordNone = 0u, kWordHit = 1u, kWordRecompute = 2u, kWordLong = 3u, kWordLongB = 4u, kWordHit16 = 5u };
 constexpr uint32_t kLongHeader = 16;      // u32 words reserved in front of the two scratch buffers of a long BPE word
 constexpr uint32_t kGroupTiles = 1024;    // tiles per scan group
 
@@ -228,8 +240,8 @@ __device__ __noinline__ SlowResult resolve_slow(const Enc &enc, const EncodeWork
                                                 uint32_t nbytes, uint32_t arena_end, uint32_t *status) {
     uint32_t buf[kShortBytes];                                   // scratch for one directly encoded word
     SlowResult r; r.kind = kWordRecompute; r.ntok = 0; r.slot = 0; r.h6 = 0;
-    int m = kMemoMiss; uint32_t meta = 0; MemoKey key; uint2 t01;
-    if (ws.memo_mask && nbytes >= 1) { memo_key(arena, b0, nbytes, arena_end, key); m = memo_probe(ws, key, r.slot, meta, t01); }
+    int m = kMemoMiss; uint32_t meta = 0; MemoKey key;
+    if (ws.memo_mask && nbytes >= 1) { memo_key(arena, b0, nbytes, arena_end, key); m = memo_probe(ws, key, r.slot, meta); }
     if (m == kMemoHit) { r.kind = kWordHit; r.ntok = (meta & 0xFFu) - 1; r.h6 = meta >> 8; return r; }
     r.ntok = enc.encode_short(arena + b0, nbytes, buf, r.h6);
     if (m == kMemoClaimed && memo_publish(ws, r.slot, key, buf, r.ntok, r.h6, status)) r.kind = kWordHit;
@@ -250,37 +262,48 @@ __device__ __noinline__ void emit_slow(const Enc &enc, const uint8_t *word, uint
     }
 }
 
-// ids of a memo hit -> dst (ids 0-13 were prefetched, the rest is fetched here)
-__device__ __forceinline__ void store_hit_ids(uint32_t *dst, uint32_t n, uint4 m, uint4 c0, uint4 c1, uint4 c2, const MemoEntry *e) {
-    if (n > 0) dst[0] = m.z;
-    if (n > 1) dst[1] = m.w;
-    if (n > 2) dst[2] = c0.x;
-    if (n > 3) dst[3] = c0.y;
-    if (n > 4) dst[4] = c0.z;
-    if (n > 5) dst[5] = c0.w;
-    if (n > 6) dst[6] = c1.x;
-    if (n > 7) dst[7] = c1.y;
-    if (n > 8) dst[8] = c1.z;
-    if (n > 9) dst[9] = c1.w;
-    if (n > 10) dst[10] = c2.x;
-    if (n > 11) dst[11] = c2.y;
-    if (n > 12) dst[12] = c2.z;
-    if (n > 13) dst[13] = c2.w;
-    for (uint32_t k0 = 12; k0 + 2 < n; k0 += 4) {
+// ids of a one-load hit (16-bit ids, at most 14) -> dst
+__device__ __forceinline__ void store_hit16_ids(uint32_t *dst, uint32_t n, uint4 a, uint4 b) {
+    if (n > 0) dst[0] = a.x & 0xFFFFu;
+    if (n > 1) dst[1] = a.x >> 16;
+    if (n > 2) dst[2] = a.y & 0xFFFFu;
+    if (n > 3) dst[3] = a.y >> 16;
+    if (n > 4) dst[4] = a.z & 0xFFFFu;
+    if (n > 5) dst[5] = a.z >> 16;
+    if (n > 6) dst[6] = a.w & 0xFFFFu;
+    if (n > 7) dst[7] = a.w >> 16;
+    if (n > 8) dst[8] = b.x & 0xFFFFu;
+    if (n > 9) dst[9] = b.x >> 16;
+    if (n > 10) dst[10] = b.y & 0xFFFFu;
+    if (n > 11) dst[11] = b.y >> 16;
+    if (n > 12) dst[12] = b.z & 0xFFFFu;
+    if (n > 13) dst[13] = b.z >> 16;
+}
+// ids of a hit found by the slow path (32-bit id list; ids 0-7 were prefetched, the rest is fetched here)
+__device__ __forceinline__ void store_hit_ids(uint32_t *dst, uint32_t n, uint4 a, uint4 b, const MemoEntry *e) {
+    if (n > 0) dst[0] = a.x;
+    if (n > 1) dst[1] = a.y;
+    if (n > 2) dst[2] = a.z;
+    if (n > 3) dst[3] = a.w;
+    if (n > 4) dst[4] = b.x;
+    if (n > 5) dst[5] = b.y;
+    if (n > 6) dst[6] = b.z;
+    if (n > 7) dst[7] = b.w;
+    for (uint32_t k0 = 8; k0 < n; k0 += 4) {
         const uint4 v = ld_ca_u32x4(&e->tok[k0]);
-        dst[k0 + 2] = v.x;
-        if (k0 + 3 < n) dst[k0 + 3] = v.y;
-        if (k0 + 4 < n) dst[k0 + 4] = v.z;
-        if (k0 + 5 < n) dst[k0 + 5] = v.w;
+        dst[k0] = v.x;
+        if (k0 + 1 < n) dst[k0 + 1] = v.y;
+        if (k0 + 2 < n) dst[k0 + 2] = v.z;
+        if (k0 + 3 < n) dst[k0 + 3] = v.w;
     }
 }
 
-// clears the key/meta sector of every memo entry (the rest of an entry is only read after its meta was published)
+// clears key and meta of every memo entry (the rest of an entry is only read after its meta / pub nibble was published)
 static __global__ void __launch_bounds__(256) memo_clear_kernel(MemoEntry *memo, uint32_t n_slots, unsigned long long *long_cursor) {
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) {
         uint4 *e = reinterpret_cast<uint4 *>(memo + i);
-        e[0] = z; e[1] = z;
+        e[0] = z; e[3] = z;                                 // key (bytes 0-15) and meta / tail_last (bytes 48-63)
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *long_cursor = 0ull;
 }
@@ -321,13 +344,12 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
         // probes.  Both words' loads are in flight together.
         uint32_t kind[kWordsPerThread], ntok[kWordsPerThread], slot[kWordsPerThread];
         uint4 kw[kWordsPerThread], ew[kWordsPerThread];           // key of the word / key found in the probed entry
-        uint32_t meta[kWordsPerThread];
         bool fastj[kWordsPerThread], slow[kWordsPerThread], is_long[kWordsPerThread];
         {
             uint32_t a0[kWordsPerThread], a1[kWordsPerThread], a2[kWordsPerThread], a3[kWordsPerThread], a4[kWordsPerThread];
 #pragma unroll
             for (int j = 0; j < kWordsPerThread; ++j) {
-                kind[j] = kWordNone; ntok[j] = 0; slot[j] = 0; slow[j] = false; meta[j] = 0;
+                kind[j] = kWordNone; ntok[j] = 0; slot[j] = 0; slow[j] = false;
                 kw[j] = ew[j] = make_uint4(0, 0, 0, 0);
                 is_long[j] = nb[j] != 0xFFFFFFFFu && nb[j] > (uint32_t)kShortBytes;
                 fastj[j] = use_memo && nb[j] >= 1 && nb[j] <= 15 && (uint64_t)b0s[j] + 24 <= arena_end;
@@ -356,9 +378,7 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
                     w3 = (n > 12 ? w3 & ((1u << (8 * (n - 12))) - 1u) : 0u) | (n << 24);
                     kw[j] = make_uint4(w0, w1, w2, w3);
                     slot[j] = memo_hash4(w0, w1, w2, w3) & ws.memo_mask;
-                    const MemoEntry *e = ws.memo + slot[j];
-                    ew[j] = ld_ca_u32x4(e);
-                    meta[j] = ld_ca_u32(&e->meta);
+                    ew[j] = ld_ca_u32x4(ws.memo + slot[j]);      // ONE scattered load per word: key + pub nibble
                 }
             }
         }
@@ -368,18 +388,16 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
             if (is_long[j]) { kind[j] = kWordLong; continue; }
             bool hit = false;
             if (fastj[j]) {
-                bool same = ew[j].x == kw[j].x && ew[j].y == kw[j].y && ew[j].z == kw[j].z && ew[j].w == kw[j].w;
+                bool same = ew[j].x == kw[j].x && ew[j].y == kw[j].y && ew[j].z == kw[j].z && ((ew[j].w ^ kw[j].w) & 0x0FFFFFFFu) == 0;
                 if (!same && (ew[j].x | ew[j].y | ew[j].z | ew[j].w) != 0) {
                     // the slot holds another word (hash collision): look at the next slot
                     slot[j] = (slot[j] + 1) & ws.memo_mask;
-                    const MemoEntry *e = ws.memo + slot[j];
-                    ew[j] = ld_ca_u32x4(e);
-                    meta[j] = ld_ca_u32(&e->meta);
-                    same = ew[j].x == kw[j].x && ew[j].y == kw[j].y && ew[j].z == kw[j].z && ew[j].w == kw[j].w;
+                    ew[j] = ld_ca_u32x4(ws.memo + slot[j]);
+                    same = ew[j].x == kw[j].x && ew[j].y == kw[j].y && ew[j].z == kw[j].z && ((ew[j].w ^ kw[j].w) & 0x0FFFFFFFu) == 0;
                 }
-                hit = same && meta[j] != 0 && meta[j] != 0xFFFFFFFFu;
+                hit = same && (ew[j].w >> 28) != 0;                  // pub nibble: ids16[] valid, n_tokens + 1
             }
-            if (hit) { kind[j] = kWordHit; ntok[j] = (meta[j] & 0xFFu) - 1; h6 += meta[j] >> 8; }
+            if (hit) { kind[j] = kWordHit16; ntok[j] = (ew[j].w >> 28) - 1; }
             else slow[j] = true;
         }
         // words not served by the first probe (longer than 15 bytes, hash collision, first occurrence) are spread over the
@@ -403,7 +421,7 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
         uint32_t packed[kWordsPerThread];
 #pragma unroll
         for (int j = 0; j < kWordsPerThread; ++j) {
-            packed[j] = (kind[j] << 29) | (ntok[j] << 23) | (kind[j] == kWordHit ? slot[j] : 0u);
+            packed[j] = (kind[j] << 29) | (ntok[j] << 23) | ((kind[j] == kWordHit || kind[j] == kWordHit16) ? slot[j] : 0u);
             if constexpr (!Enc::kScratchLong) {
                 if (is_long[j]) { ntok[j] = enc.long_count(arena + b0s[j], nb[j], h6); packed[j] = (kWordLong << 29) | ntok[j]; }
             } else {
@@ -513,19 +531,21 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
         else if (i0 < tile_words) packed[0] = ws.packed[w_tile + i0];
         const uint64_t base = ws.group_base[tile / kGroupTiles] + ws.tile_total[tile];
         uint32_t kind[kWordsPerThread], ntok[kWordsPerThread], arg[kWordsPerThread];
-        uint4 m[kWordsPerThread], c0[kWordsPerThread], c1[kWordsPerThread], c2[kWordsPerThread];
+        uint4 ra[kWordsPerThread], rb[kWordsPerThread];
 #pragma unroll
         for (int j = 0; j < kWordsPerThread; ++j) {
             kind[j] = packed[j] >> 29;
             arg[j] = packed[j] & 0x1FFFFFFFu;
-            ntok[j] = (kind[j] == kWordHit || kind[j] == kWordRecompute) ? (arg[j] >> 23) : (kind[j] == kWordLong && !Enc::kScratchLong) ? arg[j] : 0u;
-            m[j] = c0[j] = c1[j] = c2[j] = make_uint4(0, 0, 0, 0);
-            if (kind[j] == kWordHit) {                              // all id loads of both words are in flight together
-                const MemoEntry *e = ws.memo + (arg[j] & 0xFFFFFu);
-                m[j] = ld_ca_u32x4(&e->meta);
-                if (ntok[j] > 2) c0[j] = ld_ca_u32x4(&e->tok[0]);
-                if (ntok[j] > 6) c1[j] = ld_ca_u32x4(&e->tok[4]);
-                if (ntok[j] > 10) c2[j] = ld_ca_u32x4(&e->tok[8]);
+            ntok[j] = (kind[j] == kWordHit || kind[j] == kWordHit16 || kind[j] == kWordRecompute) ? (arg[j] >> 23)
+                      : (kind[j] == kWordLong && !Enc::kScratchLong) ? arg[j] : 0u;
+            ra[j] = rb[j] = make_uint4(0, 0, 0, 0);
+            const MemoEntry *e = ws.memo + (arg[j] & 0xFFFFFu);
+            if (kind[j] == kWordHit16) {                            // one or two scattered loads; both words' loads in flight together
+                if (ntok[j] > 0) ra[j] = ld_ca_u32x4(&e->ids16[0]);
+                if (ntok[j] > 8) rb[j] = ld_ca_u32x4(&e->ids16[8]);
+            } else if (kind[j] == kWordHit) {
+                if (ntok[j] > 0) ra[j] = ld_ca_u32x4(&e->tok[0]);
+                if (ntok[j] > 4) rb[j] = ld_ca_u32x4(&e->tok[4]);
             }
             if constexpr (Enc::kScratchLong) {
                 if (kind[j] == kWordLong || kind[j] == kWordLongB) ntok[j] = ws.long_scratch[(unsigned long long)arg[j] << 4];
@@ -554,10 +574,13 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
         if (!fits_out) continue;                                                    // warp-uniform (status set by the scan)
 #pragma unroll
         for (int j = 0; j < kWordsPerThread; ++j) {
-            if (kind[j] == kWordHit) {
+            if (kind[j] == kWordHit16) {
                 // two copies of the same code so that the common case compiles to shared-memory stores (STS)
-                if (use_compact) store_hit_ids(compact + run[j], ntok[j], m[j], c0[j], c1[j], c2[j], ws.memo + (arg[j] & 0xFFFFFu));
-                else store_hit_ids(out_ids + base + run[j], ntok[j], m[j], c0[j], c1[j], c2[j], ws.memo + (arg[j] & 0xFFFFFu));
+                if (use_compact) store_hit16_ids(compact + run[j], ntok[j], ra[j], rb[j]);
+                else store_hit16_ids(out_ids + base + run[j], ntok[j], ra[j], rb[j]);
+            } else if (kind[j] == kWordHit) {
+                if (use_compact) store_hit_ids(compact + run[j], ntok[j], ra[j], rb[j], ws.memo + (arg[j] & 0xFFFFFu));
+                else store_hit_ids(out_ids + base + run[j], ntok[j], ra[j], rb[j], ws.memo + (arg[j] & 0xFFFFFu));
             } else if (kind[j] == kWordRecompute || (!Enc::kScratchLong && kind[j] == kWordLong)) {
                 uint32_t *dst = use_compact ? compact + run[j] : out_ids + base + run[j];
                 const uint32_t b0 = __ldg(word_off + w_tile + i0 + j), b1 = __ldg(word_off + w_tile + i0 + j + 1);
