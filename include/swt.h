@@ -170,6 +170,13 @@ void swt_host_free(void *ptr);
  */
 typedef struct swt_bpe_trainer swt_bpe_trainer;
 
+/* SWT_TRAIN_WP runs the same machinery for NaiveWP.train (wordpiece.py:29-103): symbols
+ * 0..n_alpha-1 are the initial symbol STRINGS ("a", "##a", ...; d_init_cps/d_init_off), the merged token is a + b[2:]
+ * (:95) and each step takes the pair with the highest score pair_freq / (freq[a]*freq[b]) (:84-92, first inserted pair
+ * on ties).  Single rank only; symbol-frequency products must stay below 2^53. */
+#define SWT_TRAIN_BPE 0
+#define SWT_TRAIN_WP 1
+
 typedef struct swt_bpe_train_config {
     uint64_t n_types_local;    /* word types on this rank */
     uint64_t n_slots_local;    /* total symbols of those types (< 2^32) */
@@ -182,6 +189,7 @@ typedef struct swt_bpe_train_config {
     uint32_t world_size;       /* number of ranks sharing the job */
     uint32_t rank;
     uint64_t table_cap;        /* pair-table slots (power of two); 0 = choose */
+    uint32_t mode;             /* SWT_TRAIN_BPE or SWT_TRAIN_WP */
 } swt_bpe_train_config;
 
 /* host-visible snapshot of the trainer state */
@@ -200,8 +208,9 @@ typedef struct swt_bpe_train_state {
 size_t swt_bpe_train_workspace_bytes(const swt_bpe_train_config *cfg);
 /* d_syms/d_off/d_freq: this rank's types (u32 symbol ids, u64 offsets n_types_local+1, i64 freqs) */
 int swt_bpe_train_create(const swt_bpe_train_config *cfg, const uint32_t *d_syms, const uint64_t *d_off,
-                         const int64_t *d_freq, void *d_workspace, size_t workspace_bytes, void *stream,
-                         swt_bpe_trainer **out);
+                         const int64_t *d_freq, const uint32_t *d_init_cps /* WP only, else NULL */,
+                         const uint64_t *d_init_off /* WP only: n_alpha+1 */, void *d_workspace, size_t workspace_bytes,
+                         void *stream, swt_bpe_trainer **out);
 void swt_bpe_train_destroy(swt_bpe_trainer *t);
 /* device addresses/sizes of the exchange buffers, for the caller's collectives */
 int swt_bpe_train_buffers(const swt_bpe_trainer *t, void **init_counts_ptr, uint64_t *init_counts_elems /* i64 */,

@@ -17,6 +17,7 @@ c_vp = ctypes.c_void_p
 
 SWT_OK = 0
 SHORT_WORD_BYTES = 32
+TRAIN_BPE, TRAIN_WP = 0, 1
 
 
 class SwtError(RuntimeError):
@@ -28,7 +29,7 @@ class TrainConfig(ctypes.Structure):
         ("n_types_local", ctypes.c_uint64), ("n_slots_local", ctypes.c_uint64), ("slot_base", ctypes.c_uint64),
         ("n_alpha", ctypes.c_uint32), ("max_vocab", ctypes.c_int64), ("initial_vocab", ctypes.c_int64),
         ("max_word_len", ctypes.c_uint32), ("record_cap", ctypes.c_uint32), ("world_size", ctypes.c_uint32),
-        ("rank", ctypes.c_uint32), ("table_cap", ctypes.c_uint64),
+        ("rank", ctypes.c_uint32), ("table_cap", ctypes.c_uint64), ("mode", ctypes.c_uint32),
     ]
 
 
@@ -64,7 +65,7 @@ SIGNATURES = {
     "swt_host_alloc": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_size_t]),
     "swt_host_free": (None, [c_vp]),
     "swt_bpe_train_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(TrainConfig)]),
-    "swt_bpe_train_create": (ctypes.c_int, [ctypes.POINTER(TrainConfig), c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp,
+    "swt_bpe_train_create": (ctypes.c_int, [ctypes.POINTER(TrainConfig), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp,
                                             ctypes.POINTER(c_vp)]),
     "swt_bpe_train_destroy": (None, [c_vp]),
     "swt_bpe_train_buffers": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), c_u64p, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),

@@ -35,7 +35,7 @@ constexpr uint32_t kChunkShift = 12;            // mark scan granularity: 4096 s
 constexpr uint32_t kBlkShift = 12;              // argmax cache granularity: 4096 table slots per block
 
 enum Halt : uint32_t { kRun = 0, kDoneVocab = 1, kDoneNoPairs = 2, kNeedGrow = 3, kRecordFull = 4,
-                       kErrInternal = 16, kErrCharArena = 17, kErrSymbols = 18, kErrTableFull = 19 };
+                       kErrInternal = 16, kErrCharArena = 17, kErrSymbols = 18, kErrTableFull = 19, kErrScoreRange = 20 };
 
 struct PairEntry { uint64_t key; long long count; };
 
@@ -51,6 +51,7 @@ struct TrainState {                 // device resident, mutable
     uint32_t cur_a, cur_b, cur_z, cur_valid;
     uint64_t char_used;
     uint32_t n_dirty, n_touch_l, n_touch_r, pad0;   // lengths of the dirty-block list and of the touched-symbol lists
+    double best_score;                              // WordPiece mode: the maximal score of this step
 };
 
 struct ArgPart { long long count; uint64_t key; uint32_t n_tied; uint32_t pad; };
@@ -58,13 +59,14 @@ struct ArgPart { long long count; uint64_t key; uint32_t n_tied; uint32_t pad; }
 struct TrainDev {
     // sizes
     uint64_t n_types, n_slots, slot_base;
-    uint32_t n_alpha, vmax, record_cap, world, rank, n_parts;
+    uint32_t n_alpha, vmax, record_cap, world, rank, n_parts, mode;
     long long max_vocab;
     uint64_t char_cap, str_ht_cap;
     // arrays
     uint32_t *sym, *word_of, *start, *word_mark, *worklist;
     uint32_t *pres; uint32_t pres_words, n_chunks;   // per chunk: bitmap of the symbols that (may) occur in it
     long long *freq;
+    long long *sfreq;                 // WordPiece mode: frequency of every symbol (wordpiece.py:78-81), kept incrementally
     PairEntry *table;                 // current table (changes on grow)
     ArgPart *blk;                     // per 4096-slot block: cached (max count, a key attaining it, how many attain it)
     uint32_t *dirty;                  // block touched since its cache entry was computed
@@ -173,6 +175,89 @@ __global__ void k_rehash(const PairEntry *old_tab, uint64_t old_cap, TrainDev d,
     }
 }
 
+// ---- WordPiece mode (NaiveWP.train, reference source/wordpiece.py:29-103) -----------------------------------------------
+// Same word table, pair table, mark / apply / update as BPE.  What differs: the initial symbols are strings ("a", "##a",
+// wordpiece.py:53-57), the merged token is a + b[2:] (:95), and the pair chosen at every step maximises
+// score = pair_freq / (freq[a] * freq[b]) (:84-92) with the first-inserted pair winning ties.  Python evaluates the score
+// as int / int, i.e. the correctly rounded double of the exact quotient; freq[a]*freq[b] < 2^53 is required here so that
+// the IEEE division of the two exactly representable operands gives the same double (the trainer halts otherwise).
+__global__ void k_init_symbols_wp(TrainDev d, const uint32_t *__restrict__ init_cps, const uint64_t *__restrict__ init_off) {
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < d.n_alpha; c += gridDim.x * blockDim.x) {
+        const uint64_t b = init_off[c], e = init_off[c + 1];
+        uint64_t h = 0;
+        for (uint64_t i = b; i < e; ++i) { d.chars[i] = init_cps[i]; h = h * kHashP + ((uint64_t)init_cps[i] + 1); }
+        d.sym_len[c] = (uint32_t)(e - b); d.sym_off[c] = b; d.sym_hash[c] = h; d.sym_pow[c] = 0;
+        uint64_t slot = mix64(h) & (d.str_ht_cap - 1);                 // initial symbols are vocabulary members too
+        while (atomicCAS(&d.str_ht[slot], 0u, c + 1) != 0u) slot = (slot + 1) & (d.str_ht_cap - 1);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.st->char_used = init_off[d.n_alpha];
+}
+__global__ void k_count_sfreq(TrainDev d) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < d.n_slots; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd((unsigned long long *)&d.sfreq[d.sym[i] & ~kStart], (unsigned long long)d.freq[d.word_of[i]]);
+}
+__device__ __forceinline__ double wp_score(const TrainDev &d, uint64_t key, long long count, TrainState *st) {
+    const long long fa = d.sfreq[key >> 32], fb = d.sfreq[key & 0xFFFFFFFFull];
+    const unsigned long long prod = (unsigned long long)fa * (unsigned long long)fb;
+    if (fa <= 0 || fb <= 0 || __umul64hi((unsigned long long)fa, (unsigned long long)fb) != 0 || prod >= (1ull << 53) || count >= (1ll << 53)) {
+        atomicExch(&st->halt, (uint32_t)kErrScoreRange);
+        return 0.0;
+    }
+    return (double)count / (double)prod;                                // IEEE division == Python's correctly rounded int / int
+}
+__device__ __forceinline__ void score_combine(double &c, uint64_t &k, uint32_t &n, double c2, uint64_t k2, uint32_t n2) {
+    if (c2 > c) { c = c2; k = k2; n = n2; }
+    else if (c2 == c) { n += n2; if (k2 < k) k = k2; }
+}
+__global__ void __launch_bounds__(256) k_wp_argmax_partial(TrainDev d) {
+    TrainState *st = d.st;
+    if (st->halt) return;
+    const uint64_t cap = st->table_cap;
+    double c = 0.0; uint64_t k = kEmptyKey; uint32_t n = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const PairEntry e = d.table[i];
+        if (e.key != kEmptyKey && e.count > 0) score_combine(c, k, n, wp_score(d, e.key, e.count, st), e.key, 1u);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        double c2 = __shfl_xor_sync(0xffffffffu, c, o); uint64_t k2 = __shfl_xor_sync(0xffffffffu, k, o);
+        uint32_t n2 = __shfl_xor_sync(0xffffffffu, n, o);
+        score_combine(c, k, n, c2, k2, n2);
+    }
+    __shared__ double sc[8]; __shared__ uint64_t sk[8]; __shared__ uint32_t sn[8];
+    if ((threadIdx.x & 31) == 0) { sc[threadIdx.x >> 5] = c; sk[threadIdx.x >> 5] = k; sn[threadIdx.x >> 5] = n; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) score_combine(c, k, n, sc[w], sk[w], sn[w]);
+        d.parts[blockIdx.x] = ArgPart{(long long)__double_as_longlong(c), k, n, 0};
+    }
+}
+__global__ void __launch_bounds__(256) k_wp_select(TrainDev d) {
+    TrainState *st = d.st;
+    if (st->halt) return;
+    double c = 0.0; uint64_t k = kEmptyKey; uint32_t n = 0;
+    for (uint32_t i = threadIdx.x; i < d.n_parts; i += blockDim.x) { ArgPart p = d.parts[i]; score_combine(c, k, n, __longlong_as_double(p.count), p.key, p.n_tied); }
+    for (int o = 16; o > 0; o >>= 1) {
+        double c2 = __shfl_xor_sync(0xffffffffu, c, o); uint64_t k2 = __shfl_xor_sync(0xffffffffu, k, o);
+        uint32_t n2 = __shfl_xor_sync(0xffffffffu, n, o);
+        score_combine(c, k, n, c2, k2, n2);
+    }
+    __shared__ double sc[8]; __shared__ uint64_t sk[8]; __shared__ uint32_t sn[8];
+    if ((threadIdx.x & 31) == 0) { sc[threadIdx.x >> 5] = c; sk[threadIdx.x >> 5] = k; sn[threadIdx.x >> 5] = n; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) score_combine(c, k, n, sc[w], sk[w], sn[w]);
+        st->n_dirty = 0; st->n_touch_l = 0; st->n_touch_r = 0;
+        st->best_score = c; st->max_count = n ? 1 : 0; st->n_tied = n; st->cand_key = k;
+        st->worklist_n = 0; st->tie_ticket = 0; st->best_pos = kNoPos; st->cur_valid = 0;
+        // loop conditions of wordpiece.py:68 and :74-75, then the capacity gates (checked before any mutation)
+        if (st->vocab_size >= d.max_vocab) st->halt = kDoneVocab;
+        else if (n == 0) st->halt = kDoneNoPairs;
+        else if (st->n_recorded >= d.record_cap) st->halt = kRecordFull;
+        else if ((st->n_entries + 2 * st->n_symbols + 2) * 10 > st->table_cap * 7) st->halt = kNeedGrow;
+        else if (st->n_symbols + 1 > d.vmax) st->halt = kErrSymbols;
+    }
+}
+
 // ---- select: argmax over the table (bpe.py:102) ---------------------------------------------------------------------
 __device__ __forceinline__ void arg_combine(long long &c, uint64_t &k, uint32_t &n, long long c2, uint64_t k2, uint32_t n2) {
     if (c2 > c) { c = c2; k = k2; n = n2; }
@@ -245,6 +330,7 @@ __global__ void __launch_bounds__(256) k_tie_scan(TrainDev d) {
     TrainState *st = d.st;
     if (st->halt || st->n_tied <= 1) return;
     const long long target = st->max_count;
+    const double target_score = st->best_score;
     const uint64_t cap = st->table_cap;
     __shared__ uint32_t s_chunk, s_stop;
     __shared__ unsigned long long s_best;
@@ -262,7 +348,10 @@ __global__ void __launch_bounds__(256) k_tie_scan(TrainDev d) {
         for (uint64_t i = c0 + threadIdx.x; i < c0 + kTieChunk && i + 1 < d.n_slots; i += blockDim.x) {
             const uint32_t s = d.sym[i], nx = d.sym[i + 1];
             if (s == kHole || (nx & kStart)) continue;
-            if (table_get(d.table, cap, ((uint64_t)(s & ~kStart) << 32) | nx) == target) { mine = i; break; }
+            const uint64_t key = ((uint64_t)(s & ~kStart) << 32) | nx;
+            const long long cnt = table_get(d.table, cap, key);
+            const bool tied = d.mode == 0 ? cnt == target : (cnt > 0 && wp_score(d, key, cnt, st) == target_score);
+            if (tied) { mine = i; break; }
         }
         if (mine != kNoPos) atomicMin(&s_best, (unsigned long long)mine);
         __syncthreads();
@@ -298,9 +387,13 @@ __global__ void __launch_bounds__(32) k_begin_merge(TrainDev d) {
         if (best == kNoPos) { if (lane == 0) st->halt = kErrInternal; return; }
     }
     const uint32_t a = (uint32_t)(key >> 32), b = (uint32_t)key;
-    const uint32_t la = d.sym_len[a], lb = d.sym_len[b], L = la + lb;
-    const uint32_t *ca = d.chars + d.sym_off[a], *cb = d.chars + d.sym_off[b];
-    const uint64_t h = d.sym_hash[a] * d.sym_pow[b] + d.sym_hash[b];
+    // BPE: merged = a + b (bpe.py:103).  WordPiece: merged = a + b[2:] (wordpiece.py:95).
+    const uint32_t skip = d.mode == 1 ? min(2u, d.sym_len[b]) : 0u;
+    const uint32_t la = d.sym_len[a], lb = d.sym_len[b] - skip, L = la + lb;
+    const uint32_t *ca = d.chars + d.sym_off[a], *cb = d.chars + d.sym_off[b] + skip;
+    uint64_t h;
+    if (d.mode == 0) h = d.sym_hash[a] * d.sym_pow[b] + d.sym_hash[b];
+    else { h = 0; for (uint32_t i = 0; i < L; ++i) h = h * kHashP + ((uint64_t)(i < la ? ca[i] : cb[i - la]) + 1); }
     uint64_t slot = mix64(h) & (d.str_ht_cap - 1);
     uint32_t z = kHole;
     for (;;) {
@@ -329,7 +422,8 @@ __global__ void __launch_bounds__(32) k_begin_merge(TrainDev d) {
     }
     if (lane == 0) {
         const uint32_t r = st->n_recorded;
-        d.rec_left[r] = a; d.rec_right[r] = b; d.rec_new[r] = z; d.rec_count[r] = st->max_count;
+        d.rec_left[r] = a; d.rec_right[r] = b; d.rec_new[r] = z;
+        d.rec_count[r] = d.mode == 0 ? st->max_count : table_get(d.table, st->table_cap, key);
         st->n_recorded = r + 1; st->n_merges_total += 1;
         st->cur_a = a; st->cur_b = b; st->cur_z = z; st->cur_valid = 1; st->step_stamp += 1;
     }
@@ -440,6 +534,7 @@ __global__ void __launch_bounds__(256) k_update(TrainDev d) {
         const long long zz = d.delta[2 * (uint64_t)d.vmax], m = d.delta[2 * (uint64_t)d.vmax + 1];
         if (zz) { table_add(d.table, cap, (b << 32) | a, -zz, st, d.dirty, d.dirty_list); table_add(d.table, cap, (z << 32) | z, zz, st, d.dirty, d.dirty_list); }
         if (m) table_add(d.table, cap, (a << 32) | b, -m, st, d.dirty, d.dirty_list);
+        if (d.mode == 1) { d.sfreq[a] -= m; d.sfreq[b] -= m; d.sfreq[z] += m; }      // wordpiece.py:78-81, incrementally
         d.delta[2 * (uint64_t)d.vmax] = 0; d.delta[2 * (uint64_t)d.vmax + 1] = 0;
     }
 }
@@ -476,7 +571,7 @@ static uint32_t vmax_of(const swt_bpe_train_config *cfg) {
 }
 static uint64_t char_cap_of(const swt_bpe_train_config *cfg) {
     uint64_t want = (uint64_t)vmax_of(cfg) * std::max<uint32_t>(cfg->max_word_len, 1);
-    return std::min<uint64_t>(std::max<uint64_t>(want, 1ull << 20), 1ull << 26) + cfg->n_alpha;
+    return std::min<uint64_t>(std::max<uint64_t>(want, 1ull << 20), 1ull << 26) + 4ull * cfg->n_alpha;
 }
 
 static size_t table_region_bytes(uint64_t cap) {
@@ -508,6 +603,8 @@ static size_t train_layout(const swt_bpe_train_config *cfg, void *base, TrainDev
     d->word_mark = cv.take<uint32_t>(d->n_types + 1);
     d->worklist = cv.take<uint32_t>(d->n_types + 1);
     d->freq = cv.take<long long>(d->n_types + 1);
+    d->sfreq = cv.take<long long>(vmax);
+    d->mode = cfg->mode;
     d->delta = cv.take<long long>(2ull * vmax + 2);
     d->touch_l = cv.take<uint32_t>(vmax); d->touch_r = cv.take<uint32_t>(vmax);
     d->dense = cv.take<long long>((uint64_t)cfg->n_alpha * cfg->n_alpha + 1);
@@ -531,8 +628,8 @@ SWT_API size_t swt_bpe_train_workspace_bytes(const swt_bpe_train_config *cfg) {
 SWT_API size_t swt_bpe_train_table_bytes(uint64_t cap) { return table_region_bytes(next_pow2(cap)) + 256; }
 
 SWT_API int swt_bpe_train_create(const swt_bpe_train_config *cfg, const uint32_t *d_syms, const uint64_t *d_off,
-                                 const int64_t *d_freq, void *d_workspace, size_t workspace_bytes, void *stream,
-                                 swt_bpe_trainer **out) {
+                                 const int64_t *d_freq, const uint32_t *d_init_cps, const uint64_t *d_init_off,
+                                 void *d_workspace, size_t workspace_bytes, void *stream, swt_bpe_trainer **out) {
     SWT_REQUIRE(cfg && out && d_workspace, "NULL argument");
     SWT_REQUIRE(cfg->n_slots_local < 0xFFFFFFF0ull, "n_slots_local must be < 2^32");
     SWT_REQUIRE(cfg->n_types_local < 0xFFFFFFF0ull, "n_types_local must be < 2^32");
@@ -541,6 +638,9 @@ SWT_API int swt_bpe_train_create(const swt_bpe_train_config *cfg, const uint32_t
     SWT_REQUIRE(cfg->record_cap >= 1, "record_cap must be >= 1");
     SWT_REQUIRE(cfg->max_vocab < (1ll << 30), "max_vocab must be < 2^30");
     SWT_REQUIRE(cfg->n_types_local == 0 || (d_syms && d_off && d_freq), "NULL corpus pointer");
+    SWT_REQUIRE(cfg->mode <= 1, "mode must be SWT_TRAIN_BPE or SWT_TRAIN_WP");
+    SWT_REQUIRE(cfg->mode == 0 || (d_init_cps && d_init_off), "WordPiece mode needs the initial symbol strings");
+    SWT_REQUIRE(cfg->mode == 0 || cfg->world_size == 1, "WordPiece training is single-rank");
     cudaStream_t st = (cudaStream_t)stream;
     int device = 0;
     SWT_CUDA_OK(cudaGetDevice(&device));
@@ -557,12 +657,14 @@ SWT_API int swt_bpe_train_create(const swt_bpe_train_config *cfg, const uint32_t
     if (e != cudaSuccess) { delete t; set_error(std::string("memset: ") + cudaGetErrorString(e)); return SWT_ERR_CUDA; }
     k_fill_u64<<<t->grid_scan, 256, 0, st>>>((uint64_t *)d.table, t->table_cap, kEmptyKey, 2);
     k_init_symbols<<<32, 256, 0, st>>>(d, cfg->initial_vocab);
+    if (cfg->mode == 1) k_init_symbols_wp<<<32, 256, 0, st>>>(d, d_init_cps, d_init_off);
     k_set_table_cap<<<1, 1, 0, st>>>(d.st, t->table_cap);
     k_fill_u32<<<1, 32, 0, st>>>(d.sym + d.n_slots, 8, kHole);
     if (cfg->n_types_local) {
         k_init_words<<<t->grid_scan, 256, 0, st>>>(d, d_syms, d_off);
         e = cudaMemcpyAsync(d.freq, d_freq, cfg->n_types_local * sizeof(long long), cudaMemcpyDeviceToDevice, st);
         if (e != cudaSuccess) { delete t; set_error(std::string("freq copy: ") + cudaGetErrorString(e)); return SWT_ERR_CUDA; }
+        if (cfg->mode == 1) k_count_sfreq<<<t->grid_scan, 256, 0, st>>>(d);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) { delete t; set_error(std::string("init launch: ") + cudaGetErrorString(e)); return SWT_ERR_CUDA; }
@@ -604,8 +706,13 @@ SWT_API int swt_bpe_train_build_table(swt_bpe_trainer *t, void *stream) {
 SWT_API int swt_bpe_train_select(swt_bpe_trainer *t, void *stream) {
     SWT_REQUIRE(t != nullptr, "NULL trainer");
     cudaStream_t st = (cudaStream_t)stream;
-    k_argmax_partial<<<t->dev.n_parts, 256, 0, st>>>(t->dev);
-    k_select<<<1, 1024, 0, st>>>(t->dev);
+    if (t->cfg.mode == 1) {                       // WordPiece: scores move with the symbol frequencies -> full pass
+        k_wp_argmax_partial<<<t->dev.n_parts, 256, 0, st>>>(t->dev);
+        k_wp_select<<<1, 256, 0, st>>>(t->dev);
+    } else {
+        k_argmax_partial<<<t->dev.n_parts, 256, 0, st>>>(t->dev);
+        k_select<<<1, 1024, 0, st>>>(t->dev);
+    }
     if (t->dev.n_slots) k_tie_scan<<<t->grid_scan / 2, 256, 0, st>>>(t->dev);
     k_candidate<<<1, 1, 0, st>>>(t->dev);
     SWT_CUDA_OK(cudaGetLastError());

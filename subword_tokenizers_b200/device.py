@@ -212,14 +212,17 @@ class CudaTrainEngine:
 
     def __init__(self, syms: np.ndarray, off: np.ndarray, freq: np.ndarray, n_alpha: int, max_vocab: int,
                  initial_vocab: int, max_word_len: int, slot_base: int, rank: int, world_size: int,
-                 record_cap: int = 4096, table_cap: int = 0):
+                 record_cap: int = 4096, table_cap: int = 0, mode: int = 0, init_cps: Optional[np.ndarray] = None,
+                 init_off: Optional[np.ndarray] = None):
+        """mode 0: BPE (symbols 0..n_alpha-1 are single characters).  mode 1: WordPiece (NaiveWP.train); symbols
+        0..n_alpha-1 are the initial symbol strings given by init_cps / init_off."""
         _lib.require_cuda()
         lib = _lib.load()
         self.lib = lib
         self.dev = torch.device("cuda", current_device())
         n_types = len(off) - 1
         self.cfg = TrainConfig(n_types, int(off[-1]) if n_types else 0, slot_base, n_alpha, max_vocab, initial_vocab,
-                               max(1, max_word_len), record_cap, world_size, rank, table_cap)
+                               max(1, max_word_len), record_cap, world_size, rank, table_cap, mode)
         ws_bytes = lib.swt_bpe_train_workspace_bytes(ctypes.byref(self.cfg))
         self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=self.dev)
         self._keep = [
@@ -227,13 +230,19 @@ class CudaTrainEngine:
             torch.from_numpy(np.ascontiguousarray(off, dtype=np.uint64).view(np.int64)).to(self.dev),
             torch.from_numpy(np.ascontiguousarray(freq, dtype=np.int64)).to(self.dev),
         ]
+        if mode == _lib.TRAIN_WP:
+            self._keep.append(torch.from_numpy(np.ascontiguousarray(init_cps, dtype=np.uint32).view(np.int32)).to(self.dev))
+            self._keep.append(torch.from_numpy(np.ascontiguousarray(init_off, dtype=np.uint64).view(np.int64)).to(self.dev))
         self.handle = c_vp(None)
         # the trainer runs on its own (non-default) stream: the single-rank loop is replayed as a CUDA graph, and
         # stream capture is not possible on the legacy default stream
         torch.cuda.synchronize()
         self.stream = torch.cuda.Stream(device=self.dev)
         check(lib.swt_bpe_train_create(ctypes.byref(self.cfg), self._keep[0].data_ptr(), self._keep[1].data_ptr(),
-                                       self._keep[2].data_ptr(), self.workspace.data_ptr(), ws_bytes, self._sp(),
+                                       self._keep[2].data_ptr(),
+                                       self._keep[3].data_ptr() if mode == _lib.TRAIN_WP else None,
+                                       self._keep[4].data_ptr() if mode == _lib.TRAIN_WP else None,
+                                       self.workspace.data_ptr(), ws_bytes, self._sp(),
                                        ctypes.byref(self.handle)), "swt_bpe_train_create")
         ic, ice, cp, cgp, dp, de = c_vp(), ctypes.c_uint64(), c_vp(), c_vp(), c_vp(), ctypes.c_uint64()
         check(lib.swt_bpe_train_buffers(self.handle, ctypes.byref(ic), ctypes.byref(ice), ctypes.byref(cp), ctypes.byref(cgp),

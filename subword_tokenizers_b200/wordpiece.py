@@ -1,9 +1,9 @@
 """NaiveWP / FastWP with the reference's class surface (source/wordpiece.py).
 
 * ``FastWP.tokenize`` -> HP-2 kernel (swt_wp_encode) over the device trie.  reference wordpiece.py:233-316
-* ``NaiveWP`` (trainer with score freq/(f_a*f_b), greedy longest-prefix encoder) is not on a north-star
-  hot path; it stays a host implementation so that FastWP.train and
-  --compare keep working.
+* ``NaiveWP.train`` (score freq/(f_a*f_b), reference wordpiece.py:29-103) is the first "next" row of SURVEY.md §8(f):
+  it runs on the GPU through the WordPiece mode of the trainer kernels.  ``NaiveWP.encode_word`` (greedy
+  longest-prefix, wordpiece.py:131-158) stays a host loop; it is not a hot path and exists for --compare.
 """
 from __future__ import annotations
 
@@ -21,7 +21,8 @@ class NaiveWP(SubwordTokenizer):
     def __init__(self, tokenizer):
         super().__init__(tokenizer)
         self.vocab: set = set()
-        self.corpus_as_symbols: List[Tuple[List[str], int]] = []
+        self._corpus_cache: List[Tuple[List[str], int]] = []
+        self._train_result = None
 
     def train(self, corpus, max_vocab: int = 30_000):
         if not isinstance(corpus, list) or not all(isinstance(example, str) for example in corpus):
@@ -29,32 +30,42 @@ class NaiveWP(SubwordTokenizer):
         if not isinstance(max_vocab, int):
             raise TypeError("max_vocab must be an int.")
         self.reset()
-        word_freqs = Counter(self._pre_tokenized_words(corpus))
-        words = [([w[0]] + ["##" + c for c in w[1:]], f) for w, f in word_freqs.items()]
-        self.corpus_as_symbols.extend(words)
-        self.vocab |= {s for symbols, _ in words for s in symbols}
-        # Host loop with incrementally maintained counts; selection rule of wordpiece.py:84-92:
-        # score = pair_freq / (freq_a * freq_b) as a Python float, first-inserted pair wins ties.
-        while len(self.vocab) < max_vocab:
-            pair_freqs: Dict[Tuple[str, str], int] = {}
-            sym_freqs: Dict[str, int] = {}
-            for symbols, f in self.corpus_as_symbols:
-                prev = None
-                for s in symbols:
-                    sym_freqs[s] = sym_freqs.get(s, 0) + f
-                    if prev is not None:
-                        key = (prev, s)
-                        pair_freqs[key] = pair_freqs.get(key, 0) + f
-                    prev = s
-            if not pair_freqs:
-                break
-            best, best_score = None, -1.0
-            for pair, f in pair_freqs.items():
-                score = f / (sym_freqs[pair[0]] * sym_freqs[pair[1]])
-                if score > best_score:
-                    best, best_score = pair, score
-            self.vocab.add(best[0] + best[1][2:])
-            self.corpus_as_symbols = [(self._replace_pair(best, symbols), f) for symbols, f in self.corpus_as_symbols]
+        self.train_on_words(self._pre_tokenized_words(corpus), max_vocab)
+
+    def train_on_words(self, words: Sequence[str], max_vocab: int) -> None:
+        """The merge loop of wordpiece.py:68-102 on the GPU (SWT_TRAIN_WP mode of the trainer): score
+        pair_freq / (freq_a * freq_b), first-inserted pair on ties, merged token a + b[2:]."""
+        import numpy as np
+        import torch
+        from . import _lib, packing as P
+        from .device import CudaTrainEngine, run_training_loop
+        types = P.WpTrainTypes(words)
+        self.vocab = set(types.init_syms)
+        max_len = int(np.diff(types.off.astype(np.int64)).max()) if len(types.types) else 1
+        engine = CudaTrainEngine(types.syms, types.off, types.freq, len(types.init_syms), max_vocab, len(types.init_syms),
+                                 max_len + 2, 0, 0, 1, mode=_lib.TRAIN_WP, init_cps=types.init_cps, init_off=types.init_off)
+        left, right, new, count, state = run_training_loop(engine, 1)
+        strs = types.vocab_from_merges(left, right, new)
+        self.vocab = set(strs)
+        self._train_result = (engine, types, strs)
+        self._corpus_cache = None
+
+    @property
+    def corpus_as_symbols(self) -> List[Tuple[List[str], int]]:
+        """(symbols, freq) per word type (reference wordpiece.py:27,99-102), read back lazily from the device."""
+        if self._corpus_cache is None:
+            engine, types, strs = self._train_result
+            syms, lens = engine.read_corpus()
+            out = []
+            for k in range(len(types.types)):
+                s0 = int(types.off[k])
+                out.append(([strs[i] for i in syms[s0:s0 + int(lens[k])]], int(types.freq[k])))
+            self._corpus_cache = out
+        return self._corpus_cache
+
+    @corpus_as_symbols.setter
+    def corpus_as_symbols(self, value) -> None:
+        self._corpus_cache = value
 
     def _replace_pair(self, pair, word):
         merged = pair[0] + pair[1][2:]
@@ -82,7 +93,8 @@ class NaiveWP(SubwordTokenizer):
 
     def reset(self) -> None:
         self.vocab.clear()
-        self.corpus_as_symbols.clear()
+        self._corpus_cache = []
+        self._train_result = None
 
     def save_resources(self, path: str) -> None:
         os.makedirs(path, exist_ok=True)

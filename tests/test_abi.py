@@ -51,6 +51,9 @@ def test_no_cpu_fallback_without_a_device():
     fw = FastWP(hf)
     with pytest.raises(SwtError):
         fw.train(["ab ab"], 4)
+    from subword_tokenizers_b200 import NaiveWP
+    with pytest.raises(SwtError):
+        NaiveWP(hf).train(["ab ab"], 4)
 
 
 def test_product_never_imports_the_oracle():

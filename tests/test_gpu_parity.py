@@ -250,6 +250,45 @@ def test_bpe_train_long_word_runs(P, dev):
     assert np.array_equal(l, ol) and np.array_equal(r, orr) and np.array_equal(n, on) and np.array_equal(c, oc)
 
 
+# ------------------------------------------------------------------------------------------------ NaiveWP.train
+def _wp_train_gpu(dev, P, words, max_vocab, **kw):
+    from subword_tokenizers_b200 import _lib
+    tt = P.WpTrainTypes(words)
+    max_len = int(np.diff(tt.off.astype(np.int64)).max()) if len(tt.types) else 1
+    eng = dev.CudaTrainEngine(tt.syms, tt.off, tt.freq, len(tt.init_syms), max_vocab, len(tt.init_syms), max_len + 2, 0, 0, 1,
+                              mode=_lib.TRAIN_WP, init_cps=tt.init_cps, init_off=tt.init_off, **kw)
+    l, r, n, c, state = dev.run_training_loop(eng, 1, steps_per_sync=kw.get("record_cap", 64))
+    return tt, l, r, n, state
+
+
+def test_wp_train_random_cases_and_kat(P, dev, random_cases, pre_tokenize):
+    import oracle
+    for case in random_cases["wp_train"]:
+        words = [w for s in case["corpus"] for w in pre_tokenize(s)]
+        tt, l, r, n, state = _wp_train_gpu(dev, P, words, case["max_vocab"], record_cap=5)
+        assert sorted(tt.vocab_from_merges(l, r, n)) == case["vocab"], case["corpus"]
+        assert state["vocab_size"] == len(case["vocab"])
+        ol, orr, on, ovs = oracle.wp_train(tt.syms, tt.off, tt.freq, tt.init_cps, tt.init_off, case["max_vocab"])
+        assert np.array_equal(l, ol) and np.array_equal(r, orr) and np.array_equal(n, on)
+    kat = load_golden("kat_tests_resources.json")
+    words = [w for s in kat["corpus"] for w in pre_tokenize(s)]
+    tt, l, r, n, state = _wp_train_gpu(dev, P, words, kat["max_vocab"])
+    assert set(tt.vocab_from_merges(l, r, n)) == set(kat["NaiveWordPiece"])
+
+
+def test_wp_train_5k_matches_reference(P, dev, pre_tokenize):
+    import oracle
+    words = [w for s in load_golden("train-5K.json.gz") for w in pre_tokenize(s)]
+    tt, l, r, n, state = _wp_train_gpu(dev, P, words, 8000, record_cap=512)
+    vocab = tt.vocab_from_merges(l, r, n)
+    assert sorted(vocab) == load_golden("ref_wp_train5k_v8000_vocab.json.gz")          # the reference's own 40-minute run
+    ol, orr, on, ovs = oracle.wp_train(tt.syms, tt.off, tt.freq, tt.init_cps, tt.init_off, 8000)
+    assert np.array_equal(l, ol) and np.array_equal(r, orr) and np.array_equal(n, on) and state["vocab_size"] == ovs
+    # a prefix of the same run is the 1000-entry vocabulary
+    tt2, l2, r2, n2, _ = _wp_train_gpu(dev, P, words, 1000, record_cap=512)
+    assert sorted(tt2.vocab_from_merges(l2, r2, n2)) == load_golden("ref_wp_train5k_v1000_vocab.json.gz")
+
+
 # ------------------------------------------------------------------------------------------------ classes
 def test_classes_end_to_end(hf_tokenizer, tmp_path):
     from subword_tokenizers_b200 import FastBPE, FastWP, NaiveBPE
@@ -274,6 +313,7 @@ def test_classes_end_to_end(hf_tokenizer, tmp_path):
         fw.tokenize("no trie yet")
     fw.train(kat["corpus"], kat["max_vocab"])
     assert fw.vocab == set(kat["FastWordPiece"])
+    assert fw.corpus_as_symbols[0][1] == 1 and "".join(s.replace("##", "") for s in fw.corpus_as_symbols[0][0]) == "this"
     assert fw.tokenize(kat["readme_sentence"]) == kat["readme_tokens"]["FastWordPiece"]
     assert fw.tokenize_batch([kat["readme_sentence"], ""]) == [kat["readme_tokens"]["FastWordPiece"], []]
 
