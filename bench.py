@@ -410,6 +410,25 @@ def secondary_numbers(dev, stream, d_arena, d_off, n_words, n_bytes):
                         "n_types": tt.n_types, "n_symbols": int(len(tt.syms)),
                         "matches_reference_merges": m == merges,
                         "workload": "train-5K word types, max_vocab 8000 (merge loop only)"}
+    # NaiveWP.train (next row of the scope table), same corpus, max_vocab 8000
+    from subword_tokenizers_b200 import _lib as L
+    wt = P.WpTrainTypes(words)
+    wmax = int(np.diff(wt.off.astype(np.int64)).max())
+    best = None
+    for _ in range(2):
+        eng = device.CudaTrainEngine(wt.syms, wt.off, wt.freq, len(wt.init_syms), 8000, len(wt.init_syms), wmax + 2, 0, 0, 1,
+                                     record_cap=8192, mode=L.TRAIN_WP, init_cps=wt.init_cps, init_off=wt.init_off)
+        torch.cuda.synchronize()
+        tic = time.perf_counter()
+        l, r, n, c, state = device.run_training_loop(eng, 1, steps_per_sync=1024)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - tic
+        best = dt if best is None else min(best, dt)
+        eng.close()
+    vocab = sorted(wt.vocab_from_merges(l, r, n))
+    out["wp_train"] = {"value": len(l) / best, "unit": "merges/s", "merges": int(len(l)), "seconds": best,
+                       "matches_reference_vocab": vocab == load_golden("ref_wp_train5k_v8000_vocab.json.gz"),
+                       "workload": "NaiveWP.train, train-5K word types, max_vocab 8000 (merge loop only)"}
     return out
 
 

@@ -293,12 +293,14 @@ __global__ void __launch_bounds__(256) k_argmax_partial(TrainDev d) {
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(1024) k_select(TrainDev d) {
+__global__ void __launch_bounds__(1024) k_select(TrainDev d, int from_parts) {
     TrainState *st = d.st;
     if (st->halt) return;
     long long c = 0; uint64_t k = kEmptyKey; uint32_t n = 0;
-    const uint32_t n_blk = (uint32_t)(st->table_cap >> kBlkShift);
-    for (uint32_t i = threadIdx.x; i < n_blk; i += blockDim.x) { ArgPart p = d.blk[i]; arg_combine(c, k, n, p.count, p.key, p.n_tied); }
+    // reduce either the per-CTA partials of k_argmax_full or the per-block cache refreshed by k_argmax_partial
+    const ArgPart *src = from_parts ? d.parts : d.blk;
+    const uint32_t n_src = from_parts ? d.n_parts : (uint32_t)(st->table_cap >> kBlkShift);
+    for (uint32_t i = threadIdx.x; i < n_src; i += blockDim.x) { ArgPart p = src[i]; arg_combine(c, k, n, p.count, p.key, p.n_tied); }
     for (int o = 16; o > 0; o >>= 1) {
         long long c2 = __shfl_xor_sync(0xffffffffu, c, o); uint64_t k2 = __shfl_xor_sync(0xffffffffu, k, o);
         uint32_t n2 = __shfl_xor_sync(0xffffffffu, n, o);
@@ -322,10 +324,34 @@ __global__ void __launch_bounds__(1024) k_select(TrainDev d) {
     }
 }
 
+// Small tables (<= 2^20 slots): a plain parallel pass over the whole table beats the block cache (few, large blocks).
+__global__ void __launch_bounds__(256) k_argmax_full(TrainDev d) {
+    TrainState *st = d.st;
+    if (st->halt) return;
+    const uint64_t cap = st->table_cap;
+    long long c = 0; uint64_t k = kEmptyKey; uint32_t n = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const PairEntry e = d.table[i];
+        if (e.key != kEmptyKey && e.count > 0) arg_combine(c, k, n, e.count, e.key, 1u);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        long long c2 = __shfl_xor_sync(0xffffffffu, c, o); uint64_t k2 = __shfl_xor_sync(0xffffffffu, k, o);
+        uint32_t n2 = __shfl_xor_sync(0xffffffffu, n, o);
+        arg_combine(c, k, n, c2, k2, n2);
+    }
+    __shared__ long long sc[8]; __shared__ uint64_t sk[8]; __shared__ uint32_t sn[8];
+    if ((threadIdx.x & 31) == 0) { sc[threadIdx.x >> 5] = c; sk[threadIdx.x >> 5] = k; sn[threadIdx.x >> 5] = n; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) arg_combine(c, k, n, sc[w], sk[w], sn[w]);
+        d.parts[blockIdx.x] = ArgPart{c, k, n, 0};
+    }
+}
+
 // ---- select: tie-break scan.  Among the pairs whose count equals the maximum, the winner is the one whose first
 // occurrence comes first in (type, position) order == ascending slot order.  Chunks are handed out in ascending
 // order; a chunk that starts after an already found position is skipped, so the scan stops early.
-constexpr uint32_t kTieChunk = 4096;
+constexpr uint32_t kTieChunk = 512;    // 2 positions per thread: a chunk is one L2 round trip deep
 __global__ void __launch_bounds__(256) k_tie_scan(TrainDev d) {
     TrainState *st = d.st;
     if (st->halt || st->n_tied <= 1) return;
@@ -710,8 +736,13 @@ SWT_API int swt_bpe_train_select(swt_bpe_trainer *t, void *stream) {
         k_wp_argmax_partial<<<t->dev.n_parts, 256, 0, st>>>(t->dev);
         k_wp_select<<<1, 256, 0, st>>>(t->dev);
     } else {
-        k_argmax_partial<<<t->dev.n_parts, 256, 0, st>>>(t->dev);
-        k_select<<<1, 1024, 0, st>>>(t->dev);
+        if (t->table_cap <= (1ull << 20)) {       // small table: plain parallel pass
+            k_argmax_full<<<t->dev.n_parts, 256, 0, st>>>(t->dev);
+            k_select<<<1, 1024, 0, st>>>(t->dev, 1);
+        } else {                                  // large table: refresh only the blocks the last merge touched
+            k_argmax_partial<<<t->dev.n_parts, 256, 0, st>>>(t->dev);
+            k_select<<<1, 1024, 0, st>>>(t->dev, 0);
+        }
     }
     if (t->dev.n_slots) k_tie_scan<<<t->grid_scan / 2, 256, 0, st>>>(t->dev);
     k_candidate<<<1, 1, 0, st>>>(t->dev);
