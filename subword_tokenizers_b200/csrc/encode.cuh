@@ -327,16 +327,23 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
     const bool use_memo = ws.memo_mask != 0;
     uint32_t h6 = 0;
 
+    // offsets of this lane's two words in a tile (three consecutive offsets); the next tile's are fetched one tile ahead
+    auto load_offsets = [&](uint32_t t, uint32_t &o0, uint32_t &o1, uint32_t &o2) {
+        const uint32_t w0 = t * kTileWords, tw = min((uint32_t)kTileWords, n_words - w0), i0 = lane * kWordsPerThread;
+        o0 = i0 <= tw ? __ldg(word_off + w0 + i0) : 0u;
+        o1 = i0 + 1 <= tw ? __ldg(word_off + w0 + i0 + 1) : 0u;
+        o2 = i0 + 2 <= tw ? __ldg(word_off + w0 + i0 + 2) : 0u;
+    };
+    uint32_t po0 = 0, po1 = 0, po2 = 0;
+    if (warp_global < ws.n_tiles) load_offsets(warp_global, po0, po1, po2);
     for (uint32_t tile = warp_global; tile < ws.n_tiles; tile += n_warps) {
         const uint32_t w_tile = tile * kTileWords;
         const uint32_t tile_words = min((uint32_t)kTileWords, n_words - w_tile);
-        // ---- offsets of this lane's two words
         uint32_t nb[kWordsPerThread], b0s[kWordsPerThread];
         {
             const uint32_t i0 = lane * kWordsPerThread;
-            const uint32_t o0 = i0 <= tile_words ? __ldg(word_off + w_tile + i0) : 0u;
-            const uint32_t o1 = i0 + 1 <= tile_words ? __ldg(word_off + w_tile + i0 + 1) : 0u;
-            const uint32_t o2 = i0 + 2 <= tile_words ? __ldg(word_off + w_tile + i0 + 2) : 0u;
+            const uint32_t o0 = po0, o1 = po1, o2 = po2;
+            if (tile + n_warps < ws.n_tiles) load_offsets(tile + n_warps, po0, po1, po2);
             b0s[0] = o0; nb[0] = i0 < tile_words ? o1 - o0 : 0xFFFFFFFFu;       // 0xFFFFFFFF: no word
             b0s[1] = o1; nb[1] = i0 + 1 < tile_words ? o2 - o1 : 0xFFFFFFFFu;
         }
@@ -516,7 +523,7 @@ __global__ void __launch_bounds__(kThreads, kEmitCtasPerSm)
 encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words,
                    uint32_t *__restrict__ out_ids, uint64_t out_cap, uint32_t *__restrict__ out_tok_off, uint32_t tok_base,
                    EncodeWorkspace ws) {
-    __shared__ uint32_t s_compact[kWarps][kCompactTokens];       // per warp: the tile's ids in output order
+    __shared__ __align__(16) uint32_t s_compact[kWarps][kCompactTokens + 4];   // per warp: the tile's ids in output order
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * kThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kThreads) >> 5;
     const bool tok_off_vec = out_tok_off && (((uintptr_t)out_tok_off & 7) == 0);
@@ -572,17 +579,21 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
             }
         }
         if (!fits_out) continue;                                                    // warp-uniform (status set by the scan)
+        // the tile's ids are laid out in shared memory with the 16-byte phase of their destination, so that the copy
+        // out is LDS.128 -> STG.128 without bank conflicts
+        const uint32_t sh = (uint32_t)((uintptr_t)(out_ids + base) >> 2) & 3u;
+        uint32_t *cdst = compact + sh;
 #pragma unroll
         for (int j = 0; j < kWordsPerThread; ++j) {
             if (kind[j] == kWordHit16) {
                 // two copies of the same code so that the common case compiles to shared-memory stores (STS)
-                if (use_compact) store_hit16_ids(compact + run[j], ntok[j], ra[j], rb[j]);
+                if (use_compact) store_hit16_ids(cdst + run[j], ntok[j], ra[j], rb[j]);
                 else store_hit16_ids(out_ids + base + run[j], ntok[j], ra[j], rb[j]);
             } else if (kind[j] == kWordHit) {
-                if (use_compact) store_hit_ids(compact + run[j], ntok[j], ra[j], rb[j], ws.memo + (arg[j] & 0xFFFFFu));
+                if (use_compact) store_hit_ids(cdst + run[j], ntok[j], ra[j], rb[j], ws.memo + (arg[j] & 0xFFFFFu));
                 else store_hit_ids(out_ids + base + run[j], ntok[j], ra[j], rb[j], ws.memo + (arg[j] & 0xFFFFFu));
             } else if (kind[j] == kWordRecompute || (!Enc::kScratchLong && kind[j] == kWordLong)) {
-                uint32_t *dst = use_compact ? compact + run[j] : out_ids + base + run[j];
+                uint32_t *dst = use_compact ? cdst + run[j] : out_ids + base + run[j];
                 const uint32_t b0 = __ldg(word_off + w_tile + i0 + j), b1 = __ldg(word_off + w_tile + i0 + j + 1);
                 emit_slow(enc, arena + b0, b1 - b0, kind[j], ntok[j], dst);
             }
@@ -598,24 +609,26 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
                     const uint32_t lb0 = __ldg(word_off + w_tile + owner * kWordsPerThread + j);
                     const uint32_t lnb = __ldg(word_off + w_tile + owner * kWordsPerThread + j + 1) - lb0;
                     const uint32_t *src = ws.long_scratch + ((unsigned long long)larg << 4) + kLongHeader + (lkind == kWordLongB ? lnb : 0u);
-                    uint32_t *dst = use_compact ? compact + lrun : out_ids + base + lrun;
+                    uint32_t *dst = use_compact ? cdst + lrun : out_ids + base + lrun;
                     for (uint32_t k = lane; k < ln; k += 32) dst[k] = src[k];
                 }
             }
         }
         __syncwarp();
         if (use_compact) {
-            // coalesced store: scalar head up to 16-byte alignment of the destination, then 128-bit stores
-            uint32_t *dst = out_ids + base;
-            const uint32_t head = min(total, (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15) >> 2);
-            if (lane < head) dst[lane] = compact[lane];
-            const uint32_t nvec = (total - head) >> 2;
+            uint32_t *dsta = out_ids + base - sh;                                   // 16-byte aligned
+            const uint32_t end = sh + total, nvec = (end + 3) >> 2;
             for (uint32_t v = lane; v < nvec; v += 32) {
-                const uint32_t c = head + 4 * v;
-                *reinterpret_cast<uint4 *>(dst + c) = make_uint4(compact[c], compact[c + 1], compact[c + 2], compact[c + 3]);
+                const uint32_t c = 4 * v;
+                const uint4 q = *reinterpret_cast<const uint4 *>(compact + c);
+                if (c >= sh && c + 4 <= end) *reinterpret_cast<uint4 *>(dsta + c) = q;
+                else {                                                              // first / last vector of the tile
+                    if (c >= sh && c < end) dsta[c] = q.x;
+                    if (c + 1 >= sh && c + 1 < end) dsta[c + 1] = q.y;
+                    if (c + 2 >= sh && c + 2 < end) dsta[c + 2] = q.z;
+                    if (c + 3 < end) dsta[c + 3] = q.w;
+                }
             }
-            const uint32_t tail0 = head + 4 * nvec;
-            if (tail0 + lane < total) dst[tail0 + lane] = compact[tail0 + lane];
         }
         __syncwarp();                                            // the compact buffer is reused by the next tile
     }
