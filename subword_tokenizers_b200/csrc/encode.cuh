@@ -134,6 +134,15 @@ __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// predicated (branch-free) read-only load: 0 when the predicate is false
+__device__ __forceinline__ uint32_t ldg_u32_if(const uint32_t *p, bool pred) {
+    uint32_t v = 0;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}" : "+r"(v) : "l"(p), "r"((uint32_t)pred));
+    return v;
+}
+// mask of the lowest min(max(n, 0), 4) bytes of a 32-bit word
+__device__ __forceinline__ uint32_t low_bytes_mask(int n) { return __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(n, 0) * 8u); }
+
 // Key of a word of 1..32 bytes: the first 15 bytes + the length form the 128-bit CAS key, bytes 15..31 the tail.
 // Reads aligned 8-byte words when that stays inside the arena.
 __device__ __forceinline__ void memo_key(const uint8_t *arena, uint32_t b0, uint32_t nbytes, uint32_t arena_end, MemoKey &k) {
@@ -262,22 +271,28 @@ __device__ __noinline__ void emit_slow(const Enc &enc, const uint8_t *word, uint
     }
 }
 
-// ids of a one-load hit (16-bit ids, at most 14) -> dst
+// ids of a one-load hit (16-bit ids, at most 14) -> dst.  The first eight are predicated stores without branches
+// (a branch per token cost more than the stores); the rare second half sits behind one warp-uniform test.
+template <bool kShared>
+__device__ __forceinline__ void store_id_if(uint32_t *dst, uint32_t k, uint32_t n, uint32_t v) {
+    if constexpr (kShared) {
+        const uint32_t a = (uint32_t)__cvta_generic_to_shared(dst + k);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %0, %1;\n\t@p st.shared.u32 [%2], %3;\n\t}" ::"r"(n), "r"(k), "r"(a), "r"(v) : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %0, %1;\n\t@p st.global.u32 [%2], %3;\n\t}" ::"r"(n), "r"(k), "l"(dst + k), "r"(v) : "memory");
+    }
+}
+template <bool kShared>
 __device__ __forceinline__ void store_hit16_ids(uint32_t *dst, uint32_t n, uint4 a, uint4 b) {
-    if (n > 0) dst[0] = a.x & 0xFFFFu;
-    if (n > 1) dst[1] = a.x >> 16;
-    if (n > 2) dst[2] = a.y & 0xFFFFu;
-    if (n > 3) dst[3] = a.y >> 16;
-    if (n > 4) dst[4] = a.z & 0xFFFFu;
-    if (n > 5) dst[5] = a.z >> 16;
-    if (n > 6) dst[6] = a.w & 0xFFFFu;
-    if (n > 7) dst[7] = a.w >> 16;
-    if (n > 8) dst[8] = b.x & 0xFFFFu;
-    if (n > 9) dst[9] = b.x >> 16;
-    if (n > 10) dst[10] = b.y & 0xFFFFu;
-    if (n > 11) dst[11] = b.y >> 16;
-    if (n > 12) dst[12] = b.z & 0xFFFFu;
-    if (n > 13) dst[13] = b.z >> 16;
+    store_id_if<kShared>(dst, 0, n, a.x & 0xFFFFu); store_id_if<kShared>(dst, 1, n, a.x >> 16);
+    store_id_if<kShared>(dst, 2, n, a.y & 0xFFFFu); store_id_if<kShared>(dst, 3, n, a.y >> 16);
+    store_id_if<kShared>(dst, 4, n, a.z & 0xFFFFu); store_id_if<kShared>(dst, 5, n, a.z >> 16);
+    store_id_if<kShared>(dst, 6, n, a.w & 0xFFFFu); store_id_if<kShared>(dst, 7, n, a.w >> 16);
+    if (n > 8) {
+        store_id_if<kShared>(dst, 8, n, b.x & 0xFFFFu); store_id_if<kShared>(dst, 9, n, b.x >> 16);
+        store_id_if<kShared>(dst, 10, n, b.y & 0xFFFFu); store_id_if<kShared>(dst, 11, n, b.y >> 16);
+        store_id_if<kShared>(dst, 12, n, b.z & 0xFFFFu); store_id_if<kShared>(dst, 13, n, b.z >> 16);
+    }
 }
 // ids of a hit found by the slow path (32-bit id list; ids 0-7 were prefetched, the rest is fetched here)
 __device__ __forceinline__ void store_hit_ids(uint32_t *dst, uint32_t n, uint4 a, uint4 b, const MemoEntry *e) {
@@ -366,10 +381,8 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
                     const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
                     const uint32_t span = nb[j] + (uint32_t)(a & 3);
                     a0[j] = __ldg(q);
-                    if (span > 4) a1[j] = __ldg(q + 1);
-                    if (span > 8) a2[j] = __ldg(q + 2);
-                    if (span > 12) a3[j] = __ldg(q + 3);
-                    if (span > 16) a4[j] = __ldg(q + 4);
+                    a1[j] = ldg_u32_if(q + 1, span > 4); a2[j] = ldg_u32_if(q + 2, span > 8);
+                    a3[j] = ldg_u32_if(q + 3, span > 12); a4[j] = ldg_u32_if(q + 4, span > 16);
                 }
             }
 #pragma unroll
@@ -379,10 +392,8 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
                     uint32_t w0 = __funnelshift_r(a0[j], a1[j], sh), w1 = __funnelshift_r(a1[j], a2[j], sh);
                     uint32_t w2 = __funnelshift_r(a2[j], a3[j], sh), w3 = __funnelshift_r(a3[j], a4[j], sh);
                     // zero the bytes at and beyond n, put the length into the top byte (layout of MemoEntry::lo/hi)
-                    w0 = n >= 4 ? w0 : w0 & ((1u << (8 * n)) - 1u);
-                    w1 = n >= 8 ? w1 : (n > 4 ? w1 & ((1u << (8 * (n - 4))) - 1u) : 0u);
-                    w2 = n >= 12 ? w2 : (n > 8 ? w2 & ((1u << (8 * (n - 8))) - 1u) : 0u);
-                    w3 = (n > 12 ? w3 & ((1u << (8 * (n - 12))) - 1u) : 0u) | (n << 24);
+                    w0 &= low_bytes_mask((int)n); w1 &= low_bytes_mask((int)n - 4); w2 &= low_bytes_mask((int)n - 8);
+                    w3 = (w3 & low_bytes_mask((int)n - 12)) | (n << 24);
                     kw[j] = make_uint4(w0, w1, w2, w3);
                     slot[j] = memo_hash4(w0, w1, w2, w3) & ws.memo_mask;
                     ew[j] = ld_ca_u32x4(ws.memo + slot[j]);      // ONE scattered load per word: key + pub nibble
@@ -529,14 +540,23 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
     const bool tok_off_vec = out_tok_off && (((uintptr_t)out_tok_off & 7) == 0);
     uint32_t *compact = s_compact[threadIdx.x >> 5];
 
+    // the per-word records and the tile's output position are fetched one tile ahead
+    auto load_tile = [&](uint32_t t, uint32_t &p0, uint32_t &p1, uint64_t &b) {
+        const uint32_t w0 = t * kTileWords, tw = min((uint32_t)kTileWords, n_words - w0), i = lane * kWordsPerThread;
+        p0 = p1 = 0u;
+        if (i + 1 < tw) { const uint2 p = *reinterpret_cast<const uint2 *>(ws.packed + w0 + i); p0 = p.x; p1 = p.y; }
+        else if (i < tw) p0 = ws.packed[w0 + i];
+        b = ws.group_base[t / kGroupTiles] + ws.tile_total[t];
+    };
+    uint32_t pp0 = 0, pp1 = 0; uint64_t pbase = 0;
+    if (warp_global < ws.n_tiles) load_tile(warp_global, pp0, pp1, pbase);
     for (uint32_t tile = warp_global; tile < ws.n_tiles; tile += n_warps) {
         const uint32_t w_tile = tile * kTileWords;
         const uint32_t tile_words = min((uint32_t)kTileWords, n_words - w_tile);
         const uint32_t i0 = lane * kWordsPerThread;
-        uint32_t packed[kWordsPerThread] = {0u, 0u};
-        if (i0 + 1 < tile_words) { const uint2 p = *reinterpret_cast<const uint2 *>(ws.packed + w_tile + i0); packed[0] = p.x; packed[1] = p.y; }
-        else if (i0 < tile_words) packed[0] = ws.packed[w_tile + i0];
-        const uint64_t base = ws.group_base[tile / kGroupTiles] + ws.tile_total[tile];
+        const uint32_t packed[kWordsPerThread] = {pp0, pp1};
+        const uint64_t base = pbase;
+        if (tile + n_warps < ws.n_tiles) load_tile(tile + n_warps, pp0, pp1, pbase);
         uint32_t kind[kWordsPerThread], ntok[kWordsPerThread], arg[kWordsPerThread];
         uint4 ra[kWordsPerThread], rb[kWordsPerThread];
 #pragma unroll
@@ -587,8 +607,8 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
         for (int j = 0; j < kWordsPerThread; ++j) {
             if (kind[j] == kWordHit16) {
                 // two copies of the same code so that the common case compiles to shared-memory stores (STS)
-                if (use_compact) store_hit16_ids(cdst + run[j], ntok[j], ra[j], rb[j]);
-                else store_hit16_ids(out_ids + base + run[j], ntok[j], ra[j], rb[j]);
+                if (use_compact) store_hit16_ids<true>(cdst + run[j], ntok[j], ra[j], rb[j]);
+                else store_hit16_ids<false>(out_ids + base + run[j], ntok[j], ra[j], rb[j]);
             } else if (kind[j] == kWordHit) {
                 if (use_compact) store_hit_ids(cdst + run[j], ntok[j], ra[j], rb[j], ws.memo + (arg[j] & 0xFFFFFu));
                 else store_hit_ids(out_ids + base + run[j], ntok[j], ra[j], rb[j], ws.memo + (arg[j] & 0xFFFFFu));
