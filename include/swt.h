@@ -51,6 +51,7 @@ extern "C" {
 #define SWT_ERR_ARG 2           /* invalid argument */
 #define SWT_ERR_CAPACITY 3      /* an output or workspace capacity was too small */
 #define SWT_ERR_INTERNAL 4      /* device-side consistency check failed */
+#define SWT_ERR_RANGE 5         /* a token id does not fit the requested 16-bit output (swt_encode_host16) */
 
 #define SWT_BPE_UNKNOWN_CP 0x40000000u
 #define SWT_BPE_EMPTY_TOKEN 0xFFFFFFFEu
@@ -138,6 +139,14 @@ void swt_pipeline_destroy(swt_pipeline *p);
 int swt_encode_host(swt_pipeline *p, int which, const void *table, const uint8_t *h_arena, const uint32_t *h_word_off,
                     uint64_t n_words, uint32_t *h_out_ids, uint64_t out_cap, uint32_t *h_out_tok_off,
                     uint64_t *n_tokens, uint64_t *h6_events);
+/* The same call with 16-bit token ids in the host buffer: halves the device-to-host traffic, which bounds the
+ * end-to-end rate (PCIe).  Usable when every token id is < 65536 (WordPiece: vocabulary + 2 <= 65536; BPE: symbol
+ * ids < 32768 and no character outside the merge alphabet); otherwise the call fails with SWT_ERR_RANGE and the
+ * caller falls back to swt_encode_host.  The reference returns a flat token list (wordpiece.py:270, bpe.py:249),
+ * so h_out_tok_off == NULL is the like-for-like output. */
+int swt_encode_host16(swt_pipeline *p, int which, const void *table, const uint8_t *h_arena, const uint32_t *h_word_off,
+                      uint64_t n_words, uint16_t *h_out_ids16, uint64_t out_cap, uint32_t *h_out_tok_off,
+                      uint64_t *n_tokens, uint64_t *h6_events);
 /* pinned host allocation helpers so integrators can give the pipeline DMA-able buffers */
 int swt_host_alloc(void **ptr, size_t bytes);
 void swt_host_free(void *ptr);

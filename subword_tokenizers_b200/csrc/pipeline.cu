@@ -24,12 +24,33 @@ namespace {
 constexpr int kSlots = 3;
 struct Slot {
     uint8_t *d_arena = nullptr; uint32_t *d_off = nullptr, *d_ids = nullptr, *d_tok_off = nullptr, *d_status = nullptr;
+    uint16_t *d_ids16 = nullptr;              // allocated on the first 16-bit call
     void *d_ws = nullptr; size_t ws_bytes = 0;
     uint32_t *h_status = nullptr;             // pinned
     cudaStream_t stream = nullptr;
     cudaEvent_t kernel_done = nullptr, d2h_done = nullptr;
     bool busy = false;
 };
+
+// 32-bit ids -> 16-bit ids (8 per thread); any id that does not fit raises SWT_ERR_RANGE in the status word.
+// The token count is read from the status words of the encode call that precedes it on the stream.
+__global__ void __launch_bounds__(256) narrow_ids_kernel(const uint32_t *__restrict__ ids, uint16_t *__restrict__ out,
+                                                         uint32_t *status) {
+    const uint64_t n = ((uint64_t)status[swt::kStatusTokensHi] << 32) | status[swt::kStatusTokens];
+    if (status[swt::kStatusCode] != SWT_OK) return;
+    uint32_t wide = 0;
+    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += (uint64_t)gridDim.x * blockDim.x * 8) {
+        if (i + 8 <= n) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(ids + i), b = *reinterpret_cast<const uint4 *>(ids + i + 4);
+            wide |= a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w;
+            *reinterpret_cast<uint4 *>(out + i) = make_uint4((a.x & 0xFFFFu) | (a.y << 16), (a.z & 0xFFFFu) | (a.w << 16),
+                                                            (b.x & 0xFFFFu) | (b.y << 16), (b.z & 0xFFFFu) | (b.w << 16));
+        } else {
+            for (uint64_t k = i; k < n; ++k) { wide |= ids[k]; out[k] = (uint16_t)ids[k]; }
+        }
+    }
+    if (wide > 0xFFFFu) atomicExch(&status[swt::kStatusCode], (uint32_t)SWT_ERR_RANGE);
+}
 }  // namespace
 
 struct swt_pipeline {
@@ -76,7 +97,7 @@ SWT_API void swt_pipeline_destroy(swt_pipeline *p) {
     for (int i = 0; i < kSlots; ++i) {
         Slot &s = p->slot[i];
         if (s.stream) cudaStreamSynchronize(s.stream);
-        cudaFree(s.d_arena); cudaFree(s.d_off); cudaFree(s.d_tok_off); cudaFree(s.d_ids); cudaFree(s.d_status); cudaFree(s.d_ws);
+        cudaFree(s.d_arena); cudaFree(s.d_off); cudaFree(s.d_tok_off); cudaFree(s.d_ids); cudaFree(s.d_ids16); cudaFree(s.d_status); cudaFree(s.d_ws);
         if (s.h_status) cudaFreeHost(s.h_status);
         if (s.kernel_done) cudaEventDestroy(s.kernel_done);
         if (s.d2h_done) cudaEventDestroy(s.d2h_done);
@@ -85,14 +106,19 @@ SWT_API void swt_pipeline_destroy(swt_pipeline *p) {
     delete p;
 }
 
-SWT_API int swt_encode_host(swt_pipeline *p, int which, const void *table, const uint8_t *h_arena, const uint32_t *h_word_off,
-                            uint64_t n_words, uint32_t *h_out_ids, uint64_t out_cap, uint32_t *h_out_tok_off,
+static int encode_host_impl(swt_pipeline *p, int which, const void *table, const uint8_t *h_arena, const uint32_t *h_word_off,
+                            uint64_t n_words, void *h_out_ids_any, bool narrow, uint64_t out_cap, uint32_t *h_out_tok_off,
                             uint64_t *n_tokens, uint64_t *h6_events) {
+    uint32_t *h_out_ids = narrow ? nullptr : (uint32_t *)h_out_ids_any;
+    uint16_t *h_out_ids16 = narrow ? (uint16_t *)h_out_ids_any : nullptr;
     SWT_REQUIRE(p && table && h_word_off && n_tokens, "NULL argument");
     SWT_REQUIRE(which == 0 || which == 1, "which must be 0 (BPE) or 1 (WP)");
     SWT_REQUIRE(n_words < 0xFFFFFFFFull, "n_words must be < 2^32 per call");
-    SWT_REQUIRE(n_words == 0 || (h_arena && h_out_ids), "NULL data pointer");
+    SWT_REQUIRE(n_words == 0 || (h_arena && h_out_ids_any), "NULL data pointer");
     SWT_CUDA_OK(cudaSetDevice(p->device));
+    if (narrow)
+        for (int i = 0; i < kSlots; ++i)
+            if (!p->slot[i].d_ids16) SWT_CUDA_OK(cudaMalloc(&p->slot[i].d_ids16, (p->batch_bytes + p->max_words + 16) * 2));
     // batch boundaries: [w0, w1) with at most batch_bytes bytes and max_words words
     struct Batch { uint64_t w0, w1; };
     std::vector<Batch> batches;
@@ -136,6 +162,7 @@ SWT_API int swt_encode_host(swt_pipeline *p, int which, const void *table, const
             rc = wp_encode_launch((const swt_wp_trie *)table, arena_rebased, s.d_off, nw, s.d_ids, cap,
                                   h_out_tok_off ? s.d_tok_off : nullptr, (uint32_t)total, s.d_ws, s.ws_bytes, s.d_status, s.stream);
         if (rc) break;
+        if (narrow) narrow_ids_kernel<<<swt::kNumSMs * 8, 256, 0, s.stream>>>(s.d_ids, s.d_ids16, s.d_status);
         SWT_CUDA_OK(cudaMemcpyAsync(s.h_status, s.d_status, 8 * 4, cudaMemcpyDeviceToHost, s.stream));
         SWT_CUDA_OK(cudaEventRecord(s.kernel_done, s.stream));
         SWT_CUDA_OK(cudaEventSynchronize(s.kernel_done));
@@ -143,7 +170,8 @@ SWT_API int swt_encode_host(swt_pipeline *p, int which, const void *table, const
         const uint64_t nt = ((uint64_t)s.h_status[kStatusTokensHi] << 32) | s.h_status[kStatusTokens];
         h6 += s.h_status[kStatusH6];
         if (total + nt > out_cap) { set_error("h_out_ids capacity too small"); rc = SWT_ERR_CAPACITY; break; }
-        if (nt) SWT_CUDA_OK(cudaMemcpyAsync(h_out_ids + total, s.d_ids, nt * 4, cudaMemcpyDeviceToHost, s.stream));
+        if (nt && narrow) SWT_CUDA_OK(cudaMemcpyAsync(h_out_ids16 + total, s.d_ids16, nt * 2, cudaMemcpyDeviceToHost, s.stream));
+        else if (nt) SWT_CUDA_OK(cudaMemcpyAsync(h_out_ids + total, s.d_ids, nt * 4, cudaMemcpyDeviceToHost, s.stream));
         if (h_out_tok_off) SWT_CUDA_OK(cudaMemcpyAsync(h_out_tok_off + b.w0, s.d_tok_off, (uint64_t)nw * 4, cudaMemcpyDeviceToHost, s.stream));
         SWT_CUDA_OK(cudaEventRecord(s.d2h_done, s.stream));
         s.busy = true;
@@ -155,4 +183,16 @@ SWT_API int swt_encode_host(swt_pipeline *p, int which, const void *table, const
     *n_tokens = total;
     if (h6_events) *h6_events = h6;
     return SWT_OK;
+}
+
+SWT_API int swt_encode_host(swt_pipeline *p, int which, const void *table, const uint8_t *h_arena, const uint32_t *h_word_off,
+                            uint64_t n_words, uint32_t *h_out_ids, uint64_t out_cap, uint32_t *h_out_tok_off,
+                            uint64_t *n_tokens, uint64_t *h6_events) {
+    return encode_host_impl(p, which, table, h_arena, h_word_off, n_words, h_out_ids, false, out_cap, h_out_tok_off, n_tokens, h6_events);
+}
+
+SWT_API int swt_encode_host16(swt_pipeline *p, int which, const void *table, const uint8_t *h_arena, const uint32_t *h_word_off,
+                              uint64_t n_words, uint16_t *h_out_ids16, uint64_t out_cap, uint32_t *h_out_tok_off,
+                              uint64_t *n_tokens, uint64_t *h6_events) {
+    return encode_host_impl(p, which, table, h_arena, h_word_off, n_words, h_out_ids16, true, out_cap, h_out_tok_off, n_tokens, h6_events);
 }

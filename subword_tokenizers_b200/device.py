@@ -105,14 +105,16 @@ class _Encoder:
 
     def encode_host(self, h_arena: torch.Tensor, h_off: torch.Tensor, h_out_ids: torch.Tensor,
                     h_out_tok_off: Optional[torch.Tensor], batch_bytes: int = 64 << 20) -> Tuple[int, int]:
-        """Host (ideally pinned) tensors in and out, through swt_encode_host. -> (n_tokens, h6_events)."""
+        """Host (ideally pinned) tensors in and out, through swt_encode_host (int32/uint32 h_out_ids) or
+        swt_encode_host16 (int16/uint16 h_out_ids; raises when an id does not fit). -> (n_tokens, h6_events)."""
         lib = _lib.load()
         n_words = h_off.numel() - 1
         nt, h6 = ctypes.c_uint64(0), ctypes.c_uint64(0)
-        check(lib.swt_encode_host(self.pipeline(batch_bytes), self._which, self._handle, h_arena.data_ptr(), h_off.data_ptr(),
-                                  n_words, h_out_ids.data_ptr(), h_out_ids.numel(),
-                                  h_out_tok_off.data_ptr() if h_out_tok_off is not None else None,
-                                  ctypes.byref(nt), ctypes.byref(h6)), "swt_encode_host")
+        fn = lib.swt_encode_host16 if h_out_ids.element_size() == 2 else lib.swt_encode_host
+        check(fn(self.pipeline(batch_bytes), self._which, self._handle, h_arena.data_ptr(), h_off.data_ptr(),
+                 n_words, h_out_ids.data_ptr(), h_out_ids.numel(),
+                 h_out_tok_off.data_ptr() if h_out_tok_off is not None else None,
+                 ctypes.byref(nt), ctypes.byref(h6)), fn.__name__)
         return int(nt.value), int(h6.value)
 
     def close(self):

@@ -430,3 +430,31 @@ def test_encode_host_without_token_offsets(P, dev):
     nt, _ = benc.encode_host(torch.from_numpy(arena).pin_memory(), torch.from_numpy(off.astype(np.uint32).view(np.int32)).pin_memory(),
                              h_ids, None, batch_bytes=1 << 16)
     assert nt == len(ids) and np.array_equal(h_ids.numpy()[:nt].view(np.uint32), ids)
+
+
+def test_encode_host_16bit_ids(P, dev):
+    """swt_encode_host16: the same ids as the 32-bit call, as u16; an id that does not fit fails loudly."""
+    import torch
+    from subword_tokenizers_b200._lib import SwtError
+    from subword_tokenizers_b200.utils import naive_wp_encode_ids
+    tab = P.WpTables(load_golden("pretrained_wp_vocab.json.gz"))
+    wenc = dev.WpEncoder(tab, naive_wp_encode_ids("##", tab))
+    words = [w for l in load_golden("pan_tadeusz.json.gz") for w in l.lower().split()]
+    arena, off = P.pack_words(words)
+    ids, tok, _ = wenc.encode_packed(arena, off.astype(np.uint32))
+    h_arena = torch.from_numpy(arena).pin_memory()
+    h_off = torch.from_numpy(off.astype(np.uint32).view(np.int32)).pin_memory()
+    h16 = torch.zeros(len(arena) + len(words) + 16, dtype=torch.int16).pin_memory()
+    h_tok = torch.zeros(len(words) + 1, dtype=torch.int32).pin_memory()
+    nt, _ = wenc.encode_host(h_arena, h_off, h16, h_tok, batch_bytes=1 << 16)           # many batches, odd token bases
+    assert nt == len(ids)
+    assert np.array_equal(h16.numpy()[:nt].view(np.uint16).astype(np.uint32), ids)
+    assert np.array_equal(h_tok.numpy().view(np.uint32), tok)
+    nt2, _ = wenc.encode_host(h_arena, h_off, h16, None)                                # flat token list only
+    assert nt2 == nt and np.array_equal(h16.numpy()[:nt].view(np.uint16).astype(np.uint32), ids)
+    # BPE: a character outside the merge alphabet comes back as 0x40000000|cp, which has no 16-bit form
+    benc = dev.BpeEncoder(P.BpeTables([("a", "b")]))
+    a2, o2 = P.pack_words(["ab", "a\u4e2db"])
+    with pytest.raises(SwtError):
+        benc.encode_host(torch.from_numpy(a2).pin_memory(), torch.from_numpy(o2.astype(np.uint32).view(np.int32)).pin_memory(),
+                         torch.zeros(64, dtype=torch.int16).pin_memory(), None)
