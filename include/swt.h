@@ -123,6 +123,33 @@ int swt_wp_encode(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *
                   uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off,
                   void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream);
 
+/* ---- device-side pre-tokenization for FastWP -------------------------- */
+/*
+ * swt_pretok_*  replaces  text.lower().split()  i.e. `s = text.lower() + " "` (wordpiece.py:248) and the
+ * whitespace skipping of FastWP.tokenize (wordpiece.py:266-269), on raw UTF-8 text resident on the device.
+ * Output: the packed word arena (lower-cased bytes of the whitespace-free chunks) + n_words+1 u32 offsets,
+ * exactly what swt_wp_encode consumes.
+ *   lower_map[cp] for cp < n_lower: the lower-case code point; 0x80000000|i = one-to-many mapping stored at
+ *   multi[i] = count, multi[i+1..] = code points (U+0130); 0x40000000 = U+03A3, resolved with the final-sigma
+ *   rule of CPython (needs the Cased / Case_Ignorable bitmaps, 0x110000/8 bytes each, bit cp&7 of byte cp>>3;
+ *   both NULL = the caller guarantees the text holds no U+03A3, else the call reports SWT_ERR_ARG).
+ *   Whitespace is Python's str.isspace() set (29 code points, fixed in the kernel).
+ * The text must be valid UTF-8 (lone surrogates in their 3-byte form are passed through), 4-byte aligned, in a
+ * buffer readable up to the next multiple of 4 bytes, and < 4 GiB per call.
+ * Two calls: swt_pretok_count fills d_status (8 x u32: [0] status, [1] n_words, [2]/[3] arena bytes lo/hi) so the
+ * caller can size the outputs; swt_pretok_write (same text, same workspace, untouched in between) writes them.
+ */
+typedef struct swt_pretok swt_pretok;
+int swt_pretok_create(const uint32_t *lower_map, uint32_t n_lower, const uint32_t *multi, uint32_t n_multi,
+                      const uint8_t *cased_bitmap, const uint8_t *ignorable_bitmap, int device, swt_pretok **out);
+void swt_pretok_destroy(swt_pretok *p);
+size_t swt_pretok_workspace_bytes(uint64_t n_text_bytes);
+int swt_pretok_count(const swt_pretok *p, const uint8_t *d_text, uint64_t n_bytes, void *d_workspace, size_t workspace_bytes,
+                     uint32_t *d_status, void *stream);
+int swt_pretok_write(const swt_pretok *p, const uint8_t *d_text, uint64_t n_bytes, void *d_workspace, size_t workspace_bytes,
+                     uint8_t *d_arena_out, uint64_t arena_cap, uint32_t *d_word_off_out, uint64_t word_cap,
+                     uint32_t n_words, uint64_t n_out_bytes, uint32_t *d_status, void *stream);
+
 /* ---- host-buffer entry points (what a non-Python integrator binds) ------------------------------- */
 /*
  * Same results as the device-pointer calls above, but inputs and outputs are HOST buffers:

@@ -58,6 +58,13 @@ SIGNATURES = {
     "swt_wp_trie_stats": (ctypes.c_int, [c_vp, c_u64p, c_u64p, c_u64p, c_u64p]),
     "swt_wp_encode": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint64, c_vp, ctypes.c_uint64, c_vp,
                                      c_vp, ctypes.c_size_t, c_vp, c_vp]),
+    "swt_pretok_create": (ctypes.c_int, [c_u32p, ctypes.c_uint32, c_u32p, ctypes.c_uint32, c_u8p, c_u8p, ctypes.c_int,
+                                         ctypes.POINTER(c_vp)]),
+    "swt_pretok_destroy": (None, [c_vp]),
+    "swt_pretok_workspace_bytes": (ctypes.c_size_t, [ctypes.c_uint64]),
+    "swt_pretok_count": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint64, c_vp, ctypes.c_size_t, c_vp, c_vp]),
+    "swt_pretok_write": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint64, c_vp, ctypes.c_size_t, c_vp, ctypes.c_uint64, c_vp,
+                                        ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, c_vp, c_vp]),
     "swt_pipeline_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(c_vp)]),
     "swt_pipeline_destroy": (None, [c_vp]),
     "swt_encode_host": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_uint64, c_vp, ctypes.c_uint64, c_vp,

@@ -1,0 +1,315 @@
+// pretok.cu -- device-side pre-tokenization of FastWP.tokenize.
+//
+// Replaces, on raw UTF-8 text resident in HBM, what the reference does on the host before the trie walk:
+//     s = text.lower() + " "                      source/wordpiece.py:248
+//     ... while i < len(s) and s[i].isspace(): i += 1      :266-269 (whitespace only ever separates segments)
+// i.e. Python's  text.lower().split():  the output is the packed word arena (lower-cased UTF-8 bytes of the
+// whitespace-free chunks) + u32 offsets that swt_wp_encode consumes.
+//
+// Exactness (the tests compare with CPython on the box):
+//   * whitespace = str.isspace(): the 29 code points listed in is_space_* below; the Python host verifies at start-up
+//     that the running interpreter agrees with this list and refuses to use the device path otherwise;
+//   * str.lower(): per-code-point table generated from the running interpreter (chr(cp).lower()), including the
+//     one-to-many mapping (U+0130) and the context rule for U+03A3 (final sigma; CPython's handle_capital_sigma,
+//     Objects/unicodeobject.c) with the Cased / Case_Ignorable bitmaps derived from the same interpreter.
+//
+// Layout: one thread owns 4 consecutive text bytes and sees a 12-byte window (4 before, 4 after), so every decision
+// (character start, whitespace, "previous character was whitespace", decode, lower) is local; a warp step covers
+// 128 bytes with fully coalesced loads, a warp tile is 4 KiB.  Two passes over the text (count, write) with a scan of
+// the tile sums in between -- the same structure as the encode kernels, no inter-tile dependency.
+#include <algorithm>
+
+#include "common.cuh"
+
+struct swt_pretok {
+    int device;
+    uint32_t *d_lower; uint32_t n_lower;
+    uint32_t *d_multi; uint32_t n_multi;
+    uint8_t *d_cased, *d_ignorable;      // 0x110000 / 8 bytes each, or nullptr (text must then not contain U+03A3)
+};
+
+namespace swt {
+namespace {
+
+constexpr uint32_t kTileBytes = 4096, kStepBytes = 128, kGroupTiles = 1024;
+constexpr uint32_t kLowerMulti = 0x80000000u, kLowerSigma = 0x40000000u;
+enum { kPtCode = 0, kPtWords = 1, kPtBytesLo = 2, kPtBytesHi = 3 };
+
+struct PretokDev {
+    const uint32_t *lower; uint32_t n_lower;
+    const uint32_t *multi;
+    const uint8_t *cased, *ignorable;
+};
+struct PretokWs { unsigned long long *tile_sum; unsigned long long *group_base; uint32_t n_tiles, n_groups; };
+
+size_t pretok_layout(uint64_t n_bytes, void *base, PretokWs *ws) {
+    Carver c(base);
+    const uint64_t n_tiles = (n_bytes + kTileBytes - 1) / kTileBytes, n_groups = (n_tiles + kGroupTiles - 1) / kGroupTiles;
+    ws->tile_sum = c.take<unsigned long long>(n_tiles + 1);
+    ws->group_base = c.take<unsigned long long>(n_groups + 1);
+    ws->n_tiles = (uint32_t)n_tiles; ws->n_groups = (uint32_t)n_groups;
+    return c.used();
+}
+
+__device__ __forceinline__ bool is_space_ascii(uint32_t b) { return b == 0x20u || (b - 0x09u) < 5u || (b - 0x1Cu) < 4u; }
+// the non-ASCII str.isspace() characters: U+0085 U+00A0 | U+1680 | U+2000-200A U+2028 U+2029 U+202F | U+205F | U+3000
+__device__ __forceinline__ bool is_space_2(uint32_t b0, uint32_t b1) { return b0 == 0xC2u && (b1 == 0x85u || b1 == 0xA0u); }
+__device__ __forceinline__ bool is_space_3(uint32_t b0, uint32_t b1, uint32_t b2) {
+    if (b0 == 0xE2u) return (b1 == 0x80u && ((b2 - 0x80u) <= 0x0Au || b2 == 0xA8u || b2 == 0xA9u || b2 == 0xAFu)) || (b1 == 0x81u && b2 == 0x9Fu);
+    return (b0 == 0xE1u && b1 == 0x9Au && b2 == 0x80u) || (b0 == 0xE3u && b1 == 0x80u && b2 == 0x80u);
+}
+__device__ __forceinline__ uint32_t utf8_len_of(uint32_t cp) { return cp < 0x80u ? 1u : cp < 0x800u ? 2u : cp < 0x10000u ? 3u : 4u; }
+__device__ __forceinline__ bool bitmap_bit(const uint8_t *bm, uint32_t cp) { return cp < 0x110000u && ((bm[cp >> 3] >> (cp & 7)) & 1u); }
+__device__ __forceinline__ uint8_t *put_utf8(uint8_t *d, uint32_t cp) {
+    if (cp < 0x80u) { *d++ = (uint8_t)cp; }
+    else if (cp < 0x800u) { *d++ = (uint8_t)(0xC0u | (cp >> 6)); *d++ = (uint8_t)(0x80u | (cp & 0x3Fu)); }
+    else if (cp < 0x10000u) { *d++ = (uint8_t)(0xE0u | (cp >> 12)); *d++ = (uint8_t)(0x80u | ((cp >> 6) & 0x3Fu)); *d++ = (uint8_t)(0x80u | (cp & 0x3Fu)); }
+    else { *d++ = (uint8_t)(0xF0u | (cp >> 18)); *d++ = (uint8_t)(0x80u | ((cp >> 12) & 0x3Fu)); *d++ = (uint8_t)(0x80u | ((cp >> 6) & 0x3Fu)); *d++ = (uint8_t)(0x80u | (cp & 0x3Fu)); }
+    return d;
+}
+
+// U+03A3 at byte q lower-cases to U+03C2 iff  \p{Cased}\p{Case_Ignorable}* precedes it and no
+// \p{Case_Ignorable}*\p{Cased} follows (CPython handle_capital_sigma).  Rare: walks the text in global memory.
+static __device__ __noinline__ bool final_sigma(const PretokDev &t, const uint8_t *text, uint64_t n, uint64_t q) {
+    uint32_t c = 0, adv; bool found = false;
+    uint64_t j = q;
+    while (j > 0) {
+        uint64_t k = j - 1;
+        while (k > 0 && (text[k] & 0xC0u) == 0x80u) --k;
+        c = utf8_decode(text + k, n - k < 4 ? (uint32_t)(n - k) : 4u, adv);
+        j = k;
+        if (!bitmap_bit(t.ignorable, c)) { found = true; break; }
+    }
+    if (!found || !bitmap_bit(t.cased, c)) return false;
+    for (uint64_t k = q + 2; k < n; k += adv) {
+        c = utf8_decode(text + k, n - k < 4 ? (uint32_t)(n - k) : 4u, adv);
+        if (!bitmap_bit(t.ignorable, c)) return !bitmap_bit(t.cased, c);
+    }
+    return true;
+}
+
+// lower-case mapping of a non-ASCII code point: returns the number of output code points (1 or more) in out[]
+__device__ __forceinline__ uint32_t lower_cp(const PretokDev &t, uint32_t cp, const uint8_t *text, uint64_t n, uint64_t q,
+                                             uint32_t out[3], uint32_t *status) {
+    uint32_t lw = cp < t.n_lower ? __ldg(t.lower + cp) : cp;
+    if ((lw & (kLowerMulti | kLowerSigma)) == 0) { out[0] = lw; return 1; }
+    if (lw & kLowerSigma) {
+        if (!t.cased) { atomicExch(&status[kPtCode], (uint32_t)SWT_ERR_ARG); out[0] = 0x3C3u; return 1; }
+        out[0] = final_sigma(t, text, n, q) ? 0x3C2u : 0x3C3u;
+        return 1;
+    }
+    const uint32_t idx = lw & 0xFFFFFFu, cnt = min(__ldg(t.multi + idx), 3u);
+    for (uint32_t k = 0; k < cnt; ++k) out[k] = __ldg(t.multi + idx + 1 + k);
+    return cnt;
+}
+
+// One warp step: the 4 bytes of this lane at text[i .. i+4).  Returns (words << 16) | out_bytes of the lane; with kWrite
+// the lowered bytes go to arena + byte_pos and the word offsets to word_off + word_pos.
+template <bool kWrite>
+__device__ __forceinline__ uint32_t lane_step(const PretokDev &t, const uint8_t *text, uint64_t n, uint64_t i, uint32_t w_prev,
+                                              uint32_t w_cur, uint32_t w_next, uint8_t *arena, uint64_t byte_pos, uint32_t *word_off,
+                                              uint32_t word_pos, uint32_t *status) {
+    // window bytes B(k) = text[i + k], k in [-4, 8)
+    const uint32_t w[3] = {w_prev, w_cur, w_next};
+#define B(k) ((w[((k) + 4) >> 2] >> (8 * (((k) + 4) & 3))) & 0xFFu)
+    uint32_t words = 0, bytes = 0;
+    uint8_t *dst = kWrite ? arena + byte_pos : nullptr;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const uint64_t q = i + p;
+        const uint32_t b0 = B(p);
+        if (q >= n || (b0 & 0xC0u) == 0x80u) continue;                       // no character starts here
+        const uint32_t b1 = B(p + 1), b2 = B(p + 2), b3 = B(p + 3);
+        bool space;
+        if (b0 < 0x80u) space = is_space_ascii(b0);
+        else space = is_space_2(b0, b1) || (b0 >= 0xE1u && b0 <= 0xE3u && is_space_3(b0, b1, b2));
+        if (space) continue;
+        // does a word start here?  yes iff the previous character is whitespace (or there is none)
+        const uint32_t x = B(p - 1), y = B(p - 2), z = B(p - 3);
+        bool prev_space = q == 0 || is_space_ascii(x);
+        if (!prev_space && x >= 0x80u) prev_space = is_space_2(y, x) || is_space_3(z, y, x);
+        // lower-case and measure / write
+        uint32_t out[3], n_out = 1;
+        if (b0 < 0x80u) out[0] = (b0 - 0x41u) < 26u ? b0 + 0x20u : b0;
+        else {
+            uint32_t cp;
+            if (b0 < 0xE0u) cp = ((b0 & 0x1Fu) << 6) | (b1 & 0x3Fu);
+            else if (b0 < 0xF0u) cp = ((b0 & 0x0Fu) << 12) | ((b1 & 0x3Fu) << 6) | (b2 & 0x3Fu);
+            else cp = ((b0 & 0x07u) << 18) | ((b1 & 0x3Fu) << 12) | ((b2 & 0x3Fu) << 6) | (b3 & 0x3Fu);
+            n_out = lower_cp(t, cp, text, n, q, out, status);
+        }
+        if (prev_space) {
+            if (kWrite) word_off[word_pos + words] = (uint32_t)(byte_pos + bytes);
+            ++words;
+        }
+        for (uint32_t k = 0; k < n_out; ++k) {
+            bytes += utf8_len_of(out[k]);
+            if (kWrite) dst = put_utf8(dst, out[k]);
+        }
+    }
+#undef B
+    return (words << 16) | bytes;
+}
+
+template <bool kWrite>
+__global__ void __launch_bounds__(256) pretok_kernel(PretokDev t, const uint8_t *__restrict__ text, uint64_t n, PretokWs ws,
+                                                     uint8_t *__restrict__ arena, uint32_t *__restrict__ word_off, uint32_t n_words_total,
+                                                     uint32_t n_bytes_total, uint32_t *status) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t *t32 = reinterpret_cast<const uint32_t *>(text);
+    const uint64_t n_words32 = (n + 3) >> 2;
+    for (uint32_t tile = warp_global; tile < ws.n_tiles; tile += n_warps) {
+        uint64_t byte_pos = 0; uint32_t word_pos = 0;
+        if (kWrite) {
+            const unsigned long long base = ws.group_base[tile / kGroupTiles] + ws.tile_sum[tile];
+            byte_pos = base & 0xFFFFFFFFull; word_pos = (uint32_t)(base >> 32);
+        }
+        uint32_t tile_words = 0, tile_bytes = 0;
+        const uint64_t t0 = (uint64_t)tile * kTileBytes;
+#pragma unroll 2
+        for (uint32_t s = 0; s < kTileBytes / kStepBytes; ++s) {
+            const uint64_t i = t0 + (uint64_t)s * kStepBytes + lane * 4;
+            if (t0 + (uint64_t)s * kStepBytes >= n) break;                        // warp-uniform
+            const uint64_t wi = i >> 2;
+            const uint32_t w_cur = wi < n_words32 ? __ldg(t32 + wi) : 0u;
+            const uint32_t w_prev = (wi >= 1 && wi - 1 < n_words32) ? __ldg(t32 + wi - 1) : 0u;
+            const uint32_t w_next = wi + 1 < n_words32 ? __ldg(t32 + wi + 1) : 0u;
+            uint32_t mine = lane_step<false>(t, text, n, i, w_prev, w_cur, w_next, nullptr, 0, nullptr, 0, status);
+            if (kWrite) {
+                uint32_t incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += v; }
+                const uint32_t excl = incl - mine, total = __shfl_sync(0xffffffffu, incl, 31);
+                if (mine) lane_step<true>(t, text, n, i, w_prev, w_cur, w_next, arena, byte_pos + (excl & 0xFFFFu), word_off,
+                                          word_pos + (excl >> 16), status);
+                byte_pos += total & 0xFFFFu; word_pos += total >> 16;
+            } else {
+                tile_words += mine >> 16; tile_bytes += mine & 0xFFFFu;
+            }
+        }
+        if (!kWrite) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                tile_words += __shfl_xor_sync(0xffffffffu, tile_words, d);
+                tile_bytes += __shfl_xor_sync(0xffffffffu, tile_bytes, d);
+            }
+            if (lane == 0) ws.tile_sum[tile] = ((unsigned long long)tile_words << 32) | tile_bytes;
+        }
+    }
+    if (kWrite && blockIdx.x == 0 && threadIdx.x == 0)
+        word_off[n_words_total] = n_bytes_total;                                    // closing offset
+}
+
+// in-group exclusive prefixes of the packed (words << 32 | bytes) tile sums + the group totals
+__global__ void __launch_bounds__(256) pretok_scan_groups_kernel(PretokWs ws) {
+    __shared__ uint32_t sh_scan[36];
+    const uint32_t g = blockIdx.x, t0 = g * kGroupTiles + threadIdx.x * 4;
+    unsigned long long v[4]; uint32_t sw = 0, sb = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = t0 + k < ws.n_tiles ? ws.tile_sum[t0 + k] : 0ull; sw += (uint32_t)(v[k] >> 32); sb += (uint32_t)v[k]; }
+    uint32_t tw, tb;
+    uint32_t ew = block_exclusive_scan(sw, sh_scan, &tw);
+    uint32_t eb = block_exclusive_scan(sb, sh_scan, &tb);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (t0 + k < ws.n_tiles) ws.tile_sum[t0 + k] = ((unsigned long long)ew << 32) | eb;
+        ew += (uint32_t)(v[k] >> 32); eb += (uint32_t)v[k];
+    }
+    if (threadIdx.x == 0) ws.group_base[g] = ((unsigned long long)tw << 32) | tb;
+}
+// exclusive scan of the group totals (one thread: at most a few thousand groups) + the grand totals
+__global__ void pretok_scan_top_kernel(PretokWs ws, uint32_t *status) {
+    unsigned long long words = 0, bytes = 0;
+    for (uint32_t g = 0; g < ws.n_groups; ++g) {
+        const unsigned long long v = ws.group_base[g];
+        ws.group_base[g] = (words << 32) | (bytes & 0xFFFFFFFFull);
+        words += v >> 32; bytes += v & 0xFFFFFFFFull;
+    }
+    status[kPtWords] = (uint32_t)words; status[kPtBytesLo] = (uint32_t)bytes; status[kPtBytesHi] = (uint32_t)(bytes >> 32);
+    if (bytes >= 0xFFFFFFC0ull || words >= 0xFFFFFFFEull) status[kPtCode] = SWT_ERR_CAPACITY;
+}
+
+PretokDev dev_view(const swt_pretok *p) { return PretokDev{p->d_lower, p->n_lower, p->d_multi, p->d_cased, p->d_ignorable}; }
+int pretok_grid(uint32_t n_tiles) { return (int)std::min<uint32_t>((n_tiles + 7) / 8, kNumSMs * 8); }
+
+}  // namespace
+}  // namespace swt
+
+using namespace swt;
+
+SWT_API int swt_pretok_create(const uint32_t *lower_map, uint32_t n_lower, const uint32_t *multi, uint32_t n_multi,
+                              const uint8_t *cased_bitmap, const uint8_t *ignorable_bitmap, int device, swt_pretok **out) {
+    SWT_REQUIRE(out != nullptr && lower_map != nullptr && n_lower > 0, "NULL argument");
+    SWT_REQUIRE((cased_bitmap == nullptr) == (ignorable_bitmap == nullptr), "cased / ignorable bitmaps come together");
+    SWT_REQUIRE(n_multi == 0 || multi != nullptr, "multi is NULL");
+    SWT_CUDA_OK(cudaSetDevice(device));
+    swt_pretok *p = new swt_pretok();
+    p->device = device; p->n_lower = n_lower; p->n_multi = n_multi;
+    p->d_lower = nullptr; p->d_multi = nullptr; p->d_cased = p->d_ignorable = nullptr;
+    const size_t bm = 0x110000 / 8;
+    cudaError_t e = cudaMalloc(&p->d_lower, (size_t)n_lower * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_lower, lower_map, (size_t)n_lower * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_multi, ((size_t)n_multi + 4) * 4);
+    if (e == cudaSuccess) e = cudaMemset(p->d_multi, 0, ((size_t)n_multi + 4) * 4);
+    if (e == cudaSuccess && n_multi) e = cudaMemcpy(p->d_multi, multi, (size_t)n_multi * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && cased_bitmap) {
+        e = cudaMalloc(&p->d_cased, bm);
+        if (e == cudaSuccess) e = cudaMalloc(&p->d_ignorable, bm);
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_cased, cased_bitmap, bm, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_ignorable, ignorable_bitmap, bm, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        set_error(std::string("swt_pretok_create: ") + cudaGetErrorString(e));
+        swt_pretok_destroy(p);
+        return SWT_ERR_CUDA;
+    }
+    *out = p;
+    return SWT_OK;
+}
+
+SWT_API void swt_pretok_destroy(swt_pretok *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_lower); cudaFree(p->d_multi); cudaFree(p->d_cased); cudaFree(p->d_ignorable);
+    delete p;
+}
+
+SWT_API size_t swt_pretok_workspace_bytes(uint64_t n_text_bytes) {
+    PretokWs ws;
+    return pretok_layout(n_text_bytes, nullptr, &ws);
+}
+
+SWT_API int swt_pretok_count(const swt_pretok *p, const uint8_t *d_text, uint64_t n_bytes, void *d_workspace, size_t workspace_bytes,
+                             uint32_t *d_status, void *stream) {
+    SWT_REQUIRE(p && d_status && d_workspace, "NULL argument");
+    SWT_REQUIRE(n_bytes == 0 || d_text, "d_text is NULL");
+    SWT_REQUIRE(((uintptr_t)d_text & 3) == 0, "d_text must be 4-byte aligned");
+    SWT_REQUIRE(n_bytes < 0xFFFFFF00ull, "text must be < 4 GiB per call");
+    cudaStream_t st = (cudaStream_t)stream;
+    PretokWs ws;
+    if (pretok_layout(n_bytes, d_workspace, &ws) > workspace_bytes) { set_error("pretok workspace too small"); return SWT_ERR_CAPACITY; }
+    SWT_CUDA_OK(cudaMemsetAsync(d_status, 0, 8 * sizeof(uint32_t), st));
+    if (n_bytes == 0) return SWT_OK;
+    pretok_kernel<false><<<pretok_grid(ws.n_tiles), 256, 0, st>>>(dev_view(p), d_text, n_bytes, ws, nullptr, nullptr, 0, 0, d_status);
+    pretok_scan_groups_kernel<<<ws.n_groups, 256, 0, st>>>(ws);
+    pretok_scan_top_kernel<<<1, 1, 0, st>>>(ws, d_status);
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}
+
+SWT_API int swt_pretok_write(const swt_pretok *p, const uint8_t *d_text, uint64_t n_bytes, void *d_workspace, size_t workspace_bytes,
+                             uint8_t *d_arena_out, uint64_t arena_cap, uint32_t *d_word_off_out, uint64_t word_cap,
+                             uint32_t n_words, uint64_t n_out_bytes, uint32_t *d_status, void *stream) {
+    SWT_REQUIRE(p && d_status && d_workspace && d_word_off_out, "NULL argument");
+    SWT_REQUIRE(n_out_bytes == 0 || d_arena_out, "d_arena_out is NULL");
+    SWT_REQUIRE(((uintptr_t)d_text & 3) == 0, "d_text must be 4-byte aligned");
+    SWT_REQUIRE(arena_cap >= n_out_bytes && word_cap >= (uint64_t)n_words + 1, "output capacity below the counts of swt_pretok_count");
+    cudaStream_t st = (cudaStream_t)stream;
+    PretokWs ws;
+    if (pretok_layout(n_bytes, d_workspace, &ws) > workspace_bytes) { set_error("pretok workspace too small"); return SWT_ERR_CAPACITY; }
+    if (n_bytes == 0) { SWT_CUDA_OK(cudaMemsetAsync(d_word_off_out, 0, sizeof(uint32_t), st)); return SWT_OK; }
+    pretok_kernel<true><<<pretok_grid(ws.n_tiles), 256, 0, st>>>(dev_view(p), d_text, n_bytes, ws, d_arena_out, d_word_off_out, n_words, (uint32_t)n_out_bytes, d_status);
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}

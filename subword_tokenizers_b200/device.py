@@ -134,6 +134,75 @@ class _Encoder:
             pass
 
 
+class Pretokenizer:
+    """Device pre-tokenizer of FastWP: raw UTF-8 text -> lower-cased word arena + offsets (``text.lower().split()``;
+    reference wordpiece.py:248,266-269).  One instance per process and device; the sigma bitmaps are uploaded on
+    the first text that contains U+03A3."""
+
+    _instances = {}
+
+    @classmethod
+    def get(cls, device: Optional[int] = None) -> "Pretokenizer":
+        device = current_device() if device is None else device
+        if device not in cls._instances:
+            cls._instances[device] = cls(device)
+        return cls._instances[device]
+
+    def __init__(self, device: int):
+        _lib.require_cuda()
+        self.device = device
+        self.tables = P.PretokTables.get()
+        self._handle = c_vp(None)
+        self._with_sigma = False
+        self._create(False)
+
+    def _create(self, with_sigma: bool):
+        lib = _lib.load()
+        if self._handle:
+            lib.swt_pretok_destroy(self._handle)
+            self._handle = c_vp(None)
+        t = self.tables
+        cased = ign = None
+        if with_sigma:
+            cased, ign = t.sigma_bitmaps()
+        check(lib.swt_pretok_create(_np_ptr(t.lower_map, c_u32p), len(t.lower_map), _np_ptr(t.multi, c_u32p), len(t.multi),
+                                    _np_ptr(cased, c_u8p) if with_sigma else None, _np_ptr(ign, c_u8p) if with_sigma else None,
+                                    self.device, ctypes.byref(self._handle)), "swt_pretok_create")
+        self._with_sigma = with_sigma
+
+    def split_device(self, d_text: torch.Tensor, n_bytes: int, has_sigma: bool):
+        """d_text: uint8 CUDA tensor holding n_bytes of UTF-8 (numel a multiple of 4). -> (d_arena, d_word_off, n_words)."""
+        lib = _lib.load()
+        if has_sigma and not self._with_sigma:
+            self._create(True)
+        dev = d_text.device
+        ws = torch.empty(lib.swt_pretok_workspace_bytes(n_bytes), dtype=torch.uint8, device=dev)
+        d_status = torch.empty(8, dtype=torch.int32, device=dev)
+        check(lib.swt_pretok_count(self._handle, d_text.data_ptr(), n_bytes, ws.data_ptr(), ws.numel(), d_status.data_ptr(),
+                                   _stream_ptr()), "swt_pretok_count")
+        st = d_status.cpu().numpy().astype(np.uint32)
+        if st[0] != 0:
+            raise SwtError("pre-tokenizer status %d" % int(st[0]))
+        n_words, n_out = int(st[1]), int(st[2]) | (int(st[3]) << 32)
+        d_arena = torch.empty(n_out + 16, dtype=torch.uint8, device=dev)
+        d_off = torch.empty(n_words + 1, dtype=torch.int32, device=dev)
+        check(lib.swt_pretok_write(self._handle, d_text.data_ptr(), n_bytes, ws.data_ptr(), ws.numel(), d_arena.data_ptr(), n_out,
+                                   d_off.data_ptr(), n_words + 1, n_words, n_out, d_status.data_ptr(), _stream_ptr()),
+              "swt_pretok_write")
+        return d_arena, d_off, n_words
+
+    def split_text(self, text: str):
+        """Python str -> (d_arena, d_word_off, n_words) on the current device."""
+        data = P.encode_utf8(text)
+        n = len(data)
+        if n >= (1 << 32) - 256:
+            raise SwtError("text >= 4 GiB: split it")
+        host = np.zeros((n + 7) // 4 * 4, dtype=np.uint8)
+        host[:n] = np.frombuffer(data, dtype=np.uint8)
+        d_text = torch.from_numpy(host).to(torch.device("cuda", self.device))
+        return self.split_device(d_text, n, "\u03a3" in text)
+
+
 class BpeEncoder(_Encoder):
     """Device rank table of a merge list (reference FastBPE._bpe_ranks, bpe.py:200,257)."""
 
@@ -176,6 +245,17 @@ class WpEncoder(_Encoder):
                                      _np_ptr(ss, c_u32p), len(sharp_special),
                                      current_device() if device is None else device, ctypes.byref(self._handle)),
               "swt_wp_trie_create")
+
+    def encode_text(self, text: str, return_offsets: bool = False):
+        """FastWP.tokenize on the device from the raw text: pre-tokenization (Pretokenizer) + encode.
+        -> token ids u32 (and the u32 token offsets per word when return_offsets)."""
+        d_arena, d_off, n_words = Pretokenizer.get().split_text(text)
+        if n_words == 0:
+            return (np.zeros(0, np.uint32), np.zeros(1, np.uint32)) if return_offsets else np.zeros(0, np.uint32)
+        d_ids, d_tok_off, d_status = self.encode_device(d_arena, d_off, n_words, 0, want_offsets=return_offsets)
+        n_tok, _ = self.check_status(d_status)
+        ids = d_ids[:n_tok].cpu().numpy().view(np.uint32)
+        return (ids, d_tok_off.cpu().numpy().view(np.uint32)) if return_offsets else ids
 
     def stats(self):
         n, e, p, r = (ctypes.c_uint64(0) for _ in range(4))

@@ -42,6 +42,75 @@ def unicode_class_bitmaps() -> Tuple[np.ndarray, np.ndarray]:
     return _class_cache["alnum"], _class_cache["space"]
 
 
+# str.isspace() code points the device pre-tokenizer hard-codes (csrc/pretok.cu); checked against the interpreter
+PY_SPACE_CPS = frozenset([9, 10, 11, 12, 13, 28, 29, 30, 31, 32, 0x85, 0xA0, 0x1680, *range(0x2000, 0x200B), 0x2028, 0x2029,
+                          0x202F, 0x205F, 0x3000])
+LOWER_MULTI, LOWER_SIGMA = 0x80000000, 0x40000000
+
+
+class PretokTables:
+    """Tables of the device pre-tokenizer of FastWP (``text.lower().split()``), generated from the RUNNING interpreter so
+    that the device reproduces exactly this CPython's ``str.lower`` / ``str.isspace``.
+
+    lower_map[cp]: lower-case code point | LOWER_MULTI|index into ``multi`` (one-to-many) | LOWER_SIGMA (U+03A3).
+    ``sigma_bitmaps()``: Cased / Case_Ignorable bitmaps for the final-sigma rule, derived from ``str.lower`` itself
+    (CPython does not expose the two properties): only needed when a text contains U+03A3.
+    """
+
+    _instance = None
+
+    @classmethod
+    def get(cls) -> "PretokTables":
+        if cls._instance is None:
+            cls._instance = cls()
+        return cls._instance
+
+    def __init__(self):
+        _, space = unicode_class_bitmaps()
+        spaces = set(np.flatnonzero(np.unpackbits(space, bitorder="little")).tolist())
+        if spaces != set(PY_SPACE_CPS):
+            raise RuntimeError("str.isspace() of this interpreter differs from the set compiled into the device pre-tokenizer")
+        lower = np.arange(UNICODE_LIMIT, dtype=np.uint32)
+        multi: list = []
+        last = 0
+        for cp in range(0x80, UNICODE_LIMIT):
+            if 0xD800 <= cp < 0xE000:
+                continue
+            lo = chr(cp).lower()
+            if len(lo) == 1:
+                if ord(lo) != cp:
+                    lower[cp] = ord(lo); last = cp
+            else:
+                lower[cp] = LOWER_MULTI | len(multi); last = cp
+                multi.append(len(lo)); multi.extend(ord(c) for c in lo)
+                if len(lo) > 3:
+                    raise RuntimeError("lower() of U+%04X has more than 3 code points" % cp)
+        lower[0x3A3] = LOWER_SIGMA
+        self.lower_map = np.ascontiguousarray(lower[:max(last, 0x3A3) + 1])
+        self.multi = np.asarray(multi, dtype=np.uint32)
+        self._sigma = None
+
+    def sigma_bitmaps(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(cased, case_ignorable) bitmaps.  Cased = islower|isupper|istitle of the single character.  Case_Ignorable is
+        probed through the final-sigma rule of str.lower itself: for an uncased x, "a\u03a3" + x + "a" keeps a medial
+        sigma iff x is ignorable; for a cased x, "1" + x + "\u03a3" yields a medial sigma iff x is ignorable."""
+        if self._sigma is None:
+            cased = np.zeros(UNICODE_LIMIT, dtype=np.uint8)
+            ign = np.zeros(UNICODE_LIMIT, dtype=np.uint8)
+            for cp in range(UNICODE_LIMIT):
+                if 0xD800 <= cp < 0xE000:
+                    continue
+                ch = chr(cp)
+                if ch.islower() or ch.isupper() or ch.istitle():
+                    cased[cp] = 1
+                    if ("1" + ch + "\u03a3").lower()[-1] == "\u03c3":
+                        ign[cp] = 1
+                elif ("a\u03a3" + ch + "a").lower()[1] == "\u03c3":
+                    ign[cp] = 1
+            self._sigma = (np.packbits(cased, bitorder="little"), np.packbits(ign, bitorder="little"))
+        return self._sigma
+
+
 def encode_utf8(word: str) -> bytes:
     # lone surrogates are legal in a Python str; keep them round-trippable
     return word.encode("utf-8", "surrogatepass")

@@ -129,7 +129,7 @@ class FastWP(NaiveWP):
         if not isinstance(text, str):
             raise TypeError("Text to tokenize must be a string.")
         trie = self.vocab_trie                      # AttributeError before train/load, like the reference
-        ids, _, _ = trie.encoder.encode_words(self._chunks(text))
+        ids = trie.encoder.encode_text(text)        # lower-casing + whitespace split + LinMaxMatch, all on the device
         return trie.tables.tokens_to_strs(ids)
 
     def tokenize_batch(self, texts: Sequence[str]) -> List[List[str]]:

@@ -458,3 +458,64 @@ def test_encode_host_16bit_ids(P, dev):
     with pytest.raises(SwtError):
         benc.encode_host(torch.from_numpy(a2).pin_memory(), torch.from_numpy(o2.astype(np.uint32).view(np.int32)).pin_memory(),
                          torch.zeros(64, dtype=torch.int16).pin_memory(), None)
+
+
+# ---- device pre-tokenization of FastWP: must equal CPython's text.lower().split() -----------------
+def _device_split(dev, P, text):
+    d_arena, d_off, n_words = dev.Pretokenizer.get().split_text(text)
+    off = d_off.cpu().numpy().view(np.uint32)
+    arena = d_arena.cpu().numpy()[: int(off[-1])].tobytes()
+    assert len(off) == n_words + 1 and off[0] == 0
+    return [P.decode_utf8(arena[int(off[i]):int(off[i + 1])]) for i in range(n_words)]
+
+
+def test_pretok_matches_python_on_real_text(P, dev):
+    lines = load_golden("pan_tadeusz.json.gz")
+    for text in ("\n".join(lines), "  ".join(lines[:50]).upper(), "", " ", "\t\n", "a", " a", "a ", "Zażółć GĘŚLĄ jaźń"):
+        assert _device_split(dev, P, text) == text.lower().split()
+
+
+def test_pretok_unicode_corner_cases(P, dev):
+    spaces = "".join(chr(c) for c in sorted(P.PY_SPACE_CPS))
+    cases = [
+        spaces, "x" + "y".join(spaces) + "z",                                   # every whitespace character
+        "İstanbul İİ Kelvin K Ω ẞ ȺȾ \U00010400\U00010401 ǅ ǈ ῼ",      # length-changing / one-to-many lower()
+        "ΟΔΥΣΣΕΥΣ ΣΟΦΟΣ Σ ΑΣ' ΑΣ'Α Σ. ΆΣ́ 'Σ ΑΣ­Σ ΑΣ: ΑΣ:Α 1Σ ΣΣΣ ʰΣ ΑʰΣ",                 # final sigma contexts
+        "a\ud800b \udfff",                                                      # lone surrogates pass through
+        "éÉ" * 3000 + " " + "　".join("Abİ" for _ in range(2000)),     # multi-byte characters across tile boundaries
+        "x" * 4095 + "É" + "y" * 4093 + " " + "Z" * 9000,             # characters straddling 4 KiB tiles
+    ]
+    for text in cases:
+        assert _device_split(dev, P, text) == text.lower().split(), repr(text[:40])
+
+
+def test_pretok_every_code_point(P, dev):
+    cps = [c for c in range(0x110000) if not 0xD800 <= c < 0xE000]
+    text = " ".join(map(chr, cps))
+    assert _device_split(dev, P, text) == text.lower().split()
+    # every BMP code point (and the cased supplementary blocks) on both sides of a capital sigma
+    probe = [c for c in cps if c < 0x10000 or 0x10400 <= c < 0x10600 or 0x1D400 <= c < 0x1D800 or 0x1E900 <= c < 0x1E960
+             or 0xE0000 <= c < 0xE0200]
+    text = " ".join("a%sΣ%sb Σ%s" % (chr(c), chr(c), chr(c)) for c in probe)
+    assert _device_split(dev, P, text) == text.lower().split()
+
+
+def test_pretok_random_texts(P, dev):
+    alphabet = [chr(c) for c in (list(range(0x20, 0x7F)) + [9, 10, 13, 0x85, 0xA0, 0x130, 0x131, 0x3A3, 0x3C3, 0x3C2, 0x391, 0x3B1, 0x27,
+                                                          0x301, 0xAD, 0x1E9E, 0xDF, 0x212A, 0x2003, 0x3000, 0x4E2D, 0x10400, 0x1F600,
+                                                          0x141, 0x142, 0x17B, 0x41, 0x5A, 0x2C65, 0x23A])]
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 3, 5, 127, 128, 129, 4096, 50_000):
+        for _ in range(4):
+            text = "".join(alphabet[i] for i in rng.integers(0, len(alphabet), n))
+            assert _device_split(dev, P, text) == text.lower().split(), repr(text[:60])
+
+
+def test_fastwp_tokenize_text_on_device_equals_word_path(P, dev):
+    from subword_tokenizers_b200.utils import naive_wp_encode_ids
+    tab = P.WpTables(load_golden("pretrained_wp_vocab.json.gz"))
+    wenc = dev.WpEncoder(tab, naive_wp_encode_ids("##", tab))
+    text = "\n".join(load_golden("pan_tadeusz.json.gz")).upper()
+    ids_w, tok_w, _ = wenc.encode_words(text.lower().split())
+    ids_t, tok_t = wenc.encode_text(text, return_offsets=True)
+    assert np.array_equal(ids_w, ids_t) and np.array_equal(tok_w, tok_t)
