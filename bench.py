@@ -10,8 +10,9 @@ A "step" is one pass of the FastWP encode kernel over the whole stream.
 
   value      MB/s (10^6 input arena bytes per second) with the stream resident in HBM, CUDA-event timed,
              max over ranks, whole job.
-  e2e        same metric through the host-buffer C ABI (swt_encode_host): pinned host arena/offsets in,
-             token ids/offsets out, H2D and D2H inside the timed region.
+  e2e        same metric through the host-buffer C ABI from RAW TEXT (swt_wp_tokenize_host): pinned host text in,
+             lower-casing + whitespace split + encode on the device, flat 16-bit token ids out; H2D and D2H inside the
+             timed region.  Sub-entries: the packed-words variants (swt_encode_host16 / swt_encode_host).
   roofline   algorithmic bytes (arena + 4 B/word offset read, 4 B/token + 4 B/word offset written) per launch
              / mean kernel time, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
   cpu_baseline  the C oracle port of the reference's FastWP path on the host cores, bounded sample.
@@ -180,6 +181,24 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def device_text(d_arena, d_off, n_words):
+    """Raw text on the device for the pre-tokenizer: the stream's words joined (and followed) by single spaces.
+    -> (uint8 tensor padded to a multiple of 4, n_text_bytes)."""
+    import torch
+    dev = d_arena.device
+    n_bytes = int(d_arena.numel())
+    off = d_off[: n_words + 1].long()
+    wid = torch.repeat_interleave(torch.arange(n_words, device=dev, dtype=torch.int32), off[1:] - off[:-1])
+    pos = torch.arange(n_bytes, device=dev, dtype=torch.int64)
+    pos += wid
+    del wid
+    n_text = n_bytes + n_words
+    text = torch.full(((n_text + 7) // 4 * 4,), 0x20, dtype=torch.uint8, device=dev)
+    text[pos] = d_arena
+    text[n_text:] = 0
+    return text, n_text
+
+
 def cpu_oracle_wp(stream: "ZipfStream", vocab, sample_words: int, threads: int, repeats: int = 1):
     """Times the C oracle port of FastWP.tokenize on the first sample_words words, `threads` host threads
     (ctypes releases the GIL; every thread owns a disjoint slice). -> (MB/s, seconds, bytes)."""
@@ -331,7 +350,27 @@ def main():
     h_ids16 = torch.empty(n_tokens + 1024, dtype=torch.int16).pin_memory()
     e2e_value = time_e2e(h_ids16, None)
     e2e_ok = bool(torch.equal(h_ids16[:n_tokens].to(torch.int32) & 0xFFFF, ref_ids))
-    del h_ids16
+    # raw text (words joined by single spaces) -> device pre-tokenization (lower + whitespace split) + encode -> 16-bit ids
+    d_text, n_text = device_text(d_arena, d_off, n_words)
+    h_text = torch.empty(d_text.numel(), dtype=torch.uint8).pin_memory(); h_text.copy_(d_text)
+    del d_text
+    h_ids16.zero_()
+    enc.tokenize_host(h_text, n_text, h_ids16, has_sigma=False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    tic = time.perf_counter()
+    for _ in range(e2e_steps):
+        nt_text, nw_text, _ = enc.tokenize_host(h_text, n_text, h_ids16, has_sigma=False)
+    torch.cuda.synchronize()
+    t3 = torch.tensor([time.perf_counter() - tic], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+    assert nt_text == n_tokens and nw_text == n_words
+    e2e_text_value = job_bytes * e2e_steps / float(t3.item()) / 1e6
+    e2e_text_ok = bool(torch.equal(h_ids16[:n_tokens].to(torch.int32) & 0xFFFF, ref_ids))
+    del h_ids16, h_text
     h_ids = torch.empty(n_tokens + 1024, dtype=torch.int32).pin_memory()
     h_tok = torch.empty(n_words + 1, dtype=torch.int32).pin_memory()
     e2e32_value = time_e2e(h_ids, h_tok)
@@ -354,13 +393,20 @@ def main():
                      "traffic": TRAFFIC_1GB_WP if args.bytes == 1_000_000_000 else None, "traffic_source": TRAFFIC_SOURCE,
                      "peak_source": peak_src, "kernel": "encode_count_kernel<WpEnc> + scan + encode_emit_kernel<WpEnc> (one encode call)",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms},
-        "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": n_bytes + 4 * (n_words + 1),
-                "d2h_bytes_per_step": 2 * n_tokens + 32 * ((n_bytes >> 26) + 1), "steps": e2e_steps,
-                "call": "swt_encode_host16, flat 16-bit token ids (what tokenize() returns), no per-word offsets",
-                "matches_resident_run": e2e_ok,
-                "u32_ids_and_word_offsets": {"value": e2e32_value, "unit": "MB/s", "call": "swt_encode_host",
-                                             "d2h_bytes_per_step": 4 * n_tokens + 4 * n_words + 32 * ((n_bytes >> 26) + 1),
-                                             "matches_resident_run": e2e32_ok}},
+        "e2e": {"value": e2e_text_value, "unit": "MB/s", "h2d_bytes_per_step": n_text,
+                "d2h_bytes_per_step": 2 * n_tokens + 64 * ((n_text >> 26) + 1), "steps": e2e_steps,
+                "call": "swt_wp_tokenize_host",
+                "what": "raw UTF-8 text (the stream's words joined by single spaces) in a pinned host buffer -> H2D -> lower-casing + "
+                        "whitespace split on the device (swt_pretok_*) -> FastWP encode -> 16-bit flat token ids (the list "
+                        "tokenize() returns) D2H into a pinned host buffer; MB = word bytes, as in `value`",
+                "matches_resident_run": e2e_text_ok,
+                "packed_words_in_16bit_ids": {"value": e2e_value, "unit": "MB/s", "call": "swt_encode_host16",
+                                              "h2d_bytes_per_step": n_bytes + 4 * (n_words + 1),
+                                              "d2h_bytes_per_step": 2 * n_tokens + 32 * ((n_bytes >> 26) + 1), "matches_resident_run": e2e_ok},
+                "packed_words_in_u32_ids_and_word_offsets": {"value": e2e32_value, "unit": "MB/s", "call": "swt_encode_host",
+                                                             "h2d_bytes_per_step": n_bytes + 4 * (n_words + 1),
+                                                             "d2h_bytes_per_step": 4 * n_tokens + 4 * n_words + 32 * ((n_bytes >> 26) + 1),
+                                                             "matches_resident_run": e2e32_ok}},
         "gpu_launches": 5 * args.steps, "clocks": clocks,
         "stream": {"n_words": n_words, "n_bytes": n_bytes, "n_tokens": n_tokens, "h6_events": h6},
     }

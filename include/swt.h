@@ -174,6 +174,12 @@ int swt_encode_host(swt_pipeline *p, int which, const void *table, const uint8_t
 int swt_encode_host16(swt_pipeline *p, int which, const void *table, const uint8_t *h_arena, const uint32_t *h_word_off,
                       uint64_t n_words, uint16_t *h_out_ids16, uint64_t out_cap, uint32_t *h_out_tok_off,
                       uint64_t *n_tokens, uint64_t *h6_events);
+/* FastWP.tokenize from RAW TEXT in a host buffer (wordpiece.py:233-270 end to end): per batch H2D of the text,
+ * swt_pretok_count/_write, swt_wp_encode, D2H of the flat token ids (16-bit when ids_16bit != 0, see
+ * swt_encode_host16).  Batches are cut after ASCII whitespace.  n_words_out / h6_events may be NULL. */
+int swt_wp_tokenize_host(swt_pipeline *p, const swt_pretok *pretok, const swt_wp_trie *trie, const uint8_t *h_text,
+                         uint64_t n_bytes, void *h_out_ids, int ids_16bit, uint64_t out_cap, uint64_t *n_tokens,
+                         uint64_t *n_words_out, uint64_t *h6_events);
 /* pinned host allocation helpers so integrators can give the pipeline DMA-able buffers */
 int swt_host_alloc(void **ptr, size_t bytes);
 void swt_host_free(void *ptr);

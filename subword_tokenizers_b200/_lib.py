@@ -71,6 +71,8 @@ SIGNATURES = {
                                        c_u64p, c_u64p]),
     "swt_encode_host16": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_uint64, c_vp, ctypes.c_uint64, c_vp,
                                          c_u64p, c_u64p]),
+    "swt_wp_tokenize_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_uint64, c_vp, ctypes.c_int, ctypes.c_uint64, c_u64p,
+                                            c_u64p, c_u64p]),
     "swt_host_alloc": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_size_t]),
     "swt_host_free": (None, [c_vp]),
     "swt_bpe_train_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(TrainConfig)]),

@@ -1,6 +1,6 @@
 // pipeline.cu -- host-buffer entry point: stages a host-resident corpus through the GPU in batches.
 //
-// Three slots, one CUDA stream each; per batch k on slot k%3:  H2D(arena slice, offset slice) -> encode
+// Five slots, one CUDA stream each; per batch k on slot k%5:  H2D(arena slice, offset slice) -> encode
 // kernel -> D2H(token ids, token offsets).  H2D of batch k+1 and D2H of batch k-1 overlap the kernel of
 // batch k (PCIe is full duplex).  The kernel of batch k is launched once the token total of batch k-1 is
 // known, so that token offsets come out global and ids land compactly in the caller's buffer.
@@ -21,10 +21,12 @@ int wp_encode_launch(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_
 }
 
 namespace {
-constexpr int kSlots = 3;
+constexpr int kSlots = 5;
+constexpr uint64_t kLowerGrowthNum = 3, kLowerGrowthDen = 2;   // str.lower() grows UTF-8 text by at most 3/2 (2-byte -> 3-byte)
 struct Slot {
     uint8_t *d_arena = nullptr; uint32_t *d_off = nullptr, *d_ids = nullptr, *d_tok_off = nullptr, *d_status = nullptr;
     uint16_t *d_ids16 = nullptr;              // allocated on the first 16-bit call
+    uint8_t *d_text = nullptr; void *d_ptws = nullptr; size_t ptws_bytes = 0;   // raw-text mode (allocated on first use)
     void *d_ws = nullptr; size_t ws_bytes = 0;
     uint32_t *h_status = nullptr;             // pinned
     cudaStream_t stream = nullptr;
@@ -71,10 +73,10 @@ SWT_API int swt_pipeline_create(int device, uint64_t batch_bytes, swt_pipeline *
         Slot &s = p->slot[i];
         // BPE long-word scratch is sized for the worst case (every word of the batch is long)
         s.ws_bytes = swt_encode_workspace_bytes((uint32_t)p->max_words, batch_bytes);
-        cudaError_t e = cudaMalloc(&s.d_arena, batch_bytes + 16);
+        cudaError_t e = cudaMalloc(&s.d_arena, batch_bytes * kLowerGrowthNum / kLowerGrowthDen + 16);
         if (e == cudaSuccess) e = cudaMalloc(&s.d_off, (p->max_words + 1) * 4);
         if (e == cudaSuccess) e = cudaMalloc(&s.d_tok_off, (p->max_words + 1) * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&s.d_ids, (batch_bytes + p->max_words + 16) * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_ids, (batch_bytes * kLowerGrowthNum / kLowerGrowthDen + p->max_words + 16) * 4);
         if (e == cudaSuccess) e = cudaMalloc(&s.d_status, 8 * 4);
         if (e == cudaSuccess) e = cudaMalloc(&s.d_ws, s.ws_bytes);
         if (e == cudaSuccess) e = cudaHostAlloc((void **)&s.h_status, 8 * 4, cudaHostAllocDefault);
@@ -97,7 +99,7 @@ SWT_API void swt_pipeline_destroy(swt_pipeline *p) {
     for (int i = 0; i < kSlots; ++i) {
         Slot &s = p->slot[i];
         if (s.stream) cudaStreamSynchronize(s.stream);
-        cudaFree(s.d_arena); cudaFree(s.d_off); cudaFree(s.d_tok_off); cudaFree(s.d_ids); cudaFree(s.d_ids16); cudaFree(s.d_status); cudaFree(s.d_ws);
+        cudaFree(s.d_arena); cudaFree(s.d_off); cudaFree(s.d_tok_off); cudaFree(s.d_ids); cudaFree(s.d_ids16); cudaFree(s.d_text); cudaFree(s.d_ptws); cudaFree(s.d_status); cudaFree(s.d_ws);
         if (s.h_status) cudaFreeHost(s.h_status);
         if (s.kernel_done) cudaEventDestroy(s.kernel_done);
         if (s.d2h_done) cudaEventDestroy(s.d2h_done);
@@ -118,7 +120,7 @@ static int encode_host_impl(swt_pipeline *p, int which, const void *table, const
     SWT_CUDA_OK(cudaSetDevice(p->device));
     if (narrow)
         for (int i = 0; i < kSlots; ++i)
-            if (!p->slot[i].d_ids16) SWT_CUDA_OK(cudaMalloc(&p->slot[i].d_ids16, (p->batch_bytes + p->max_words + 16) * 2));
+            if (!p->slot[i].d_ids16) SWT_CUDA_OK(cudaMalloc(&p->slot[i].d_ids16, (p->batch_bytes * kLowerGrowthNum / kLowerGrowthDen + p->max_words + 16) * 2));
     // batch boundaries: [w0, w1) with at most batch_bytes bytes and max_words words
     struct Batch { uint64_t w0, w1; };
     std::vector<Batch> batches;
@@ -195,4 +197,92 @@ SWT_API int swt_encode_host16(swt_pipeline *p, int which, const void *table, con
                               uint64_t n_words, uint16_t *h_out_ids16, uint64_t out_cap, uint32_t *h_out_tok_off,
                               uint64_t *n_tokens, uint64_t *h6_events) {
     return encode_host_impl(p, which, table, h_arena, h_word_off, n_words, h_out_ids16, true, out_cap, h_out_tok_off, n_tokens, h6_events);
+}
+
+// ---- raw text in, flat token ids out: pre-tokenization (pretok.cu) + FastWP encode per batch --------------------------------
+static bool ascii_space(uint8_t b) { return b == 0x20 || (b >= 0x09 && b <= 0x0D) || (b >= 0x1C && b <= 0x1F); }
+
+SWT_API int swt_wp_tokenize_host(swt_pipeline *p, const swt_pretok *pretok, const swt_wp_trie *trie, const uint8_t *h_text,
+                                 uint64_t n_bytes, void *h_out_ids, int ids_16bit, uint64_t out_cap, uint64_t *n_tokens,
+                                 uint64_t *n_words_out, uint64_t *h6_events) {
+    SWT_REQUIRE(p && pretok && trie && n_tokens, "NULL argument");
+    SWT_REQUIRE(n_bytes == 0 || (h_text && h_out_ids), "NULL data pointer");
+    SWT_CUDA_OK(cudaSetDevice(p->device));
+    const bool narrow = ids_16bit != 0;
+    const uint64_t slice_max = p->batch_bytes - 8;
+    for (int i = 0; i < kSlots; ++i) {
+        Slot &s = p->slot[i];
+        if (narrow && !s.d_ids16) SWT_CUDA_OK(cudaMalloc(&s.d_ids16, (p->batch_bytes * kLowerGrowthNum / kLowerGrowthDen + p->max_words + 16) * 2));
+        if (!s.d_text) {
+            SWT_CUDA_OK(cudaMalloc(&s.d_text, p->batch_bytes + 16));
+            s.ptws_bytes = swt_pretok_workspace_bytes(p->batch_bytes);
+            SWT_CUDA_OK(cudaMalloc(&s.d_ptws, s.ptws_bytes));
+        }
+    }
+    // batches end just after an ASCII whitespace byte (a whole character in UTF-8), so no word is cut
+    struct Batch { uint64_t b0, b1; };
+    std::vector<Batch> batches;
+    for (uint64_t b0 = 0; b0 < n_bytes;) {
+        uint64_t b1 = std::min<uint64_t>(n_bytes, b0 + slice_max);
+        if (b1 < n_bytes) {
+            uint64_t j = b1;
+            while (j > b0 && !ascii_space(h_text[j - 1])) --j;
+            if (j == b0) { set_error("no ASCII whitespace within one pipeline batch: raise batch_bytes"); return SWT_ERR_CAPACITY; }
+            b1 = j;
+        }
+        batches.push_back({b0, b1});
+        b0 = b1;
+    }
+    auto enqueue_h2d = [&](size_t k) -> int {
+        Slot &s = p->slot[k % kSlots];
+        if (s.busy) { SWT_CUDA_OK(cudaEventSynchronize(s.d2h_done)); s.busy = false; }
+        const Batch &b = batches[k];
+        const uint64_t nb = b.b1 - b.b0;
+        SWT_CUDA_OK(cudaMemcpyAsync(s.d_text, h_text + b.b0, nb, cudaMemcpyHostToDevice, s.stream));
+        SWT_CUDA_OK(cudaMemsetAsync(s.d_text + nb, 0, 8, s.stream));
+        int rc = swt_pretok_count(pretok, s.d_text, nb, s.d_ptws, s.ptws_bytes, s.d_status, s.stream);
+        if (rc) return rc;
+        SWT_CUDA_OK(cudaMemcpyAsync(s.h_status, s.d_status, 8 * 4, cudaMemcpyDeviceToHost, s.stream));
+        SWT_CUDA_OK(cudaEventRecord(s.kernel_done, s.stream));
+        return SWT_OK;
+    };
+    uint64_t total = 0, h6 = 0, words = 0;
+    int rc = SWT_OK;
+    if (!batches.empty()) rc = enqueue_h2d(0);
+    for (size_t k = 0; k < batches.size() && rc == SWT_OK; ++k) {
+        if (k + 1 < batches.size()) { rc = enqueue_h2d(k + 1); if (rc) break; }
+        Slot &s = p->slot[k % kSlots];
+        const uint64_t nb = batches[k].b1 - batches[k].b0;
+        SWT_CUDA_OK(cudaEventSynchronize(s.kernel_done));                       // counts of this batch
+        if (s.h_status[0] != SWT_OK) { set_error("pre-tokenizer reported status " + std::to_string(s.h_status[0])); rc = (int)s.h_status[0]; break; }
+        const uint32_t nw = s.h_status[1];
+        const uint64_t n_arena = ((uint64_t)s.h_status[3] << 32) | s.h_status[2];
+        if (nw > p->max_words) { set_error("more words in a batch than the pipeline was sized for"); rc = SWT_ERR_CAPACITY; break; }
+        rc = swt_pretok_write(pretok, s.d_text, nb, s.d_ptws, s.ptws_bytes, s.d_arena, n_arena, s.d_off, p->max_words + 1, nw, n_arena,
+                              s.d_status, s.stream);
+        if (rc) break;
+        words += nw;
+        if (nw == 0) continue;
+        rc = wp_encode_launch(trie, s.d_arena, s.d_off, nw, s.d_ids, n_arena + nw + 16, nullptr, 0, s.d_ws, s.ws_bytes, s.d_status, s.stream);
+        if (rc) break;
+        if (narrow) narrow_ids_kernel<<<swt::kNumSMs * 8, 256, 0, s.stream>>>(s.d_ids, s.d_ids16, s.d_status);
+        SWT_CUDA_OK(cudaMemcpyAsync(s.h_status, s.d_status, 8 * 4, cudaMemcpyDeviceToHost, s.stream));
+        SWT_CUDA_OK(cudaEventRecord(s.kernel_done, s.stream));
+        SWT_CUDA_OK(cudaEventSynchronize(s.kernel_done));
+        if (s.h_status[kStatusCode] != SWT_OK) { set_error("encode kernel reported status " + std::to_string(s.h_status[kStatusCode])); rc = (int)s.h_status[kStatusCode]; break; }
+        const uint64_t nt = ((uint64_t)s.h_status[kStatusTokensHi] << 32) | s.h_status[kStatusTokens];
+        h6 += s.h_status[kStatusH6];
+        if (total + nt > out_cap) { set_error("h_out_ids capacity too small"); rc = SWT_ERR_CAPACITY; break; }
+        if (nt && narrow) SWT_CUDA_OK(cudaMemcpyAsync((uint16_t *)h_out_ids + total, s.d_ids16, nt * 2, cudaMemcpyDeviceToHost, s.stream));
+        else if (nt) SWT_CUDA_OK(cudaMemcpyAsync((uint32_t *)h_out_ids + total, s.d_ids, nt * 4, cudaMemcpyDeviceToHost, s.stream));
+        SWT_CUDA_OK(cudaEventRecord(s.d2h_done, s.stream));
+        s.busy = true;
+        total += nt;
+    }
+    for (int i = 0; i < kSlots; ++i) { cudaStreamSynchronize(p->slot[i].stream); p->slot[i].busy = false; }
+    if (rc != SWT_OK) return rc;
+    *n_tokens = total;
+    if (n_words_out) *n_words_out = words;
+    if (h6_events) *h6_events = h6;
+    return SWT_OK;
 }

@@ -257,6 +257,20 @@ class WpEncoder(_Encoder):
         ids = d_ids[:n_tok].cpu().numpy().view(np.uint32)
         return (ids, d_tok_off.cpu().numpy().view(np.uint32)) if return_offsets else ids
 
+    def tokenize_host(self, h_text: torch.Tensor, n_bytes: int, h_out_ids: torch.Tensor, has_sigma: bool = True,
+                      batch_bytes: int = 64 << 20) -> Tuple[int, int, int]:
+        """Raw UTF-8 text in a host (ideally pinned) uint8 tensor -> flat token ids in h_out_ids (int16/uint16 or int32),
+        through swt_wp_tokenize_host. -> (n_tokens, n_words, h6_events)."""
+        lib = _lib.load()
+        pt = Pretokenizer.get()
+        if has_sigma and not pt._with_sigma:
+            pt._create(True)
+        nt, nw, h6 = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint64(0)
+        check(lib.swt_wp_tokenize_host(self.pipeline(batch_bytes), pt._handle, self._handle, h_text.data_ptr(), n_bytes,
+                                       h_out_ids.data_ptr(), 1 if h_out_ids.element_size() == 2 else 0, h_out_ids.numel(),
+                                       ctypes.byref(nt), ctypes.byref(nw), ctypes.byref(h6)), "swt_wp_tokenize_host")
+        return int(nt.value), int(nw.value), int(h6.value)
+
     def stats(self):
         n, e, p, r = (ctypes.c_uint64(0) for _ in range(4))
         check(_lib.load().swt_wp_trie_stats(self._handle, ctypes.byref(n), ctypes.byref(e), ctypes.byref(p), ctypes.byref(r)))

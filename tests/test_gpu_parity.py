@@ -519,3 +519,22 @@ def test_fastwp_tokenize_text_on_device_equals_word_path(P, dev):
     ids_w, tok_w, _ = wenc.encode_words(text.lower().split())
     ids_t, tok_t = wenc.encode_text(text, return_offsets=True)
     assert np.array_equal(ids_w, ids_t) and np.array_equal(tok_w, tok_t)
+
+
+def test_wp_tokenize_host_from_raw_text(P, dev):
+    """swt_wp_tokenize_host: raw text in a host buffer, many small batches, 16- and 32-bit ids."""
+    import torch
+    from subword_tokenizers_b200.utils import naive_wp_encode_ids
+    tab = P.WpTables(load_golden("pretrained_wp_vocab.json.gz"))
+    wenc = dev.WpEncoder(tab, naive_wp_encode_ids("##", tab))
+    text = "\n".join(load_golden("pan_tadeusz.json.gz")) + " ΟΔΥΣΣΕΥΣ İstanbul　x"
+    ids, _, _ = wenc.encode_words(text.lower().split())
+    data = np.frombuffer(P.encode_utf8(text), dtype=np.uint8)
+    h_text = torch.from_numpy(data.copy()).pin_memory()
+    for dtype in (torch.int16, torch.int32):
+        h_ids = torch.zeros(len(data) * 2 + 64, dtype=dtype).pin_memory()
+        nt, nw, _ = wenc.tokenize_host(h_text, len(data), h_ids, batch_bytes=1 << 16)
+        assert nw == len(text.lower().split()) and nt == len(ids)
+        got = h_ids.numpy()[:nt]
+        got = got.view(np.uint16).astype(np.uint32) if dtype == torch.int16 else got.view(np.uint32)
+        assert np.array_equal(got, ids)
