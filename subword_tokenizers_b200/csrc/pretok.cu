@@ -103,52 +103,112 @@ __device__ __forceinline__ uint32_t lower_cp(const PretokDev &t, uint32_t cp, co
     return cnt;
 }
 
-// One warp step: the 4 bytes of this lane at text[i .. i+4).  Returns (words << 16) | out_bytes of the lane; with kWrite
-// the lowered bytes go to arena + byte_pos and the word offsets to word_off + word_pos.
-template <bool kWrite>
-__device__ __forceinline__ uint32_t lane_step(const PretokDev &t, const uint8_t *text, uint64_t n, uint64_t i, uint32_t w_prev,
-                                              uint32_t w_cur, uint32_t w_next, uint8_t *arena, uint64_t byte_pos, uint32_t *word_off,
-                                              uint32_t word_pos, uint32_t *status) {
-    // window bytes B(k) = text[i + k], k in [-4, 8)
+// ---- one warp step = 128 text bytes; a lane owns text[i .. i+4) ------------------------------------------------------------
+// All per-byte decisions are taken with SWAR arithmetic on the lane's 32-bit word (flags live in bit 7 of each byte);
+// only characters outside ASCII (at most two can start in four bytes) go through a short loop, and the multi-byte
+// whitespace characters through a rare exact path that is entered only when one of their lead bytes is in sight.
+constexpr uint32_t kHi = 0x80808080u;
+__device__ __forceinline__ uint32_t swar_ge(uint32_t x7, uint32_t a) { return (x7 + (0x80u - a) * 0x01010101u) & kHi; }   // per byte: x7 >= a
+
+struct LaneStep {
+    uint32_t ns;        // flags: a non-whitespace character starts at this byte
+    uint32_t wstart;    // flags: ... and it starts a word
+    uint32_t lowered;   // the lane's bytes with ASCII upper case folded
+    uint32_t lw[2];     // lower-case table entries of the (up to two) non-ASCII characters, in order
+    uint32_t mine;      // (words << 16) | output bytes
+};
+
+__device__ __forceinline__ uint32_t decode_at(uint32_t c4) {          // c4: the character's bytes, first byte in bits 0-7
+    const uint32_t b0 = c4 & 0xFFu, b1 = (c4 >> 8) & 0x3Fu, b2 = (c4 >> 16) & 0x3Fu, b3 = (c4 >> 24) & 0x3Fu;
+    if (b0 < 0xE0u) return ((b0 & 0x1Fu) << 6) | b1;
+    if (b0 < 0xF0u) return ((b0 & 0x0Fu) << 12) | (b1 << 6) | b2;
+    return ((b0 & 0x07u) << 18) | (b1 << 12) | (b2 << 6) | b3;
+}
+
+// rare exact path: multi-byte whitespace in the window.  msp: flags of own bytes that START a multi-byte whitespace
+// character; psp: flags of own bytes whose PREVIOUS character is a multi-byte whitespace character.
+static __device__ __noinline__ void multibyte_spaces(uint32_t w_prev, uint32_t w_cur, uint32_t w_next, uint32_t &msp, uint32_t &psp) {
     const uint32_t w[3] = {w_prev, w_cur, w_next};
 #define B(k) ((w[((k) + 4) >> 2] >> (8 * (((k) + 4) & 3))) & 0xFFu)
-    uint32_t words = 0, bytes = 0;
-    uint8_t *dst = kWrite ? arena + byte_pos : nullptr;
+    msp = psp = 0;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-        const uint64_t q = i + p;
-        const uint32_t b0 = B(p);
-        if (q >= n || (b0 & 0xC0u) == 0x80u) continue;                       // no character starts here
-        const uint32_t b1 = B(p + 1), b2 = B(p + 2), b3 = B(p + 3);
-        bool space;
-        if (b0 < 0x80u) space = is_space_ascii(b0);
-        else space = is_space_2(b0, b1) || (b0 >= 0xE1u && b0 <= 0xE3u && is_space_3(b0, b1, b2));
-        if (space) continue;
-        // does a word start here?  yes iff the previous character is whitespace (or there is none)
-        const uint32_t x = B(p - 1), y = B(p - 2), z = B(p - 3);
-        bool prev_space = q == 0 || is_space_ascii(x);
-        if (!prev_space && x >= 0x80u) prev_space = is_space_2(y, x) || is_space_3(z, y, x);
-        // lower-case and measure / write
-        uint32_t out[3], n_out = 1;
-        if (b0 < 0x80u) out[0] = (b0 - 0x41u) < 26u ? b0 + 0x20u : b0;
-        else {
-            uint32_t cp;
-            if (b0 < 0xE0u) cp = ((b0 & 0x1Fu) << 6) | (b1 & 0x3Fu);
-            else if (b0 < 0xF0u) cp = ((b0 & 0x0Fu) << 12) | ((b1 & 0x3Fu) << 6) | (b2 & 0x3Fu);
-            else cp = ((b0 & 0x07u) << 18) | ((b1 & 0x3Fu) << 12) | ((b2 & 0x3Fu) << 6) | (b3 & 0x3Fu);
-            n_out = lower_cp(t, cp, text, n, q, out, status);
-        }
-        if (prev_space) {
-            if (kWrite) word_off[word_pos + words] = (uint32_t)(byte_pos + bytes);
-            ++words;
-        }
-        for (uint32_t k = 0; k < n_out; ++k) {
-            bytes += utf8_len_of(out[k]);
-            if (kWrite) dst = put_utf8(dst, out[k]);
-        }
+        const uint32_t b0 = B(p), b1 = B(p + 1), b2 = B(p + 2), x = B(p - 1), y = B(p - 2), z = B(p - 3);
+        if (is_space_2(b0, b1) || (b0 >= 0xE1u && b0 <= 0xE3u && is_space_3(b0, b1, b2))) msp |= 0x80u << (8 * p);
+        if (x >= 0x80u && (is_space_2(y, x) || is_space_3(z, y, x))) psp |= 0x80u << (8 * p);
     }
 #undef B
-    return (words << 16) | bytes;
+}
+
+__device__ __forceinline__ LaneStep analyze(const PretokDev &t, const uint8_t *text, uint64_t n, uint64_t i, uint32_t w_prev,
+                                            uint32_t w_cur, uint32_t w_next, uint32_t *status) {
+    LaneStep r;
+    const uint32_t n_valid = i >= n ? 0u : (n - i >= 4 ? 4u : (uint32_t)(n - i));
+    const uint32_t vm = n_valid >= 4 ? kHi : (((1u << (8 * n_valid)) - 1u) & kHi);
+    const uint32_t hi = w_cur & kHi, x7 = w_cur & 0x7F7F7F7Fu;
+    const uint32_t cont = hi & ~((w_cur << 1) & kHi);                                    // 10xxxxxx
+    const uint32_t start = ~cont & vm;
+    uint32_t space = ((swar_ge(x7, 0x09) & ~swar_ge(x7, 0x0E)) | (swar_ge(x7, 0x1C) & ~swar_ge(x7, 0x21))) & ~hi;
+    const uint32_t upper = swar_ge(x7, 0x41) & ~swar_ge(x7, 0x5B) & ~hi;
+    r.lowered = w_cur | (upper >> 2);
+    const uint32_t xb = w_prev >> 24;
+    uint32_t prev_space = (space << 8) | ((i == 0 || is_space_ascii(xb)) ? 0x80u : 0u);
+    // lead bytes of the multi-byte whitespace characters: C2, E1, E2, E3 (within three bytes before, or in, the lane's word)
+    const uint32_t p7 = w_prev & 0x7F7F7F7Fu;
+    const uint32_t lead_cur = hi & ((swar_ge(x7, 0x42) & ~swar_ge(x7, 0x43)) | (swar_ge(x7, 0x61) & ~swar_ge(x7, 0x64)));
+    const uint32_t lead_prev = (w_prev & 0x80808000u) & ((swar_ge(p7, 0x42) & ~swar_ge(p7, 0x43)) | (swar_ge(p7, 0x61) & ~swar_ge(p7, 0x64)));
+    if (lead_cur | lead_prev) {
+        uint32_t msp, psp;
+        multibyte_spaces(w_prev, w_cur, w_next, msp, psp);
+        space |= msp; prev_space |= psp;
+    }
+    r.ns = start & ~space;
+    r.wstart = r.ns & prev_space;
+    uint32_t bytes = __popc(r.ns & ~hi);
+    r.lw[0] = r.lw[1] = 0;
+    uint32_t nas = r.ns & hi;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (nas) {
+            const uint32_t bit = __ffs(nas) - 1; nas &= nas - 1;                          // bit = 8 p + 7
+            const uint32_t cp = decode_at(__funnelshift_r(w_cur, w_next, bit - 7));
+            const uint32_t lw = cp < t.n_lower ? __ldg(t.lower + cp) : cp;
+            r.lw[k] = lw;
+            if ((lw & (kLowerMulti | kLowerSigma)) == 0) bytes += utf8_len_of(lw);
+            else {
+                uint32_t out[3];
+                const uint32_t cnt = lower_cp(t, cp, text, n, i + ((bit - 7) >> 3), out, status);
+                for (uint32_t c = 0; c < cnt; ++c) bytes += utf8_len_of(out[c]);
+            }
+        }
+    }
+    r.mine = ((uint32_t)__popc(r.wstart) << 16) | bytes;
+    return r;
+}
+
+// writes the lane's lowered bytes at arena + byte_pos and its word offsets at word_off + word_pos
+__device__ __forceinline__ void emit(const PretokDev &t, const uint8_t *text, uint64_t n, uint64_t i, uint32_t w_cur, uint32_t w_next,
+                                     const LaneStep &r, uint8_t *arena, uint64_t byte_pos, uint32_t *word_off, uint32_t word_pos,
+                                     uint32_t *status) {
+    uint8_t *dst = arena + byte_pos;
+    uint32_t used = 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const uint32_t flag = 0x80u << (8 * p);
+        if (!(r.ns & flag)) continue;
+        if (r.wstart & flag) word_off[word_pos++] = (uint32_t)(dst - arena);
+        const uint32_t b = (r.lowered >> (8 * p)) & 0xFFu;
+        if (b < 0x80u) { *dst++ = (uint8_t)b; continue; }
+        if (used == 2) continue;                            // only reachable with malformed UTF-8: never write more than was counted
+        const uint32_t lw = used ? r.lw[1] : r.lw[0];
+        ++used;
+        if ((lw & (kLowerMulti | kLowerSigma)) == 0) dst = put_utf8(dst, lw);
+        else {
+            uint32_t out[3];
+            const uint32_t cnt = lower_cp(t, decode_at(__funnelshift_r(w_cur, w_next, 8 * p)), text, n, i + p, out, status);
+            for (uint32_t c = 0; c < cnt; ++c) dst = put_utf8(dst, out[c]);
+        }
+    }
 }
 
 template <bool kWrite>
@@ -167,25 +227,25 @@ __global__ void __launch_bounds__(256) pretok_kernel(PretokDev t, const uint8_t 
         }
         uint32_t tile_words = 0, tile_bytes = 0;
         const uint64_t t0 = (uint64_t)tile * kTileBytes;
-#pragma unroll 2
+        // the lane's words of consecutive steps are 32 words apart; w_prev / w_next come from the neighbour lanes
         for (uint32_t s = 0; s < kTileBytes / kStepBytes; ++s) {
-            const uint64_t i = t0 + (uint64_t)s * kStepBytes + lane * 4;
-            if (t0 + (uint64_t)s * kStepBytes >= n) break;                        // warp-uniform
-            const uint64_t wi = i >> 2;
+            const uint64_t step0 = t0 + (uint64_t)s * kStepBytes;
+            if (step0 >= n) break;                                                  // warp-uniform
+            const uint64_t i = step0 + lane * 4, wi = i >> 2;
             const uint32_t w_cur = wi < n_words32 ? __ldg(t32 + wi) : 0u;
-            const uint32_t w_prev = (wi >= 1 && wi - 1 < n_words32) ? __ldg(t32 + wi - 1) : 0u;
-            const uint32_t w_next = wi + 1 < n_words32 ? __ldg(t32 + wi + 1) : 0u;
-            uint32_t mine = lane_step<false>(t, text, n, i, w_prev, w_cur, w_next, nullptr, 0, nullptr, 0, status);
+            uint32_t w_prev = __shfl_up_sync(0xffffffffu, w_cur, 1), w_next = __shfl_down_sync(0xffffffffu, w_cur, 1);
+            if (lane == 0) w_prev = wi >= 1 ? __ldg(t32 + wi - 1) : 0u;
+            if (lane == 31) w_next = wi + 1 < n_words32 ? __ldg(t32 + wi + 1) : 0u;
+            const LaneStep r = analyze(t, text, n, i, w_prev, w_cur, w_next, status);
             if (kWrite) {
-                uint32_t incl = mine;
+                uint32_t incl = r.mine;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += v; }
-                const uint32_t excl = incl - mine, total = __shfl_sync(0xffffffffu, incl, 31);
-                if (mine) lane_step<true>(t, text, n, i, w_prev, w_cur, w_next, arena, byte_pos + (excl & 0xFFFFu), word_off,
-                                          word_pos + (excl >> 16), status);
+                const uint32_t excl = incl - r.mine, total = __shfl_sync(0xffffffffu, incl, 31);
+                if (r.ns) emit(t, text, n, i, w_cur, w_next, r, arena, byte_pos + (excl & 0xFFFFu), word_off, word_pos + (excl >> 16), status);
                 byte_pos += total & 0xFFFFu; word_pos += total >> 16;
             } else {
-                tile_words += mine >> 16; tile_bytes += mine & 0xFFFFu;
+                tile_words += r.mine >> 16; tile_bytes += r.mine & 0xFFFFu;
             }
         }
         if (!kWrite) {
@@ -197,8 +257,7 @@ __global__ void __launch_bounds__(256) pretok_kernel(PretokDev t, const uint8_t 
             if (lane == 0) ws.tile_sum[tile] = ((unsigned long long)tile_words << 32) | tile_bytes;
         }
     }
-    if (kWrite && blockIdx.x == 0 && threadIdx.x == 0)
-        word_off[n_words_total] = n_bytes_total;                                    // closing offset
+    if (kWrite && blockIdx.x == 0 && threadIdx.x == 0) word_off[n_words_total] = n_bytes_total;      // closing offset
 }
 
 // in-group exclusive prefixes of the packed (words << 32 | bytes) tile sums + the group totals
