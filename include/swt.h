@@ -134,7 +134,7 @@ int swt_wp_encode(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *
  *   rule of CPython (needs the Cased / Case_Ignorable bitmaps, 0x110000/8 bytes each, bit cp&7 of byte cp>>3;
  *   both NULL = the caller guarantees the text holds no U+03A3, else the call reports SWT_ERR_ARG).
  *   Whitespace is Python's str.isspace() set (29 code points, fixed in the kernel).
- * The text must be valid UTF-8 (lone surrogates in their 3-byte form are passed through), 4-byte aligned, in a
+ * The text must be valid UTF-8 (lone surrogates in their 3-byte form are passed through), 16-byte aligned, in a
  * buffer readable up to the next multiple of 4 bytes, and < 4 GiB per call.
  * Two calls: swt_pretok_count fills d_status (8 x u32: [0] status, [1] n_words, [2]/[3] arena bytes lo/hi) so the
  * caller can size the outputs; swt_pretok_write (same text, same workspace, untouched in between) writes them.

@@ -13,9 +13,9 @@
 //     one-to-many mapping (U+0130) and the context rule for U+03A3 (final sigma; CPython's handle_capital_sigma,
 //     Objects/unicodeobject.c) with the Cased / Case_Ignorable bitmaps derived from the same interpreter.
 //
-// Layout: one thread owns 4 consecutive text bytes and sees a 12-byte window (4 before, 4 after), so every decision
-// (character start, whitespace, "previous character was whitespace", decode, lower) is local; a warp step covers
-// 128 bytes with fully coalesced loads, a warp tile is 4 KiB.  Two passes over the text (count, write) with a scan of
+// Layout: the text is analysed as 32-bit words, each with a 12-byte window (4 before, 4 after), so every decision
+// (character start, whitespace, "previous character was whitespace", decode, lower) is local.  4 KiB per warp tile; the
+// count pass gives a lane 16 consecutive bytes per step (128-bit loads), the write pass 4 (contiguous byte stores).  Two passes over the text (count, write) with a scan of
 // the tile sums in between -- the same structure as the encode kernels, no inter-tile dependency.
 #include <algorithm>
 
@@ -31,7 +31,7 @@ struct swt_pretok {
 namespace swt {
 namespace {
 
-constexpr uint32_t kTileBytes = 4096, kStepBytes = 128, kGroupTiles = 1024;
+constexpr uint32_t kTileBytes = 4096, kGroupTiles = 1024;
 constexpr uint32_t kLowerMulti = 0x80000000u, kLowerSigma = 0x40000000u;
 enum { kPtCode = 0, kPtWords = 1, kPtBytesLo = 2, kPtBytesHi = 3 };
 
@@ -103,7 +103,7 @@ __device__ __forceinline__ uint32_t lower_cp(const PretokDev &t, uint32_t cp, co
     return cnt;
 }
 
-// ---- one warp step = 128 text bytes; a lane owns text[i .. i+4) ------------------------------------------------------------
+// ---- analysis of one 32-bit word of text, text[i .. i+4) ------------------------------------------------------------
 // All per-byte decisions are taken with SWAR arithmetic on the lane's 32-bit word (flags live in bit 7 of each byte);
 // only characters outside ASCII (at most two can start in four bytes) go through a short loop, and the multi-byte
 // whitespace characters through a rare exact path that is entered only when one of their lead bytes is in sight.
@@ -220,41 +220,68 @@ __global__ void __launch_bounds__(256) pretok_kernel(PretokDev t, const uint8_t 
     const uint32_t *t32 = reinterpret_cast<const uint32_t *>(text);
     const uint64_t n_words32 = (n + 3) >> 2;
     for (uint32_t tile = warp_global; tile < ws.n_tiles; tile += n_warps) {
-        uint64_t byte_pos = 0; uint32_t word_pos = 0;
-        if (kWrite) {
-            const unsigned long long base = ws.group_base[tile / kGroupTiles] + ws.tile_sum[tile];
-            byte_pos = base & 0xFFFFFFFFull; word_pos = (uint32_t)(base >> 32);
-        }
-        uint32_t tile_words = 0, tile_bytes = 0;
         const uint64_t t0 = (uint64_t)tile * kTileBytes;
-        // the lane's words of consecutive steps are 32 words apart; w_prev / w_next come from the neighbour lanes
-        for (uint32_t s = 0; s < kTileBytes / kStepBytes; ++s) {
-            const uint64_t step0 = t0 + (uint64_t)s * kStepBytes;
-            if (step0 >= n) break;                                                  // warp-uniform
-            const uint64_t i = step0 + lane * 4, wi = i >> 2;
-            const uint32_t w_cur = wi < n_words32 ? __ldg(t32 + wi) : 0u;
-            uint32_t w_prev = __shfl_up_sync(0xffffffffu, w_cur, 1), w_next = __shfl_down_sync(0xffffffffu, w_cur, 1);
-            if (lane == 0) w_prev = wi >= 1 ? __ldg(t32 + wi - 1) : 0u;
-            if (lane == 31) w_next = wi + 1 < n_words32 ? __ldg(t32 + wi + 1) : 0u;
-            const LaneStep r = analyze(t, text, n, i, w_prev, w_cur, w_next, status);
-            if (kWrite) {
-                uint32_t incl = r.mine;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += v; }
-                const uint32_t excl = incl - r.mine, total = __shfl_sync(0xffffffffu, incl, 31);
-                if (r.ns) emit(t, text, n, i, w_cur, w_next, r, arena, byte_pos + (excl & 0xFFFFu), word_off, word_pos + (excl >> 16), status);
-                byte_pos += total & 0xFFFFu; word_pos += total >> 16;
-            } else {
-                tile_words += r.mine >> 16; tile_bytes += r.mine & 0xFFFFu;
+        if constexpr (!kWrite) {
+            // count pass: a lane owns 16 consecutive bytes per step (one 128-bit load, 512 bytes per warp step); the words
+            // before and after them come from the neighbour lanes
+            uint32_t tile_words = 0, tile_bytes = 0;
+            for (uint32_t s = 0; s < kTileBytes / 512; ++s) {
+                const uint64_t step0 = t0 + (uint64_t)s * 512;
+                if (step0 >= n) break;                                              // warp-uniform
+                const uint64_t i = step0 + lane * 16, wi = i >> 2;
+                uint4 q;
+                if (wi + 4 <= n_words32) q = __ldg(reinterpret_cast<const uint4 *>(t32 + wi));
+                else {
+                    q.x = wi < n_words32 ? __ldg(t32 + wi) : 0u; q.y = wi + 1 < n_words32 ? __ldg(t32 + wi + 1) : 0u;
+                    q.z = wi + 2 < n_words32 ? __ldg(t32 + wi + 2) : 0u; q.w = 0u;
+                }
+                uint32_t w_prev = __shfl_up_sync(0xffffffffu, q.w, 1), w_next = __shfl_down_sync(0xffffffffu, q.x, 1);
+                if (lane == 0) w_prev = wi >= 1 ? __ldg(t32 + wi - 1) : 0u;
+                if (lane == 31) w_next = wi + 4 < n_words32 ? __ldg(t32 + wi + 4) : 0u;
+                const uint32_t mine = analyze(t, text, n, i, w_prev, q.x, q.y, status).mine + analyze(t, text, n, i + 4, q.x, q.y, q.z, status).mine +
+                                      analyze(t, text, n, i + 8, q.y, q.z, q.w, status).mine + analyze(t, text, n, i + 12, q.z, q.w, w_next, status).mine;
+                tile_words += mine >> 16; tile_bytes += mine & 0xFFFFu;
             }
-        }
-        if (!kWrite) {
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) {
                 tile_words += __shfl_xor_sync(0xffffffffu, tile_words, d);
                 tile_bytes += __shfl_xor_sync(0xffffffffu, tile_bytes, d);
             }
             if (lane == 0) ws.tile_sum[tile] = ((unsigned long long)tile_words << 32) | tile_bytes;
+        } else {
+            // write pass: a lane owns 4 consecutive bytes per step (128 bytes per warp step), so that the byte stores of a
+            // warp land in one contiguous run; the loads of four steps are issued together
+            const unsigned long long base = ws.group_base[tile / kGroupTiles] + ws.tile_sum[tile];
+            uint64_t byte_pos = base & 0xFFFFFFFFull; uint32_t word_pos = (uint32_t)(base >> 32);
+            for (uint32_t s4 = 0; s4 < kTileBytes / 512; ++s4) {
+                const uint64_t blk0 = t0 + (uint64_t)s4 * 512;
+                if (blk0 >= n) break;                                               // warp-uniform
+                uint32_t wq[6];                                                     // words lane-1 .. of the four steps: wq[k+1] = step k
+                const uint64_t wi0 = (blk0 >> 2) + lane;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) wq[k + 1] = wi0 + 32 * k < n_words32 ? __ldg(t32 + wi0 + 32 * k) : 0u;
+                wq[0] = (lane == 0 && wi0 >= 1) ? __ldg(t32 + wi0 - 1) : 0u;
+                wq[5] = (lane == 31 && wi0 + 97 < n_words32) ? __ldg(t32 + wi0 + 97) : 0u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t step0 = blk0 + 128 * k;
+                    if (step0 >= n) break;                                          // warp-uniform
+                    const uint64_t i = step0 + lane * 4;
+                    const uint32_t w_cur = wq[k + 1];
+                    uint32_t w_prev = __shfl_up_sync(0xffffffffu, w_cur, 1), w_next = __shfl_down_sync(0xffffffffu, w_cur, 1);
+                    // lane 0's previous word is lane 31's word of the previous step; lane 31's next word is lane 0's of the next
+                    const uint32_t from31 = __shfl_sync(0xffffffffu, wq[k], 31), from0 = __shfl_sync(0xffffffffu, wq[k + 2 > 5 ? 5 : k + 2], 0);
+                    if (lane == 0) w_prev = k == 0 ? wq[0] : from31;
+                    if (lane == 31) w_next = k == 3 ? wq[5] : from0;
+                    const LaneStep r = analyze(t, text, n, i, w_prev, w_cur, w_next, status);
+                    uint32_t incl = r.mine;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += v; }
+                    const uint32_t excl = incl - r.mine, total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (r.ns) emit(t, text, n, i, w_cur, w_next, r, arena, byte_pos + (excl & 0xFFFFu), word_off, word_pos + (excl >> 16), status);
+                    byte_pos += total & 0xFFFFu; word_pos += total >> 16;
+                }
+            }
         }
     }
     if (kWrite && blockIdx.x == 0 && threadIdx.x == 0) word_off[n_words_total] = n_bytes_total;      // closing offset
@@ -343,7 +370,7 @@ SWT_API int swt_pretok_count(const swt_pretok *p, const uint8_t *d_text, uint64_
                              uint32_t *d_status, void *stream) {
     SWT_REQUIRE(p && d_status && d_workspace, "NULL argument");
     SWT_REQUIRE(n_bytes == 0 || d_text, "d_text is NULL");
-    SWT_REQUIRE(((uintptr_t)d_text & 3) == 0, "d_text must be 4-byte aligned");
+    SWT_REQUIRE(((uintptr_t)d_text & 15) == 0, "d_text must be 16-byte aligned");
     SWT_REQUIRE(n_bytes < 0xFFFFFF00ull, "text must be < 4 GiB per call");
     cudaStream_t st = (cudaStream_t)stream;
     PretokWs ws;
@@ -362,7 +389,7 @@ SWT_API int swt_pretok_write(const swt_pretok *p, const uint8_t *d_text, uint64_
                              uint32_t n_words, uint64_t n_out_bytes, uint32_t *d_status, void *stream) {
     SWT_REQUIRE(p && d_status && d_workspace && d_word_off_out, "NULL argument");
     SWT_REQUIRE(n_out_bytes == 0 || d_arena_out, "d_arena_out is NULL");
-    SWT_REQUIRE(((uintptr_t)d_text & 3) == 0, "d_text must be 4-byte aligned");
+    SWT_REQUIRE(((uintptr_t)d_text & 15) == 0, "d_text must be 16-byte aligned");
     SWT_REQUIRE(arena_cap >= n_out_bytes && word_cap >= (uint64_t)n_words + 1, "output capacity below the counts of swt_pretok_count");
     cudaStream_t st = (cudaStream_t)stream;
     PretokWs ws;
