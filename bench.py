@@ -50,8 +50,8 @@ def load_golden(name):
 ZIPF_C = 200_000
 # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of ONE FastWP encode call over the 1 GB bench stream
 # (ncu --set full, see profiles/r01_final_ncu_wp_1GB.txt); None until measured
-TRAFFIC_1GB_WP = 5_916_539_000
-TRAFFIC_SOURCE = "profiles/r01_final_ncu_wp_1GB.txt"
+TRAFFIC_1GB_WP = 6_032_663_000
+TRAFFIC_SOURCE = "profiles/r01_final2_ncu_wp_1GB.txt"
 DRAW_CHUNK = 1 << 24
 
 
@@ -413,7 +413,7 @@ def main():
     # ---- CPU baseline: oracle port on the host cores, bounded sample (N=1 only)
     if args.gpus == 1:
         threads = os.cpu_count() or 1
-        sample_words = min(n_words, 2_000_000 * max(1, threads // 2))
+        sample_words = min(n_words, 4_000_000 * max(1, threads))
         mbps, sec, nb, _ = cpu_oracle_wp(ZipfStream(args.seed), vocab, sample_words, threads)
         line["cpu_baseline"] = {"value": mbps, "unit": "MB/s", "cores": threads, "kind": "port",
                                 "sample": "first %d words (%.1f MB) of the stream, %.2f s" % (sample_words, nb / 1e6, sec)}
