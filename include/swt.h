@@ -138,10 +138,15 @@ int swt_wp_encode(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *
  * buffer readable up to the next multiple of 4 bytes, and < 4 GiB per call.
  * Two calls: swt_pretok_count fills d_status (8 x u32: [0] status, [1] n_words, [2]/[3] arena bytes lo/hi) so the
  * caller can size the outputs; swt_pretok_write (same text, same workspace, untouched in between) writes them.
+ * mode SWT_PRETOK_BERT  replaces  pre_tokenize_str(example.lower())  of SubwordTokenizer.preprocessing (utils.py:26-29,
+ * the Rust BertPreTokenizer): whitespace is Rust's char::is_whitespace (no U+001C-001F), and every punctuation
+ * character (is_bert_punc: ASCII punctuation, or bit 29 = 0x20000000 of its lower_map entry) is a word of its own.
  */
+#define SWT_PRETOK_PYTHON_SPLIT 0
+#define SWT_PRETOK_BERT 1
 typedef struct swt_pretok swt_pretok;
 int swt_pretok_create(const uint32_t *lower_map, uint32_t n_lower, const uint32_t *multi, uint32_t n_multi,
-                      const uint8_t *cased_bitmap, const uint8_t *ignorable_bitmap, int device, swt_pretok **out);
+                      const uint8_t *cased_bitmap, const uint8_t *ignorable_bitmap, int mode, int device, swt_pretok **out);
 void swt_pretok_destroy(swt_pretok *p);
 size_t swt_pretok_workspace_bytes(uint64_t n_text_bytes);
 int swt_pretok_count(const swt_pretok *p, const uint8_t *d_text, uint64_t n_bytes, void *d_workspace, size_t workspace_bytes,

@@ -18,6 +18,7 @@ c_vp = ctypes.c_void_p
 SWT_OK = 0
 SHORT_WORD_BYTES = 32
 TRAIN_BPE, TRAIN_WP = 0, 1
+PRETOK_PYTHON_SPLIT, PRETOK_BERT = 0, 1
 
 
 class SwtError(RuntimeError):
@@ -58,7 +59,7 @@ SIGNATURES = {
     "swt_wp_trie_stats": (ctypes.c_int, [c_vp, c_u64p, c_u64p, c_u64p, c_u64p]),
     "swt_wp_encode": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint64, c_vp, ctypes.c_uint64, c_vp,
                                      c_vp, ctypes.c_size_t, c_vp, c_vp]),
-    "swt_pretok_create": (ctypes.c_int, [c_u32p, ctypes.c_uint32, c_u32p, ctypes.c_uint32, c_u8p, c_u8p, ctypes.c_int,
+    "swt_pretok_create": (ctypes.c_int, [c_u32p, ctypes.c_uint32, c_u32p, ctypes.c_uint32, c_u8p, c_u8p, ctypes.c_int, ctypes.c_int,
                                          ctypes.POINTER(c_vp)]),
     "swt_pretok_destroy": (None, [c_vp]),
     "swt_pretok_workspace_bytes": (ctypes.c_size_t, [ctypes.c_uint64]),

@@ -183,10 +183,23 @@ class FastBPE(NaiveBPE):
     def tokenize(self, text: str) -> List[str]:
         if not isinstance(text, str):
             raise TypeError("Text must be a string.")
-        words = self._pre_tokenized_words([text])
         enc = self._device_encoder()
-        ids, _, _ = enc.encode_words(words)
+        if self._device_pretok_ok():
+            ids = enc.encode_text(text)             # lower-casing + BERT pre-tokenization + merge loop, all on the device
+        else:
+            ids, _, _ = enc.encode_words(self._pre_tokenized_words([text]))
         return enc.tables.tokens_to_strs(ids)
+
+    def _device_pretok_ok(self) -> bool:
+        """The device pre-tokenizer reproduces the Rust BertPreTokenizer (the only one the reference ever uses, cli.py:163);
+        any other pre-tokenizer object, or a `tokenizers` build whose character classes differ from the shipped table, keeps
+        the host call of utils.py:27."""
+        ok = getattr(self, "_pretok_checked", None)
+        if ok is None:
+            pre = self.tokenizer.backend_tokenizer.pre_tokenizer
+            ok = type(pre).__name__ == "BertPreTokenizer" and P.bert_pretokenizer_matches(pre)
+            self._pretok_checked = ok
+        return ok
 
     def tokenize_batch(self, texts: Sequence[str]) -> List[List[str]]:
         """All texts in one launch; returns one token list per text."""

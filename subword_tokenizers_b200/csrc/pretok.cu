@@ -22,7 +22,7 @@
 #include "common.cuh"
 
 struct swt_pretok {
-    int device;
+    int device; int mode;                // SWT_PRETOK_PYTHON_SPLIT / SWT_PRETOK_BERT
     uint32_t *d_lower; uint32_t n_lower;
     uint32_t *d_multi; uint32_t n_multi;
     uint8_t *d_cased, *d_ignorable;      // 0x110000 / 8 bytes each, or nullptr (text must then not contain U+03A3)
@@ -32,7 +32,7 @@ namespace swt {
 namespace {
 
 constexpr uint32_t kTileBytes = 4096, kGroupTiles = 1024;
-constexpr uint32_t kLowerMulti = 0x80000000u, kLowerSigma = 0x40000000u;
+constexpr uint32_t kLowerMulti = 0x80000000u, kLowerSigma = 0x40000000u, kLowerPunct = 0x20000000u, kLowerCpMask = 0x1FFFFFu;
 enum { kPtCode = 0, kPtWords = 1, kPtBytesLo = 2, kPtBytesHi = 3 };
 
 struct PretokDev {
@@ -92,13 +92,13 @@ static __device__ __noinline__ bool final_sigma(const PretokDev &t, const uint8_
 __device__ __forceinline__ uint32_t lower_cp(const PretokDev &t, uint32_t cp, const uint8_t *text, uint64_t n, uint64_t q,
                                              uint32_t out[3], uint32_t *status) {
     uint32_t lw = cp < t.n_lower ? __ldg(t.lower + cp) : cp;
-    if ((lw & (kLowerMulti | kLowerSigma)) == 0) { out[0] = lw; return 1; }
+    if ((lw & (kLowerMulti | kLowerSigma)) == 0) { out[0] = lw & kLowerCpMask; return 1; }
     if (lw & kLowerSigma) {
         if (!t.cased) { atomicExch(&status[kPtCode], (uint32_t)SWT_ERR_ARG); out[0] = 0x3C3u; return 1; }
         out[0] = final_sigma(t, text, n, q) ? 0x3C2u : 0x3C3u;
         return 1;
     }
-    const uint32_t idx = lw & 0xFFFFFFu, cnt = min(__ldg(t.multi + idx), 3u);
+    const uint32_t idx = lw & 0xFFFFFu, cnt = min(__ldg(t.multi + idx), 3u);
     for (uint32_t k = 0; k < cnt; ++k) out[k] = __ldg(t.multi + idx + 1 + k);
     return cnt;
 }
@@ -140,6 +140,18 @@ static __device__ __noinline__ void multibyte_spaces(uint32_t w_prev, uint32_t w
 #undef B
 }
 
+// BERT mode: is the character that ENDS just before byte p of the window (a non-ASCII one) punctuation?  window as in B(k)
+static __device__ __noinline__ bool prev_char_is_punct(const PretokDev &t, uint32_t w_prev, uint32_t w_cur, int p) {
+    const unsigned long long v = ((unsigned long long)w_cur << 32) | w_prev;            // byte k of the window at bits 8 (k + 4)
+    int k = p - 1;                                                                       // last byte of the previous character
+    while (k > -4 && (((uint32_t)(v >> (8 * (k + 4))) & 0xC0u) == 0x80u)) --k;
+    const uint32_t c4 = (uint32_t)(v >> (8 * (k + 4)));
+    if ((c4 & 0xFFu) < 0x80u || (c4 & 0xC0u) == 0x80u) return false;
+    const uint32_t cp = decode_at(c4);
+    return cp < t.n_lower && (__ldg(t.lower + cp) & kLowerPunct) != 0;
+}
+
+template <bool kBert>
 __device__ __forceinline__ LaneStep analyze(const PretokDev &t, const uint8_t *text, uint64_t n, uint64_t i, uint32_t w_prev,
                                             uint32_t w_cur, uint32_t w_next, uint32_t *status) {
     LaneStep r;
@@ -148,11 +160,21 @@ __device__ __forceinline__ LaneStep analyze(const PretokDev &t, const uint8_t *t
     const uint32_t hi = w_cur & kHi, x7 = w_cur & 0x7F7F7F7Fu;
     const uint32_t cont = hi & ~((w_cur << 1) & kHi);                                    // 10xxxxxx
     const uint32_t start = ~cont & vm;
-    uint32_t space = ((swar_ge(x7, 0x09) & ~swar_ge(x7, 0x0E)) | (swar_ge(x7, 0x1C) & ~swar_ge(x7, 0x21))) & ~hi;
+    // ASCII whitespace: str.isspace() = 09-0D, 1C-20; Rust char::is_whitespace (BERT pre-tokenizer) = 09-0D, 20
+    uint32_t space = ((swar_ge(x7, 0x09) & ~swar_ge(x7, 0x0E)) | (swar_ge(x7, kBert ? 0x20 : 0x1C) & ~swar_ge(x7, 0x21))) & ~hi;
     const uint32_t upper = swar_ge(x7, 0x41) & ~swar_ge(x7, 0x5B) & ~hi;
     r.lowered = w_cur | (upper >> 2);
     const uint32_t xb = w_prev >> 24;
-    uint32_t prev_space = (space << 8) | ((i == 0 || is_space_ascii(xb)) ? 0x80u : 0u);
+    const bool xb_space = kBert ? (xb == 0x20u || (xb - 0x09u) < 5u) : is_space_ascii(xb);
+    uint32_t prev_space = (space << 8) | ((i == 0 || xb_space) ? 0x80u : 0u);
+    // BERT mode: punctuation characters are words of their own (is_bert_punc: ASCII punctuation, or the table bit)
+    uint32_t punct = 0, prev_punct = 0;
+    if (kBert) {
+        punct = ((swar_ge(x7, 0x21) & ~swar_ge(x7, 0x30)) | (swar_ge(x7, 0x3A) & ~swar_ge(x7, 0x41)) | (swar_ge(x7, 0x5B) & ~swar_ge(x7, 0x61)) |
+                 (swar_ge(x7, 0x7B) & ~swar_ge(x7, 0x7F))) & ~hi;
+        const bool xb_punct = (xb - 0x21u) < 15u || (xb - 0x3Au) < 7u || (xb - 0x5Bu) < 6u || (xb - 0x7Bu) < 4u;
+        prev_punct = (punct << 8) | (xb_punct ? 0x80u : 0u);
+    }
     // lead bytes of the multi-byte whitespace characters: C2, E1, E2, E3 (within three bytes before, or in, the lane's word)
     const uint32_t p7 = w_prev & 0x7F7F7F7Fu;
     const uint32_t lead_cur = hi & ((swar_ge(x7, 0x42) & ~swar_ge(x7, 0x43)) | (swar_ge(x7, 0x61) & ~swar_ge(x7, 0x64)));
@@ -163,7 +185,14 @@ __device__ __forceinline__ LaneStep analyze(const PretokDev &t, const uint8_t *t
         space |= msp; prev_space |= psp;
     }
     r.ns = start & ~space;
-    r.wstart = r.ns & prev_space;
+    if (kBert) {
+        // character starts that follow a non-ASCII character: that character may be punctuation
+        uint32_t after_hi = r.ns & ((hi << 8) | (xb >= 0x80u ? 0x80u : 0u));
+        while (after_hi) {
+            const uint32_t bit = __ffs(after_hi) - 1; after_hi &= after_hi - 1;
+            if (prev_char_is_punct(t, w_prev, w_cur, (int)((bit - 7) >> 3))) prev_punct |= 1u << bit;
+        }
+    }
     uint32_t bytes = __popc(r.ns & ~hi);
     r.lw[0] = r.lw[1] = 0;
     uint32_t nas = r.ns & hi;
@@ -174,7 +203,8 @@ __device__ __forceinline__ LaneStep analyze(const PretokDev &t, const uint8_t *t
             const uint32_t cp = decode_at(__funnelshift_r(w_cur, w_next, bit - 7));
             const uint32_t lw = cp < t.n_lower ? __ldg(t.lower + cp) : cp;
             r.lw[k] = lw;
-            if ((lw & (kLowerMulti | kLowerSigma)) == 0) bytes += utf8_len_of(lw);
+            if (kBert && (lw & kLowerPunct)) punct |= 1u << bit;
+            if ((lw & (kLowerMulti | kLowerSigma)) == 0) bytes += utf8_len_of(lw & kLowerCpMask);
             else {
                 uint32_t out[3];
                 const uint32_t cnt = lower_cp(t, cp, text, n, i + ((bit - 7) >> 3), out, status);
@@ -182,6 +212,7 @@ __device__ __forceinline__ LaneStep analyze(const PretokDev &t, const uint8_t *t
             }
         }
     }
+    r.wstart = r.ns & (prev_space | prev_punct | punct);
     r.mine = ((uint32_t)__popc(r.wstart) << 16) | bytes;
     return r;
 }
@@ -202,7 +233,7 @@ __device__ __forceinline__ void emit(const PretokDev &t, const uint8_t *text, ui
         if (used == 2) continue;                            // only reachable with malformed UTF-8: never write more than was counted
         const uint32_t lw = used ? r.lw[1] : r.lw[0];
         ++used;
-        if ((lw & (kLowerMulti | kLowerSigma)) == 0) dst = put_utf8(dst, lw);
+        if ((lw & (kLowerMulti | kLowerSigma)) == 0) dst = put_utf8(dst, lw & kLowerCpMask);
         else {
             uint32_t out[3];
             const uint32_t cnt = lower_cp(t, decode_at(__funnelshift_r(w_cur, w_next, 8 * p)), text, n, i + p, out, status);
@@ -211,7 +242,7 @@ __device__ __forceinline__ void emit(const PretokDev &t, const uint8_t *text, ui
     }
 }
 
-template <bool kWrite>
+template <bool kWrite, bool kBert>
 __global__ void __launch_bounds__(256) pretok_kernel(PretokDev t, const uint8_t *__restrict__ text, uint64_t n, PretokWs ws,
                                                      uint8_t *__restrict__ arena, uint32_t *__restrict__ word_off, uint32_t n_words_total,
                                                      uint32_t n_bytes_total, uint32_t *status) {
@@ -238,8 +269,8 @@ __global__ void __launch_bounds__(256) pretok_kernel(PretokDev t, const uint8_t 
                 uint32_t w_prev = __shfl_up_sync(0xffffffffu, q.w, 1), w_next = __shfl_down_sync(0xffffffffu, q.x, 1);
                 if (lane == 0) w_prev = wi >= 1 ? __ldg(t32 + wi - 1) : 0u;
                 if (lane == 31) w_next = wi + 4 < n_words32 ? __ldg(t32 + wi + 4) : 0u;
-                const uint32_t mine = analyze(t, text, n, i, w_prev, q.x, q.y, status).mine + analyze(t, text, n, i + 4, q.x, q.y, q.z, status).mine +
-                                      analyze(t, text, n, i + 8, q.y, q.z, q.w, status).mine + analyze(t, text, n, i + 12, q.z, q.w, w_next, status).mine;
+                const uint32_t mine = analyze<kBert>(t, text, n, i, w_prev, q.x, q.y, status).mine + analyze<kBert>(t, text, n, i + 4, q.x, q.y, q.z, status).mine +
+                                      analyze<kBert>(t, text, n, i + 8, q.y, q.z, q.w, status).mine + analyze<kBert>(t, text, n, i + 12, q.z, q.w, w_next, status).mine;
                 tile_words += mine >> 16; tile_bytes += mine & 0xFFFFu;
             }
 #pragma unroll
@@ -273,7 +304,7 @@ __global__ void __launch_bounds__(256) pretok_kernel(PretokDev t, const uint8_t 
                     const uint32_t from31 = __shfl_sync(0xffffffffu, wq[k], 31), from0 = __shfl_sync(0xffffffffu, wq[k + 2 > 5 ? 5 : k + 2], 0);
                     if (lane == 0) w_prev = k == 0 ? wq[0] : from31;
                     if (lane == 31) w_next = k == 3 ? wq[5] : from0;
-                    const LaneStep r = analyze(t, text, n, i, w_prev, w_cur, w_next, status);
+                    const LaneStep r = analyze<kBert>(t, text, n, i, w_prev, w_cur, w_next, status);
                     uint32_t incl = r.mine;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += v; }
@@ -325,13 +356,14 @@ int pretok_grid(uint32_t n_tiles) { return (int)std::min<uint32_t>((n_tiles + 7)
 using namespace swt;
 
 SWT_API int swt_pretok_create(const uint32_t *lower_map, uint32_t n_lower, const uint32_t *multi, uint32_t n_multi,
-                              const uint8_t *cased_bitmap, const uint8_t *ignorable_bitmap, int device, swt_pretok **out) {
+                              const uint8_t *cased_bitmap, const uint8_t *ignorable_bitmap, int mode, int device, swt_pretok **out) {
+    SWT_REQUIRE(mode == SWT_PRETOK_PYTHON_SPLIT || mode == SWT_PRETOK_BERT, "unknown pre-tokenizer mode");
     SWT_REQUIRE(out != nullptr && lower_map != nullptr && n_lower > 0, "NULL argument");
     SWT_REQUIRE((cased_bitmap == nullptr) == (ignorable_bitmap == nullptr), "cased / ignorable bitmaps come together");
     SWT_REQUIRE(n_multi == 0 || multi != nullptr, "multi is NULL");
     SWT_CUDA_OK(cudaSetDevice(device));
     swt_pretok *p = new swt_pretok();
-    p->device = device; p->n_lower = n_lower; p->n_multi = n_multi;
+    p->device = device; p->mode = mode; p->n_lower = n_lower; p->n_multi = n_multi;
     p->d_lower = nullptr; p->d_multi = nullptr; p->d_cased = p->d_ignorable = nullptr;
     const size_t bm = 0x110000 / 8;
     cudaError_t e = cudaMalloc(&p->d_lower, (size_t)n_lower * 4);
@@ -377,7 +409,8 @@ SWT_API int swt_pretok_count(const swt_pretok *p, const uint8_t *d_text, uint64_
     if (pretok_layout(n_bytes, d_workspace, &ws) > workspace_bytes) { set_error("pretok workspace too small"); return SWT_ERR_CAPACITY; }
     SWT_CUDA_OK(cudaMemsetAsync(d_status, 0, 8 * sizeof(uint32_t), st));
     if (n_bytes == 0) return SWT_OK;
-    pretok_kernel<false><<<pretok_grid(ws.n_tiles), 256, 0, st>>>(dev_view(p), d_text, n_bytes, ws, nullptr, nullptr, 0, 0, d_status);
+    if (p->mode == SWT_PRETOK_BERT) pretok_kernel<false, true><<<pretok_grid(ws.n_tiles), 256, 0, st>>>(dev_view(p), d_text, n_bytes, ws, nullptr, nullptr, 0, 0, d_status);
+    else pretok_kernel<false, false><<<pretok_grid(ws.n_tiles), 256, 0, st>>>(dev_view(p), d_text, n_bytes, ws, nullptr, nullptr, 0, 0, d_status);
     pretok_scan_groups_kernel<<<ws.n_groups, 256, 0, st>>>(ws);
     pretok_scan_top_kernel<<<1, 1, 0, st>>>(ws, d_status);
     SWT_CUDA_OK(cudaGetLastError());
@@ -395,7 +428,10 @@ SWT_API int swt_pretok_write(const swt_pretok *p, const uint8_t *d_text, uint64_
     PretokWs ws;
     if (pretok_layout(n_bytes, d_workspace, &ws) > workspace_bytes) { set_error("pretok workspace too small"); return SWT_ERR_CAPACITY; }
     if (n_bytes == 0) { SWT_CUDA_OK(cudaMemsetAsync(d_word_off_out, 0, sizeof(uint32_t), st)); return SWT_OK; }
-    pretok_kernel<true><<<pretok_grid(ws.n_tiles), 256, 0, st>>>(dev_view(p), d_text, n_bytes, ws, d_arena_out, d_word_off_out, n_words, (uint32_t)n_out_bytes, d_status);
+    if (p->mode == SWT_PRETOK_BERT)
+        pretok_kernel<true, true><<<pretok_grid(ws.n_tiles), 256, 0, st>>>(dev_view(p), d_text, n_bytes, ws, d_arena_out, d_word_off_out, n_words, (uint32_t)n_out_bytes, d_status);
+    else
+        pretok_kernel<true, false><<<pretok_grid(ws.n_tiles), 256, 0, st>>>(dev_view(p), d_text, n_bytes, ws, d_arena_out, d_word_off_out, n_words, (uint32_t)n_out_bytes, d_status);
     SWT_CUDA_OK(cudaGetLastError());
     return SWT_OK;
 }

@@ -135,22 +135,24 @@ class _Encoder:
 
 
 class Pretokenizer:
-    """Device pre-tokenizer of FastWP: raw UTF-8 text -> lower-cased word arena + offsets (``text.lower().split()``;
-    reference wordpiece.py:248,266-269).  One instance per process and device; the sigma bitmaps are uploaded on
-    the first text that contains U+03A3."""
+    """Device pre-tokenizer: raw UTF-8 text -> lower-cased word arena + offsets.  PRETOK_PYTHON_SPLIT = ``text.lower().split()``
+    of FastWP.tokenize (reference wordpiece.py:248,266-269); PRETOK_BERT = ``pre_tokenize_str(text.lower())`` of the BPE classes
+    (utils.py:26-29, Rust BertPreTokenizer).  One instance per process, device and mode; the sigma bitmaps are uploaded on the
+    first text that contains U+03A3."""
 
     _instances = {}
 
     @classmethod
-    def get(cls, device: Optional[int] = None) -> "Pretokenizer":
+    def get(cls, device: Optional[int] = None, mode: int = _lib.PRETOK_PYTHON_SPLIT) -> "Pretokenizer":
         device = current_device() if device is None else device
-        if device not in cls._instances:
-            cls._instances[device] = cls(device)
-        return cls._instances[device]
+        if (device, mode) not in cls._instances:
+            cls._instances[(device, mode)] = cls(device, mode)
+        return cls._instances[(device, mode)]
 
-    def __init__(self, device: int):
+    def __init__(self, device: int, mode: int = _lib.PRETOK_PYTHON_SPLIT):
         _lib.require_cuda()
         self.device = device
+        self.mode = mode
         self.tables = P.PretokTables.get()
         self._handle = c_vp(None)
         self._with_sigma = False
@@ -162,12 +164,13 @@ class Pretokenizer:
             lib.swt_pretok_destroy(self._handle)
             self._handle = c_vp(None)
         t = self.tables
+        lower = t.bert_lower_map() if self.mode == _lib.PRETOK_BERT else t.lower_map
         cased = ign = None
         if with_sigma:
             cased, ign = t.sigma_bitmaps()
-        check(lib.swt_pretok_create(_np_ptr(t.lower_map, c_u32p), len(t.lower_map), _np_ptr(t.multi, c_u32p), len(t.multi),
+        check(lib.swt_pretok_create(_np_ptr(lower, c_u32p), len(lower), _np_ptr(t.multi, c_u32p), len(t.multi),
                                     _np_ptr(cased, c_u8p) if with_sigma else None, _np_ptr(ign, c_u8p) if with_sigma else None,
-                                    self.device, ctypes.byref(self._handle)), "swt_pretok_create")
+                                    self.mode, self.device, ctypes.byref(self._handle)), "swt_pretok_create")
         self._with_sigma = with_sigma
 
     def split_device(self, d_text: torch.Tensor, n_bytes: int, has_sigma: bool):
@@ -224,6 +227,22 @@ class BpeEncoder(_Encoder):
         if self._handle:
             _lib.load().swt_bpe_table_destroy(self._handle)
             self._handle = c_vp(None)
+
+
+def _bpe_encode_text(self, text: str, return_offsets: bool = False):
+    """FastBPE.tokenize on the device from the raw text: BERT pre-tokenization (Pretokenizer, PRETOK_BERT) + encode."""
+    d_arena, d_off, n_words = Pretokenizer.get(mode=_lib.PRETOK_BERT).split_text(text)
+    if n_words == 0:
+        return (np.zeros(0, np.uint32), np.zeros(1, np.uint32)) if return_offsets else np.zeros(0, np.uint32)
+    lens = (d_off[1:n_words + 1] - d_off[:n_words]).long()                    # bytes of the long words size the scratch
+    long_bytes = int(lens[lens > SHORT_WORD_BYTES].sum().item())
+    d_ids, d_tok_off, d_status = self.encode_device(d_arena, d_off, n_words, long_bytes, want_offsets=return_offsets)
+    n_tok, _ = self.check_status(d_status)
+    ids = d_ids[:n_tok].cpu().numpy().view(np.uint32)
+    return (ids, d_tok_off.cpu().numpy().view(np.uint32)) if return_offsets else ids
+
+
+BpeEncoder.encode_text = _bpe_encode_text
 
 
 class WpEncoder(_Encoder):

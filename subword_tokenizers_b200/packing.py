@@ -45,7 +45,42 @@ def unicode_class_bitmaps() -> Tuple[np.ndarray, np.ndarray]:
 # str.isspace() code points the device pre-tokenizer hard-codes (csrc/pretok.cu); checked against the interpreter
 PY_SPACE_CPS = frozenset([9, 10, 11, 12, 13, 28, 29, 30, 31, 32, 0x85, 0xA0, 0x1680, *range(0x2000, 0x200B), 0x2028, 0x2029,
                           0x202F, 0x205F, 0x3000])
-LOWER_MULTI, LOWER_SIGMA = 0x80000000, 0x40000000
+LOWER_MULTI, LOWER_SIGMA, LOWER_PUNCT = 0x80000000, 0x40000000, 0x20000000
+# whitespace of the Rust BertPreTokenizer (char::is_whitespace); the device kernel hard-codes it
+RUST_SPACE_CPS = frozenset(PY_SPACE_CPS - {28, 29, 30, 31})
+_bert_classes = None
+
+
+def load_bert_classes() -> dict:
+    """{'space': [[lo, hi], ...], 'punct': [[lo, hi], ...]} of the Rust BertPreTokenizer."""
+    global _bert_classes
+    if _bert_classes is None:
+        import json
+        import os
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "bert_pretok_classes.json")) as f:
+            _bert_classes = json.load(f)
+        spaces = {c for a, b in _bert_classes["space"] for c in range(a, b + 1)}
+        if spaces != set(RUST_SPACE_CPS):
+            raise RuntimeError("bert_pretok_classes.json: whitespace set differs from the one compiled into the device pre-tokenizer")
+    return _bert_classes
+
+
+def bert_pretokenizer_matches(pre) -> bool:
+    """Spot check of the shipped class table against a live pre-tokenizer object (every code point below U+3100 and both
+    ends of every range): False sends the caller to the host pre-tokenizer."""
+    cls = load_bert_classes()
+    kind = {}
+    for name, code in (("space", 2), ("punct", 3)):
+        for a, b in cls[name]:
+            for c in range(a, b + 1):
+                kind[c] = code
+    probe = set(range(0x3100)) | {c for name in ("space", "punct") for a, b in cls[name] for c in (a - 1, a, b, b + 1)}
+    for c in sorted(probe):
+        if c < 0 or 0xD800 <= c < 0xE000 or c >= UNICODE_LIMIT:
+            continue
+        if len(pre.pre_tokenize_str("a" + chr(c) + "b")) != kind.get(c, 1):
+            return False
+    return True
 
 
 class PretokTables:
@@ -86,9 +121,24 @@ class PretokTables:
                 if len(lo) > 3:
                     raise RuntimeError("lower() of U+%04X has more than 3 code points" % cp)
         lower[0x3A3] = LOWER_SIGMA
+        self._lower_full = lower
         self.lower_map = np.ascontiguousarray(lower[:max(last, 0x3A3) + 1])
         self.multi = np.asarray(multi, dtype=np.uint32)
         self._sigma = None
+        self._bert = None
+
+    def bert_lower_map(self) -> np.ndarray:
+        """lower_map with bit 29 (LOWER_PUNCT) on the characters the Rust BertPreTokenizer isolates (data/bert_pretok_classes.json,
+        probed from the `tokenizers` library by data/make_bert_classes.py)."""
+        if self._bert is None:
+            cls = load_bert_classes()
+            m = self._lower_full.copy()
+            top = len(self.lower_map)
+            for a, b in cls["punct"]:
+                m[a:b + 1] |= LOWER_PUNCT
+                top = max(top, b + 1)
+            self._bert = np.ascontiguousarray(m[:top])
+        return self._bert
 
     def sigma_bitmaps(self) -> Tuple[np.ndarray, np.ndarray]:
         """(cased, case_ignorable) bitmaps.  Cased = islower|isupper|istitle of the single character.  Case_Ignorable is

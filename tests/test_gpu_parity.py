@@ -538,3 +538,54 @@ def test_wp_tokenize_host_from_raw_text(P, dev):
         got = h_ids.numpy()[:nt]
         got = got.view(np.uint16).astype(np.uint32) if dtype == torch.int16 else got.view(np.uint32)
         assert np.array_equal(got, ids)
+
+
+# ---- device BERT pre-tokenization (BPE classes): must equal tokenizers' BertPreTokenizer on text.lower() ------------------
+def _device_bert_split(dev, P, text):
+    from subword_tokenizers_b200 import _lib
+    d_arena, d_off, n_words = dev.Pretokenizer.get(mode=_lib.PRETOK_BERT).split_text(text)
+    off = d_off.cpu().numpy().view(np.uint32)
+    arena = d_arena.cpu().numpy()[: int(off[-1])].tobytes()
+    return [P.decode_utf8(arena[int(off[i]):int(off[i + 1])]) for i in range(n_words)]
+
+
+def _bert_words(text):
+    from tokenizers import pre_tokenizers
+    return [w for w, _ in pre_tokenizers.BertPreTokenizer().pre_tokenize_str(text.lower())]
+
+
+def test_bert_pretok_matches_tokenizers_library(P, dev):
+    from tokenizers import pre_tokenizers
+    assert P.bert_pretokenizer_matches(pre_tokenizers.BertPreTokenizer())
+    lines = load_golden("pan_tadeusz.json.gz")
+    cases = ["\n".join(lines), "  ".join(lines[:50]).upper(), "", " ", "a", "!", "!!", "a!b", " a,b.c ", "«Zażółć» GĘŚLĄ – jaźń…", "x\x1cy\x1fz",
+             "İstanbul,İİ.Kelvin K;Ω ẞ ȺȾ", "ΟΔΥΣΣΕΥΣ, ΣΟΦΟΣ. Σ ΑΣ' ΑΣ'Α «Σ» ΑΣ:Α", "日本語。テスト、です！ 「x」", "¿qué? ¡sí!",
+             "é" * 4095 + "!" + "É" * 4097 + "…" + "x" * 5000 + "、" + "y"]
+    for text in cases:
+        assert _device_bert_split(dev, P, text) == _bert_words(text), repr(text[:40])
+
+
+def test_bert_pretok_every_code_point(P, dev):
+    cps = [c for c in range(0x110000) if not 0xD800 <= c < 0xE000]
+    text = "".join("a%sb%s " % (chr(c), chr(c)) for c in cps)
+    assert _device_bert_split(dev, P, text) == _bert_words(text)
+
+
+def test_bert_pretok_random_texts(P, dev):
+    alphabet = [chr(c) for c in (list(range(0x20, 0x7F)) + [9, 10, 13, 0x1C, 0x85, 0xA0, 0xA1, 0xAB, 0xBB, 0x130, 0x3A3, 0x3C3, 0x391, 0x27, 0x301, 0x37E,
+                                                          0x2003, 0x2013, 0x2014, 0x2026, 0x3000, 0x3001, 0x4E2D, 0x10400, 0x1F600, 0x141, 0x142, 0x17B,
+                                                          0x1DA87, 0xFF01, 0xFE50])]
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 3, 5, 127, 128, 129, 4096, 50_000):
+        for _ in range(4):
+            text = "".join(alphabet[i] for i in rng.integers(0, len(alphabet), n))
+            assert _device_bert_split(dev, P, text) == _bert_words(text), repr(text[:60])
+
+
+def test_fastbpe_tokenize_text_on_device_equals_word_path(P, dev):
+    tab = P.BpeTables([tuple(p) for p in load_golden("pretrained_bpe_merges.json.gz")])
+    benc = dev.BpeEncoder(tab)
+    text = "\n".join(load_golden("pan_tadeusz.json.gz")).upper() + " " + "x" * 100 + "-" + "ab" * 40
+    ids_w, tok_w, _ = benc.encode_words(_bert_words(text))
+    ids_t, tok_t = benc.encode_text(text, return_offsets=True)
+    assert np.array_equal(ids_w, ids_t) and np.array_equal(tok_w, tok_t)
