@@ -10,7 +10,7 @@ A "step" is one pass of the FastWP encode kernel over the whole stream.
 
   value      MB/s (10^6 input arena bytes per second) with the stream resident in HBM, CUDA-event timed,
              max over ranks, whole job.
-  e2e        same metric through the host-buffer C ABI from RAW TEXT (swt_wp_tokenize_host): pinned host text in,
+  e2e        same metric through the host-buffer C ABI from RAW TEXT (swt_tokenize_text_host): pinned host text in,
              lower-casing + whitespace split + encode on the device, flat 16-bit token ids out; H2D and D2H inside the
              timed region.  Sub-entries: the packed-words variants (swt_encode_host16 / swt_encode_host).
   roofline   algorithmic bytes (arena + 4 B/word offset read, 4 B/token + 4 B/word offset written) per launch
@@ -395,7 +395,7 @@ def main():
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms},
         "e2e": {"value": e2e_text_value, "unit": "MB/s", "h2d_bytes_per_step": n_text,
                 "d2h_bytes_per_step": 2 * n_tokens + 64 * ((n_text >> 26) + 1), "steps": e2e_steps,
-                "call": "swt_wp_tokenize_host",
+                "call": "swt_tokenize_text_host",
                 "what": "raw UTF-8 text (the stream's words joined by single spaces) in a pinned host buffer -> H2D -> lower-casing + "
                         "whitespace split on the device (swt_pretok_*) -> FastWP encode -> 16-bit flat token ids (the list "
                         "tokenize() returns) D2H into a pinned host buffer; MB = word bytes, as in `value`",

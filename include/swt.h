@@ -123,6 +123,22 @@ int swt_wp_encode(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *
                   uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off,
                   void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream);
 
+/* ---- the Naive encoders ---------------------------------------------- */
+/*
+ * swt_bpe_encode_naive  replaces  NaiveBPE.encode_word  (bpe.py:114-132): the merge list replayed in order.  Same
+ *   table, arguments and outputs as swt_bpe_encode.  Exact for merge lists in which no (left, right) pair is listed
+ *   twice (the table keeps one rank per pair); the Python class keeps the host replay for lists with repeats.
+ * swt_wp_encode_naive   replaces  NaiveWP.encode_word   (wordpiece.py:131-158): greedy longest prefix, "##" + rest,
+ *   whole word -> "[UNK]" (id n_vocab + 1) when a piece has no match.  Same trie, arguments and outputs as swt_wp_encode;
+ *   the input words are the BERT pre-tokenized words (wordpiece.py:176-178), not whitespace chunks.
+ */
+int swt_bpe_encode_naive(const swt_bpe_table *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
+                         uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off,
+                         void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream);
+int swt_wp_encode_naive(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
+                        uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off,
+                        void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream);
+
 /* ---- device-side pre-tokenization for FastWP -------------------------- */
 /*
  * swt_pretok_*  replaces  text.lower().split()  i.e. `s = text.lower() + " "` (wordpiece.py:248) and the
@@ -179,12 +195,14 @@ int swt_encode_host(swt_pipeline *p, int which, const void *table, const uint8_t
 int swt_encode_host16(swt_pipeline *p, int which, const void *table, const uint8_t *h_arena, const uint32_t *h_word_off,
                       uint64_t n_words, uint16_t *h_out_ids16, uint64_t out_cap, uint32_t *h_out_tok_off,
                       uint64_t *n_tokens, uint64_t *h6_events);
-/* FastWP.tokenize from RAW TEXT in a host buffer (wordpiece.py:233-270 end to end): per batch H2D of the text,
- * swt_pretok_count/_write, swt_wp_encode, D2H of the flat token ids (16-bit when ids_16bit != 0, see
- * swt_encode_host16).  Batches are cut after ASCII whitespace.  n_words_out / h6_events may be NULL. */
-int swt_wp_tokenize_host(swt_pipeline *p, const swt_pretok *pretok, const swt_wp_trie *trie, const uint8_t *h_text,
-                         uint64_t n_bytes, void *h_out_ids, int ids_16bit, uint64_t out_cap, uint64_t *n_tokens,
-                         uint64_t *n_words_out, uint64_t *h6_events);
+/* FastWP.tokenize / FastBPE.tokenize from RAW TEXT in a host buffer (wordpiece.py:233-270 / bpe.py:245-249 end to end):
+ * per batch H2D of the text, swt_pretok_count/_write, the encode call, D2H of the flat token ids (16-bit when
+ * ids_16bit != 0, see swt_encode_host16).  which / table as in swt_encode_host; pretok must have the matching mode
+ * (SWT_PRETOK_PYTHON_SPLIT for WP, SWT_PRETOK_BERT for BPE).  Batches are cut after ASCII whitespace.
+ * n_words_out / h6_events may be NULL. */
+int swt_tokenize_text_host(swt_pipeline *p, const swt_pretok *pretok, int which, const void *table, const uint8_t *h_text,
+                           uint64_t n_bytes, void *h_out_ids, int ids_16bit, uint64_t out_cap, uint64_t *n_tokens,
+                           uint64_t *n_words_out, uint64_t *h6_events);
 /* pinned host allocation helpers so integrators can give the pipeline DMA-able buffers */
 int swt_host_alloc(void **ptr, size_t bytes);
 void swt_host_free(void *ptr);

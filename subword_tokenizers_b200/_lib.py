@@ -53,6 +53,10 @@ SIGNATURES = {
     "swt_encode_workspace_bytes": (ctypes.c_size_t, [ctypes.c_uint32, ctypes.c_uint64]),
     "swt_bpe_encode": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint64, c_vp, ctypes.c_uint64, c_vp,
                                       c_vp, ctypes.c_size_t, c_vp, c_vp]),
+    "swt_bpe_encode_naive": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint64, c_vp, ctypes.c_uint64, c_vp,
+                                            c_vp, ctypes.c_size_t, c_vp, c_vp]),
+    "swt_wp_encode_naive": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint64, c_vp, ctypes.c_uint64, c_vp,
+                                           c_vp, ctypes.c_size_t, c_vp, c_vp]),
     "swt_wp_trie_create": (ctypes.c_int, [c_u32p, c_u64p, ctypes.c_uint32, c_u8p, c_u32p, ctypes.c_uint32, ctypes.c_int,
                                           ctypes.POINTER(c_vp)]),
     "swt_wp_trie_destroy": (None, [c_vp]),
@@ -72,8 +76,8 @@ SIGNATURES = {
                                        c_u64p, c_u64p]),
     "swt_encode_host16": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_uint64, c_vp, ctypes.c_uint64, c_vp,
                                          c_u64p, c_u64p]),
-    "swt_wp_tokenize_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_uint64, c_vp, ctypes.c_int, ctypes.c_uint64, c_u64p,
-                                            c_u64p, c_u64p]),
+    "swt_tokenize_text_host": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_uint64, c_vp, ctypes.c_int, ctypes.c_uint64,
+                                              c_u64p, c_u64p, c_u64p]),
     "swt_host_alloc": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_size_t]),
     "swt_host_free": (None, [c_vp]),
     "swt_bpe_train_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(TrainConfig)]),

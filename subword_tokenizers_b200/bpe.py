@@ -108,9 +108,36 @@ class NaiveBPE(SubwordTokenizer):
             pieces = self._replace_pair(pair, pieces)
         return pieces[:1] + ["##" + p for p in pieces[1:]]
 
+    def _naive_device_encoder(self):
+        """In-order replay on the device (swt_bpe_encode_naive), or None when the merge list repeats a pair (the device table
+        keeps one rank per pair; the host replay below stays exact for such lists)."""
+        from .device import BpeEncoder
+        quick = (id(self.merges_list), len(self.merges_list))
+        if getattr(self, "_naive_quick", None) != quick:
+            pairs = [tuple(p) for p in self.merges_list]
+            self._naive_encoder = BpeEncoder(P.BpeTables(pairs), naive=True) if len(set(pairs)) == len(pairs) else None
+            self._naive_quick = quick
+        return self._naive_encoder
+
+    def encode_words(self, words: Sequence[str]) -> List[List[str]]:
+        """Batch form of encode_word: one kernel launch for all words (host replay when the merge list repeats a pair)."""
+        enc = self._naive_device_encoder()
+        if enc is None:
+            return [self.encode_word(w) for w in words]
+        ids, tok_off, _ = enc.encode_words(words)
+        strs = enc.tables.tokens_to_strs(ids)
+        return [strs[int(tok_off[i]):int(tok_off[i + 1])] for i in range(len(words))]
+
     def tokenize(self, text: str) -> List[str]:
         if not isinstance(text, str):
             raise TypeError("Text to tokenize must be a string.")
+        enc = self._naive_device_encoder()
+        if enc is not None:
+            if self._device_pretok_ok():
+                ids = enc.encode_text(text)
+            else:
+                ids, _, _ = enc.encode_words(self._pre_tokenized_words([text]))
+            return enc.tables.tokens_to_strs(ids)
         out: List[str] = []
         for word in self._pre_tokenized_words([text]):
             out.extend(self.encode_word(word))
@@ -143,6 +170,7 @@ class FastBPE(NaiveBPE):
         self._bpe_ranks: Dict[Tuple[str, str], int] = {}
         self._encoder = None
         self._encoder_key = None
+        self._encoder_quick = None
 
     def _rebuild_ranks(self) -> None:
         self._bpe_ranks = {pair: i for i, pair in enumerate(self.merges_list)}
@@ -160,11 +188,15 @@ class FastBPE(NaiveBPE):
         """The rank table on the device, rebuilt when merges_list / _bpe_ranks changed."""
         from .device import BpeEncoder
         # honour direct assignment to _bpe_ranks (the reference reads only that dict in encode_word)
+        quick = (id(self._bpe_ranks), len(self._bpe_ranks))           # O(1) on the per-call path
+        if self._encoder is not None and self._encoder_quick == quick:
+            return self._encoder
         ranked = sorted(self._bpe_ranks.items(), key=lambda kv: kv[1])
         key = (len(ranked), hash(tuple(p for p, _ in ranked[:64])), hash(tuple(p for p, _ in ranked[-64:])))
         if self._encoder is None or self._encoder_key != key:
             self._encoder = BpeEncoder(P.BpeTables([p for p, _ in ranked]))
             self._encoder_key = key
+        self._encoder_quick = quick
         return self._encoder
 
     def _pairs(self, seq: List[str]) -> set:
@@ -189,17 +221,6 @@ class FastBPE(NaiveBPE):
         else:
             ids, _, _ = enc.encode_words(self._pre_tokenized_words([text]))
         return enc.tables.tokens_to_strs(ids)
-
-    def _device_pretok_ok(self) -> bool:
-        """The device pre-tokenizer reproduces the Rust BertPreTokenizer (the only one the reference ever uses, cli.py:163);
-        any other pre-tokenizer object, or a `tokenizers` build whose character classes differ from the shipped table, keeps
-        the host call of utils.py:27."""
-        ok = getattr(self, "_pretok_checked", None)
-        if ok is None:
-            pre = self.tokenizer.backend_tokenizer.pre_tokenizer
-            ok = type(pre).__name__ == "BertPreTokenizer" and P.bert_pretokenizer_matches(pre)
-            self._pretok_checked = ok
-        return ok
 
     def tokenize_batch(self, texts: Sequence[str]) -> List[List[str]]:
         """All texts in one launch; returns one token list per text."""

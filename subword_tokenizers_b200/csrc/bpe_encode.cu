@@ -61,23 +61,28 @@ __device__ __forceinline__ uint32_t bpe_probe(const BpeTableDev &t, uint32_t a, 
 }
 
 // ---- short words: one thread, symbols in a thread-local buffer ----------------------------------------------------
+// kNaive = NaiveBPE.encode_word (bpe.py:114-132): the merges are replayed in list order, i.e. the next merge applied is the
+// lowest-ranked pair present whose rank is ABOVE the last one applied (a pair that only appears after its turn is skipped).
+template <bool kNaive>
 __device__ __forceinline__ uint32_t bpe_encode_short(const BpeTableDev &t, const uint8_t *p, uint32_t nbytes, uint32_t *s) {
     uint32_t n = 0;
     for (uint32_t i = 0; i < nbytes;) {
         uint32_t adv; uint32_t cp = utf8_decode(p + i, nbytes - i, adv); i += adv;
         s[n++] = bpe_char_symbol(t, cp);
     }
-    if (n == 0) { s[0] = SWT_BPE_EMPTY_TOKEN; return 1; }         // bpe.py:207-208
+    if (n == 0) { if (kNaive) return 0; s[0] = SWT_BPE_EMPTY_TOKEN; return 1; }   // FastBPE: [""] (bpe.py:207-208); NaiveBPE: [] (:131-132)
+    uint32_t last = kEmptyRank;                                     // kNaive: rank of the merge applied last
     while (n >= 2) {
         uint32_t best = kEmptyRank, ba = 0, bb = 0, bz = 0;
         uint32_t prev = s[0];
         for (uint32_t i = 0; i + 1 < n; ++i) {                      // min rank over the adjacent pairs (bpe.py:212-217)
             uint32_t cur = s[i + 1], z;
             uint32_t r = bpe_probe(t, prev, cur, z);
-            if (r < best) { best = r; ba = prev; bb = cur; bz = z; }
+            if (r < best && (!kNaive || last == kEmptyRank || r > last)) { best = r; ba = prev; bb = cur; bz = z; }
             prev = cur;
         }
         if (best == kEmptyRank) break;
+        last = best;
         uint32_t r = 0, o = 0;                                      // greedy left-to-right replacement (bpe.py:221-235)
         while (r < n) {
             uint32_t v = s[r];
@@ -94,6 +99,7 @@ __device__ __forceinline__ uint32_t bpe_encode_short(const BpeTableDev &t, const
 // ---- long words: one WARP works on the word in global scratch ----------------------------------------------------------
 // bufA/bufB are ping-pong symbol buffers of at least nbytes entries.  Returns the final symbol count; *result points
 // at the buffer holding the final symbols (already in token form).  All 32 lanes must call this.
+template <bool kNaive>
 __device__ __noinline__ uint32_t bpe_encode_long_warp(const BpeTableDev &t, const uint8_t *p, uint32_t nbytes, uint32_t *bufA,
                                                       uint32_t *bufB, uint32_t **result) {
     const uint32_t lane = threadIdx.x & 31;
@@ -115,13 +121,18 @@ __device__ __noinline__ uint32_t bpe_encode_long_warp(const BpeTableDev &t, cons
     }
     __syncwarp();
     uint32_t *src = bufA, *dst = bufB;
+    uint32_t last = kEmptyRank;
     while (n >= 2) {
         // 2. min rank over all adjacent pairs (bpe.py:212-217)
         uint32_t best = kEmptyRank;
-        for (uint32_t i = lane; i + 1 < n; i += 32) { uint32_t z; const uint32_t r = bpe_probe(t, src[i], src[i + 1], z); best = min(best, r); }
+        for (uint32_t i = lane; i + 1 < n; i += 32) {
+            uint32_t z; const uint32_t r = bpe_probe(t, src[i], src[i + 1], z);
+            if (!kNaive || last == kEmptyRank || r > last) best = min(best, r);
+        }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
         if (best == kEmptyRank) break;
+        last = best;
         const uint32_t a = __ldg(&t.m_left[best]), b = __ldg(&t.m_right[best]), z = __ldg(&t.m_new[best]);
         // 3. greedy left-to-right replacement (bpe.py:221-235); each lane owns one contiguous segment
         const uint32_t seg = (n + 31) / 32;
@@ -155,18 +166,21 @@ __device__ __noinline__ uint32_t bpe_encode_long_warp(const BpeTableDev &t, cons
     return n;
 }
 
-struct BpeEnc {
+template <bool kNaive>
+struct BpeEncT {
     BpeTableDev t;
     static constexpr bool kScratchLong = true;
     __device__ __forceinline__ uint32_t encode_short(const uint8_t *p, uint32_t nbytes, uint32_t *buf, uint32_t &h6) const {
         (void)h6;
-        return bpe_encode_short(t, p, nbytes, buf);
+        return bpe_encode_short<kNaive>(t, p, nbytes, buf);
     }
     __device__ __forceinline__ uint32_t encode_long_warp(const uint8_t *p, uint32_t nbytes, uint32_t *bufA, uint32_t *bufB,
                                                          uint32_t **result) const {
-        return bpe_encode_long_warp(t, p, nbytes, bufA, bufB, result);
+        return bpe_encode_long_warp<kNaive>(t, p, nbytes, bufA, bufB, result);
     }
 };
+using BpeEnc = BpeEncT<false>;          // FastBPE.encode_word
+using NaiveBpeEnc = BpeEncT<true>;      // NaiveBPE.encode_word (merge lists without repeated pairs)
 
 }  // namespace swt
 
@@ -244,6 +258,14 @@ int bpe_encode_launch(const swt_bpe_table *t, const uint8_t *d_arena, const uint
                                tok_base, d_workspace, workspace_bytes, d_status, st);
 }
 }  // namespace swt
+
+SWT_API int swt_bpe_encode_naive(const swt_bpe_table *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
+                                 uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off,
+                                 void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream) {
+    SWT_REQUIRE(t != nullptr, "NULL table");
+    return launch_encode_tiles(NaiveBpeEnc{t->dev}, d_arena, d_word_off, n_words, long_word_bytes, d_out_ids, out_cap, d_out_tok_off,
+                               0u, d_workspace, workspace_bytes, d_status, (cudaStream_t)stream);
+}
 
 SWT_API int swt_bpe_encode(const swt_bpe_table *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
                            uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off,

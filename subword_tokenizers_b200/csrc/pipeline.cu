@@ -72,7 +72,7 @@ SWT_API int swt_pipeline_create(int device, uint64_t batch_bytes, swt_pipeline *
     for (int i = 0; i < kSlots; ++i) {
         Slot &s = p->slot[i];
         // BPE long-word scratch is sized for the worst case (every word of the batch is long)
-        s.ws_bytes = swt_encode_workspace_bytes((uint32_t)p->max_words, batch_bytes);
+        s.ws_bytes = swt_encode_workspace_bytes((uint32_t)p->max_words, batch_bytes * kLowerGrowthNum / kLowerGrowthDen);
         cudaError_t e = cudaMalloc(&s.d_arena, batch_bytes * kLowerGrowthNum / kLowerGrowthDen + 16);
         if (e == cudaSuccess) e = cudaMalloc(&s.d_off, (p->max_words + 1) * 4);
         if (e == cudaSuccess) e = cudaMalloc(&s.d_tok_off, (p->max_words + 1) * 4);
@@ -199,13 +199,14 @@ SWT_API int swt_encode_host16(swt_pipeline *p, int which, const void *table, con
     return encode_host_impl(p, which, table, h_arena, h_word_off, n_words, h_out_ids16, true, out_cap, h_out_tok_off, n_tokens, h6_events);
 }
 
-// ---- raw text in, flat token ids out: pre-tokenization (pretok.cu) + FastWP encode per batch --------------------------------
+// ---- raw text in, flat token ids out: pre-tokenization (pretok.cu) + FastBPE / FastWP encode per batch --------------------------------
 static bool ascii_space(uint8_t b) { return b == 0x20 || (b >= 0x09 && b <= 0x0D) || (b >= 0x1C && b <= 0x1F); }
 
-SWT_API int swt_wp_tokenize_host(swt_pipeline *p, const swt_pretok *pretok, const swt_wp_trie *trie, const uint8_t *h_text,
-                                 uint64_t n_bytes, void *h_out_ids, int ids_16bit, uint64_t out_cap, uint64_t *n_tokens,
-                                 uint64_t *n_words_out, uint64_t *h6_events) {
-    SWT_REQUIRE(p && pretok && trie && n_tokens, "NULL argument");
+SWT_API int swt_tokenize_text_host(swt_pipeline *p, const swt_pretok *pretok, int which, const void *table, const uint8_t *h_text,
+                                   uint64_t n_bytes, void *h_out_ids, int ids_16bit, uint64_t out_cap, uint64_t *n_tokens,
+                                   uint64_t *n_words_out, uint64_t *h6_events) {
+    SWT_REQUIRE(p && pretok && table && n_tokens, "NULL argument");
+    SWT_REQUIRE(which == 0 || which == 1, "which must be 0 (BPE) or 1 (WP)");
     SWT_REQUIRE(n_bytes == 0 || (h_text && h_out_ids), "NULL data pointer");
     SWT_CUDA_OK(cudaSetDevice(p->device));
     const bool narrow = ids_16bit != 0;
@@ -263,7 +264,12 @@ SWT_API int swt_wp_tokenize_host(swt_pipeline *p, const swt_pretok *pretok, cons
         if (rc) break;
         words += nw;
         if (nw == 0) continue;
-        rc = wp_encode_launch(trie, s.d_arena, s.d_off, nw, s.d_ids, n_arena + nw + 16, nullptr, 0, s.d_ws, s.ws_bytes, s.d_status, s.stream);
+        if (which == 0)
+            rc = bpe_encode_launch((const swt_bpe_table *)table, s.d_arena, s.d_off, nw, n_arena, s.d_ids, n_arena + nw + 16, nullptr, 0, s.d_ws,
+                                   s.ws_bytes, s.d_status, s.stream);
+        else
+            rc = wp_encode_launch((const swt_wp_trie *)table, s.d_arena, s.d_off, nw, s.d_ids, n_arena + nw + 16, nullptr, 0, s.d_ws, s.ws_bytes,
+                                  s.d_status, s.stream);
         if (rc) break;
         if (narrow) narrow_ids_kernel<<<swt::kNumSMs * 8, 256, 0, s.stream>>>(s.d_ids, s.d_ids16, s.d_status);
         SWT_CUDA_OK(cudaMemcpyAsync(s.h_status, s.d_status, 8 * 4, cudaMemcpyDeviceToHost, s.stream));

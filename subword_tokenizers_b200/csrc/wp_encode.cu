@@ -5,7 +5,7 @@
 // precompute of utils.py:108-139 breadth first from [root, root_sharp], and flattens it into
 //   edge table   open-addressing hash, 16-byte slots {node, code point, child, -}  (one 128-bit load/probe)
 //   root_lut     direct child table of the root for code points < kRootLut
-//   node_info    16 bytes per node {failure link, pops offset, pops count, -}
+//   node_info    16 bytes per node {failure link, pops offset, pops count, vocabulary id of the entry ending here}
 //   pops         token ids emitted on a failure transition
 //   alnum        Python str.isalnum bitmap (wordpiece.py:287-288, utils.py:137)
 // all small enough to stay L2/L1 resident (about 3 MB for a 20K vocabulary).
@@ -118,6 +118,52 @@ __device__ __forceinline__ void wp_encode_chunk(const WpTrieDev &t, const uint8_
         if (i >= nbytes) break;                                             // the virtual space ends the chunk
     }
 }
+
+// NaiveWP.encode_word (wordpiece.py:131-158): greedy longest prefix in the vocabulary; the rest is looked up as "##" + rest.
+// The whole word becomes "[UNK]" (id n_vocab + 1) when a piece has no match.  A continuation piece must match at least one
+// character beyond its "##" (a bare "#"/"##" match makes the reference's remainder grow forever; DESIGN.md, parity domain).
+template <class Emit>
+__device__ __forceinline__ void wp_naive_encode_word(const WpTrieDev &t, const uint8_t *p, uint32_t nbytes, Emit &emit) {
+    const uint32_t seg = emit.size();
+    uint32_t i = 0;
+    bool first = true;
+    while (i < nbytes) {
+        uint32_t node = first ? kNodeRoot : kNodeRootSharp, best = kNone, best_end = i, j = i;
+        while (j < nbytes) {
+            uint32_t adv;
+            const uint32_t cp = utf8_decode(p + j, nbytes - j, adv);
+            const uint32_t child = wp_edge(t, node, cp);
+            if (child == kNone) break;
+            node = child; j += adv;
+            const uint32_t tok = __ldg(&t.node_info[node]).w;                // vocabulary id of the entry ending here, or kNone
+            if (tok != kNone) { best = tok; best_end = j; }
+        }
+        if (best == kNone) { emit.truncate(seg); emit.push(t.n_vocab + 1); return; }
+        emit.push(best); i = best_end; first = false;
+    }
+}
+
+struct NaiveWpEnc {
+    WpTrieDev t;
+    static constexpr bool kScratchLong = false;
+    __device__ __forceinline__ uint32_t encode_short(const uint8_t *p, uint32_t nbytes, uint32_t *buf, uint32_t &h6) const {
+        (void)h6;
+        ArrayEmit e{buf, (uint32_t)kShortBytes};
+        wp_naive_encode_word(t, p, nbytes, e);
+        return e.n;
+    }
+    __device__ __forceinline__ uint32_t long_count(const uint8_t *p, uint32_t nbytes, uint32_t &h6) const {
+        (void)h6;
+        CountEmit e;
+        wp_naive_encode_word(t, p, nbytes, e);
+        return e.n;
+    }
+    __device__ __forceinline__ void long_emit(const uint8_t *p, uint32_t nbytes, uint32_t *dst, uint32_t cap, uint32_t &h6) const {
+        (void)h6;
+        ArrayEmit e{dst, cap};
+        wp_naive_encode_word(t, p, nbytes, e);
+    }
+};
 
 struct WpEnc {
     WpTrieDev t;
@@ -240,7 +286,7 @@ SWT_API int swt_wp_trie_create(const uint32_t *h_vocab_cps, const uint64_t *h_vo
     std::vector<uint32_t> pops;
     uint64_t n_rootp = 0;
     for (uint32_t node = 0; node < n_nodes; ++node) {
-        info[node] = make_uint4(T.fail[node], (uint32_t)pops.size(), (uint32_t)T.pops[node].size(), 0);
+        info[node] = make_uint4(T.fail[node], (uint32_t)pops.size(), (uint32_t)T.pops[node].size(), T.token[node]);
         pops.insert(pops.end(), T.pops[node].begin(), T.pops[node].end());
         n_rootp += (T.fail[node] == kNodeRootP);
     }
@@ -300,4 +346,13 @@ SWT_API int swt_wp_encode(const swt_wp_trie *t, const uint8_t *d_arena, const ui
     (void)long_word_bytes;   // long chunks are walked twice instead of using scratch
     return wp_encode_launch(t, d_arena, d_word_off, n_words, d_out_ids, out_cap, d_out_tok_off, 0u, d_workspace, workspace_bytes,
                             d_status, (cudaStream_t)stream);
+}
+
+SWT_API int swt_wp_encode_naive(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
+                                uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off,
+                                void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream) {
+    (void)long_word_bytes;
+    SWT_REQUIRE(t != nullptr, "NULL trie");
+    return launch_encode_tiles(NaiveWpEnc{t->dev}, d_arena, d_word_off, n_words, 0, d_out_ids, out_cap, d_out_tok_off, 0u, d_workspace,
+                               workspace_bytes, d_status, (cudaStream_t)stream);
 }

@@ -33,10 +33,17 @@ class _Encoder:
 
     _which = -1
 
+    naive = False          # True: the Naive* encoder of the same table (swt_*_encode_naive)
+
     def __init__(self):
         self._handle = c_vp(None)
         self._pipeline = c_vp(None)
         self._pipeline_batch = 0
+
+    @property
+    def _pretok_mode(self) -> int:
+        # FastWP works on whitespace chunks; the three other encoders on BERT pre-tokenized words
+        return _lib.PRETOK_PYTHON_SPLIT if (self._which == 1 and not self.naive) else _lib.PRETOK_BERT
 
     # -- device-resident call ---------------------------------------------------------------------------
     def encode_device(self, d_arena: torch.Tensor, d_off: torch.Tensor, n_words: int, long_word_bytes: int,
@@ -57,7 +64,10 @@ class _Encoder:
 
     def encode_into(self, d_arena, d_off, n_words, long_word_bytes, d_ids, out_cap, d_tok_off, d_ws, d_status):
         lib = _lib.load()
-        fn = lib.swt_bpe_encode if self._which == 0 else lib.swt_wp_encode
+        if self.naive:
+            fn = lib.swt_bpe_encode_naive if self._which == 0 else lib.swt_wp_encode_naive
+        else:
+            fn = lib.swt_bpe_encode if self._which == 0 else lib.swt_wp_encode
         check(fn(self._handle, d_arena.data_ptr(), d_off.data_ptr(), n_words, long_word_bytes, d_ids.data_ptr(), out_cap,
                  d_tok_off.data_ptr() if d_tok_off is not None else None, d_ws.data_ptr(), d_ws.numel(),
                  d_status.data_ptr(), _stream_ptr()), "swt_encode")
@@ -116,6 +126,42 @@ class _Encoder:
                  h_out_tok_off.data_ptr() if h_out_tok_off is not None else None,
                  ctypes.byref(nt), ctypes.byref(h6)), fn.__name__)
         return int(nt.value), int(h6.value)
+
+    def tokenize_host(self, h_text, n_bytes: int, h_out_ids, has_sigma: bool = True, batch_bytes: int = 64 << 20) -> Tuple[int, int, int]:
+        """Raw UTF-8 text in a host buffer (torch tensor, ideally pinned, or numpy array) -> flat token ids in h_out_ids
+        (16- or 32-bit elements), through swt_tokenize_text_host. -> (n_tokens, n_words, h6_events)."""
+        lib = _lib.load()
+        if self.naive:
+            raise SwtError("the host-buffer pipeline serves the Fast encoders only")
+        pt = Pretokenizer.get(mode=self._pretok_mode)
+        if has_sigma and not pt._with_sigma:
+            pt._create(True)
+        is_np = isinstance(h_text, np.ndarray)
+        text_ptr = h_text.ctypes.data if is_np else h_text.data_ptr()
+        out_ptr = h_out_ids.ctypes.data if isinstance(h_out_ids, np.ndarray) else h_out_ids.data_ptr()
+        out_n = h_out_ids.size if isinstance(h_out_ids, np.ndarray) else h_out_ids.numel()
+        elem = h_out_ids.itemsize if isinstance(h_out_ids, np.ndarray) else h_out_ids.element_size()
+        nt, nw, h6 = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint64(0)
+        check(lib.swt_tokenize_text_host(self.pipeline(batch_bytes), pt._handle, self._which, self._handle, text_ptr, n_bytes,
+                                         out_ptr, 1 if elem == 2 else 0, out_n, ctypes.byref(nt), ctypes.byref(nw), ctypes.byref(h6)),
+              "swt_tokenize_text_host")
+        return int(nt.value), int(nw.value), int(h6.value)
+
+    SMALL_TEXT_BYTES = 1 << 20
+
+    def encode_text(self, text: str, return_offsets: bool = False):
+        """tokenize() on the device from the raw text: pre-tokenization (lower-casing, splitting) + encode.  Texts up to 1 MiB take
+        the single C call (swt_tokenize_text_host, three synchronisations); larger ones stay resident (Pretokenizer + encode_device).
+        -> token ids u32 (and the u32 token offsets per word when return_offsets)."""
+        data = P.encode_utf8(text)
+        if not return_offsets and not self.naive and len(data) <= self.SMALL_TEXT_BYTES:
+            if not data:
+                return np.zeros(0, np.uint32)
+            out = np.empty(2 * len(data) + 16, dtype=np.uint32)
+            nt, _, _ = self.tokenize_host(np.frombuffer(data, dtype=np.uint8), len(data), out, has_sigma="\u03a3" in text,
+                                          batch_bytes=self.SMALL_TEXT_BYTES + 64)
+            return out[:nt]
+        return self._encode_text_resident(text, return_offsets)
 
     def close(self):
         lib = _lib.load()
@@ -211,8 +257,9 @@ class BpeEncoder(_Encoder):
 
     _which = 0
 
-    def __init__(self, tables: P.BpeTables, device: Optional[int] = None):
+    def __init__(self, tables: P.BpeTables, device: Optional[int] = None, naive: bool = False):
         super().__init__()
+        self.naive = naive
         _lib.require_cuda()
         lib = _lib.load()
         self.tables = tables
@@ -229,9 +276,9 @@ class BpeEncoder(_Encoder):
             self._handle = c_vp(None)
 
 
-def _bpe_encode_text(self, text: str, return_offsets: bool = False):
+def _bpe_encode_text_resident(self, text: str, return_offsets: bool = False):
     """FastBPE.tokenize on the device from the raw text: BERT pre-tokenization (Pretokenizer, PRETOK_BERT) + encode."""
-    d_arena, d_off, n_words = Pretokenizer.get(mode=_lib.PRETOK_BERT).split_text(text)
+    d_arena, d_off, n_words = Pretokenizer.get(mode=self._pretok_mode).split_text(text)
     if n_words == 0:
         return (np.zeros(0, np.uint32), np.zeros(1, np.uint32)) if return_offsets else np.zeros(0, np.uint32)
     lens = (d_off[1:n_words + 1] - d_off[:n_words]).long()                    # bytes of the long words size the scratch
@@ -242,7 +289,7 @@ def _bpe_encode_text(self, text: str, return_offsets: bool = False):
     return (ids, d_tok_off.cpu().numpy().view(np.uint32)) if return_offsets else ids
 
 
-BpeEncoder.encode_text = _bpe_encode_text
+BpeEncoder._encode_text_resident = _bpe_encode_text_resident
 
 
 class WpEncoder(_Encoder):
@@ -250,8 +297,9 @@ class WpEncoder(_Encoder):
 
     _which = 1
 
-    def __init__(self, tables: P.WpTables, sharp_special: Sequence[int], device: Optional[int] = None):
+    def __init__(self, tables: P.WpTables, sharp_special: Sequence[int], device: Optional[int] = None, naive: bool = False):
         super().__init__()
+        self.naive = naive
         _lib.require_cuda()
         lib = _lib.load()
         self.tables = tables
@@ -265,30 +313,14 @@ class WpEncoder(_Encoder):
                                      current_device() if device is None else device, ctypes.byref(self._handle)),
               "swt_wp_trie_create")
 
-    def encode_text(self, text: str, return_offsets: bool = False):
-        """FastWP.tokenize on the device from the raw text: pre-tokenization (Pretokenizer) + encode.
-        -> token ids u32 (and the u32 token offsets per word when return_offsets)."""
-        d_arena, d_off, n_words = Pretokenizer.get().split_text(text)
+    def _encode_text_resident(self, text: str, return_offsets: bool = False):
+        d_arena, d_off, n_words = Pretokenizer.get(mode=self._pretok_mode).split_text(text)
         if n_words == 0:
             return (np.zeros(0, np.uint32), np.zeros(1, np.uint32)) if return_offsets else np.zeros(0, np.uint32)
         d_ids, d_tok_off, d_status = self.encode_device(d_arena, d_off, n_words, 0, want_offsets=return_offsets)
         n_tok, _ = self.check_status(d_status)
         ids = d_ids[:n_tok].cpu().numpy().view(np.uint32)
         return (ids, d_tok_off.cpu().numpy().view(np.uint32)) if return_offsets else ids
-
-    def tokenize_host(self, h_text: torch.Tensor, n_bytes: int, h_out_ids: torch.Tensor, has_sigma: bool = True,
-                      batch_bytes: int = 64 << 20) -> Tuple[int, int, int]:
-        """Raw UTF-8 text in a host (ideally pinned) uint8 tensor -> flat token ids in h_out_ids (int16/uint16 or int32),
-        through swt_wp_tokenize_host. -> (n_tokens, n_words, h6_events)."""
-        lib = _lib.load()
-        pt = Pretokenizer.get()
-        if has_sigma and not pt._with_sigma:
-            pt._create(True)
-        nt, nw, h6 = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint64(0)
-        check(lib.swt_wp_tokenize_host(self.pipeline(batch_bytes), pt._handle, self._handle, h_text.data_ptr(), n_bytes,
-                                       h_out_ids.data_ptr(), 1 if h_out_ids.element_size() == 2 else 0, h_out_ids.numel(),
-                                       ctypes.byref(nt), ctypes.byref(nw), ctypes.byref(h6)), "swt_wp_tokenize_host")
-        return int(nt.value), int(nw.value), int(h6.value)
 
     def stats(self):
         n, e, p, r = (ctypes.c_uint64(0) for _ in range(4))

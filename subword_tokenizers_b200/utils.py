@@ -22,6 +22,18 @@ class SubwordTokenizer:
         pre = self.tokenizer.backend_tokenizer.pre_tokenizer
         return [w for example in corpus for w, _ in pre.pre_tokenize_str(example.lower())]
 
+    def _device_pretok_ok(self) -> bool:
+        """The device pre-tokenizer reproduces the Rust BertPreTokenizer (the only one the reference ever uses, cli.py:163);
+        any other pre-tokenizer object, or a `tokenizers` build whose character classes differ from the shipped table, keeps
+        the host call of utils.py:27."""
+        ok = getattr(self, "_pretok_checked", None)
+        if ok is None:
+            from . import packing as P
+            pre = self.tokenizer.backend_tokenizer.pre_tokenizer
+            ok = type(pre).__name__ == "BertPreTokenizer" and P.bert_pretokenizer_matches(pre)
+            self._pretok_checked = ok
+        return ok
+
     def vocab_length(self, corpus: List[str]) -> int:
         return len({symbol for example in corpus for symbol in example})
 

@@ -12,6 +12,7 @@ import os
 from collections import Counter
 from typing import Dict, List, Sequence, Tuple
 
+from . import packing as P
 from .utils import SubwordTokenizer, WPTrie_E2E, naive_wp_encode
 
 
@@ -83,13 +84,33 @@ class NaiveWP(SubwordTokenizer):
     def encode_word(self, word):
         return naive_wp_encode(word, self.vocab)
 
+    def _naive_device_encoder(self):
+        """Greedy longest-prefix encoder on the device (swt_wp_encode_naive) over the trie of the current vocabulary."""
+        from .device import WpEncoder
+        from .utils import naive_wp_encode_ids
+        quick = (id(self.vocab), len(self.vocab))
+        if getattr(self, "_naive_quick", None) != quick:
+            tables = P.WpTables(self.vocab)
+            self._naive_encoder = WpEncoder(tables, naive_wp_encode_ids("##", tables), naive=True)
+            self._naive_quick = quick
+        return self._naive_encoder
+
+    def encode_words(self, words: Sequence[str]) -> List[List[str]]:
+        """Batch form of encode_word: one kernel launch for all words."""
+        enc = self._naive_device_encoder()
+        ids, tok_off, _ = enc.encode_words(words)
+        strs = enc.tables.tokens_to_strs(ids)
+        return [strs[int(tok_off[i]):int(tok_off[i + 1])] for i in range(len(words))]
+
     def tokenize(self, text):
         if not isinstance(text, str):
             raise TypeError("Text to tokenize must be a string.")
-        out: List[str] = []
-        for word in self._pre_tokenized_words([text]):
-            out.extend(self.encode_word(word))
-        return out
+        enc = self._naive_device_encoder()
+        if self._device_pretok_ok():
+            ids = enc.encode_text(text)                 # lower-casing + BERT pre-tokenization + greedy matching on the device
+        else:
+            ids, _, _ = enc.encode_words(self._pre_tokenized_words([text]))
+        return enc.tables.tokens_to_strs(ids)
 
     def reset(self) -> None:
         self.vocab.clear()

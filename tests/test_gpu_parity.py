@@ -522,7 +522,7 @@ def test_fastwp_tokenize_text_on_device_equals_word_path(P, dev):
 
 
 def test_wp_tokenize_host_from_raw_text(P, dev):
-    """swt_wp_tokenize_host: raw text in a host buffer, many small batches, 16- and 32-bit ids."""
+    """swt_tokenize_text_host: raw text in a host buffer, many small batches, 16- and 32-bit ids."""
     import torch
     from subword_tokenizers_b200.utils import naive_wp_encode_ids
     tab = P.WpTables(load_golden("pretrained_wp_vocab.json.gz"))
@@ -589,3 +589,69 @@ def test_fastbpe_tokenize_text_on_device_equals_word_path(P, dev):
     ids_w, tok_w, _ = benc.encode_words(_bert_words(text))
     ids_t, tok_t = benc.encode_text(text, return_offsets=True)
     assert np.array_equal(ids_w, ids_t) and np.array_equal(tok_w, tok_t)
+
+
+def test_bpe_tokenize_text_host_and_small_text_path(P, dev):
+    """swt_tokenize_text_host with the BPE table (BERT pre-tokenization), and the single-call path of encode_text."""
+    import torch
+    tab = P.BpeTables([tuple(p) for p in load_golden("pretrained_bpe_merges.json.gz")])
+    benc = dev.BpeEncoder(tab)
+    text = "\n".join(load_golden("pan_tadeusz.json.gz")) + " ΟΔΥΣΣΕΥΣ, İstanbul!　x " + "q" * 70 + "."
+    ids, _, _ = benc.encode_words(_bert_words(text))
+    data = np.frombuffer(P.encode_utf8(text), dtype=np.uint8)
+    h_ids = torch.zeros(len(data) * 2 + 64, dtype=torch.int32).pin_memory()
+    nt, nw, _ = benc.tokenize_host(torch.from_numpy(data.copy()).pin_memory(), len(data), h_ids, batch_bytes=1 << 16)
+    assert nw == len(_bert_words(text)) and nt == len(ids) and np.array_equal(h_ids.numpy()[:nt].view(np.uint32), ids)
+    assert np.array_equal(benc.encode_text(text), ids)                       # <= 1 MiB: one C call
+    assert np.array_equal(benc._encode_text_resident(text), ids)
+    big = (text + " ") * 30                                                  # > 1 MiB: resident path
+    assert len(P.encode_utf8(big)) > benc.SMALL_TEXT_BYTES
+    assert np.array_equal(benc.encode_text(big), np.tile(ids, 30))
+
+
+# ---- the Naive encoders as kernels (SURVEY.md §8 f-3) ---------------------------------------------------------------------
+def test_naive_encoders_on_device_match_golden_tokens(P, dev):
+    """NaiveBPE.tokenize / NaiveWP.tokenize through the device path reproduce data/pan_tadeusz.tokens.json."""
+    from subword_tokenizers_b200 import NaiveBPE, NaiveWP, make_hf_tokenizer
+    lines = load_golden("pan_tadeusz.json.gz")
+    gold = load_golden("pan_tadeusz.tokens.json.gz")
+    hf = make_hf_tokenizer()
+    nb = NaiveBPE(hf); nb.merges_list = [tuple(p) for p in load_golden("pretrained_bpe_merges.json.gz")]
+    nw = NaiveWP(hf); nw.vocab = set(load_golden("pretrained_wp_vocab.json.gz"))
+    assert nb._naive_device_encoder() is not None and nb._device_pretok_ok()
+    for k in range(0, len(lines), 7):
+        assert nb.tokenize(lines[k]) == gold["NaiveBPE"][k], k
+        assert nw.tokenize(lines[k]) == gold["NaiveWordPiece"][k], k
+    text = "\n".join(lines)
+    assert nb.tokenize(text) == [t for l in gold["NaiveBPE"] for t in l]
+    assert nw.tokenize(text) == [t for l in gold["NaiveWordPiece"] for t in l]
+
+
+def test_naive_encoders_on_device_match_reference_on_random_cases(P, dev):
+    """180 randomized merge lists / vocabularies (tests/golden/ref_random_cases.json.gz, outputs of the unmodified reference):
+    untrainable merge orders (Naive != Fast), tiny alphabets, '#'-heavy vocabularies."""
+    from subword_tokenizers_b200.utils import naive_wp_encode_ids
+    cases = load_golden("ref_random_cases.json.gz")
+    n_bpe = n_wp = n_diff = 0
+    for case in cases["bpe_encode"]:
+        pairs = [tuple(p) for p in case["merges"]]
+        if len(set(pairs)) != len(pairs):
+            continue                                   # repeated pair: the class keeps the host replay
+        tab = P.BpeTables(pairs)
+        arena, off = P.pack_words(case["words"])
+        ids, tok, _ = dev.BpeEncoder(tab, naive=True).encode_packed(arena, off.astype(np.uint32))
+        strs = tab.tokens_to_strs(ids)
+        got = [strs[int(tok[i]):int(tok[i + 1])] for i in range(len(case["words"]))]
+        assert got == case["naive"]
+        n_bpe += 1
+        n_diff += case["naive"] != case["fast"]
+    for case in cases["wp_encode"]:
+        tab = P.WpTables(case["vocab"])
+        enc = dev.WpEncoder(tab, naive_wp_encode_ids("##", tab), naive=True)
+        for text, naive in zip(case["texts"], case["naive"]):
+            if naive is None:
+                continue                               # the reference does not terminate on this input
+            ids = enc._encode_text_resident(text)
+            assert tab.tokens_to_strs(ids) == naive, (case["vocab"], text)
+            n_wp += 1
+    assert n_bpe >= 20 and n_diff >= 1 and n_wp >= 500

@@ -99,18 +99,23 @@ def test_naive_bpe_host_encoder_matches_reference(hf_tokenizer, random_cases):
     gold = load_golden("pan_tadeusz.tokens.json.gz")["NaiveBPE"]
     nb.merges_list = [tuple(p) for p in load_golden("pretrained_bpe_merges.json.gz")]
     lines = load_golden("pan_tadeusz.json.gz")
-    assert [nb.tokenize(l) for l in lines[:3]] == gold[:3]
+    # encode_word is the host replay (bpe.py:114-132); tokenize() runs on the GPU (tests/test_gpu_parity.py)
+    assert [[t for w in nb._pre_tokenized_words([l]) for t in nb.encode_word(w)] for l in lines[:3]] == gold[:3]
     assert nb.encode_word("") == []
 
 
 def test_naive_wp_host_encoder_matches_reference(hf_tokenizer, random_cases):
-    """NaiveWP.encode_word / tokenize are host code (NaiveWP.train runs on the GPU: tests/test_gpu_parity.py)."""
+    """NaiveWP.encode_word is host code (wordpiece.py:131-158); NaiveWP.tokenize / train run on the GPU
+    (tests/test_gpu_parity.py)."""
     nw = NaiveWP(hf_tokenizer)
+
+    def host_tokenize(text):
+        return [t for w in nw._pre_tokenized_words([text]) for t in nw.encode_word(w)]
     for case in random_cases["wp_encode"]:
         nw.vocab = set(case["vocab"])
         for text, naive in zip(case["texts"], case["naive"]):
             if naive is not None:
-                assert nw.tokenize(text) == naive
+                assert host_tokenize(text) == naive
     nw.vocab = set(load_golden("pretrained_wp_vocab.json.gz"))
     lines = load_golden("pan_tadeusz.json.gz")
-    assert [nw.tokenize(l) for l in lines] == load_golden("pan_tadeusz.tokens.json.gz")["NaiveWordPiece"]
+    assert [host_tokenize(l) for l in lines] == load_golden("pan_tadeusz.tokens.json.gz")["NaiveWordPiece"]
