@@ -168,8 +168,10 @@ size_t swt_pretok_workspace_bytes(uint64_t n_text_bytes);
 int swt_pretok_count(const swt_pretok *p, const uint8_t *d_text, uint64_t n_bytes, void *d_workspace, size_t workspace_bytes,
                      uint32_t *d_status, void *stream);
 int swt_pretok_write(const swt_pretok *p, const uint8_t *d_text, uint64_t n_bytes, void *d_workspace, size_t workspace_bytes,
-                     uint8_t *d_arena_out, uint64_t arena_cap, uint32_t *d_word_off_out, uint64_t word_cap,
+                     uint8_t *d_arena_out, uint64_t arena_cap, uint32_t *d_word_off_out, uint32_t *d_word_src_out, uint64_t word_cap,
                      uint32_t n_words, uint64_t n_out_bytes, uint32_t *d_status, void *stream);
+/* d_word_src_out (n_words u32, may be NULL): byte position in the text at which each word starts, so that a caller who
+ * concatenated many texts can cut the token stream per text (tokenize_batch; the harness row of SURVEY.md section 8f). */
 
 /* ---- host-buffer entry points (what a non-Python integrator binds) ------------------------------- */
 /*

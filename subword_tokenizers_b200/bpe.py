@@ -18,6 +18,21 @@ from . import packing as P
 from .utils import SubwordTokenizer
 
 
+def _batch_lists(tok, enc, texts: Sequence[str]) -> List[List[str]]:
+    """Shared body of tokenize_batch: device batch call when the pre-tokenizer is the BERT one, else host pre-tokenization."""
+    if not all(isinstance(t, str) for t in texts):
+        raise TypeError("Text must be a string.")
+    if tok._device_pretok_ok():
+        ids, cut = enc.encode_texts(texts)
+    else:
+        pre = tok.tokenizer.backend_tokenizer.pre_tokenizer
+        per_text = [[w for w, _ in pre.pre_tokenize_str(t.lower())] for t in texts]
+        ids, tok_off, _ = enc.encode_words([w for ws in per_text for w in ws])
+        cut = tok_off.astype(np.int64)[np.cumsum([0] + [len(ws) for ws in per_text])]
+    strs = enc.tables.tokens_to_strs(ids)
+    return [strs[int(cut[k]):int(cut[k + 1])] for k in range(len(texts))]
+
+
 class NaiveBPE(SubwordTokenizer):
     """Byte-Pair-Encoding tokenizer (reference source/bpe.py:9-189)."""
 
@@ -128,6 +143,13 @@ class NaiveBPE(SubwordTokenizer):
         strs = enc.tables.tokens_to_strs(ids)
         return [strs[int(tok_off[i]):int(tok_off[i + 1])] for i in range(len(words))]
 
+    def tokenize_batch(self, texts: Sequence[str]) -> List[List[str]]:
+        """tokenize() of every text with one pass over their concatenation."""
+        enc = self._naive_device_encoder()
+        if enc is None:
+            return [self.tokenize(t) for t in texts]
+        return _batch_lists(self, enc, texts)
+
     def tokenize(self, text: str) -> List[str]:
         if not isinstance(text, str):
             raise TypeError("Text to tokenize must be a string.")
@@ -223,17 +245,10 @@ class FastBPE(NaiveBPE):
         return enc.tables.tokens_to_strs(ids)
 
     def tokenize_batch(self, texts: Sequence[str]) -> List[List[str]]:
-        """All texts in one launch; returns one token list per text."""
-        pre = self.tokenizer.backend_tokenizer.pre_tokenizer
-        per_text = [[w for w, _ in pre.pre_tokenize_str(t.lower())] for t in texts]
+        """tokenize() of every text with one pass over their concatenation (pre-tokenization and merge loop on the device);
+        returns one token list per text."""
         enc = self._device_encoder()
-        ids, tok_off, _ = enc.encode_words([w for ws in per_text for w in ws])
-        strs = enc.tables.tokens_to_strs(ids)
-        out, wi = [], 0
-        for ws in per_text:
-            out.append(strs[int(tok_off[wi]):int(tok_off[wi + len(ws)])])
-            wi += len(ws)
-        return out
+        return _batch_lists(self, enc, texts)
 
     def load_resources(self, path: str) -> None:
         super().load_resources(path)

@@ -259,7 +259,7 @@ SWT_API int swt_tokenize_text_host(swt_pipeline *p, const swt_pretok *pretok, in
         const uint32_t nw = s.h_status[1];
         const uint64_t n_arena = ((uint64_t)s.h_status[3] << 32) | s.h_status[2];
         if (nw > p->max_words) { set_error("more words in a batch than the pipeline was sized for"); rc = SWT_ERR_CAPACITY; break; }
-        rc = swt_pretok_write(pretok, s.d_text, nb, s.d_ptws, s.ptws_bytes, s.d_arena, n_arena, s.d_off, p->max_words + 1, nw, n_arena,
+        rc = swt_pretok_write(pretok, s.d_text, nb, s.d_ptws, s.ptws_bytes, s.d_arena, n_arena, s.d_off, nullptr, p->max_words + 1, nw, n_arena,
                               s.d_status, s.stream);
         if (rc) break;
         words += nw;

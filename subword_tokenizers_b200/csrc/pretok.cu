@@ -219,7 +219,7 @@ __device__ __forceinline__ LaneStep analyze(const PretokDev &t, const uint8_t *t
 
 // writes the lane's lowered bytes at arena + byte_pos and its word offsets at word_off + word_pos
 __device__ __forceinline__ void emit(const PretokDev &t, const uint8_t *text, uint64_t n, uint64_t i, uint32_t w_cur, uint32_t w_next,
-                                     const LaneStep &r, uint8_t *arena, uint64_t byte_pos, uint32_t *word_off, uint32_t word_pos,
+                                     const LaneStep &r, uint8_t *arena, uint64_t byte_pos, uint32_t *word_off, uint32_t *word_src, uint32_t word_pos,
                                      uint32_t *status) {
     uint8_t *dst = arena + byte_pos;
     uint32_t used = 0;
@@ -227,7 +227,10 @@ __device__ __forceinline__ void emit(const PretokDev &t, const uint8_t *text, ui
     for (int p = 0; p < 4; ++p) {
         const uint32_t flag = 0x80u << (8 * p);
         if (!(r.ns & flag)) continue;
-        if (r.wstart & flag) word_off[word_pos++] = (uint32_t)(dst - arena);
+        if (r.wstart & flag) {
+            if (word_src) word_src[word_pos] = (uint32_t)(i + p);             // where the word starts in the text
+            word_off[word_pos++] = (uint32_t)(dst - arena);
+        }
         const uint32_t b = (r.lowered >> (8 * p)) & 0xFFu;
         if (b < 0x80u) { *dst++ = (uint8_t)b; continue; }
         if (used == 2) continue;                            // only reachable with malformed UTF-8: never write more than was counted
@@ -244,7 +247,7 @@ __device__ __forceinline__ void emit(const PretokDev &t, const uint8_t *text, ui
 
 template <bool kWrite, bool kBert>
 __global__ void __launch_bounds__(256) pretok_kernel(PretokDev t, const uint8_t *__restrict__ text, uint64_t n, PretokWs ws,
-                                                     uint8_t *__restrict__ arena, uint32_t *__restrict__ word_off, uint32_t n_words_total,
+                                                     uint8_t *__restrict__ arena, uint32_t *__restrict__ word_off, uint32_t *__restrict__ word_src, uint32_t n_words_total,
                                                      uint32_t n_bytes_total, uint32_t *status) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(256) pretok_kernel(PretokDev t, const uint8_t 
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += v; }
                     const uint32_t excl = incl - r.mine, total = __shfl_sync(0xffffffffu, incl, 31);
-                    if (r.ns) emit(t, text, n, i, w_cur, w_next, r, arena, byte_pos + (excl & 0xFFFFu), word_off, word_pos + (excl >> 16), status);
+                    if (r.ns) emit(t, text, n, i, w_cur, w_next, r, arena, byte_pos + (excl & 0xFFFFu), word_off, word_src, word_pos + (excl >> 16), status);
                     byte_pos += total & 0xFFFFu; word_pos += total >> 16;
                 }
             }
@@ -409,8 +412,8 @@ SWT_API int swt_pretok_count(const swt_pretok *p, const uint8_t *d_text, uint64_
     if (pretok_layout(n_bytes, d_workspace, &ws) > workspace_bytes) { set_error("pretok workspace too small"); return SWT_ERR_CAPACITY; }
     SWT_CUDA_OK(cudaMemsetAsync(d_status, 0, 8 * sizeof(uint32_t), st));
     if (n_bytes == 0) return SWT_OK;
-    if (p->mode == SWT_PRETOK_BERT) pretok_kernel<false, true><<<pretok_grid(ws.n_tiles), 256, 0, st>>>(dev_view(p), d_text, n_bytes, ws, nullptr, nullptr, 0, 0, d_status);
-    else pretok_kernel<false, false><<<pretok_grid(ws.n_tiles), 256, 0, st>>>(dev_view(p), d_text, n_bytes, ws, nullptr, nullptr, 0, 0, d_status);
+    if (p->mode == SWT_PRETOK_BERT) pretok_kernel<false, true><<<pretok_grid(ws.n_tiles), 256, 0, st>>>(dev_view(p), d_text, n_bytes, ws, nullptr, nullptr, nullptr, 0, 0, d_status);
+    else pretok_kernel<false, false><<<pretok_grid(ws.n_tiles), 256, 0, st>>>(dev_view(p), d_text, n_bytes, ws, nullptr, nullptr, nullptr, 0, 0, d_status);
     pretok_scan_groups_kernel<<<ws.n_groups, 256, 0, st>>>(ws);
     pretok_scan_top_kernel<<<1, 1, 0, st>>>(ws, d_status);
     SWT_CUDA_OK(cudaGetLastError());
@@ -418,7 +421,7 @@ SWT_API int swt_pretok_count(const swt_pretok *p, const uint8_t *d_text, uint64_
 }
 
 SWT_API int swt_pretok_write(const swt_pretok *p, const uint8_t *d_text, uint64_t n_bytes, void *d_workspace, size_t workspace_bytes,
-                             uint8_t *d_arena_out, uint64_t arena_cap, uint32_t *d_word_off_out, uint64_t word_cap,
+                             uint8_t *d_arena_out, uint64_t arena_cap, uint32_t *d_word_off_out, uint32_t *d_word_src_out, uint64_t word_cap,
                              uint32_t n_words, uint64_t n_out_bytes, uint32_t *d_status, void *stream) {
     SWT_REQUIRE(p && d_status && d_workspace && d_word_off_out, "NULL argument");
     SWT_REQUIRE(n_out_bytes == 0 || d_arena_out, "d_arena_out is NULL");
@@ -429,9 +432,9 @@ SWT_API int swt_pretok_write(const swt_pretok *p, const uint8_t *d_text, uint64_
     if (pretok_layout(n_bytes, d_workspace, &ws) > workspace_bytes) { set_error("pretok workspace too small"); return SWT_ERR_CAPACITY; }
     if (n_bytes == 0) { SWT_CUDA_OK(cudaMemsetAsync(d_word_off_out, 0, sizeof(uint32_t), st)); return SWT_OK; }
     if (p->mode == SWT_PRETOK_BERT)
-        pretok_kernel<true, true><<<pretok_grid(ws.n_tiles), 256, 0, st>>>(dev_view(p), d_text, n_bytes, ws, d_arena_out, d_word_off_out, n_words, (uint32_t)n_out_bytes, d_status);
+        pretok_kernel<true, true><<<pretok_grid(ws.n_tiles), 256, 0, st>>>(dev_view(p), d_text, n_bytes, ws, d_arena_out, d_word_off_out, d_word_src_out, n_words, (uint32_t)n_out_bytes, d_status);
     else
-        pretok_kernel<true, false><<<pretok_grid(ws.n_tiles), 256, 0, st>>>(dev_view(p), d_text, n_bytes, ws, d_arena_out, d_word_off_out, n_words, (uint32_t)n_out_bytes, d_status);
+        pretok_kernel<true, false><<<pretok_grid(ws.n_tiles), 256, 0, st>>>(dev_view(p), d_text, n_bytes, ws, d_arena_out, d_word_off_out, d_word_src_out, n_words, (uint32_t)n_out_bytes, d_status);
     SWT_CUDA_OK(cudaGetLastError());
     return SWT_OK;
 }

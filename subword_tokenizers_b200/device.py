@@ -147,6 +147,29 @@ class _Encoder:
               "swt_tokenize_text_host")
         return int(nt.value), int(nw.value), int(h6.value)
 
+    def encode_texts(self, texts: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
+        """tokenize() of many texts in ONE pass over their concatenation (the harness batch entry point).
+        -> (token ids u32 of all texts back to back, int64 offsets[len(texts) + 1] of each text's tokens)."""
+        enc = [P.encode_utf8(t) for t in texts]
+        bounds = np.zeros(len(texts) + 1, dtype=np.int64)
+        np.cumsum([len(b) + 1 for b in enc], out=bounds[1:])                 # +1: the "\n" that separates two texts
+        data = b"\n".join(enc)
+        if not data:
+            return np.zeros(0, np.uint32), np.zeros(len(texts) + 1, np.int64)
+        d_arena, d_off, n_words, d_src = Pretokenizer.get(mode=self._pretok_mode).split_text(data, want_src=True)
+        if n_words == 0:
+            return np.zeros(0, np.uint32), np.zeros(len(texts) + 1, np.int64)
+        long_bytes = 0
+        if self._which == 0:
+            lens = (d_off[1:n_words + 1] - d_off[:n_words]).long()
+            long_bytes = int(lens[lens > SHORT_WORD_BYTES].sum().item())
+        d_ids, d_tok_off, d_status = self.encode_device(d_arena, d_off, n_words, long_bytes)
+        n_tok, _ = self.check_status(d_status)
+        ids = d_ids[:n_tok].cpu().numpy().view(np.uint32)
+        tok_off = d_tok_off.cpu().numpy().view(np.uint32).astype(np.int64)
+        first_word = np.searchsorted(d_src[:n_words].cpu().numpy().view(np.uint32), bounds, side="left")
+        return ids, tok_off[first_word]
+
     SMALL_TEXT_BYTES = 1 << 20
 
     def encode_text(self, text: str, return_offsets: bool = False):
@@ -219,8 +242,9 @@ class Pretokenizer:
                                     self.mode, self.device, ctypes.byref(self._handle)), "swt_pretok_create")
         self._with_sigma = with_sigma
 
-    def split_device(self, d_text: torch.Tensor, n_bytes: int, has_sigma: bool):
-        """d_text: uint8 CUDA tensor holding n_bytes of UTF-8 (numel a multiple of 4). -> (d_arena, d_word_off, n_words)."""
+    def split_device(self, d_text: torch.Tensor, n_bytes: int, has_sigma: bool, want_src: bool = False):
+        """d_text: uint8 CUDA tensor holding n_bytes of UTF-8 (numel a multiple of 4). -> (d_arena, d_word_off, n_words), plus the
+        int32 tensor of the words' start positions in the text when want_src."""
         lib = _lib.load()
         if has_sigma and not self._with_sigma:
             self._create(True)
@@ -235,21 +259,23 @@ class Pretokenizer:
         n_words, n_out = int(st[1]), int(st[2]) | (int(st[3]) << 32)
         d_arena = torch.empty(n_out + 16, dtype=torch.uint8, device=dev)
         d_off = torch.empty(n_words + 1, dtype=torch.int32, device=dev)
+        d_src = torch.empty(max(n_words, 1), dtype=torch.int32, device=dev) if want_src else None
         check(lib.swt_pretok_write(self._handle, d_text.data_ptr(), n_bytes, ws.data_ptr(), ws.numel(), d_arena.data_ptr(), n_out,
-                                   d_off.data_ptr(), n_words + 1, n_words, n_out, d_status.data_ptr(), _stream_ptr()),
-              "swt_pretok_write")
-        return d_arena, d_off, n_words
+                                   d_off.data_ptr(), d_src.data_ptr() if want_src else None, n_words + 1, n_words, n_out,
+                                   d_status.data_ptr(), _stream_ptr()), "swt_pretok_write")
+        return (d_arena, d_off, n_words, d_src) if want_src else (d_arena, d_off, n_words)
 
-    def split_text(self, text: str):
-        """Python str -> (d_arena, d_word_off, n_words) on the current device."""
-        data = P.encode_utf8(text)
+    def split_text(self, text, want_src: bool = False):
+        """Python str (or its UTF-8 bytes) -> (d_arena, d_word_off, n_words[, d_word_src]) on the current device."""
+        data = text if isinstance(text, (bytes, bytearray)) else P.encode_utf8(text)
         n = len(data)
         if n >= (1 << 32) - 256:
             raise SwtError("text >= 4 GiB: split it")
         host = np.zeros((n + 7) // 4 * 4, dtype=np.uint8)
         host[:n] = np.frombuffer(data, dtype=np.uint8)
         d_text = torch.from_numpy(host).to(torch.device("cuda", self.device))
-        return self.split_device(d_text, n, "\u03a3" in text)
+        has_sigma = (b"\xce\xa3" in data) if isinstance(text, (bytes, bytearray)) else ("\u03a3" in text)
+        return self.split_device(d_text, n, has_sigma, want_src)
 
 
 class BpeEncoder(_Encoder):

@@ -241,15 +241,25 @@ class BpeTables:
         return "##" + s if cont else s
 
     def tokens_to_strs(self, toks: Iterable[int]) -> List[str]:
-        cache: Dict[int, str] = {}
-        out = []
-        for t in toks:
-            t = int(t)
-            s = cache.get(t)
-            if s is None:
-                s = cache[t] = self.token_to_str(t)
-            out.append(s)
-        return out
+        """Token ids -> the reference's token strings.  Vectorised: one fancy-indexing pass over an object array of
+        [symbol, "##" + symbol] pairs; ids outside it (characters no merge mentions, the empty word) take the scalar path."""
+        toks = np.asarray(toks, dtype=np.uint32) if not isinstance(toks, np.ndarray) else toks.astype(np.uint32, copy=False)
+        if toks.size == 0:
+            return []
+        lut = getattr(self, "_str_lut", None)
+        if lut is None:
+            lut = np.empty(2 * len(self.id_to_str), dtype=object)
+            lut[0::2] = self.id_to_str
+            lut[1::2] = ["##" + x for x in self.id_to_str]
+            self._str_lut = lut
+        known = toks < len(lut)
+        if known.all():
+            return lut[toks].tolist()
+        out = np.empty(toks.size, dtype=object)
+        out[known] = lut[toks[known]]
+        for k in np.flatnonzero(~known):
+            out[k] = self.token_to_str(int(toks[k]))
+        return out.tolist()
 
 
 class WpTables:
@@ -272,8 +282,11 @@ class WpTables:
         return len(self.tokens)
 
     def tokens_to_strs(self, toks: Iterable[int]) -> List[str]:
-        t = self.id_to_str
-        return [t[int(i)] for i in toks]
+        lut = getattr(self, "_str_lut", None)
+        if lut is None:
+            lut = self._str_lut = np.array(self.id_to_str, dtype=object)
+        toks = np.asarray(toks, dtype=np.int64)
+        return lut[toks].tolist() if toks.size else []
 
 
 class TrainTypes:

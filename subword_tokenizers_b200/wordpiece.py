@@ -102,6 +102,11 @@ class NaiveWP(SubwordTokenizer):
         strs = enc.tables.tokens_to_strs(ids)
         return [strs[int(tok_off[i]):int(tok_off[i + 1])] for i in range(len(words))]
 
+    def tokenize_batch(self, texts: Sequence[str]) -> List[List[str]]:
+        """tokenize() of every text with one pass over their concatenation."""
+        from .bpe import _batch_lists
+        return _batch_lists(self, self._naive_device_encoder(), texts)
+
     def tokenize(self, text):
         if not isinstance(text, str):
             raise TypeError("Text to tokenize must be a string.")
@@ -154,15 +159,13 @@ class FastWP(NaiveWP):
         return trie.tables.tokens_to_strs(ids)
 
     def tokenize_batch(self, texts: Sequence[str]) -> List[List[str]]:
+        """tokenize() of every text with one pass over their concatenation (lower-casing, splitting and matching on the device)."""
+        if not all(isinstance(t, str) for t in texts):
+            raise TypeError("Text to tokenize must be a string.")
         trie = self.vocab_trie
-        per_text = [self._chunks(t) for t in texts]
-        ids, tok_off, _ = trie.encoder.encode_words([c for cs in per_text for c in cs])
+        ids, cut = trie.encoder.encode_texts(texts)
         strs = trie.tables.tokens_to_strs(ids)
-        out, wi = [], 0
-        for cs in per_text:
-            out.append(strs[int(tok_off[wi]):int(tok_off[wi + len(cs)])])
-            wi += len(cs)
-        return out
+        return [strs[int(cut[k]):int(cut[k + 1])] for k in range(len(texts))]
 
     def load_resources(self, path: str) -> None:
         super().load_resources(path)

@@ -655,3 +655,25 @@ def test_naive_encoders_on_device_match_reference_on_random_cases(P, dev):
             assert tab.tokens_to_strs(ids) == naive, (case["vocab"], text)
             n_wp += 1
     assert n_bpe >= 20 and n_diff >= 1 and n_wp >= 500
+
+
+def test_tokenize_batch_equals_per_text_calls_for_all_four_classes(P, dev):
+    """The harness batch entry: one pass over the concatenated texts, cut per text on the device-reported
+    word positions; must equal tokenize() text by text and the reference's golden token lists."""
+    from subword_tokenizers_b200 import NaiveBPE, FastBPE, NaiveWP, FastWP, make_hf_tokenizer
+    from subword_tokenizers_b200.utils import WPTrie_E2E
+    lines = load_golden("pan_tadeusz.json.gz")
+    gold = load_golden("pan_tadeusz.tokens.json.gz")
+    hf = make_hf_tokenizer()
+    merges = [tuple(p) for p in load_golden("pretrained_bpe_merges.json.gz")]
+    vocab = set(load_golden("pretrained_wp_vocab.json.gz"))
+    nb = NaiveBPE(hf); nb.merges_list = merges
+    fb = FastBPE(hf); fb.merges_list = merges; fb._rebuild_ranks()
+    nw = NaiveWP(hf); nw.vocab = vocab
+    fw = FastWP(hf); fw.vocab = vocab; fw.vocab_trie = WPTrie_E2E(vocab)
+    texts = lines[:200] + ["", "   ", "ΟΔΥΣΣΕΥΣ", "x"]
+    for tok, key in ((nb, "NaiveBPE"), (fb, "FastBPE"), (nw, "NaiveWordPiece"), (fw, "FastWordPiece")):
+        got = tok.tokenize_batch(texts)
+        assert got[:200] == gold[key][:200], key
+        assert got[200:] == [tok.tokenize(t) for t in texts[200:]], key
+        assert got[200] == [] and got[201] == []
