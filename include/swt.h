@@ -173,6 +173,32 @@ int swt_pretok_write(const swt_pretok *p, const uint8_t *d_text, uint64_t n_byte
 /* d_word_src_out (n_words u32, may be NULL): byte position in the text at which each word starts, so that a caller who
  * concatenated many texts can cut the token stream per text (tokenize_batch; the harness row of SURVEY.md section 8f). */
 
+/* ---- word-type table for the trainers, built on the device ------------------------------------------- */
+/*
+ * swt_types_*  replaces  `word_freqs = Counter(words)` in first-occurrence order and the per-type symbol lists in front
+ * of the two merge loops (bpe.py:73-81, wordpiece.py:49-60), on the packed words that swt_pretok_write produced
+ * (SWT_PRETOK_BERT).  Types come out in FIRST-OCCURRENCE order (both trainers break ties by it).
+ *   swt_types_count   : hash-dedupes the words; d_status (8 x u32): [0] status (SWT_ERR_CAPACITY: more than max_types
+ *                       distinct words -- call again with a larger max_types), [1] n_types.
+ *   swt_types_write   : (same arena / workspace, untouched) per type: index of its first-occurrence word, frequency,
+ *                       character count, exclusive symbol offsets (n_types + 1); d_status [2]/[3] = total symbols lo/hi.
+ *                       Clears the two bitmaps.
+ *   swt_types_symbols : the code points of every type at its symbol offset, and the presence bitmaps (0x110000 bits
+ *                       each) of the characters seen in first / in later positions (the initial alphabet).
+ *   swt_types_map_symbols : code points -> symbol ids in place through caller-built dense tables (BPE: the same table
+ *                       twice; WordPiece: first-position and "##" tables), 0xFFFFFFFF for cp >= n_lut.
+ */
+size_t swt_types_workspace_bytes(uint64_t n_words, uint64_t max_types);
+int swt_types_count(const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words, uint64_t max_types, void *d_workspace,
+                    size_t workspace_bytes, uint32_t *d_status, void *stream);
+int swt_types_write(const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words, uint64_t max_types, void *d_workspace,
+                    size_t workspace_bytes, uint32_t n_types, uint32_t *d_type_word, int64_t *d_freq, uint32_t *d_n_chars,
+                    uint64_t *d_sym_off, uint32_t *d_first_bitmap, uint32_t *d_later_bitmap, uint32_t *d_status, void *stream);
+int swt_types_symbols(const uint8_t *d_arena, const uint32_t *d_word_off, const uint32_t *d_type_word, uint32_t n_types,
+                      const uint64_t *d_sym_off, uint32_t *d_cps_out, uint32_t *d_first_bitmap, uint32_t *d_later_bitmap, void *stream);
+int swt_types_map_symbols(uint32_t *d_cps_inout, uint64_t n_syms, const uint64_t *d_sym_off, uint32_t n_types, const uint32_t *d_lut_first,
+                          const uint32_t *d_lut_later, uint32_t n_lut, void *stream);
+
 /* ---- host-buffer entry points (what a non-Python integrator binds) ------------------------------- */
 /*
  * Same results as the device-pointer calls above, but inputs and outputs are HOST buffers:

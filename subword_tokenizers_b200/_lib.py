@@ -70,6 +70,12 @@ SIGNATURES = {
     "swt_pretok_count": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint64, c_vp, ctypes.c_size_t, c_vp, c_vp]),
     "swt_pretok_write": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint64, c_vp, ctypes.c_size_t, c_vp, ctypes.c_uint64, c_vp, c_vp,
                                         ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, c_vp, c_vp]),
+    "swt_types_workspace_bytes": (ctypes.c_size_t, [ctypes.c_uint64, ctypes.c_uint64]),
+    "swt_types_count": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint64, c_vp, ctypes.c_size_t, c_vp, c_vp]),
+    "swt_types_write": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint64, c_vp, ctypes.c_size_t, ctypes.c_uint32, c_vp, c_vp,
+                                       c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "swt_types_symbols": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "swt_types_map_symbols": (ctypes.c_int, [c_vp, ctypes.c_uint64, c_vp, ctypes.c_uint32, c_vp, c_vp, ctypes.c_uint32, c_vp]),
     "swt_pipeline_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(c_vp)]),
     "swt_pipeline_destroy": (None, [c_vp]),
     "swt_encode_host": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_uint64, c_vp, ctypes.c_uint64, c_vp,

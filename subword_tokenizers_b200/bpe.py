@@ -51,10 +51,16 @@ class NaiveBPE(SubwordTokenizer):
         if not isinstance(max_vocab, int):
             raise TypeError("Maximum vocabulary size must be an integer.")
         self.reset()
-        words = self._pre_tokenized_words(corpus)
-        self.train_on_words(words, max_vocab)
+        if self._device_pretok_ok():
+            from .device import device_train_types
+            self._train_on_types(device_train_types(corpus, wordpiece=False), max_vocab)   # pre-tokenization + counting on the GPU
+        else:
+            self.train_on_words(self._pre_tokenized_words(corpus), max_vocab)
 
     def train_on_words(self, words: Sequence[str], max_vocab: int, group=None) -> None:
+        self._train_on_types(P.TrainTypes(words), max_vocab, group)
+
+    def _train_on_types(self, types, max_vocab: int, group=None) -> None:
         """The merge loop on pre-tokenized words.  With torch.distributed initialised (world > 1) the
         word types are sharded across ranks and every rank returns the same merge list."""
         import time
@@ -62,7 +68,6 @@ class NaiveBPE(SubwordTokenizer):
         import torch.distributed as dist
         from .device import CudaTrainEngine, run_training_loop, shard_types
 
-        types = P.TrainTypes(words)
         self.vocab = set(types.alphabet)
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         rank = dist.get_rank(group) if world > 1 else 0

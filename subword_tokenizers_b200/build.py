@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libswt.so")
-SOURCES = ["api.cu", "bpe_encode.cu", "wp_encode.cu", "bpe_train.cu", "pipeline.cu", "pretok.cu"]
+SOURCES = ["api.cu", "bpe_encode.cu", "wp_encode.cu", "bpe_train.cu", "pipeline.cu", "pretok.cu", "types.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--shared", "-cudart", "shared",

@@ -360,6 +360,86 @@ class WpEncoder(_Encoder):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# word-type table of a corpus, built on the device (pre-tokenization + dedupe in front of the trainers)
+# ------------------------------------------------------------------------------------------------------------
+
+def device_train_types(corpus: Sequence[str], wordpiece: bool):
+    """Corpus (list of texts) -> packing.TrainTypes / packing.WpTrainTypes with the same content as the host constructors
+    on ``pre_tokenize_str(example.lower())`` words, computed on the GPU: BERT pre-tokenization (swt_pretok_*), hash dedupe in
+    first-occurrence order with frequencies (swt_types_*), symbol ids.  (WordPiece symbol ids are numbered by code point
+    instead of by first occurrence; the trainer's result does not depend on the numbering.)"""
+    _lib.require_cuda()
+    lib = _lib.load()
+    data = b"\n".join(P.encode_utf8(t) for t in corpus)
+    dev = torch.device("cuda", current_device())
+    d_arena, d_off, n_words = Pretokenizer.get(mode=_lib.PRETOK_BERT).split_text(data)
+    sp = _stream_ptr()
+    d_status = torch.empty(8, dtype=torch.int32, device=dev)
+    max_types = max(1024, min(n_words, 1 << 22))
+    while True:
+        ws = torch.empty(lib.swt_types_workspace_bytes(n_words, max_types), dtype=torch.uint8, device=dev)
+        check(lib.swt_types_count(d_arena.data_ptr(), d_off.data_ptr(), n_words, max_types, ws.data_ptr(), ws.numel(),
+                                  d_status.data_ptr(), sp), "swt_types_count")
+        st = d_status.cpu().numpy().astype(np.uint32)
+        if st[0] == 0 and int(st[1]) <= max_types:
+            break
+        if max_types >= n_words:
+            raise SwtError("swt_types_count status %d" % int(st[0]))
+        max_types = min(n_words, max_types * 8)
+    n_types = int(st[1])
+    d_type_word = torch.empty(max(n_types, 1), dtype=torch.int32, device=dev)
+    d_freq = torch.empty(max(n_types, 1), dtype=torch.int64, device=dev)
+    d_nch = torch.empty(max(n_types, 1), dtype=torch.int32, device=dev)
+    d_soff = torch.empty(n_types + 1, dtype=torch.int64, device=dev)
+    d_bm1 = torch.empty(0x110000 // 32, dtype=torch.int32, device=dev)
+    d_bm2 = torch.empty(0x110000 // 32, dtype=torch.int32, device=dev)
+    check(lib.swt_types_write(d_arena.data_ptr(), d_off.data_ptr(), n_words, max_types, ws.data_ptr(), ws.numel(), n_types,
+                              d_type_word.data_ptr(), d_freq.data_ptr(), d_nch.data_ptr(), d_soff.data_ptr(), d_bm1.data_ptr(),
+                              d_bm2.data_ptr(), d_status.data_ptr(), sp), "swt_types_write")
+    st = d_status.cpu().numpy().astype(np.uint32)
+    n_syms = int(st[2]) | (int(st[3]) << 32)
+    d_syms = torch.empty(max(n_syms, 1), dtype=torch.int32, device=dev)
+    check(lib.swt_types_symbols(d_arena.data_ptr(), d_off.data_ptr(), d_type_word.data_ptr(), n_types, d_soff.data_ptr(),
+                                d_syms.data_ptr(), d_bm1.data_ptr(), d_bm2.data_ptr(), sp), "swt_types_symbols")
+    first = np.flatnonzero(np.unpackbits(d_bm1.cpu().numpy().view(np.uint8), bitorder="little"))
+    later = np.flatnonzero(np.unpackbits(d_bm2.cpu().numpy().view(np.uint8), bitorder="little"))
+    if wordpiece:
+        out = object.__new__(P.WpTrainTypes)
+        out.init_syms = [chr(c) for c in first] + ["##" + chr(c) for c in later]
+        ids_first, ids_later = (first, np.arange(len(first))), (later, len(first) + np.arange(len(later)))
+    else:
+        out = object.__new__(P.TrainTypes)
+        alpha = np.union1d(first, later)
+        out.alphabet = [chr(c) for c in alpha]
+        ids_first = ids_later = (alpha, np.arange(len(alpha)))
+    n_lut = int(max(first.max() if len(first) else 0, later.max() if len(later) else 0)) + 1
+    luts = []
+    for cps, ids in (ids_first, ids_later):
+        lut = np.full(n_lut, 0xFFFFFFFF, dtype=np.uint32)
+        lut[cps] = ids
+        luts.append(torch.from_numpy(lut.view(np.int32)).to(dev))
+    check(lib.swt_types_map_symbols(d_syms.data_ptr(), n_syms, d_soff.data_ptr(), n_types, luts[0].data_ptr(), luts[1].data_ptr(),
+                                    n_lut, sp), "swt_types_map_symbols")
+    out.freq = d_freq[:n_types].cpu().numpy()
+    out.off = d_soff.cpu().numpy().view(np.uint64)
+    out.syms = d_syms[:n_syms].cpu().numpy().view(np.uint32)
+    # the type strings are only materialised when somebody asks for them
+    h_arena = h_off = None
+    type_word = d_type_word[:n_types].cpu().numpy().view(np.uint32)
+
+    def type_strings():
+        nonlocal h_arena, h_off
+        if h_arena is None:
+            h_arena, h_off = d_arena.cpu().numpy(), d_off.cpu().numpy().view(np.uint32)
+        return [P.decode_utf8(h_arena[int(h_off[w]):int(h_off[w + 1])].tobytes()) for w in type_word]
+    out._type_strings = type_strings
+    out._n_types = n_types
+    if wordpiece:
+        out.init_cps, out.init_off = P.pack_strings_as_cps(out.init_syms)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
 # HP-3 trainer
 # ------------------------------------------------------------------------------------------------------------
 

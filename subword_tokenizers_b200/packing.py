@@ -310,9 +310,16 @@ class TrainTypes:
             self.syms = np.zeros(0, dtype=np.uint32)
         self.off = off
 
+    def __getattr__(self, name):
+        # instances built on the device (device.device_train_types) materialise the type strings on demand
+        if name == "types" and "_type_strings" in self.__dict__:
+            self.types = self._type_strings()
+            return self.types
+        raise AttributeError(name)
+
     @property
     def n_types(self) -> int:
-        return len(self.types)
+        return len(self.freq)
 
     @property
     def n_alpha(self) -> int:
@@ -354,6 +361,12 @@ class WpTrainTypes:
         self.syms = np.array(syms, dtype=np.uint32)
         self.off = np.array(off, dtype=np.uint64)
         self.init_cps, self.init_off = pack_strings_as_cps(self.init_syms)
+
+    def __getattr__(self, name):
+        if name == "types" and "_type_strings" in self.__dict__:
+            self.types = self._type_strings()
+            return self.types
+        raise AttributeError(name)
 
     def vocab_from_merges(self, left, right, new) -> List[str]:
         strs: List[str] = list(self.init_syms)

@@ -31,18 +31,25 @@ class NaiveWP(SubwordTokenizer):
         if not isinstance(max_vocab, int):
             raise TypeError("max_vocab must be an int.")
         self.reset()
-        self.train_on_words(self._pre_tokenized_words(corpus), max_vocab)
+        if self._device_pretok_ok():
+            from .device import device_train_types
+            self._train_on_types(device_train_types(corpus, wordpiece=True), max_vocab)   # pre-tokenization + counting on the GPU
+        else:
+            self.train_on_words(self._pre_tokenized_words(corpus), max_vocab)
 
     def train_on_words(self, words: Sequence[str], max_vocab: int) -> None:
+        from . import packing as P
+        self._train_on_types(P.WpTrainTypes(words), max_vocab)
+
+    def _train_on_types(self, types, max_vocab: int) -> None:
         """The merge loop of wordpiece.py:68-102 on the GPU (SWT_TRAIN_WP mode of the trainer): score
         pair_freq / (freq_a * freq_b), first-inserted pair on ties, merged token a + b[2:]."""
         import numpy as np
         import torch
         from . import _lib, packing as P
         from .device import CudaTrainEngine, run_training_loop
-        types = P.WpTrainTypes(words)
         self.vocab = set(types.init_syms)
-        max_len = int(np.diff(types.off.astype(np.int64)).max()) if len(types.types) else 1
+        max_len = int(np.diff(types.off.astype(np.int64)).max()) if len(types.freq) else 1
         engine = CudaTrainEngine(types.syms, types.off, types.freq, len(types.init_syms), max_vocab, len(types.init_syms),
                                  max_len + 2, 0, 0, 1, mode=_lib.TRAIN_WP, init_cps=types.init_cps, init_off=types.init_off)
         left, right, new, count, state = run_training_loop(engine, 1)
@@ -58,7 +65,7 @@ class NaiveWP(SubwordTokenizer):
             engine, types, strs = self._train_result
             syms, lens = engine.read_corpus()
             out = []
-            for k in range(len(types.types)):
+            for k in range(len(types.freq)):
                 s0 = int(types.off[k])
                 out.append(([strs[i] for i in syms[s0:s0 + int(lens[k])]], int(types.freq[k])))
             self._corpus_cache = out

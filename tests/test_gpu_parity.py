@@ -677,3 +677,47 @@ def test_tokenize_batch_equals_per_text_calls_for_all_four_classes(P, dev):
         assert got[:200] == gold[key][:200], key
         assert got[200:] == [tok.tokenize(t) for t in texts[200:]], key
         assert got[200] == [] and got[201] == []
+
+
+# ---- word-type table built on the device (pre-tokenization + dedupe in front of the trainers) ------------------------------
+def test_device_train_types_equal_host_types(P, dev):
+    from tokenizers import pre_tokenizers
+    pre = pre_tokenizers.BertPreTokenizer()
+    corpora = [load_golden("train-5K.json.gz"), ["a b a", "B, a! ΣΑΣ ςσ", "", "İ i̇"], ["x"], [" "], []]
+    rng = np.random.default_rng(3)
+    alphabet = list("abcAB .,ąŁ") + ["\n", "中", "\U00010400"]
+    corpora += [["".join(alphabet[i] for i in rng.integers(0, len(alphabet), 200)) for _ in range(50)]]
+    for corpus in corpora:
+        words = [w for ex in corpus for w, _ in pre.pre_tokenize_str(ex.lower())]
+        host = P.TrainTypes(words)
+        got = dev.device_train_types(corpus, wordpiece=False)
+        assert got.alphabet == host.alphabet
+        assert np.array_equal(got.freq, host.freq) and np.array_equal(got.off, host.off) and np.array_equal(got.syms, host.syms)
+        assert got.types == host.types
+        hw = P.WpTrainTypes(words)
+        gw = dev.device_train_types(corpus, wordpiece=True)
+        assert sorted(gw.init_syms) == sorted(hw.init_syms)
+        assert np.array_equal(gw.freq, hw.freq) and np.array_equal(gw.off, hw.off)
+        assert [gw.init_syms[i] for i in gw.syms] == [hw.init_syms[i] for i in hw.syms]
+
+
+def test_train_from_corpus_on_device_matches_reference(P, dev):
+    """train(corpus) with pre-tokenization, type counting and the merge loop all on the GPU: the reference's merge lists /
+    vocabularies on its randomized corpora and on train-5K at max_vocab 1000."""
+    from subword_tokenizers_b200 import NaiveBPE, NaiveWP, make_hf_tokenizer
+    hf = make_hf_tokenizer()
+    cases = load_golden("ref_random_cases.json.gz")
+    nb, nw = NaiveBPE(hf), NaiveWP(hf)
+    assert nb._device_pretok_ok()
+    for case in cases["bpe_train"]:
+        nb.train(case["corpus"], case["max_vocab"])
+        assert [list(m) for m in nb.merges_list] == [list(m) for m in case["merges"]]
+        assert len(nb.vocab) == case["vocab_size"]
+    for case in cases["wp_train"]:
+        nw.train(case["corpus"], case["max_vocab"])
+        assert nw.vocab == set(case["vocab"])
+    corpus = load_golden("train-5K.json.gz")
+    nb.train(corpus, 1000)
+    assert [list(m) for m in nb.merges_list] == load_golden("ref_bpe_train5k_v1000_merges.json.gz")
+    nw.train(corpus, 1000)
+    assert nw.vocab == set(load_golden("ref_wp_train5k_v1000_vocab.json.gz"))
