@@ -16,7 +16,7 @@ A "step" is one pass of the FastWP encode kernel over the whole stream.
   roofline   algorithmic bytes (arena + 4 B/word offset read, 4 B/token + 4 B/word offset written) per launch
              / mean kernel time, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
   cpu_baseline  the C oracle port of the reference's FastWP path on the host cores, bounded sample.
-  also       secondary numbers of the other two hot paths (FastBPE tokenize MB/s, BPE train merges/s).
+  also       secondary numbers: FastBPE tokenize MB/s, device pre-tokenization MB/s, BPE / WordPiece train merges/s.
 
 --impl reference: times the CPU implementation of the same path (oracle C port -- the reference itself is
 pure Python and cannot travel to the GPU box) with all host threads on a bounded sample of the same stream.
@@ -451,6 +451,30 @@ def secondary_numbers(dev, stream, d_arena, d_off, n_words, n_bytes):
     out["fastbpe_tokenize"] = {"value": n_bytes / (ms / 1e3) / 1e6, "unit": "MB/s", "merges": len(merges), "kernel_ms": ms,
                                "n_tokens": nt, "roofline_frac": alg / (ms / 1e3) / 1e9 / peak}
     del ids, tok, ws
+    # device pre-tokenization (lower-casing + whitespace split, FastWP) over the raw-text form of the stream, resident
+    lib = device._lib.load()
+    d_text, n_text = device_text(d_arena, d_off, n_words)
+    pt = device.Pretokenizer.get()
+    pws = torch.empty(lib.swt_pretok_workspace_bytes(n_text), dtype=torch.uint8, device=dev)
+    o_arena = torch.empty(n_bytes + 16, dtype=torch.uint8, device=dev)
+    o_off = torch.empty(n_words + 2, dtype=torch.int32, device=dev)
+    sp = torch.cuda.current_stream().cuda_stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_cnt = t_wr = 0.0
+    for it in range(4):
+        ev[0].record()
+        device.check(lib.swt_pretok_count(pt._handle, d_text.data_ptr(), n_text, pws.data_ptr(), pws.numel(), status.data_ptr(), sp))
+        ev[1].record()
+        device.check(lib.swt_pretok_write(pt._handle, d_text.data_ptr(), n_text, pws.data_ptr(), pws.numel(), o_arena.data_ptr(), n_bytes,
+                                          o_off.data_ptr(), None, n_words + 2, n_words, n_bytes, status.data_ptr(), sp))
+        ev[2].record(); torch.cuda.synchronize()
+        if it:
+            t_cnt += ev[0].elapsed_time(ev[1]) / 3; t_wr += ev[1].elapsed_time(ev[2]) / 3
+    same = bool(torch.equal(o_arena[:n_bytes], d_arena[:n_bytes]) and torch.equal(o_off[:n_words + 1], d_off[:n_words + 1]))
+    out["fastwp_pretokenize"] = {"value": n_text / ((t_cnt + t_wr) / 1e3) / 1e6, "unit": "MB/s of raw text", "text_bytes": n_text,
+                                 "count_ms": t_cnt, "write_ms": t_wr, "reproduces_the_packed_stream": same,
+                                 "workload": "text.lower().split() on the device over the stream's words joined by spaces"}
+    del d_text, pws, o_arena, o_off
     # BPE training, config-1 corpus at max_vocab 8000
     from subword_tokenizers_b200.hf_shim import make_hf_tokenizer
     pre = make_hf_tokenizer().backend_tokenizer.pre_tokenizer

@@ -119,3 +119,36 @@ def test_naive_wp_host_encoder_matches_reference(hf_tokenizer, random_cases):
     nw.vocab = set(load_golden("pretrained_wp_vocab.json.gz"))
     lines = load_golden("pan_tadeusz.json.gz")
     assert [host_tokenize(l) for l in lines] == load_golden("pan_tadeusz.tokens.json.gz")["NaiveWordPiece"]
+
+
+def test_pretok_tables_come_from_the_running_interpreter():
+    """Tables of the device pre-tokenizer (packing.PretokTables): generated from CPython's own str.lower / str.isspace."""
+    from subword_tokenizers_b200 import packing as P
+    t = P.PretokTables.get()
+    assert {c for c in range(0x110000) if chr(c).isspace()} == set(P.PY_SPACE_CPS)
+    for ch in "ŁÉΩЖ\U00010400ẞ\u212a\u2126":                      # (ASCII is folded by SWAR arithmetic in the kernel, not by the table)
+        assert int(t.lower_map[ord(ch)]) == ord(ch.lower())
+    e = int(t.lower_map[0x130])
+    assert e & P.LOWER_MULTI and [int(x) for x in t.multi[(e & 0xFFFFF):(e & 0xFFFFF) + 3]] == [2, 0x69, 0x307]
+    assert int(t.lower_map[0x3A3]) == P.LOWER_SIGMA
+    assert all(int(t.lower_map[c]) == c for c in (0x142, 0x4E2D, 0x20AC))
+    cased, ign = (np.unpackbits(b, bitorder="little") for b in t.sigma_bitmaps())
+    assert cased[ord("a")] and cased[ord("Σ")] and not cased[ord("1")] and not cased[ord(" ")]
+    assert ign[ord("'")] and ign[0x301] and ign[ord(".")] and not ign[ord("a")] and not ign[ord(" ")] and not ign[ord("-")]
+    assert cased[0x2B0] and ign[0x2B0]                                   # MODIFIER LETTER SMALL H: cased and case-ignorable
+
+
+def test_bert_class_table_matches_the_tokenizers_library(hf_tokenizer):
+    """data/bert_pretok_classes.json was probed from the Rust BertPreTokenizer; it must agree with the library installed here."""
+    from subword_tokenizers_b200 import packing as P
+    pre = hf_tokenizer.backend_tokenizer.pre_tokenizer
+    assert P.bert_pretokenizer_matches(pre)
+    cls = P.load_bert_classes()
+    assert sum(b - a + 1 for a, b in cls["punct"]) == 726 and sum(b - a + 1 for a, b in cls["space"]) == 25
+    m = P.PretokTables.get().bert_lower_map()
+    assert m[ord("«")] & P.LOWER_PUNCT and m[0x3001] & P.LOWER_PUNCT and not (m[ord("é")] & P.LOWER_PUNCT)
+
+    class Other:                                                           # any other pre-tokenizer keeps the host path
+        def pre_tokenize_str(self, s):
+            return [(w, (0, 0)) for w in s.split()]
+    assert not P.bert_pretokenizer_matches(Other())
