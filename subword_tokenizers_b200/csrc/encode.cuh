@@ -224,7 +224,7 @@ __device__ __forceinline__ bool memo_publish(const EncodeWorkspace &ws, uint32_t
     MemoEntry *e = ws.memo + slot;
     if (ntok > (uint32_t)kMemoTokens || h6 > 0xFFFFFFu) { st_release_u32(&e->meta, 0xFFFFFFFFu); return false; }
     e->tail_a = key.tail_a; e->tail_b = key.tail_b; e->tail_last = key.tail_last;
-    bool narrow = ntok <= 14 && h6 == 0 && key.nbytes <= 15;            // servable by the one-load fast path?
+    bool narrow = ntok <= 14 && h6 == 0;                                // servable by the one-load fast path?
     for (uint32_t k = 0; k < ntok; ++k) { e->tok[k] = buf[k]; narrow = narrow && buf[k] < 65536u; }
     if (narrow) for (uint32_t k = 0; k < ntok; ++k) e->ids16[k] = (uint16_t)buf[k];
     st_release_u32(&e->meta, (ntok + 1) | (h6 << 8));                   // release: everything above is visible first
@@ -374,12 +374,13 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
                 kind[j] = kWordNone; ntok[j] = 0; slot[j] = 0; slow[j] = false;
                 kw[j] = ew[j] = make_uint4(0, 0, 0, 0);
                 is_long[j] = nb[j] != 0xFFFFFFFFu && nb[j] > (uint32_t)kShortBytes;
-                fastj[j] = use_memo && nb[j] >= 1 && nb[j] <= 15 && (uint64_t)b0s[j] + 24 <= arena_end;
+                // words of 16..32 bytes take the same first probe on their 15-byte prefix (length nibble 0); their tail is checked below
+                fastj[j] = use_memo && nb[j] >= 1 && nb[j] <= (uint32_t)kShortBytes && (uint64_t)b0s[j] + 40 <= arena_end;
                 a0[j] = a1[j] = a2[j] = a3[j] = a4[j] = 0;
                 if (fastj[j]) {                                   // the (up to five) aligned 32-bit words that hold the word
                     const uintptr_t a = (uintptr_t)(arena + b0s[j]);
                     const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
-                    const uint32_t span = nb[j] + (uint32_t)(a & 3);
+                    const uint32_t span = min(nb[j], 15u) + (uint32_t)(a & 3);
                     a0[j] = __ldg(q);
                     a1[j] = ldg_u32_if(q + 1, span > 4); a2[j] = ldg_u32_if(q + 2, span > 8);
                     a3[j] = ldg_u32_if(q + 3, span > 12); a4[j] = ldg_u32_if(q + 4, span > 16);
@@ -388,12 +389,12 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
 #pragma unroll
             for (int j = 0; j < kWordsPerThread; ++j) {
                 if (fastj[j]) {
-                    const uint32_t sh = (uint32_t)((uintptr_t)(arena + b0s[j]) & 3) * 8, n = nb[j];
+                    const uint32_t sh = (uint32_t)((uintptr_t)(arena + b0s[j]) & 3) * 8, n = min(nb[j], 15u);
                     uint32_t w0 = __funnelshift_r(a0[j], a1[j], sh), w1 = __funnelshift_r(a1[j], a2[j], sh);
                     uint32_t w2 = __funnelshift_r(a2[j], a3[j], sh), w3 = __funnelshift_r(a3[j], a4[j], sh);
                     // zero the bytes at and beyond n, put the length into the top byte (layout of MemoEntry::lo/hi)
                     w0 &= low_bytes_mask((int)n); w1 &= low_bytes_mask((int)n - 4); w2 &= low_bytes_mask((int)n - 8);
-                    w3 = (w3 & low_bytes_mask((int)n - 12)) | (n << 24);
+                    w3 = (w3 & low_bytes_mask((int)n - 12)) | ((nb[j] <= 15u ? n : 0u) << 24);
                     kw[j] = make_uint4(w0, w1, w2, w3);
                     slot[j] = memo_hash4(w0, w1, w2, w3) & ws.memo_mask;
                     ew[j] = ld_ca_u32x4(ws.memo + slot[j]);      // ONE scattered load per word: key + pub nibble
@@ -414,6 +415,14 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
                     same = ew[j].x == kw[j].x && ew[j].y == kw[j].y && ew[j].z == kw[j].z && ((ew[j].w ^ kw[j].w) & 0x0FFFFFFFu) == 0;
                 }
                 hit = same && (ew[j].w >> 28) != 0;                  // pub nibble: ids16[] valid, n_tokens + 1
+                if (hit && nb[j] > 15u) {                            // rare: compare bytes 15.. with the tail stored in the entry
+                    MemoKey key;
+                    memo_key(arena, b0s[j], nb[j], arena_end, key);
+                    const MemoEntry *e = ws.memo + slot[j];
+                    unsigned long long ta, tb;
+                    ld_ca_u64x2(&e->tail_a, ta, tb);
+                    hit = ta == key.tail_a && tb == key.tail_b && ld_ca_u32(&e->tail_last) == key.tail_last;
+                }
             }
             if (hit) { kind[j] = kWordHit16; ntok[j] = (ew[j].w >> 28) - 1; }
             else slow[j] = true;
