@@ -20,6 +20,7 @@
 // Multi-GPU: types are sharded; L/R/ZZ/M are summed across ranks (NCCL all-reduce by the caller) and every
 // rank folds the same global deltas into its replica of the table, so replicas stay identical.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -59,7 +60,7 @@ struct ArgPart { long long count; uint64_t key; uint32_t n_tied; uint32_t pad; }
 struct TrainDev {
     // sizes
     uint64_t n_types, n_slots, slot_base;
-    uint32_t n_alpha, vmax, record_cap, world, rank, n_parts, mode;
+    uint32_t n_alpha, vmax, record_cap, world, rank, n_parts, mode, tie_chunk;
     long long max_vocab;
     uint64_t char_cap, str_ht_cap;
     // arrays
@@ -351,7 +352,9 @@ __global__ void __launch_bounds__(256) k_argmax_full(TrainDev d) {
 // ---- select: tie-break scan.  Among the pairs whose count equals the maximum, the winner is the one whose first
 // occurrence comes first in (type, position) order == ascending slot order.  Chunks are handed out in ascending
 // order; a chunk that starts after an already found position is skipped, so the scan stops early.
-constexpr uint32_t kTieChunk = 512;    // 2 positions per thread: a chunk is one L2 round trip deep
+// chunk of the tie scan (TrainDev::tie_chunk): 512 slots = 2 positions per thread, one L2 round trip deep.  Larger chunks make
+// every thread issue its table probes one after the other: 10 M types, 31,955 merges: 512 -> 4.38 s, 2048 -> 4.56 s, 4096 -> 4.87 s,
+// 16384 -> 7.50 s; train-5K: 512 -> 0.28 s, 4096 -> 0.69 s.
 __global__ void __launch_bounds__(256) k_tie_scan(TrainDev d) {
     TrainState *st = d.st;
     if (st->halt || st->n_tied <= 1) return;
@@ -363,15 +366,15 @@ __global__ void __launch_bounds__(256) k_tie_scan(TrainDev d) {
     for (;;) {
         if (threadIdx.x == 0) {
             s_chunk = atomicAdd(&st->tie_ticket, 1u); s_best = kNoPos;
-            const uint64_t c = (uint64_t)s_chunk * kTieChunk;
+            const uint64_t c = (uint64_t)s_chunk * d.tie_chunk;
             // stop when past the end, or when an earlier chunk already holds an occurrence
             s_stop = (c >= d.n_slots) || (*(volatile uint64_t *)&st->best_pos < d.slot_base + c);
         }
         __syncthreads();
         if (s_stop) break;
-        const uint64_t c0 = (uint64_t)s_chunk * kTieChunk;
+        const uint64_t c0 = (uint64_t)s_chunk * d.tie_chunk;
         uint64_t mine = kNoPos;
-        for (uint64_t i = c0 + threadIdx.x; i < c0 + kTieChunk && i + 1 < d.n_slots; i += blockDim.x) {
+        for (uint64_t i = c0 + threadIdx.x; i < c0 + d.tie_chunk && i + 1 < d.n_slots; i += blockDim.x) {
             const uint32_t s = d.sym[i], nx = d.sym[i + 1];
             if (s == kHole || (nx & kStart)) continue;
             const uint64_t key = ((uint64_t)(s & ~kStart) << 32) | nx;
@@ -618,6 +621,8 @@ static size_t train_layout(const swt_bpe_train_config *cfg, void *base, TrainDev
     d->n_types = cfg->n_types_local; d->n_slots = cfg->n_slots_local; d->slot_base = cfg->slot_base;
     d->n_alpha = cfg->n_alpha; d->vmax = vmax; d->record_cap = cfg->record_cap; d->world = cfg->world_size; d->rank = cfg->rank;
     d->max_vocab = cfg->max_vocab; d->n_parts = kNumSMs * 4;
+    d->tie_chunk = 512;                                       // measured best from 23 k to 10 M types (profiles/README.md)
+    if (const char *e = getenv("SWT_TIE_CHUNK")) { const long v = atol(e); if (v >= 256 && v <= 65536) d->tie_chunk = (uint32_t)v; }   // experiments
     d->char_cap = char_cap_of(cfg); d->str_ht_cap = next_pow2(4ull * vmax);
     d->st = cv.take<TrainState>(1);
     d->sym = cv.take<uint32_t>(d->n_slots + 8);

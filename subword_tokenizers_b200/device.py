@@ -28,6 +28,23 @@ def current_device() -> int:
     return torch.cuda.current_device()
 
 
+_PIPELINES: "dict[Tuple[int, int], c_vp]" = {}       # (device, batch_bytes) -> swt_pipeline*, most recently used last
+
+
+def _pipeline_for(device: int, batch_bytes: int):
+    """Pipelines hold no table state, so one per (device, batch size) serves every encoder; at most three sizes are kept."""
+    lib = _lib.load()
+    key = (device, batch_bytes)
+    h = _PIPELINES.pop(key, None)
+    if h is None:
+        while len(_PIPELINES) >= 3:
+            lib.swt_pipeline_destroy(_PIPELINES.pop(next(iter(_PIPELINES))))
+        h = c_vp(None)
+        check(lib.swt_pipeline_create(device, batch_bytes, ctypes.byref(h)), "swt_pipeline_create")
+    _PIPELINES[key] = h
+    return h
+
+
 class _Encoder:
     """Shared encode plumbing: words -> arena on device -> libswt encode -> token ids (+ offsets)."""
 
@@ -37,8 +54,6 @@ class _Encoder:
 
     def __init__(self):
         self._handle = c_vp(None)
-        self._pipeline = c_vp(None)
-        self._pipeline_batch = 0
 
     @property
     def _pretok_mode(self) -> int:
@@ -104,14 +119,8 @@ class _Encoder:
 
     # -- host-buffer pipeline (the e2e path) --------------------------------------------------------------------
     def pipeline(self, batch_bytes: int = 64 << 20):
-        lib = _lib.load()
-        if not self._pipeline or self._pipeline_batch != batch_bytes:
-            if self._pipeline:
-                lib.swt_pipeline_destroy(self._pipeline)
-            h = c_vp(None)
-            check(lib.swt_pipeline_create(current_device(), batch_bytes, ctypes.byref(h)), "swt_pipeline_create")
-            self._pipeline, self._pipeline_batch = h, batch_bytes
-        return self._pipeline
+        """The staging pipeline (device buffers + streams) for this batch size; shared by all encoders of the process."""
+        return _pipeline_for(current_device(), batch_bytes)
 
     def encode_host(self, h_arena: torch.Tensor, h_off: torch.Tensor, h_out_ids: torch.Tensor,
                     h_out_tok_off: Optional[torch.Tensor], batch_bytes: int = 64 << 20) -> Tuple[int, int]:
@@ -187,10 +196,6 @@ class _Encoder:
         return self._encode_text_resident(text, return_offsets)
 
     def close(self):
-        lib = _lib.load()
-        if self._pipeline:
-            lib.swt_pipeline_destroy(self._pipeline)
-            self._pipeline = c_vp(None)
         self._destroy()
 
     def _destroy(self):
