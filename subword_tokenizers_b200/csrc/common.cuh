@@ -36,10 +36,6 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return x;
 }
-__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
-    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-    return x;
-}
 static inline uint64_t next_pow2(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -66,57 +62,6 @@ __device__ __forceinline__ uint32_t utf8_decode(const uint8_t *p, uint32_t avail
     if (c < 0xF0u && avail >= 3) { adv = 3; return ((c & 0x0Fu) << 12) | ((p[1] & 0x3Fu) << 6) | (p[2] & 0x3Fu); }
     if (avail >= 4) { adv = 4; return ((c & 0x07u) << 18) | ((p[1] & 0x3Fu) << 12) | ((p[2] & 0x3Fu) << 6) | (p[3] & 0x3Fu); }
     adv = 1; return c;
-}
-
-// ---- single-pass tile prefix (decoupled look-back) ------------------------------------------------
-// One 64-bit word per tile: [63:62] status, [61:0] value.  Tiles are numbered by an atomic ticket so
-// that every predecessor of a running tile is itself running or finished (no deadlock).
-constexpr uint64_t kTileInvalid = 0ull, kTileAggregate = 1ull, kTilePrefix = 2ull;
-constexpr uint64_t kTileValueMask = (1ull << 62) - 1;
-
-// tile states carry status and value in ONE 64-bit word, so relaxed (L2-served) accesses are enough
-__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
-    uint64_t v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t *p) {
-    uint64_t v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// Called by ONE thread of the tile. Publishes this tile's aggregate and returns the exclusive prefix
-// (sum of the aggregates of all earlier tiles).  *err is set if a predecessor never shows up.
-__device__ inline uint64_t tile_exclusive_prefix(uint64_t *tile_state, uint32_t tile, uint64_t aggregate, uint32_t *err) {
-    if (tile == 0) {
-        st_release_u64(&tile_state[0], (kTilePrefix << 62) | aggregate);
-        return 0;
-    }
-    st_release_u64(&tile_state[tile], (kTileAggregate << 62) | aggregate);
-    uint64_t running = 0;
-    int64_t p = (int64_t)tile - 1;
-    uint64_t spins = 0;
-    while (p >= 0) {
-        uint64_t s = ld_acquire_u64(&tile_state[p]);
-        uint64_t st = s >> 62;
-        if (st == kTileInvalid) {
-            if (++spins > (1ull << 26)) { atomicExch(err, (uint32_t)SWT_ERR_INTERNAL); break; }   // never hang the GPU
-            __nanosleep(100);
-            continue;
-        }
-        running += s & kTileValueMask;
-        if (st == kTilePrefix) break;
-        --p;
-    }
-    st_release_u64(&tile_state[tile], (kTilePrefix << 62) | ((running + aggregate) & kTileValueMask));
-    return running;
 }
 
 // block-wide exclusive scan of one u32 per thread (blockDim.x <= 1024, multiple of 32);

@@ -1,4 +1,4 @@
-// encode.cuh -- the tile kernel shared by the two tokenize paths (HP-1 FastBPE, HP-2 FastWP).
+// encode.cuh -- the tile kernels shared by all encoders (HP-1 FastBPE, HP-2 FastWP, and the NaiveBPE / NaiveWP encoders).
 //
 // Data flow of one encode call (north-star subsystem 1: packed word-offset/byte arena).  Tile = 64 consecutive words per
 // WARP (2 per lane), tiles assigned round-robin to a persistent grid; warps never synchronise with each other.
@@ -94,11 +94,6 @@ __device__ __forceinline__ uint2 ld_cg_u32x2(const void *p) {
     asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ uint4 ld_cg_u32x4(const void *p) {
-    uint4 v;
-    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
 // L1-cached variants for the FAST path.  Hot word types (Zipf) then hit the 100+ KB L1 instead of going to L2.  This is
 // safe although the memo is written during the launch: a key never changes once set and meta goes 0 -> final exactly
 // once, after the ids of the same sector were written (release); L1 fills are whole 32-byte sectors.  A stale L1 sector can
@@ -112,24 +107,13 @@ __device__ __forceinline__ uint4 ld_ca_u32x4(const void *p) {
     asm volatile("ld.global.ca.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ uint2 ld_ca_u32x2(const void *p) {
-    uint2 v;
-    asm volatile("ld.global.ca.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ uint32_t ld_ca_u32(const void *p) {
     uint32_t v;
     asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// meta is read with a STRONG RELAXED load served at L2, not an acquire: ld.acquire.gpu compiles to LDG + CCTL.IVALL
-// (a full L1 invalidate per probe).  Ordering comes from the writer's release (ids are performed at L2 before meta)
-// plus the reader's control dependency (ids are loaded, at L2, only after a valid meta has been observed).
-__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
+// (no acquire loads anywhere: ld.acquire.gpu compiles to LDG + CCTL.IVALL, a full L1 invalidate per probe.  Ordering comes from the
+// writer's release -- ids are performed at L2 before meta / the pub nibble -- plus the reader's control dependency.)
 __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
