@@ -151,13 +151,6 @@ class FastWP(NaiveWP):
         super().train(corpus, max_vocab)
         self.vocab_trie = WPTrie_E2E(self.vocab)
 
-    @staticmethod
-    def _chunks(text: str) -> List[str]:
-        # s = text.lower() + " " (wordpiece.py:248); whitespace (Python str.isspace, :268) only ever separates
-        # segments, so the device works on the whitespace-free chunks.  str.split() splits on exactly the
-        # characters for which str.isspace() is true.
-        return text.lower().split()
-
     def tokenize(self, text):
         if not isinstance(text, str):
             raise TypeError("Text to tokenize must be a string.")
