@@ -27,7 +27,7 @@ for it in range(4):
     device.check(lib.swt_pretok_count(pt._handle, d_text.data_ptr(), n_text, ws.data_ptr(), ws.numel(), st.data_ptr(), sp))
     ev[1].record()
     device.check(lib.swt_pretok_write(pt._handle, d_text.data_ptr(), n_text, ws.data_ptr(), ws.numel(), out_arena.data_ptr(), n_text,
-                                      out_off.data_ptr(), n_words + 2, n_words, int(d_arena.numel()), st.data_ptr(), sp))
+                                      out_off.data_ptr(), None, n_words + 2, n_words, int(d_arena.numel()), st.data_ptr(), sp))
     ev[2].record(); torch.cuda.synchronize()
     print("pretok count %.3f ms  write %.3f ms  (%d text bytes, %d words)" % (ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), n_text, n_words))
 s = st.cpu().numpy()
