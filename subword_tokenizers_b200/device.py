@@ -156,10 +156,28 @@ class _Encoder:
               "swt_tokenize_text_host")
         return int(nt.value), int(nw.value), int(h6.value)
 
+    BATCH_TEXT_BYTES = 1 << 30            # texts are concatenated up to this many bytes per device pass
+
     def encode_texts(self, texts: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
-        """tokenize() of many texts in ONE pass over their concatenation (the harness batch entry point).
+        """tokenize() of many texts in one pass over their concatenation (the harness batch entry point, SURVEY.md §8f row 4;
+        several passes when the texts exceed BATCH_TEXT_BYTES together).
         -> (token ids u32 of all texts back to back, int64 offsets[len(texts) + 1] of each text's tokens)."""
         enc = [P.encode_utf8(t) for t in texts]
+        if sum(len(b) + 1 for b in enc) > self.BATCH_TEXT_BYTES and len(enc) > 1:
+            ids_parts, cuts, base, k = [], [np.zeros(1, np.int64)], 0, 0
+            while k < len(enc):
+                k1, size = k, 0
+                while k1 < len(enc) and (k1 == k or size + len(enc[k1]) + 1 <= self.BATCH_TEXT_BYTES):
+                    size += len(enc[k1]) + 1
+                    k1 += 1
+                ids, cut = self._encode_texts_once(enc[k:k1])
+                ids_parts.append(ids); cuts.append(cut[1:] + base)
+                base += len(ids); k = k1
+            return np.concatenate(ids_parts), np.concatenate(cuts)
+        return self._encode_texts_once(enc)
+
+    def _encode_texts_once(self, enc: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
+        texts = enc
         bounds = np.zeros(len(texts) + 1, dtype=np.int64)
         np.cumsum([len(b) + 1 for b in enc], out=bounds[1:])                 # +1: the "\n" that separates two texts
         data = b"\n".join(enc)

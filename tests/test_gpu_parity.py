@@ -677,6 +677,13 @@ def test_tokenize_batch_equals_per_text_calls_for_all_four_classes(P, dev):
         assert got[:200] == gold[key][:200], key
         assert got[200:] == [tok.tokenize(t) for t in texts[200:]], key
         assert got[200] == [] and got[201] == []
+    # texts that exceed the per-pass byte budget together are processed in several passes with the same result
+    enc = fw.vocab_trie.encoder
+    ids_1, cut_1 = enc.encode_texts(texts)
+    enc.BATCH_TEXT_BYTES = 3000
+    ids_n, cut_n = enc.encode_texts(texts)
+    del enc.BATCH_TEXT_BYTES
+    assert np.array_equal(ids_1, ids_n) and np.array_equal(cut_1, cut_n)
 
 
 # ---- word-type table built on the device (pre-tokenization + dedupe in front of the trainers) ------------------------------
