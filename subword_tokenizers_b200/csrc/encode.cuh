@@ -39,7 +39,7 @@ constexpr int kEmitCtasPerSm = 4;
 constexpr int kWordsPerThread = 2;
 constexpr int kTileWords = 32 * kWordsPerThread;         // 64 words per (warp) tile
 constexpr int kShortBytes = 32;        // words up to this many bytes are encoded by one thread (and memoised)
-constexpr int kCompactTokens = 1024;   // tile token totals up to this are assembled in smem before the store
+constexpr int kCompactTokens = 640;    // tile token totals up to this are assembled in smem before the store
 constexpr int kMemoTokens = 44;        // >= kShortBytes: every word of up to 32 bytes fits (ids <= bytes)
 constexpr int kMemoProbes = 8;
 
