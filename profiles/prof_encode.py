@@ -27,4 +27,4 @@ for name, enc in (("wp", wenc), ("bpe", benc)):
     a.record(); enc.encode_into(d_arena, d_off, n_words, 0, ids, cap, tok, ws, status); b.record(); torch.cuda.synchronize()
     nt, h6 = enc.check_status(status)
     st = status.cpu().numpy()
-    print(name, "ms", a.elapsed_time(b), "tokens", nt, "memo types", int(st[4]), "words", n_words, "bytes", int(d_arena.numel()))
+    print(name, "ms", a.elapsed_time(b), "tokens", nt, "memo types", int(st[4]), "slow-path words", int(st[5]), "words", n_words, "bytes", int(d_arena.numel()))

@@ -170,6 +170,7 @@ template <bool kNaive>
 struct BpeEncT {
     BpeTableDev t;
     static constexpr bool kScratchLong = true;
+    static constexpr bool kBatchSlowPath = false;
     __device__ __forceinline__ uint32_t encode_short(const uint8_t *p, uint32_t nbytes, uint32_t *buf, uint32_t &h6) const {
         (void)h6;
         return bpe_encode_short<kNaive>(t, p, nbytes, buf);

@@ -146,6 +146,7 @@ __device__ __forceinline__ void wp_naive_encode_word(const WpTrieDev &t, const u
 struct NaiveWpEnc {
     WpTrieDev t;
     static constexpr bool kScratchLong = false;
+    static constexpr bool kBatchSlowPath = true;
     __device__ __forceinline__ uint32_t encode_short(const uint8_t *p, uint32_t nbytes, uint32_t *buf, uint32_t &h6) const {
         (void)h6;
         ArrayEmit e{buf, (uint32_t)kShortBytes};
@@ -168,6 +169,7 @@ struct NaiveWpEnc {
 struct WpEnc {
     WpTrieDev t;
     static constexpr bool kScratchLong = false;
+    static constexpr bool kBatchSlowPath = true;
     __device__ __forceinline__ uint32_t encode_short(const uint8_t *p, uint32_t nbytes, uint32_t *buf, uint32_t &h6) const {
         ArrayEmit e{buf, (uint32_t)kShortBytes};
         wp_encode_chunk(t, p, nbytes, e, h6);
