@@ -85,7 +85,8 @@ size_t swt_encode_workspace_bytes(uint32_t n_words, uint64_t long_word_bytes);
 /*
  * swt_bpe_encode  replaces  [tok for w in words for tok in FastBPE.encode_word(w)]   (bpe.py:205-249)
  *   d_status (8 x u32): [0] SWT_OK / SWT_ERR_CAPACITY / SWT_ERR_INTERNAL, [1] total tokens (low 32 bits,
- *   [3] high bits; also written to d_out_tok_off[n_words] when that is not NULL), [2] H6 events (WP).
+ *   [3] high bits; also written to d_out_tok_off[n_words] when that is not NULL), [2] H6 events (WP);
+ *   diagnostics: [4] word types published in the call's memo, [5] words that took the slow path.
  *   Asynchronous on `stream`; returns only argument/launch errors.
  */
 int swt_bpe_encode(const swt_bpe_table *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
