@@ -46,16 +46,17 @@ constexpr int kMemoProbes = 8;
 // status words written by the encode kernels
 enum { kStatusCode = 0, kStatusTokens = 1, kStatusH6 = 2, kStatusTokensHi = 3, kStatusMemoTypes = 4, kStatusSlowWords = 5 };
 
-struct alignas(256) MemoEntry {         // 256 bytes; a fast-path hit touches the first 16 (count pass) + 16..32 (emit pass) bytes
+struct alignas(256) MemoEntry {         // 256 bytes; a fast-path hit touches bytes 0..15 (count pass) and 32..47 (emit pass)
     unsigned long long lo, hi;          // CAS key: word bytes 0..7 | bytes 8..14, bits 56-59 = length (0 for words > 15 bytes),
                                         // bits 60-63 = "pub": 0, or n_tokens + 1 once ids16[] is valid (set after the CAS claim)
-    uint16_t ids16[16];                 // ids 0..15 as 16-bit values (only when every id of the word is < 65536)
     uint32_t meta;                      // 0 = claimed, not published; else (n_tokens + 1) | (h6 << 8); ~0 = not cacheable
     uint32_t tail_last;                 // words > 15 bytes: byte 31 | length << 8
-    uint32_t pad[2];
+    uint32_t pad[2];                    // (bytes 0..31 = the one sector memo_clear_kernel has to zero)
+    uint16_t ids16[16];                 // at byte 32: ids 0..15 as 16-bit values (only when every id of the word is < 65536)
     unsigned long long tail_a, tail_b;  // at byte 64; words > 15 bytes: bytes 15..22 | 23..30 (verified after the key)
     uint32_t tok[kMemoTokens];          // all ids as 32-bit values, at byte 80
 };
+constexpr uint32_t kMemoSlotBits = 23, kMemoSlotMask = (1u << kMemoSlotBits) - 1u;     // slot field of the per-word record
 static_assert(sizeof(MemoEntry) == 256, "MemoEntry must be 256 bytes");
 constexpr unsigned long long kPubMask = 0xFull << 60;
 
@@ -220,7 +221,7 @@ __device__ __forceinline__ bool memo_publish(const EncodeWorkspace &ws, uint32_t
 }
 
 // per-word record between the two passes, packed into 32 bits:
-//   [31:29] kind; Hit / Hit16 (ids16[] valid): [28:23] n_tokens, [19:0] memo slot; Recompute: [28:23] n_tokens;
+//   [31:29] kind; Hit / Hit16 (ids16[] valid): [28:23] n_tokens, [22:0] memo slot; Recompute: [28:23] n_tokens;
 //   WP long: [28:0] n_tokens; BPE long: [28:0] scratch granule (16 u32) -- header word 0 holds n_tokens
 enum : uint32_t { kWordNone = 0u, kWordHit = 1u, kWordRecompute = 2u, kWordLong = 3u, kWordLongB = 4u, kWordHit16 = 5u };
 constexpr uint32_t kLongHeader = 16;      // u32 words reserved in front of the two scratch buffers of a long BPE word
@@ -306,7 +307,7 @@ static __global__ void __launch_bounds__(256) memo_clear_kernel(MemoEntry *memo,
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) {
         uint4 *e = reinterpret_cast<uint4 *>(memo + i);
-        e[0] = z; e[3] = z;                                 // key (bytes 0-15) and meta / tail_last (bytes 48-63)
+        e[0] = z; e[1] = z;                                 // key (bytes 0-15) and meta / tail_last (bytes 16-31): one sector
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *long_cursor = 0ull;
 }
@@ -614,7 +615,7 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
             ntok[j] = (kind[j] == kWordHit || kind[j] == kWordHit16 || kind[j] == kWordRecompute) ? (arg[j] >> 23)
                       : (kind[j] == kWordLong && !Enc::kScratchLong) ? arg[j] : 0u;
             ra[j] = rb[j] = make_uint4(0, 0, 0, 0);
-            const MemoEntry *e = ws.memo + (arg[j] & 0xFFFFFu);
+            const MemoEntry *e = ws.memo + (arg[j] & kMemoSlotMask);
             if (kind[j] == kWordHit16) {                            // one or two scattered loads; both words' loads in flight together
                 if (ntok[j] > 0) ra[j] = ld_ca_u32x4(&e->ids16[0]);
                 if (ntok[j] > 8) rb[j] = ld_ca_u32x4(&e->ids16[8]);
@@ -658,8 +659,8 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
                 if (use_compact) store_hit16_ids<true>(cdst + run[j], ntok[j], ra[j], rb[j]);
                 else store_hit16_ids<false>(out_ids + base + run[j], ntok[j], ra[j], rb[j]);
             } else if (kind[j] == kWordHit) {
-                if (use_compact) store_hit_ids(cdst + run[j], ntok[j], ra[j], rb[j], ws.memo + (arg[j] & 0xFFFFFu));
-                else store_hit_ids(out_ids + base + run[j], ntok[j], ra[j], rb[j], ws.memo + (arg[j] & 0xFFFFFu));
+                if (use_compact) store_hit_ids(cdst + run[j], ntok[j], ra[j], rb[j], ws.memo + (arg[j] & kMemoSlotMask));
+                else store_hit_ids(out_ids + base + run[j], ntok[j], ra[j], rb[j], ws.memo + (arg[j] & kMemoSlotMask));
             } else if (kind[j] == kWordRecompute || (!Enc::kScratchLong && kind[j] == kWordLong)) {
                 uint32_t *dst = use_compact ? cdst + run[j] : out_ids + base + run[j];
                 const uint32_t b0 = __ldg(word_off + w_tile + i0 + j), b1 = __ldg(word_off + w_tile + i0 + j + 1);
