@@ -50,8 +50,8 @@ def load_golden(name):
 ZIPF_C = 200_000
 # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of ONE FastWP encode call over the 1 GB bench stream
 # (ncu --set full, see profiles/r01_final_ncu_wp_1GB.txt); None until measured
-TRAFFIC_1GB_WP = 6_281_293_000
-TRAFFIC_SOURCE = "profiles/r01_final5_ncu_wp_1GB.txt"
+TRAFFIC_1GB_WP = 6_195_873_000
+TRAFFIC_SOURCE = "profiles/r01_final6_ncu_wp_1GB.txt"
 DRAW_CHUNK = 1 << 24
 
 
