@@ -152,3 +152,36 @@ def test_bert_class_table_matches_the_tokenizers_library(hf_tokenizer):
         def pre_tokenize_str(self, s):
             return [(w, (0, 0)) for w in s.split()]
     assert not P.bert_pretokenizer_matches(Other())
+
+
+def test_encode_texts_splits_large_batches_on_the_host():
+    """_Encoder.encode_texts cuts a batch that exceeds BATCH_TEXT_BYTES into several device passes and stitches ids / per-text
+    cuts back together (host logic; the device pass is replaced by a stand-in that emits one id per whitespace word)."""
+    from subword_tokenizers_b200.device import _Encoder
+
+    class Stub(_Encoder):
+        calls = 0
+
+        def __init__(self):                      # no device handle
+            pass
+
+        def _encode_texts_once(self, enc):
+            Stub.calls += 1
+            counts = [len(b.split()) for b in enc]
+            ids = np.array([len(w) for b in enc for w in b.split()], dtype=np.uint32)
+            return ids, np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+
+        def __del__(self):
+            pass
+
+    texts = ["a bb ccc", "", "dddd e", "ff", "   ", "g hh iii jjjj"] * 7
+    s = Stub()
+    ids_1, cut_1 = s.encode_texts(texts)
+    assert Stub.calls == 1 and cut_1[-1] == len(ids_1) and len(cut_1) == len(texts) + 1
+    s.BATCH_TEXT_BYTES = 20
+    Stub.calls = 0
+    ids_n, cut_n = s.encode_texts(texts)
+    assert Stub.calls > 5
+    assert np.array_equal(ids_1, ids_n) and np.array_equal(cut_1, cut_n)
+    for k, t in enumerate(texts):
+        assert ids_n[cut_n[k]:cut_n[k + 1]].tolist() == [len(w) for w in t.split()]
