@@ -185,3 +185,18 @@ def test_encode_texts_splits_large_batches_on_the_host():
     assert np.array_equal(ids_1, ids_n) and np.array_equal(cut_1, cut_n)
     for k, t in enumerate(texts):
         assert ids_n[cut_n[k]:cut_n[k + 1]].tolist() == [len(w) for w in t.split()]
+
+
+def test_token_id_to_string_tables():
+    """Vectorised id -> string materialisation (packing.*Tables.tokens_to_strs) against the scalar definitions of include/swt.h."""
+    bt = P.BpeTables([("a", "b"), ("ab", "c"), ("x", "y")])
+    sym = {s: i for i, s in enumerate(bt.id_to_str)}
+    toks = np.array([sym["abc"] << 1, (sym["xy"] << 1) | 1, ((P.BPE_UNKNOWN_CP | ord("ż")) << 1) & 0xFFFFFFFF | 1,
+                     (P.BPE_UNKNOWN_CP | 0x1F600) << 1 & 0xFFFFFFFF, P.BPE_EMPTY_TOKEN, (sym["a"] << 1) | 1], dtype=np.uint32)
+    want = [bt.token_to_str(int(t)) for t in toks]
+    assert want[:2] == ["abc", "##xy"] and want[4] == "" and want[5] == "##a"
+    assert bt.tokens_to_strs(toks) == want
+    assert bt.tokens_to_strs(toks[:2]) == want[:2] and bt.tokens_to_strs([]) == []
+    wt = P.WpTables(["b", "##a", "a"])
+    assert wt.tokens_to_strs(np.array([0, 1, 2, 3, 4], dtype=np.uint32)) == ["##a", "a", "b", "['UNK']", "[UNK]"]
+    assert wt.tokens_to_strs([]) == []
