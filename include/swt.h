@@ -60,6 +60,11 @@ extern "C" {
 int swt_abi_version(void);
 const char *swt_last_error(void);
 int swt_device_count(int *count);
+/* Process-wide experiment knobs (diagnostics; defaults are the measured best).  "memo_max_log2" (10..23, default 22): cap of the
+ * word-type memo of an encode call; "memo_off" (0/1): disable the memo, every word takes the direct path; "bulk_store" (0/1):
+ * cp.async.bulk copy-out in the emit pass; "warp_words": FastBPE warp-per-word threshold; "timing" (0/1): per-kernel times on
+ * stderr.  A change of the memo knobs changes swt_encode_workspace_bytes: size workspaces after setting them. */
+int swt_tune(const char *name, int value);
 
 /* ---- HP-1: FastBPE rank table + encode ------------------------------------------------------ */
 /*
@@ -310,9 +315,16 @@ void swt_bpe_train_destroy(swt_bpe_trainer *t);
 int swt_bpe_train_buffers(const swt_bpe_trainer *t, void **init_counts_ptr, uint64_t *init_counts_elems /* i64 */,
                           void **cand_ptr /* 2 x u64 */, void **cand_gather_ptr /* world x 2 x u64 */,
                           void **delta_ptr, uint64_t *delta_elems /* i64 */);
-/* initial pair count: local dense count -> [all_reduce(SUM) over init_counts] -> table build */
+/* initial pair count (bpe.py:90-95 before the first merge).
+ * n_alpha <= 4096: local dense count -> [all_reduce(SUM) over init_counts] -> table build.
+ * larger alphabets (init_counts_elems == 0): count_local inserts this rank's counts straight into the pair table and
+ * build_table is a no-op; sharded callers then swt_bpe_train_export_pairs (2 x u64 per entry: key, count; *d_n_out = number
+ * of entries, which may exceed out_cap_entries -- call again with a larger buffer), all-gather the lists and
+ * swt_bpe_train_import_pairs the lists of the OTHER ranks, so that every replica holds the global counts. */
 int swt_bpe_train_count_local(swt_bpe_trainer *t, void *stream);
 int swt_bpe_train_build_table(swt_bpe_trainer *t, void *stream);
+int swt_bpe_train_export_pairs(swt_bpe_trainer *t, uint64_t *d_out, uint64_t out_cap_entries, uint64_t *d_n_out, void *stream);
+int swt_bpe_train_import_pairs(swt_bpe_trainer *t, const uint64_t *d_in, uint64_t n_entries, void *stream);
 int swt_bpe_train_select(swt_bpe_trainer *t, void *stream);
 int swt_bpe_train_merge(swt_bpe_trainer *t, void *stream);
 int swt_bpe_train_update(swt_bpe_trainer *t, void *stream);

@@ -6,8 +6,8 @@ training run as hand-written sm_100a CUDA kernels behind the C ABI of include/sw
 """
 from .bpe import FastBPE, NaiveBPE
 from .wordpiece import FastWP, NaiveWP
-from .utils import SubwordTokenizer, WPTrie_E2E, recover_sentence
+from .utils import SubwordTokenizer, WPTrie_E2E
 from .hf_shim import make_hf_tokenizer
 
-__all__ = ["NaiveBPE", "FastBPE", "NaiveWP", "FastWP", "SubwordTokenizer", "WPTrie_E2E", "recover_sentence",
+__all__ = ["NaiveBPE", "FastBPE", "NaiveWP", "FastWP", "SubwordTokenizer", "WPTrie_E2E",
            "make_hf_tokenizer"]

@@ -47,6 +47,7 @@ SIGNATURES = {
     "swt_abi_version": (ctypes.c_int, []),
     "swt_last_error": (ctypes.c_char_p, []),
     "swt_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "swt_tune": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "swt_bpe_table_create": (ctypes.c_int, [c_u32p, c_u32p, c_u32p, ctypes.c_uint32, c_u32p, c_u32p, ctypes.c_uint32,
                                             ctypes.c_int, ctypes.POINTER(c_vp)]),
     "swt_bpe_table_destroy": (None, [c_vp]),
@@ -94,6 +95,8 @@ SIGNATURES = {
                                              ctypes.POINTER(c_vp), c_u64p]),
     "swt_bpe_train_count_local": (ctypes.c_int, [c_vp, c_vp]),
     "swt_bpe_train_build_table": (ctypes.c_int, [c_vp, c_vp]),
+    "swt_bpe_train_export_pairs": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint64, c_vp, c_vp]),
+    "swt_bpe_train_import_pairs": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint64, c_vp]),
     "swt_bpe_train_select": (ctypes.c_int, [c_vp, c_vp]),
     "swt_bpe_train_merge": (ctypes.c_int, [c_vp, c_vp]),
     "swt_bpe_train_update": (ctypes.c_int, [c_vp, c_vp]),

@@ -15,6 +15,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import packing as P
+from ._tracked import TrackedDict, TrackedList, TrackedSet, stamp, tracked_attribute
 from .utils import SubwordTokenizer
 
 
@@ -35,6 +36,10 @@ def _batch_lists(tok, enc, texts: Sequence[str]) -> List[List[str]]:
 
 class NaiveBPE(SubwordTokenizer):
     """Byte-Pair-Encoding tokenizer (reference source/bpe.py:9-189)."""
+
+    # mutation-counting containers: the device tables are rebuilt whenever the live Python object changed (_tracked.py)
+    merges_list = tracked_attribute("merges_list", TrackedList)
+    vocab = tracked_attribute("vocab", TrackedSet)
 
     def __init__(self, tokenizer) -> None:
         super().__init__(tokenizer)
@@ -69,14 +74,23 @@ class NaiveBPE(SubwordTokenizer):
         from .device import CudaTrainEngine, run_training_loop, shard_types
 
         self.vocab = set(types.alphabet)
+        if types.n_types == 0 or types.n_alpha == 0:          # empty corpus: the reference returns with no merges (bpe.py:88,98-99)
+            self.merges_list = []
+            self._train_result = None
+            self._corpus_cache = []
+            self.last_train_stats = {"merge_loop_s": 0.0, "merges": 0, "n_types": 0, "n_symbols": 0, "world_size": 1}
+            return
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         rank = dist.get_rank(group) if world > 1 else 0
         t0, t1 = shard_types(types.off, world)[rank]
         off = types.off[t0:t1 + 1] - types.off[t0]
         syms = types.syms[int(types.off[t0]):int(types.off[t1])]
         max_len = int(np.diff(types.off.astype(np.int64)).max()) if types.n_types else 1
+        # alphabets beyond the dense-count limit insert their initial pairs directly: a sharded table must then be sized
+        # for the pairs of ALL ranks from the start
+        table_cap = 2 * int(len(types.syms)) + 8 * max(max_vocab, 1) if (world > 1 and types.n_alpha > 4096) else 0
         engine = CudaTrainEngine(syms, off, types.freq[t0:t1], types.n_alpha, max_vocab, len(types.alphabet), max_len,
-                                 int(types.off[t0]), rank, world)
+                                 int(types.off[t0]), rank, world, table_cap=table_cap)
         torch.cuda.synchronize()
         tic = time.perf_counter()
         left, right, new, count, state = run_training_loop(engine, world, group)
@@ -132,7 +146,7 @@ class NaiveBPE(SubwordTokenizer):
         """In-order replay on the device (swt_bpe_encode_naive), or None when the merge list repeats a pair (the device table
         keeps one rank per pair; the host replay below stays exact for such lists)."""
         from .device import BpeEncoder
-        quick = (id(self.merges_list), len(self.merges_list))
+        quick = stamp(self.merges_list)
         if getattr(self, "_naive_quick", None) != quick:
             pairs = [tuple(p) for p in self.merges_list]
             self._naive_encoder = BpeEncoder(P.BpeTables(pairs), naive=True) if len(set(pairs)) == len(pairs) else None
@@ -192,11 +206,12 @@ class NaiveBPE(SubwordTokenizer):
 class FastBPE(NaiveBPE):
     """Rank-map BPE inference (reference source/bpe.py:192-263) on the GPU."""
 
+    _bpe_ranks = tracked_attribute("_bpe_ranks", TrackedDict)
+
     def __init__(self, tokenizer):
         super().__init__(tokenizer)
-        self._bpe_ranks: Dict[Tuple[str, str], int] = {}
+        self._bpe_ranks = {}
         self._encoder = None
-        self._encoder_key = None
         self._encoder_quick = None
 
     def _rebuild_ranks(self) -> None:
@@ -214,15 +229,13 @@ class FastBPE(NaiveBPE):
     def _device_encoder(self):
         """The rank table on the device, rebuilt when merges_list / _bpe_ranks changed."""
         from .device import BpeEncoder
-        # honour direct assignment to _bpe_ranks (the reference reads only that dict in encode_word)
-        quick = (id(self._bpe_ranks), len(self._bpe_ranks))           # O(1) on the per-call path
+        # honour direct assignment to / in-place edits of _bpe_ranks (the reference reads only that dict in encode_word):
+        # the dict counts its mutations, so the check is O(1) on the per-call path and still exact
+        quick = stamp(self._bpe_ranks)
         if self._encoder is not None and self._encoder_quick == quick:
             return self._encoder
         ranked = sorted(self._bpe_ranks.items(), key=lambda kv: kv[1])
-        key = (len(ranked), hash(tuple(p for p, _ in ranked[:64])), hash(tuple(p for p, _ in ranked[-64:])))
-        if self._encoder is None or self._encoder_key != key:
-            self._encoder = BpeEncoder(P.BpeTables([p for p, _ in ranked]))
-            self._encoder_key = key
+        self._encoder = BpeEncoder(P.BpeTables([p for p, _ in ranked]))
         self._encoder_quick = quick
         return self._encoder
 

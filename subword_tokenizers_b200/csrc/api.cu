@@ -10,27 +10,35 @@ namespace swt {
 static thread_local std::string g_last_error;
 void set_error(const std::string &msg) { g_last_error = msg; }
 
+Tuning g_tune;
+
 size_t encode_workspace_layout(uint32_t n_words, uint64_t long_bytes, void *base, EncodeWorkspace *ws) {
     Carver cv(base);
     const uint32_t n_tiles = (n_words + kTileWords - 1) / kTileWords;
     ws->n_tiles = n_tiles;
-    ws->long_cursor = cv.take<unsigned long long>(1);
-    // word-type memo: rebuilt from empty by every launch; sized with the batch, at most 2^20 entries (256 MB) by default.
-    // Measured on the 1 GB bench stream (23 k types): 2^16 1.44+1.45 ms (count+emit), 2^18 1.22+1.38, 2^20 1.18+1.39,
-    // 2^22 1.53+1.73 (the hot entries spread over 1 GB: TLB reach); a stream with 1.85 M types: 2^20 9.4 ms, 2^22 4.6 ms.
-    // SWT_MEMO_MAX_LOG2 (10..23) overrides the cap for corpora with millions of word types.
+    ws->long_cursor = cv.take<unsigned long long>(2);
+    // Word-type memo: rebuilt from empty by every launch; one slot per four words of the batch, at most 2^22 slots by default
+    // (keys 64 MB + ids16 128 MB + ext 128 MB + tok32 128 MB; only the keys are cleared and probed by the count pass).
+    // swt_tune("memo_max_log2", 10..23) moves the cap; swt_tune("memo_off", 1) disables the memo (direct-path rates).
     uint64_t slots = next_pow2(std::max<uint64_t>(n_words / 4, 1024));
-    static const int cap_log2 = [] { const char *e = getenv("SWT_MEMO_MAX_LOG2"); const int v = e ? atoi(e) : 0; return (v >= 10 && v <= 23) ? v : 20; }();
+    const int cap_log2 = std::min(std::max(g_tune.memo_max_log2, 10), (int)kMemoSlotBits);
     slots = std::min<uint64_t>(slots, 1ull << cap_log2);
-    ws->memo = cv.take<MemoEntry>(slots);
-    ws->memo_mask = (uint32_t)(slots - 1);
-    ws->zero_bytes = cv.used();
+    if (g_tune.memo_off) slots = 0;
+    ws->keys = cv.take<uint4>(slots);
+    ws->memo_mask = slots ? (uint32_t)(slots - 1) : 0u;
+    ws->ids16 = cv.take<uint4>(2 * slots);
+    ws->ext = cv.take<MemoExt>(slots);
+    ws->tok32_cap = (uint32_t)std::min<uint64_t>(8 * slots, 1ull << 30);
+    ws->tok32 = cv.take<uint32_t>((size_t)ws->tok32_cap + 1);
     ws->packed = cv.take<uint32_t>((size_t)n_words + 2);
     ws->tile_total = cv.take<uint32_t>((size_t)n_tiles + 1);
     ws->group_base = cv.take<unsigned long long>((size_t)n_tiles / 1024 + 2);
-    // BPE long words: 16-word header + two symbol buffers each, allocated in 16-word granules
-    ws->long_scratch_elems = long_bytes ? 2 * long_bytes + 32 * (long_bytes / 33 + 1) : 0;
+    ws->long_tiles = cv.take<uint32_t>((size_t)n_tiles / 32 + 2);
+    // long words: a 16-word header + per-byte scratch each, allocated in 16-word granules.  BPE: two symbol buffers (2 words per
+    // byte); WP: a 4-word segment record per boundary position of a long chunk (at most one per byte)
+    ws->long_scratch_elems = long_bytes ? 4 * long_bytes + 32 * (long_bytes / 33 + 1) : 0;
     ws->long_scratch = cv.take<uint32_t>(ws->long_scratch_elems + 1);
+    ws->flags = g_tune.bulk_store ? kFlagBulkStore : 0u;
     return cv.used();
 }
 
@@ -45,6 +53,19 @@ SWT_API int swt_device_count(int *count) {
     SWT_REQUIRE(count != nullptr, "count is NULL");
     *count = 0;
     SWT_CUDA_OK(cudaGetDeviceCount(count));
+    return SWT_OK;
+}
+
+SWT_API int swt_tune(const char *name, int value) {
+    SWT_REQUIRE(name != nullptr, "name is NULL");
+    const std::string n(name);
+    if (n == "memo_max_log2") g_tune.memo_max_log2 = value;
+    else if (n == "memo_off") g_tune.memo_off = value;
+    else if (n == "bulk_store") g_tune.bulk_store = value;
+    else if (n == "timing") g_tune.timing = value;
+    else if (n == "warp_words") g_tune.warp_words = value;
+    else if (n == "bpe_queue") g_tune.bpe_queue = value;
+    else { set_error("swt_tune: unknown knob " + n); return SWT_ERR_ARG; }
     return SWT_OK;
 }
 

@@ -31,7 +31,8 @@ constexpr uint32_t kStart = 0x80000000u;
 constexpr uint32_t kHole = 0xFFFFFFFFu;
 constexpr uint64_t kEmptyKey = ~0ull;
 constexpr uint64_t kNoPos = ~0ull;
-constexpr uint32_t kMaxDenseAlpha = 4096;
+constexpr uint32_t kMaxDenseAlpha = 4096;       // up to here the initial pair counts go through a dense n_alpha^2 array (one all-reduce
+                                                // when sharded); larger alphabets (CJK, multilingual) count straight into the pair table
 constexpr uint32_t kChunkShift = 12;            // mark scan granularity: 4096 slots per chunk
 constexpr uint32_t kBlkShift = 12;              // argmax cache granularity: 4096 table slots per block
 
@@ -155,6 +156,29 @@ __global__ void k_count_dense(TrainDev d) {
         const uint32_t a = s & ~kStart;
         atomicAdd((unsigned long long *)&d.dense[(uint64_t)a * d.n_alpha + nx], (unsigned long long)d.freq[d.word_of[i]]);
     }
+}
+// large alphabets: the initial counts go straight into the pair table (this rank's types only; see export / import below)
+__global__ void k_count_sparse(TrainDev d, uint64_t cap) {
+    const uint64_t n = d.n_slots;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i + 1 < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = d.sym[i], nx = d.sym[i + 1];
+        if (nx & kStart) continue;
+        table_add(d.table, cap, ((uint64_t)(s & ~kStart) << 32) | nx, d.freq[d.word_of[i]], d.st, d.dirty, d.dirty_list);
+    }
+}
+// sharded training with a large alphabet: every rank lists its local (pair, count) entries, the lists are all-gathered by
+// the caller and the entries of the OTHER ranks are added, so that all replicas of the table hold the global counts
+__global__ void k_export_pairs(TrainDev d, uint64_t cap, uint64_t *out, uint64_t out_cap, unsigned long long *n_out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const PairEntry e = d.table[i];
+        if (e.key == kEmptyKey || e.count == 0) continue;
+        const unsigned long long k = atomicAdd(n_out, 1ull);
+        if (k < out_cap) { out[2 * k] = e.key; out[2 * k + 1] = (uint64_t)e.count; }
+    }
+}
+__global__ void k_import_pairs(TrainDev d, uint64_t cap, const uint64_t *in, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        table_add(d.table, cap, in[2 * i], (long long)in[2 * i + 1], d.st, d.dirty, d.dirty_list);
 }
 __global__ void k_build_table(TrainDev d, uint64_t cap) {
     const uint64_t n = (uint64_t)d.n_alpha * d.n_alpha;
@@ -590,6 +614,10 @@ static constexpr uint32_t kStepsPerGraph = 32;
 
 static uint64_t choose_table_cap(const swt_bpe_train_config *cfg) {
     if (cfg->table_cap) return std::max<uint64_t>(next_pow2(cfg->table_cap), 1ull << kBlkShift);
+    // large alphabet: the initial count inserts directly, so the table must hold every distinct pair of the corpus from the
+    // start (at most one per symbol slot; sharded callers pass table_cap sized from the GLOBAL slot count)
+    if (cfg->n_alpha > kMaxDenseAlpha)
+        return next_pow2(std::max<uint64_t>(1ull << 16, 2 * cfg->n_slots_local + 8ull * (uint64_t)std::max<int64_t>(cfg->max_vocab, 1)));
     uint64_t a2 = (uint64_t)cfg->n_alpha * cfg->n_alpha;
     uint64_t want = std::max<uint64_t>(1ull << 16, 4 * std::min<uint64_t>(a2, 1ull << 24));
     want = std::max<uint64_t>(want, 8ull * (uint64_t)std::max<int64_t>(cfg->max_vocab, 1));
@@ -638,7 +666,7 @@ static size_t train_layout(const swt_bpe_train_config *cfg, void *base, TrainDev
     d->mode = cfg->mode;
     d->delta = cv.take<long long>(2ull * vmax + 2);
     d->touch_l = cv.take<uint32_t>(vmax); d->touch_r = cv.take<uint32_t>(vmax);
-    d->dense = cv.take<long long>((uint64_t)cfg->n_alpha * cfg->n_alpha + 1);
+    d->dense = cv.take<long long>(cfg->n_alpha <= kMaxDenseAlpha ? (uint64_t)cfg->n_alpha * cfg->n_alpha + 1 : 1);
     d->cand = cv.take<uint64_t>(2);
     d->cand_gather = cv.take<uint64_t>(2ull * cfg->world_size);
     d->parts = cv.take<ArgPart>(d->n_parts);
@@ -664,7 +692,7 @@ SWT_API int swt_bpe_train_create(const swt_bpe_train_config *cfg, const uint32_t
     SWT_REQUIRE(cfg && out && d_workspace, "NULL argument");
     SWT_REQUIRE(cfg->n_slots_local < 0xFFFFFFF0ull, "n_slots_local must be < 2^32");
     SWT_REQUIRE(cfg->n_types_local < 0xFFFFFFF0ull, "n_types_local must be < 2^32");
-    SWT_REQUIRE(cfg->n_alpha >= 1 && cfg->n_alpha <= kMaxDenseAlpha, "n_alpha must be in [1, 4096]");
+    SWT_REQUIRE(cfg->n_alpha >= 1 && cfg->n_alpha < (1u << 30), "n_alpha must be in [1, 2^30)");
     SWT_REQUIRE(cfg->world_size >= 1 && cfg->rank < cfg->world_size, "bad rank/world_size");
     SWT_REQUIRE(cfg->record_cap >= 1, "record_cap must be >= 1");
     SWT_REQUIRE(cfg->max_vocab < (1ll << 30), "max_vocab must be < 2^30");
@@ -713,7 +741,7 @@ SWT_API int swt_bpe_train_buffers(const swt_bpe_trainer *t, void **init_counts_p
                                   void **cand_ptr, void **cand_gather_ptr, void **delta_ptr, uint64_t *delta_elems) {
     SWT_REQUIRE(t != nullptr, "NULL trainer");
     if (init_counts_ptr) *init_counts_ptr = t->dev.dense;
-    if (init_counts_elems) *init_counts_elems = (uint64_t)t->cfg.n_alpha * t->cfg.n_alpha;
+    if (init_counts_elems) *init_counts_elems = t->cfg.n_alpha <= kMaxDenseAlpha ? (uint64_t)t->cfg.n_alpha * t->cfg.n_alpha : 0;
     if (cand_ptr) *cand_ptr = t->dev.cand;
     if (cand_gather_ptr) *cand_gather_ptr = t->dev.cand_gather;
     if (delta_ptr) *delta_ptr = t->dev.delta;
@@ -723,13 +751,30 @@ SWT_API int swt_bpe_train_buffers(const swt_bpe_trainer *t, void **init_counts_p
 
 SWT_API int swt_bpe_train_count_local(swt_bpe_trainer *t, void *stream) {
     SWT_REQUIRE(t != nullptr, "NULL trainer");
-    if (t->dev.n_slots) k_count_dense<<<t->grid_scan, 256, 0, (cudaStream_t)stream>>>(t->dev);
+    if (t->dev.n_slots) {
+        if (t->cfg.n_alpha <= kMaxDenseAlpha) k_count_dense<<<t->grid_scan, 256, 0, (cudaStream_t)stream>>>(t->dev);
+        else k_count_sparse<<<t->grid_scan, 256, 0, (cudaStream_t)stream>>>(t->dev, t->table_cap);
+    }
     SWT_CUDA_OK(cudaGetLastError());
     return SWT_OK;
 }
 SWT_API int swt_bpe_train_build_table(swt_bpe_trainer *t, void *stream) {
     SWT_REQUIRE(t != nullptr, "NULL trainer");
-    k_build_table<<<t->grid_scan, 256, 0, (cudaStream_t)stream>>>(t->dev, t->table_cap);
+    if (t->cfg.n_alpha <= kMaxDenseAlpha) k_build_table<<<t->grid_scan, 256, 0, (cudaStream_t)stream>>>(t->dev, t->table_cap);
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}
+SWT_API int swt_bpe_train_export_pairs(swt_bpe_trainer *t, uint64_t *d_out, uint64_t out_cap_entries, uint64_t *d_n_out, void *stream) {
+    SWT_REQUIRE(t && d_n_out && (d_out || out_cap_entries == 0), "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    SWT_CUDA_OK(cudaMemsetAsync(d_n_out, 0, sizeof(uint64_t), st));
+    k_export_pairs<<<t->grid_scan, 256, 0, st>>>(t->dev, t->table_cap, d_out, out_cap_entries, (unsigned long long *)d_n_out);
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}
+SWT_API int swt_bpe_train_import_pairs(swt_bpe_trainer *t, const uint64_t *d_in, uint64_t n_entries, void *stream) {
+    SWT_REQUIRE(t && (d_in || n_entries == 0), "NULL argument");
+    if (n_entries) k_import_pairs<<<t->grid_scan, 256, 0, (cudaStream_t)stream>>>(t->dev, t->table_cap, d_in, n_entries);
     SWT_CUDA_OK(cudaGetLastError());
     return SWT_OK;
 }

@@ -8,8 +8,9 @@
 //                                 count, memo slot) and the tile's token total.
 //   scan    two tiny kernels      exclusive scan of the tile totals (in-group prefixes + group bases)
 //   pass 2  encode_emit_kernel    per word: copy the ids memo entry -> the warp's shared-memory buffer at their tile-local
-//                                 position; the tile's ids leave shared memory as 128-bit coalesced stores at their final
-//                                 position, u32 token offsets as 8-byte stores.
+//                                 position; the tile's ids leave shared memory as ONE bulk copy (cp.async.bulk shared::cta ->
+//                                 global, issued by one lane: no LSU wavefronts) at their final position, u32 token offsets as
+//                                 8-byte stores.
 //
 // An earlier single-pass version (decoupled look-back over tile states) was measured slower: with warp-sized tiles
 // the look-back walked hundreds of in-flight predecessors, with CTA-sized tiles the CTA barriers serialised the L2
@@ -18,8 +19,8 @@
 // Word-type memo: encode_word is a pure function of the word and word streams are
 // Zipf-distributed, so every launch keeps a hash table  word bytes -> token ids  in its workspace.  The first
 // thread that meets a word type claims a slot with ONE 128-bit CAS (key = first 15 bytes + length; the
-// remaining bytes of longer words are stored in the entry and compared, so a hit is always exact), encodes
-// the word and publishes the ids with a release store; later occurrences copy the ids instead of re-walking
+// remaining bytes of longer words are stored beside the entry and compared, so a hit is always exact), encodes
+// the word and publishes the ids with a release; later occurrences copy the ids instead of re-walking
 // the rank table / trie.  The memo is rebuilt from empty by every launch (nothing is carried over between
 // calls), readers never wait (a slot that is claimed but not yet published is simply recomputed), and words
 // that do not fit (longer than 32 bytes, table full) take the direct path.
@@ -46,33 +47,57 @@ constexpr int kMemoProbes = 8;
 // status words written by the encode kernels
 enum { kStatusCode = 0, kStatusTokens = 1, kStatusH6 = 2, kStatusTokensHi = 3, kStatusMemoTypes = 4, kStatusSlowWords = 5 };
 
-struct alignas(256) MemoEntry {         // 256 bytes; a fast-path hit touches bytes 0..15 (count pass) and 32..47 (emit pass)
-    unsigned long long lo, hi;          // CAS key: word bytes 0..7 | bytes 8..14, bits 56-59 = length (0 for words > 15 bytes),
-                                        // bits 60-63 = "pub": 0, or n_tokens + 1 once ids16[] is valid (set after the CAS claim)
-    uint32_t meta;                      // 0 = claimed, not published; else (n_tokens + 1) | (h6 << 8); ~0 = not cacheable
+// Word-type memo, structure of arrays (one slot index addresses all three):
+//   keys[slot]   16 B  the CAS key: word bytes 0..7 | bytes 8..14, bits 56-59 = length (0 for words > 15 bytes), bits 60-63 = "pub":
+//                      0 = claimed, not published; 1..14 = n_tokens + 1 and ids16[slot] is valid; 15 = published in ext[slot]
+//                      (ids that do not fit 16 bits, more than 13 tokens, H6 events, or "not cacheable").  The ONLY array a call clears.
+//   ids16[slot]  32 B  up to 16 ids as 16-bit values (Enc::narrow16 / Enc::expand16), read by the emit pass
+//   ext[slot]    32 B  tail of words of 16..32 bytes (compared on every hit, so a hit is exact), meta and the position of the 32-bit
+//                      id list in the tok32 arena (bump allocated)
+// Round 1 kept one 256-byte record per word type: a memo for millions of types then spans gigabytes and the hot entries of a
+// Zipf stream each sit in their own 2 MB page (TLB reach: 2^22 entries cost the bench stream 30 %).  With 16-byte keys the
+// count pass probes a table of 64 MB at 2^22 slots, two keys per sector, and nothing else has to be cleared.
+struct alignas(32) MemoExt {
+    uint32_t meta;                      // (n_tokens + 1) | (h6 << 8); 0xFFFFFFFF = not cacheable
     uint32_t tail_last;                 // words > 15 bytes: byte 31 | length << 8
-    uint32_t pad[2];                    // (bytes 0..31 = the one sector memo_clear_kernel has to zero)
-    uint16_t ids16[16];                 // at byte 32: ids 0..15 as 16-bit values (only when every id of the word is < 65536)
-    unsigned long long tail_a, tail_b;  // at byte 64; words > 15 bytes: bytes 15..22 | 23..30 (verified after the key)
-    uint32_t tok[kMemoTokens];          // all ids as 32-bit values, at byte 80
+    unsigned long long tail_a, tail_b;  // words > 15 bytes: bytes 15..22 | 23..30
+    uint32_t tok32_off;                 // first id of the 32-bit list in EncodeWorkspace::tok32
+    uint32_t pad;
 };
 constexpr uint32_t kMemoSlotBits = 23, kMemoSlotMask = (1u << kMemoSlotBits) - 1u;     // slot field of the per-word record
-static_assert(sizeof(MemoEntry) == 256, "MemoEntry must be 256 bytes");
+static_assert(sizeof(MemoExt) == 32, "MemoExt must be 32 bytes");
 constexpr unsigned long long kPubMask = 0xFull << 60;
+constexpr uint32_t kPubExt = 15;          // pub nibble: look in ext[slot]
+constexpr uint32_t kNarrowMaxTokens = 13; // pub nibble 1..14
 
 struct MemoKey { unsigned long long lo, hi, tail_a, tail_b; uint32_t tail_last; uint32_t nbytes; };
 
 struct EncodeWorkspace {
-    unsigned long long *long_cursor; // 1 (BPE: allocation cursor into long_scratch, in u32 units)
-    MemoEntry *memo; uint32_t memo_mask;   // memo_mask == 0: memo disabled
+    unsigned long long *long_cursor; // [0]: allocation cursor into long_scratch (u32 units); [1]: bump cursor into tok32
+    uint4 *keys; uint32_t memo_mask; // memo_mask == 0: memo disabled
+    uint4 *ids16;                    // 2 x uint4 per slot
+    MemoExt *ext;
+    uint32_t *tok32; uint32_t tok32_cap;
     uint32_t *packed;                // n_words: per-word record handed from the count pass to the emit pass
     uint32_t *tile_total;            // n_tiles: tokens per tile, then (after the scan) the in-group exclusive prefix
     unsigned long long *group_base;  // n_groups: tokens per group of 1024 tiles, then the group's global token offset
-    uint32_t *long_scratch;          // BPE symbol ping-pong buffers for long words
+    uint32_t *long_tiles;            // bitmap over the tiles: the tile holds a word longer than kShortBytes (rare; cleared per call)
+    uint32_t *long_scratch;          // BPE: symbol ping-pong buffers of long words; WP: segment records of long chunks
     uint64_t long_scratch_elems;
     uint32_t n_tiles;
-    size_t zero_bytes;               // prefix of the workspace that must be zeroed before a launch
+    uint32_t flags;                  // kFlag*
 };
+enum : uint32_t { kFlagBulkStore = 1u };   // emit pass: tile copy-out with cp.async.bulk (shared::cta -> global)
+
+struct Tuning {                     // process-wide knobs for experiments (swt_tune); defaults are the measured best
+    int memo_max_log2 = 22;         // cap of the memo size (10..23)
+    int memo_off = 0;               // 1: no memo -- every word takes the direct path (reported as *_direct rates)
+    int bulk_store = 1;             // emit pass copy-out through cp.async.bulk
+    int timing = 0;                 // per-kernel CUDA-event times of every encode call on stderr (synchronises)
+    int warp_words = 3;             // FastBPE: up to this many missed words are encoded by the whole warp, one after the other
+    int bpe_queue = 1;              // FastBPE: memo misses go through the warp's pending queue (0: resolved inside their tile)
+};
+extern Tuning g_tune;
 
 size_t encode_workspace_layout(uint32_t n_words, uint64_t long_bytes, void *base, EncodeWorkspace *ws);
 int encode_grid(const void *kernel, int block, size_t dyn_smem);
@@ -80,26 +105,27 @@ int encode_grid(const void *kernel, int block, size_t dyn_smem);
 #ifdef __CUDACC__
 enum { kMemoHit = 0, kMemoClaimed = 1, kMemoMiss = 2, kMemoPending = 3 };
 
-__device__ __forceinline__ void cas128(MemoEntry *e, unsigned long long lo, unsigned long long hi,
+__device__ __forceinline__ void cas128(uint4 *e, unsigned long long lo, unsigned long long hi,
                                        unsigned long long &old_lo, unsigned long long &old_hi) {
     asm volatile("{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 v, {%4, %5};\n\t"
                  "atom.global.cas.b128 o, [%6], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
                  : "=l"(old_lo), "=l"(old_hi) : "l"(0ull), "l"(0ull), "l"(lo), "l"(hi), "l"(e) : "memory");
 }
-// the memo is written during the launch: read it at L2 (never through the non-coherent L1)
+// the memo is written during the launch: the slow path reads it at L2 (never through the non-coherent L1)
 __device__ __forceinline__ void ld_cg_u64x2(const void *p, unsigned long long &a, unsigned long long &b) {
     asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
-__device__ __forceinline__ uint2 ld_cg_u32x2(const void *p) {
-    uint2 v;
-    asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+__device__ __forceinline__ uint4 ld_cg_u32x4(const void *p) {
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 // L1-cached variants for the FAST path.  Hot word types (Zipf) then hit the 100+ KB L1 instead of going to L2.  This is
-// safe although the memo is written during the launch: a key never changes once set and meta goes 0 -> final exactly
-// once, after the ids of the same sector were written (release); L1 fills are whole 32-byte sectors.  A stale L1 sector can
+// safe although the memo is written during the launch: a key never changes once set and its pub nibble goes 0 -> final exactly
+// once, after the ids / ext record were written and fenced (release); L1 fills are whole 32-byte sectors.  A stale L1 sector can
 // therefore only show "empty" or "not published yet", which sends the word to the slow path, and the slow path re-probes
-// at L2 (ld.cg).  Id sectors beyond the first are only ever read after a valid meta was seen, i.e. after publication.
+// at L2 (ld.cg).  ids16[] / ext[] of a slot are only ever read after a non-zero pub nibble was seen, i.e. after publication;
+// nobody reads them before (so no stale copy of them can sit in an L1), and the emit pass is a later launch.
 __device__ __forceinline__ void ld_ca_u64x2(const void *p, unsigned long long &a, unsigned long long &b) {
     asm volatile("ld.global.ca.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
@@ -108,16 +134,8 @@ __device__ __forceinline__ uint4 ld_ca_u32x4(const void *p) {
     asm volatile("ld.global.ca.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ uint32_t ld_ca_u32(const void *p) {
-    uint32_t v;
-    asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 // (no acquire loads anywhere: ld.acquire.gpu compiles to LDG + CCTL.IVALL, a full L1 invalidate per probe.  Ordering comes from the
-// writer's release -- ids are performed at L2 before meta / the pub nibble -- plus the reader's control dependency.)
-__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
+// writer's fence -- ids are performed at L2 before the pub nibble -- plus the reader's control dependency.)
 
 // predicated (branch-free) read-only load: 0 when the predicate is false
 __device__ __forceinline__ uint32_t ldg_u32_if(const uint32_t *p, bool pred) {
@@ -164,103 +182,192 @@ __device__ __forceinline__ void memo_key(const uint8_t *arena, uint32_t b0, uint
     k.nbytes = nbytes;
 }
 
-// slot hash of a key, in 32-bit operations (the 64-bit mixer costs ~4x the instructions on the fast path)
+// slot hash of a key: a multilinear form of the four key words (four IMADs) and one avalanche round -- half the
+// instructions of the murmur-style mixer of round 1, on the path every word takes
 __device__ __forceinline__ uint32_t memo_hash4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-    uint32_t h = (w0 ^ 0x9E3779B9u) * 0x85EBCA6Bu;
-    h = (h ^ (h >> 15) ^ w1) * 0xC2B2AE35u;
-    h = (h ^ (h >> 13) ^ w2) * 0x27D4EB2Fu;
-    h = (h ^ (h >> 16) ^ w3) * 0x165667B1u;
-    return h ^ (h >> 15);
+    uint32_t h = w0 * 0x9E3779B1u + w1 * 0x85EBCA77u + w2 * 0xC2B2AE3Du + w3 * 0x27D4EB2Fu + 0x165667B1u;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
+    return h;
 }
 __device__ __forceinline__ uint32_t memo_hash(unsigned long long lo, unsigned long long hi) {
-    return memo_hash4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+    return memo_hash4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32) & 0x0FFFFFFFu);
 }
 
-// Probes the memo at L2 (slow path).  kMemoHit: slot/meta describe a published entry for exactly this word.
+// Probes the memo at L2 (slow path).  kMemoHit: slot/meta describe a published entry for exactly this word (`narrow`: its ids
+// live in ids16[] and meta is the pub nibble, else meta is MemoExt::meta and the ids are in the tok32 arena).
 // kMemoClaimed: this thread now owns `slot` and must call memo_publish after encoding.  kMemoPending: another thread owns the
 // slot of exactly this word (words of up to 15 bytes: the key is the whole word) and will have published it by the time the
 // emit pass runs -- encode for the count, but let the emit pass read the ids from `slot`.  kMemoMiss: encode directly, publish nothing.
-static __device__ __noinline__ int memo_probe(const EncodeWorkspace &ws, const MemoKey &key, uint32_t &slot, uint32_t &meta_out) {
+static __device__ __noinline__ int memo_probe(const EncodeWorkspace &ws, const MemoKey &key, uint32_t &slot, uint32_t &meta_out, bool &narrow) {
     uint32_t h = memo_hash(key.lo, key.hi) & ws.memo_mask;
     for (int probe = 0; probe < kMemoProbes; ++probe, h = (h + 1) & ws.memo_mask) {
-        MemoEntry *e = ws.memo + h;
+        uint4 *e = ws.keys + h;
         unsigned long long klo, khi;
         ld_cg_u64x2(e, klo, khi);
-        uint2 m = ld_cg_u32x2(&e->meta);                                 // meta, tail_last
         if (klo == 0 && khi == 0) {
             cas128(e, key.lo, key.hi, klo, khi);
             if (klo == 0 && khi == 0) { slot = h; return kMemoClaimed; }
-            m.x = 0;                                                     // lost the race: the winner has not published yet
+            // lost the race: (klo, khi) is what the winner stored (its pub nibble may already be set)
         }
         if (klo != key.lo || (khi & ~kPubMask) != key.hi) continue;
-        if (m.x == 0 && key.nbytes <= 15) { slot = h; return kMemoPending; }   // claimed by another thread, not published yet
-        if (m.x == 0 || m.x == 0xFFFFFFFFu) return kMemoMiss;            // (long word: tail not comparable yet) / not cacheable
-        if (key.nbytes > 15) {                                           // same 15-byte prefix: check the rest and the length
-            unsigned long long ta, tb;
-            ld_cg_u64x2(&e->tail_a, ta, tb);
-            if (ta != key.tail_a || tb != key.tail_b || m.y != key.tail_last) continue;
+        const uint32_t pub = (uint32_t)(khi >> 60);
+        if (pub == 0) {                                                   // claimed by another thread, not published yet
+            if (key.nbytes <= 15) { slot = h; return kMemoPending; }
+            return kMemoMiss;                                             // long word: its tail is not comparable yet
         }
-        slot = h; meta_out = m.x;
+        const uint4 x = ld_cg_u32x4(&ws.ext[h]);                          // meta, tail_last, tail_a
+        if (key.nbytes > 15) {                                            // same 15-byte prefix: check the rest and the length
+            const unsigned long long ta = (unsigned long long)x.z | ((unsigned long long)x.w << 32);
+            unsigned long long tb, dummy;
+            ld_cg_u64x2(&ws.ext[h].tail_b, tb, dummy);
+            if (ta != key.tail_a || tb != key.tail_b || x.y != key.tail_last) continue;
+        }
+        narrow = pub != kPubExt;
+        if (!narrow && x.x == 0xFFFFFFFFu) return kMemoMiss;              // not cacheable
+        slot = h;
+        meta_out = narrow ? pub : x.x;
         return kMemoHit;
     }
     return kMemoMiss;
 }
-// returns true when the entry now holds the ids (false: too many ids, marked not cacheable)
-__device__ __forceinline__ bool memo_publish(const EncodeWorkspace &ws, uint32_t slot, const MemoKey &key, const uint32_t *buf,
-                                             uint32_t ntok, uint32_t h6, uint32_t *status) {
-    MemoEntry *e = ws.memo + slot;
-    if (ntok > (uint32_t)kMemoTokens || h6 > 0xFFFFFFu) { st_release_u32(&e->meta, 0xFFFFFFFFu); return false; }
-    e->tail_a = key.tail_a; e->tail_b = key.tail_b; e->tail_last = key.tail_last;
-    bool narrow = ntok <= 14 && h6 == 0;                                // servable by the one-load fast path?
-    for (uint32_t k = 0; k < ntok; ++k) { e->tok[k] = buf[k]; narrow = narrow && buf[k] < 65536u; }
-    if (narrow) for (uint32_t k = 0; k < ntok; ++k) e->ids16[k] = (uint16_t)buf[k];
-    st_release_u32(&e->meta, (ntok + 1) | (h6 << 8));                   // release: everything above is visible first
-    if (narrow) atomicOr(reinterpret_cast<uint32_t *>(&e->hi) + 1, (ntok + 1) << 28);   // pub nibble, after the release
-    atomicAdd(&status[kStatusMemoTypes], 1u);
-    return true;
-}
 
 // per-word record between the two passes, packed into 32 bits:
-//   [31:29] kind; Hit / Hit16 (ids16[] valid): [28:23] n_tokens, [22:0] memo slot; Recompute: [28:23] n_tokens;
-//   WP long: [28:0] n_tokens; BPE long: [28:0] scratch granule (16 u32) -- header word 0 holds n_tokens
-enum : uint32_t { kWordNone = 0u, kWordHit = 1u, kWordRecompute = 2u, kWordLong = 3u, kWordLongB = 4u, kWordHit16 = 5u };
-constexpr uint32_t kLongHeader = 16;      // u32 words reserved in front of the two scratch buffers of a long BPE word
+//   [31:29] kind; Hit (32-bit ids in tok32) / Hit16 (ids16[] valid): [28:23] n_tokens, [22:0] memo slot; Recompute: [28:23] n_tokens;
+//   WP long, walked by its lane: [28:0] n_tokens; long word with scratch (BPE; WP segment records): [28:0] scratch granule (16 u32),
+//   header word 0 of the granule holds n_tokens
+enum : uint32_t { kWordNone = 0u, kWordHit = 1u, kWordRecompute = 2u, kWordLong = 3u, kWordLongB = 4u, kWordHit16 = 5u, kWordLongSeg = 6u };
+constexpr uint32_t kLongHeader = 16;      // u32 words reserved in front of the scratch of a long word
 constexpr uint32_t kGroupTiles = 1024;    // tiles per scan group
+
+template <class Enc>
+__device__ __forceinline__ bool ids_are_narrow(const uint32_t *buf, uint32_t ntok, uint32_t h6) {
+    bool nar = ntok <= kNarrowMaxTokens && h6 == 0;
+    uint32_t dummy;
+    for (uint32_t k = 0; k < ntok && nar; ++k) nar = Enc::narrow16(buf[k], k, dummy);
+    return nar;
+}
+
+// Publishes the ids of a claimed slot.  Returns the record kind under which this occurrence is served: kWordHit16 (ids16[]),
+// kWordHit (tok32 arena) or kWordRecompute (not cacheable: the arena is full).
+template <class Enc>
+__device__ __forceinline__ uint32_t memo_publish(const EncodeWorkspace &ws, uint32_t slot, const MemoKey &key, const uint32_t *buf,
+                                                 uint32_t ntok, uint32_t h6, uint32_t *status) {
+    MemoExt *x = ws.ext + slot;
+    if (key.nbytes > 15) { x->tail_a = key.tail_a; x->tail_b = key.tail_b; x->tail_last = key.tail_last; }
+    uint32_t pub, kind;
+    if (ids_are_narrow<Enc>(buf, ntok, h6)) {
+        uint32_t v[14];
+#pragma unroll
+        for (uint32_t k = 0; k < 14; ++k) { v[k] = 0; if (k < ntok) Enc::narrow16(buf[k], k, v[k]); }
+        ws.ids16[2 * (size_t)slot] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+        if (ntok > 8) ws.ids16[2 * (size_t)slot + 1] = make_uint4(v[8] | (v[9] << 16), v[10] | (v[11] << 16), v[12] | (v[13] << 16), 0u);
+        pub = ntok + 1; kind = kWordHit16;
+    } else {
+        const unsigned long long off = ntok <= (uint32_t)kMemoTokens && h6 <= 0xFFFFFFu ? atomicAdd(ws.long_cursor + 1, (unsigned long long)ntok) : ~0ull;
+        if (off != ~0ull && off + ntok <= ws.tok32_cap) {
+            for (uint32_t k = 0; k < ntok; ++k) ws.tok32[off + k] = buf[k];
+            x->tok32_off = (uint32_t)off; x->meta = (ntok + 1) | (h6 << 8); kind = kWordHit;
+        } else { x->meta = 0xFFFFFFFFu; kind = kWordRecompute; }
+        pub = kPubExt;
+    }
+    __threadfence();                                                      // release: everything above is performed before the pub nibble
+    atomicOr(reinterpret_cast<uint32_t *>(ws.keys + slot) + 3, pub << 28);
+    atomicAdd(&status[kStatusMemoTypes], 1u);
+    return kind;
+}
 
 struct SlowResult { uint32_t kind, ntok, slot, h6; };
 
 // pass 1 slow path (first probe did not hit): full probe at L2, then direct encode + publish.  Out of line so that
 // the unrolled fast path stays small.
 template <class Enc>
-__device__ __noinline__ SlowResult resolve_slow(const Enc &enc, const EncodeWorkspace &ws, const uint8_t *arena, uint32_t b0,
-                                                uint32_t nbytes, uint32_t arena_end, uint32_t *status) {
+__device__ __noinline__ SlowResult resolve_slow(const Enc &enc, const typename Enc::Stage *sg, const EncodeWorkspace &ws, const uint8_t *arena,
+                                                uint32_t b0, uint32_t nbytes, uint32_t arena_end, uint32_t *status) {
     uint32_t buf[kShortBytes];                                   // scratch for one directly encoded word
     SlowResult r; r.kind = kWordRecompute; r.ntok = 0; r.slot = 0; r.h6 = 0;
-    int m = kMemoMiss; uint32_t meta = 0; MemoKey key;
-    if (ws.memo_mask && nbytes >= 1) { memo_key(arena, b0, nbytes, arena_end, key); m = memo_probe(ws, key, r.slot, meta); }
-    if (m == kMemoHit) { r.kind = kWordHit; r.ntok = (meta & 0xFFu) - 1; r.h6 = meta >> 8; return r; }
-    r.ntok = enc.encode_short(arena + b0, nbytes, buf, r.h6);
-    if (m == kMemoClaimed && memo_publish(ws, r.slot, key, buf, r.ntok, r.h6, status)) r.kind = kWordHit;
-    // the owner publishes under the same condition (memo_publish), so the ids will be there for the emit pass
-    if (m == kMemoPending && r.ntok <= (uint32_t)kMemoTokens && r.h6 <= 0xFFFFFFu) r.kind = kWordHit;
+    int m = kMemoMiss; uint32_t meta = 0; MemoKey key; bool narrow = false;
+    if (ws.memo_mask && nbytes >= 1) { memo_key(arena, b0, nbytes, arena_end, key); m = memo_probe(ws, key, r.slot, meta, narrow); }
+    if (m == kMemoHit) {
+        if (narrow) { r.kind = kWordHit16; r.ntok = meta - 1; }
+        else { r.kind = kWordHit; r.ntok = (meta & 0xFFu) - 1; r.h6 = meta >> 8; }
+        return r;
+    }
+    r.ntok = enc.encode_short(sg, arena + b0, nbytes, buf, r.h6);
+    if (m == kMemoClaimed) r.kind = memo_publish<Enc>(ws, r.slot, key, buf, r.ntok, r.h6, status);
+    // Pending: the owner publishes the same ids in the same form (memo_publish is a function of the ids); an id list that goes to the
+    // tok32 arena may turn out not cacheable, which the emit pass sees in ext[slot].meta and answers by re-encoding
+    else if (m == kMemoPending) r.kind = ids_are_narrow<Enc>(buf, r.ntok, r.h6) ? kWordHit16 : kWordHit;
     return r;
 }
-// pass 2 slow paths: re-encode a word whose ids were not kept, or emit a long word (Enc without scratch)
+// The same for ONE word by the whole warp (Enc::kWarpShort): lane 0 probes (and claims), all lanes encode (encode_short_warp leaves
+// the ids in `ids`, 32 words of shared memory), lane 0 publishes.  The result is returned on every lane.
+template <class Enc>
+__device__ __noinline__ SlowResult resolve_slow_warp(const Enc &enc, const typename Enc::Stage *sg, const EncodeWorkspace &ws, const uint8_t *arena,
+                                                     uint32_t b0, uint32_t nbytes, uint32_t arena_end, uint32_t *status, uint32_t *ids) {
+    const uint32_t lane = threadIdx.x & 31;
+    int pm = kMemoMiss; uint32_t pslot = 0, pmeta = 0; bool pnarrow = false; MemoKey key;
+    if (lane == 0 && ws.memo_mask && nbytes >= 1) { memo_key(arena, b0, nbytes, arena_end, key); pm = memo_probe(ws, key, pslot, pmeta, pnarrow); }
+    pm = __shfl_sync(0xffffffffu, pm, 0);
+    SlowResult r; r.kind = kWordRecompute; r.ntok = 0; r.slot = pslot; r.h6 = 0;
+    if (pm == kMemoHit) {
+        if (pnarrow) { r.kind = kWordHit16; r.ntok = pmeta - 1; } else { r.kind = kWordHit; r.ntok = (pmeta & 0xFFu) - 1; }
+    } else {
+        const uint32_t n = enc.encode_short_warp(sg, arena + b0, nbytes, ids);       // ids[0..n)
+        __syncwarp();
+        r.ntok = n;
+        if (lane == 0) {
+            if (pm == kMemoClaimed) r.kind = memo_publish<Enc>(ws, pslot, key, ids, n, 0u, status);
+            else if (pm == kMemoPending) r.kind = ids_are_narrow<Enc>(ids, n, 0u) ? kWordHit16 : kWordHit;
+        }
+        __syncwarp();
+    }
+    r.kind = __shfl_sync(0xffffffffu, r.kind, 0); r.ntok = __shfl_sync(0xffffffffu, r.ntok, 0); r.slot = __shfl_sync(0xffffffffu, r.slot, 0);
+    return r;
+}
+
+// The slow words of one tile row (ballot m; this lane's word is b0 / nbytes when its bit is set), resolved now: up to `warp_words` of
+// them one after the other by the whole warp (Enc::kWarpShort), more of them one word per lane.  Returns this lane's own result
+// (h6: the events this lane counted while resolving, for whichever word).
+template <class Enc>
+__device__ __noinline__ SlowResult resolve_slow_tile(const Enc &enc, const typename Enc::Stage *sg, const EncodeWorkspace &ws, const uint8_t *arena,
+                                                     uint32_t arena_end, uint32_t *status, uint32_t *ids, uint32_t m, uint32_t b0, uint32_t nbytes,
+                                                     uint32_t warp_words) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n_slow = __popc(m);
+    SlowResult mine; mine.kind = kWordNone; mine.ntok = 0; mine.slot = 0; mine.h6 = 0;
+    if constexpr (Enc::kWarpShort) {
+        if (n_slow <= warp_words) {
+            for (uint32_t mm = m; mm;) {
+                const uint32_t owner = __ffs(mm) - 1; mm &= mm - 1;
+                const uint32_t sb0 = __shfl_sync(0xffffffffu, b0, owner), snb = __shfl_sync(0xffffffffu, nbytes, owner);
+                const SlowResult r = resolve_slow_warp(enc, sg, ws, arena, sb0, snb, arena_end, status, ids);   // same on all lanes
+                if (lane == owner) mine = r;
+            }
+            return mine;
+        }
+    }
+    const uint32_t src = __fns(m, 0, lane + 1);                                     // lane -> owner of the lane-th slow word
+    const uint32_t sb0 = __shfl_sync(0xffffffffu, b0, src & 31), snb = __shfl_sync(0xffffffffu, nbytes, src & 31);
+    SlowResult r; r.kind = kWordNone; r.ntok = 0; r.slot = 0; r.h6 = 0;
+    if (lane < n_slow) r = resolve_slow(enc, sg, ws, arena, sb0, snb, arena_end, status);
+    const uint32_t rank = __popc(m & ((1u << lane) - 1u));                          // this lane's word was resolved by lane `rank`
+    mine.kind = __shfl_sync(0xffffffffu, r.kind, rank); mine.ntok = __shfl_sync(0xffffffffu, r.ntok, rank);
+    mine.slot = __shfl_sync(0xffffffffu, r.slot, rank); mine.h6 = r.h6;
+    return mine;
+}
+
+// pass 2 slow path: re-encode a short word whose ids were not kept
 template <class Enc>
 __device__ __noinline__ void emit_slow(const Enc &enc, const uint8_t *word, uint32_t nbytes, uint32_t kind, uint32_t ntok,
                                        uint32_t *dst) {
-    if (kind == kWordRecompute) {
-        uint32_t buf[kShortBytes];
-        uint32_t dummy = 0;
-        const uint32_t n = enc.encode_short(word, nbytes, buf, dummy);
-        for (uint32_t k = 0; k < n; ++k) dst[k] = buf[k];
-    } else if constexpr (!Enc::kScratchLong) {
-        uint32_t dummy = 0;
-        enc.long_emit(word, nbytes, dst, ntok, dummy);
-    }
+    (void)kind; (void)ntok;
+    uint32_t buf[kShortBytes];
+    uint32_t dummy = 0;
+    const uint32_t n = enc.encode_short(nullptr, word, nbytes, buf, dummy);
+    for (uint32_t k = 0; k < n; ++k) dst[k] = buf[k];
 }
 
-// ids of a one-load hit (16-bit ids, at most 14) -> dst.  The first eight are predicated stores without branches
+// ids of a one-load hit (16-bit ids, at most 13) -> dst.  The first eight are predicated stores without branches
 // (a branch per token cost more than the stores); the rare second half sits behind one warp-uniform test.
 template <bool kShared>
 __device__ __forceinline__ void store_id_if(uint32_t *dst, uint32_t k, uint32_t n, uint32_t v) {
@@ -271,59 +378,54 @@ __device__ __forceinline__ void store_id_if(uint32_t *dst, uint32_t k, uint32_t 
         asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %0, %1;\n\t@p st.global.u32 [%2], %3;\n\t}" ::"r"(n), "r"(k), "l"(dst + k), "r"(v) : "memory");
     }
 }
-template <bool kShared>
+template <class Enc, bool kShared>
 __device__ __forceinline__ void store_hit16_ids(uint32_t *dst, uint32_t n, uint4 a, uint4 b) {
-    store_id_if<kShared>(dst, 0, n, a.x & 0xFFFFu); store_id_if<kShared>(dst, 1, n, a.x >> 16);
-    store_id_if<kShared>(dst, 2, n, a.y & 0xFFFFu); store_id_if<kShared>(dst, 3, n, a.y >> 16);
-    store_id_if<kShared>(dst, 4, n, a.z & 0xFFFFu); store_id_if<kShared>(dst, 5, n, a.z >> 16);
-    store_id_if<kShared>(dst, 6, n, a.w & 0xFFFFu); store_id_if<kShared>(dst, 7, n, a.w >> 16);
+    store_id_if<kShared>(dst, 0, n, Enc::expand16(a.x & 0xFFFFu, 0)); store_id_if<kShared>(dst, 1, n, Enc::expand16(a.x >> 16, 1));
+    store_id_if<kShared>(dst, 2, n, Enc::expand16(a.y & 0xFFFFu, 2)); store_id_if<kShared>(dst, 3, n, Enc::expand16(a.y >> 16, 3));
+    store_id_if<kShared>(dst, 4, n, Enc::expand16(a.z & 0xFFFFu, 4)); store_id_if<kShared>(dst, 5, n, Enc::expand16(a.z >> 16, 5));
+    store_id_if<kShared>(dst, 6, n, Enc::expand16(a.w & 0xFFFFu, 6)); store_id_if<kShared>(dst, 7, n, Enc::expand16(a.w >> 16, 7));
     if (n > 8) {
-        store_id_if<kShared>(dst, 8, n, b.x & 0xFFFFu); store_id_if<kShared>(dst, 9, n, b.x >> 16);
-        store_id_if<kShared>(dst, 10, n, b.y & 0xFFFFu); store_id_if<kShared>(dst, 11, n, b.y >> 16);
-        store_id_if<kShared>(dst, 12, n, b.z & 0xFFFFu); store_id_if<kShared>(dst, 13, n, b.z >> 16);
-    }
-}
-// ids of a hit found by the slow path (32-bit id list; ids 0-7 were prefetched, the rest is fetched here)
-__device__ __forceinline__ void store_hit_ids(uint32_t *dst, uint32_t n, uint4 a, uint4 b, const MemoEntry *e) {
-    if (n > 0) dst[0] = a.x;
-    if (n > 1) dst[1] = a.y;
-    if (n > 2) dst[2] = a.z;
-    if (n > 3) dst[3] = a.w;
-    if (n > 4) dst[4] = b.x;
-    if (n > 5) dst[5] = b.y;
-    if (n > 6) dst[6] = b.z;
-    if (n > 7) dst[7] = b.w;
-    for (uint32_t k0 = 8; k0 < n; k0 += 4) {
-        const uint4 v = ld_ca_u32x4(&e->tok[k0]);
-        dst[k0] = v.x;
-        if (k0 + 1 < n) dst[k0 + 1] = v.y;
-        if (k0 + 2 < n) dst[k0 + 2] = v.z;
-        if (k0 + 3 < n) dst[k0 + 3] = v.w;
+        store_id_if<kShared>(dst, 8, n, Enc::expand16(b.x & 0xFFFFu, 8)); store_id_if<kShared>(dst, 9, n, Enc::expand16(b.x >> 16, 9));
+        store_id_if<kShared>(dst, 10, n, Enc::expand16(b.y & 0xFFFFu, 10)); store_id_if<kShared>(dst, 11, n, Enc::expand16(b.y >> 16, 11));
+        store_id_if<kShared>(dst, 12, n, Enc::expand16(b.z & 0xFFFFu, 12));
     }
 }
 
-// clears key and meta of every memo entry (the rest of an entry is only read after its meta / pub nibble was published)
-static __global__ void __launch_bounds__(256) memo_clear_kernel(MemoEntry *memo, uint32_t n_slots, unsigned long long *long_cursor) {
+// clears the keys of the memo (ids16 / ext / tok32 are only read after a pub nibble was published) and the two cursors
+static __global__ void __launch_bounds__(256) memo_clear_kernel(uint4 *keys, uint32_t n_slots, unsigned long long *long_cursor) {
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) {
-        uint4 *e = reinterpret_cast<uint4 *>(memo + i);
-        e[0] = z; e[1] = z;                                 // key (bytes 0-15) and meta / tail_last (bytes 16-31): one sector
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *long_cursor = 0ull;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) keys[i] = z;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { long_cursor[0] = 0ull; long_cursor[1] = 0ull; }
 }
 
 // resolves `count` (<= 32) pending words of a warp, one per lane: record, token count into the tile total.  Returns the lane's
 // H6 events.  Out of line: keeps the registers of the slow path out of the count loop.
 template <class Enc>
-__device__ __noinline__ uint32_t flush_pending_words(const Enc &enc, const EncodeWorkspace &ws, const uint8_t *arena, const uint32_t *word_off,
-                                                     uint32_t arena_end, uint32_t *status, const uint32_t *pend, uint32_t count) {
+__device__ __noinline__ uint32_t flush_pending_words(const Enc &enc, const typename Enc::Stage *sg, const EncodeWorkspace &ws, const uint8_t *arena,
+                                                     const uint32_t *word_off, uint32_t arena_end, uint32_t *status, const uint32_t *pend,
+                                                     uint32_t count, uint32_t warp_words, uint32_t *ids) {
     const uint32_t lane = threadIdx.x & 31;
     uint32_t h6 = 0;
+    if constexpr (Enc::kWarpShort) {
+        if (count <= warp_words) {                              // a few left-over words: the whole warp encodes them one after the other
+            for (uint32_t k = 0; k < count; ++k) {
+                const uint32_t w = pend[k];
+                const uint32_t wb0 = __ldg(word_off + w), wnb = __ldg(word_off + w + 1) - wb0;
+                const SlowResult r = resolve_slow_warp(enc, sg, ws, arena, wb0, wnb, arena_end, status, ids);
+                if (lane == 0) {
+                    ws.packed[w] = (r.kind << 29) | (r.ntok << 23) | ((r.kind == kWordHit || r.kind == kWordHit16) ? r.slot : 0u);
+                    if (r.ntok) atomicAdd(&ws.tile_total[w / kTileWords], r.ntok);
+                }
+            }
+            __syncwarp();
+            return 0u;
+        }
+    }
     if (lane < count) {
         const uint32_t w = pend[lane];
         const uint32_t wb0 = __ldg(word_off + w), wnb = __ldg(word_off + w + 1) - wb0;
-        const SlowResult r = resolve_slow(enc, ws, arena, wb0, wnb, arena_end, status);
-        ws.packed[w] = (r.kind << 29) | (r.ntok << 23) | (r.kind == kWordHit ? r.slot : 0u);
+        const SlowResult r = resolve_slow(enc, sg, ws, arena, wb0, wnb, arena_end, status);
+        ws.packed[w] = (r.kind << 29) | (r.ntok << 23) | ((r.kind == kWordHit || r.kind == kWordHit16) ? r.slot : 0u);
         if (r.ntok) atomicAdd(&ws.tile_total[w / kTileWords], r.ntok);
         h6 = r.h6;
     }
@@ -333,9 +435,13 @@ __device__ __noinline__ uint32_t flush_pending_words(const Enc &enc, const Encod
 
 // ---- pass 1: count ---------------------------------------------------------------------------------------------------
 // Enc provides
-//   uint32_t encode_short(const uint8_t *p, uint32_t nbytes, uint32_t *buf /*thread-local, kShortBytes*/, uint32_t &h6) const
-//   static constexpr bool kScratchLong, kBatchSlowPath
+//   struct Stage; void stage_init(Stage &) const   tables the CTA keeps in shared memory (FastBPE: Bloom filter + hot low-rank merges)
+//   uint32_t encode_short(const Stage *, const uint8_t *p, uint32_t nbytes, uint32_t *buf /*thread-local, kShortBytes*/, uint32_t &h6) const
+//   static bool narrow16(uint32_t id, uint32_t k, uint32_t &v16);  static uint32_t expand16(uint32_t v16, uint32_t k)
+//   static constexpr bool kScratchLong, kBatchSlowPath, kWarpShort, kWarpLong
+//   kWarpShort           : uint32_t encode_short_warp(const Stage *, p, nbytes, uint32_t *ids_smem /*32*/) const   (all 32 lanes, one word)
 //   kScratchLong == false: uint32_t long_count(p, nbytes, h6) const;  void long_emit(p, nbytes, uint32_t *dst, uint32_t cap, uint32_t &h6) const
+//   kWarpLong            : long_scratch_need(nbytes); long_count_warp(p, nbytes, scratch, h6); long_emit_warp(p, nbytes, scratch, dst, n)
 //   kScratchLong == true : uint32_t encode_long_warp(p, nbytes, bufA, bufB, uint32_t **result) const   (all 32 lanes)
 //
 // Every warp owns tiles of kTileWords = 64 consecutive words (2 per lane), assigned round-robin; warps never wait for
@@ -343,12 +449,15 @@ __device__ __noinline__ uint32_t flush_pending_words(const Enc &enc, const Encod
 template <class Enc>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words,
-                    EncodeWorkspace ws, uint32_t *status) {
+                    EncodeWorkspace ws, uint32_t *status, uint32_t warp_words) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * kThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kThreads) >> 5;
     const uint32_t arena_end = word_off[n_words];
     const bool use_memo = ws.memo_mask != 0;
     uint32_t h6 = 0;
+    __shared__ typename Enc::Stage s_stage;
+    enc.stage_init(s_stage);                                        // cooperative copy + __syncthreads (no-op for encoders without tables)
+    const typename Enc::Stage *sg = &s_stage;
 
     // offsets of this lane's two words in a tile (three consecutive offsets); the next tile's are fetched one tile ahead
     auto load_offsets = [&](uint32_t t, uint32_t &o0, uint32_t &o1, uint32_t &o2) {
@@ -357,13 +466,14 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
         o1 = i0 + 1 <= tw ? __ldg(word_off + w0 + i0 + 1) : 0u;
         o2 = i0 + 2 <= tw ? __ldg(word_off + w0 + i0 + 2) : 0u;
     };
-    // pending queue of the warp: words waiting for the slow path (at most 31 left over + 64 from one tile)
-    __shared__ uint32_t s_pend[kWarps][96];
+    // pending queue of the warp: words waiting for the slow path (at most 31 left over + 64 from one tile), followed by the 32-word
+    // id staging row of the warp-per-word encoder (FastBPE)
+    __shared__ uint32_t s_pend[kWarps][96 + 32];
     uint32_t *pend = s_pend[threadIdx.x >> 5];
     uint32_t n_pend = 0;
     uint32_t n_slow_words = 0;                                                      // diagnostic (status word 5), warp-uniform
     auto flush_pending = [&](uint32_t first, uint32_t count) {
-        h6 += flush_pending_words(enc, ws, arena, word_off, arena_end, status, pend + first, count);
+        h6 += flush_pending_words(enc, sg, ws, arena, word_off, arena_end, status, pend + first, count, warp_words, pend + 96);
         n_slow_words += count;
     };
     uint32_t po0 = 0, po1 = 0, po2 = 0;
@@ -379,7 +489,7 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
             b0s[0] = o0; nb[0] = i0 < tile_words ? o1 - o0 : 0xFFFFFFFFu;       // 0xFFFFFFFF: no word
             b0s[1] = o1; nb[1] = i0 + 1 < tile_words ? o2 - o1 : 0xFFFFFFFFu;
         }
-        // ---- fast path (words of 1..15 bytes): 128-bit key from aligned 8-byte loads, then up to two L1-cached memo
+        // ---- fast path (words of 1..32 bytes): 128-bit key from aligned 4-byte loads, then up to two L1-cached memo
         // probes.  Both words' loads are in flight together.
         uint32_t kind[kWordsPerThread], ntok[kWordsPerThread], slot[kWordsPerThread];
         uint4 kw[kWordsPerThread], ew[kWordsPerThread];           // key of the word / key found in the probed entry
@@ -409,12 +519,12 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
                     const uint32_t sh = (uint32_t)((uintptr_t)(arena + b0s[j]) & 3) * 8, n = min(nb[j], 15u);
                     uint32_t w0 = __funnelshift_r(a0[j], a1[j], sh), w1 = __funnelshift_r(a1[j], a2[j], sh);
                     uint32_t w2 = __funnelshift_r(a2[j], a3[j], sh), w3 = __funnelshift_r(a3[j], a4[j], sh);
-                    // zero the bytes at and beyond n, put the length into the top byte (layout of MemoEntry::lo/hi)
+                    // zero the bytes at and beyond n, put the length into the top byte (layout of the key: lo | hi)
                     w0 &= low_bytes_mask((int)n); w1 &= low_bytes_mask((int)n - 4); w2 &= low_bytes_mask((int)n - 8);
                     w3 = (w3 & low_bytes_mask((int)n - 12)) | ((nb[j] <= 15u ? n : 0u) << 24);
                     kw[j] = make_uint4(w0, w1, w2, w3);
                     slot[j] = memo_hash4(w0, w1, w2, w3) & ws.memo_mask;
-                    ew[j] = ld_ca_u32x4(ws.memo + slot[j]);      // ONE scattered load per word: key + pub nibble
+                    ew[j] = ld_ca_u32x4(ws.keys + slot[j]);      // ONE scattered load per word: key + pub nibble
                 }
             }
         }
@@ -426,29 +536,34 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
             if (fastj[j]) {
                 bool same = ew[j].x == kw[j].x && ew[j].y == kw[j].y && ew[j].z == kw[j].z && ((ew[j].w ^ kw[j].w) & 0x0FFFFFFFu) == 0;
                 if (!same && (ew[j].x | ew[j].y | ew[j].z | ew[j].w) != 0) {
-                    // the slot holds another word (hash collision): look at the next slot
+                    // the slot holds another word (hash collision): look at the next slot (usually the same 32-byte sector)
                     slot[j] = (slot[j] + 1) & ws.memo_mask;
-                    ew[j] = ld_ca_u32x4(ws.memo + slot[j]);
+                    ew[j] = ld_ca_u32x4(ws.keys + slot[j]);
                     same = ew[j].x == kw[j].x && ew[j].y == kw[j].y && ew[j].z == kw[j].z && ((ew[j].w ^ kw[j].w) & 0x0FFFFFFFu) == 0;
                 }
-                hit = same && (ew[j].w >> 28) != 0;                  // pub nibble: ids16[] valid, n_tokens + 1
-                if (hit && nb[j] > 15u) {                            // rare: compare bytes 15.. with the tail stored in the entry
+                const uint32_t pub = ew[j].w >> 28;
+                hit = same && pub != 0 && pub != kPubExt;            // pub nibble: ids16[] valid, n_tokens + 1
+                if (hit && nb[j] > 15u) {                            // rare: compare bytes 15.. with the tail stored beside the entry
                     MemoKey key;
                     memo_key(arena, b0s[j], nb[j], arena_end, key);
-                    const MemoEntry *e = ws.memo + slot[j];
-                    unsigned long long ta, tb;
-                    ld_ca_u64x2(&e->tail_a, ta, tb);
-                    hit = ta == key.tail_a && tb == key.tail_b && ld_ca_u32(&e->tail_last) == key.tail_last;
+                    const MemoExt *e = ws.ext + slot[j];
+                    const uint4 x = ld_ca_u32x4(e);
+                    unsigned long long tb, dummy;
+                    ld_ca_u64x2(&e->tail_b, tb, dummy);
+                    hit = ((unsigned long long)x.z | ((unsigned long long)x.w << 32)) == key.tail_a && tb == key.tail_b && x.y == key.tail_last;
                 }
+                if (hit) ntok[j] = pub - 1;
             }
-            if (hit) { kind[j] = kWordHit16; ntok[j] = (ew[j].w >> 28) - 1; }
+            if (hit) kind[j] = kWordHit16;
             else slow[j] = true;
         }
-        // Words not served by the first probe (first occurrence, hash collision, more than 14 tokens).  A single trie walk /
-        // merge loop is a chain of dependent L2 accesses (10-25 us) during which the other lanes of the warp would idle.
-        // kBatchSlowPath: they go to the warp's pending queue and are resolved 32 at a time, one per lane (flush below) --
-        // 5 % faster on the bench stream for FastWP and 30-40 % on streams with 10^5..10^6 word types.  Otherwise (FastBPE,
-        // where the queue cost the count pass 10 %): the slow words of the tile are spread over the lanes and resolved now.
+        // Words not served by the first probe (first occurrence, hash collision, ids that need the 32-bit list).  A single trie
+        // walk / merge loop is a chain of dependent L2 accesses (10-25 us) during which the other lanes of the warp would idle.
+        // kBatchSlowPath (FastWP): they go to the warp's pending queue and are resolved 32 at a time, one per lane (flush below) --
+        // 5 % faster on the bench stream and 30-40 % on streams with 10^5..10^6 word types.  Otherwise (FastBPE, where the queue
+        // cost the count pass 10 %): a few slow words are encoded by the WHOLE WARP one after the other (kWarpShort: one lane per
+        // adjacent pair, shuffle min-reduce -- latency of a word = its merges, not its pair probes); more than `warp_words` of
+        // them are spread over the lanes, one word per lane.
         if constexpr (Enc::kBatchSlowPath) {
 #pragma unroll
             for (int j = 0; j < kWordsPerThread; ++j) {
@@ -462,48 +577,19 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
             for (int j = 0; j < kWordsPerThread; ++j) {
                 const uint32_t m = __ballot_sync(0xffffffffu, slow[j]);
                 if (m == 0) continue;                                               // warp-uniform
-                const uint32_t n_slow = __popc(m);
-                const uint32_t src = __fns(m, 0, lane + 1);                         // lane -> owner of the lane-th slow word
-                const uint32_t sb0 = __shfl_sync(0xffffffffu, b0s[j], src & 31), snb = __shfl_sync(0xffffffffu, nb[j], src & 31);
-                SlowResult r; r.kind = kWordNone; r.ntok = 0; r.slot = 0; r.h6 = 0;
-                if (lane < n_slow) r = resolve_slow(enc, ws, arena, sb0, snb, arena_end, status);
+                n_slow_words += __popc(m);
+                const SlowResult r = resolve_slow_tile(enc, sg, ws, arena, arena_end, status, pend + 96, m, b0s[j], nb[j], warp_words);
                 h6 += r.h6;
-                const uint32_t rank = __popc(m & ((1u << lane) - 1u));             // this lane's word was resolved by lane `rank`
-                const uint32_t k_ = __shfl_sync(0xffffffffu, r.kind, rank), n_ = __shfl_sync(0xffffffffu, r.ntok, rank);
-                const uint32_t s_ = __shfl_sync(0xffffffffu, r.slot, rank);
-                if (slow[j]) { kind[j] = k_; ntok[j] = n_; slot[j] = s_; slow[j] = false; }
-                n_slow_words += n_slow;
+                if (slow[j]) { kind[j] = r.kind; ntok[j] = r.ntok; slot[j] = r.slot; slow[j] = false; }
             }
         }
-        // long words (rare)
+        // long words (rare): left to encode_long_count_kernel, which runs between this pass and the scan; here the tile is only
+        // flagged, so that the code of the long paths (warp-cooperative merge loop / segment walk) stays out of this kernel
         uint32_t packed[kWordsPerThread];
 #pragma unroll
-        for (int j = 0; j < kWordsPerThread; ++j) {
+        for (int j = 0; j < kWordsPerThread; ++j)
             packed[j] = (kind[j] << 29) | (ntok[j] << 23) | ((kind[j] == kWordHit || kind[j] == kWordHit16) ? slot[j] : 0u);
-            if constexpr (!Enc::kScratchLong) {
-                if (is_long[j]) { ntok[j] = enc.long_count(arena + b0s[j], nb[j], h6); packed[j] = (kWordLong << 29) | ntok[j]; }
-            } else {
-                uint32_t m = __ballot_sync(0xffffffffu, is_long[j]);
-                while (m) {                                                         // the whole warp works on one long word
-                    const uint32_t owner = __ffs(m) - 1; m &= m - 1;
-                    const uint32_t lb0 = __shfl_sync(0xffffffffu, b0s[j], owner), lnb = __shfl_sync(0xffffffffu, nb[j], owner);
-                    const unsigned long long need = (kLongHeader + 2ull * lnb + 15ull) & ~15ull;
-                    unsigned long long so = 0;
-                    if (lane == 0) so = atomicAdd(ws.long_cursor, need);
-                    so = __shfl_sync(0xffffffffu, so, 0);
-                    uint32_t c = 0; uint32_t *res = nullptr;
-                    const bool fits = so + need <= ws.long_scratch_elems && (so >> 4) < (1ull << 29);
-                    uint32_t *bufA = ws.long_scratch + so + kLongHeader;
-                    if (fits) c = enc.encode_long_warp(arena + lb0, lnb, bufA, bufA + lnb, &res);
-                    else if (lane == 0) atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY);
-                    if (lane == owner) {
-                        ntok[j] = c;
-                        if (fits) { ws.long_scratch[so] = c; packed[j] = ((res == bufA ? kWordLong : kWordLongB) << 29) | (uint32_t)(so >> 4); }
-                        else packed[j] = 0;
-                    }
-                }
-            }
-        }
+        if (__any_sync(0xffffffffu, is_long[0] || is_long[1])) { if (lane == 0) atomicOr(&ws.long_tiles[tile >> 5], 1u << (tile & 31u)); }
         // ---- per-word records and the tile total (pending words: record and token count are added by the flush)
         {
             const uint32_t i0 = lane * kWordsPerThread;
@@ -525,6 +611,140 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
     if constexpr (Enc::kBatchSlowPath) { if (n_pend) flush_pending(0, n_pend); }
     if (h6) atomicAdd(&status[kStatusH6], h6);
     if (lane == 0 && n_slow_words) atomicAdd(&status[kStatusSlowWords], n_slow_words);
+}
+
+// ---- long words (> kShortBytes), between pass 1 and the scan -------------------------------------------------------------------
+// One warp per flagged tile: for every long word of the tile the whole warp runs the encoder's long path, writes the word's final
+// record and adds its tokens to the tile total.
+//   kScratchLong (BPE): merge loop over symbols in global scratch, result kept there (record = scratch granule)
+//   kWarpLong (FastWP) with scratch: the chunk's segments are walked by different lanes (record = granule of the segment records)
+//   otherwise: the owning lane walks the word alone (record = token count; walked again by encode_long_emit_kernel)
+template <class Enc>
+__global__ void __launch_bounds__(256) encode_long_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off,
+                                                                uint32_t n_words, EncodeWorkspace ws, uint32_t *status) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n_bm = (ws.n_tiles + 31) >> 5;
+    uint32_t h6 = 0;
+    for (uint32_t bw = warp_global; bw < n_bm; bw += n_warps) {
+        uint32_t bits = ws.long_tiles[bw];                                          // warp-uniform
+        while (bits) {
+            const uint32_t tile = (bw << 5) + (__ffs(bits) - 1); bits &= bits - 1;
+            const uint32_t w_tile = tile * kTileWords, tile_words = min((uint32_t)kTileWords, n_words - w_tile);
+            uint32_t added = 0;
+            for (uint32_t k = 0; k < tile_words; ++k) {                             // warp-uniform loop over the tile's words
+                const uint32_t w = w_tile + k;
+                const uint32_t lb0 = __ldg(word_off + w), lnb = __ldg(word_off + w + 1) - lb0;
+                if (lnb <= (uint32_t)kShortBytes) continue;
+                uint32_t rec = 0, c = 0;
+                if constexpr (Enc::kScratchLong) {
+                    const unsigned long long need = (kLongHeader + 2ull * lnb + 15ull) & ~15ull;
+                    unsigned long long so = 0;
+                    if (lane == 0) so = atomicAdd(ws.long_cursor, need);
+                    so = __shfl_sync(0xffffffffu, so, 0);
+                    const bool fits = so + need <= ws.long_scratch_elems && (so >> 4) < (1ull << 29);
+                    uint32_t *res = nullptr;
+                    uint32_t *bufA = ws.long_scratch + so + kLongHeader;
+                    if (fits) {
+                        c = enc.encode_long_warp(arena + lb0, lnb, bufA, bufA + lnb, &res);
+                        if (lane == 0) ws.long_scratch[so] = c;
+                        rec = ((res == bufA ? kWordLong : kWordLongB) << 29) | (uint32_t)(so >> 4);
+                    } else if (lane == 0) atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY);
+                } else {
+                    bool done = false;
+                    if constexpr (Enc::kWarpLong) {
+                        const unsigned long long need = Enc::long_scratch_need(lnb);
+                        unsigned long long so = 0;
+                        if (lane == 0 && ws.long_scratch_elems) so = atomicAdd(ws.long_cursor, need);
+                        so = __shfl_sync(0xffffffffu, so, 0);
+                        if (ws.long_scratch_elems && so + need <= ws.long_scratch_elems && (so >> 4) < (1ull << 29)) {
+                            uint32_t lh6 = 0;
+                            c = enc.long_count_warp(arena + lb0, lnb, ws.long_scratch + so, lh6);
+                            h6 += lh6;
+                            rec = (kWordLongSeg << 29) | (uint32_t)(so >> 4);
+                            done = true;
+                        }
+                    }
+                    if (!done) {
+                        if (lane == 0) c = enc.long_count(arena + lb0, lnb, h6);
+                        c = __shfl_sync(0xffffffffu, c, 0);
+                        if (c >= (1u << 29)) { if (lane == 0) atomicExch(&status[kStatusCode], (uint32_t)SWT_ERR_CAPACITY); c = 0; }
+                        rec = (kWordLong << 29) | c;
+                    }
+                }
+                if (lane == 0) ws.packed[w] = rec;
+                added += c;
+            }
+            if (lane == 0 && added) atomicAdd(&ws.tile_total[tile], added);
+        }
+    }
+    if (h6) atomicAdd(&status[kStatusH6], h6);
+}
+
+// token count of a per-word record (after encode_long_count_kernel)
+template <class Enc>
+__device__ __forceinline__ uint32_t record_ntok(uint32_t packed, const uint32_t *long_scratch) {
+    const uint32_t kind = packed >> 29, arg = packed & 0x1FFFFFFFu;
+    if (kind == kWordHit || kind == kWordHit16 || kind == kWordRecompute) return arg >> 23;
+    if (kind == kWordLongSeg || (Enc::kScratchLong && (kind == kWordLong || kind == kWordLongB))) return long_scratch[(unsigned long long)arg << 4];
+    if (kind == kWordLong) return arg;
+    return 0u;
+}
+
+// ---- long words, after pass 2: their ids are written at their final position (pass 2 left the gap) ------------------------------
+template <class Enc>
+__global__ void __launch_bounds__(256) encode_long_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off,
+                                                               uint32_t n_words, uint32_t *__restrict__ out_ids, uint64_t out_cap, EncodeWorkspace ws) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n_bm = (ws.n_tiles + 31) >> 5;
+    for (uint32_t bw = warp_global; bw < n_bm; bw += n_warps) {
+        uint32_t bits = ws.long_tiles[bw];
+        while (bits) {
+            const uint32_t tile = (bw << 5) + (__ffs(bits) - 1); bits &= bits - 1;
+            const uint32_t w_tile = tile * kTileWords, tile_words = min((uint32_t)kTileWords, n_words - w_tile);
+            const uint64_t base = ws.group_base[tile / kGroupTiles] + ws.tile_total[tile];
+            // tile-local token offsets of the words: lane holds words 2*lane, 2*lane + 1 like pass 2
+            const uint32_t i0 = lane * kWordsPerThread;
+            uint32_t pk[kWordsPerThread], nt[kWordsPerThread], run[kWordsPerThread], count = 0;
+#pragma unroll
+            for (int j = 0; j < kWordsPerThread; ++j) {
+                pk[j] = i0 + j < tile_words ? ws.packed[w_tile + i0 + j] : 0u;
+                nt[j] = record_ntok<Enc>(pk[j], ws.long_scratch);
+                run[j] = count; count += nt[j];
+            }
+            uint32_t incl = count;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += v; }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (base + total > out_cap) continue;                                   // status set by the scan
+#pragma unroll
+            for (int j = 0; j < kWordsPerThread; ++j) {
+                run[j] += incl - count;
+                const uint32_t kj = pk[j] >> 29;
+                uint32_t lm = __ballot_sync(0xffffffffu, kj == kWordLong || kj == kWordLongB || kj == kWordLongSeg);
+                while (lm) {
+                    const uint32_t owner = __ffs(lm) - 1; lm &= lm - 1;
+                    const uint32_t ln = __shfl_sync(0xffffffffu, nt[j], owner), lrun = __shfl_sync(0xffffffffu, run[j], owner);
+                    const uint32_t lpk = __shfl_sync(0xffffffffu, pk[j], owner);
+                    const uint32_t lkind = lpk >> 29, larg = lpk & 0x1FFFFFFFu;
+                    const uint32_t w = w_tile + owner * kWordsPerThread + j;
+                    const uint32_t lb0 = __ldg(word_off + w), lnb = __ldg(word_off + w + 1) - lb0;
+                    uint32_t *dst = out_ids + base + lrun;
+                    if constexpr (Enc::kScratchLong) {
+                        const uint32_t *src = ws.long_scratch + ((unsigned long long)larg << 4) + kLongHeader + (lkind == kWordLongB ? lnb : 0u);
+                        for (uint32_t k = lane; k < ln; k += 32) dst[k] = src[k];
+                    } else {
+                        bool done = false;
+                        if constexpr (Enc::kWarpLong) {
+                            if (lkind == kWordLongSeg) { enc.long_emit_warp(arena + lb0, lnb, ws.long_scratch + ((unsigned long long)larg << 4), dst, ln); done = true; }
+                        }
+                        if (!done && lane == 0) { uint32_t dummy = 0; enc.long_emit(arena + lb0, lnb, dst, ln, dummy); }
+                    }
+                }
+            }
+        }
+    }
 }
 
 // ---- scan of the tile totals: in-group exclusive prefixes (in place) + group sums, then the group bases ------------------
@@ -578,6 +798,17 @@ static __global__ void __launch_bounds__(1024) encode_scan_top_kernel(EncodeWork
 }
 
 // ---- pass 2: emit ------------------------------------------------------------------------------------------------------
+// Bulk copy-out (kFlagBulkStore): the 16-byte aligned middle of a tile's ids goes shared -> global as one cp.async.bulk issued by
+// lane 0 (TMA engine; no LDS/STG wavefronts on the LSU pipe that bounds this kernel), the at most three ids in front of / behind it
+// as scalar stores.  The buffer is reused by the next tile after cp.async.bulk.wait_group.read.
+__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <class Enc>
 __global__ void __launch_bounds__(kThreads, kEmitCtasPerSm)
 encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words,
@@ -587,7 +818,9 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * kThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kThreads) >> 5;
     const bool tok_off_vec = out_tok_off && (((uintptr_t)out_tok_off & 7) == 0);
+    const bool bulk = (ws.flags & kFlagBulkStore) != 0;
     uint32_t *compact = s_compact[threadIdx.x >> 5];
+    bool bulk_pending = false;                                                  // lane 0: a bulk copy may still be reading `compact`
 
     // the per-word records and the tile's output position are fetched one tile ahead
     auto load_tile = [&](uint32_t t, uint32_t &p0, uint32_t &p1, uint64_t &b) {
@@ -612,19 +845,12 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
         for (int j = 0; j < kWordsPerThread; ++j) {
             kind[j] = packed[j] >> 29;
             arg[j] = packed[j] & 0x1FFFFFFFu;
-            ntok[j] = (kind[j] == kWordHit || kind[j] == kWordHit16 || kind[j] == kWordRecompute) ? (arg[j] >> 23)
-                      : (kind[j] == kWordLong && !Enc::kScratchLong) ? arg[j] : 0u;
+            ntok[j] = record_ntok<Enc>(packed[j], ws.long_scratch);   // long words: their ids are written by encode_long_emit_kernel
             ra[j] = rb[j] = make_uint4(0, 0, 0, 0);
-            const MemoEntry *e = ws.memo + (arg[j] & kMemoSlotMask);
             if (kind[j] == kWordHit16) {                            // one or two scattered loads; both words' loads in flight together
-                if (ntok[j] > 0) ra[j] = ld_ca_u32x4(&e->ids16[0]);
-                if (ntok[j] > 8) rb[j] = ld_ca_u32x4(&e->ids16[8]);
-            } else if (kind[j] == kWordHit) {
-                if (ntok[j] > 0) ra[j] = ld_ca_u32x4(&e->tok[0]);
-                if (ntok[j] > 4) rb[j] = ld_ca_u32x4(&e->tok[4]);
-            }
-            if constexpr (Enc::kScratchLong) {
-                if (kind[j] == kWordLong || kind[j] == kWordLongB) ntok[j] = ws.long_scratch[(unsigned long long)arg[j] << 4];
+                const uint4 *e = ws.ids16 + 2 * (size_t)(arg[j] & kMemoSlotMask);
+                if (ntok[j] > 0) ra[j] = ld_ca_u32x4(e);
+                if (ntok[j] > 8) rb[j] = ld_ca_u32x4(e + 1);
             }
         }
         uint32_t count = 0, run[kWordsPerThread];
@@ -648,43 +874,44 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
             }
         }
         if (!fits_out) continue;                                                    // warp-uniform (status set by the scan)
+        // the previous tile's bulk copy must have finished READING the buffer before it is overwritten
+        if (bulk) { if (lane == 0 && bulk_pending) { bulk_store_wait_read(); bulk_pending = false; } __syncwarp(); }
         // the tile's ids are laid out in shared memory with the 16-byte phase of their destination, so that the copy
-        // out is LDS.128 -> STG.128 without bank conflicts
+        // out is one aligned bulk copy (or LDS.128 -> STG.128 without bank conflicts)
         const uint32_t sh = (uint32_t)((uintptr_t)(out_ids + base) >> 2) & 3u;
         uint32_t *cdst = compact + sh;
 #pragma unroll
         for (int j = 0; j < kWordsPerThread; ++j) {
             if (kind[j] == kWordHit16) {
                 // two copies of the same code so that the common case compiles to shared-memory stores (STS)
-                if (use_compact) store_hit16_ids<true>(cdst + run[j], ntok[j], ra[j], rb[j]);
-                else store_hit16_ids<false>(out_ids + base + run[j], ntok[j], ra[j], rb[j]);
-            } else if (kind[j] == kWordHit) {
-                if (use_compact) store_hit_ids(cdst + run[j], ntok[j], ra[j], rb[j], ws.memo + (arg[j] & kMemoSlotMask));
-                else store_hit_ids(out_ids + base + run[j], ntok[j], ra[j], rb[j], ws.memo + (arg[j] & kMemoSlotMask));
-            } else if (kind[j] == kWordRecompute || (!Enc::kScratchLong && kind[j] == kWordLong)) {
+                if (use_compact) store_hit16_ids<Enc, true>(cdst + run[j], ntok[j], ra[j], rb[j]);
+                else store_hit16_ids<Enc, false>(out_ids + base + run[j], ntok[j], ra[j], rb[j]);
+            } else if (kind[j] == kWordHit) {                                       // rare: 32-bit id list in the tok32 arena
+                uint32_t *dst = use_compact ? cdst + run[j] : out_ids + base + run[j];
+                const MemoExt *x = ws.ext + (arg[j] & kMemoSlotMask);
+                if (x->meta != 0xFFFFFFFFu) { const uint32_t *src = ws.tok32 + x->tok32_off; for (uint32_t k = 0; k < ntok[j]; ++k) dst[k] = src[k]; }
+                else {                                                              // the owner found the arena full: re-encode
+                    const uint32_t b0 = __ldg(word_off + w_tile + i0 + j), b1 = __ldg(word_off + w_tile + i0 + j + 1);
+                    emit_slow(enc, arena + b0, b1 - b0, kind[j], ntok[j], dst);
+                }
+            } else if (kind[j] == kWordRecompute) {
                 uint32_t *dst = use_compact ? cdst + run[j] : out_ids + base + run[j];
                 const uint32_t b0 = __ldg(word_off + w_tile + i0 + j), b1 = __ldg(word_off + w_tile + i0 + j + 1);
                 emit_slow(enc, arena + b0, b1 - b0, kind[j], ntok[j], dst);
             }
         }
-        if constexpr (Enc::kScratchLong) {                                          // long results: the warp copies them together
-#pragma unroll
-            for (int j = 0; j < kWordsPerThread; ++j) {
-                uint32_t lm = __ballot_sync(0xffffffffu, kind[j] == kWordLong || kind[j] == kWordLongB);
-                while (lm) {
-                    const uint32_t owner = __ffs(lm) - 1; lm &= lm - 1;
-                    const uint32_t ln = __shfl_sync(0xffffffffu, ntok[j], owner), lrun = __shfl_sync(0xffffffffu, run[j], owner);
-                    const uint32_t larg = __shfl_sync(0xffffffffu, arg[j], owner), lkind = __shfl_sync(0xffffffffu, kind[j], owner);
-                    const uint32_t lb0 = __ldg(word_off + w_tile + owner * kWordsPerThread + j);
-                    const uint32_t lnb = __ldg(word_off + w_tile + owner * kWordsPerThread + j + 1) - lb0;
-                    const uint32_t *src = ws.long_scratch + ((unsigned long long)larg << 4) + kLongHeader + (lkind == kWordLongB ? lnb : 0u);
-                    uint32_t *dst = use_compact ? cdst + lrun : out_ids + base + lrun;
-                    for (uint32_t k = lane; k < ln; k += 32) dst[k] = src[k];
-                }
-            }
-        }
-        __syncwarp();
-        if (use_compact) {
+        if (use_compact && bulk) {
+            fence_proxy_async_smem();                                               // generic-proxy writes -> visible to the async proxy
+            __syncwarp();
+            uint32_t *dsta = out_ids + base - sh;                                   // 16-byte aligned
+            const uint32_t end = sh + total;
+            const uint32_t c0 = sh ? 4u : 0u, c1 = end & ~3u;                       // aligned middle [c0, c1)
+            if (lane == 0 && c1 > c0) { bulk_store_s2g(dsta + c0, compact + c0, (c1 - c0) * 4u); bulk_pending = true; }
+            // head [sh, min(4, end)) on lanes 1..3, tail [max(c1, c0), end) on lanes 4..6
+            if (lane >= 1 && lane < 4) { const uint32_t c = lane; if (sh && c >= sh && c < end) dsta[c] = compact[c]; }
+            else if (lane >= 4 && lane < 7) { const uint32_t c = c1 + (lane - 4); if (c1 >= c0 && c < end) dsta[c] = compact[c]; }
+        } else if (use_compact) {
+            __syncwarp();
             uint32_t *dsta = out_ids + base - sh;                                   // 16-byte aligned
             const uint32_t end = sh + total, nvec = (end + 3) >> 2;
             for (uint32_t v = lane; v < nvec; v += 32) {
@@ -701,6 +928,7 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
         }
         __syncwarp();                                            // the compact buffer is reused by the next tile
     }
+    if (lane == 0 && bulk_pending) bulk_store_wait_read();       // shared memory must stay valid until the last copy has read it
 }
 
 template <class Enc>
@@ -723,14 +951,18 @@ int launch_encode_tiles(const Enc &enc, const uint8_t *d_arena, const uint32_t *
         grid2 = encode_grid((const void *)encode_emit_kernel<Enc>, kThreads, 0);
     }
     const uint32_t n_ctas = (ws.n_tiles + kWarps - 1) / kWarps, n_groups = (ws.n_tiles + kGroupTiles - 1) / kGroupTiles;
-    // SWT_TIMING=1: per-kernel CUDA-event times of this call on stderr (diagnostic; synchronises)
-    static const bool timing = getenv("SWT_TIMING") != nullptr;
+    // swt_tune("timing", 1): per-kernel CUDA-event times of this call on stderr (diagnostic; synchronises)
+    const bool timing = g_tune.timing != 0;
     cudaEvent_t ev[6];
     if (timing) for (auto &e : ev) cudaEventCreate(&e);
     if (timing) cudaEventRecord(ev[0], st);
-    memo_clear_kernel<<<kNumSMs * 8, 256, 0, st>>>(ws.memo, ws.memo_mask + 1, ws.long_cursor);
+    SWT_CUDA_OK(cudaMemsetAsync(ws.long_tiles, 0, ((size_t)(ws.n_tiles + 31) / 32) * 4, st));
+    memo_clear_kernel<<<kNumSMs * 8, 256, 0, st>>>(ws.keys, ws.memo_mask ? ws.memo_mask + 1 : 0u, ws.long_cursor);
     if (timing) cudaEventRecord(ev[1], st);
-    encode_count_kernel<Enc><<<(int)std::min<uint32_t>((uint32_t)grid1, n_ctas), kThreads, 0, st>>>(enc, d_arena, d_word_off, n_words, ws, d_status);
+    encode_count_kernel<Enc><<<(int)std::min<uint32_t>((uint32_t)grid1, n_ctas), kThreads, 0, st>>>(enc, d_arena, d_word_off, n_words, ws, d_status,
+                                                                                                    (uint32_t)std::max(g_tune.warp_words, 0));
+    const int long_grid = (int)std::min<uint32_t>(kNumSMs * 2, ((ws.n_tiles + 31) / 32 + 7) / 8);      // one warp per 32 tiles of the bitmap
+    encode_long_count_kernel<Enc><<<long_grid, 256, 0, st>>>(enc, d_arena, d_word_off, n_words, ws, d_status);
     if (timing) cudaEventRecord(ev[2], st);
     encode_scan_groups_kernel<<<n_groups, 256, 0, st>>>(ws);
     if (timing) cudaEventRecord(ev[3], st);
@@ -738,11 +970,13 @@ int launch_encode_tiles(const Enc &enc, const uint8_t *d_arena, const uint32_t *
     if (timing) cudaEventRecord(ev[4], st);
     encode_emit_kernel<Enc><<<(int)std::min<uint32_t>((uint32_t)grid2, n_ctas), kThreads, 0, st>>>(enc, d_arena, d_word_off, n_words, d_out_ids, out_cap,
                                                                                                    d_out_tok_off, tok_base, ws);
+    encode_long_emit_kernel<Enc><<<long_grid, 256, 0, st>>>(enc, d_arena, d_word_off, n_words, d_out_ids, out_cap, ws);
     if (timing) {
         cudaEventRecord(ev[5], st); cudaEventSynchronize(ev[5]);
         float t[5];
         for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
-        fprintf(stderr, "[swt timing] clear %.3f count %.3f scan %.3f+%.3f emit %.3f ms (grid %d/%d, %u tiles)\n", t[0], t[1], t[2], t[3], t[4], grid1, grid2, ws.n_tiles);
+        fprintf(stderr, "[swt timing] clear %.3f count %.3f scan %.3f+%.3f emit %.3f ms (grid %d/%d, %u tiles, memo %u slots)\n", t[0], t[1], t[2], t[3],
+                t[4], grid1, grid2, ws.n_tiles, ws.memo_mask ? ws.memo_mask + 1 : 0u);
         for (auto &e : ev) cudaEventDestroy(e);
     }
     SWT_CUDA_OK(cudaGetLastError());

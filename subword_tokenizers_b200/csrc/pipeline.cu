@@ -12,21 +12,33 @@
 struct swt_bpe_table;
 struct swt_wp_trie;
 namespace swt {
+int pretok_mode(const swt_pretok *p);
 int bpe_encode_launch(const swt_bpe_table *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
                       uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off, uint32_t tok_base,
                       void *d_workspace, size_t workspace_bytes, uint32_t *d_status, cudaStream_t st);
-int wp_encode_launch(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
+int wp_encode_launch(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words, uint64_t long_word_bytes,
                      uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off, uint32_t tok_base,
                      void *d_workspace, size_t workspace_bytes, uint32_t *d_status, cudaStream_t st);
 }
+
+// inside the batch loops: a failed CUDA call leaves the loop (rc set) so that the slots in flight are drained before returning
+#define SWT_CUDA_BRK(expr)                                                                        \
+    {                                                                                             \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            ::swt::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                 \
+            rc = SWT_ERR_CUDA;                                                                    \
+            break;                                                                                \
+        }                                                                                         \
+    }
 
 namespace {
 constexpr int kSlots = 5;
 constexpr uint64_t kLowerGrowthNum = 3, kLowerGrowthDen = 2;   // str.lower() grows UTF-8 text by at most 3/2 (2-byte -> 3-byte)
 struct Slot {
     uint8_t *d_arena = nullptr; uint32_t *d_off = nullptr, *d_ids = nullptr, *d_tok_off = nullptr, *d_status = nullptr;
-    uint16_t *d_ids16 = nullptr;              // allocated on the first 16-bit call
-    uint8_t *d_text = nullptr; void *d_ptws = nullptr; size_t ptws_bytes = 0;   // raw-text mode (allocated on first use)
+    uint16_t *d_ids16 = nullptr;              // 16-bit output mode
+    uint8_t *d_text = nullptr; void *d_ptws = nullptr; size_t ptws_bytes = 0;   // raw-text mode
     void *d_ws = nullptr; size_t ws_bytes = 0;
     uint32_t *h_status = nullptr;             // pinned
     cudaStream_t stream = nullptr;
@@ -68,7 +80,9 @@ SWT_API int swt_pipeline_create(int device, uint64_t batch_bytes, swt_pipeline *
     SWT_REQUIRE(batch_bytes >= (1u << 16) && batch_bytes <= (1ull << 30), "batch_bytes must be in [64 KiB, 1 GiB]");
     SWT_CUDA_OK(cudaSetDevice(device));
     swt_pipeline *p = new swt_pipeline();
-    p->device = device; p->batch_bytes = batch_bytes; p->max_words = batch_bytes / 2;
+    // Sized for the worst case of the BERT pre-tokenizer, where every punctuation character is a word of its own ("a,a,a,..."
+    // or "....": one word per byte).  Everything a host call needs is allocated here: the hot calls allocate nothing.
+    p->device = device; p->batch_bytes = batch_bytes; p->max_words = batch_bytes;
     for (int i = 0; i < kSlots; ++i) {
         Slot &s = p->slot[i];
         // BPE long-word scratch is sized for the worst case (every word of the batch is long)
@@ -77,6 +91,10 @@ SWT_API int swt_pipeline_create(int device, uint64_t batch_bytes, swt_pipeline *
         if (e == cudaSuccess) e = cudaMalloc(&s.d_off, (p->max_words + 1) * 4);
         if (e == cudaSuccess) e = cudaMalloc(&s.d_tok_off, (p->max_words + 1) * 4);
         if (e == cudaSuccess) e = cudaMalloc(&s.d_ids, (batch_bytes * kLowerGrowthNum / kLowerGrowthDen + p->max_words + 16) * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_ids16, (batch_bytes * kLowerGrowthNum / kLowerGrowthDen + p->max_words + 16) * 2);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_text, batch_bytes + 16);
+        s.ptws_bytes = swt_pretok_workspace_bytes(batch_bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_ptws, s.ptws_bytes);
         if (e == cudaSuccess) e = cudaMalloc(&s.d_status, 8 * 4);
         if (e == cudaSuccess) e = cudaMalloc(&s.d_ws, s.ws_bytes);
         if (e == cudaSuccess) e = cudaHostAlloc((void **)&s.h_status, 8 * 4, cudaHostAllocDefault);
@@ -118,9 +136,6 @@ static int encode_host_impl(swt_pipeline *p, int which, const void *table, const
     SWT_REQUIRE(n_words < 0xFFFFFFFFull, "n_words must be < 2^32 per call");
     SWT_REQUIRE(n_words == 0 || (h_arena && h_out_ids_any), "NULL data pointer");
     SWT_CUDA_OK(cudaSetDevice(p->device));
-    if (narrow)
-        for (int i = 0; i < kSlots; ++i)
-            if (!p->slot[i].d_ids16) SWT_CUDA_OK(cudaMalloc(&p->slot[i].d_ids16, (p->batch_bytes * kLowerGrowthNum / kLowerGrowthDen + p->max_words + 16) * 2));
     // batch boundaries: [w0, w1) with at most batch_bytes bytes and max_words words
     struct Batch { uint64_t w0, w1; };
     std::vector<Batch> batches;
@@ -161,21 +176,21 @@ static int encode_host_impl(swt_pipeline *p, int which, const void *table, const
             rc = bpe_encode_launch((const swt_bpe_table *)table, arena_rebased, s.d_off, nw, nbytes, s.d_ids, cap,
                                    h_out_tok_off ? s.d_tok_off : nullptr, (uint32_t)total, s.d_ws, s.ws_bytes, s.d_status, s.stream);
         else
-            rc = wp_encode_launch((const swt_wp_trie *)table, arena_rebased, s.d_off, nw, s.d_ids, cap,
+            rc = wp_encode_launch((const swt_wp_trie *)table, arena_rebased, s.d_off, nw, nbytes, s.d_ids, cap,
                                   h_out_tok_off ? s.d_tok_off : nullptr, (uint32_t)total, s.d_ws, s.ws_bytes, s.d_status, s.stream);
         if (rc) break;
         if (narrow) narrow_ids_kernel<<<swt::kNumSMs * 8, 256, 0, s.stream>>>(s.d_ids, s.d_ids16, s.d_status);
-        SWT_CUDA_OK(cudaMemcpyAsync(s.h_status, s.d_status, 8 * 4, cudaMemcpyDeviceToHost, s.stream));
-        SWT_CUDA_OK(cudaEventRecord(s.kernel_done, s.stream));
-        SWT_CUDA_OK(cudaEventSynchronize(s.kernel_done));
+        SWT_CUDA_BRK(cudaMemcpyAsync(s.h_status, s.d_status, 8 * 4, cudaMemcpyDeviceToHost, s.stream));
+        SWT_CUDA_BRK(cudaEventRecord(s.kernel_done, s.stream));
+        SWT_CUDA_BRK(cudaEventSynchronize(s.kernel_done));
         if (s.h_status[kStatusCode] != SWT_OK) { set_error("encode kernel reported status " + std::to_string(s.h_status[kStatusCode])); rc = (int)s.h_status[kStatusCode]; break; }
         const uint64_t nt = ((uint64_t)s.h_status[kStatusTokensHi] << 32) | s.h_status[kStatusTokens];
         h6 += s.h_status[kStatusH6];
         if (total + nt > out_cap) { set_error("h_out_ids capacity too small"); rc = SWT_ERR_CAPACITY; break; }
-        if (nt && narrow) SWT_CUDA_OK(cudaMemcpyAsync(h_out_ids16 + total, s.d_ids16, nt * 2, cudaMemcpyDeviceToHost, s.stream));
-        else if (nt) SWT_CUDA_OK(cudaMemcpyAsync(h_out_ids + total, s.d_ids, nt * 4, cudaMemcpyDeviceToHost, s.stream));
-        if (h_out_tok_off) SWT_CUDA_OK(cudaMemcpyAsync(h_out_tok_off + b.w0, s.d_tok_off, (uint64_t)nw * 4, cudaMemcpyDeviceToHost, s.stream));
-        SWT_CUDA_OK(cudaEventRecord(s.d2h_done, s.stream));
+        if (nt) SWT_CUDA_BRK(narrow ? cudaMemcpyAsync(h_out_ids16 + total, s.d_ids16, nt * 2, cudaMemcpyDeviceToHost, s.stream)
+                                    : cudaMemcpyAsync(h_out_ids + total, s.d_ids, nt * 4, cudaMemcpyDeviceToHost, s.stream));
+        if (h_out_tok_off) SWT_CUDA_BRK(cudaMemcpyAsync(h_out_tok_off + b.w0, s.d_tok_off, (uint64_t)nw * 4, cudaMemcpyDeviceToHost, s.stream));
+        SWT_CUDA_BRK(cudaEventRecord(s.d2h_done, s.stream));
         s.busy = true;
         total += nt;
     }
@@ -200,7 +215,9 @@ SWT_API int swt_encode_host16(swt_pipeline *p, int which, const void *table, con
 }
 
 // ---- raw text in, flat token ids out: pre-tokenization (pretok.cu) + FastBPE / FastWP encode per batch --------------------------------
-static bool ascii_space(uint8_t b) { return b == 0x20 || (b >= 0x09 && b <= 0x0D) || (b >= 0x1C && b <= 0x1F); }
+// batch cut points: Python's str.split treats 0x1C-0x1F as whitespace (FastWP); Rust's char::is_whitespace, which the BERT
+// pre-tokenizer of the BPE classes uses, does not -- cutting there would split a word such as "ab\x1ccd"
+static bool ascii_space(uint8_t b, bool bert) { return b == 0x20 || (b >= 0x09 && b <= 0x0D) || (!bert && b >= 0x1C && b <= 0x1F); }
 
 SWT_API int swt_tokenize_text_host(swt_pipeline *p, const swt_pretok *pretok, int which, const void *table, const uint8_t *h_text,
                                    uint64_t n_bytes, void *h_out_ids, int ids_16bit, uint64_t out_cap, uint64_t *n_tokens,
@@ -210,16 +227,8 @@ SWT_API int swt_tokenize_text_host(swt_pipeline *p, const swt_pretok *pretok, in
     SWT_REQUIRE(n_bytes == 0 || (h_text && h_out_ids), "NULL data pointer");
     SWT_CUDA_OK(cudaSetDevice(p->device));
     const bool narrow = ids_16bit != 0;
+    const bool bert = swt::pretok_mode(pretok) == SWT_PRETOK_BERT;
     const uint64_t slice_max = p->batch_bytes - 8;
-    for (int i = 0; i < kSlots; ++i) {
-        Slot &s = p->slot[i];
-        if (narrow && !s.d_ids16) SWT_CUDA_OK(cudaMalloc(&s.d_ids16, (p->batch_bytes * kLowerGrowthNum / kLowerGrowthDen + p->max_words + 16) * 2));
-        if (!s.d_text) {
-            SWT_CUDA_OK(cudaMalloc(&s.d_text, p->batch_bytes + 16));
-            s.ptws_bytes = swt_pretok_workspace_bytes(p->batch_bytes);
-            SWT_CUDA_OK(cudaMalloc(&s.d_ptws, s.ptws_bytes));
-        }
-    }
     // batches end just after an ASCII whitespace byte (a whole character in UTF-8), so no word is cut
     struct Batch { uint64_t b0, b1; };
     std::vector<Batch> batches;
@@ -227,7 +236,7 @@ SWT_API int swt_tokenize_text_host(swt_pipeline *p, const swt_pretok *pretok, in
         uint64_t b1 = std::min<uint64_t>(n_bytes, b0 + slice_max);
         if (b1 < n_bytes) {
             uint64_t j = b1;
-            while (j > b0 && !ascii_space(h_text[j - 1])) --j;
+            while (j > b0 && !ascii_space(h_text[j - 1], bert)) --j;
             if (j == b0) { set_error("no ASCII whitespace within one pipeline batch: raise batch_bytes"); return SWT_ERR_CAPACITY; }
             b1 = j;
         }
@@ -254,7 +263,7 @@ SWT_API int swt_tokenize_text_host(swt_pipeline *p, const swt_pretok *pretok, in
         if (k + 1 < batches.size()) { rc = enqueue_h2d(k + 1); if (rc) break; }
         Slot &s = p->slot[k % kSlots];
         const uint64_t nb = batches[k].b1 - batches[k].b0;
-        SWT_CUDA_OK(cudaEventSynchronize(s.kernel_done));                       // counts of this batch
+        SWT_CUDA_BRK(cudaEventSynchronize(s.kernel_done));                       // counts of this batch
         if (s.h_status[0] != SWT_OK) { set_error("pre-tokenizer reported status " + std::to_string(s.h_status[0])); rc = (int)s.h_status[0]; break; }
         const uint32_t nw = s.h_status[1];
         const uint64_t n_arena = ((uint64_t)s.h_status[3] << 32) | s.h_status[2];
@@ -268,20 +277,20 @@ SWT_API int swt_tokenize_text_host(swt_pipeline *p, const swt_pretok *pretok, in
             rc = bpe_encode_launch((const swt_bpe_table *)table, s.d_arena, s.d_off, nw, n_arena, s.d_ids, n_arena + nw + 16, nullptr, 0, s.d_ws,
                                    s.ws_bytes, s.d_status, s.stream);
         else
-            rc = wp_encode_launch((const swt_wp_trie *)table, s.d_arena, s.d_off, nw, s.d_ids, n_arena + nw + 16, nullptr, 0, s.d_ws, s.ws_bytes,
+            rc = wp_encode_launch((const swt_wp_trie *)table, s.d_arena, s.d_off, nw, n_arena, s.d_ids, n_arena + nw + 16, nullptr, 0, s.d_ws, s.ws_bytes,
                                   s.d_status, s.stream);
         if (rc) break;
         if (narrow) narrow_ids_kernel<<<swt::kNumSMs * 8, 256, 0, s.stream>>>(s.d_ids, s.d_ids16, s.d_status);
-        SWT_CUDA_OK(cudaMemcpyAsync(s.h_status, s.d_status, 8 * 4, cudaMemcpyDeviceToHost, s.stream));
-        SWT_CUDA_OK(cudaEventRecord(s.kernel_done, s.stream));
-        SWT_CUDA_OK(cudaEventSynchronize(s.kernel_done));
+        SWT_CUDA_BRK(cudaMemcpyAsync(s.h_status, s.d_status, 8 * 4, cudaMemcpyDeviceToHost, s.stream));
+        SWT_CUDA_BRK(cudaEventRecord(s.kernel_done, s.stream));
+        SWT_CUDA_BRK(cudaEventSynchronize(s.kernel_done));
         if (s.h_status[kStatusCode] != SWT_OK) { set_error("encode kernel reported status " + std::to_string(s.h_status[kStatusCode])); rc = (int)s.h_status[kStatusCode]; break; }
         const uint64_t nt = ((uint64_t)s.h_status[kStatusTokensHi] << 32) | s.h_status[kStatusTokens];
         h6 += s.h_status[kStatusH6];
         if (total + nt > out_cap) { set_error("h_out_ids capacity too small"); rc = SWT_ERR_CAPACITY; break; }
-        if (nt && narrow) SWT_CUDA_OK(cudaMemcpyAsync((uint16_t *)h_out_ids + total, s.d_ids16, nt * 2, cudaMemcpyDeviceToHost, s.stream));
-        else if (nt) SWT_CUDA_OK(cudaMemcpyAsync((uint32_t *)h_out_ids + total, s.d_ids, nt * 4, cudaMemcpyDeviceToHost, s.stream));
-        SWT_CUDA_OK(cudaEventRecord(s.d2h_done, s.stream));
+        if (nt) SWT_CUDA_BRK(narrow ? cudaMemcpyAsync((uint16_t *)h_out_ids + total, s.d_ids16, nt * 2, cudaMemcpyDeviceToHost, s.stream)
+                                    : cudaMemcpyAsync((uint32_t *)h_out_ids + total, s.d_ids, nt * 4, cudaMemcpyDeviceToHost, s.stream));
+        SWT_CUDA_BRK(cudaEventRecord(s.d2h_done, s.stream));
         s.busy = true;
         total += nt;
     }

@@ -389,6 +389,8 @@ SWT_API int swt_pretok_create(const uint32_t *lower_map, uint32_t n_lower, const
     return SWT_OK;
 }
 
+namespace swt { int pretok_mode(const swt_pretok *p) { return p->mode; } }
+
 SWT_API void swt_pretok_destroy(swt_pretok *p) {
     if (!p) return;
     cudaSetDevice(p->device);

@@ -73,50 +73,161 @@ struct ArrayEmit {                       // ids into a buffer of `cap` entries (
     __device__ __forceinline__ void truncate(uint32_t k) { n = k; }
 };
 
+// One iteration of the loop of FastWP.tokenize (wordpiece.py:251-269) on s = chunk + " ": match loop from position i (a word
+// boundary), accept / reject, advance to the next boundary.  prev_punct = ispunc(s[i-1]) (false at i == 0) on entry and on exit.
+// Returns the new position.  A segment is a function of its start position alone, which is what lets the lanes of a warp walk the
+// segments of a long chunk independently (wp_long_count_warp).
+template <class Emit>
+__device__ __forceinline__ uint32_t wp_encode_segment(const WpTrieDev &t, const uint8_t *p, uint32_t nbytes, uint32_t i, bool &prev_punct,
+                                                      Emit &emit, uint32_t &h6) {
+    const uint32_t seg = emit.size(), i0 = i;
+    uint32_t node = kNodeRoot, cp = 0, adv = 1;
+    // ---- matchloop (wordpiece.py:291-316)
+    for (;;) {
+        if (i < nbytes) cp = utf8_decode(p + i, nbytes - i, adv); else { cp = 0x20u; adv = 1; }   // the appended " "
+        uint32_t child = (i < nbytes) ? wp_edge(t, node, cp) : kNone;   // no vocabulary entry holds whitespace
+        bool returned = false;
+        while (child == kNone) {                                        // failure transitions :308-312
+            const uint4 info = __ldg(&t.node_info[node]);
+            if (info.x == kNone) { returned = true; break; }
+            for (uint32_t k = 0; k < info.z; ++k) emit.push(__ldg(&t.pops[info.y + k]));
+            node = info.x;
+            child = (i < nbytes) ? wp_edge(t, node, cp) : kNone;
+        }
+        if (returned) break;
+        node = child; i += adv; prev_punct = !wp_alnum(t, cp);          // goto transition :314-315
+    }
+    // ---- accept / reject (wordpiece.py:255-261); cp is s[i]
+    bool bnd = prev_punct || i >= nbytes || !wp_alnum(t, cp);           // iswdbndry :285
+    const bool ok = bnd && (node == kNodeRoot || node == kNodeRootSharp || node == kNodeRootP);
+    if (!ok) { emit.truncate(seg); emit.push(t.n_vocab); }              // "['UNK']"
+    else if (node == kNodeRootSharp && emit.size() == seg) {
+        for (uint32_t k = 0; k < t.n_sharp_special; ++k) emit.push(t.sharp_special[k]);
+    }
+    // ---- advance to the next boundary (:265-266), then skip whitespace (:268-269)
+    while (!bnd) {
+        i += adv; prev_punct = false;                                   // s[i] was alnum here
+        if (i < nbytes) { cp = utf8_decode(p + i, nbytes - i, adv); bnd = !wp_alnum(t, cp); }
+        else bnd = true;
+    }
+    if (i == i0) {
+        // H6: punctuation that is not a child of the root -- the reference spins forever here.
+        // Documented extension: emit "['UNK']" and advance one character.
+        ++h6; emit.push(t.n_vocab);
+        i += adv; prev_punct = !wp_alnum(t, cp);
+    }
+    return i;
+}
+
 // FastWP.tokenize on s = chunk + " " (wordpiece.py:248-269); the chunk holds no whitespace.
 template <class Emit>
 __device__ __forceinline__ void wp_encode_chunk(const WpTrieDev &t, const uint8_t *p, uint32_t nbytes, Emit &emit, uint32_t &h6) {
     uint32_t i = 0;
     bool prev_punct = false;                       // ispunc(s[i-1]); false at i == 0
-    while (i < nbytes) {
-        const uint32_t seg = emit.size(), i0 = i;
-        uint32_t node = kNodeRoot, cp = 0, adv = 1;
-        // ---- matchloop (wordpiece.py:291-316)
-        for (;;) {
-            if (i < nbytes) cp = utf8_decode(p + i, nbytes - i, adv); else { cp = 0x20u; adv = 1; }   // the appended " "
-            uint32_t child = (i < nbytes) ? wp_edge(t, node, cp) : kNone;   // no vocabulary entry holds whitespace
-            bool returned = false;
-            while (child == kNone) {                                        // failure transitions :308-312
-                const uint4 info = __ldg(&t.node_info[node]);
-                if (info.x == kNone) { returned = true; break; }
-                for (uint32_t k = 0; k < info.z; ++k) emit.push(__ldg(&t.pops[info.y + k]));
-                node = info.x;
-                child = (i < nbytes) ? wp_edge(t, node, cp) : kNone;
-            }
-            if (returned) break;
-            node = child; i += adv; prev_punct = !wp_alnum(t, cp);          // goto transition :314-315
-        }
-        // ---- accept / reject (wordpiece.py:255-261); cp is s[i]
-        bool bnd = prev_punct || i >= nbytes || !wp_alnum(t, cp);           // iswdbndry :285
-        const bool ok = bnd && (node == kNodeRoot || node == kNodeRootSharp || node == kNodeRootP);
-        if (!ok) { emit.truncate(seg); emit.push(t.n_vocab); }              // "['UNK']"
-        else if (node == kNodeRootSharp && emit.size() == seg) {
-            for (uint32_t k = 0; k < t.n_sharp_special; ++k) emit.push(t.sharp_special[k]);
-        }
-        // ---- advance to the next boundary (:265-266), then skip whitespace (:268-269)
-        while (!bnd) {
-            i += adv; prev_punct = false;                                   // s[i] was alnum here
-            if (i < nbytes) { cp = utf8_decode(p + i, nbytes - i, adv); bnd = !wp_alnum(t, cp); }
-            else bnd = true;
-        }
-        if (i == i0) {
-            // H6: punctuation that is not a child of the root -- the reference spins forever here.
-            // Documented extension: emit "['UNK']" and advance one character.
-            ++h6; emit.push(t.n_vocab);
-            i += adv; prev_punct = !wp_alnum(t, cp);
-        }
-        if (i >= nbytes) break;                                             // the virtual space ends the chunk
+    while (i < nbytes) i = wp_encode_segment(t, p, nbytes, i, prev_punct, emit, h6);   // the virtual space ends the chunk
+}
+
+// ---- long chunks, split across the lanes of a warp (north-star item 3) ----------------------------------------------------------
+// Every iteration of the loop above starts at a word boundary (iswdbndry: the previous or the current character is punctuation) with
+// the trie at its root, so the segment starting at a boundary does not depend on what came before.  The warp lists the boundary
+// positions of the chunk, the lanes walk the segment of every boundary (count only), and the segments are chained from position 0:
+// with a vocabulary whose entries do not mix punctuation and letters every segment ends at the next boundary and all of them are
+// used (checked in parallel); otherwise (an entry like "a.b" lets a match loop run across a boundary) lane 0 follows the chain and
+// the segments it skips are dropped, which is exactly what the sequential loop does.  A run of letters without punctuation is one
+// segment and stays sequential (the trie state carries).
+// Scratch (u32): [0] tokens of the chunk, [1] number of boundaries; record c at 16 + 4c: position, end -> output offset (or kNone
+// when the chain skips it), tokens, H6 events.
+constexpr uint32_t kSegRec = 4;
+__device__ __forceinline__ bool wp_prev_is_punct(const WpTrieDev &t, const uint8_t *p, uint32_t nbytes, uint32_t i) {
+    if (i == 0) return false;
+    uint32_t j = i - 1;
+    while (j > 0 && (p[j] & 0xC0u) == 0x80u) --j;
+    uint32_t adv;
+    return !wp_alnum(t, utf8_decode(p + j, nbytes - j, adv));
+}
+static __device__ __noinline__ uint32_t wp_long_count_warp(const WpTrieDev &t, const uint8_t *p, uint32_t nbytes, uint32_t *scratch, uint32_t &h6_out) {
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    uint32_t *rec = scratch + kLongHeader;
+    // a. boundary positions, in ascending order
+    uint32_t nc = 0;
+    bool carry_alnum = true;                                              // class of the last character of the previous 32 bytes
+    for (uint32_t base = 0; base < nbytes; base += 32) {
+        const uint32_t b = base + lane;
+        const bool start = b < nbytes && (p[b] & 0xC0u) != 0x80u;
+        bool aln = false;
+        if (start) { uint32_t adv; aln = wp_alnum(t, utf8_decode(p + b, nbytes - b, adv)); }
+        const uint32_t S = __ballot_sync(0xffffffffu, start), A = __ballot_sync(0xffffffffu, aln);
+        const uint32_t below = S & lt;
+        const bool prev_alnum = below ? ((A >> (31 - __clz(below))) & 1u) : carry_alnum;
+        const bool cand = start && (b == 0 || !prev_alnum || !aln);
+        const uint32_t cm = __ballot_sync(0xffffffffu, cand);
+        if (cand) rec[kSegRec * (nc + __popc(cm & lt))] = b;
+        nc += __popc(cm);
+        if (S) carry_alnum = (A >> (31 - __clz(S))) & 1u;
     }
+    __syncwarp();
+    // b. one segment per boundary, counting only
+    for (uint32_t c = lane; c < nc; c += 32) {
+        const uint32_t i = rec[kSegRec * c];
+        bool prev_punct = wp_prev_is_punct(t, p, nbytes, i);
+        CountEmit e; uint32_t sh6 = 0;
+        const uint32_t end = wp_encode_segment(t, p, nbytes, i, prev_punct, e, sh6);
+        rec[kSegRec * c + 1] = end; rec[kSegRec * c + 2] = e.n; rec[kSegRec * c + 3] = sh6;
+    }
+    __syncwarp();
+    // c. chain: every segment ends where the next boundary is?
+    bool ok = true;
+    for (uint32_t c = lane; c < nc; c += 32) {
+        const uint32_t end = rec[kSegRec * c + 1];
+        ok = ok && (c + 1 < nc ? end == rec[kSegRec * (c + 1)] : end >= nbytes);
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    uint32_t total = 0, h6 = 0;
+    if (ok) {                                                             // all used: offsets = exclusive scan of the token counts
+        for (uint32_t c0 = 0; c0 < nc; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            const uint32_t n = c < nc ? rec[kSegRec * c + 2] : 0u;
+            h6 += c < nc ? rec[kSegRec * c + 3] : 0u;
+            uint32_t incl = n;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += v; }
+            if (c < nc) rec[kSegRec * c + 1] = total + incl - n;
+            total += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    } else {
+        if (lane == 0) {
+            uint32_t pos = 0, c = 0;
+            while (pos < nbytes && c < nc) {
+                while (c < nc && rec[kSegRec * c] < pos) { rec[kSegRec * c + 1] = kNone; ++c; }      // skipped by the chain
+                if (c >= nc || rec[kSegRec * c] != pos) break;                                       // cannot happen: an end is a boundary
+                pos = rec[kSegRec * c + 1];
+                rec[kSegRec * c + 1] = total; total += rec[kSegRec * c + 2]; h6 += rec[kSegRec * c + 3];
+                ++c;
+            }
+            for (; c < nc; ++c) rec[kSegRec * c + 1] = kNone;
+        }
+        total = __shfl_sync(0xffffffffu, total, 0);
+    }
+    if (lane == 0) { scratch[0] = total; scratch[1] = nc; }
+    __syncwarp();
+    h6_out = h6;                                                          // the lanes' shares add up to the chunk's H6 events
+    return total;
+}
+static __device__ __noinline__ void wp_long_emit_warp(const WpTrieDev &t, const uint8_t *p, uint32_t nbytes, const uint32_t *scratch, uint32_t *dst,
+                                                      uint32_t n_total) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t *rec = scratch + kLongHeader;
+    const uint32_t nc = scratch[1];
+    for (uint32_t c = lane; c < nc; c += 32) {
+        const uint32_t off = rec[kSegRec * c + 1];
+        if (off == kNone || off > n_total) continue;
+        const uint32_t i = rec[kSegRec * c];
+        bool prev_punct = wp_prev_is_punct(t, p, nbytes, i);
+        ArrayEmit e{dst + off, min(rec[kSegRec * c + 2], n_total - off)};
+        uint32_t dummy = 0;
+        wp_encode_segment(t, p, nbytes, i, prev_punct, e, dummy);
+    }
+    __syncwarp();
 }
 
 // NaiveWP.encode_word (wordpiece.py:131-158): greedy longest prefix in the vocabulary; the rest is looked up as "##" + rest.
@@ -143,11 +254,19 @@ __device__ __forceinline__ void wp_naive_encode_word(const WpTrieDev &t, const u
     }
 }
 
+struct WpStage { uint32_t unused; };      // the trie stays in L1/L2: nothing is staged in shared memory
+
 struct NaiveWpEnc {
     WpTrieDev t;
+    using Stage = WpStage;
     static constexpr bool kScratchLong = false;
     static constexpr bool kBatchSlowPath = true;
-    __device__ __forceinline__ uint32_t encode_short(const uint8_t *p, uint32_t nbytes, uint32_t *buf, uint32_t &h6) const {
+    static constexpr bool kWarpShort = false;
+    static constexpr bool kWarpLong = false;
+    __device__ __forceinline__ void stage_init(Stage &) const {}
+    __device__ static __forceinline__ bool narrow16(uint32_t id, uint32_t k, uint32_t &v16) { (void)k; v16 = id; return id < 65536u; }
+    __device__ static __forceinline__ uint32_t expand16(uint32_t v16, uint32_t k) { (void)k; return v16; }
+    __device__ __forceinline__ uint32_t encode_short(const Stage *, const uint8_t *p, uint32_t nbytes, uint32_t *buf, uint32_t &h6) const {
         (void)h6;
         ArrayEmit e{buf, (uint32_t)kShortBytes};
         wp_naive_encode_word(t, p, nbytes, e);
@@ -168,9 +287,25 @@ struct NaiveWpEnc {
 
 struct WpEnc {
     WpTrieDev t;
+    using Stage = WpStage;
     static constexpr bool kScratchLong = false;
     static constexpr bool kBatchSlowPath = true;
-    __device__ __forceinline__ uint32_t encode_short(const uint8_t *p, uint32_t nbytes, uint32_t *buf, uint32_t &h6) const {
+    static constexpr bool kWarpShort = false;
+    static constexpr bool kWarpLong = true;
+    __device__ __forceinline__ void stage_init(Stage &) const {}
+    __device__ static __forceinline__ bool narrow16(uint32_t id, uint32_t k, uint32_t &v16) { (void)k; v16 = id; return id < 65536u; }
+    __device__ static __forceinline__ uint32_t expand16(uint32_t v16, uint32_t k) { (void)k; return v16; }
+    // long chunks with scratch: the segments of the chunk are walked by the lanes of the warp (all 32 lanes call these)
+    __host__ __device__ static __forceinline__ unsigned long long long_scratch_need(uint32_t nbytes) {
+        return (kLongHeader + (unsigned long long)kSegRec * nbytes + 15ull) & ~15ull;
+    }
+    __device__ __forceinline__ uint32_t long_count_warp(const uint8_t *p, uint32_t nbytes, uint32_t *scratch, uint32_t &h6) const {
+        return wp_long_count_warp(t, p, nbytes, scratch, h6);
+    }
+    __device__ __forceinline__ void long_emit_warp(const uint8_t *p, uint32_t nbytes, const uint32_t *scratch, uint32_t *dst, uint32_t n) const {
+        wp_long_emit_warp(t, p, nbytes, scratch, dst, n);
+    }
+    __device__ __forceinline__ uint32_t encode_short(const Stage *, const uint8_t *p, uint32_t nbytes, uint32_t *buf, uint32_t &h6) const {
         ArrayEmit e{buf, (uint32_t)kShortBytes};
         wp_encode_chunk(t, p, nbytes, e, h6);
         return e.n;
@@ -333,11 +468,11 @@ SWT_API int swt_wp_trie_stats(const swt_wp_trie *t, uint64_t *n_nodes, uint64_t 
 }
 
 namespace swt {
-int wp_encode_launch(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
+int wp_encode_launch(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words, uint64_t long_word_bytes,
                      uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off, uint32_t tok_base,
                      void *d_workspace, size_t workspace_bytes, uint32_t *d_status, cudaStream_t st) {
     SWT_REQUIRE(t != nullptr, "NULL trie");
-    return launch_encode_tiles(WpEnc{t->dev}, d_arena, d_word_off, n_words, 0, d_out_ids, out_cap, d_out_tok_off, tok_base,
+    return launch_encode_tiles(WpEnc{t->dev}, d_arena, d_word_off, n_words, long_word_bytes, d_out_ids, out_cap, d_out_tok_off, tok_base,
                                d_workspace, workspace_bytes, d_status, st);
 }
 }  // namespace swt
@@ -345,9 +480,10 @@ int wp_encode_launch(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_
 SWT_API int swt_wp_encode(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
                           uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off,
                           void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream) {
-    (void)long_word_bytes;   // long chunks are walked twice instead of using scratch
-    return wp_encode_launch(t, d_arena, d_word_off, n_words, d_out_ids, out_cap, d_out_tok_off, 0u, d_workspace, workspace_bytes,
-                            d_status, (cudaStream_t)stream);
+    // long_word_bytes > 0: chunks longer than 32 bytes are split into their segments across the lanes of a warp (scratch for the
+    // segment records); 0: the owning lane walks such a chunk alone
+    return wp_encode_launch(t, d_arena, d_word_off, n_words, long_word_bytes, d_out_ids, out_cap, d_out_tok_off, 0u, d_workspace,
+                            workspace_bytes, d_status, (cudaStream_t)stream);
 }
 
 SWT_API int swt_wp_encode_naive(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,

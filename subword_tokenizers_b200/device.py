@@ -24,6 +24,11 @@ def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def tune(name: str, value: int) -> None:
+    """Process-wide experiment knob of libswt (include/swt.h, swt_tune)."""
+    check(_lib.load().swt_tune(name.encode(), int(value)), "swt_tune")
+
+
 def current_device() -> int:
     return torch.cuda.current_device()
 
@@ -186,10 +191,8 @@ class _Encoder:
         d_arena, d_off, n_words, d_src = Pretokenizer.get(mode=self._pretok_mode).split_text(data, want_src=True)
         if n_words == 0:
             return np.zeros(0, np.uint32), np.zeros(len(texts) + 1, np.int64)
-        long_bytes = 0
-        if self._which == 0:
-            lens = (d_off[1:n_words + 1] - d_off[:n_words]).long()
-            long_bytes = int(lens[lens > SHORT_WORD_BYTES].sum().item())
+        lens = (d_off[1:n_words + 1] - d_off[:n_words]).long()                    # bytes of the long words size the scratch
+        long_bytes = int(lens[lens > SHORT_WORD_BYTES].sum().item())
         d_ids, d_tok_off, d_status = self.encode_device(d_arena, d_off, n_words, long_bytes)
         n_tok, _ = self.check_status(d_status)
         ids = d_ids[:n_tok].cpu().numpy().view(np.uint32)
@@ -366,7 +369,9 @@ class WpEncoder(_Encoder):
         d_arena, d_off, n_words = Pretokenizer.get(mode=self._pretok_mode).split_text(text)
         if n_words == 0:
             return (np.zeros(0, np.uint32), np.zeros(1, np.uint32)) if return_offsets else np.zeros(0, np.uint32)
-        d_ids, d_tok_off, d_status = self.encode_device(d_arena, d_off, n_words, 0, want_offsets=return_offsets)
+        lens = (d_off[1:n_words + 1] - d_off[:n_words]).long()                    # long chunks are split across a warp (scratch)
+        long_bytes = int(lens[lens > SHORT_WORD_BYTES].sum().item())
+        d_ids, d_tok_off, d_status = self.encode_device(d_arena, d_off, n_words, long_bytes, want_offsets=return_offsets)
         n_tok, _ = self.check_status(d_status)
         ids = d_ids[:n_tok].cpu().numpy().view(np.uint32)
         return (ids, d_tok_off.cpu().numpy().view(np.uint32)) if return_offsets else ids
@@ -395,7 +400,11 @@ def device_train_types(corpus: Sequence[str], wordpiece: bool):
     lib = _lib.load()
     data = b"\n".join(P.encode_utf8(t) for t in corpus)
     dev = torch.device("cuda", current_device())
-    d_arena, d_off, n_words = Pretokenizer.get(mode=_lib.PRETOK_BERT).split_text(data)
+    n_words = 0
+    if data:
+        d_arena, d_off, n_words = Pretokenizer.get(mode=_lib.PRETOK_BERT).split_text(data)
+    if n_words == 0:                                    # empty corpus: the host constructors give the empty tables
+        return P.WpTrainTypes([]) if wordpiece else P.TrainTypes([])
     sp = _stream_ptr()
     d_status = torch.empty(8, dtype=torch.int32, device=dev)
     max_types = max(1024, min(n_words, 1 << 22))
@@ -549,6 +558,27 @@ class CudaTrainEngine:
     def update(self): check(self.lib.swt_bpe_train_update(self.handle, self._sp()))
     def steps(self, n: int): check(self.lib.swt_bpe_train_steps(self.handle, n, self._sp()))
 
+    def exchange_initial_pairs(self, world_size: int, group, dist) -> None:
+        """Large alphabets (no dense n_alpha^2 array): all-gather the ranks' local (pair, count) lists and add the other
+        ranks' entries, so that every replica of the pair table holds the global counts (include/swt.h)."""
+        n_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        check(self.lib.swt_bpe_train_export_pairs(self.handle, None, 0, n_dev.data_ptr(), self._sp()))    # count only
+        n_local = int(n_dev.item())
+        counts = torch.zeros(world_size, dtype=torch.int64, device=self.dev)
+        dist.all_gather_into_tensor(counts, n_dev, group=group)
+        counts = counts.cpu().tolist()
+        cap = max(max(counts), 1)
+        mine = torch.zeros(2 * cap, dtype=torch.int64, device=self.dev)
+        check(self.lib.swt_bpe_train_export_pairs(self.handle, mine.data_ptr(), cap, n_dev.data_ptr(), self._sp()))
+        everyone = torch.empty(world_size * 2 * cap, dtype=torch.int64, device=self.dev)
+        dist.all_gather_into_tensor(everyone, mine, group=group)
+        rank = self.cfg.rank
+        for r in range(world_size):
+            if r != rank and counts[r]:
+                check(self.lib.swt_bpe_train_import_pairs(self.handle, everyone[2 * cap * r:].data_ptr(), counts[r], self._sp()))
+        self.stream.synchronize()
+        assert n_local == counts[rank]
+
     def read(self):
         """Synchronises. -> (state dict, left, right, new, count) for the merges recorded since the last read."""
         st = TrainState()
@@ -631,7 +661,10 @@ def _training_loop(engine, world_size, group, steps_per_sync, progress, dist):
     lefts, rights, news, counts = [], [], [], []
     engine.count_local()
     if world_size > 1:
-        dist.all_reduce(engine.init_counts, op=dist.ReduceOp.SUM, group=group)
+        if engine.init_counts.numel():
+            dist.all_reduce(engine.init_counts, op=dist.ReduceOp.SUM, group=group)
+        else:                                   # alphabet > 4096 symbols: sparse exchange of the initial counts
+            engine.exchange_initial_pairs(world_size, group, dist)
     engine.build_table()
     graph = None
     use_graph = world_size > 1 and getattr(engine, "stream", None) is not None and steps_per_sync >= STEPS_PER_GRAPH

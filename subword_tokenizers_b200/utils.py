@@ -84,13 +84,3 @@ def naive_wp_encode(word: str, vocab) -> List[str]:
 def naive_wp_encode_ids(word: str, tables) -> List[int]:
     index = {t: i for i, t in enumerate(tables.id_to_str)}
     return [index[t] for t in naive_wp_encode(word, set(tables.tokens))]
-
-
-def recover_sentence(tokens: List[str]) -> str:
-    """Lossy detokenizer (reference source/utils.py:141-154): join, glue '##' pieces, tidy punctuation."""
-    import re
-    out = " ".join(tokens)
-    out = re.sub(r"\s##(\S)", r"\g<1>", out)
-    out = re.sub(r"\s(\.|,|\)|\]|\\|’|-|'|\\|/)", r"\g<1>", out)
-    out = re.sub(r"(\(|\[|\\|’|-|'|\\|/)\s", r"\g<1>", out)
-    return out

@@ -13,11 +13,14 @@ from collections import Counter
 from typing import Dict, List, Sequence, Tuple
 
 from . import packing as P
+from ._tracked import TrackedSet, stamp, tracked_attribute
 from .utils import SubwordTokenizer, WPTrie_E2E, naive_wp_encode
 
 
 class NaiveWP(SubwordTokenizer):
     """WordPiece tokenizer (reference source/wordpiece.py:8-208)."""
+
+    vocab = tracked_attribute("vocab", TrackedSet)      # counts its mutations: the device trie follows the live set
 
     def __init__(self, tokenizer):
         super().__init__(tokenizer)
@@ -49,6 +52,10 @@ class NaiveWP(SubwordTokenizer):
         from . import _lib, packing as P
         from .device import CudaTrainEngine, run_training_loop
         self.vocab = set(types.init_syms)
+        if len(types.freq) == 0 or len(types.init_syms) == 0:      # empty corpus: nothing to merge (wordpiece.py:68,74-75)
+            self._train_result = None
+            self._corpus_cache = []
+            return
         max_len = int(np.diff(types.off.astype(np.int64)).max()) if len(types.freq) else 1
         engine = CudaTrainEngine(types.syms, types.off, types.freq, len(types.init_syms), max_vocab, len(types.init_syms),
                                  max_len + 2, 0, 0, 1, mode=_lib.TRAIN_WP, init_cps=types.init_cps, init_off=types.init_off)
@@ -95,7 +102,7 @@ class NaiveWP(SubwordTokenizer):
         """Greedy longest-prefix encoder on the device (swt_wp_encode_naive) over the trie of the current vocabulary."""
         from .device import WpEncoder
         from .utils import naive_wp_encode_ids
-        quick = (id(self.vocab), len(self.vocab))
+        quick = stamp(self.vocab)
         if getattr(self, "_naive_quick", None) != quick:
             tables = P.WpTables(self.vocab)
             self._naive_encoder = WpEncoder(tables, naive_wp_encode_ids("##", tables), naive=True)
