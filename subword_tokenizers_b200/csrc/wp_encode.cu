@@ -119,6 +119,20 @@ __device__ __forceinline__ uint32_t wp_encode_segment(const WpTrieDev &t, const 
     return i;
 }
 
+// The segments from a word boundary i up to the NEXT word boundary.  Normally that is one segment; only the H6 extension can leave
+// the position inside a run of letters (it advances one character after a boundary at which nothing matched), and the segments
+// that follow until the next boundary belong to the same unit of work.
+template <class Emit>
+__device__ __forceinline__ uint32_t wp_encode_to_boundary(const WpTrieDev &t, const uint8_t *p, uint32_t nbytes, uint32_t i, bool &prev_punct,
+                                                          Emit &emit, uint32_t &h6) {
+    for (;;) {
+        i = wp_encode_segment(t, p, nbytes, i, prev_punct, emit, h6);
+        if (i >= nbytes || prev_punct) return i;
+        uint32_t adv;
+        if (!wp_alnum(t, utf8_decode(p + i, nbytes - i, adv))) return i;
+    }
+}
+
 // FastWP.tokenize on s = chunk + " " (wordpiece.py:248-269); the chunk holds no whitespace.
 template <class Emit>
 __device__ __forceinline__ void wp_encode_chunk(const WpTrieDev &t, const uint8_t *p, uint32_t nbytes, Emit &emit, uint32_t &h6) {
@@ -130,7 +144,8 @@ __device__ __forceinline__ void wp_encode_chunk(const WpTrieDev &t, const uint8_
 // ---- long chunks, split across the lanes of a warp (north-star item 3) ----------------------------------------------------------
 // Every iteration of the loop above starts at a word boundary (iswdbndry: the previous or the current character is punctuation) with
 // the trie at its root, so the segment starting at a boundary does not depend on what came before.  The warp lists the boundary
-// positions of the chunk, the lanes walk the segment of every boundary (count only), and the segments are chained from position 0:
+// positions of the chunk, the lanes walk the segment of every boundary (count only; "segment" = up to the next boundary, see
+// wp_encode_to_boundary), and the segments are chained from position 0:
 // with a vocabulary whose entries do not mix punctuation and letters every segment ends at the next boundary and all of them are
 // used (checked in parallel); otherwise (an entry like "a.b" lets a match loop run across a boundary) lane 0 follows the chain and
 // the segments it skips are dropped, which is exactly what the sequential loop does.  A run of letters without punctuation is one
@@ -171,7 +186,7 @@ static __device__ __noinline__ uint32_t wp_long_count_warp(const WpTrieDev &t, c
         const uint32_t i = rec[kSegRec * c];
         bool prev_punct = wp_prev_is_punct(t, p, nbytes, i);
         CountEmit e; uint32_t sh6 = 0;
-        const uint32_t end = wp_encode_segment(t, p, nbytes, i, prev_punct, e, sh6);
+        const uint32_t end = wp_encode_to_boundary(t, p, nbytes, i, prev_punct, e, sh6);
         rec[kSegRec * c + 1] = end; rec[kSegRec * c + 2] = e.n; rec[kSegRec * c + 3] = sh6;
     }
     __syncwarp();
@@ -225,7 +240,7 @@ static __device__ __noinline__ void wp_long_emit_warp(const WpTrieDev &t, const 
         bool prev_punct = wp_prev_is_punct(t, p, nbytes, i);
         ArrayEmit e{dst + off, min(rec[kSegRec * c + 2], n_total - off)};
         uint32_t dummy = 0;
-        wp_encode_segment(t, p, nbytes, i, prev_punct, e, dummy);
+        wp_encode_to_boundary(t, p, nbytes, i, prev_punct, e, dummy);
     }
     __syncwarp();
 }
