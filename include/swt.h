@@ -302,6 +302,7 @@ typedef struct swt_bpe_train_state {
     uint64_t n_table_entries;
     uint64_t table_cap;
     uint64_t n_live_slots;     /* live symbols on this rank */
+    uint64_t n_tie_steps;      /* steps in which several pairs attained the maximum (first-occurrence scan) */
 } swt_bpe_train_state;
 
 size_t swt_bpe_train_workspace_bytes(const swt_bpe_train_config *cfg);

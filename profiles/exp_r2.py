@@ -15,6 +15,7 @@ ap.add_argument("--bytes", type=int, default=1_000_000_000)
 ap.add_argument("--many", type=int, default=2_000_000)
 ap.add_argument("--many-words", type=int, default=45_000_000)
 ap.add_argument("--skip-many", action="store_true")
+ap.add_argument("--quick", action="store_true", help="default knobs only")
 ap.add_argument("--check-words", type=int, default=2_000_000)
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -80,9 +81,9 @@ wenc = device.WpEncoder(wtab, naive_wp_encode_ids("##", wtab))
 merges = [tuple(p) for p in B.load_golden("ref_bpe_train5k_v8000_merges.json.gz")]
 btab = P.BpeTables(merges)
 benc = device.BpeEncoder(btab)
-for knobs in ({}, {"bulk_store": 0}, {"memo_max_log2": 20}, {"memo_max_log2": 18}, {"memo_off": 1}):
+for knobs in (({},) if args.quick else ({}, {"bulk_store": 0}, {"memo_max_log2": 20}, {"memo_max_log2": 18}, {"memo_off": 1})):
     run("wp_bench_stream", wenc, "wp", wtab, d_arena, d_off, n_words, pre, knobs, reps=5 if not knobs.get("memo_off") else 2)
-for knobs in ({}, {"bulk_store": 0}, {"bpe_queue": 0}, {"bpe_queue": 0, "warp_words": 0}, {"warp_words": 0}, {"warp_words": 8}, {"memo_off": 1}):
+for knobs in (({}, {"bpe_queue": 0}) if args.quick else ({}, {"bulk_store": 0}, {"bpe_queue": 0}, {"bpe_queue": 0, "warp_words": 0}, {"warp_words": 0}, {"warp_words": 8}, {"memo_off": 1})):
     run("bpe_bench_stream", benc, "bpe", btab, d_arena, d_off, n_words, pre, knobs, reps=5 if not knobs.get("memo_off") else 2)
 del d_arena, d_off
 
@@ -98,7 +99,7 @@ if not args.skip_many:
     wenc2 = device.WpEncoder(wtab2, naive_wp_encode_ids("##", wtab2))
     btab2 = P.BpeTables([tuple(p) for p in B.load_golden("pretrained_bpe_merges.json.gz")])
     benc2 = device.BpeEncoder(btab2)
-    for knobs in ({}, {"memo_max_log2": 23}, {"memo_max_log2": 20}, {"memo_off": 1}):
+    for knobs in (({},) if args.quick else ({}, {"memo_max_log2": 23}, {"memo_max_log2": 20}, {"memo_off": 1})):
         run("wp_many_types", wenc2, "wp", wtab2, d_arena, d_off, n_words, pre, knobs, reps=3)
-    for knobs in ({}, {"memo_max_log2": 23}, {"bpe_queue": 0}, {"memo_off": 1}):
+    for knobs in (({},) if args.quick else ({}, {"memo_max_log2": 23}, {"bpe_queue": 0}, {"memo_off": 1})):
         run("bpe_many_types", benc2, "bpe", btab2, d_arena, d_off, n_words, pre, knobs, reps=3)

@@ -7,7 +7,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libswt.so")
+LIB_PATH = os.environ.get("SWT_LIB_PATH") or os.path.join(_HERE, "libswt.so")      # SWT_LIB_PATH: kernel-variant experiments
 
 c_u8p = ctypes.POINTER(ctypes.c_uint8)
 c_u32p = ctypes.POINTER(ctypes.c_uint32)
@@ -38,7 +38,7 @@ class TrainState(ctypes.Structure):
     _fields_ = [
         ("halt", ctypes.c_uint32), ("n_recorded", ctypes.c_uint32), ("n_merges_total", ctypes.c_uint64),
         ("vocab_size", ctypes.c_int64), ("n_symbols", ctypes.c_uint64), ("n_table_entries", ctypes.c_uint64),
-        ("table_cap", ctypes.c_uint64), ("n_live_slots", ctypes.c_uint64),
+        ("table_cap", ctypes.c_uint64), ("n_live_slots", ctypes.c_uint64), ("n_tie_steps", ctypes.c_uint64),
     ]
 
 

@@ -34,7 +34,9 @@ constexpr uint64_t kNoPos = ~0ull;
 constexpr uint32_t kMaxDenseAlpha = 4096;       // up to here the initial pair counts go through a dense n_alpha^2 array (one all-reduce
                                                 // when sharded); larger alphabets (CJK, multilingual) count straight into the pair table
 constexpr uint32_t kChunkShift = 12;            // mark scan granularity: 4096 slots per chunk
-constexpr uint32_t kBlkShift = 12;              // argmax cache granularity: 4096 table slots per block
+constexpr uint32_t kFiltBits = 16384;           // per-chunk pair filter: one bit per hashed pair that (may) occur in the chunk
+constexpr uint32_t kBlkShift = 8;               // argmax cache, level 1: 256 table slots (4 KB) per block, refreshed by one warp
+constexpr uint32_t kGrpShift = 8;               // level 2: 256 blocks (65,536 slots) per group
 
 enum Halt : uint32_t { kRun = 0, kDoneVocab = 1, kDoneNoPairs = 2, kNeedGrow = 3, kRecordFull = 4,
                        kErrInternal = 16, kErrCharArena = 17, kErrSymbols = 18, kErrTableFull = 19, kErrScoreRange = 20 };
@@ -52,11 +54,13 @@ struct TrainState {                 // device resident, mutable
     uint64_t cand_key, best_pos;
     uint32_t cur_a, cur_b, cur_z, cur_valid;
     uint64_t char_used;
-    uint32_t n_dirty, n_touch_l, n_touch_r, pad0;   // lengths of the dirty-block list and of the touched-symbol lists
+    uint32_t n_dirty, n_touch_l, n_touch_r, n_gdirty;   // lengths of the dirty-block / dirty-group lists and of the touched-symbol lists
     double best_score;                              // WordPiece mode: the maximal score of this step
+    uint64_t n_tie_steps;                           // steps whose maximum was attained by several pairs (first-occurrence scan needed)
 };
 
 struct ArgPart { long long count; uint64_t key; uint32_t n_tied; uint32_t pad; };
+struct DirtyLists { uint32_t *dirty, *dirty_list, *gdirty, *gdirty_list; };
 
 struct TrainDev {
     // sizes
@@ -66,13 +70,15 @@ struct TrainDev {
     uint64_t char_cap, str_ht_cap;
     // arrays
     uint32_t *sym, *word_of, *start, *word_mark, *worklist;
-    uint32_t *pres; uint32_t pres_words, n_chunks;   // per chunk: bitmap of the symbols that (may) occur in it
+    uint32_t *filt; uint32_t n_chunks, mark_group;    // pair filter, bit-major: filt[(bit >> 5) * n_chunks + chunk]; chunks per CTA group of k_mark
     long long *freq;
     long long *sfreq;                 // WordPiece mode: frequency of every symbol (wordpiece.py:78-81), kept incrementally
     PairEntry *table;                 // current table (changes on grow)
-    ArgPart *blk;                     // per 4096-slot block: cached (max count, a key attaining it, how many attain it)
+    ArgPart *blk;                     // per 256-slot block: cached (max count, the smallest key attaining it, how many attain it)
+    ArgPart *grp;                     // per group of 256 blocks: the same over the group's blocks
     uint32_t *dirty;                  // block touched since its cache entry was computed
     uint32_t *dirty_list;             // the blocks whose flag went 0 -> 1 (what the next select has to refresh)
+    uint32_t *gdirty, *gdirty_list;   // the same per group
     uint32_t *touch_l, *touch_r;      // symbols x / y whose L[x] / R[y] became non-zero in this step
     long long *delta;                 // L[vmax] | R[vmax] | ZZ | M
     long long *dense;                 // n_alpha^2 initial counts
@@ -82,6 +88,7 @@ struct TrainDev {
     uint32_t *rec_left, *rec_right, *rec_new; long long *rec_count;
     uint32_t *sym_len; uint64_t *sym_off, *sym_hash, *sym_pow; uint32_t *chars; uint32_t *str_ht;
     TrainState *st;
+    __host__ __device__ DirtyLists dl() const { return DirtyLists{dirty, dirty_list, gdirty, gdirty_list}; }
 };
 
 constexpr uint64_t kHashP = 0x9E3779B97F4A7C15ull | 1ull;
@@ -96,8 +103,7 @@ __device__ __forceinline__ long long table_get(const PairEntry *tab, uint64_t ca
         h = (h + 1) & (cap - 1);
     }
 }
-__device__ __forceinline__ void table_add(PairEntry *tab, uint64_t cap, uint64_t key, long long d, TrainState *st, uint32_t *dirty,
-                                          uint32_t *dirty_list) {
+__device__ __forceinline__ void table_add(PairEntry *tab, uint64_t cap, uint64_t key, long long d, TrainState *st, const DirtyLists &dl) {
     uint64_t h = mix64(key) & (cap - 1);
     for (uint64_t probes = 0; probes <= cap; ++probes) {
         uint64_t k = *(volatile uint64_t *)&tab[h].key;
@@ -109,7 +115,11 @@ __device__ __forceinline__ void table_add(PairEntry *tab, uint64_t cap, uint64_t
         if (k == key) {
             atomicAdd((unsigned long long *)&tab[h].count, (unsigned long long)d);
             const uint32_t b = (uint32_t)(h >> kBlkShift);
-            if (*(volatile uint32_t *)&dirty[b] == 0u && atomicExch(&dirty[b], 1u) == 0u) dirty_list[atomicAdd(&st->n_dirty, 1u)] = b;
+            if (*(volatile uint32_t *)&dl.dirty[b] == 0u && atomicExch(&dl.dirty[b], 1u) == 0u) {
+                dl.dirty_list[atomicAdd(&st->n_dirty, 1u)] = b;
+                const uint32_t g = b >> kGrpShift;
+                if (*(volatile uint32_t *)&dl.gdirty[g] == 0u && atomicExch(&dl.gdirty[g], 1u) == 0u) dl.gdirty_list[atomicAdd(&st->n_gdirty, 1u)] = g;
+            }
             return;
         }
         h = (h + 1) & (cap - 1);
@@ -117,14 +127,17 @@ __device__ __forceinline__ void table_add(PairEntry *tab, uint64_t cap, uint64_t
     atomicExch(&st->halt, (uint32_t)kErrTableFull);
 }
 
-// ---- per-chunk symbol presence: lets the mark scan skip chunks that cannot contain the pair -----------------------
-__device__ __forceinline__ bool pres_has(const TrainDev &d, uint32_t chunk, uint32_t sym) {
-    return (d.pres[(uint64_t)chunk * d.pres_words + (sym >> 5)] >> (sym & 31u)) & 1u;
-}
-__device__ __forceinline__ void pres_set(const TrainDev &d, uint64_t slot, uint32_t sym) {
-    uint32_t *w = &d.pres[(slot >> kChunkShift) * d.pres_words + (sym >> 5)];
-    const uint32_t bit = 1u << (sym & 31u);
-    if (!(*(volatile uint32_t *)w & bit)) atomicOr(w, bit);
+// ---- per-chunk pair filter: lets the mark scan skip the chunks that cannot contain the pair --------------------------------
+// One bit per hashed pair and chunk of 4096 slots (16,384 bits per chunk, so a chunk's ~2,500 distinct pairs fill ~15 % of them).
+// Bits are only ever set (a stale bit costs one wasted chunk scan).  The layout is bit-major, filt[(bit >> 5) * n_chunks + chunk],
+// so that the query of one pair over all chunks is a contiguous read of 4 B per chunk (94 KB at 10 M word types) instead of the
+// 385 MB word table.  Round 1 kept a per-chunk SYMBOL bitmap, which stops filtering once both symbols of a pair are common.
+__device__ __forceinline__ uint32_t filt_bit(uint64_t key) { return (uint32_t)(mix64(key) >> 20) & (kFiltBits - 1u); }
+__device__ __forceinline__ void filt_set(const TrainDev &d, uint64_t slot, uint32_t a, uint32_t b) {
+    const uint32_t bit = filt_bit(((uint64_t)a << 32) | b);
+    uint32_t *w = &d.filt[(uint64_t)(bit >> 5) * d.n_chunks + (slot >> kChunkShift)];
+    const uint32_t m = 1u << (bit & 31u);
+    if (!(*(volatile uint32_t *)w & m)) atomicOr(w, m);
 }
 
 // ---- init -----------------------------------------------------------------------------------------------------
@@ -133,7 +146,10 @@ __global__ void k_init_words(TrainDev d, const uint32_t *__restrict__ syms, cons
     for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < d.n_types; t += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t b = off[t], e = off[t + 1];
         d.start[t] = (uint32_t)b;
-        for (uint64_t i = b; i < e; ++i) { d.sym[i] = syms[i] | (i == b ? kStart : 0u); d.word_of[i] = (uint32_t)t; pres_set(d, i, syms[i]); }
+        for (uint64_t i = b; i < e; ++i) {
+            d.sym[i] = syms[i] | (i == b ? kStart : 0u); d.word_of[i] = (uint32_t)t;
+            if (i + 1 < e) filt_set(d, i, syms[i], syms[i + 1]);
+        }
         if (t == d.n_types - 1) d.start[d.n_types] = (uint32_t)e;
     }
 }
@@ -145,7 +161,8 @@ __global__ void k_init_symbols(TrainDev d, long long initial_vocab) {
         TrainState *st = d.st;
         st->halt = kRun; st->n_recorded = 0; st->n_merges_total = 0; st->vocab_size = initial_vocab;
         st->n_symbols = d.n_alpha; st->n_entries = 0; st->n_live = d.n_slots; st->step_stamp = 0;
-        st->char_used = d.n_alpha; st->cur_valid = 0; st->worklist_n = 0; st->n_dirty = 0; st->n_touch_l = 0; st->n_touch_r = 0;
+        st->n_tie_steps = 0;
+        st->char_used = d.n_alpha; st->cur_valid = 0; st->worklist_n = 0; st->n_dirty = 0; st->n_gdirty = 0; st->n_touch_l = 0; st->n_touch_r = 0;
     }
 }
 __global__ void k_count_dense(TrainDev d) {
@@ -163,7 +180,7 @@ __global__ void k_count_sparse(TrainDev d, uint64_t cap) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i + 1 < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t s = d.sym[i], nx = d.sym[i + 1];
         if (nx & kStart) continue;
-        table_add(d.table, cap, ((uint64_t)(s & ~kStart) << 32) | nx, d.freq[d.word_of[i]], d.st, d.dirty, d.dirty_list);
+        table_add(d.table, cap, ((uint64_t)(s & ~kStart) << 32) | nx, d.freq[d.word_of[i]], d.st, d.dl());
     }
 }
 // sharded training with a large alphabet: every rank lists its local (pair, count) entries, the lists are all-gathered by
@@ -178,13 +195,13 @@ __global__ void k_export_pairs(TrainDev d, uint64_t cap, uint64_t *out, uint64_t
 }
 __global__ void k_import_pairs(TrainDev d, uint64_t cap, const uint64_t *in, uint64_t n) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        table_add(d.table, cap, in[2 * i], (long long)in[2 * i + 1], d.st, d.dirty, d.dirty_list);
+        table_add(d.table, cap, in[2 * i], (long long)in[2 * i + 1], d.st, d.dl());
 }
 __global__ void k_build_table(TrainDev d, uint64_t cap) {
     const uint64_t n = (uint64_t)d.n_alpha * d.n_alpha;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const long long c = d.dense[i];
-        if (c != 0) table_add(d.table, cap, ((i / d.n_alpha) << 32) | (i % d.n_alpha), c, d.st, d.dirty, d.dirty_list);
+        if (c != 0) table_add(d.table, cap, ((i / d.n_alpha) << 32) | (i % d.n_alpha), c, d.st, d.dl());
     }
 }
 __global__ void k_fill_u64(uint64_t *p, uint64_t n, uint64_t v, uint64_t stride_words) {
@@ -196,7 +213,7 @@ __global__ void k_fill_u32(uint32_t *p, uint64_t n, uint32_t v) {
 __global__ void k_rehash(const PairEntry *old_tab, uint64_t old_cap, TrainDev d, uint64_t new_cap) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_cap; i += (uint64_t)gridDim.x * blockDim.x) {
         const PairEntry e = old_tab[i];
-        if (e.key != kEmptyKey && e.count != 0) table_add(d.table, new_cap, e.key, e.count, d.st, d.dirty, d.dirty_list);
+        if (e.key != kEmptyKey && e.count != 0) table_add(d.table, new_cap, e.key, e.count, d.st, d.dl());
     }
 }
 
@@ -271,7 +288,7 @@ __global__ void __launch_bounds__(256) k_wp_select(TrainDev d) {
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; ++w) score_combine(c, k, n, sc[w], sk[w], sn[w]);
-        st->n_dirty = 0; st->n_touch_l = 0; st->n_touch_r = 0;
+        st->n_dirty = 0; st->n_gdirty = 0; st->n_touch_l = 0; st->n_touch_r = 0;
         st->best_score = c; st->max_count = n ? 1 : 0; st->n_tied = n; st->cand_key = k;
         st->worklist_n = 0; st->tie_ticket = 0; st->best_pos = kNoPos; st->cur_valid = 0;
         // loop conditions of wordpiece.py:68 and :74-75, then the capacity gates (checked before any mutation)
@@ -288,19 +305,22 @@ __device__ __forceinline__ void arg_combine(long long &c, uint64_t &k, uint32_t 
     if (c2 > c) { c = c2; k = k2; n = n2; }
     else if (c2 == c) { n += n2; if (k2 < k) k = k2; }
 }
-// Refreshes the cached maximum of every table block that was touched since the last step (usually a few
-// hundred of the thousands of blocks), so that select does not have to stream the whole table every merge.
-__global__ void __launch_bounds__(256) k_argmax_partial(TrainDev d) {
+// Two-level cache of the table maximum.  Level 1: one entry per 256-slot block (4 KB of table), refreshed by ONE WARP per block
+// that the last merge touched (a merge moves a few hundred pair counts, each in its own block: round 1 refreshed 4096-slot
+// blocks, 64 KB each, 42 us per step at 10 M types).  Level 2: one entry per group of 256 blocks, refreshed from the level-1
+// entries of the groups that hold a refreshed block.  k_select then reduces cap / 65,536 group entries.
+__global__ void __launch_bounds__(256) k_argmax_blocks(TrainDev d) {
     TrainState *st = d.st;
     if (st->halt) return;
     const uint32_t n_dirty = st->n_dirty;
-    __shared__ long long sc[8]; __shared__ uint64_t sk[8]; __shared__ uint32_t sn[8];
-    for (uint32_t q = blockIdx.x; q < n_dirty; q += gridDim.x) {
+    const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t q = warp; q < n_dirty; q += n_warps) {
         const uint32_t b = d.dirty_list[q];
         long long c = 0; uint64_t k = kEmptyKey; uint32_t n = 0;
-        const uint64_t s0 = (uint64_t)b << kBlkShift;
-        for (uint32_t i = threadIdx.x; i < (1u << kBlkShift); i += blockDim.x) {
-            const PairEntry e = d.table[s0 + i];
+        const PairEntry *base = d.table + ((uint64_t)b << kBlkShift);
+#pragma unroll
+        for (uint32_t i = 0; i < (1u << kBlkShift) / 32; ++i) {
+            const PairEntry e = base[i * 32 + lane];
             if (e.key != kEmptyKey && e.count > 0) arg_combine(c, k, n, e.count, e.key, 1u);
         }
         for (int o = 16; o > 0; o >>= 1) {
@@ -308,23 +328,37 @@ __global__ void __launch_bounds__(256) k_argmax_partial(TrainDev d) {
             uint32_t n2 = __shfl_xor_sync(0xffffffffu, n, o);
             arg_combine(c, k, n, c2, k2, n2);
         }
-        if ((threadIdx.x & 31) == 0) { sc[threadIdx.x >> 5] = c; sk[threadIdx.x >> 5] = k; sn[threadIdx.x >> 5] = n; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < 8; ++w) arg_combine(c, k, n, sc[w], sk[w], sn[w]);
-            d.blk[b] = ArgPart{c, k, n, 0};
-            d.dirty[b] = 0;
+        if (lane == 0) { d.blk[b] = ArgPart{c, k, n, 0}; d.dirty[b] = 0; }
+    }
+}
+__global__ void __launch_bounds__(256) k_argmax_groups(TrainDev d) {
+    TrainState *st = d.st;
+    if (st->halt) return;
+    const uint32_t n_gdirty = st->n_gdirty;
+    const uint32_t n_blk = (uint32_t)(st->table_cap >> kBlkShift);
+    const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t q = warp; q < n_gdirty; q += n_warps) {
+        const uint32_t g = d.gdirty_list[q];
+        long long c = 0; uint64_t k = kEmptyKey; uint32_t n = 0;
+        for (uint32_t i = lane; i < (1u << kGrpShift); i += 32) {
+            const uint32_t b = (g << kGrpShift) + i;
+            if (b < n_blk) { const ArgPart p = d.blk[b]; arg_combine(c, k, n, p.count, p.key, p.n_tied); }
         }
-        __syncthreads();
+        for (int o = 16; o > 0; o >>= 1) {
+            long long c2 = __shfl_xor_sync(0xffffffffu, c, o); uint64_t k2 = __shfl_xor_sync(0xffffffffu, k, o);
+            uint32_t n2 = __shfl_xor_sync(0xffffffffu, n, o);
+            arg_combine(c, k, n, c2, k2, n2);
+        }
+        if (lane == 0) { d.grp[g] = ArgPart{c, k, n, 0}; d.gdirty[g] = 0; }
     }
 }
 __global__ void __launch_bounds__(1024) k_select(TrainDev d, int from_parts) {
     TrainState *st = d.st;
     if (st->halt) return;
     long long c = 0; uint64_t k = kEmptyKey; uint32_t n = 0;
-    // reduce either the per-CTA partials of k_argmax_full or the per-block cache refreshed by k_argmax_partial
-    const ArgPart *src = from_parts ? d.parts : d.blk;
-    const uint32_t n_src = from_parts ? d.n_parts : (uint32_t)(st->table_cap >> kBlkShift);
+    // reduce either the per-CTA partials of k_argmax_full or the group level of the cache (k_argmax_blocks / k_argmax_groups)
+    const ArgPart *src = from_parts ? d.parts : d.grp;
+    const uint32_t n_src = from_parts ? d.n_parts : (uint32_t)((st->table_cap + (1ull << (kBlkShift + kGrpShift)) - 1) >> (kBlkShift + kGrpShift));
     for (uint32_t i = threadIdx.x; i < n_src; i += blockDim.x) { ArgPart p = src[i]; arg_combine(c, k, n, p.count, p.key, p.n_tied); }
     for (int o = 16; o > 0; o >>= 1) {
         long long c2 = __shfl_xor_sync(0xffffffffu, c, o); uint64_t k2 = __shfl_xor_sync(0xffffffffu, k, o);
@@ -336,7 +370,7 @@ __global__ void __launch_bounds__(1024) k_select(TrainDev d, int from_parts) {
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 32; ++w) arg_combine(c, k, n, sc[w], sk[w], sn[w]);
-        st->n_dirty = 0;                                    // every listed block was refreshed by k_argmax_partial
+        st->n_dirty = 0; st->n_gdirty = 0;                  // every listed block / group was refreshed
         st->n_touch_l = 0; st->n_touch_r = 0;               // consumed by the previous step's k_update
         st->max_count = c; st->n_tied = n; st->cand_key = k;
         st->worklist_n = 0; st->tie_ticket = 0; st->best_pos = kNoPos; st->cur_valid = 0;
@@ -416,6 +450,7 @@ __global__ void k_candidate(TrainDev d) {
     TrainState *st = d.st;
     uint64_t pos = kNoPos, key = kEmptyKey;
     if (!st->halt) {
+        if (st->n_tied > 1) st->n_tie_steps += 1;
         if (st->n_tied <= 1) key = st->cand_key;
         else if (st->best_pos != kNoPos) {
             pos = st->best_pos;
@@ -482,36 +517,52 @@ __global__ void __launch_bounds__(32) k_begin_merge(TrainDev d) {
     }
 }
 
-// ---- merge: mark the types that contain (a,b) -- a pure streaming read of sym[] -----------------------------------------
+// ---- merge: mark the types that contain (a,b): the pair filter names the candidate chunks, which are then read with 128-bit loads ----
+// A CTA owns groups of 64 consecutive chunks: 64 threads test the filter bit of one chunk each (one coalesced 256-byte read), the
+// flagged chunks are compacted into shared memory and scanned by the whole CTA.
+constexpr uint32_t kMarkGroup = 64;
 __global__ void __launch_bounds__(256) k_mark(TrainDev d) {
     const TrainState *st = d.st;
     if (st->halt || !st->cur_valid) return;
     const uint32_t a = st->cur_a, b = st->cur_b, stamp = st->step_stamp;
     const uint64_t n = d.n_slots;
     const uint32_t lane = threadIdx.x & 31;
-    for (uint32_t chunk = blockIdx.x; chunk < d.n_chunks; chunk += gridDim.x) {
-        // a chunk can hold an occurrence only if `a` occurs in it and `b` occurs in it or at the start of the next one
-        if (!pres_has(d, chunk, a)) continue;                                        // CTA-uniform
-        if (!pres_has(d, chunk, b) && !(chunk + 1 < d.n_chunks && pres_has(d, chunk + 1, b))) continue;
-        const uint64_t c0 = (uint64_t)chunk << kChunkShift;
-        for (uint32_t it = 0; it < (1u << kChunkShift) / (256 * 4); ++it) {
-            const uint64_t i = c0 + ((uint64_t)it * 256 + threadIdx.x) * 4;           // 4 slots per thread, 128-bit load
-            uint4 v = make_uint4(kHole, kHole, kHole, kHole);
-            if (i < n) v = *reinterpret_cast<const uint4 *>(d.sym + i);              // sym[] is padded with dead slots
-            uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x, 1);
-            if (lane == 31) nxt = (i + 4 < n) ? d.sym[i + 4] : kHole;
-            const bool m0 = (v.x & ~kStart) == a && v.y == b, m1 = (v.y & ~kStart) == a && v.z == b;
-            const bool m2 = (v.z & ~kStart) == a && v.w == b, m3 = (v.w & ~kStart) == a && nxt == b;
-            if (m0 | m1 | m2 | m3) {
+    const uint32_t bit = filt_bit(((uint64_t)a << 32) | b);
+    const uint32_t *frow = d.filt + (uint64_t)(bit >> 5) * d.n_chunks;
+    const uint32_t fmask = 1u << (bit & 31u);
+    __shared__ uint32_t s_list[kMarkGroup], s_n;
+    const uint32_t grp = d.mark_group, n_groups = (d.n_chunks + grp - 1) / grp;
+    for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        if (threadIdx.x < grp) {
+            const uint32_t chunk = g * grp + threadIdx.x;
+            if (chunk < d.n_chunks && (frow[chunk] & fmask)) s_list[atomicAdd(&s_n, 1u)] = chunk;
+        }
+        __syncthreads();
+        const uint32_t n_list = s_n;
+        for (uint32_t q = 0; q < n_list; ++q) {
+            const uint64_t c0 = (uint64_t)s_list[q] << kChunkShift;
+            for (uint32_t it = 0; it < (1u << kChunkShift) / (256 * 4); ++it) {
+                const uint64_t i = c0 + ((uint64_t)it * 256 + threadIdx.x) * 4;           // 4 slots per thread, 128-bit load
+                uint4 v = make_uint4(kHole, kHole, kHole, kHole);
+                if (i < n) v = *reinterpret_cast<const uint4 *>(d.sym + i);              // sym[] is padded with dead slots
+                uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x, 1);
+                if (lane == 31) nxt = (i + 4 < n) ? d.sym[i + 4] : kHole;
+                const bool m0 = (v.x & ~kStart) == a && v.y == b, m1 = (v.y & ~kStart) == a && v.z == b;
+                const bool m2 = (v.z & ~kStart) == a && v.w == b, m3 = (v.w & ~kStart) == a && nxt == b;
+                if (m0 | m1 | m2 | m3) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const bool m = k == 0 ? m0 : k == 1 ? m1 : k == 2 ? m2 : m3;
-                    if (!m) continue;
-                    const uint32_t w = d.word_of[i + k];
-                    if (atomicExch(&d.word_mark[w], stamp) != stamp) d.worklist[atomicAdd(&d.st->worklist_n, 1u)] = w;
+                    for (int k = 0; k < 4; ++k) {
+                        const bool m = k == 0 ? m0 : k == 1 ? m1 : k == 2 ? m2 : m3;
+                        if (!m) continue;
+                        const uint32_t w = d.word_of[i + k];
+                        if (atomicExch(&d.word_mark[w], stamp) != stamp) d.worklist[atomicAdd(&d.st->worklist_n, 1u)] = w;
+                    }
                 }
             }
         }
+        __syncthreads();
     }
 }
 
@@ -538,10 +589,13 @@ __global__ void __launch_bounds__(128) k_apply(TrainDev d) {
                     else if (atomicAdd((unsigned long long *)&L[prev], (unsigned long long)f) == 0ull) d.touch_l[atomicAdd(&st->n_touch_l, 1u)] = prev;
                 }
                 m += f;
-                d.sym[o] = z; pres_set(d, o, z); prev = z; last_merge = true; r += 2;
+                if (have_prev) filt_set(d, o - 1, prev, z);          // the pair now in front of the merged symbol lives at slot o - 1
+                d.sym[o] = z; prev = z; last_merge = true; r += 2;
             } else {
                 if (have_prev && last_merge && atomicAdd((unsigned long long *)&R[s], (unsigned long long)f) == 0ull) d.touch_r[atomicAdd(&st->n_touch_r, 1u)] = s;
-                d.sym[o] = s; if (o != r) pres_set(d, o, s); prev = s; last_merge = false; r += 1;
+                // a pair that is new (z in front) or that moved left with the compaction may now belong to another chunk
+                if (have_prev && (last_merge || o != r)) filt_set(d, o - 1, prev, s);
+                d.sym[o] = s; prev = s; last_merge = false; r += 1;
             }
             have_prev = true; ++o;
         }
@@ -567,26 +621,26 @@ __global__ void __launch_bounds__(256) k_update(TrainDev d) {
         const uint32_t nl = st->n_touch_l, nr = st->n_touch_r;
         for (uint32_t i = gtid; i < nl; i += gsz) {
             const uint64_t x = d.touch_l[i]; const long long l = L[x];
-            table_add(d.table, cap, (x << 32) | a, -l, st, d.dirty, d.dirty_list); table_add(d.table, cap, (x << 32) | z, l, st, d.dirty, d.dirty_list);
+            table_add(d.table, cap, (x << 32) | a, -l, st, d.dl()); table_add(d.table, cap, (x << 32) | z, l, st, d.dl());
             L[x] = 0;
         }
         for (uint32_t i = gtid; i < nr; i += gsz) {
             const uint64_t y = d.touch_r[i]; const long long r = R[y];
-            table_add(d.table, cap, (b << 32) | y, -r, st, d.dirty, d.dirty_list); table_add(d.table, cap, (z << 32) | y, r, st, d.dirty, d.dirty_list);
+            table_add(d.table, cap, (b << 32) | y, -r, st, d.dl()); table_add(d.table, cap, (z << 32) | y, r, st, d.dl());
             R[y] = 0;
         }
     } else {
         // sharded: the deltas were summed over ranks, the lists are rank-local -> visit every symbol
         for (uint32_t x = gtid; x < d.vmax; x += gsz) {
             const long long l = L[x], r = R[x];
-            if (l) { table_add(d.table, cap, ((uint64_t)x << 32) | a, -l, st, d.dirty, d.dirty_list); table_add(d.table, cap, ((uint64_t)x << 32) | z, l, st, d.dirty, d.dirty_list); L[x] = 0; }
-            if (r) { table_add(d.table, cap, (b << 32) | x, -r, st, d.dirty, d.dirty_list); table_add(d.table, cap, (z << 32) | x, r, st, d.dirty, d.dirty_list); R[x] = 0; }
+            if (l) { table_add(d.table, cap, ((uint64_t)x << 32) | a, -l, st, d.dl()); table_add(d.table, cap, ((uint64_t)x << 32) | z, l, st, d.dl()); L[x] = 0; }
+            if (r) { table_add(d.table, cap, (b << 32) | x, -r, st, d.dl()); table_add(d.table, cap, (z << 32) | x, r, st, d.dl()); R[x] = 0; }
         }
     }
     if (gtid == 0) {
         const long long zz = d.delta[2 * (uint64_t)d.vmax], m = d.delta[2 * (uint64_t)d.vmax + 1];
-        if (zz) { table_add(d.table, cap, (b << 32) | a, -zz, st, d.dirty, d.dirty_list); table_add(d.table, cap, (z << 32) | z, zz, st, d.dirty, d.dirty_list); }
-        if (m) table_add(d.table, cap, (a << 32) | b, -m, st, d.dirty, d.dirty_list);
+        if (zz) { table_add(d.table, cap, (b << 32) | a, -zz, st, d.dl()); table_add(d.table, cap, (z << 32) | z, zz, st, d.dl()); }
+        if (m) table_add(d.table, cap, (a << 32) | b, -m, st, d.dl());
         if (d.mode == 1) { d.sfreq[a] -= m; d.sfreq[b] -= m; d.sfreq[z] += m; }      // wordpiece.py:78-81, incrementally
         d.delta[2 * (uint64_t)d.vmax] = 0; d.delta[2 * (uint64_t)d.vmax + 1] = 0;
     }
@@ -596,7 +650,7 @@ __global__ void k_clear_halt(TrainState *st, uint32_t which, uint32_t reset_reco
     if (st->halt == which) st->halt = kRun;
     if (reset_records) st->n_recorded = 0;
 }
-__global__ void k_set_table_cap(TrainState *st, uint64_t cap) { st->table_cap = cap; st->n_entries = 0; st->n_dirty = 0; }
+__global__ void k_set_table_cap(TrainState *st, uint64_t cap) { st->table_cap = cap; st->n_entries = 0; st->n_dirty = 0; st->n_gdirty = 0; }
 
 }  // namespace swt
 
@@ -632,16 +686,20 @@ static uint64_t char_cap_of(const swt_bpe_train_config *cfg) {
 }
 
 static size_t table_region_bytes(uint64_t cap) {
-    const uint64_t n_blk = cap >> kBlkShift;
-    return align_up(cap * sizeof(PairEntry), 256) + align_up(n_blk * sizeof(ArgPart), 256) + 2 * align_up(n_blk * sizeof(uint32_t), 256);
+    const uint64_t n_blk = cap >> kBlkShift, n_grp = (n_blk >> kGrpShift) + 1;
+    return align_up(cap * sizeof(PairEntry), 256) + align_up(n_blk * sizeof(ArgPart), 256) + 2 * align_up(n_blk * sizeof(uint32_t), 256) +
+           align_up(n_grp * sizeof(ArgPart), 256) + 2 * align_up(n_grp * sizeof(uint32_t), 256);
 }
 static void table_region_carve(void *base, uint64_t cap, TrainDev *d) {
     uint8_t *p = (uint8_t *)base;
-    const uint64_t n_blk = cap >> kBlkShift;
+    const uint64_t n_blk = cap >> kBlkShift, n_grp = (n_blk >> kGrpShift) + 1;
     d->table = (PairEntry *)p; p += align_up(cap * sizeof(PairEntry), 256);
     d->blk = (ArgPart *)p; p += align_up(n_blk * sizeof(ArgPart), 256);
     d->dirty = (uint32_t *)p; p += align_up(n_blk * sizeof(uint32_t), 256);
-    d->dirty_list = (uint32_t *)p;
+    d->dirty_list = (uint32_t *)p; p += align_up(n_blk * sizeof(uint32_t), 256);
+    d->grp = (ArgPart *)p; p += align_up(n_grp * sizeof(ArgPart), 256);
+    d->gdirty = (uint32_t *)p; p += align_up(n_grp * sizeof(uint32_t), 256);
+    d->gdirty_list = (uint32_t *)p;
 }
 static size_t train_layout(const swt_bpe_train_config *cfg, void *base, TrainDev *d, uint64_t table_cap) {
     Carver cv(base);
@@ -655,8 +713,8 @@ static size_t train_layout(const swt_bpe_train_config *cfg, void *base, TrainDev
     d->st = cv.take<TrainState>(1);
     d->sym = cv.take<uint32_t>(d->n_slots + 8);
     d->n_chunks = (uint32_t)((d->n_slots + (1ull << kChunkShift) - 1) >> kChunkShift);
-    d->pres_words = (vmax + 31) / 32;
-    d->pres = cv.take<uint32_t>((uint64_t)d->n_chunks * d->pres_words + 1);
+    d->filt = cv.take<uint32_t>((uint64_t)d->n_chunks * (kFiltBits / 32) + 1);
+    d->mark_group = std::min<uint32_t>(kMarkGroup, std::max<uint32_t>(1u, d->n_chunks / (2 * kNumSMs)));      // small corpora: one chunk per CTA
     d->word_of = cv.take<uint32_t>(d->n_slots + 1);
     d->start = cv.take<uint32_t>(d->n_types + 1);
     d->word_mark = cv.take<uint32_t>(d->n_types + 1);
@@ -789,8 +847,9 @@ SWT_API int swt_bpe_train_select(swt_bpe_trainer *t, void *stream) {
         if (t->table_cap <= (1ull << 20)) {       // small table: plain parallel pass
             k_argmax_full<<<t->dev.n_parts, 256, 0, st>>>(t->dev);
             k_select<<<1, 1024, 0, st>>>(t->dev, 1);
-        } else {                                  // large table: refresh only the blocks the last merge touched
-            k_argmax_partial<<<t->dev.n_parts, 256, 0, st>>>(t->dev);
+        } else {                                  // large table: refresh only the blocks (then groups) the last merge touched
+            k_argmax_blocks<<<kNumSMs, 256, 0, st>>>(t->dev);
+            k_argmax_groups<<<32, 256, 0, st>>>(t->dev);
             k_select<<<1, 1024, 0, st>>>(t->dev, 0);
         }
     }
@@ -804,7 +863,7 @@ SWT_API int swt_bpe_train_merge(swt_bpe_trainer *t, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     k_begin_merge<<<1, 32, 0, st>>>(t->dev);
     if (t->dev.n_slots) {
-        k_mark<<<(int)std::min<uint32_t>((uint32_t)t->grid_scan, t->dev.n_chunks), 256, 0, st>>>(t->dev);
+        k_mark<<<(int)std::min<uint32_t>((uint32_t)t->grid_scan, (t->dev.n_chunks + t->dev.mark_group - 1) / t->dev.mark_group), 256, 0, st>>>(t->dev);
         k_apply<<<t->grid_scan / 2, 128, 0, st>>>(t->dev);
     }
     SWT_CUDA_OK(cudaGetLastError());
@@ -869,6 +928,7 @@ SWT_API int swt_bpe_train_read(swt_bpe_trainer *t, uint32_t *h_left, uint32_t *h
     SWT_CUDA_OK(cudaStreamSynchronize(st));
     state->halt = hs.halt; state->n_recorded = n; state->n_merges_total = hs.n_merges_total; state->vocab_size = hs.vocab_size;
     state->n_symbols = hs.n_symbols; state->n_table_entries = hs.n_entries; state->table_cap = hs.table_cap; state->n_live_slots = hs.n_live;
+    state->n_tie_steps = hs.n_tie_steps;
     return SWT_OK;
 }
 

@@ -35,8 +35,14 @@ namespace swt {
 
 constexpr int kWarps = 8;              // warps per CTA; every warp owns its own tile
 constexpr int kThreads = kWarps * 32;
-constexpr int kCtasPerSm = 4;
-constexpr int kEmitCtasPerSm = 4;
+#ifndef SWT_COUNT_CTAS
+#define SWT_COUNT_CTAS 4
+#endif
+#ifndef SWT_EMIT_CTAS
+#define SWT_EMIT_CTAS 4
+#endif
+constexpr int kCtasPerSm = SWT_COUNT_CTAS;        // resident CTAs per SM the count / emit kernels are compiled for (register budget)
+constexpr int kEmitCtasPerSm = SWT_EMIT_CTAS;
 constexpr int kWordsPerThread = 2;
 constexpr int kTileWords = 32 * kWordsPerThread;         // 64 words per (warp) tile
 constexpr int kShortBytes = 32;        // words up to this many bytes are encoded by one thread (and memoised)
@@ -476,6 +482,8 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
         h6 += flush_pending_words(enc, sg, ws, arena, word_off, arena_end, status, pend + first, count, warp_words, pend + 96);
         n_slow_words += count;
     };
+    // the offsets of the next tile are fetched one tile ahead.  (Measured, round 2: fetching them two tiles ahead cost 20 % -- register
+    // pressure; prefetch.global.L1 of the next tile's arena lines / memo ids compiles to CCTL and more than doubled the emit pass.)
     uint32_t po0 = 0, po1 = 0, po2 = 0;
     if (warp_global < ws.n_tiles) load_offsets(warp_global, po0, po1, po2);
     for (uint32_t tile = warp_global; tile < ws.n_tiles; tile += n_warps) {
@@ -822,23 +830,26 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
     uint32_t *compact = s_compact[threadIdx.x >> 5];
     bool bulk_pending = false;                                                  // lane 0: a bulk copy may still be reading `compact`
 
-    // the per-word records and the tile's output position are fetched one tile ahead
-    auto load_tile = [&](uint32_t t, uint32_t &p0, uint32_t &p1, uint64_t &b) {
+    // software pipeline: the per-word records and the tile's output position are fetched two tiles ahead (the two addends of the
+    // position are kept apart: adding them at load time made every iteration wait for the loads it had just issued)
+    auto load_tile = [&](uint32_t t, uint32_t &p0, uint32_t &p1, unsigned long long &gb, uint32_t &tt) {
         const uint32_t w0 = t * kTileWords, tw = min((uint32_t)kTileWords, n_words - w0), i = lane * kWordsPerThread;
         p0 = p1 = 0u;
         if (i + 1 < tw) { const uint2 p = *reinterpret_cast<const uint2 *>(ws.packed + w0 + i); p0 = p.x; p1 = p.y; }
         else if (i < tw) p0 = ws.packed[w0 + i];
-        b = ws.group_base[t / kGroupTiles] + ws.tile_total[t];
+        gb = ws.group_base[t / kGroupTiles]; tt = ws.tile_total[t];
     };
-    uint32_t pp0 = 0, pp1 = 0; uint64_t pbase = 0;
-    if (warp_global < ws.n_tiles) load_tile(warp_global, pp0, pp1, pbase);
+    uint32_t pp0 = 0, pp1 = 0, ptt = 0, qp0 = 0, qp1 = 0, qtt = 0; unsigned long long pgb = 0, qgb = 0;
+    if (warp_global < ws.n_tiles) load_tile(warp_global, pp0, pp1, pgb, ptt);
+    if (warp_global + n_warps < ws.n_tiles) load_tile(warp_global + n_warps, qp0, qp1, qgb, qtt);
     for (uint32_t tile = warp_global; tile < ws.n_tiles; tile += n_warps) {
         const uint32_t w_tile = tile * kTileWords;
         const uint32_t tile_words = min((uint32_t)kTileWords, n_words - w_tile);
         const uint32_t i0 = lane * kWordsPerThread;
         const uint32_t packed[kWordsPerThread] = {pp0, pp1};
-        const uint64_t base = pbase;
-        if (tile + n_warps < ws.n_tiles) load_tile(tile + n_warps, pp0, pp1, pbase);
+        const uint64_t base = pgb + ptt;
+        pp0 = qp0; pp1 = qp1; pgb = qgb; ptt = qtt;
+        if (tile + 2 * n_warps < ws.n_tiles) load_tile(tile + 2 * n_warps, qp0, qp1, qgb, qtt);
         uint32_t kind[kWordsPerThread], ntok[kWordsPerThread], arg[kWordsPerThread];
         uint4 ra[kWordsPerThread], rb[kWordsPerThread];
 #pragma unroll
