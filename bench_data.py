@@ -54,19 +54,26 @@ def synth_type_table(n_types: int, seed: int, max_len: int = 22):
     pos = np.arange(max_len, dtype=np.int64)
     pw = np.uint64(0x9E3779B97F4A7C15) ** np.arange(1, max_len + 1, dtype=np.uint64)      # wraps mod 2^64
     rows, seen, have = [], np.zeros(0, dtype=np.uint64), 0
+    u_len32, u_off32, pos32 = u_len.astype(np.int32), u_off.astype(np.int32), pos.astype(np.int32)
     while have < n_types:
         m = int(min(2_000_000, max(1 << 16, (n_types - have) * 5 // 4)))
         k = rng.integers(1, 5, size=m)
-        idx = rng.integers(0, nu, size=(m, 4))
-        tgt = np.clip(np.rint(rng.normal(8.2, 3.0, size=m)), 2, max_len).astype(np.int64)     # train-5K: mode 7-8, mean 8.18, max 22
-        ul = u_len[idx] * (np.arange(4)[None, :] < k[:, None])
-        cum = np.cumsum(ul, axis=1)                                                          # [m, 4] inclusive
+        idx = rng.integers(0, nu, size=(m, 4)).astype(np.int32)
+        tgt = np.clip(np.rint(rng.normal(8.2, 3.0, size=m)), 2, max_len).astype(np.int32)     # train-5K: mode 7-8, mean 8.18, max 22
+        ul = u_len32[idx] * (np.arange(4, dtype=np.int32)[None, :] < k[:, None])
+        cum = np.cumsum(ul, axis=1, dtype=np.int32)                                          # [m, 4] inclusive
         total = np.minimum(cum[:, 3], tgt)
-        u = (pos[None, :, None] >= cum[:, None, :]).sum(-1).clip(0, 3)                       # unit that holds position j
-        start = np.take_along_axis(np.concatenate([np.zeros((m, 1), np.int64), cum[:, :3]], axis=1), u, axis=1)
-        src = u_off[np.take_along_axis(idx, u, axis=1)] + (pos[None, :] - start)
-        valid = pos[None, :] < total[:, None]
-        mat = np.where(valid, u_arena[np.where(valid, src, 0)], 0).astype(np.uint16)
+        # unit that holds position j, the unit's first position, and the source index of the character
+        src = np.empty((m, max_len), dtype=np.int32)
+        c0, c1, c2 = cum[:, 0:1], cum[:, 1:2], cum[:, 2:3]
+        p = pos32[None, :]
+        in0, in1, in2 = p < c0, p < c1, p < c2
+        uo = u_off32[idx]                                                                    # [m, 4] first character of every unit
+        src[:] = np.where(in0, uo[:, 0:1] + p, np.where(in1, uo[:, 1:2] + (p - c0), np.where(in2, uo[:, 2:3] + (p - c1), uo[:, 3:4] + (p - c2))))
+        valid = p < total[:, None]
+        np.putmask(src, ~valid, 0)
+        mat = u_arena[src]
+        np.putmask(mat, ~valid, 0)
         h = (mat.astype(np.uint64) * pw[None, :]).sum(axis=1, dtype=np.uint64) + total.astype(np.uint64)
         _, first = np.unique(h, return_index=True)
         keep = np.zeros(m, dtype=bool)
@@ -74,7 +81,7 @@ def synth_type_table(n_types: int, seed: int, max_len: int = 22):
         if len(seen):
             keep &= ~np.isin(h, seen)
         sel = np.flatnonzero(keep)[: n_types - have]
-        rows.append((mat[sel], total[sel]))
+        rows.append((mat[sel], total[sel].astype(np.int64)))
         seen = np.concatenate([seen, h[sel]])
         have += len(sel)
     mat = np.concatenate([r[0] for r in rows])

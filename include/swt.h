@@ -337,7 +337,12 @@ int swt_bpe_train_read(swt_bpe_trainer *t, uint32_t *h_left, uint32_t *h_right, 
 /* replaces the pair table by one of `new_cap` slots inside a caller-provided buffer; clears halt==3 */
 size_t swt_bpe_train_table_bytes(uint64_t cap);
 int swt_bpe_train_grow_table(swt_bpe_trainer *t, void *d_new_table, uint64_t new_cap, void *stream);
-/* copies the current segmentation of this rank's types to the host: symbol ids + per-type lengths */
+/* Maintenance between batches of steps (call it where the merges are read back, every few hundred steps; n_live_slots from the
+ * state): rebuilds the per-chunk pair filter of the mark scan from the live pairs and, once fewer than 60 % of the slots are
+ * live, compacts the word table so that the scans shrink with the corpus.  *kernels_changed = 1 when the kernels' extents
+ * changed: CUDA graphs the CALLER captured over select / merge / update must be re-captured.  May synchronise and allocate. */
+int swt_bpe_train_maintain(swt_bpe_trainer *t, uint64_t n_live_slots, int *kernels_changed, void *stream);
+/* copies the current segmentation of this rank's types to the host: symbol ids (type w at its original offset) + per-type lengths */
 int swt_bpe_train_read_corpus(swt_bpe_trainer *t, uint32_t *h_syms /* n_slots_local */, uint32_t *h_len /* n_types_local */,
                               void *stream);
 

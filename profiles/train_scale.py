@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--check-oracle-steps", type=int, default=0, help="compare the first K merges with the CPU oracle")
     ap.add_argument("--steps-per-sync", type=int, default=512)
     ap.add_argument("--no-peer", action="store_true", help="keep the two NCCL collectives per step (round-1 exchange)")
+    ap.add_argument("--timing", action="store_true", help="per-kernel device times (eager launches, synchronised: slow)")
     args = ap.parse_args()
     import torch, torch.distributed as dist
     from subword_tokenizers_b200 import device
@@ -28,6 +29,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.no_peer:
         os.environ["SWT_NO_PEER_EXCHANGE"] = "1"
+    if args.timing:
+        device.tune("train_timing", 1)
     t0 = time.perf_counter()
     mat, lens = BD.synth_type_table(args.types, args.seed)
     cps, off = BD.table_to_cps(mat, lens)
@@ -63,6 +66,7 @@ def main():
         out["oracle_prefix_checked"] = m
         out["oracle_prefix_equal"] = bool(np.array_equal(l[:m], ol[:m]) and np.array_equal(r[:m], orr[:m]) and
                                           np.array_equal(n[:m], on[:m]) and np.array_equal(c[:m], oc[:m]))
+    eng.close()
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:

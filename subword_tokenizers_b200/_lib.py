@@ -104,6 +104,7 @@ SIGNATURES = {
     "swt_bpe_train_read": (ctypes.c_int, [c_vp, c_u32p, c_u32p, c_u32p, c_i64p, ctypes.POINTER(TrainState), c_vp]),
     "swt_bpe_train_table_bytes": (ctypes.c_size_t, [ctypes.c_uint64]),
     "swt_bpe_train_grow_table": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint64, c_vp]),
+    "swt_bpe_train_maintain": (ctypes.c_int, [c_vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_int), c_vp]),
     "swt_bpe_train_read_corpus": (ctypes.c_int, [c_vp, c_u32p, c_u32p, c_vp]),
 }
 

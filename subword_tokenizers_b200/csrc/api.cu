@@ -11,6 +11,7 @@ static thread_local std::string g_last_error;
 void set_error(const std::string &msg) { g_last_error = msg; }
 
 Tuning g_tune;
+int g_train_timing = 0;
 
 size_t encode_workspace_layout(uint32_t n_words, uint64_t long_bytes, void *base, EncodeWorkspace *ws) {
     Carver cv(base);
@@ -65,6 +66,7 @@ SWT_API int swt_tune(const char *name, int value) {
     else if (n == "timing") g_tune.timing = value;
     else if (n == "warp_words") g_tune.warp_words = value;
     else if (n == "bpe_queue") g_tune.bpe_queue = value;
+    else if (n == "train_timing") g_train_timing = value;
     else { set_error("swt_tune: unknown knob " + n); return SWT_ERR_ARG; }
     return SWT_OK;
 }

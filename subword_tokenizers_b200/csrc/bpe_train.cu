@@ -21,9 +21,14 @@
 // rank folds the same global deltas into its replica of the table, so replicas stay identical.
 #include <algorithm>
 #include <cstdlib>
+#include <map>
 #include <vector>
 
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
+
+namespace swt { extern int g_train_timing; }
 
 namespace swt {
 
@@ -57,7 +62,10 @@ struct TrainState {                 // device resident, mutable
     uint32_t n_dirty, n_touch_l, n_touch_r, n_gdirty;   // lengths of the dirty-block / dirty-group lists and of the touched-symbol lists
     double best_score;                              // WordPiece mode: the maximal score of this step
     uint64_t n_tie_steps;                           // steps whose maximum was attained by several pairs (first-occurrence scan needed)
+    uint32_t n_tie_keys, pad1;                      // the tied pairs themselves when there are at most kTieKeys of them (else 0)
+    uint64_t tie_keys[32];
 };
+constexpr uint32_t kTieKeys = 32;
 
 struct ArgPart { long long count; uint64_t key; uint32_t n_tied; uint32_t pad; };
 struct DirtyLists { uint32_t *dirty, *dirty_list, *gdirty, *gdirty_list; };
@@ -70,6 +78,7 @@ struct TrainDev {
     uint64_t char_cap, str_ht_cap;
     // arrays
     uint32_t *sym, *word_of, *start, *word_mark, *worklist;
+    uint32_t *sym2, *word_of2, *start2;             // second copies for the compaction of the word table (swt_bpe_train_maintain)
     uint32_t *filt; uint32_t n_chunks, mark_group;    // pair filter, bit-major: filt[(bit >> 5) * n_chunks + chunk]; chunks per CTA group of k_mark
     long long *freq;
     long long *sfreq;                 // WordPiece mode: frequency of every symbol (wordpiece.py:78-81), kept incrementally
@@ -214,6 +223,35 @@ __global__ void k_rehash(const PairEntry *old_tab, uint64_t old_cap, TrainDev d,
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < old_cap; i += (uint64_t)gridDim.x * blockDim.x) {
         const PairEntry e = old_tab[i];
         if (e.key != kEmptyKey && e.count != 0) table_add(d.table, new_cap, e.key, e.count, d.st, d.dl());
+    }
+}
+
+// ---- maintenance between step batches (swt_bpe_train_maintain) ------------------------------------------------------------------
+// Merged words are compacted to the front of their own slot range, so the word table keeps its initial extent while three quarters
+// of it die; the pair filter only ever gains bits.  Every few hundred steps the host asks for (a) a rebuild of the filter from the
+// live pairs and, once less than 60 % of the slots are live, (b) a compaction of the whole table (words keep their order, so slot
+// order is still first-occurrence order): the mark and tie scans then shrink with the corpus.
+__global__ void k_word_len(TrainDev d, uint32_t *len) {
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < d.n_types; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = d.start[t], e = d.start[t + 1];
+        uint32_t n = 0;
+        while (s + n < e && d.sym[s + n] != kHole) ++n;
+        len[t] = n;
+    }
+}
+__global__ void k_compact_words(TrainDev d, const uint32_t *len, uint32_t n_new) {
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < d.n_types; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = d.start[t], ns = d.start2[t], n = len[t];
+        for (uint32_t k = 0; k < n; ++k) { d.sym2[ns + k] = d.sym[s + k]; d.word_of2[ns + k] = (uint32_t)t; }
+        if (t == d.n_types - 1) { d.start2[d.n_types] = n_new; for (uint32_t k = 0; k < 8; ++k) d.sym2[n_new + k] = kHole; }
+    }
+}
+__global__ void k_build_filter(TrainDev d) {
+    const uint64_t n = d.n_slots;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i + 1 < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = d.sym[i], nx = d.sym[i + 1];
+        if (s == kHole || (nx & kStart)) continue;                       // dead slot / last symbol of its type (kHole has the start bit)
+        filt_set(d, i, s & ~kStart, nx);
     }
 }
 
@@ -373,13 +411,29 @@ __global__ void __launch_bounds__(1024) k_select(TrainDev d, int from_parts) {
         st->n_dirty = 0; st->n_gdirty = 0;                  // every listed block / group was refreshed
         st->n_touch_l = 0; st->n_touch_r = 0;               // consumed by the previous step's k_update
         st->max_count = c; st->n_tied = n; st->cand_key = k;
-        st->worklist_n = 0; st->tie_ticket = 0; st->best_pos = kNoPos; st->cur_valid = 0;
+        st->worklist_n = 0; st->tie_ticket = 0; st->best_pos = kNoPos; st->cur_valid = 0; st->n_tie_keys = 0;
         // loop conditions of bpe.py:88 and :98-99, then the capacity gates (checked before any mutation)
         if (st->vocab_size >= d.max_vocab) st->halt = kDoneVocab;
         else if (c <= 0) st->halt = kDoneNoPairs;
         else if (st->n_recorded >= d.record_cap) st->halt = kRecordFull;
         else if ((st->n_entries + 2 * st->n_symbols + 2) * 10 > st->table_cap * 7) st->halt = kNeedGrow;
         else if (st->n_symbols + 1 > d.vmax) st->halt = kErrSymbols;
+        sc[0] = c; sn[0] = (st->halt == kRun && !from_parts && d.mode == 0 && n >= 2 && n <= kTieKeys) ? n : 0u;
+    }
+    __syncthreads();
+    // A tie among a few pairs: list them (the blocks whose cached maximum equals the maximum hold them), so that the first-occurrence
+    // scan can use the pair filter and compare keys instead of probing the table at every position.
+    if (sn[0]) {
+        const long long cmax = sc[0];
+        const uint32_t n_blk = (uint32_t)(st->table_cap >> kBlkShift);
+        for (uint32_t b = threadIdx.x; b < n_blk; b += blockDim.x) {
+            if (d.blk[b].count != cmax) continue;
+            const PairEntry *base = d.table + ((uint64_t)b << kBlkShift);
+            for (uint32_t i = 0; i < (1u << kBlkShift); ++i) {
+                const PairEntry e = base[i];
+                if (e.key != kEmptyKey && e.count == cmax) { const uint32_t q = atomicAdd(&st->n_tie_keys, 1u); if (q < kTieKeys) st->tie_keys[q] = e.key; }
+            }
+        }
     }
 }
 
@@ -421,6 +475,62 @@ __global__ void __launch_bounds__(256) k_tie_scan(TrainDev d) {
     const uint64_t cap = st->table_cap;
     __shared__ uint32_t s_chunk, s_stop;
     __shared__ unsigned long long s_best;
+    if (st->n_tie_keys == st->n_tied) {
+        // ---- the tied pairs are listed (k_select): groups of 64 filter chunks in ascending order; a chunk is read only when the
+        // filter admits one of the pairs, and positions are compared with the listed keys (no table probes)
+        __shared__ uint64_t s_keys[kTieKeys];
+        __shared__ uint32_t s_row[kTieKeys], s_mask[kTieKeys], s_list[64], s_flag[64], s_n;
+        const uint32_t nk = st->n_tie_keys;
+        if (threadIdx.x < nk) {
+            const uint64_t k = st->tie_keys[threadIdx.x];
+            const uint32_t bit = filt_bit(k);
+            s_keys[threadIdx.x] = k; s_row[threadIdx.x] = bit >> 5; s_mask[threadIdx.x] = 1u << (bit & 31u);
+        }
+        const uint64_t group_slots = 64ull << kChunkShift;
+        for (;;) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_chunk = atomicAdd(&st->tie_ticket, 1u); s_best = kNoPos; s_n = 0;
+                const uint64_t c = (uint64_t)s_chunk * group_slots;
+                s_stop = (c >= d.n_slots) || (*(volatile uint64_t *)&st->best_pos < d.slot_base + c);
+            }
+            __syncthreads();
+            if (s_stop) break;
+            if (threadIdx.x < 64) {                                                          // one chunk per thread: any key's bit set?
+                const uint32_t chunk = s_chunk * 64 + threadIdx.x;
+                bool f = false;
+                if (chunk < d.n_chunks) for (uint32_t k = 0; k < nk && !f; ++k) f = (d.filt[(uint64_t)s_row[k] * d.n_chunks + chunk] & s_mask[k]) != 0;
+                s_flag[threadIdx.x] = f ? 1u : 0u;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {                                                          // ascending list of the flagged chunks
+                uint32_t n = 0;
+                for (uint32_t q = 0; q < 64; ++q) if (s_flag[q]) s_list[n++] = s_chunk * 64 + q;
+                s_n = n;
+            }
+            __syncthreads();
+            const uint32_t n_list = s_n;
+            for (uint32_t q = 0; q < n_list; ++q) {
+                const uint64_t c0 = (uint64_t)s_list[q] << kChunkShift;
+                if (s_best != kNoPos) break;                                                 // an earlier chunk of this group already matched
+                uint64_t mine = kNoPos;
+                for (uint32_t it = 0; it < (1u << kChunkShift) / 256 && mine == kNoPos; ++it) {
+                    const uint64_t i = c0 + (uint64_t)it * 256 + threadIdx.x;
+                    if (i + 1 < d.n_slots) {
+                        const uint32_t sy = d.sym[i], nx = d.sym[i + 1];
+                        if (sy != kHole && !(nx & kStart)) {
+                            const uint64_t key = ((uint64_t)(sy & ~kStart) << 32) | nx;
+                            for (uint32_t k = 0; k < nk; ++k) if (s_keys[k] == key) mine = i;
+                        }
+                    }
+                }
+                if (mine != kNoPos) atomicMin(&s_best, (unsigned long long)mine);
+                __syncthreads();
+            }
+            if (threadIdx.x == 0 && s_best != kNoPos) atomicMin((unsigned long long *)&st->best_pos, (unsigned long long)(d.slot_base + s_best));
+        }
+        return;
+    }
     for (;;) {
         if (threadIdx.x == 0) {
             s_chunk = atomicAdd(&st->tie_ticket, 1u); s_best = kNoPos;
@@ -662,8 +772,26 @@ struct swt_bpe_trainer {
     int device;
     uint64_t table_cap;
     int grid_scan;      // persistent grid for streaming passes
+    const uint64_t *d_off0 = nullptr;   // the caller's type offsets (layout of swt_bpe_train_read_corpus)
+    uint64_t n_slots0 = 0;              // slots at create (the table is compacted as it shrinks)
+    uint32_t n_compactions = 0;
     cudaGraphExec_t step_graph = nullptr;   // kStepsPerGraph whole steps, captured once (re-captured after a table grow)
+    // swt_tune("train_timing", 1): every kernel is launched eagerly between two events and synchronised; totals on stderr at destroy
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::map<std::string, std::pair<double, uint64_t>> acc;
 };
+// launches one kernel of the step; in timing mode its device time is accumulated under `name`
+#define TRAIN_LAUNCH(name, ...)                                                                                        \
+    do {                                                                                                               \
+        if (t->timing) cudaEventRecord(t->ev0, st);                                                                    \
+        __VA_ARGS__;                                                                                                   \
+        if (t->timing) {                                                                                               \
+            cudaEventRecord(t->ev1, st); cudaEventSynchronize(t->ev1);                                                 \
+            float ms = 0; cudaEventElapsedTime(&ms, t->ev0, t->ev1);                                                   \
+            auto &a = t->acc[name]; a.first += ms; a.second += 1;                                                      \
+        }                                                                                                              \
+    } while (0)
 static constexpr uint32_t kStepsPerGraph = 32;
 
 static uint64_t choose_table_cap(const swt_bpe_train_config *cfg) {
@@ -717,6 +845,9 @@ static size_t train_layout(const swt_bpe_train_config *cfg, void *base, TrainDev
     d->mark_group = std::min<uint32_t>(kMarkGroup, std::max<uint32_t>(1u, d->n_chunks / (2 * kNumSMs)));      // small corpora: one chunk per CTA
     d->word_of = cv.take<uint32_t>(d->n_slots + 1);
     d->start = cv.take<uint32_t>(d->n_types + 1);
+    d->sym2 = cv.take<uint32_t>(d->n_slots + 8);
+    d->word_of2 = cv.take<uint32_t>(d->n_slots + 1);
+    d->start2 = cv.take<uint32_t>(d->n_types + 1);
     d->word_mark = cv.take<uint32_t>(d->n_types + 1);
     d->worklist = cv.take<uint32_t>(d->n_types + 1);
     d->freq = cv.take<long long>(d->n_types + 1);
@@ -763,6 +894,9 @@ SWT_API int swt_bpe_train_create(const swt_bpe_train_config *cfg, const uint32_t
     SWT_CUDA_OK(cudaGetDevice(&device));
     swt_bpe_trainer *t = new swt_bpe_trainer();
     t->cfg = *cfg; t->device = device; t->table_cap = choose_table_cap(cfg);
+    t->d_off0 = d_off; t->n_slots0 = cfg->n_slots_local;
+    t->timing = g_train_timing != 0;
+    if (t->timing) { cudaEventCreate(&t->ev0); cudaEventCreate(&t->ev1); }
     size_t need = train_layout(cfg, d_workspace, &t->dev, t->table_cap);
     if (need > workspace_bytes) { delete t; set_error("train workspace too small"); return SWT_ERR_CAPACITY; }
     int sms = kNumSMs; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -792,6 +926,14 @@ SWT_API int swt_bpe_train_create(const swt_bpe_train_config *cfg, const uint32_t
 SWT_API void swt_bpe_train_destroy(swt_bpe_trainer *t) {
     if (!t) return;
     if (t->step_graph) cudaGraphExecDestroy(t->step_graph);
+    if (t->timing) {
+        double tot = 0;
+        for (auto &kv : t->acc) tot += kv.second.first;
+        for (auto &kv : t->acc)
+            fprintf(stderr, "[swt train timing] %-18s %9.3f ms total %8llu launches %8.2f us each %5.1f %%\n", kv.first.c_str(), kv.second.first,
+                    (unsigned long long)kv.second.second, 1e3 * kv.second.first / std::max<uint64_t>(kv.second.second, 1), 100 * kv.second.first / tot);
+        cudaEventDestroy(t->ev0); cudaEventDestroy(t->ev1);
+    }
     delete t;
 }
 
@@ -841,30 +983,30 @@ SWT_API int swt_bpe_train_select(swt_bpe_trainer *t, void *stream) {
     SWT_REQUIRE(t != nullptr, "NULL trainer");
     cudaStream_t st = (cudaStream_t)stream;
     if (t->cfg.mode == 1) {                       // WordPiece: scores move with the symbol frequencies -> full pass
-        k_wp_argmax_partial<<<t->dev.n_parts, 256, 0, st>>>(t->dev);
-        k_wp_select<<<1, 256, 0, st>>>(t->dev);
+        TRAIN_LAUNCH("wp_argmax", k_wp_argmax_partial<<<t->dev.n_parts, 256, 0, st>>>(t->dev));
+        TRAIN_LAUNCH("wp_select", k_wp_select<<<1, 256, 0, st>>>(t->dev));
     } else {
         if (t->table_cap <= (1ull << 20)) {       // small table: plain parallel pass
-            k_argmax_full<<<t->dev.n_parts, 256, 0, st>>>(t->dev);
-            k_select<<<1, 1024, 0, st>>>(t->dev, 1);
+            TRAIN_LAUNCH("argmax_full", k_argmax_full<<<t->dev.n_parts, 256, 0, st>>>(t->dev));
+            TRAIN_LAUNCH("select", k_select<<<1, 1024, 0, st>>>(t->dev, 1));
         } else {                                  // large table: refresh only the blocks (then groups) the last merge touched
-            k_argmax_blocks<<<kNumSMs, 256, 0, st>>>(t->dev);
-            k_argmax_groups<<<32, 256, 0, st>>>(t->dev);
-            k_select<<<1, 1024, 0, st>>>(t->dev, 0);
+            TRAIN_LAUNCH("argmax_blocks", k_argmax_blocks<<<kNumSMs, 256, 0, st>>>(t->dev));
+            TRAIN_LAUNCH("argmax_groups", k_argmax_groups<<<32, 256, 0, st>>>(t->dev));
+            TRAIN_LAUNCH("select", k_select<<<1, 1024, 0, st>>>(t->dev, 0));
         }
     }
-    if (t->dev.n_slots) k_tie_scan<<<t->grid_scan / 2, 256, 0, st>>>(t->dev);
-    k_candidate<<<1, 1, 0, st>>>(t->dev);
+    if (t->dev.n_slots) TRAIN_LAUNCH("tie_scan", k_tie_scan<<<t->grid_scan / 2, 256, 0, st>>>(t->dev));
+    TRAIN_LAUNCH("candidate", k_candidate<<<1, 1, 0, st>>>(t->dev));
     SWT_CUDA_OK(cudaGetLastError());
     return SWT_OK;
 }
 SWT_API int swt_bpe_train_merge(swt_bpe_trainer *t, void *stream) {
     SWT_REQUIRE(t != nullptr, "NULL trainer");
     cudaStream_t st = (cudaStream_t)stream;
-    k_begin_merge<<<1, 32, 0, st>>>(t->dev);
+    TRAIN_LAUNCH("begin_merge", k_begin_merge<<<1, 32, 0, st>>>(t->dev));
     if (t->dev.n_slots) {
-        k_mark<<<(int)std::min<uint32_t>((uint32_t)t->grid_scan, (t->dev.n_chunks + t->dev.mark_group - 1) / t->dev.mark_group), 256, 0, st>>>(t->dev);
-        k_apply<<<t->grid_scan / 2, 128, 0, st>>>(t->dev);
+        TRAIN_LAUNCH("mark", k_mark<<<(int)std::min<uint32_t>((uint32_t)t->grid_scan, (t->dev.n_chunks + t->dev.mark_group - 1) / t->dev.mark_group), 256, 0, st>>>(t->dev));
+        TRAIN_LAUNCH("apply", k_apply<<<t->grid_scan / 2, 128, 0, st>>>(t->dev));
     }
     SWT_CUDA_OK(cudaGetLastError());
     return SWT_OK;
@@ -872,7 +1014,8 @@ SWT_API int swt_bpe_train_merge(swt_bpe_trainer *t, void *stream) {
 SWT_API int swt_bpe_train_update(swt_bpe_trainer *t, void *stream) {
     SWT_REQUIRE(t != nullptr, "NULL trainer");
     const int blocks = t->cfg.world_size == 1 ? 32 : (int)std::min<uint64_t>((t->dev.vmax + 255) / 256, 4096);
-    k_update<<<blocks, 256, 0, (cudaStream_t)stream>>>(t->dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    TRAIN_LAUNCH("update", k_update<<<blocks, 256, 0, st>>>(t->dev));
     SWT_CUDA_OK(cudaGetLastError());
     return SWT_OK;
 }
@@ -888,7 +1031,7 @@ SWT_API int swt_bpe_train_steps(swt_bpe_trainer *t, uint32_t n_steps, void *stre
     cudaStream_t st = (cudaStream_t)stream;
     // The step is launch-bound on small corpora (9 short kernels), so kStepsPerGraph steps are captured into one CUDA
     // graph and replayed; every kernel is self-gating on the halt flag, so replaying past the end is harmless.
-    if (!t->step_graph && n_steps >= kStepsPerGraph && st != nullptr) {
+    if (!t->step_graph && n_steps >= kStepsPerGraph && st != nullptr && !t->timing) {
         cudaGraph_t g = nullptr;
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             int rc = SWT_OK;
@@ -951,17 +1094,59 @@ SWT_API int swt_bpe_train_grow_table(swt_bpe_trainer *t, void *d_new_table, uint
     return SWT_OK;
 }
 
+SWT_API int swt_bpe_train_maintain(swt_bpe_trainer *t, uint64_t n_live_slots, int *kernels_changed, void *stream) {
+    SWT_REQUIRE(t != nullptr, "NULL trainer");
+    cudaStream_t st = (cudaStream_t)stream;
+    TrainDev &d = t->dev;
+    if (kernels_changed) *kernels_changed = 0;
+    if (d.n_slots == 0) return SWT_OK;
+    if (n_live_slots * 10 <= d.n_slots * 6 && d.n_slots >= (1u << 16)) {
+        // ---- compaction: live length per type -> exclusive scan -> copy into the second buffers -> swap
+        uint32_t *len = d.worklist;                                  // free between steps
+        k_word_len<<<t->grid_scan, 256, 0, st>>>(d, len);
+        size_t tmp_bytes = 0;
+        SWT_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, len, d.start2, (int)d.n_types, st));
+        void *tmp = nullptr;
+        SWT_CUDA_OK(cudaMalloc(&tmp, tmp_bytes + 16));
+        cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, len, d.start2, (int)d.n_types, st);
+        uint32_t last[2] = {0, 0};
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&last[0], d.start2 + d.n_types - 1, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&last[1], len + d.n_types - 1, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(tmp);
+        if (e != cudaSuccess) { set_error(std::string("compaction scan: ") + cudaGetErrorString(e)); return SWT_ERR_CUDA; }
+        const uint32_t n_new = last[0] + last[1];
+        k_compact_words<<<t->grid_scan, 256, 0, st>>>(d, len, n_new);
+        std::swap(d.sym, d.sym2); std::swap(d.word_of, d.word_of2); std::swap(d.start, d.start2);
+        d.n_slots = n_new;
+        d.n_chunks = (uint32_t)((d.n_slots + (1ull << kChunkShift) - 1) >> kChunkShift);
+        d.mark_group = std::min<uint32_t>(kMarkGroup, std::max<uint32_t>(1u, d.n_chunks / (2 * kNumSMs)));
+        t->n_compactions += 1;
+        if (t->step_graph) { cudaGraphExecDestroy(t->step_graph); t->step_graph = nullptr; }     // the captured kernels hold the old extents
+        if (kernels_changed) *kernels_changed = 1;
+    }
+    // ---- pair filter rebuilt from the live pairs (stale bits of merged-away pairs cost chunk scans)
+    SWT_CUDA_OK(cudaMemsetAsync(d.filt, 0, ((size_t)d.n_chunks * (kFiltBits / 32) + 1) * 4, st));
+    k_build_filter<<<t->grid_scan, 256, 0, st>>>(d);
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}
+
 SWT_API int swt_bpe_train_read_corpus(swt_bpe_trainer *t, uint32_t *h_syms, uint32_t *h_len, void *stream) {
     SWT_REQUIRE(t && h_syms && h_len, "NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t n = t->dev.n_slots, nt = t->dev.n_types;
-    std::vector<uint32_t> start(nt + 1);
-    SWT_CUDA_OK(cudaMemcpyAsync(h_syms, t->dev.sym, n * 4, cudaMemcpyDeviceToHost, st));
+    // h_syms keeps the CALLER's layout (type w at its original offset) although the device table may have been compacted
+    std::vector<uint32_t> start(nt + 1), cur(n + 1);
+    std::vector<uint64_t> off0(nt + 1);
+    SWT_CUDA_OK(cudaMemcpyAsync(cur.data(), t->dev.sym, n * 4, cudaMemcpyDeviceToHost, st));
     SWT_CUDA_OK(cudaMemcpyAsync(start.data(), t->dev.start, (nt + 1) * 4, cudaMemcpyDeviceToHost, st));
+    if (nt) SWT_CUDA_OK(cudaMemcpyAsync(off0.data(), t->d_off0, (nt + 1) * 8, cudaMemcpyDeviceToHost, st));
     SWT_CUDA_OK(cudaStreamSynchronize(st));
     for (uint64_t w = 0; w < nt; ++w) {
         uint32_t len = 0;
-        for (uint32_t i = start[w]; i < start[w + 1] && h_syms[i] != kHole; ++i) { h_syms[i] &= ~kStart; ++len; }
+        const uint64_t o = off0[w] - off0[0];
+        for (uint32_t i = start[w]; i < start[w + 1] && cur[i] != kHole; ++i) { h_syms[o + len] = cur[i] & ~kStart; ++len; }
         h_len[w] = len;
     }
     return SWT_OK;

@@ -589,8 +589,14 @@ class CudaTrainEngine:
         state = {f[0]: getattr(st, f[0]) for f in TrainState._fields_}
         return state, self._rec[0][:n].copy(), self._rec[1][:n].copy(), self._rec[2][:n].copy(), self._rec[3][:n].copy()
 
+    def maintain(self, n_live_slots: int) -> bool:
+        """Filter rebuild / word-table compaction between batches of steps; True when captured graphs must be re-captured."""
+        changed = ctypes.c_int(0)
+        check(self.lib.swt_bpe_train_maintain(self.handle, int(n_live_slots), ctypes.byref(changed), self._sp()), "swt_bpe_train_maintain")
+        return bool(changed.value)
+
     def grow_table(self, cur_cap: int):
-        new_cap = cur_cap * 4
+        new_cap = cur_cap * 2
         buf = torch.empty(self.lib.swt_bpe_train_table_bytes(new_cap), dtype=torch.uint8, device=self.dev)
         self._tables.append(buf)                       # keep alive; older tables are released after the rehash ran
         check(self.lib.swt_bpe_train_grow_table(self.handle, buf.data_ptr(), new_cap, self._sp()))
@@ -690,11 +696,15 @@ def _training_loop(engine, world_size, group, steps_per_sync, progress, dist):
         halt = state["halt"]
         if halt in (HALT_DONE_VOCAB, HALT_DONE_NOPAIRS):
             break
+        recapture = False
         if halt == HALT_GROW:
             engine.grow_table(state["table_cap"])
-            if graph is not None:                                    # the captured kernels hold the old table pointer
-                graph = _capture_steps(engine, group, dist)
+            recapture = True                                         # the captured kernels hold the old table pointer
         elif halt >= 16:
             raise SwtError("BPE trainer halted with device error %d" % halt)
+        if hasattr(engine, "maintain"):
+            recapture = engine.maintain(state["n_live_slots"]) or recapture
+        if recapture and graph is not None:
+            graph = _capture_steps(engine, group, dist)
     cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dtype=dt)
     return cat(lefts, np.uint32), cat(rights, np.uint32), cat(news, np.uint32), cat(counts, np.int64), state

@@ -238,6 +238,40 @@ def test_training_with_an_alphabet_beyond_4096_symbols(P, dev):
     assert state["vocab_size"] == ovs
 
 
+def test_training_large_table_paths_ties_filter_compaction(P, dev):
+    """The paths only big corpora take, forced on a small one: two-level argmax cache + listed tie keys (table_cap 2^21), the pair
+    filter of the mark scan, its rebuild and the word-table compaction (maintenance every 32 steps).  Heavy ties: all types have
+    frequency 1 or 2.  Merge list, chosen counts and the final segmentation equal the oracle's / a replay."""
+    import oracle
+    rng = np.random.default_rng(41)
+    alphabet = list("abcdefghijklmnopqrstuvwxyz")
+    words = ["".join(rng.choice(alphabet, size=int(rng.integers(2, 14)))) for _ in range(24_000)]
+    words += words[:3000]                                            # frequency 2 for the first types
+    tt = P.TrainTypes(words)
+    max_len = int(np.diff(tt.off.astype(np.int64)).max())
+    max_vocab = 26 + 1500
+    eng = dev.CudaTrainEngine(tt.syms, tt.off, tt.freq, tt.n_alpha, max_vocab, tt.n_alpha, max_len, 0, 0, 1, record_cap=64, table_cap=1 << 21)
+    l, r, n, c, state = dev.run_training_loop(eng, 1, steps_per_sync=32)
+    ol, orr, on, oc, ovs = oracle.bpe_train(tt.syms, tt.off, tt.freq, tt.n_alpha, max_vocab)
+    assert len(l) == len(ol) == 1500
+    assert np.array_equal(c, oc) and np.array_equal(l, ol) and np.array_equal(r, orr) and np.array_equal(n, on)
+    assert state["n_tie_steps"] > 500
+    merges, strs = tt.merges_to_strs(l, r, n)
+    syms, lens = eng.read_corpus()
+    for k in range(0, tt.n_types, 211):
+        word = list(tt.types[k])
+        for a, b in merges:
+            out, i = [], 0
+            while i < len(word):
+                if i + 1 < len(word) and word[i] == a and word[i + 1] == b:
+                    out.append(a + b); i += 2
+                else:
+                    out.append(word[i]); i += 1
+            word = out
+        s0 = int(tt.off[k])
+        assert [strs[j] for j in syms[s0:s0 + int(lens[k])]] == word
+
+
 def test_empty_corpus_and_live_container_tracking(hf_tokenizer):
     from subword_tokenizers_b200 import FastBPE, FastWP, NaiveBPE, NaiveWP
     for cls in (NaiveBPE, FastBPE, NaiveWP, FastWP):
