@@ -303,6 +303,7 @@ typedef struct swt_bpe_train_state {
     uint64_t table_cap;
     uint64_t n_live_slots;     /* live symbols on this rank */
     uint64_t n_tie_steps;      /* steps in which several pairs attained the maximum (first-occurrence scan) */
+    uint64_t n_tie_listed;     /* ... of which the tied pairs were few enough to be listed (filtered scan, no table probes) */
 } swt_bpe_train_state;
 
 size_t swt_bpe_train_workspace_bytes(const swt_bpe_train_config *cfg);

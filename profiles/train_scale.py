@@ -55,7 +55,7 @@ def main():
     h = hashlib.sha256(np.stack([l, r, n]).tobytes() + c.tobytes()).hexdigest()
     out = {"n_gpus": world, "n_types": args.types, "n_symbols": int(off[-1]), "n_alpha": n_alpha, "max_vocab": args.max_vocab,
            "merges": int(len(l)), "seconds": dt, "merges_per_s": len(l) / dt, "us_per_step": 1e6 * dt / max(1, len(l)), "vocab_size": int(state["vocab_size"]),
-           "table_entries": int(state["n_table_entries"]), "table_cap": int(state["table_cap"]), "tie_steps": int(state["n_tie_steps"]),
+           "table_entries": int(state["n_table_entries"]), "table_cap": int(state["table_cap"]), "tie_steps": int(state["n_tie_steps"]), "tie_steps_listed": int(state["n_tie_listed"]),
            "live_slots_rank0": int(state["n_live_slots"]), "merges_sha256": h, "gen_seconds": t_gen, "halt": int(state["halt"]),
            "exchange": getattr(eng, "exchange_kind", "none")}
     if args.check_oracle_steps and rank == 0:

@@ -39,6 +39,7 @@ class TrainState(ctypes.Structure):
         ("halt", ctypes.c_uint32), ("n_recorded", ctypes.c_uint32), ("n_merges_total", ctypes.c_uint64),
         ("vocab_size", ctypes.c_int64), ("n_symbols", ctypes.c_uint64), ("n_table_entries", ctypes.c_uint64),
         ("table_cap", ctypes.c_uint64), ("n_live_slots", ctypes.c_uint64), ("n_tie_steps", ctypes.c_uint64),
+        ("n_tie_listed", ctypes.c_uint64),
     ]
 
 

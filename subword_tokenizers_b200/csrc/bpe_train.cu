@@ -62,7 +62,7 @@ struct TrainState {                 // device resident, mutable
     uint32_t n_dirty, n_touch_l, n_touch_r, n_gdirty;   // lengths of the dirty-block / dirty-group lists and of the touched-symbol lists
     double best_score;                              // WordPiece mode: the maximal score of this step
     uint64_t n_tie_steps;                           // steps whose maximum was attained by several pairs (first-occurrence scan needed)
-    uint32_t n_tie_keys, pad1;                      // the tied pairs themselves when there are at most kTieKeys of them (else 0)
+    uint32_t n_tie_keys, n_tie_listed;              // the tied pairs themselves when there are at most kTieKeys of them (else 0); listed steps
     uint64_t tie_keys[32];
 };
 constexpr uint32_t kTieKeys = 32;
@@ -170,7 +170,7 @@ __global__ void k_init_symbols(TrainDev d, long long initial_vocab) {
         TrainState *st = d.st;
         st->halt = kRun; st->n_recorded = 0; st->n_merges_total = 0; st->vocab_size = initial_vocab;
         st->n_symbols = d.n_alpha; st->n_entries = 0; st->n_live = d.n_slots; st->step_stamp = 0;
-        st->n_tie_steps = 0;
+        st->n_tie_steps = 0; st->n_tie_listed = 0;
         st->char_used = d.n_alpha; st->cur_valid = 0; st->worklist_n = 0; st->n_dirty = 0; st->n_gdirty = 0; st->n_touch_l = 0; st->n_touch_r = 0;
     }
 }
@@ -255,6 +255,16 @@ __global__ void k_build_filter(TrainDev d) {
     }
 }
 
+// single rank: the delta vectors of the previous step are cleared through its touched-symbol lists (k_update reads every delta from
+// two threads, so it cannot clear them itself); called by every thread of the select kernel before the lists are reset
+__device__ __forceinline__ void clear_touched_deltas(const TrainDev &d, const TrainState *st) {
+    if (d.world != 1) return;
+    long long *L = d.delta, *R = d.delta + d.vmax;
+    const uint32_t nl = st->n_touch_l, nr = st->n_touch_r;
+    for (uint32_t i = threadIdx.x; i < nl; i += blockDim.x) L[d.touch_l[i]] = 0;
+    for (uint32_t i = threadIdx.x; i < nr; i += blockDim.x) R[d.touch_r[i]] = 0;
+}
+
 // ---- WordPiece mode (NaiveWP.train, reference source/wordpiece.py:29-103) -----------------------------------------------
 // Same word table, pair table, mark / apply / update as BPE.  What differs: the initial symbols are strings ("a", "##a",
 // wordpiece.py:53-57), the merged token is a + b[2:] (:95), and the pair chosen at every step maximises
@@ -314,6 +324,7 @@ __global__ void __launch_bounds__(256) k_wp_argmax_partial(TrainDev d) {
 __global__ void __launch_bounds__(256) k_wp_select(TrainDev d) {
     TrainState *st = d.st;
     if (st->halt) return;
+    clear_touched_deltas(d, st);
     double c = 0.0; uint64_t k = kEmptyKey; uint32_t n = 0;
     for (uint32_t i = threadIdx.x; i < d.n_parts; i += blockDim.x) { ArgPart p = d.parts[i]; score_combine(c, k, n, __longlong_as_double(p.count), p.key, p.n_tied); }
     for (int o = 16; o > 0; o >>= 1) {
@@ -393,6 +404,7 @@ __global__ void __launch_bounds__(256) k_argmax_groups(TrainDev d) {
 __global__ void __launch_bounds__(1024) k_select(TrainDev d, int from_parts) {
     TrainState *st = d.st;
     if (st->halt) return;
+    clear_touched_deltas(d, st);
     long long c = 0; uint64_t k = kEmptyKey; uint32_t n = 0;
     // reduce either the per-CTA partials of k_argmax_full or the group level of the cache (k_argmax_blocks / k_argmax_groups)
     const ArgPart *src = from_parts ? d.parts : d.grp;
@@ -424,16 +436,28 @@ __global__ void __launch_bounds__(1024) k_select(TrainDev d, int from_parts) {
     // A tie among a few pairs: list them (the blocks whose cached maximum equals the maximum hold them), so that the first-occurrence
     // scan can use the pair filter and compare keys instead of probing the table at every position.
     if (sn[0]) {
+        // groups whose cached maximum is the maximum -> their blocks -> their slots: three short parallel phases
         const long long cmax = sc[0];
         const uint32_t n_blk = (uint32_t)(st->table_cap >> kBlkShift);
-        for (uint32_t b = threadIdx.x; b < n_blk; b += blockDim.x) {
-            if (d.blk[b].count != cmax) continue;
-            const PairEntry *base = d.table + ((uint64_t)b << kBlkShift);
-            for (uint32_t i = 0; i < (1u << kBlkShift); ++i) {
-                const PairEntry e = base[i];
-                if (e.key != kEmptyKey && e.count == cmax) { const uint32_t q = atomicAdd(&st->n_tie_keys, 1u); if (q < kTieKeys) st->tie_keys[q] = e.key; }
-            }
+        __shared__ uint32_t s_grp[64], s_blk[64], s_ng, s_nb;
+        if (threadIdx.x == 0) { s_ng = 0; s_nb = 0; }
+        __syncthreads();
+        for (uint32_t g = threadIdx.x; g < n_src; g += blockDim.x)
+            if (d.grp[g].count == cmax) { const uint32_t q = atomicAdd(&s_ng, 1u); if (q < 64) s_grp[q] = g; }
+        __syncthreads();
+        const uint32_t ng = min(s_ng, 64u);
+        for (uint32_t w = threadIdx.x; w < ng << kGrpShift; w += blockDim.x) {
+            const uint32_t b = (s_grp[w >> kGrpShift] << kGrpShift) + (w & ((1u << kGrpShift) - 1u));
+            if (b < n_blk && d.blk[b].count == cmax) { const uint32_t q = atomicAdd(&s_nb, 1u); if (q < 64) s_blk[q] = b; }
         }
+        __syncthreads();
+        const uint32_t nb = min(s_nb, 64u);
+        for (uint32_t w = threadIdx.x; w < nb << kBlkShift; w += blockDim.x) {
+            const PairEntry e = d.table[((uint64_t)s_blk[w >> kBlkShift] << kBlkShift) + (w & ((1u << kBlkShift) - 1u))];
+            if (e.key != kEmptyKey && e.count == cmax) { const uint32_t q = atomicAdd(&st->n_tie_keys, 1u); if (q < kTieKeys) st->tie_keys[q] = e.key; }
+        }
+        // (more than 64 groups / blocks cannot happen with at most kTieKeys tied pairs; a short list simply fails the n_tie_keys == n_tied
+        // test of the scans and the table-probing scan runs instead)
     }
 }
 
@@ -475,62 +499,7 @@ __global__ void __launch_bounds__(256) k_tie_scan(TrainDev d) {
     const uint64_t cap = st->table_cap;
     __shared__ uint32_t s_chunk, s_stop;
     __shared__ unsigned long long s_best;
-    if (st->n_tie_keys == st->n_tied) {
-        // ---- the tied pairs are listed (k_select): groups of 64 filter chunks in ascending order; a chunk is read only when the
-        // filter admits one of the pairs, and positions are compared with the listed keys (no table probes)
-        __shared__ uint64_t s_keys[kTieKeys];
-        __shared__ uint32_t s_row[kTieKeys], s_mask[kTieKeys], s_list[64], s_flag[64], s_n;
-        const uint32_t nk = st->n_tie_keys;
-        if (threadIdx.x < nk) {
-            const uint64_t k = st->tie_keys[threadIdx.x];
-            const uint32_t bit = filt_bit(k);
-            s_keys[threadIdx.x] = k; s_row[threadIdx.x] = bit >> 5; s_mask[threadIdx.x] = 1u << (bit & 31u);
-        }
-        const uint64_t group_slots = 64ull << kChunkShift;
-        for (;;) {
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                s_chunk = atomicAdd(&st->tie_ticket, 1u); s_best = kNoPos; s_n = 0;
-                const uint64_t c = (uint64_t)s_chunk * group_slots;
-                s_stop = (c >= d.n_slots) || (*(volatile uint64_t *)&st->best_pos < d.slot_base + c);
-            }
-            __syncthreads();
-            if (s_stop) break;
-            if (threadIdx.x < 64) {                                                          // one chunk per thread: any key's bit set?
-                const uint32_t chunk = s_chunk * 64 + threadIdx.x;
-                bool f = false;
-                if (chunk < d.n_chunks) for (uint32_t k = 0; k < nk && !f; ++k) f = (d.filt[(uint64_t)s_row[k] * d.n_chunks + chunk] & s_mask[k]) != 0;
-                s_flag[threadIdx.x] = f ? 1u : 0u;
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {                                                          // ascending list of the flagged chunks
-                uint32_t n = 0;
-                for (uint32_t q = 0; q < 64; ++q) if (s_flag[q]) s_list[n++] = s_chunk * 64 + q;
-                s_n = n;
-            }
-            __syncthreads();
-            const uint32_t n_list = s_n;
-            for (uint32_t q = 0; q < n_list; ++q) {
-                const uint64_t c0 = (uint64_t)s_list[q] << kChunkShift;
-                if (s_best != kNoPos) break;                                                 // an earlier chunk of this group already matched
-                uint64_t mine = kNoPos;
-                for (uint32_t it = 0; it < (1u << kChunkShift) / 256 && mine == kNoPos; ++it) {
-                    const uint64_t i = c0 + (uint64_t)it * 256 + threadIdx.x;
-                    if (i + 1 < d.n_slots) {
-                        const uint32_t sy = d.sym[i], nx = d.sym[i + 1];
-                        if (sy != kHole && !(nx & kStart)) {
-                            const uint64_t key = ((uint64_t)(sy & ~kStart) << 32) | nx;
-                            for (uint32_t k = 0; k < nk; ++k) if (s_keys[k] == key) mine = i;
-                        }
-                    }
-                }
-                if (mine != kNoPos) atomicMin(&s_best, (unsigned long long)mine);
-                __syncthreads();
-            }
-            if (threadIdx.x == 0 && s_best != kNoPos) atomicMin((unsigned long long *)&st->best_pos, (unsigned long long)(d.slot_base + s_best));
-        }
-        return;
-    }
+    if (st->n_tie_keys == st->n_tied) return;                       // handled by k_tie_scan_listed
     for (;;) {
         if (threadIdx.x == 0) {
             s_chunk = atomicAdd(&st->tie_ticket, 1u); s_best = kNoPos;
@@ -556,11 +525,80 @@ __global__ void __launch_bounds__(256) k_tie_scan(TrainDev d) {
         __syncthreads();
     }
 }
+// The tied pairs are listed (k_select found at most kTieKeys of them): groups of 64 filter chunks in ascending order; a chunk is
+// read only when the pair filter admits one of the pairs, and positions are compared with the listed keys (no table probes).
+__global__ void __launch_bounds__(256) k_tie_scan_listed(TrainDev d) {
+    TrainState *st = d.st;
+    if (st->halt || st->n_tied <= 1 || st->n_tie_keys != st->n_tied) return;
+    __shared__ uint32_t s_chunk, s_stop;
+    __shared__ unsigned long long s_best;
+    {
+        // ---- the tied pairs are listed (k_select): groups of 64 filter chunks in ascending order; a chunk is read only when the
+        // filter admits one of the pairs, and positions are compared with the listed keys (no table probes)
+        __shared__ uint64_t s_keys[kTieKeys];
+        __shared__ uint32_t s_row[kTieKeys], s_mask[kTieKeys], s_list[64], s_flag[64], s_n;
+        const uint32_t nk = st->n_tie_keys;
+        if (threadIdx.x < nk) {
+            const uint64_t k = st->tie_keys[threadIdx.x];
+            const uint32_t bit = filt_bit(k);
+            s_keys[threadIdx.x] = k; s_row[threadIdx.x] = bit >> 5; s_mask[threadIdx.x] = 1u << (bit & 31u);
+        }
+        constexpr uint32_t kTieGroup = 8;                                                    // chunks per ticket: all CTAs busy at once
+        const uint64_t group_slots = (uint64_t)kTieGroup << kChunkShift;
+        const uint32_t lane = threadIdx.x & 31;
+        for (;;) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_chunk = atomicAdd(&st->tie_ticket, 1u); s_best = kNoPos; s_n = 0;
+                const uint64_t c = (uint64_t)s_chunk * group_slots;
+                s_stop = (c >= d.n_slots) || (*(volatile uint64_t *)&st->best_pos < d.slot_base + c);
+            }
+            __syncthreads();
+            if (s_stop) break;
+            if (threadIdx.x < kTieGroup) {                                                   // one chunk per thread: any key's bit set?
+                const uint32_t chunk = s_chunk * kTieGroup + threadIdx.x;
+                bool f = false;
+                if (chunk < d.n_chunks) for (uint32_t k = 0; k < nk && !f; ++k) f = (d.filt[(uint64_t)s_row[k] * d.n_chunks + chunk] & s_mask[k]) != 0;
+                s_flag[threadIdx.x] = f ? 1u : 0u;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {                                                          // ascending list of the flagged chunks
+                uint32_t n = 0;
+                for (uint32_t q = 0; q < kTieGroup; ++q) if (s_flag[q]) s_list[n++] = s_chunk * kTieGroup + q;
+                s_n = n;
+            }
+            __syncthreads();
+            const uint32_t n_list = s_n;
+            uint64_t mine = kNoPos;
+            for (uint32_t q = 0; q < n_list; ++q) {
+                const uint64_t c0 = (uint64_t)s_list[q] << kChunkShift;
+#pragma unroll
+                for (uint32_t it = 0; it < (1u << kChunkShift) / (256 * 4); ++it) {           // 4 slots per thread, 128-bit loads, all in flight
+                    const uint64_t i = c0 + ((uint64_t)it * 256 + threadIdx.x) * 4;
+                    uint4 v = make_uint4(kHole, kHole, kHole, kHole);
+                    if (i < d.n_slots) v = *reinterpret_cast<const uint4 *>(d.sym + i);      // sym[] is padded with dead slots
+                    uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x, 1);
+                    if (lane == 31) nxt = (i + 4 < d.n_slots) ? d.sym[i + 4] : kHole;
+                    const uint32_t sy[5] = {v.x, v.y, v.z, v.w, nxt};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (sy[j] == kHole || (sy[j + 1] & kStart)) continue;
+                        const uint64_t key = ((uint64_t)(sy[j] & ~kStart) << 32) | sy[j + 1];
+                        for (uint32_t k = 0; k < nk; ++k) if (s_keys[k] == key) mine = min(mine, i + j);
+                    }
+                }
+            }
+            if (mine != kNoPos) atomicMin(&s_best, (unsigned long long)mine);
+            __syncthreads();
+            if (threadIdx.x == 0 && s_best != kNoPos) atomicMin((unsigned long long *)&st->best_pos, (unsigned long long)(d.slot_base + s_best));
+        }
+    }
+}
 __global__ void k_candidate(TrainDev d) {
     TrainState *st = d.st;
     uint64_t pos = kNoPos, key = kEmptyKey;
     if (!st->halt) {
-        if (st->n_tied > 1) st->n_tie_steps += 1;
+        if (st->n_tied > 1) { st->n_tie_steps += 1; if (st->n_tie_keys == st->n_tied) st->n_tie_listed += 1; }
         if (st->n_tied <= 1) key = st->cand_key;
         else if (st->best_pos != kNoPos) {
             pos = st->best_pos;
@@ -728,16 +766,18 @@ __global__ void __launch_bounds__(256) k_update(TrainDev d) {
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     if (d.world == 1) {
         // single rank: only the symbols whose delta became non-zero (listed by k_apply) have to be visited
+        // one table update per thread (the -delta and the +delta of an entry are independent chains of random accesses);
+        // L / R are cleared by k_clear_deltas afterwards
         const uint32_t nl = st->n_touch_l, nr = st->n_touch_r;
-        for (uint32_t i = gtid; i < nl; i += gsz) {
-            const uint64_t x = d.touch_l[i]; const long long l = L[x];
-            table_add(d.table, cap, (x << 32) | a, -l, st, d.dl()); table_add(d.table, cap, (x << 32) | z, l, st, d.dl());
-            L[x] = 0;
-        }
-        for (uint32_t i = gtid; i < nr; i += gsz) {
-            const uint64_t y = d.touch_r[i]; const long long r = R[y];
-            table_add(d.table, cap, (b << 32) | y, -r, st, d.dl()); table_add(d.table, cap, (z << 32) | y, r, st, d.dl());
-            R[y] = 0;
+        for (uint32_t i = gtid; i < 2 * (nl + nr); i += gsz) {
+            const uint32_t e = i >> 1; const bool plus = i & 1u;
+            if (e < nl) {
+                const uint64_t x = d.touch_l[e]; const long long l = L[x];
+                table_add(d.table, cap, (x << 32) | (plus ? z : a), plus ? l : -l, st, d.dl());
+            } else {
+                const uint64_t y = d.touch_r[e - nl]; const long long r = R[y];
+                table_add(d.table, cap, ((plus ? z : b) << 32) | y, plus ? r : -r, st, d.dl());
+            }
         }
     } else {
         // sharded: the deltas were summed over ranks, the lists are rank-local -> visit every symbol
@@ -995,7 +1035,10 @@ SWT_API int swt_bpe_train_select(swt_bpe_trainer *t, void *stream) {
             TRAIN_LAUNCH("select", k_select<<<1, 1024, 0, st>>>(t->dev, 0));
         }
     }
-    if (t->dev.n_slots) TRAIN_LAUNCH("tie_scan", k_tie_scan<<<t->grid_scan / 2, 256, 0, st>>>(t->dev));
+    if (t->dev.n_slots) {
+        TRAIN_LAUNCH("tie_scan_listed", k_tie_scan_listed<<<t->grid_scan / 2, 256, 0, st>>>(t->dev));
+        TRAIN_LAUNCH("tie_scan", k_tie_scan<<<t->grid_scan / 2, 256, 0, st>>>(t->dev));
+    }
     TRAIN_LAUNCH("candidate", k_candidate<<<1, 1, 0, st>>>(t->dev));
     SWT_CUDA_OK(cudaGetLastError());
     return SWT_OK;
@@ -1071,7 +1114,7 @@ SWT_API int swt_bpe_train_read(swt_bpe_trainer *t, uint32_t *h_left, uint32_t *h
     SWT_CUDA_OK(cudaStreamSynchronize(st));
     state->halt = hs.halt; state->n_recorded = n; state->n_merges_total = hs.n_merges_total; state->vocab_size = hs.vocab_size;
     state->n_symbols = hs.n_symbols; state->n_table_entries = hs.n_entries; state->table_cap = hs.table_cap; state->n_live_slots = hs.n_live;
-    state->n_tie_steps = hs.n_tie_steps;
+    state->n_tie_steps = hs.n_tie_steps; state->n_tie_listed = hs.n_tie_listed;
     return SWT_OK;
 }
 
