@@ -55,8 +55,9 @@ enum { kStatusCode = 0, kStatusTokens = 1, kStatusH6 = 2, kStatusTokensHi = 3, k
 
 // Word-type memo, structure of arrays (one slot index addresses all three):
 //   keys[slot]   16 B  the CAS key: word bytes 0..7 | bytes 8..14, bits 56-59 = length (0 for words > 15 bytes), bits 60-63 = "pub":
-//                      0 = claimed, not published; 1..14 = n_tokens + 1 and ids16[slot] is valid; 15 = published in ext[slot]
-//                      (ids that do not fit 16 bits, more than 13 tokens, H6 events, or "not cacheable").  The ONLY array a call clears.
+//                      0 = claimed, not published; 1..13 = n_tokens and ids16[slot] is valid; 14 = ids16[slot] valid with 14..16
+//                      tokens (count in ext[slot].meta); 15 = published in ext[slot] (ids that do not fit 16 bits, more than 16
+//                      tokens, H6 events, or "not cacheable").  The ONLY array a call clears.
 //   ids16[slot]  32 B  up to 16 ids as 16-bit values (Enc::narrow16 / Enc::expand16), read by the emit pass
 //   ext[slot]    32 B  tail of words of 16..32 bytes (compared on every hit, so a hit is exact), meta and the position of the 32-bit
 //                      id list in the tok32 arena (bump allocated)
@@ -74,7 +75,8 @@ constexpr uint32_t kMemoSlotBits = 23, kMemoSlotMask = (1u << kMemoSlotBits) - 1
 static_assert(sizeof(MemoExt) == 32, "MemoExt must be 32 bytes");
 constexpr unsigned long long kPubMask = 0xFull << 60;
 constexpr uint32_t kPubExt = 15;          // pub nibble: look in ext[slot]
-constexpr uint32_t kNarrowMaxTokens = 13; // pub nibble 1..14
+constexpr uint32_t kPubWide = 14;         // pub nibble: ids16[slot] valid, 14..16 tokens (the count is in ext[slot].meta unless the length pins it)
+constexpr uint32_t kNarrowMaxTokens = 16; // pub nibble 1..13 = n_tokens (a memoised word has at least one token), 14 = kPubWide
 
 struct MemoKey { unsigned long long lo, hi, tail_a, tail_b; uint32_t tail_last; uint32_t nbytes; };
 
@@ -204,7 +206,7 @@ __device__ __forceinline__ uint32_t memo_hash(unsigned long long lo, unsigned lo
 // kMemoClaimed: this thread now owns `slot` and must call memo_publish after encoding.  kMemoPending: another thread owns the
 // slot of exactly this word (words of up to 15 bytes: the key is the whole word) and will have published it by the time the
 // emit pass runs -- encode for the count, but let the emit pass read the ids from `slot`.  kMemoMiss: encode directly, publish nothing.
-static __device__ __noinline__ int memo_probe(const EncodeWorkspace &ws, const MemoKey &key, uint32_t &slot, uint32_t &meta_out, bool &narrow) {
+static __device__ __noinline__ int memo_probe(const EncodeWorkspace &ws, const MemoKey &key, uint32_t &slot, uint32_t &ntok_out, uint32_t &h6_out, bool &narrow) {
     uint32_t h = memo_hash(key.lo, key.hi) & ws.memo_mask;
     for (int probe = 0; probe < kMemoProbes; ++probe, h = (h + 1) & ws.memo_mask) {
         uint4 *e = ws.keys + h;
@@ -221,7 +223,8 @@ static __device__ __noinline__ int memo_probe(const EncodeWorkspace &ws, const M
             if (key.nbytes <= 15) { slot = h; return kMemoPending; }
             return kMemoMiss;                                             // long word: its tail is not comparable yet
         }
-        const uint4 x = ld_cg_u32x4(&ws.ext[h]);                          // meta, tail_last, tail_a
+        uint4 x = make_uint4(0, 0, 0, 0);
+        if (key.nbytes > 15 || pub >= kPubWide) x = ld_cg_u32x4(&ws.ext[h]);   // meta, tail_last, tail_a
         if (key.nbytes > 15) {                                            // same 15-byte prefix: check the rest and the length
             const unsigned long long ta = (unsigned long long)x.z | ((unsigned long long)x.w << 32);
             unsigned long long tb, dummy;
@@ -231,7 +234,8 @@ static __device__ __noinline__ int memo_probe(const EncodeWorkspace &ws, const M
         narrow = pub != kPubExt;
         if (!narrow && x.x == 0xFFFFFFFFu) return kMemoMiss;              // not cacheable
         slot = h;
-        meta_out = narrow ? pub : x.x;
+        ntok_out = pub < kPubWide ? pub : (x.x & 0xFFu) - 1u;
+        h6_out = narrow ? 0u : x.x >> 8;
         return kMemoHit;
     }
     return kMemoMiss;
@@ -247,7 +251,7 @@ constexpr uint32_t kGroupTiles = 1024;    // tiles per scan group
 
 template <class Enc>
 __device__ __forceinline__ bool ids_are_narrow(const uint32_t *buf, uint32_t ntok, uint32_t h6) {
-    bool nar = ntok <= kNarrowMaxTokens && h6 == 0;
+    bool nar = ntok >= 1 && ntok <= kNarrowMaxTokens && h6 == 0;
     uint32_t dummy;
     for (uint32_t k = 0; k < ntok && nar; ++k) nar = Enc::narrow16(buf[k], k, dummy);
     return nar;
@@ -261,13 +265,14 @@ __device__ __forceinline__ uint32_t memo_publish(const EncodeWorkspace &ws, uint
     MemoExt *x = ws.ext + slot;
     if (key.nbytes > 15) { x->tail_a = key.tail_a; x->tail_b = key.tail_b; x->tail_last = key.tail_last; }
     uint32_t pub, kind;
-    if (ids_are_narrow<Enc>(buf, ntok, h6)) {
-        uint32_t v[14];
+    if (ntok >= 1 && ids_are_narrow<Enc>(buf, ntok, h6)) {
+        uint32_t v[16];
 #pragma unroll
-        for (uint32_t k = 0; k < 14; ++k) { v[k] = 0; if (k < ntok) Enc::narrow16(buf[k], k, v[k]); }
+        for (uint32_t k = 0; k < 16; ++k) { v[k] = 0; if (k < ntok) Enc::narrow16(buf[k], k, v[k]); }
         ws.ids16[2 * (size_t)slot] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
-        if (ntok > 8) ws.ids16[2 * (size_t)slot + 1] = make_uint4(v[8] | (v[9] << 16), v[10] | (v[11] << 16), v[12] | (v[13] << 16), 0u);
-        pub = ntok + 1; kind = kWordHit16;
+        if (ntok > 8) ws.ids16[2 * (size_t)slot + 1] = make_uint4(v[8] | (v[9] << 16), v[10] | (v[11] << 16), v[12] | (v[13] << 16), v[14] | (v[15] << 16));
+        if (ntok >= kPubWide) { x->meta = ntok + 1; pub = kPubWide; } else pub = ntok;
+        kind = kWordHit16;
     } else {
         const unsigned long long off = ntok <= (uint32_t)kMemoTokens && h6 <= 0xFFFFFFu ? atomicAdd(ws.long_cursor + 1, (unsigned long long)ntok) : ~0ull;
         if (off != ~0ull && off + ntok <= ws.tok32_cap) {
@@ -291,11 +296,10 @@ __device__ __noinline__ SlowResult resolve_slow(const Enc &enc, const typename E
                                                 uint32_t b0, uint32_t nbytes, uint32_t arena_end, uint32_t *status) {
     uint32_t buf[kShortBytes];                                   // scratch for one directly encoded word
     SlowResult r; r.kind = kWordRecompute; r.ntok = 0; r.slot = 0; r.h6 = 0;
-    int m = kMemoMiss; uint32_t meta = 0; MemoKey key; bool narrow = false;
-    if (ws.memo_mask && nbytes >= 1) { memo_key(arena, b0, nbytes, arena_end, key); m = memo_probe(ws, key, r.slot, meta, narrow); }
+    int m = kMemoMiss; uint32_t hit_ntok = 0, hit_h6 = 0; MemoKey key; bool narrow = false;
+    if (ws.memo_mask && nbytes >= 1) { memo_key(arena, b0, nbytes, arena_end, key); m = memo_probe(ws, key, r.slot, hit_ntok, hit_h6, narrow); }
     if (m == kMemoHit) {
-        if (narrow) { r.kind = kWordHit16; r.ntok = meta - 1; }
-        else { r.kind = kWordHit; r.ntok = (meta & 0xFFu) - 1; r.h6 = meta >> 8; }
+        r.kind = narrow ? kWordHit16 : kWordHit; r.ntok = hit_ntok; r.h6 = hit_h6;
         return r;
     }
     r.ntok = enc.encode_short(sg, arena + b0, nbytes, buf, r.h6);
@@ -311,12 +315,12 @@ template <class Enc>
 __device__ __noinline__ SlowResult resolve_slow_warp(const Enc &enc, const typename Enc::Stage *sg, const EncodeWorkspace &ws, const uint8_t *arena,
                                                      uint32_t b0, uint32_t nbytes, uint32_t arena_end, uint32_t *status, uint32_t *ids) {
     const uint32_t lane = threadIdx.x & 31;
-    int pm = kMemoMiss; uint32_t pslot = 0, pmeta = 0; bool pnarrow = false; MemoKey key;
-    if (lane == 0 && ws.memo_mask && nbytes >= 1) { memo_key(arena, b0, nbytes, arena_end, key); pm = memo_probe(ws, key, pslot, pmeta, pnarrow); }
+    int pm = kMemoMiss; uint32_t pslot = 0, pntok = 0, ph6 = 0; bool pnarrow = false; MemoKey key;
+    if (lane == 0 && ws.memo_mask && nbytes >= 1) { memo_key(arena, b0, nbytes, arena_end, key); pm = memo_probe(ws, key, pslot, pntok, ph6, pnarrow); }
     pm = __shfl_sync(0xffffffffu, pm, 0);
     SlowResult r; r.kind = kWordRecompute; r.ntok = 0; r.slot = pslot; r.h6 = 0;
     if (pm == kMemoHit) {
-        if (pnarrow) { r.kind = kWordHit16; r.ntok = pmeta - 1; } else { r.kind = kWordHit; r.ntok = (pmeta & 0xFFu) - 1; }
+        r.kind = pnarrow ? kWordHit16 : kWordHit; r.ntok = pntok;
     } else {
         const uint32_t n = enc.encode_short_warp(sg, arena + b0, nbytes, ids);       // ids[0..n)
         __syncwarp();
@@ -393,7 +397,8 @@ __device__ __forceinline__ void store_hit16_ids(uint32_t *dst, uint32_t n, uint4
     if (n > 8) {
         store_id_if<kShared>(dst, 8, n, Enc::expand16(b.x & 0xFFFFu, 8)); store_id_if<kShared>(dst, 9, n, Enc::expand16(b.x >> 16, 9));
         store_id_if<kShared>(dst, 10, n, Enc::expand16(b.y & 0xFFFFu, 10)); store_id_if<kShared>(dst, 11, n, Enc::expand16(b.y >> 16, 11));
-        store_id_if<kShared>(dst, 12, n, Enc::expand16(b.z & 0xFFFFu, 12));
+        store_id_if<kShared>(dst, 12, n, Enc::expand16(b.z & 0xFFFFu, 12)); store_id_if<kShared>(dst, 13, n, Enc::expand16(b.z >> 16, 13));
+        store_id_if<kShared>(dst, 14, n, Enc::expand16(b.w & 0xFFFFu, 14)); store_id_if<kShared>(dst, 15, n, Enc::expand16(b.w >> 16, 15));
     }
 }
 
@@ -452,6 +457,31 @@ __device__ __noinline__ uint32_t flush_pending_words(const Enc &enc, const typen
 //
 // Every warp owns tiles of kTileWords = 64 consecutive words (2 per lane), assigned round-robin; warps never wait for
 // each other, so the L2 latencies of one warp's probes are covered by the other warps of the SM.
+// Fast path of pass 1, one row = 32 consecutive words, word w_row + lane on lane `lane`.  The row's key bytes come from three aligned
+// 8-byte loads per word (fewer L1 wavefronts than five 4-byte loads: this pass is bound by the L1 data pipe, not by the ALUs).
+struct RowLoads { uint2 a, b, c; };
+__device__ __forceinline__ RowLoads row_load(const uint8_t *arena_al, uint32_t pos /* byte offset of the word + phase of the arena */) {
+    const uint2 *p = reinterpret_cast<const uint2 *>(arena_al + (pos & ~7u));
+    RowLoads r;
+    r.a = __ldg(p); r.b = __ldg(p + 1); r.c = __ldg(p + 2);
+    return r;
+}
+// 128-bit memo key of a word of `nb` (1..32) bytes from the loaded words: first 15 bytes, zero padded, length nibble in the top byte
+__device__ __forceinline__ uint4 row_key(const RowLoads &r, uint32_t pos, uint32_t nb) {
+    const bool hi = (pos & 4u) != 0;
+    const uint32_t sh = (pos & 3u) * 8u, n = min(nb, 15u);
+    const uint32_t x0 = hi ? r.a.y : r.a.x, x1 = hi ? r.b.x : r.a.y, x2 = hi ? r.b.y : r.b.x, x3 = hi ? r.c.x : r.b.y, x4 = hi ? r.c.y : r.c.x;
+    uint4 k;
+    k.x = __funnelshift_r(x0, x1, sh) & low_bytes_mask((int)n);
+    k.y = __funnelshift_r(x1, x2, sh) & low_bytes_mask((int)n - 4);
+    k.z = __funnelshift_r(x2, x3, sh) & low_bytes_mask((int)n - 8);
+    k.w = (__funnelshift_r(x3, x4, sh) & low_bytes_mask((int)n - 12)) | ((nb <= 15u ? nb : 0u) << 24);
+    return k;
+}
+// (entry ^ key) without the pub nibble: 0 when the slot holds this key
+__device__ __forceinline__ uint32_t key_diff(const uint4 &e, const uint4 &k) {
+    return (e.x ^ k.x) | (e.y ^ k.y) | (e.z ^ k.z) | ((e.w ^ k.w) & 0x0FFFFFFFu);
+}
 template <class Enc>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words,
@@ -460,18 +490,13 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
     const uint32_t warp_global = (blockIdx.x * kThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kThreads) >> 5;
     const uint32_t arena_end = word_off[n_words];
     const bool use_memo = ws.memo_mask != 0;
+    const uint8_t *arena_al = reinterpret_cast<const uint8_t *>((uintptr_t)arena & ~(uintptr_t)7);   // 8-byte aligned base of the key loads
+    const uint32_t aphase = (uint32_t)((uintptr_t)arena & 7);
     uint32_t h6 = 0;
     __shared__ typename Enc::Stage s_stage;
     enc.stage_init(s_stage);                                        // cooperative copy + __syncthreads (no-op for encoders without tables)
     const typename Enc::Stage *sg = &s_stage;
 
-    // offsets of this lane's two words in a tile (three consecutive offsets); the next tile's are fetched one tile ahead
-    auto load_offsets = [&](uint32_t t, uint32_t &o0, uint32_t &o1, uint32_t &o2) {
-        const uint32_t w0 = t * kTileWords, tw = min((uint32_t)kTileWords, n_words - w0), i0 = lane * kWordsPerThread;
-        o0 = i0 <= tw ? __ldg(word_off + w0 + i0) : 0u;
-        o1 = i0 + 1 <= tw ? __ldg(word_off + w0 + i0 + 1) : 0u;
-        o2 = i0 + 2 <= tw ? __ldg(word_off + w0 + i0 + 2) : 0u;
-    };
     // pending queue of the warp: words waiting for the slow path (at most 31 left over + 64 from one tile), followed by the 32-word
     // id staging row of the warp-per-word encoder (FastBPE)
     __shared__ uint32_t s_pend[kWarps][96 + 32];
@@ -482,134 +507,101 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
         h6 += flush_pending_words(enc, sg, ws, arena, word_off, arena_end, status, pend + first, count, warp_words, pend + 96);
         n_slow_words += count;
     };
-    // the offsets of the next tile are fetched one tile ahead.  (Measured, round 2: fetching them two tiles ahead cost 20 % -- register
-    // pressure; prefetch.global.L1 of the next tile's arena lines / memo ids compiles to CCTL and more than doubled the emit pass.)
-    uint32_t po0 = 0, po1 = 0, po2 = 0;
-    if (warp_global < ws.n_tiles) load_offsets(warp_global, po0, po1, po2);
+    // A tile is two rows of 32 words (word w_tile + 32 j + lane on lane `lane`): offsets, records and token offsets are coalesced 4-byte
+    // accesses and the key loads of a row touch few lines.  The four offsets of the next tile are fetched one tile ahead.
+    const uint32_t n_full = n_words / kTileWords;                                   // tiles below this one have all 64 words
+    uint32_t po[4] = {0, 0, 0, 0};
+    auto load_offsets = [&](uint32_t t) {
+        const uint32_t *q = word_off + (size_t)t * kTileWords + lane;
+        po[0] = __ldg(q); po[1] = __ldg(q + 1); po[2] = __ldg(q + 32); po[3] = __ldg(q + 33);
+    };
+    if (warp_global < n_full) load_offsets(warp_global);
     for (uint32_t tile = warp_global; tile < ws.n_tiles; tile += n_warps) {
         const uint32_t w_tile = tile * kTileWords;
-        const uint32_t tile_words = min((uint32_t)kTileWords, n_words - w_tile);
-        uint32_t nb[kWordsPerThread], b0s[kWordsPerThread];
-        {
-            const uint32_t i0 = lane * kWordsPerThread;
-            const uint32_t o0 = po0, o1 = po1, o2 = po2;
-            if (tile + n_warps < ws.n_tiles) load_offsets(tile + n_warps, po0, po1, po2);
-            b0s[0] = o0; nb[0] = i0 < tile_words ? o1 - o0 : 0xFFFFFFFFu;       // 0xFFFFFFFF: no word
-            b0s[1] = o1; nb[1] = i0 + 1 < tile_words ? o2 - o1 : 0xFFFFFFFFu;
-        }
-        // ---- fast path (words of 1..32 bytes): 128-bit key from aligned 4-byte loads, then up to two L1-cached memo
-        // probes.  Both words' loads are in flight together.
-        uint32_t kind[kWordsPerThread], ntok[kWordsPerThread], slot[kWordsPerThread];
-        uint4 kw[kWordsPerThread], ew[kWordsPerThread];           // key of the word / key found in the probed entry
-        bool fastj[kWordsPerThread], slow[kWordsPerThread], is_long[kWordsPerThread];
-        {
-            uint32_t a0[kWordsPerThread], a1[kWordsPerThread], a2[kWordsPerThread], a3[kWordsPerThread], a4[kWordsPerThread];
+        uint32_t rec[kWordsPerThread] = {0u, 0u}, ntok[kWordsPerThread] = {0u, 0u};
+        bool slow[kWordsPerThread] = {false, false}, is_long[kWordsPerThread] = {false, false};
+        const uint32_t o[4] = {po[0], po[1], po[2], po[3]};
+        if (tile + n_warps < n_full) load_offsets(tile + n_warps);
+        // the whole tile takes the fast path when it is full and 40 bytes can be read from the start of its last word
+        const uint32_t last_start = __shfl_sync(0xffffffffu, o[2], 31);
+        if (tile < n_full && use_memo && (uint64_t)last_start + 40 <= arena_end) {
+            RowLoads ld[kWordsPerThread];
+            uint32_t nb[kWordsPerThread], pos[kWordsPerThread], slot[kWordsPerThread];
+            uint4 kw[kWordsPerThread], ew[kWordsPerThread];
+#pragma unroll
+            for (int j = 0; j < kWordsPerThread; ++j) { nb[j] = o[2 * j + 1] - o[2 * j]; pos[j] = o[2 * j] + aphase; ld[j] = row_load(arena_al, pos[j]); }
 #pragma unroll
             for (int j = 0; j < kWordsPerThread; ++j) {
-                kind[j] = kWordNone; ntok[j] = 0; slot[j] = 0; slow[j] = false;
-                kw[j] = ew[j] = make_uint4(0, 0, 0, 0);
-                is_long[j] = nb[j] != 0xFFFFFFFFu && nb[j] > (uint32_t)kShortBytes;
-                // words of 16..32 bytes take the same first probe on their 15-byte prefix (length nibble 0); their tail is checked below
-                fastj[j] = use_memo && nb[j] >= 1 && nb[j] <= (uint32_t)kShortBytes && (uint64_t)b0s[j] + 40 <= arena_end;
-                a0[j] = a1[j] = a2[j] = a3[j] = a4[j] = 0;
-                if (fastj[j]) {                                   // the (up to five) aligned 32-bit words that hold the word
-                    const uintptr_t a = (uintptr_t)(arena + b0s[j]);
-                    const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
-                    const uint32_t span = min(nb[j], 15u) + (uint32_t)(a & 3);
-                    a0[j] = __ldg(q);
-                    a1[j] = ldg_u32_if(q + 1, span > 4); a2[j] = ldg_u32_if(q + 2, span > 8);
-                    a3[j] = ldg_u32_if(q + 3, span > 12); a4[j] = ldg_u32_if(q + 4, span > 16);
-                }
+                kw[j] = row_key(ld[j], pos[j], nb[j]);
+                slot[j] = memo_hash4(kw[j].x, kw[j].y, kw[j].z, kw[j].w) & ws.memo_mask;
+                ew[j] = ld_ca_u32x4(ws.keys + slot[j]);              // ONE scattered load per word: key + pub nibble
             }
 #pragma unroll
             for (int j = 0; j < kWordsPerThread; ++j) {
-                if (fastj[j]) {
-                    const uint32_t sh = (uint32_t)((uintptr_t)(arena + b0s[j]) & 3) * 8, n = min(nb[j], 15u);
-                    uint32_t w0 = __funnelshift_r(a0[j], a1[j], sh), w1 = __funnelshift_r(a1[j], a2[j], sh);
-                    uint32_t w2 = __funnelshift_r(a2[j], a3[j], sh), w3 = __funnelshift_r(a3[j], a4[j], sh);
-                    // zero the bytes at and beyond n, put the length into the top byte (layout of the key: lo | hi)
-                    w0 &= low_bytes_mask((int)n); w1 &= low_bytes_mask((int)n - 4); w2 &= low_bytes_mask((int)n - 8);
-                    w3 = (w3 & low_bytes_mask((int)n - 12)) | ((nb[j] <= 15u ? n : 0u) << 24);
-                    kw[j] = make_uint4(w0, w1, w2, w3);
-                    slot[j] = memo_hash4(w0, w1, w2, w3) & ws.memo_mask;
-                    ew[j] = ld_ca_u32x4(ws.keys + slot[j]);      // ONE scattered load per word: key + pub nibble
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < kWordsPerThread; ++j) {
-            if (nb[j] == 0xFFFFFFFFu) continue;
-            if (is_long[j]) { kind[j] = kWordLong; continue; }
-            bool hit = false;
-            if (fastj[j]) {
-                bool same = ew[j].x == kw[j].x && ew[j].y == kw[j].y && ew[j].z == kw[j].z && ((ew[j].w ^ kw[j].w) & 0x0FFFFFFFu) == 0;
-                if (!same && (ew[j].x | ew[j].y | ew[j].z | ew[j].w) != 0) {
-                    // the slot holds another word (hash collision): look at the next slot (usually the same 32-byte sector)
+                // Served here: the first slot holds this word (at most 15 bytes, so the key is the whole word) with 1..13 tokens.
+                // Everything else is rare and goes to the slow path, 32 words at a time: longer probe sequences, words of 16..32
+                // bytes (tail compare), entries with 14..16 tokens or a 32-bit id list, first occurrences.  No calls in this loop.
+                uint32_t d = key_diff(ew[j], kw[j]);
+                if (d != 0 && (ew[j].x | ew[j].y | ew[j].z | ew[j].w) != 0) {       // another word lives here: try the neighbouring slot
                     slot[j] = (slot[j] + 1) & ws.memo_mask;
                     ew[j] = ld_ca_u32x4(ws.keys + slot[j]);
-                    same = ew[j].x == kw[j].x && ew[j].y == kw[j].y && ew[j].z == kw[j].z && ((ew[j].w ^ kw[j].w) & 0x0FFFFFFFu) == 0;
+                    d = key_diff(ew[j], kw[j]);
                 }
                 const uint32_t pub = ew[j].w >> 28;
-                hit = same && pub != 0 && pub != kPubExt;            // pub nibble: ids16[] valid, n_tokens + 1
-                if (hit && nb[j] > 15u) {                            // rare: compare bytes 15.. with the tail stored beside the entry
-                    MemoKey key;
-                    memo_key(arena, b0s[j], nb[j], arena_end, key);
-                    const MemoExt *e = ws.ext + slot[j];
-                    const uint4 x = ld_ca_u32x4(e);
-                    unsigned long long tb, dummy;
-                    ld_ca_u64x2(&e->tail_b, tb, dummy);
-                    hit = ((unsigned long long)x.z | ((unsigned long long)x.w << 32)) == key.tail_a && tb == key.tail_b && x.y == key.tail_last;
-                }
-                if (hit) ntok[j] = pub - 1;
+                const bool hit = d == 0 && pub - 1u < kPubWide - 1u && nb[j] - 1u < 15u;
+                ntok[j] = hit ? pub : 0u;
+                is_long[j] = nb[j] > (uint32_t)kShortBytes;
+                slow[j] = !hit && !is_long[j];
+                rec[j] = hit ? (kWordHit16 << 29) | (pub << 23) | slot[j] : is_long[j] ? kWordLong << 29 : 0u;
             }
-            if (hit) kind[j] = kWordHit16;
-            else slow[j] = true;
+        } else {
+            // last tiles of the call (partial, or too close to the end of the arena for the unguarded loads) and calls without memo:
+            // every word goes to the slow path, which builds its key bytewise
+#pragma unroll
+            for (int j = 0; j < kWordsPerThread; ++j) {
+                const uint32_t w = w_tile + 32u * j + lane;
+                if (w < n_words) {
+                    const uint32_t nbj = __ldg(word_off + w + 1) - __ldg(word_off + w);
+                    is_long[j] = nbj > (uint32_t)kShortBytes;
+                    slow[j] = !is_long[j];
+                    rec[j] = is_long[j] ? kWordLong << 29 : 0u;
+                }
+            }
         }
         // Words not served by the first probe (first occurrence, hash collision, ids that need the 32-bit list).  A single trie
         // walk / merge loop is a chain of dependent L2 accesses (10-25 us) during which the other lanes of the warp would idle.
-        // kBatchSlowPath (FastWP): they go to the warp's pending queue and are resolved 32 at a time, one per lane (flush below) --
-        // 5 % faster on the bench stream and 30-40 % on streams with 10^5..10^6 word types.  Otherwise (FastBPE, where the queue
-        // cost the count pass 10 %): a few slow words are encoded by the WHOLE WARP one after the other (kWarpShort: one lane per
-        // adjacent pair, shuffle min-reduce -- latency of a word = its merges, not its pair probes); more than `warp_words` of
-        // them are spread over the lanes, one word per lane.
-        if constexpr (Enc::kBatchSlowPath) {
+        // kBatchSlowPath: they go to the warp's pending queue and are resolved 32 at a time, one per lane (flush below).
+        // Otherwise (swt_tune("bpe_queue", 0)): a few slow words are encoded by the WHOLE WARP one after the other (kWarpShort: one
+        // lane per adjacent pair, shuffle min-reduce); more than `warp_words` of them are spread over the lanes, one word per lane.
 #pragma unroll
-            for (int j = 0; j < kWordsPerThread; ++j) {
-                const uint32_t m = __ballot_sync(0xffffffffu, slow[j]);
-                if (m == 0) continue;                                               // warp-uniform
-                if (slow[j]) pend[n_pend + __popc(m & ((1u << lane) - 1u))] = w_tile + lane * kWordsPerThread + j;
+        for (int j = 0; j < kWordsPerThread; ++j) {
+            const uint32_t m = __ballot_sync(0xffffffffu, slow[j]);
+            if (m == 0) continue;                                                   // warp-uniform, the common case
+            if constexpr (Enc::kBatchSlowPath) {
+                if (slow[j]) pend[n_pend + __popc(m & ((1u << lane) - 1u))] = w_tile + 32u * j + lane;
                 n_pend += __popc(m);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < kWordsPerThread; ++j) {
-                const uint32_t m = __ballot_sync(0xffffffffu, slow[j]);
-                if (m == 0) continue;                                               // warp-uniform
+            } else {
                 n_slow_words += __popc(m);
-                const SlowResult r = resolve_slow_tile(enc, sg, ws, arena, arena_end, status, pend + 96, m, b0s[j], nb[j], warp_words);
+                uint32_t b0 = 0, nbj = 0;
+                if (slow[j]) { b0 = __ldg(word_off + w_tile + 32u * j + lane); nbj = __ldg(word_off + w_tile + 32u * j + lane + 1) - b0; }
+                const SlowResult r = resolve_slow_tile(enc, sg, ws, arena, arena_end, status, pend + 96, m, b0, nbj, warp_words);
                 h6 += r.h6;
-                if (slow[j]) { kind[j] = r.kind; ntok[j] = r.ntok; slot[j] = r.slot; slow[j] = false; }
+                if (slow[j]) {
+                    ntok[j] = r.ntok; slow[j] = false;
+                    rec[j] = (r.kind << 29) | (r.ntok << 23) | ((r.kind == kWordHit || r.kind == kWordHit16) ? r.slot : 0u);
+                }
             }
         }
         // long words (rare): left to encode_long_count_kernel, which runs between this pass and the scan; here the tile is only
         // flagged, so that the code of the long paths (warp-cooperative merge loop / segment walk) stays out of this kernel
-        uint32_t packed[kWordsPerThread];
-#pragma unroll
-        for (int j = 0; j < kWordsPerThread; ++j)
-            packed[j] = (kind[j] << 29) | (ntok[j] << 23) | ((kind[j] == kWordHit || kind[j] == kWordHit16) ? slot[j] : 0u);
         if (__any_sync(0xffffffffu, is_long[0] || is_long[1])) { if (lane == 0) atomicOr(&ws.long_tiles[tile >> 5], 1u << (tile & 31u)); }
         // ---- per-word records and the tile total (pending words: record and token count are added by the flush)
-        {
-            const uint32_t i0 = lane * kWordsPerThread;
-            if (i0 + 1 < tile_words && !slow[0] && !slow[1]) *reinterpret_cast<uint2 *>(ws.packed + w_tile + i0) = make_uint2(packed[0], packed[1]);
-            else {
-                if (i0 < tile_words && !slow[0]) ws.packed[w_tile + i0] = packed[0];
-                if (i0 + 1 < tile_words && !slow[1]) ws.packed[w_tile + i0 + 1] = packed[1];
-            }
-        }
-        uint32_t total = ntok[0] + ntok[1];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+        for (int j = 0; j < kWordsPerThread; ++j) {
+            const uint32_t w = w_tile + 32u * j + lane;
+            if (w < n_words && !slow[j]) ws.packed[w] = rec[j];
+        }
+        const uint32_t total = __reduce_add_sync(0xffffffffu, ntok[0] + ntok[1]);
         if (lane == 0) ws.tile_total[tile] = total;
         if constexpr (Enc::kBatchSlowPath) {
             __syncwarp();
@@ -817,6 +809,18 @@ __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uin
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// rare record kinds of pass 2, out of line: the 32-bit id list of the tok32 arena, words that have to be encoded again
+template <class Enc>
+__device__ __noinline__ void emit_special(const Enc &enc, const uint8_t *arena, const uint32_t *word_off, const EncodeWorkspace &ws, uint32_t w,
+                                          uint32_t kind, uint32_t ntok, uint32_t arg, uint32_t *dst) {
+    if (kind == kWordHit) {
+        const MemoExt *x = ws.ext + (arg & kMemoSlotMask);
+        if (x->meta != 0xFFFFFFFFu) { const uint32_t *src = ws.tok32 + x->tok32_off; for (uint32_t k = 0; k < ntok; ++k) dst[k] = src[k]; return; }
+    }                                                           // (the owner found the arena full: encode again)
+    const uint32_t b0 = __ldg(word_off + w), b1 = __ldg(word_off + w + 1);
+    emit_slow(enc, arena + b0, b1 - b0, kind, ntok, dst);
+}
+
 template <class Enc>
 __global__ void __launch_bounds__(kThreads, kEmitCtasPerSm)
 encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words,
@@ -825,18 +829,17 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
     __shared__ __align__(16) uint32_t s_compact[kWarps][kCompactTokens + 4];   // per warp: the tile's ids in output order
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * kThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kThreads) >> 5;
-    const bool tok_off_vec = out_tok_off && (((uintptr_t)out_tok_off & 7) == 0);
     const bool bulk = (ws.flags & kFlagBulkStore) != 0;
     uint32_t *compact = s_compact[threadIdx.x >> 5];
     bool bulk_pending = false;                                                  // lane 0: a bulk copy may still be reading `compact`
 
-    // software pipeline: the per-word records and the tile's output position are fetched two tiles ahead (the two addends of the
-    // position are kept apart: adding them at load time made every iteration wait for the loads it had just issued)
+    // software pipeline: the per-word records (two rows of 32 words, word w_tile + 32 j + lane on lane `lane`) and the tile's output
+    // position are fetched two tiles ahead (the two addends of the position are kept apart: adding them at load time made every
+    // iteration wait for the loads it had just issued)
     auto load_tile = [&](uint32_t t, uint32_t &p0, uint32_t &p1, unsigned long long &gb, uint32_t &tt) {
-        const uint32_t w0 = t * kTileWords, tw = min((uint32_t)kTileWords, n_words - w0), i = lane * kWordsPerThread;
-        p0 = p1 = 0u;
-        if (i + 1 < tw) { const uint2 p = *reinterpret_cast<const uint2 *>(ws.packed + w0 + i); p0 = p.x; p1 = p.y; }
-        else if (i < tw) p0 = ws.packed[w0 + i];
+        const uint32_t w = t * kTileWords + lane;
+        p0 = w < n_words ? ws.packed[w] : 0u;
+        p1 = w + 32 < n_words ? ws.packed[w + 32] : 0u;
         gb = ws.group_base[t / kGroupTiles]; tt = ws.tile_total[t];
     };
     uint32_t pp0 = 0, pp1 = 0, ptt = 0, qp0 = 0, qp1 = 0, qtt = 0; unsigned long long pgb = 0, qgb = 0;
@@ -844,47 +847,42 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
     if (warp_global + n_warps < ws.n_tiles) load_tile(warp_global + n_warps, qp0, qp1, qgb, qtt);
     for (uint32_t tile = warp_global; tile < ws.n_tiles; tile += n_warps) {
         const uint32_t w_tile = tile * kTileWords;
-        const uint32_t tile_words = min((uint32_t)kTileWords, n_words - w_tile);
-        const uint32_t i0 = lane * kWordsPerThread;
         const uint32_t packed[kWordsPerThread] = {pp0, pp1};
         const uint64_t base = pgb + ptt;
         pp0 = qp0; pp1 = qp1; pgb = qgb; ptt = qtt;
         if (tile + 2 * n_warps < ws.n_tiles) load_tile(tile + 2 * n_warps, qp0, qp1, qgb, qtt);
-        uint32_t kind[kWordsPerThread], ntok[kWordsPerThread], arg[kWordsPerThread];
+        uint32_t kind[kWordsPerThread], ntok[kWordsPerThread];
         uint4 ra[kWordsPerThread], rb[kWordsPerThread];
 #pragma unroll
         for (int j = 0; j < kWordsPerThread; ++j) {
             kind[j] = packed[j] >> 29;
-            arg[j] = packed[j] & 0x1FFFFFFFu;
-            ntok[j] = record_ntok<Enc>(packed[j], ws.long_scratch);   // long words: their ids are written by encode_long_emit_kernel
+            ntok[j] = (packed[j] >> 23) & 63u;                      // Hit16 / Hit / Recompute; kind 0: no word, or an empty one
+            if (kind[j] == kWordLong || kind[j] == kWordLongB || kind[j] == kWordLongSeg)             // rare: ids written by encode_long_emit_kernel
+                ntok[j] = record_ntok<Enc>(packed[j], ws.long_scratch);
             ra[j] = rb[j] = make_uint4(0, 0, 0, 0);
-            if (kind[j] == kWordHit16) {                            // one or two scattered loads; both words' loads in flight together
-                const uint4 *e = ws.ids16 + 2 * (size_t)(arg[j] & kMemoSlotMask);
-                if (ntok[j] > 0) ra[j] = ld_ca_u32x4(e);
+            if (kind[j] == kWordHit16) {                            // one or two scattered loads; both rows' loads in flight together
+                const uint4 *e = ws.ids16 + 2 * (size_t)(packed[j] & kMemoSlotMask);
+                ra[j] = ld_ca_u32x4(e);
                 if (ntok[j] > 8) rb[j] = ld_ca_u32x4(e + 1);
             }
         }
-        uint32_t count = 0, run[kWordsPerThread];
+        // tile-local token offset of every word: row 0 comes first in the output
+        uint32_t run[kWordsPerThread], total = 0;
 #pragma unroll
-        for (int j = 0; j < kWordsPerThread; ++j) { run[j] = count; count += ntok[j]; }
-        uint32_t incl = count;
+        for (int j = 0; j < kWordsPerThread; ++j) {
+            uint32_t incl = ntok[j];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += v; }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), excl = incl - count;
-#pragma unroll
-        for (int j = 0; j < kWordsPerThread; ++j) run[j] += excl;
-        const bool fits_out = base + total <= out_cap;
-        const bool use_compact = total <= (uint32_t)kCompactTokens;
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += v; }
+            run[j] = total + incl - ntok[j];
+            total += __shfl_sync(0xffffffffu, incl, 31);
+        }
         if (out_tok_off) {
             const uint32_t o0 = tok_base + (uint32_t)base;
-            if (tok_off_vec && i0 + kWordsPerThread <= tile_words)
-                *reinterpret_cast<uint2 *>(out_tok_off + w_tile + i0) = make_uint2(o0 + run[0], o0 + run[1]);
-            else {
 #pragma unroll
-                for (int j = 0; j < kWordsPerThread; ++j) if (i0 + j < tile_words) out_tok_off[w_tile + i0 + j] = o0 + run[j];
-            }
+            for (int j = 0; j < kWordsPerThread; ++j) if (w_tile + 32u * j + lane < n_words) out_tok_off[w_tile + 32u * j + lane] = o0 + run[j];
         }
-        if (!fits_out) continue;                                                    // warp-uniform (status set by the scan)
+        if (base + total > out_cap) continue;                                       // warp-uniform (status set by the scan)
+        const bool use_compact = total <= (uint32_t)kCompactTokens;
         // the previous tile's bulk copy must have finished READING the buffer before it is overwritten
         if (bulk) { if (lane == 0 && bulk_pending) { bulk_store_wait_read(); bulk_pending = false; } __syncwarp(); }
         // the tile's ids are laid out in shared memory with the 16-byte phase of their destination, so that the copy
@@ -897,18 +895,11 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
                 // two copies of the same code so that the common case compiles to shared-memory stores (STS)
                 if (use_compact) store_hit16_ids<Enc, true>(cdst + run[j], ntok[j], ra[j], rb[j]);
                 else store_hit16_ids<Enc, false>(out_ids + base + run[j], ntok[j], ra[j], rb[j]);
-            } else if (kind[j] == kWordHit) {                                       // rare: 32-bit id list in the tok32 arena
-                uint32_t *dst = use_compact ? cdst + run[j] : out_ids + base + run[j];
-                const MemoExt *x = ws.ext + (arg[j] & kMemoSlotMask);
-                if (x->meta != 0xFFFFFFFFu) { const uint32_t *src = ws.tok32 + x->tok32_off; for (uint32_t k = 0; k < ntok[j]; ++k) dst[k] = src[k]; }
-                else {                                                              // the owner found the arena full: re-encode
-                    const uint32_t b0 = __ldg(word_off + w_tile + i0 + j), b1 = __ldg(word_off + w_tile + i0 + j + 1);
-                    emit_slow(enc, arena + b0, b1 - b0, kind[j], ntok[j], dst);
-                }
-            } else if (kind[j] == kWordRecompute) {
-                uint32_t *dst = use_compact ? cdst + run[j] : out_ids + base + run[j];
-                const uint32_t b0 = __ldg(word_off + w_tile + i0 + j), b1 = __ldg(word_off + w_tile + i0 + j + 1);
-                emit_slow(enc, arena + b0, b1 - b0, kind[j], ntok[j], dst);
+            }
+            const bool special = kind[j] == kWordHit || kind[j] == kWordRecompute;
+            if (__any_sync(0xffffffffu, special)) {                                 // rare
+                if (special) emit_special(enc, arena, word_off, ws, w_tile + 32u * j + lane, kind[j], ntok[j], packed[j] & 0x1FFFFFFFu,
+                                          use_compact ? cdst + run[j] : out_ids + base + run[j]);
             }
         }
         if (use_compact && bulk) {
