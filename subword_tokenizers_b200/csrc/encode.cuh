@@ -245,7 +245,8 @@ static __device__ __noinline__ int memo_probe(const EncodeWorkspace &ws, const M
 //   [31:29] kind; Hit (32-bit ids in tok32) / Hit16 (ids16[] valid): [28:23] n_tokens, [22:0] memo slot; Recompute: [28:23] n_tokens;
 //   WP long, walked by its lane: [28:0] n_tokens; long word with scratch (BPE; WP segment records): [28:0] scratch granule (16 u32),
 //   header word 0 of the granule holds n_tokens
-enum : uint32_t { kWordNone = 0u, kWordHit = 1u, kWordRecompute = 2u, kWordLong = 3u, kWordLongB = 4u, kWordHit16 = 5u, kWordLongSeg = 6u };
+// (numbered so that the emit pass tests the common case with one compare: records >= kWordHit << 29 are the unusual ones)
+enum : uint32_t { kWordNone = 0u, kWordHit16 = 1u, kWordHit = 2u, kWordRecompute = 3u, kWordLong = 5u, kWordLongB = 6u, kWordLongSeg = 7u };
 constexpr uint32_t kLongHeader = 16;      // u32 words reserved in front of the scratch of a long word
 constexpr uint32_t kGroupTiles = 1024;    // tiles per scan group
 
@@ -809,16 +810,51 @@ __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uin
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// rare record kinds of pass 2, out of line: the 32-bit id list of the tok32 arena, words that have to be encoded again
+// Tiles of pass 2 with an unusual record (32-bit id list of the tok32 arena, a word that has to be encoded again, a long word whose
+// ids encode_long_emit_kernel writes) or with more tokens than the shared-memory buffer holds: rare, out of line, ids written straight
+// to global memory.  ntok[] / run[] are recomputed here because the counts of long words do not fit the packed scan of the fast path.
 template <class Enc>
-__device__ __noinline__ void emit_special(const Enc &enc, const uint8_t *arena, const uint32_t *word_off, const EncodeWorkspace &ws, uint32_t w,
-                                          uint32_t kind, uint32_t ntok, uint32_t arg, uint32_t *dst) {
-    if (kind == kWordHit) {
-        const MemoExt *x = ws.ext + (arg & kMemoSlotMask);
-        if (x->meta != 0xFFFFFFFFu) { const uint32_t *src = ws.tok32 + x->tok32_off; for (uint32_t k = 0; k < ntok; ++k) dst[k] = src[k]; return; }
-    }                                                           // (the owner found the arena full: encode again)
-    const uint32_t b0 = __ldg(word_off + w), b1 = __ldg(word_off + w + 1);
-    emit_slow(enc, arena + b0, b1 - b0, kind, ntok, dst);
+__device__ __noinline__ void emit_tile_generic(const Enc &enc, const uint8_t *arena, const uint32_t *word_off, uint32_t n_words, uint32_t *out_ids,
+                                               uint64_t out_cap, uint32_t *out_tok_off, uint32_t tok_base, const EncodeWorkspace &ws, uint32_t w_tile,
+                                               uint64_t base, uint32_t p0, uint32_t p1) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t packed[kWordsPerThread] = {p0, p1};
+    uint32_t ntok[kWordsPerThread], run[kWordsPerThread], total = 0;
+#pragma unroll
+    for (int j = 0; j < kWordsPerThread; ++j) {
+        ntok[j] = record_ntok<Enc>(packed[j], ws.long_scratch);
+        uint32_t incl = ntok[j];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += v; }
+        run[j] = total + incl - ntok[j];
+        total += __shfl_sync(0xffffffffu, incl, 31);
+    }
+#pragma unroll
+    for (int j = 0; j < kWordsPerThread; ++j) {
+        const uint32_t w = w_tile + 32u * j + lane;
+        if (out_tok_off && w < n_words) out_tok_off[w] = tok_base + (uint32_t)base + run[j];
+    }
+    if (base + total > out_cap) return;                                             // status set by the scan
+#pragma unroll
+    for (int j = 0; j < kWordsPerThread; ++j) {
+        const uint32_t kind = packed[j] >> 29, arg = packed[j] & 0x1FFFFFFFu, w = w_tile + 32u * j + lane;
+        uint32_t *dst = out_ids + base + run[j];
+        if (kind == kWordHit16) {
+            const uint4 *e = ws.ids16 + 2 * (size_t)(arg & kMemoSlotMask);
+            const uint4 a = ld_ca_u32x4(e), b = ntok[j] > 8 ? ld_ca_u32x4(e + 1) : make_uint4(0, 0, 0, 0);
+            store_hit16_ids<Enc, false>(dst, ntok[j], a, b);
+        } else if (kind == kWordHit) {                                              // 32-bit id list in the tok32 arena
+            const MemoExt *x = ws.ext + (arg & kMemoSlotMask);
+            if (x->meta != 0xFFFFFFFFu) { const uint32_t *src = ws.tok32 + x->tok32_off; for (uint32_t k = 0; k < ntok[j]; ++k) dst[k] = src[k]; }
+            else {                                                                  // the owner found the arena full: encode again
+                const uint32_t b0 = __ldg(word_off + w), b1 = __ldg(word_off + w + 1);
+                emit_slow(enc, arena + b0, b1 - b0, kind, ntok[j], dst);
+            }
+        } else if (kind == kWordRecompute) {
+            const uint32_t b0 = __ldg(word_off + w), b1 = __ldg(word_off + w + 1);
+            emit_slow(enc, arena + b0, b1 - b0, kind, ntok[j], dst);
+        }
+    }
 }
 
 template <class Enc>
@@ -826,10 +862,9 @@ __global__ void __launch_bounds__(kThreads, kEmitCtasPerSm)
 encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words,
                    uint32_t *__restrict__ out_ids, uint64_t out_cap, uint32_t *__restrict__ out_tok_off, uint32_t tok_base,
                    EncodeWorkspace ws) {
-    __shared__ __align__(16) uint32_t s_compact[kWarps][kCompactTokens + 4];   // per warp: the tile's ids in output order
+    __shared__ __align__(16) uint32_t s_compact[kWarps][kCompactTokens + 8];   // per warp: the tile's ids in output order
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * kThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kThreads) >> 5;
-    const bool bulk = (ws.flags & kFlagBulkStore) != 0;
     uint32_t *compact = s_compact[threadIdx.x >> 5];
     bool bulk_pending = false;                                                  // lane 0: a bulk copy may still be reading `compact`
 
@@ -847,86 +882,60 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
     if (warp_global + n_warps < ws.n_tiles) load_tile(warp_global + n_warps, qp0, qp1, qgb, qtt);
     for (uint32_t tile = warp_global; tile < ws.n_tiles; tile += n_warps) {
         const uint32_t w_tile = tile * kTileWords;
-        const uint32_t packed[kWordsPerThread] = {pp0, pp1};
+        const uint32_t p0 = pp0, p1 = pp1;
         const uint64_t base = pgb + ptt;
         pp0 = qp0; pp1 = qp1; pgb = qgb; ptt = qtt;
         if (tile + 2 * n_warps < ws.n_tiles) load_tile(tile + 2 * n_warps, qp0, qp1, qgb, qtt);
-        uint32_t kind[kWordsPerThread], ntok[kWordsPerThread];
-        uint4 ra[kWordsPerThread], rb[kWordsPerThread];
-#pragma unroll
-        for (int j = 0; j < kWordsPerThread; ++j) {
-            kind[j] = packed[j] >> 29;
-            ntok[j] = (packed[j] >> 23) & 63u;                      // Hit16 / Hit / Recompute; kind 0: no word, or an empty one
-            if (kind[j] == kWordLong || kind[j] == kWordLongB || kind[j] == kWordLongSeg)             // rare: ids written by encode_long_emit_kernel
-                ntok[j] = record_ntok<Enc>(packed[j], ws.long_scratch);
-            ra[j] = rb[j] = make_uint4(0, 0, 0, 0);
-            if (kind[j] == kWordHit16) {                            // one or two scattered loads; both rows' loads in flight together
-                const uint4 *e = ws.ids16 + 2 * (size_t)(packed[j] & kMemoSlotMask);
-                ra[j] = ld_ca_u32x4(e);
-                if (ntok[j] > 8) rb[j] = ld_ca_u32x4(e + 1);
-            }
+        // records are kWordNone (no word / no token) or kWordHit16 in all but a few tiles
+        if (__any_sync(0xffffffffu, (p0 | p1) >= (kWordHit << 29))) {
+            emit_tile_generic(enc, arena, word_off, n_words, out_ids, out_cap, out_tok_off, tok_base, ws, w_tile, base, p0, p1);
+            continue;
         }
-        // tile-local token offset of every word: row 0 comes first in the output
-        uint32_t run[kWordsPerThread], total = 0;
+        // ids of both rows: one scattered 16-byte load per word (a second one for words of more than 8 tokens), all in flight together
+        const uint32_t n0 = (p0 >> 23) & 63u, n1 = (p1 >> 23) & 63u;                // kWordNone records are zero
+        const uint4 *e0 = ws.ids16 + 2 * (size_t)(p0 & kMemoSlotMask), *e1 = ws.ids16 + 2 * (size_t)(p1 & kMemoSlotMask);
+        uint4 a0 = make_uint4(0, 0, 0, 0), b0 = a0, a1 = a0, b1 = a0;
+        if (n0) a0 = ld_ca_u32x4(e0);
+        if (n1) a1 = ld_ca_u32x4(e1);
+        if (n0 > 8) b0 = ld_ca_u32x4(e0 + 1);
+        if (n1 > 8) b1 = ld_ca_u32x4(e1 + 1);
+        // tile-local token offsets: ONE inclusive scan over both rows' counts packed into 16-bit halves (a row has at most 32 * 16 tokens)
+        uint32_t incl = n0 | (n1 << 16);
 #pragma unroll
-        for (int j = 0; j < kWordsPerThread; ++j) {
-            uint32_t incl = ntok[j];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += v; }
-            run[j] = total + incl - ntok[j];
-            total += __shfl_sync(0xffffffffu, incl, 31);
-        }
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += v; }
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t tot0 = tot & 0xFFFFu, total = tot0 + (tot >> 16);
+        const uint32_t run0 = (incl & 0xFFFFu) - n0, run1 = tot0 + (incl >> 16) - n1;     // row 0 comes first in the output
         if (out_tok_off) {
-            const uint32_t o0 = tok_base + (uint32_t)base;
-#pragma unroll
-            for (int j = 0; j < kWordsPerThread; ++j) if (w_tile + 32u * j + lane < n_words) out_tok_off[w_tile + 32u * j + lane] = o0 + run[j];
+            const uint32_t o0 = tok_base + (uint32_t)base, w = w_tile + lane;
+            if (w < n_words) out_tok_off[w] = o0 + run0;
+            if (w + 32 < n_words) out_tok_off[w + 32] = o0 + run1;
         }
         if (base + total > out_cap) continue;                                       // warp-uniform (status set by the scan)
-        const bool use_compact = total <= (uint32_t)kCompactTokens;
+        if (total > (uint32_t)kCompactTokens) {                                     // more tokens than the buffer holds (rare)
+            emit_tile_generic(enc, arena, word_off, n_words, out_ids, out_cap, nullptr, tok_base, ws, w_tile, base, p0, p1);
+            continue;
+        }
         // the previous tile's bulk copy must have finished READING the buffer before it is overwritten
-        if (bulk) { if (lane == 0 && bulk_pending) { bulk_store_wait_read(); bulk_pending = false; } __syncwarp(); }
-        // the tile's ids are laid out in shared memory with the 16-byte phase of their destination, so that the copy
-        // out is one aligned bulk copy (or LDS.128 -> STG.128 without bank conflicts)
+        if (lane == 0 && bulk_pending) { bulk_store_wait_read(); bulk_pending = false; }
+        __syncwarp();
+        // The tile's ids are laid out in shared memory with the 16-byte phase of their destination and leave as ONE bulk copy
+        // (cp.async.bulk shared::cta -> global: no LDS/STG wavefronts on the LSU pipe that bounds this kernel); the at most three ids in
+        // front of / behind the 16-byte aligned middle are plain stores of lanes 1..6.
         const uint32_t sh = (uint32_t)((uintptr_t)(out_ids + base) >> 2) & 3u;
         uint32_t *cdst = compact + sh;
-#pragma unroll
-        for (int j = 0; j < kWordsPerThread; ++j) {
-            if (kind[j] == kWordHit16) {
-                // two copies of the same code so that the common case compiles to shared-memory stores (STS)
-                if (use_compact) store_hit16_ids<Enc, true>(cdst + run[j], ntok[j], ra[j], rb[j]);
-                else store_hit16_ids<Enc, false>(out_ids + base + run[j], ntok[j], ra[j], rb[j]);
-            }
-            const bool special = kind[j] == kWordHit || kind[j] == kWordRecompute;
-            if (__any_sync(0xffffffffu, special)) {                                 // rare
-                if (special) emit_special(enc, arena, word_off, ws, w_tile + 32u * j + lane, kind[j], ntok[j], packed[j] & 0x1FFFFFFFu,
-                                          use_compact ? cdst + run[j] : out_ids + base + run[j]);
-            }
-        }
-        if (use_compact && bulk) {
-            fence_proxy_async_smem();                                               // generic-proxy writes -> visible to the async proxy
-            __syncwarp();
-            uint32_t *dsta = out_ids + base - sh;                                   // 16-byte aligned
-            const uint32_t end = sh + total;
-            const uint32_t c0 = sh ? 4u : 0u, c1 = end & ~3u;                       // aligned middle [c0, c1)
-            if (lane == 0 && c1 > c0) { bulk_store_s2g(dsta + c0, compact + c0, (c1 - c0) * 4u); bulk_pending = true; }
-            // head [sh, min(4, end)) on lanes 1..3, tail [max(c1, c0), end) on lanes 4..6
-            if (lane >= 1 && lane < 4) { const uint32_t c = lane; if (sh && c >= sh && c < end) dsta[c] = compact[c]; }
-            else if (lane >= 4 && lane < 7) { const uint32_t c = c1 + (lane - 4); if (c1 >= c0 && c < end) dsta[c] = compact[c]; }
-        } else if (use_compact) {
-            __syncwarp();
-            uint32_t *dsta = out_ids + base - sh;                                   // 16-byte aligned
-            const uint32_t end = sh + total, nvec = (end + 3) >> 2;
-            for (uint32_t v = lane; v < nvec; v += 32) {
-                const uint32_t c = 4 * v;
-                const uint4 q = *reinterpret_cast<const uint4 *>(compact + c);
-                if (c >= sh && c + 4 <= end) *reinterpret_cast<uint4 *>(dsta + c) = q;
-                else {                                                              // first / last vector of the tile
-                    if (c >= sh && c < end) dsta[c] = q.x;
-                    if (c + 1 >= sh && c + 1 < end) dsta[c + 1] = q.y;
-                    if (c + 2 >= sh && c + 2 < end) dsta[c + 2] = q.z;
-                    if (c + 3 < end) dsta[c + 3] = q.w;
-                }
-            }
+        store_hit16_ids<Enc, true>(cdst + run0, n0, a0, b0);
+        store_hit16_ids<Enc, true>(cdst + run1, n1, a1, b1);
+        fence_proxy_async_smem();                                                   // generic-proxy writes -> visible to the async proxy
+        __syncwarp();
+        uint32_t *dsta = out_ids + base - sh;                                       // 16-byte aligned
+        const uint32_t end = sh + total;
+        const uint32_t c0 = sh ? 4u : 0u, c1 = end & ~3u;                           // aligned middle [c0, c1)
+        if (lane == 0 && c1 > c0) { bulk_store_s2g(dsta + c0, compact + c0, (c1 - c0) * 4u); bulk_pending = true; }
+        {   // head [sh, min(4, end)) on lanes 1..3, tail [max(c1, c0), end) on lanes 4..6
+            const uint32_t c = lane < 4 ? lane : c1 + lane - 4;
+            const bool head = lane < 4 && c >= sh && sh != 0, tail = lane >= 4 && lane < 7 && c1 >= c0;
+            if ((head || tail) && c < end) dsta[c] = compact[c];
         }
         __syncwarp();                                            // the compact buffer is reused by the next tile
     }
