@@ -237,6 +237,19 @@ int swt_encode_host16(swt_pipeline *p, int which, const void *table, const uint8
 int swt_tokenize_text_host(swt_pipeline *p, const swt_pretok *pretok, int which, const void *table, const uint8_t *h_text,
                            uint64_t n_bytes, void *h_out_ids, int ids_16bit, uint64_t out_cap, uint64_t *n_tokens,
                            uint64_t *n_words_out, uint64_t *h6_events);
+/* Small calls: ONE short text per call -- the pattern of the reference's CLI, which calls tokenize() once per line
+ * (cli.py:253-264; wordpiece.py:233-270 / bpe.py:245-249 end to end, and the Naive encoders bpe.py:134-158 /
+ * wordpiece.py:160-179 when naive != 0).  The swt_small object owns a pinned, device-mapped input and output buffer, device
+ * scratch and a stream; a call copies the text into the pinned buffer, launches ONE single-CTA kernel (pre-tokenizer +
+ * encoder; no memo, no batching) and synchronises once.  Nothing is allocated per call.  Texts of up to
+ * swt_small_max_bytes() bytes; *ids points into the object's output buffer (u32 ids) and stays valid until the next call.
+ * which / table / pretok as in swt_tokenize_text_host.  n_words / h6_events may be NULL. */
+typedef struct swt_small swt_small;
+int swt_small_create(int device, swt_small **out);
+void swt_small_destroy(swt_small *s);
+uint32_t swt_small_max_bytes(void);
+int swt_tokenize_small(swt_small *s, const swt_pretok *pretok, int which, const void *table, int naive, const uint8_t *text,
+                       uint32_t n_bytes, const uint32_t **ids, uint32_t *n_tokens, uint32_t *n_words, uint32_t *h6_events);
 /* pinned host allocation helpers so integrators can give the pipeline DMA-able buffers */
 int swt_host_alloc(void **ptr, size_t bytes);
 void swt_host_free(void *ptr);

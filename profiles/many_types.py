@@ -1,10 +1,10 @@
-"""Tokenize rate as the number of distinct word types grows (the word-type memo holds at most 2^20 entries): Zipf streams over
-N synthetic types (profiles/train_scale.synth_types), FastWP with the pretrained 20 K vocabulary, ~400 MB per stream."""
+"""Tokenize rate as the number of distinct word types grows (the word-type memo holds at most 2^22 entries): Zipf streams over
+N synthetic types (bench_data.synth_type_table), FastWP with the pretrained 20 K vocabulary, ~400 MB per stream."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np, torch
-import bench, train_scale
+import bench, bench_data as BD
 from subword_tokenizers_b200 import device, packing as P
 from subword_tokenizers_b200.utils import naive_wp_encode_ids
 
@@ -13,8 +13,8 @@ tab = P.WpTables(bench.load_golden("pretrained_wp_vocab.json.gz"))
 wenc = device.WpEncoder(tab, naive_wp_encode_ids("##", tab))
 out = {}
 for n_types in (20_000, 200_000, 2_000_000):
-    types, _ = train_scale.synth_types(n_types, 1)
-    t_arena, t_off = P.pack_words(types)
+    mat, lens_ = BD.synth_type_table(n_types, 1)
+    t_arena, t_off = BD.table_to_utf8(mat, lens_)
     rng = np.random.Generator(np.random.PCG64(2))
     n_words = 45_000_000
     w = 1.0 / np.arange(1, n_types + 1)                              # Zipf(s = 1) over the types

@@ -86,6 +86,11 @@ SIGNATURES = {
                                          c_u64p, c_u64p]),
     "swt_tokenize_text_host": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_uint64, c_vp, ctypes.c_int, ctypes.c_uint64,
                                               c_u64p, c_u64p, c_u64p]),
+    "swt_small_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "swt_small_destroy": (None, [c_vp]),
+    "swt_small_max_bytes": (ctypes.c_uint32, []),
+    "swt_tokenize_small": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_char_p, ctypes.c_uint32, ctypes.POINTER(c_vp),
+                                          c_u32p, c_u32p, c_u32p]),
     "swt_host_alloc": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_size_t]),
     "swt_host_free": (None, [c_vp]),
     "swt_bpe_train_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(TrainConfig)]),

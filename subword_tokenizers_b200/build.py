@@ -44,7 +44,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for s in SOURCES:
         src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s[:-3] + ".o")
         if force or _newer(obj, [src] + hdrs):
-            jobs.append((s, [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]))
+            extra = os.environ.get("SWT_NVCC_EXTRA", "").split()          # experiments: e.g. -DSWT_COUNT_CTAS=3
+            jobs.append((s, [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]))
 
     def run(job):
         name, cmd = job

@@ -30,6 +30,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "pretok.cuh"
 
 namespace swt {
 
@@ -516,8 +517,12 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
         const uint32_t *q = word_off + (size_t)t * kTileWords + lane;
         po[0] = __ldg(q); po[1] = __ldg(q + 1); po[2] = __ldg(q + 32); po[3] = __ldg(q + 33);
     };
-    if (warp_global < n_full) load_offsets(warp_global);
-    for (uint32_t tile = warp_global; tile < ws.n_tiles; tile += n_warps) {
+    // The tile loop holds no calls: when 32 words are pending the warp leaves it, resolves them (flush_pending_words, out of line) and
+    // enters it again, so that nothing of the loop's state (the prefetched offsets) has to survive a call.
+    uint32_t tile = warp_global;
+    while (tile < ws.n_tiles) {
+    if (tile < n_full) load_offsets(tile);
+    for (; tile < ws.n_tiles && n_pend < 32; tile += n_warps) {
         const uint32_t w_tile = tile * kTileWords;
         uint32_t rec[kWordsPerThread] = {0u, 0u}, ntok[kWordsPerThread] = {0u, 0u};
         bool slow[kWordsPerThread] = {false, false}, is_long[kWordsPerThread] = {false, false};
@@ -604,12 +609,11 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
         }
         const uint32_t total = __reduce_add_sync(0xffffffffu, ntok[0] + ntok[1]);
         if (lane == 0) ws.tile_total[tile] = total;
-        if constexpr (Enc::kBatchSlowPath) {
-            __syncwarp();
-            while (n_pend >= 32) { n_pend -= 32; flush_pending(n_pend, 32); }
-        }
     }
-    if constexpr (Enc::kBatchSlowPath) { if (n_pend) flush_pending(0, n_pend); }
+    __syncwarp();
+    while (n_pend >= 32) { n_pend -= 32; flush_pending(n_pend, 32); }
+    }
+    if (n_pend) flush_pending(0, n_pend);
     if (h6) atomicAdd(&status[kStatusH6], h6);
     if (lane == 0 && n_slow_words) atomicAdd(&status[kStatusSlowWords], n_slow_words);
 }
@@ -940,6 +944,129 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
         __syncwarp();                                            // the compact buffer is reused by the next tile
     }
     if (lane == 0 && bulk_pending) bulk_store_wait_read();       // shared memory must stay valid until the last copy has read it
+}
+
+// ---- small calls: ONE CTA pre-tokenizes and encodes one short text (swt_tokenize_small) -------------------------------------------
+// The call pattern of the reference's CLI is one tokenize() per line (cli.py:253-264): a few dozen bytes per call.  The batch kernels
+// above cost a dozen launches, a memo clear and three synchronisations; here a single CTA does everything in one launch:
+//   1. pre-tokenizer (pretok.cuh): one warp per 4 KiB tile counts, thread 0 scans the tile sums, the warps write the lower-cased word
+//      arena + offsets to device scratch.  The text is read from mapped pinned host memory (zero copy).
+//   2. encoder: every word directly, one thread per word, no memo (rank table / trie in L2).  Texts of up to 256 words without a
+//      word longer than kShortBytes keep the ids in the thread and write them straight to `out`; otherwise the ids go through
+//      scratch (ids of word w at scratch[off[w] + w ...]: a word has at most max(bytes, 1) tokens) and a compacted copy.
+//   out (mapped pinned host memory): [0] status code, [1] tokens, [2] H6 events, [3] words, ids from out[8]
+struct SmallArgs {
+    uint8_t *arena; uint32_t *word_off;            // device scratch: lower-cased words of the text, n_words + 1 offsets
+    uint32_t *scratch, *cnt, *compact, *long_buf;  // u32[arena + words + 1], u32[words], u32[tokens + 4], u32[2 * arena + 32] (BPE long words)
+    uint32_t *out; uint32_t out_cap;
+};
+constexpr int kSmallThreads = 256;
+template <class Enc, bool kBert>
+__global__ void __launch_bounds__(kSmallThreads) tokenize_small_kernel(Enc enc, pt::PretokDev t, const uint8_t *__restrict__ text, uint32_t n, SmallArgs a) {
+    __shared__ unsigned long long s_sum[pt::kSmallTiles + 1];
+    __shared__ uint32_t s_status[8], sh_scan[36], s_h6, s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- 1. pre-tokenizer
+    const uint32_t n_tiles = (n + pt::kTileBytes - 1) / pt::kTileBytes;
+    if (tid < 8) s_status[tid] = 0u;
+    if (tid == 0) { s_h6 = 0; s_carry = 0; }
+    __syncthreads();
+    if (warp < n_tiles) { const unsigned long long sum = pt::count_tile<kBert>(t, text, n, warp, s_status); if (lane == 0) s_sum[warp] = sum; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long words = 0, bytes = 0;
+        for (uint32_t k = 0; k < n_tiles; ++k) { const unsigned long long v = s_sum[k]; s_sum[k] = (words << 32) | bytes; words += v >> 32; bytes += v & 0xFFFFFFFFull; }
+        s_status[pt::kPtWords] = (uint32_t)words;
+        a.word_off[words] = (uint32_t)bytes;                                          // closing offset
+    }
+    __syncthreads();
+    if (warp < n_tiles) pt::write_tile<kBert>(t, text, n, warp, s_sum[warp], a.arena, a.word_off, nullptr, s_status);
+    __syncthreads();
+    const uint32_t n_words = s_status[pt::kPtWords];
+    if (s_status[pt::kPtCode] != SWT_OK) { if (tid == 0) { a.out[0] = s_status[pt::kPtCode]; a.out[1] = a.out[2] = a.out[3] = 0; } return; }
+    // ---- 2. encoder
+    uint32_t h6 = 0;
+    if (n_words <= (uint32_t)kSmallThreads) {
+        // one word per thread, ids stay in the thread until their position is known
+        uint32_t buf[kShortBytes];
+        uint32_t b0 = 0, nb = 0, cnt = 0;
+        if (tid < n_words) { b0 = a.word_off[tid]; nb = a.word_off[tid + 1] - b0; }
+        if (!__syncthreads_or(nb > (uint32_t)kShortBytes)) {
+            if (tid < n_words) cnt = enc.encode_short(nullptr, a.arena + b0, nb, buf, h6);
+            if (h6) atomicAdd(&s_h6, h6);
+            uint32_t total;
+            const uint32_t pos = block_exclusive_scan(cnt, sh_scan, &total);
+            if (pos + cnt <= a.out_cap) for (uint32_t k = 0; k < cnt; ++k) a.out[8 + pos + k] = buf[k];
+            if (tid == 0) {
+                a.out[0] = total > a.out_cap ? (uint32_t)SWT_ERR_CAPACITY : (uint32_t)SWT_OK;
+                a.out[1] = total; a.out[2] = s_h6; a.out[3] = n_words;
+            }
+            return;
+        }
+    }
+    // general case.  Words of up to kShortBytes bytes: one thread each
+    for (uint32_t w = tid; w < n_words; w += kSmallThreads) {
+        const uint32_t b0 = a.word_off[w], nb = a.word_off[w + 1] - b0;
+        if (nb > (uint32_t)kShortBytes) continue;
+        uint32_t buf[kShortBytes];
+        const uint32_t c = enc.encode_short(nullptr, a.arena + b0, nb, buf, h6);
+        uint32_t *dst = a.scratch + b0 + w;
+        for (uint32_t k = 0; k < c; ++k) dst[k] = buf[k];
+        a.cnt[w] = c;
+    }
+    // longer words (rare): BPE by a whole warp in the ping-pong buffers, WordPiece by one lane (count, then write)
+    for (uint32_t w = warp; w < n_words; w += kSmallThreads / 32) {
+        const uint32_t b0 = a.word_off[w], nb = a.word_off[w + 1] - b0;
+        if (nb <= (uint32_t)kShortBytes) continue;                                  // warp-uniform
+        uint32_t *dst = a.scratch + b0 + w;
+        if constexpr (Enc::kScratchLong) {
+            uint32_t *res = nullptr, *buf_a = a.long_buf + 2 * (size_t)b0;
+            const uint32_t c = enc.encode_long_warp(a.arena + b0, nb, buf_a, buf_a + nb, &res);
+            for (uint32_t k = lane; k < c; k += 32) dst[k] = res[k];
+            if (lane == 0) a.cnt[w] = c;
+        } else if (lane == 0) {
+            uint32_t dummy = 0;
+            const uint32_t c = enc.long_count(a.arena + b0, nb, h6);
+            enc.long_emit(a.arena + b0, nb, dst, c, dummy);
+            a.cnt[w] = c;
+        }
+    }
+    if (h6) atomicAdd(&s_h6, h6);
+    __syncthreads();
+    // output positions: block scan over the counts, 4 consecutive words per thread and round; then the ids move to their position
+    for (uint32_t w0 = 0; w0 < n_words; w0 += 4 * kSmallThreads) {
+        const uint32_t w = w0 + 4 * tid;
+        uint32_t c[4], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { c[k] = w + k < n_words ? a.cnt[w + k] : 0u; sum += c[k]; }
+        uint32_t total;
+        uint32_t pos = s_carry + block_exclusive_scan(sum, sh_scan, &total);         // (ends with a barrier: s_carry is read before it moves)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (w + k < n_words && pos + c[k] <= a.out_cap) {
+                const uint32_t *src = a.scratch + a.word_off[w + k] + w + k;
+                for (uint32_t i = 0; i < c[k]; ++i) a.compact[pos + i] = src[i];
+            }
+            pos += c[k];
+        }
+        if (tid == 0) s_carry += total;
+        __syncthreads();
+    }
+    const uint32_t n_tokens = s_carry, n_copy = min(n_tokens, a.out_cap);
+    uint4 *o4 = reinterpret_cast<uint4 *>(a.out + 8);
+    const uint4 *c4 = reinterpret_cast<const uint4 *>(a.compact);
+    for (uint32_t v = tid; v < (n_copy + 3) / 4; v += kSmallThreads) o4[v] = c4[v];
+    if (tid == 0) {
+        a.out[0] = n_tokens > a.out_cap ? (uint32_t)SWT_ERR_CAPACITY : (uint32_t)SWT_OK;
+        a.out[1] = n_tokens; a.out[2] = s_h6; a.out[3] = n_words;
+    }
+}
+template <class Enc>
+int launch_tokenize_small(const Enc &enc, const pt::PretokDev &t, bool bert, const uint8_t *d_text, uint32_t n, const SmallArgs &a, cudaStream_t st) {
+    if (bert) tokenize_small_kernel<Enc, true><<<1, kSmallThreads, 0, st>>>(enc, t, d_text, n, a);
+    else tokenize_small_kernel<Enc, false><<<1, kSmallThreads, 0, st>>>(enc, t, d_text, n, a);
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
 }
 
 template <class Enc>

@@ -5,6 +5,7 @@
 // batch k (PCIe is full duplex).  The kernel of batch k is launched once the token total of batch k-1 is
 // known, so that token offsets come out global and ids land compactly in the caller's buffer.
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "encode.cuh"
@@ -13,6 +14,10 @@ struct swt_bpe_table;
 struct swt_wp_trie;
 namespace swt {
 int pretok_mode(const swt_pretok *p);
+uint32_t pretok_small_max_bytes();
+pt::PretokDev pretok_dev_view(const swt_pretok *p);
+int bpe_small_launch(const swt_bpe_table *t, int naive, const pt::PretokDev &pd, bool bert, const uint8_t *d_text, uint32_t n, const SmallArgs &a, cudaStream_t st);
+int wp_small_launch(const swt_wp_trie *t, int naive, const pt::PretokDev &pd, bool bert, const uint8_t *d_text, uint32_t n, const SmallArgs &a, cudaStream_t st);
 int bpe_encode_launch(const swt_bpe_table *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
                       uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off, uint32_t tok_base,
                       void *d_workspace, size_t workspace_bytes, uint32_t *d_status, cudaStream_t st);
@@ -299,5 +304,82 @@ SWT_API int swt_tokenize_text_host(swt_pipeline *p, const swt_pretok *pretok, in
     *n_tokens = total;
     if (n_words_out) *n_words_out = words;
     if (h6_events) *h6_events = h6;
+    return SWT_OK;
+}
+
+// ---- small calls: one short text per call (the per-line tokenize() pattern of the reference's CLI, cli.py:253-264) ----------------------
+// Everything the call needs is owned by the swt_small object: a pinned, device-mapped input and output buffer (zero copy: the
+// kernels read the text from and write the ids to host memory), device scratch, one stream.  A call is a memcpy of the text into
+// the pinned buffer, ONE single-CTA launch (pre-tokenizer + encoder, tokenize_small_kernel) and ONE synchronisation; nothing is allocated.
+struct swt_small {
+    int device;
+    uint32_t max_bytes, out_cap;
+    uint8_t *h_in = nullptr, *d_in = nullptr;        // pinned + mapped: host and device view of the text
+    uint32_t *h_out = nullptr, *d_out = nullptr;     // pinned + mapped: header (8 words) + ids
+    uint8_t *d_blob = nullptr;                       // device scratch
+    uint8_t *d_arena; uint32_t *d_off, *d_scratch, *d_cnt, *d_compact, *d_long;
+    cudaStream_t stream = nullptr;
+};
+
+SWT_API int swt_small_create(int device, swt_small **out) {
+    SWT_REQUIRE(out != nullptr, "out is NULL");
+    SWT_CUDA_OK(cudaSetDevice(device));
+    swt_small *s = new swt_small();
+    s->device = device;
+    s->max_bytes = pretok_small_max_bytes();
+    const size_t arena_cap = (size_t)s->max_bytes * kLowerGrowthNum / kLowerGrowthDen + 64, max_words = s->max_bytes + 1;
+    s->out_cap = (uint32_t)(arena_cap + max_words);
+    Carver sz(nullptr);
+    sz.take<uint8_t>(arena_cap); sz.take<uint32_t>(max_words + 1); sz.take<uint32_t>(s->out_cap + 16); sz.take<uint32_t>(max_words);
+    sz.take<uint32_t>(s->out_cap + 16); sz.take<uint32_t>(2 * arena_cap + 32);
+    cudaError_t e = cudaHostAlloc((void **)&s->h_in, s->max_bytes + 64, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&s->h_out, ((size_t)s->out_cap + 16) * 4, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&s->d_in, s->h_in, 0);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&s->d_out, s->h_out, 0);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_blob, sz.used());
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error(std::string("swt_small_create: ") + cudaGetErrorString(e)); swt_small_destroy(s); return SWT_ERR_CUDA; }
+    Carver cv(s->d_blob);
+    s->d_arena = cv.take<uint8_t>(arena_cap); s->d_off = cv.take<uint32_t>(max_words + 1);
+    s->d_scratch = cv.take<uint32_t>(s->out_cap + 16); s->d_cnt = cv.take<uint32_t>(max_words); s->d_compact = cv.take<uint32_t>(s->out_cap + 16);
+    s->d_long = cv.take<uint32_t>(2 * arena_cap + 32);
+    *out = s;
+    return SWT_OK;
+}
+
+SWT_API void swt_small_destroy(swt_small *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+    cudaFree(s->d_blob);
+    if (s->h_in) cudaFreeHost(s->h_in);
+    if (s->h_out) cudaFreeHost(s->h_out);
+    delete s;
+}
+
+SWT_API uint32_t swt_small_max_bytes(void) { return pretok_small_max_bytes(); }
+
+SWT_API int swt_tokenize_small(swt_small *s, const swt_pretok *pretok, int which, const void *table, int naive, const uint8_t *text, uint32_t n_bytes,
+                               const uint32_t **ids, uint32_t *n_tokens, uint32_t *n_words, uint32_t *h6_events) {
+    SWT_REQUIRE(s && pretok && table && ids && n_tokens, "NULL argument");
+    SWT_REQUIRE(which == 0 || which == 1, "which must be 0 (BPE) or 1 (WP)");
+    SWT_REQUIRE(n_bytes <= s->max_bytes, "text longer than swt_small_max_bytes()");
+    SWT_REQUIRE(n_bytes == 0 || text, "text is NULL");
+    *ids = s->h_out + 8; *n_tokens = 0;
+    if (n_words) *n_words = 0;
+    if (h6_events) *h6_events = 0;
+    if (n_bytes == 0) return SWT_OK;
+    memcpy(s->h_in, text, n_bytes);
+    memset(s->h_in + n_bytes, 0, 16);
+    const SmallArgs a{s->d_arena, s->d_off, s->d_scratch, s->d_cnt, s->d_compact, s->d_long, s->d_out, s->out_cap};
+    const bool bert = swt::pretok_mode(pretok) == SWT_PRETOK_BERT;
+    const int rc = which == 0 ? bpe_small_launch((const swt_bpe_table *)table, naive, pretok_dev_view(pretok), bert, s->d_in, n_bytes, a, s->stream)
+                              : wp_small_launch((const swt_wp_trie *)table, naive, pretok_dev_view(pretok), bert, s->d_in, n_bytes, a, s->stream);
+    if (rc) return rc;
+    SWT_CUDA_OK(cudaStreamSynchronize(s->stream));
+    if (s->h_out[0] != SWT_OK) { set_error("small-call kernels reported status " + std::to_string(s->h_out[0])); return (int)s->h_out[0]; }
+    *n_tokens = s->h_out[1];
+    if (h6_events) *h6_events = s->h_out[2];
+    if (n_words) *n_words = s->h_out[3];
     return SWT_OK;
 }

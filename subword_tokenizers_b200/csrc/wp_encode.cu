@@ -492,6 +492,14 @@ int wp_encode_launch(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_
 }
 }  // namespace swt
 
+namespace swt {
+int wp_small_launch(const swt_wp_trie *t, int naive, const pt::PretokDev &pd, bool bert, const uint8_t *d_text, uint32_t n, const SmallArgs &a, cudaStream_t st) {
+    SWT_REQUIRE(t != nullptr, "NULL trie");
+    if (naive) return launch_tokenize_small(NaiveWpEnc{t->dev}, pd, bert, d_text, n, a, st);
+    return launch_tokenize_small(WpEnc{t->dev}, pd, bert, d_text, n, a, st);
+}
+}  // namespace swt
+
 SWT_API int swt_wp_encode(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
                           uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off,
                           void *d_workspace, size_t workspace_bytes, uint32_t *d_status, void *stream) {

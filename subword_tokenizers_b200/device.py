@@ -50,6 +50,43 @@ def _pipeline_for(device: int, batch_bytes: int):
     return h
 
 
+class SmallCall:
+    """Per-device state of the small-call path (swt_small_*): pinned mapped in/out buffers, device scratch, a stream.  One per process
+    and device, shared by every encoder."""
+
+    _instances = {}
+
+    @classmethod
+    def get(cls, device: Optional[int] = None) -> "SmallCall":
+        device = current_device() if device is None else device
+        inst = cls._instances.get(device)
+        if inst is None:
+            inst = cls._instances[device] = cls(device)
+        return inst
+
+    def __init__(self, device: int):
+        lib = _lib.load()
+        self.handle = c_vp(None)
+        check(lib.swt_small_create(device, ctypes.byref(self.handle)), "swt_small_create")
+        self.max_bytes = int(lib.swt_small_max_bytes())
+        self._fn = lib.swt_tokenize_small
+        self._ids, self._nt, self._h6 = c_vp(None), ctypes.c_uint32(0), ctypes.c_uint32(0)
+        self._refs = (ctypes.byref(self._ids), ctypes.byref(self._nt), ctypes.byref(self._h6))
+        self._view = None                      # numpy view of the pinned output ids (fixed address)
+
+    def tokenize(self, pretok_handle, which: int, table_handle, naive: bool, data: bytes) -> np.ndarray:
+        """-> a COPY of the token ids (u32) of `data` (raw UTF-8 text, at most max_bytes)."""
+        rc = self._fn(self.handle, pretok_handle, which, table_handle, 1 if naive else 0, data, len(data), self._refs[0], self._refs[1], None,
+                      self._refs[2])
+        if rc:
+            check(rc, "swt_tokenize_small")
+        if self._view is None and self._ids.value:
+            cap = (self.max_bytes * 3 // 2 + 64) + self.max_bytes + 1
+            self._view = np.ctypeslib.as_array(ctypes.cast(self._ids, c_u32p), shape=(cap,))
+        n = self._nt.value
+        return self._view[:n].copy() if n else np.zeros(0, np.uint32)
+
+
 class _Encoder:
     """Shared encode plumbing: words -> arena on device -> libswt encode -> token ids (+ offsets)."""
 
@@ -59,6 +96,7 @@ class _Encoder:
 
     def __init__(self):
         self._handle = c_vp(None)
+        self._small_ctx = None
 
     @property
     def _pretok_mode(self) -> int:
@@ -207,6 +245,16 @@ class _Encoder:
         the single C call (swt_tokenize_text_host, three synchronisations); larger ones stay resident (Pretokenizer + encode_device).
         -> token ids u32 (and the u32 token offsets per word when return_offsets)."""
         data = P.encode_utf8(text)
+        if not return_offsets:
+            ctx = self._small_ctx
+            if ctx is None:                    # (small-call state, pre-tokenizer) of this encoder's device, looked up once
+                ctx = self._small_ctx = (SmallCall.get(), Pretokenizer.get(mode=self._pretok_mode))
+            sc, pt = ctx
+            if len(data) <= sc.max_bytes:
+                # one short text (the per-line pattern of the reference's CLI): ONE single-CTA kernel, zero-copy buffers, one sync
+                if not pt._with_sigma and "\u03a3" in text:
+                    pt._create(True)
+                return sc.tokenize(pt._handle, self._which, self._handle, self.naive, data)
         if not return_offsets and not self.naive and len(data) <= self.SMALL_TEXT_BYTES:
             if not data:
                 return np.zeros(0, np.uint32)

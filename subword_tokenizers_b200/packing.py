@@ -285,7 +285,8 @@ class WpTables:
         lut = getattr(self, "_str_lut", None)
         if lut is None:
             lut = self._str_lut = np.array(self.id_to_str, dtype=object)
-        toks = np.asarray(toks, dtype=np.int64)
+        if not isinstance(toks, np.ndarray):
+            toks = np.asarray(toks, dtype=np.int64)
         return lut[toks].tolist() if toks.size else []
 
 

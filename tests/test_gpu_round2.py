@@ -314,3 +314,41 @@ def test_multi_gpu_trainer_matches_single_gpu_and_oracle():
         res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
         assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
         assert "MGPU_TRAIN_OK world=%d" % world in res.stdout
+
+
+# ------------------------------------------------------------------------------------------------ small calls (cli.py:253-264)
+def test_small_call_path_equals_the_batch_path(hf_tokenizer, tmp_path):
+    """swt_tokenize_small (two single-CTA kernels, zero-copy buffers) against the resident batch path and the golden lines: texts
+    around the size limit, words longer than 32 bytes, capital sigma, unknown characters, empty and whitespace-only texts."""
+    from subword_tokenizers_b200 import FastBPE, FastWP, NaiveBPE, NaiveWP
+    from subword_tokenizers_b200.device import SmallCall
+    merges = load_golden("pretrained_bpe_merges.json.gz")
+    vocab = load_golden("pretrained_wp_vocab.json.gz")
+    lines = load_golden("pan_tadeusz.json.gz")
+    rng = np.random.default_rng(5)
+    limit = SmallCall.get().max_bytes
+    texts = ["", " ", "\n\t ", "a", "Litwo! Ojczyzno moja", "ΑΣ ΑΣΑ Σ ΟΔΥΣΣΕΎΣ", "x" * 33 + " " + "y" * 200 + " tail", "a,b.c;d" * 50, "€§ zażółć GĘŚLĄ jaźń İstanbul",
+             "słowo " * ((limit - 8) // 7), ("ab " * (limit // 3))[:limit], ("ab " * (limit // 3))[:limit - 1] + "Z", "q" * limit, " ".join(lines[:40]),
+             "".join(rng.choice(list("abcdeiknorstwyzłó .,-!?'"), size=3000))]
+    for cls, payload in ((FastWP, vocab), (FastBPE, merges), (NaiveWP, vocab), (NaiveBPE, merges[:3000])):
+        tok = cls(hf_tokenizer)
+        if cls in (FastWP, NaiveWP):
+            tok.vocab = set(payload)
+            if cls is FastWP:
+                from subword_tokenizers_b200.utils import WPTrie_E2E
+                tok.vocab_trie = WPTrie_E2E(tok.vocab)
+            enc = tok.vocab_trie.encoder if cls is FastWP else tok._naive_device_encoder()
+        else:
+            tok.merges_list = [tuple(p) for p in payload]
+            if cls is FastBPE:
+                tok._rebuild_ranks()
+                enc = tok._device_encoder()
+            else:
+                enc = tok._naive_device_encoder()
+        for t in texts:
+            data = t.encode()
+            assert len(data) <= limit or cls is not None
+            small = enc.encode_text(t) if len(data) <= limit else None
+            big = enc._encode_text_resident(t)
+            if small is not None:
+                assert np.array_equal(small, big), (cls.__name__, t[:30], len(data))
