@@ -250,6 +250,14 @@ void swt_small_destroy(swt_small *s);
 uint32_t swt_small_max_bytes(void);
 int swt_tokenize_small(swt_small *s, const swt_pretok *pretok, int which, const void *table, int naive, const uint8_t *text,
                        uint32_t n_bytes, const uint32_t **ids, uint32_t *n_tokens, uint32_t *n_words, uint32_t *h6_events);
+/* The same call with the (pre-tokenizer, table) pair bound once (hosts where every argument conversion counts, e.g. ctypes):
+ * swt_tokenize_small_bound takes the text only; the results are read from the output buffer swt_small_output(s):
+ * [0] status, [1] tokens, [2] H6 events, [3] words, u32 ids from word 8.  At most 64 bindings at a time (SWT_ERR_CAPACITY
+ * beyond: use swt_tokenize_small); swt_small_unbind releases one, e.g. before its table is destroyed. */
+int swt_small_bind(swt_small *s, const swt_pretok *pretok, int which, const void *table, int naive, uint32_t *binding);
+void swt_small_unbind(swt_small *s, uint32_t binding);
+const uint32_t *swt_small_output(const swt_small *s);
+int swt_tokenize_small_bound(swt_small *s, uint32_t binding, const uint8_t *text, uint32_t n_bytes);
 /* pinned host allocation helpers so integrators can give the pipeline DMA-able buffers */
 int swt_host_alloc(void **ptr, size_t bytes);
 void swt_host_free(void *ptr);
@@ -344,6 +352,17 @@ int swt_bpe_train_select(swt_bpe_trainer *t, void *stream);
 int swt_bpe_train_merge(swt_bpe_trainer *t, void *stream);
 int swt_bpe_train_update(swt_bpe_trainer *t, void *stream);
 int swt_bpe_train_steps(swt_bpe_trainer *t, uint32_t n_steps, void *stream);
+/* Peer-memory exchange for the sharded trainer (world_size 2..8 GPUs of one box, NVLink / NVSwitch): instead of the caller's two
+ * collectives per step, every rank pushes its tie-break candidate (tie steps only) and its list of touched (symbol, delta) pairs
+ * straight into an inbox of every rank with P2P stores, followed by a flag barrier -- two small kernels inside the step, which
+ * swt_bpe_train_steps then captures into its CUDA graph like the single-rank loop.  Every rank allocates one buffer of
+ * swt_bpe_train_peer_bytes(cfg) bytes that ALL ranks can address (symmetric memory / CUDA IPC), zeroes it, and passes the
+ * world_size device pointers (index = rank) to swt_bpe_train_set_peers after create and before the first step.  The initial
+ * pair counts still go through the caller's all-reduce (once). */
+size_t swt_bpe_train_peer_bytes(const swt_bpe_train_config *cfg);
+int swt_bpe_train_set_peers(swt_bpe_trainer *t, void *const *peer_buffers, uint32_t n_peers);
+int swt_bpe_train_exchange_candidates(swt_bpe_trainer *t, void *stream);
+int swt_bpe_train_exchange_deltas(swt_bpe_trainer *t, void *stream);
 /* synchronises `stream`, copies out the recorded merges (left,right,new ids + chosen pair count)
    and the state; resets the record buffer and clears halt==4. Arrays need record_cap entries. */
 int swt_bpe_train_read(swt_bpe_trainer *t, uint32_t *h_left, uint32_t *h_right, uint32_t *h_new, int64_t *h_count,

@@ -91,6 +91,10 @@ SIGNATURES = {
     "swt_small_max_bytes": (ctypes.c_uint32, []),
     "swt_tokenize_small": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_char_p, ctypes.c_uint32, ctypes.POINTER(c_vp),
                                           c_u32p, c_u32p, c_u32p]),
+    "swt_small_bind": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_vp, ctypes.c_int, c_u32p]),
+    "swt_small_unbind": (None, [c_vp, ctypes.c_uint32]),
+    "swt_small_output": (c_vp, [c_vp]),
+    "swt_tokenize_small_bound": (ctypes.c_int, [c_vp, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32]),
     "swt_host_alloc": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_size_t]),
     "swt_host_free": (None, [c_vp]),
     "swt_bpe_train_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(TrainConfig)]),
@@ -107,6 +111,10 @@ SIGNATURES = {
     "swt_bpe_train_merge": (ctypes.c_int, [c_vp, c_vp]),
     "swt_bpe_train_update": (ctypes.c_int, [c_vp, c_vp]),
     "swt_bpe_train_steps": (ctypes.c_int, [c_vp, ctypes.c_uint32, c_vp]),
+    "swt_bpe_train_peer_bytes": (ctypes.c_size_t, [ctypes.POINTER(TrainConfig)]),
+    "swt_bpe_train_set_peers": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.c_uint32]),
+    "swt_bpe_train_exchange_candidates": (ctypes.c_int, [c_vp, c_vp]),
+    "swt_bpe_train_exchange_deltas": (ctypes.c_int, [c_vp, c_vp]),
     "swt_bpe_train_read": (ctypes.c_int, [c_vp, c_u32p, c_u32p, c_u32p, c_i64p, ctypes.POINTER(TrainState), c_vp]),
     "swt_bpe_train_table_bytes": (ctypes.c_size_t, [ctypes.c_uint64]),
     "swt_bpe_train_grow_table": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint64, c_vp]),

@@ -371,10 +371,11 @@ int bpe_encode_launch(const swt_bpe_table *t, const uint8_t *d_arena, const uint
 }  // namespace swt
 
 namespace swt {
-int bpe_small_launch(const swt_bpe_table *t, int naive, const pt::PretokDev &pd, bool bert, const uint8_t *d_text, uint32_t n, const SmallArgs &a, cudaStream_t st) {
+int bpe_small_launch(const swt_bpe_table *t, int naive, const pt::PretokDev &pd, bool bert, const uint8_t *h_text, const uint8_t *d_text, uint32_t n, const SmallArgs &a,
+                     cudaStream_t st) {
     SWT_REQUIRE(t != nullptr, "NULL table");
-    if (naive) return launch_tokenize_small(NaiveBpeEnc{t->dev}, pd, bert, d_text, n, a, st);
-    return launch_tokenize_small(BpeEnc{t->dev}, pd, bert, d_text, n, a, st);
+    if (naive) return launch_tokenize_small(NaiveBpeEnc{t->dev}, pd, bert, h_text, d_text, n, a, st);
+    return launch_tokenize_small(BpeEnc{t->dev}, pd, bert, h_text, d_text, n, a, st);
 }
 }  // namespace swt
 

@@ -44,7 +44,7 @@ constexpr uint32_t kBlkShift = 8;               // argmax cache, level 1: 256 ta
 constexpr uint32_t kGrpShift = 8;               // level 2: 256 blocks (65,536 slots) per group
 
 enum Halt : uint32_t { kRun = 0, kDoneVocab = 1, kDoneNoPairs = 2, kNeedGrow = 3, kRecordFull = 4,
-                       kErrInternal = 16, kErrCharArena = 17, kErrSymbols = 18, kErrTableFull = 19, kErrScoreRange = 20 };
+                       kErrInternal = 16, kErrCharArena = 17, kErrSymbols = 18, kErrTableFull = 19, kErrScoreRange = 20, kErrPeerTimeout = 21 };
 
 struct PairEntry { uint64_t key; long long count; };
 
@@ -64,8 +64,31 @@ struct TrainState {                 // device resident, mutable
     uint64_t n_tie_steps;                           // steps whose maximum was attained by several pairs (first-occurrence scan needed)
     uint32_t n_tie_keys, n_tie_listed;              // the tied pairs themselves when there are at most kTieKeys of them (else 0); listed steps
     uint64_t tie_keys[32];
+    uint32_t xchg_epoch, pad_xchg;                  // peer exchange: number of cross-GPU barriers passed so far
 };
 constexpr uint32_t kTieKeys = 32;
+
+// ---- peer-memory exchange of the sharded trainer (NVLink / NVSwitch P2P stores, no NCCL call on the per-step path) -----------------
+// Every rank owns one exchange buffer that all ranks map (symmetric memory).  Layout of a buffer:
+//   [0, 256)      u32 flags[kMaxPeers]: flags[s] = number of barriers rank s has reached (written by rank s, read by the owner)
+//   [256, 512)    u64 cand_in[kMaxPeers][2]: tie-break candidate (first position, pair) of every rank
+//   [512, ...)    delta inboxes, two generations (barrier parity) x kMaxPeers source ranks x `stride` u64 words:
+//                 header {n_l, n_r, zz, m}, then n_l + n_r entries {symbol, i64 delta}
+// A rank PUSHES its data into the inbox of every rank (itself included), fences to system scope, raises its flag in every buffer
+// and waits until all flags of its own buffer reached the barrier number.  One barrier per step (two on a tie step).
+constexpr uint32_t kMaxPeers = 8;
+struct PeerXchg {
+    uint32_t enabled, pad;
+    uint64_t stride;                                // u64 words of one source rank's delta inbox
+    uint8_t *base[kMaxPeers];
+};
+__host__ __device__ __forceinline__ uint32_t *px_flags(uint8_t *b) { return reinterpret_cast<uint32_t *>(b); }
+__host__ __device__ __forceinline__ uint64_t *px_cand(uint8_t *b) { return reinterpret_cast<uint64_t *>(b + 256); }
+__host__ __device__ __forceinline__ uint64_t *px_delta(uint8_t *b, uint32_t parity, uint32_t src, uint64_t stride) {
+    return reinterpret_cast<uint64_t *>(b + 512) + ((uint64_t)parity * kMaxPeers + src) * stride;
+}
+static inline uint64_t px_stride(uint32_t vmax) { return 4ull + 4ull * vmax; }       // header + 2 lists of up to vmax entries of 2 words
+static inline size_t px_bytes(uint32_t vmax) { return 512 + 2ull * kMaxPeers * px_stride(vmax) * 8ull; }
 
 struct ArgPart { long long count; uint64_t key; uint32_t n_tied; uint32_t pad; };
 struct DirtyLists { uint32_t *dirty, *dirty_list, *gdirty, *gdirty_list; };
@@ -97,6 +120,7 @@ struct TrainDev {
     uint32_t *rec_left, *rec_right, *rec_new; long long *rec_count;
     uint32_t *sym_len; uint64_t *sym_off, *sym_hash, *sym_pow; uint32_t *chars; uint32_t *str_ht;
     TrainState *st;
+    PeerXchg px;
     __host__ __device__ DirtyLists dl() const { return DirtyLists{dirty, dirty_list, gdirty, gdirty_list}; }
 };
 
@@ -796,6 +820,87 @@ __global__ void __launch_bounds__(256) k_update(TrainDev d) {
     }
 }
 
+// ---- peer exchange kernels ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Cross-GPU barrier number `epoch`, by the lanes of ONE warp after the caller's pushes were fenced: lane p raises this rank's flag in
+// rank p's buffer and waits for rank p's flag in the own buffer.  Bounded spin: a rank that never arrives is an error, not a hang.
+__device__ __forceinline__ bool px_barrier(const TrainDev &d, uint32_t epoch) {
+    const uint32_t lane = threadIdx.x & 31;
+    bool ok = true;
+    if (lane < d.world) {
+        st_release_sys_u32(px_flags(d.px.base[lane]) + d.rank, epoch);
+        const uint32_t *mine = px_flags(d.px.base[d.rank]) + lane;
+        uint32_t spins = 0;
+        while ((int32_t)(ld_acquire_sys_u32(mine) - epoch) < 0) { if (++spins > (1u << 27)) { ok = false; break; } }
+    }
+    return __all_sync(0xffffffffu, ok);
+}
+// tie steps only: every rank learns every rank's candidate (first position of a tied pair in its shard); replaces the all_gather
+__global__ void __launch_bounds__(32) k_xchg_cand(TrainDev d) {
+    TrainState *st = d.st;
+    if (st->halt || st->n_tied <= 1) return;                        // replicated state: all ranks take the same branch
+    const uint32_t lane = threadIdx.x, epoch = st->xchg_epoch + 1;
+    if (lane < d.world) { uint64_t *dst = px_cand(d.px.base[lane]) + 2 * d.rank; dst[0] = d.cand[0]; dst[1] = d.cand[1]; __threadfence_system(); }
+    const bool ok = px_barrier(d, epoch);
+    if (lane == 0) { st->xchg_epoch = epoch; if (!ok) st->halt = kErrPeerTimeout; }
+}
+// every step: this rank's touched (symbol, delta) lists + ZZ / M go to every rank; replaces the all_reduce over 2 * vmax + 2 values
+__global__ void __launch_bounds__(1024) k_xchg_delta(TrainDev d) {
+    TrainState *st = d.st;
+    if (st->halt || !st->cur_valid) return;
+    const uint32_t nl = st->n_touch_l, nr = st->n_touch_r, epoch = st->xchg_epoch + 1, parity = epoch & 1u;
+    long long *L = d.delta, *R = d.delta + d.vmax;
+    for (uint32_t p = 0; p < d.world; ++p) {
+        uint64_t *dst = px_delta(d.px.base[p], parity, d.rank, d.px.stride);
+        for (uint32_t i = threadIdx.x; i < nl + nr; i += blockDim.x) {
+            const uint32_t sym = i < nl ? d.touch_l[i] : d.touch_r[i - nl];
+            dst[4 + 2 * (uint64_t)i] = sym;
+            dst[5 + 2 * (uint64_t)i] = (uint64_t)(i < nl ? L[sym] : R[sym]);
+        }
+        if (threadIdx.x == 0) { dst[0] = nl; dst[1] = nr; dst[2] = (uint64_t)d.delta[2 * (uint64_t)d.vmax]; dst[3] = (uint64_t)d.delta[2 * (uint64_t)d.vmax + 1]; }
+    }
+    __syncthreads();                                                // every read of L / R happened
+    for (uint32_t i = threadIdx.x; i < nl + nr; i += blockDim.x) { if (i < nl) L[d.touch_l[i]] = 0; else R[d.touch_r[i - nl]] = 0; }
+    if (threadIdx.x == 0) { d.delta[2 * (uint64_t)d.vmax] = 0; d.delta[2 * (uint64_t)d.vmax + 1] = 0; }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const bool ok = px_barrier(d, epoch);
+        if (threadIdx.x == 0) { st->xchg_epoch = epoch; if (!ok) st->halt = kErrPeerTimeout; }
+    }
+}
+// update from the inboxes: the lists of all ranks are folded into this rank's replica of the pair table (integer adds commute, so every
+// replica ends up identical)
+__global__ void __launch_bounds__(256) k_update_peer(TrainDev d) {
+    TrainState *st = d.st;
+    if (st->halt || !st->cur_valid) return;
+    const uint64_t a = st->cur_a, b = st->cur_b, z = st->cur_z, cap = st->table_cap;
+    const uint32_t parity = st->xchg_epoch & 1u;                    // the generation the barrier of this step closed
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    long long zz = 0, m = 0;
+    for (uint32_t r = 0; r < d.world; ++r) {
+        const uint64_t *src = px_delta(d.px.base[d.rank], parity, r, d.px.stride);
+        const uint32_t nl = (uint32_t)src[0], nr = (uint32_t)src[1];
+        zz += (long long)src[2]; m += (long long)src[3];
+        for (uint32_t i = gtid; i < 2 * (nl + nr); i += gsz) {      // one table update per thread: the - and the + of an entry are independent
+            const uint32_t e = i >> 1; const bool plus = i & 1u;
+            const uint64_t x = src[4 + 2 * (uint64_t)e]; const long long v = (long long)src[5 + 2 * (uint64_t)e];
+            if (e < nl) table_add(d.table, cap, (x << 32) | (plus ? z : a), plus ? v : -v, st, d.dl());
+            else table_add(d.table, cap, ((plus ? z : b) << 32) | x, plus ? v : -v, st, d.dl());
+        }
+    }
+    if (gtid == 0) {
+        if (zz) { table_add(d.table, cap, (b << 32) | a, -zz, st, d.dl()); table_add(d.table, cap, (z << 32) | z, zz, st, d.dl()); }
+        if (m) table_add(d.table, cap, (a << 32) | b, -m, st, d.dl());
+        if (d.mode == 1) { d.sfreq[a] -= m; d.sfreq[b] -= m; d.sfreq[z] += m; }
+    }
+}
+
 __global__ void k_clear_halt(TrainState *st, uint32_t which, uint32_t reset_records) {
     if (st->halt == which) st->halt = kRun;
     if (reset_records) st->n_recorded = 0;
@@ -1056,21 +1161,53 @@ SWT_API int swt_bpe_train_merge(swt_bpe_trainer *t, void *stream) {
 }
 SWT_API int swt_bpe_train_update(swt_bpe_trainer *t, void *stream) {
     SWT_REQUIRE(t != nullptr, "NULL trainer");
-    const int blocks = t->cfg.world_size == 1 ? 32 : (int)std::min<uint64_t>((t->dev.vmax + 255) / 256, 4096);
     cudaStream_t st = (cudaStream_t)stream;
-    TRAIN_LAUNCH("update", k_update<<<blocks, 256, 0, st>>>(t->dev));
+    if (t->dev.px.enabled) TRAIN_LAUNCH("update_peer", k_update_peer<<<32, 256, 0, st>>>(t->dev));
+    else {
+        const int blocks = t->cfg.world_size == 1 ? 32 : (int)std::min<uint64_t>((t->dev.vmax + 255) / 256, 4096);
+        TRAIN_LAUNCH("update", k_update<<<blocks, 256, 0, st>>>(t->dev));
+    }
     SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}
+// peer exchange (swt_bpe_train_set_peers): the two exchanges of a sharded step as kernels of the step itself
+SWT_API int swt_bpe_train_exchange_candidates(swt_bpe_trainer *t, void *stream) {
+    SWT_REQUIRE(t != nullptr && t->dev.px.enabled, "peer exchange is not set up");
+    cudaStream_t st = (cudaStream_t)stream;
+    TRAIN_LAUNCH("xchg_cand", k_xchg_cand<<<1, 32, 0, st>>>(t->dev));
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}
+SWT_API int swt_bpe_train_exchange_deltas(swt_bpe_trainer *t, void *stream) {
+    SWT_REQUIRE(t != nullptr && t->dev.px.enabled, "peer exchange is not set up");
+    cudaStream_t st = (cudaStream_t)stream;
+    TRAIN_LAUNCH("xchg_delta", k_xchg_delta<<<1, 1024, 0, st>>>(t->dev));
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}
+SWT_API size_t swt_bpe_train_peer_bytes(const swt_bpe_train_config *cfg) { return cfg ? px_bytes(vmax_of(cfg)) : 0; }
+SWT_API int swt_bpe_train_set_peers(swt_bpe_trainer *t, void *const *peer_buffers, uint32_t n_peers) {
+    SWT_REQUIRE(t && peer_buffers, "NULL argument");
+    SWT_REQUIRE(n_peers == t->cfg.world_size && n_peers <= kMaxPeers, "one buffer per rank, at most 8 ranks");
+    for (uint32_t p = 0; p < n_peers; ++p) { SWT_REQUIRE(peer_buffers[p] != nullptr, "NULL peer buffer"); t->dev.px.base[p] = (uint8_t *)peer_buffers[p]; }
+    t->dev.px.stride = px_stride(t->dev.vmax);
+    t->dev.px.enabled = 1;
+    t->dev.cand_gather = px_cand(t->dev.px.base[t->cfg.rank]);       // k_begin_merge reads the candidates of all ranks from the own inbox
+    if (t->step_graph) { cudaGraphExecDestroy(t->step_graph); t->step_graph = nullptr; }
     return SWT_OK;
 }
 static int enqueue_step(swt_bpe_trainer *t, void *stream) {
     int rc = swt_bpe_train_select(t, stream); if (rc) return rc;
+    if (t->dev.px.enabled) { rc = swt_bpe_train_exchange_candidates(t, stream); if (rc) return rc; }
     rc = swt_bpe_train_merge(t, stream); if (rc) return rc;
+    if (t->dev.px.enabled) { rc = swt_bpe_train_exchange_deltas(t, stream); if (rc) return rc; }
     return swt_bpe_train_update(t, stream);
 }
 
 SWT_API int swt_bpe_train_steps(swt_bpe_trainer *t, uint32_t n_steps, void *stream) {
     SWT_REQUIRE(t != nullptr, "NULL trainer");
-    SWT_REQUIRE(t->cfg.world_size == 1, "swt_bpe_train_steps is the single-rank loop; use select/merge/update with collectives");
+    SWT_REQUIRE(t->cfg.world_size == 1 || t->dev.px.enabled, "swt_bpe_train_steps needs the peer exchange when sharded (swt_bpe_train_set_peers); "
+                "otherwise use select/merge/update with collectives");
     cudaStream_t st = (cudaStream_t)stream;
     // The step is launch-bound on small corpora (9 short kernels), so kStepsPerGraph steps are captured into one CUDA
     // graph and replayed; every kernel is self-gating on the halt flag, so replaying past the end is harmless.

@@ -28,6 +28,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "pretok.cuh"
@@ -954,24 +955,40 @@ encode_emit_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *_
 //   2. encoder: every word directly, one thread per word, no memo (rank table / trie in L2).  Texts of up to 256 words without a
 //      word longer than kShortBytes keep the ids in the thread and write them straight to `out`; otherwise the ids go through
 //      scratch (ids of word w at scratch[off[w] + w ...]: a word has at most max(bytes, 1) tokens) and a compacted copy.
-//   out (mapped pinned host memory): [0] status code, [1] tokens, [2] H6 events, [3] words, ids from out[8]
+//   out (mapped pinned host memory): [0] status code, [1] tokens, [2] H6 events, [3] words, [4] sequence number of the call (the
+//   completion flag), [5..7] SM cycles from kernel start to the end of the pre-tokenizer / the encoder / the id stores, ids from out[8]
 struct SmallArgs {
     uint8_t *arena; uint32_t *word_off;            // device scratch: lower-cased words of the text, n_words + 1 offsets
     uint32_t *scratch, *cnt, *compact, *long_buf;  // u32[arena + words + 1], u32[words], u32[tokens + 4], u32[2 * arena + 32] (BPE long words)
     uint32_t *out; uint32_t out_cap;
+    uint32_t seq;                                  // written to out[4] LAST (system-scope fence before it): the host polls this word
 };
 constexpr int kSmallThreads = 256;
-template <class Enc, bool kBert>
-__global__ void __launch_bounds__(kSmallThreads) tokenize_small_kernel(Enc enc, pt::PretokDev t, const uint8_t *__restrict__ text, uint32_t n, SmallArgs a) {
+// texts of up to kInlineTextBytes travel in the kernel's parameter buffer (no read over PCIe at all)
+constexpr uint32_t kInlineTextBytes = 240;
+struct InlineText { uint4 v[kInlineTextBytes / 16 + 1]; };
+template <class Enc, bool kBert, bool kInline>
+__global__ void __launch_bounds__(kSmallThreads) tokenize_small_kernel(Enc enc, pt::PretokDev t, const uint8_t *__restrict__ text, InlineText inl, uint32_t n,
+                                                                       SmallArgs a) {
     __shared__ unsigned long long s_sum[pt::kSmallTiles + 1];
     __shared__ uint32_t s_status[8], sh_scan[36], s_h6, s_carry;
+    __shared__ __align__(16) uint8_t s_text[pt::kSmallTiles * pt::kTileBytes + 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long clk0 = clock64();                               // diagnostic: SM cycles of the phases go to out[5..7]
     // ---- 1. pre-tokenizer
     const uint32_t n_tiles = (n + pt::kTileBytes - 1) / pt::kTileBytes;
     if (tid < 8) s_status[tid] = 0u;
     if (tid == 0) { s_h6 = 0; s_carry = 0; }
     __syncthreads();
-    if (warp < n_tiles) { const unsigned long long sum = pt::count_tile<kBert>(t, text, n, warp, s_status); if (lane == 0) s_sum[warp] = sum; }
+    // the text is read ONCE from (mapped host) memory into shared memory; both passes of the pre-tokenizer run on that copy
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(text);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_text);
+        if constexpr (kInline) { if (tid < sizeof(InlineText) / 16) dst[tid] = inl.v[tid]; }
+        else for (uint32_t v = tid; v < (n + 16 + 15) / 16; v += kSmallThreads) dst[v] = __ldg(src + v);  // (+16: the zero padding behind the text)
+    }
+    __syncthreads();
+    if (warp < n_tiles) { const unsigned long long sum = pt::count_tile<kBert, false>(t, s_text, n, warp, s_status); if (lane == 0) s_sum[warp] = sum; }
     __syncthreads();
     if (tid == 0) {
         unsigned long long words = 0, bytes = 0;
@@ -980,10 +997,23 @@ __global__ void __launch_bounds__(kSmallThreads) tokenize_small_kernel(Enc enc, 
         a.word_off[words] = (uint32_t)bytes;                                          // closing offset
     }
     __syncthreads();
-    if (warp < n_tiles) pt::write_tile<kBert>(t, text, n, warp, s_sum[warp], a.arena, a.word_off, nullptr, s_status);
+    if (warp < n_tiles) pt::write_tile<kBert, false>(t, s_text, n, warp, s_sum[warp], a.arena, a.word_off, nullptr, s_status);
     __syncthreads();
     const uint32_t n_words = s_status[pt::kPtWords];
-    if (s_status[pt::kPtCode] != SWT_OK) { if (tid == 0) { a.out[0] = s_status[pt::kPtCode]; a.out[1] = a.out[2] = a.out[3] = 0; } return; }
+    const uint32_t clk_pretok = (uint32_t)(clock64() - clk0);
+    // header + completion flag: every id store of the CTA is fenced to system scope before the flag is written
+    auto finish = [&](uint32_t code, uint32_t n_tokens, uint32_t n_h6) {
+        const uint32_t clk_encode = (uint32_t)(clock64() - clk0);
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            a.out[0] = code; a.out[1] = n_tokens; a.out[2] = n_h6; a.out[3] = n_words;
+            a.out[5] = clk_pretok; a.out[6] = clk_encode; a.out[7] = (uint32_t)(clock64() - clk0);
+            __threadfence_system();
+            *(volatile uint32_t *)(a.out + 4) = a.seq;
+        }
+    };
+    if (s_status[pt::kPtCode] != SWT_OK) { finish(s_status[pt::kPtCode], 0u, 0u); return; }
     // ---- 2. encoder
     uint32_t h6 = 0;
     if (n_words <= (uint32_t)kSmallThreads) {
@@ -997,10 +1027,7 @@ __global__ void __launch_bounds__(kSmallThreads) tokenize_small_kernel(Enc enc, 
             uint32_t total;
             const uint32_t pos = block_exclusive_scan(cnt, sh_scan, &total);
             if (pos + cnt <= a.out_cap) for (uint32_t k = 0; k < cnt; ++k) a.out[8 + pos + k] = buf[k];
-            if (tid == 0) {
-                a.out[0] = total > a.out_cap ? (uint32_t)SWT_ERR_CAPACITY : (uint32_t)SWT_OK;
-                a.out[1] = total; a.out[2] = s_h6; a.out[3] = n_words;
-            }
+            finish(total > a.out_cap ? (uint32_t)SWT_ERR_CAPACITY : (uint32_t)SWT_OK, total, s_h6);
             return;
         }
     }
@@ -1056,15 +1083,22 @@ __global__ void __launch_bounds__(kSmallThreads) tokenize_small_kernel(Enc enc, 
     uint4 *o4 = reinterpret_cast<uint4 *>(a.out + 8);
     const uint4 *c4 = reinterpret_cast<const uint4 *>(a.compact);
     for (uint32_t v = tid; v < (n_copy + 3) / 4; v += kSmallThreads) o4[v] = c4[v];
-    if (tid == 0) {
-        a.out[0] = n_tokens > a.out_cap ? (uint32_t)SWT_ERR_CAPACITY : (uint32_t)SWT_OK;
-        a.out[1] = n_tokens; a.out[2] = s_h6; a.out[3] = n_words;
-    }
+    finish(n_tokens > a.out_cap ? (uint32_t)SWT_ERR_CAPACITY : (uint32_t)SWT_OK, n_tokens, s_h6);
 }
 template <class Enc>
-int launch_tokenize_small(const Enc &enc, const pt::PretokDev &t, bool bert, const uint8_t *d_text, uint32_t n, const SmallArgs &a, cudaStream_t st) {
-    if (bert) tokenize_small_kernel<Enc, true><<<1, kSmallThreads, 0, st>>>(enc, t, d_text, n, a);
-    else tokenize_small_kernel<Enc, false><<<1, kSmallThreads, 0, st>>>(enc, t, d_text, n, a);
+int launch_tokenize_small(const Enc &enc, const pt::PretokDev &t, bool bert, const uint8_t *h_text, const uint8_t *d_text, uint32_t n, const SmallArgs &a,
+                          cudaStream_t st) {
+    if (n <= kInlineTextBytes) {                       // the text rides in the parameter buffer
+        InlineText inl;
+        memset(&inl, 0, sizeof(inl));
+        memcpy(&inl, h_text, n);
+        if (bert) tokenize_small_kernel<Enc, true, true><<<1, kSmallThreads, 0, st>>>(enc, t, nullptr, inl, n, a);
+        else tokenize_small_kernel<Enc, false, true><<<1, kSmallThreads, 0, st>>>(enc, t, nullptr, inl, n, a);
+    } else {
+        const InlineText none{};
+        if (bert) tokenize_small_kernel<Enc, true, false><<<1, kSmallThreads, 0, st>>>(enc, t, d_text, none, n, a);
+        else tokenize_small_kernel<Enc, false, false><<<1, kSmallThreads, 0, st>>>(enc, t, d_text, none, n, a);
+    }
     SWT_CUDA_OK(cudaGetLastError());
     return SWT_OK;
 }

@@ -16,8 +16,10 @@ namespace swt {
 int pretok_mode(const swt_pretok *p);
 uint32_t pretok_small_max_bytes();
 pt::PretokDev pretok_dev_view(const swt_pretok *p);
-int bpe_small_launch(const swt_bpe_table *t, int naive, const pt::PretokDev &pd, bool bert, const uint8_t *d_text, uint32_t n, const SmallArgs &a, cudaStream_t st);
-int wp_small_launch(const swt_wp_trie *t, int naive, const pt::PretokDev &pd, bool bert, const uint8_t *d_text, uint32_t n, const SmallArgs &a, cudaStream_t st);
+int bpe_small_launch(const swt_bpe_table *t, int naive, const pt::PretokDev &pd, bool bert, const uint8_t *h_text, const uint8_t *d_text, uint32_t n,
+                     const SmallArgs &a, cudaStream_t st);
+int wp_small_launch(const swt_wp_trie *t, int naive, const pt::PretokDev &pd, bool bert, const uint8_t *h_text, const uint8_t *d_text, uint32_t n,
+                     const SmallArgs &a, cudaStream_t st);
 int bpe_encode_launch(const swt_bpe_table *t, const uint8_t *d_arena, const uint32_t *d_word_off, uint32_t n_words,
                       uint64_t long_word_bytes, uint32_t *d_out_ids, uint64_t out_cap, uint32_t *d_out_tok_off, uint32_t tok_base,
                       void *d_workspace, size_t workspace_bytes, uint32_t *d_status, cudaStream_t st);
@@ -319,6 +321,10 @@ struct swt_small {
     uint8_t *d_blob = nullptr;                       // device scratch
     uint8_t *d_arena; uint32_t *d_off, *d_scratch, *d_cnt, *d_compact, *d_long;
     cudaStream_t stream = nullptr;
+    uint32_t seq = 0;                                // sequence number of the last call (completion flag)
+    struct Bound { const swt_pretok *pretok; const void *table; int which, naive; };
+    static constexpr uint32_t kMaxBound = 64;
+    Bound bound[kMaxBound]; uint32_t n_bound = 0;
 };
 
 SWT_API int swt_small_create(int device, swt_small **out) {
@@ -343,6 +349,7 @@ SWT_API int swt_small_create(int device, swt_small **out) {
     s->d_arena = cv.take<uint8_t>(arena_cap); s->d_off = cv.take<uint32_t>(max_words + 1);
     s->d_scratch = cv.take<uint32_t>(s->out_cap + 16); s->d_cnt = cv.take<uint32_t>(max_words); s->d_compact = cv.take<uint32_t>(s->out_cap + 16);
     s->d_long = cv.take<uint32_t>(2 * arena_cap + 32);
+    memset(s->h_out, 0, 64);
     *out = s;
     return SWT_OK;
 }
@@ -359,6 +366,35 @@ SWT_API void swt_small_destroy(swt_small *s) {
 
 SWT_API uint32_t swt_small_max_bytes(void) { return pretok_small_max_bytes(); }
 
+// One call: memcpy of the text into the pinned buffer, one launch, then the host polls the completion flag the kernel writes last
+// (out[4] = sequence number of the call; cheaper than a stream synchronisation); a stream query every few thousand polls catches a
+// failed launch.
+static int small_run(swt_small *s, const swt_pretok *pretok, int which, const void *table, int naive, const uint8_t *text, uint32_t n_bytes) {
+    s->h_out[1] = 0;
+    if (n_bytes == 0) { s->h_out[0] = SWT_OK; s->h_out[2] = s->h_out[3] = 0; return SWT_OK; }
+    if (n_bytes > kInlineTextBytes) {                  // shorter texts ride in the kernel's parameter buffer
+        memcpy(s->h_in, text, n_bytes);
+        memset(s->h_in + n_bytes, 0, 16);
+    }
+    const uint32_t seq = ++s->seq;
+    const SmallArgs a{s->d_arena, s->d_off, s->d_scratch, s->d_cnt, s->d_compact, s->d_long, s->d_out, s->out_cap, seq};
+    const bool bert = swt::pretok_mode(pretok) == SWT_PRETOK_BERT;
+    const int rc = which == 0 ? bpe_small_launch((const swt_bpe_table *)table, naive, pretok_dev_view(pretok), bert, text, s->d_in, n_bytes, a, s->stream)
+                              : wp_small_launch((const swt_wp_trie *)table, naive, pretok_dev_view(pretok), bert, text, s->d_in, n_bytes, a, s->stream);
+    if (rc) return rc;
+    volatile uint32_t *flag = s->h_out + 4;
+    for (uint32_t spins = 0; *flag != seq; ++spins) {
+        if ((spins & 0xFFFu) == 0xFFFu) {
+            const cudaError_t e = cudaStreamQuery(s->stream);
+            if (e == cudaSuccess) break;                                             // finished: the flag is (about to be) visible
+            if (e != cudaErrorNotReady) { set_error(std::string("small-call kernel: ") + cudaGetErrorString(e)); return SWT_ERR_CUDA; }
+        }
+    }
+    if (*flag != seq) SWT_CUDA_OK(cudaStreamSynchronize(s->stream));
+    if (s->h_out[0] != SWT_OK) { set_error("small-call kernel reported status " + std::to_string(s->h_out[0])); return (int)s->h_out[0]; }
+    return SWT_OK;
+}
+
 SWT_API int swt_tokenize_small(swt_small *s, const swt_pretok *pretok, int which, const void *table, int naive, const uint8_t *text, uint32_t n_bytes,
                                const uint32_t **ids, uint32_t *n_tokens, uint32_t *n_words, uint32_t *h6_events) {
     SWT_REQUIRE(s && pretok && table && ids && n_tokens, "NULL argument");
@@ -368,18 +404,37 @@ SWT_API int swt_tokenize_small(swt_small *s, const swt_pretok *pretok, int which
     *ids = s->h_out + 8; *n_tokens = 0;
     if (n_words) *n_words = 0;
     if (h6_events) *h6_events = 0;
-    if (n_bytes == 0) return SWT_OK;
-    memcpy(s->h_in, text, n_bytes);
-    memset(s->h_in + n_bytes, 0, 16);
-    const SmallArgs a{s->d_arena, s->d_off, s->d_scratch, s->d_cnt, s->d_compact, s->d_long, s->d_out, s->out_cap};
-    const bool bert = swt::pretok_mode(pretok) == SWT_PRETOK_BERT;
-    const int rc = which == 0 ? bpe_small_launch((const swt_bpe_table *)table, naive, pretok_dev_view(pretok), bert, s->d_in, n_bytes, a, s->stream)
-                              : wp_small_launch((const swt_wp_trie *)table, naive, pretok_dev_view(pretok), bert, s->d_in, n_bytes, a, s->stream);
+    const int rc = small_run(s, pretok, which, table, naive, text, n_bytes);
     if (rc) return rc;
-    SWT_CUDA_OK(cudaStreamSynchronize(s->stream));
-    if (s->h_out[0] != SWT_OK) { set_error("small-call kernels reported status " + std::to_string(s->h_out[0])); return (int)s->h_out[0]; }
     *n_tokens = s->h_out[1];
     if (h6_events) *h6_events = s->h_out[2];
     if (n_words) *n_words = s->h_out[3];
     return SWT_OK;
+}
+
+// The same call for hosts where every argument conversion counts (ctypes): the (pre-tokenizer, table) pair is bound once, the call
+// takes the text only and the results are read from the output buffer (swt_small_output: [0] status, [1] tokens, [2] H6 events,
+// [3] words, ids from word 8).
+SWT_API int swt_small_bind(swt_small *s, const swt_pretok *pretok, int which, const void *table, int naive, uint32_t *binding) {
+    SWT_REQUIRE(s && pretok && table && binding, "NULL argument");
+    SWT_REQUIRE(which == 0 || which == 1, "which must be 0 (BPE) or 1 (WP)");
+    for (uint32_t k = 0; k < s->n_bound; ++k)
+        if (s->bound[k].pretok == pretok && s->bound[k].table == table && s->bound[k].which == which && s->bound[k].naive == naive) { *binding = k; return SWT_OK; }
+    uint32_t k = 0;
+    while (k < s->n_bound && s->bound[k].table != nullptr) ++k;                     // first free slot
+    if (k == swt_small::kMaxBound) { set_error("swt_small_bind: all bindings in use (swt_small_unbind the ones of destroyed tables)"); return SWT_ERR_CAPACITY; }
+    if (k == s->n_bound) ++s->n_bound;
+    s->bound[k] = {pretok, table, which, naive};
+    *binding = k;
+    return SWT_OK;
+}
+SWT_API void swt_small_unbind(swt_small *s, uint32_t binding) {
+    if (s && binding < s->n_bound) s->bound[binding] = {nullptr, nullptr, 0, 0};
+}
+SWT_API const uint32_t *swt_small_output(const swt_small *s) { return s ? s->h_out : nullptr; }
+SWT_API int swt_tokenize_small_bound(swt_small *s, uint32_t binding, const uint8_t *text, uint32_t n_bytes) {
+    SWT_REQUIRE(s && binding < s->n_bound && s->bound[binding].table != nullptr, "unknown binding");
+    SWT_REQUIRE(n_bytes <= s->max_bytes, "text longer than swt_small_max_bytes()");
+    const auto &b = s->bound[binding];
+    return small_run(s, b.pretok, b.which, b.table, b.naive, text, n_bytes);
 }

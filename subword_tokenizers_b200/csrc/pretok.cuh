@@ -230,9 +230,13 @@ __device__ __forceinline__ void emit(const PretokDev &t, const uint8_t *text, ui
     }
 }
 
+// text loads: read-only path for text in global memory (kLdg), plain loads when the tile functions run on a copy in shared memory
+template <bool kLdg> __device__ __forceinline__ uint32_t ld_text32(const uint32_t *p) { if constexpr (kLdg) return __ldg(p); else return *p; }
+template <bool kLdg> __device__ __forceinline__ uint4 ld_text128(const uint4 *p) { if constexpr (kLdg) return __ldg(p); else return *p; }
+
 // count pass over one 4 KiB tile by one warp: a lane owns 16 consecutive bytes per step (one 128-bit load, 512 bytes per warp step);
 // the words before and after them come from the neighbour lanes.  Returns (words << 32) | bytes of the tile on every lane.
-template <bool kBert>
+template <bool kBert, bool kLdg = true>
 __device__ __forceinline__ unsigned long long count_tile(const PretokDev &t, const uint8_t *__restrict__ text, uint64_t n, uint32_t tile, uint32_t *status) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t *t32 = reinterpret_cast<const uint32_t *>(text);
@@ -243,14 +247,14 @@ __device__ __forceinline__ unsigned long long count_tile(const PretokDev &t, con
         if (step0 >= n) break;                                              // warp-uniform
         const uint64_t i = step0 + lane * 16, wi = i >> 2;
         uint4 q;
-        if (wi + 4 <= n_words32) q = __ldg(reinterpret_cast<const uint4 *>(t32 + wi));
+        if (wi + 4 <= n_words32) q = ld_text128<kLdg>(reinterpret_cast<const uint4 *>(t32 + wi));
         else {
-            q.x = wi < n_words32 ? __ldg(t32 + wi) : 0u; q.y = wi + 1 < n_words32 ? __ldg(t32 + wi + 1) : 0u;
-            q.z = wi + 2 < n_words32 ? __ldg(t32 + wi + 2) : 0u; q.w = 0u;
+            q.x = wi < n_words32 ? ld_text32<kLdg>(t32 + wi) : 0u; q.y = wi + 1 < n_words32 ? ld_text32<kLdg>(t32 + wi + 1) : 0u;
+            q.z = wi + 2 < n_words32 ? ld_text32<kLdg>(t32 + wi + 2) : 0u; q.w = 0u;
         }
         uint32_t w_prev = __shfl_up_sync(0xffffffffu, q.w, 1), w_next = __shfl_down_sync(0xffffffffu, q.x, 1);
-        if (lane == 0) w_prev = wi >= 1 ? __ldg(t32 + wi - 1) : 0u;
-        if (lane == 31) w_next = wi + 4 < n_words32 ? __ldg(t32 + wi + 4) : 0u;
+        if (lane == 0) w_prev = wi >= 1 ? ld_text32<kLdg>(t32 + wi - 1) : 0u;
+        if (lane == 31) w_next = wi + 4 < n_words32 ? ld_text32<kLdg>(t32 + wi + 4) : 0u;
         const uint32_t mine = analyze<kBert>(t, text, n, i, w_prev, q.x, q.y, status).mine + analyze<kBert>(t, text, n, i + 4, q.x, q.y, q.z, status).mine +
                               analyze<kBert>(t, text, n, i + 8, q.y, q.z, q.w, status).mine + analyze<kBert>(t, text, n, i + 12, q.z, q.w, w_next, status).mine;
         tile_words += mine >> 16; tile_bytes += mine & 0xFFFFu;
@@ -266,7 +270,7 @@ __device__ __forceinline__ unsigned long long count_tile(const PretokDev &t, con
 // write pass over one tile by one warp, from the tile's output position `base` = (first word << 32) | first byte: a lane owns 4
 // consecutive bytes per step (128 bytes per warp step), so that the byte stores of a warp land in one contiguous run; the loads of
 // four steps are issued together
-template <bool kBert>
+template <bool kBert, bool kLdg = true>
 __device__ __forceinline__ void write_tile(const PretokDev &t, const uint8_t *__restrict__ text, uint64_t n, uint32_t tile, unsigned long long base,
                                            uint8_t *__restrict__ arena, uint32_t *__restrict__ word_off, uint32_t *__restrict__ word_src, uint32_t *status) {
     const uint32_t lane = threadIdx.x & 31;
@@ -279,9 +283,9 @@ __device__ __forceinline__ void write_tile(const PretokDev &t, const uint8_t *__
         uint32_t wq[6];                                                     // words lane-1 .. of the four steps: wq[k+1] = step k
         const uint64_t wi0 = (blk0 >> 2) + lane;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) wq[k + 1] = wi0 + 32 * k < n_words32 ? __ldg(t32 + wi0 + 32 * k) : 0u;
-        wq[0] = (lane == 0 && wi0 >= 1) ? __ldg(t32 + wi0 - 1) : 0u;
-        wq[5] = (lane == 31 && wi0 + 97 < n_words32) ? __ldg(t32 + wi0 + 97) : 0u;
+        for (int k = 0; k < 4; ++k) wq[k + 1] = wi0 + 32 * k < n_words32 ? ld_text32<kLdg>(t32 + wi0 + 32 * k) : 0u;
+        wq[0] = (lane == 0 && wi0 >= 1) ? ld_text32<kLdg>(t32 + wi0 - 1) : 0u;
+        wq[5] = (lane == 31 && wi0 + 97 < n_words32) ? ld_text32<kLdg>(t32 + wi0 + 97) : 0u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint64_t step0 = blk0 + 128 * k;

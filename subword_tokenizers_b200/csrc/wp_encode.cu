@@ -57,6 +57,9 @@ __device__ __forceinline__ uint32_t wp_edge(const WpTrieDev &t, uint32_t node, u
     }
 }
 __device__ __forceinline__ bool wp_alnum(const WpTrieDev &t, uint32_t cp) {
+    // ASCII without a table access (str.isalnum of an ASCII character: 0-9, A-Z, a-z): the bitmap load would sit on the dependent chain
+    // of every character of the trie walk
+    if (cp < 0x80u) return (cp - 0x30u) < 10u || ((cp | 0x20u) - 0x61u) < 26u;
     return cp < 0x110000u && ((__ldg(&t.alnum[cp >> 5]) >> (cp & 31u)) & 1u);
 }
 
@@ -493,10 +496,11 @@ int wp_encode_launch(const swt_wp_trie *t, const uint8_t *d_arena, const uint32_
 }  // namespace swt
 
 namespace swt {
-int wp_small_launch(const swt_wp_trie *t, int naive, const pt::PretokDev &pd, bool bert, const uint8_t *d_text, uint32_t n, const SmallArgs &a, cudaStream_t st) {
+int wp_small_launch(const swt_wp_trie *t, int naive, const pt::PretokDev &pd, bool bert, const uint8_t *h_text, const uint8_t *d_text, uint32_t n, const SmallArgs &a,
+                     cudaStream_t st) {
     SWT_REQUIRE(t != nullptr, "NULL trie");
-    if (naive) return launch_tokenize_small(NaiveWpEnc{t->dev}, pd, bert, d_text, n, a, st);
-    return launch_tokenize_small(WpEnc{t->dev}, pd, bert, d_text, n, a, st);
+    if (naive) return launch_tokenize_small(NaiveWpEnc{t->dev}, pd, bert, h_text, d_text, n, a, st);
+    return launch_tokenize_small(WpEnc{t->dev}, pd, bert, h_text, d_text, n, a, st);
 }
 }  // namespace swt
 

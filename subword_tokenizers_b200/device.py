@@ -66,25 +66,40 @@ class SmallCall:
 
     def __init__(self, device: int):
         lib = _lib.load()
+        self.lib = lib
         self.handle = c_vp(None)
         check(lib.swt_small_create(device, ctypes.byref(self.handle)), "swt_small_create")
         self.max_bytes = int(lib.swt_small_max_bytes())
-        self._fn = lib.swt_tokenize_small
-        self._ids, self._nt, self._h6 = c_vp(None), ctypes.c_uint32(0), ctypes.c_uint32(0)
-        self._refs = (ctypes.byref(self._ids), ctypes.byref(self._nt), ctypes.byref(self._h6))
-        self._view = None                      # numpy view of the pinned output ids (fixed address)
+        self._fn = lib.swt_tokenize_small_bound
+        cap = (self.max_bytes * 3 // 2 + 64) + self.max_bytes + 1
+        out = lib.swt_small_output(self.handle)
+        # numpy view of the pinned output buffer (fixed address): header words 0..7, then the ids
+        self._out = np.ctypeslib.as_array(ctypes.cast(out, c_u32p), shape=(cap + 8,))
+        self._ids = self._out[8:]
 
-    def tokenize(self, pretok_handle, which: int, table_handle, naive: bool, data: bytes) -> np.ndarray:
+    def bind(self, pretok_handle, which: int, table_handle, naive: bool):
+        """Binds a (pre-tokenizer, table) pair once; tokenize() then passes the text only.  -> binding index, or the argument tuple of
+        the unbound call when all bindings are in use."""
+        k = ctypes.c_uint32(0)
+        if self.lib.swt_small_bind(self.handle, pretok_handle, which, table_handle, 1 if naive else 0, ctypes.byref(k)) != 0:
+            return (pretok_handle, which, table_handle, 1 if naive else 0)
+        return int(k.value)
+
+    def unbind(self, binding) -> None:
+        if isinstance(binding, int):
+            self.lib.swt_small_unbind(self.handle, binding)
+
+    def tokenize(self, binding: int, data: bytes) -> np.ndarray:
         """-> a COPY of the token ids (u32) of `data` (raw UTF-8 text, at most max_bytes)."""
-        rc = self._fn(self.handle, pretok_handle, which, table_handle, 1 if naive else 0, data, len(data), self._refs[0], self._refs[1], None,
-                      self._refs[2])
+        if isinstance(binding, int):
+            rc = self._fn(self.handle, binding, data, len(data))
+        else:
+            ids, nt = c_vp(None), ctypes.c_uint32(0)
+            rc = self.lib.swt_tokenize_small(self.handle, binding[0], binding[1], binding[2], binding[3], data, len(data), ctypes.byref(ids),
+                                             ctypes.byref(nt), None, None)
         if rc:
             check(rc, "swt_tokenize_small")
-        if self._view is None and self._ids.value:
-            cap = (self.max_bytes * 3 // 2 + 64) + self.max_bytes + 1
-            self._view = np.ctypeslib.as_array(ctypes.cast(self._ids, c_u32p), shape=(cap,))
-        n = self._nt.value
-        return self._view[:n].copy() if n else np.zeros(0, np.uint32)
+        return self._ids[:int(self._out[1])].copy()
 
 
 class _Encoder:
@@ -247,14 +262,21 @@ class _Encoder:
         data = P.encode_utf8(text)
         if not return_offsets:
             ctx = self._small_ctx
-            if ctx is None:                    # (small-call state, pre-tokenizer) of this encoder's device, looked up once
-                ctx = self._small_ctx = (SmallCall.get(), Pretokenizer.get(mode=self._pretok_mode))
-            sc, pt = ctx
+            if ctx is not None and ctx[2] != ctx[1]._handle.value:
+                ctx[0].unbind(ctx[3])
+                ctx = None
+            if ctx is None:
+                # (small-call state, pre-tokenizer, its handle, binding) of this encoder's device, set up once (and again when
+                # the pre-tokenizer was re-created with the sigma bitmaps)
+                sc, pt = SmallCall.get(), Pretokenizer.get(mode=self._pretok_mode)
+                ctx = self._small_ctx = (sc, pt, pt._handle.value, sc.bind(pt._handle, self._which, self._handle, self.naive))
+            sc = ctx[0]
             if len(data) <= sc.max_bytes:
-                # one short text (the per-line pattern of the reference's CLI): ONE single-CTA kernel, zero-copy buffers, one sync
-                if not pt._with_sigma and "\u03a3" in text:
-                    pt._create(True)
-                return sc.tokenize(pt._handle, self._which, self._handle, self.naive, data)
+                # one short text (the per-line pattern of the reference's CLI): ONE single-CTA kernel, zero-copy buffers, no stream sync
+                if not ctx[1]._with_sigma and "\u03a3" in text:
+                    ctx[1]._create(True)
+                    return self.encode_text(text)
+                return sc.tokenize(ctx[3], data)
         if not return_offsets and not self.naive and len(data) <= self.SMALL_TEXT_BYTES:
             if not data:
                 return np.zeros(0, np.uint32)
@@ -265,6 +287,9 @@ class _Encoder:
         return self._encode_text_resident(text, return_offsets)
 
     def close(self):
+        ctx, self._small_ctx = self._small_ctx, None
+        if ctx is not None:
+            ctx[0].unbind(ctx[3])              # the small-call binding points at the table about to be destroyed
         self._destroy()
 
     def _destroy(self):
@@ -598,6 +623,39 @@ class CudaTrainEngine:
     def _sp(self) -> int:
         return self.stream.cuda_stream
 
+    exchange_kind = "nccl all_gather + all_reduce per step"
+
+    def setup_peer_exchange(self, group=None) -> bool:
+        """Sharded runs on one box: replaces the two NCCL collectives of every step by the trainer's own peer-memory exchange
+        (include/swt.h, swt_bpe_train_set_peers).  The exchange buffer is symmetric memory (torch.distributed._symmetric_memory:
+        every rank maps every rank's buffer over NVLink); the kernels that push and barrier are libswt's.  -> True when set up."""
+        import os
+        import torch.distributed as dist
+        world = self.cfg.world_size
+        if world < 2 or world > 8 or os.environ.get("SWT_NO_PEER_EXCHANGE"):
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            nbytes = int(self.lib.swt_bpe_train_peer_bytes(ctypes.byref(self.cfg)))
+            buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.dev)
+            buf.zero_()
+            grp = group if group is not None else dist.group.WORLD
+            hdl = symm_mem.rendezvous(buf, grp)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) != world or not all(ptrs):
+                return False
+            torch.cuda.synchronize()
+            dist.barrier(group=group)                      # every buffer is zeroed before anybody pushes into it
+            arr = (c_vp * world)(*[c_vp(p) for p in ptrs])
+            check(self.lib.swt_bpe_train_set_peers(self.handle, arr, world), "swt_bpe_train_set_peers")
+            self._peer = (buf, hdl)                        # keep the mapping alive
+            self.peer_exchange = True
+            self.exchange_kind = "peer memory: P2P stores + flag barrier inside the step graph (1 kernel per step, 2 on tie steps)"
+            return True
+        except Exception as e:                              # noqa: BLE001 - any failure keeps the NCCL exchange
+            self.peer_error = repr(e)
+            return False
+
     # phases (all asynchronous on the trainer's stream)
     def count_local(self): check(self.lib.swt_bpe_train_count_local(self.handle, self._sp()))
     def build_table(self): check(self.lib.swt_bpe_train_build_table(self.handle, self._sp()))
@@ -721,13 +779,15 @@ def _training_loop(engine, world_size, group, steps_per_sync, progress, dist):
             engine.exchange_initial_pairs(world_size, group, dist)
     engine.build_table()
     graph = None
-    use_graph = world_size > 1 and getattr(engine, "stream", None) is not None and steps_per_sync >= STEPS_PER_GRAPH
+    # sharded on GPUs of one box: the per-step exchange runs over peer memory inside the step graph (no collective call per step)
+    peer = world_size > 1 and hasattr(engine, "setup_peer_exchange") and engine.setup_peer_exchange(group)
+    use_graph = world_size > 1 and not peer and getattr(engine, "stream", None) is not None and steps_per_sync >= STEPS_PER_GRAPH
     if use_graph:
         _one_step_with_collectives(engine, group, dist)             # eager once: communicators and kernels are warm
         engine.stream.synchronize()
         graph = _capture_steps(engine, group, dist)
     while True:
-        if world_size == 1:
+        if world_size == 1 or peer:
             engine.steps(steps_per_sync)
         else:
             done = 0

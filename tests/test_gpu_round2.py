@@ -328,6 +328,7 @@ def test_small_call_path_equals_the_batch_path(hf_tokenizer, tmp_path):
     rng = np.random.default_rng(5)
     limit = SmallCall.get().max_bytes
     texts = ["", " ", "\n\t ", "a", "Litwo! Ojczyzno moja", "ΑΣ ΑΣΑ Σ ΟΔΥΣΣΕΎΣ", "x" * 33 + " " + "y" * 200 + " tail", "a,b.c;d" * 50, "€§ zażółć GĘŚLĄ jaźń İstanbul",
+             "a" * 239, "ab " * 80, "ż" * 120, "a" * 241, "Ab,c " * 48 + "x",          # around the 240 bytes that travel as kernel parameters
              "słowo " * ((limit - 8) // 7), ("ab " * (limit // 3))[:limit], ("ab " * (limit // 3))[:limit - 1] + "Z", "q" * limit, " ".join(lines[:40]),
              "".join(rng.choice(list("abcdeiknorstwyzłó .,-!?'"), size=3000))]
     for cls, payload in ((FastWP, vocab), (FastBPE, merges), (NaiveWP, vocab), (NaiveBPE, merges[:3000])):
