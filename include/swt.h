@@ -325,6 +325,9 @@ typedef struct swt_bpe_train_state {
     uint64_t n_live_slots;     /* live symbols on this rank */
     uint64_t n_tie_steps;      /* steps in which several pairs attained the maximum (first-occurrence scan) */
     uint64_t n_tie_listed;     /* ... of which the tied pairs were few enough to be listed (filtered scan, no table probes) */
+    uint64_t n_peer_barriers;  /* peer exchange: cross-GPU barriers passed ... */
+    uint64_t peer_wait_cycles; /* ... and SM cycles one lane waited in them (rank skew + NVLink latency) */
+    uint64_t peer_kernel_cycles[3]; /* diagnostic: SM cycles inside the candidate exchange, the delta exchange, CTA 0 of the peer update */
 } swt_bpe_train_state;
 
 size_t swt_bpe_train_workspace_bytes(const swt_bpe_train_config *cfg);
@@ -363,6 +366,8 @@ size_t swt_bpe_train_peer_bytes(const swt_bpe_train_config *cfg);
 int swt_bpe_train_set_peers(swt_bpe_trainer *t, void *const *peer_buffers, uint32_t n_peers);
 int swt_bpe_train_exchange_candidates(swt_bpe_trainer *t, void *stream);
 int swt_bpe_train_exchange_deltas(swt_bpe_trainer *t, void *stream);
+/* diagnostic: n_rounds cross-GPU barriers and nothing else (every rank must call it with the same n_rounds) */
+int swt_bpe_train_exchange_probe(swt_bpe_trainer *t, uint32_t n_rounds, void *stream);
 /* synchronises `stream`, copies out the recorded merges (left,right,new ids + chosen pair count)
    and the state; resets the record buffer and clears halt==4. Arrays need record_cap entries. */
 int swt_bpe_train_read(swt_bpe_trainer *t, uint32_t *h_left, uint32_t *h_right, uint32_t *h_new, int64_t *h_count,

@@ -1,0 +1,2 @@
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 profiles/train_scale.py --types 1000000 2>&1 | grep -v OMP | tail -1 | cut -c1-1500
+timeout 600 python profiles/train_scale.py --types 1000000 2>&1 | tail -1 | cut -c1-330

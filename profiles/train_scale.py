@@ -57,7 +57,8 @@ def main():
            "merges": int(len(l)), "seconds": dt, "merges_per_s": len(l) / dt, "us_per_step": 1e6 * dt / max(1, len(l)), "vocab_size": int(state["vocab_size"]),
            "table_entries": int(state["n_table_entries"]), "table_cap": int(state["table_cap"]), "tie_steps": int(state["n_tie_steps"]), "tie_steps_listed": int(state["n_tie_listed"]),
            "live_slots_rank0": int(state["n_live_slots"]), "merges_sha256": h, "gen_seconds": t_gen, "halt": int(state["halt"]),
-           "exchange": getattr(eng, "exchange_kind", "none")}
+           "exchange": getattr(eng, "exchange_kind", "none"),
+           "peer_barriers": int(state.get("n_peer_barriers", 0)), "peer_kernel_cycles_per_step": [int(x) / max(1, len(l)) for x in state.get("peer_kernel_cycles", [0, 0, 0])], "peer_wait_cycles_per_barrier": int(state.get("peer_wait_cycles", 0)) / max(1, int(state.get("n_peer_barriers", 0)))}
     if args.check_oracle_steps and rank == 0:
         import oracle
         k = args.check_oracle_steps

@@ -39,7 +39,8 @@ class TrainState(ctypes.Structure):
         ("halt", ctypes.c_uint32), ("n_recorded", ctypes.c_uint32), ("n_merges_total", ctypes.c_uint64),
         ("vocab_size", ctypes.c_int64), ("n_symbols", ctypes.c_uint64), ("n_table_entries", ctypes.c_uint64),
         ("table_cap", ctypes.c_uint64), ("n_live_slots", ctypes.c_uint64), ("n_tie_steps", ctypes.c_uint64),
-        ("n_tie_listed", ctypes.c_uint64),
+        ("n_tie_listed", ctypes.c_uint64), ("n_peer_barriers", ctypes.c_uint64), ("peer_wait_cycles", ctypes.c_uint64),
+        ("peer_kernel_cycles", ctypes.c_uint64 * 3),
     ]
 
 
@@ -115,6 +116,7 @@ SIGNATURES = {
     "swt_bpe_train_set_peers": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.c_uint32]),
     "swt_bpe_train_exchange_candidates": (ctypes.c_int, [c_vp, c_vp]),
     "swt_bpe_train_exchange_deltas": (ctypes.c_int, [c_vp, c_vp]),
+    "swt_bpe_train_exchange_probe": (ctypes.c_int, [c_vp, ctypes.c_uint32, c_vp]),
     "swt_bpe_train_read": (ctypes.c_int, [c_vp, c_u32p, c_u32p, c_u32p, c_i64p, ctypes.POINTER(TrainState), c_vp]),
     "swt_bpe_train_table_bytes": (ctypes.c_size_t, [ctypes.c_uint64]),
     "swt_bpe_train_grow_table": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint64, c_vp]),

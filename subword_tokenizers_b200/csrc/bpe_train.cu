@@ -65,6 +65,8 @@ struct TrainState {                 // device resident, mutable
     uint32_t n_tie_keys, n_tie_listed;              // the tied pairs themselves when there are at most kTieKeys of them (else 0); listed steps
     uint64_t tie_keys[32];
     uint32_t xchg_epoch, pad_xchg;                  // peer exchange: number of cross-GPU barriers passed so far
+    unsigned long long xchg_wait_cycles;            // ... and the SM cycles spent waiting in them (skew between the ranks + NVLink latency)
+    unsigned long long xchg_cycles[3];              // diagnostic: SM cycles inside k_xchg_cand / k_xchg_delta / CTA 0 of k_update_peer
 };
 constexpr uint32_t kTieKeys = 32;
 
@@ -836,7 +838,9 @@ __device__ __forceinline__ bool px_barrier(const TrainDev &d, uint32_t epoch) {
         st_release_sys_u32(px_flags(d.px.base[lane]) + d.rank, epoch);
         const uint32_t *mine = px_flags(d.px.base[d.rank]) + lane;
         uint32_t spins = 0;
+        const long long c0 = clock64();
         while ((int32_t)(ld_acquire_sys_u32(mine) - epoch) < 0) { if (++spins > (1u << 27)) { ok = false; break; } }
+        if (lane == (d.rank + 1) % d.world) atomicAdd(&d.st->xchg_wait_cycles, (unsigned long long)(clock64() - c0));   // one sample per barrier
     }
     return __all_sync(0xffffffffu, ok);
 }
@@ -845,9 +849,11 @@ __global__ void __launch_bounds__(32) k_xchg_cand(TrainDev d) {
     TrainState *st = d.st;
     if (st->halt || st->n_tied <= 1) return;                        // replicated state: all ranks take the same branch
     const uint32_t lane = threadIdx.x, epoch = st->xchg_epoch + 1;
-    if (lane < d.world) { uint64_t *dst = px_cand(d.px.base[lane]) + 2 * d.rank; dst[0] = d.cand[0]; dst[1] = d.cand[1]; __threadfence_system(); }
+    const long long c0 = clock64();
+    // (the release store of px_barrier, by the same lane, orders these stores before the flag)
+    if (lane < d.world) { uint64_t *dst = px_cand(d.px.base[lane]) + 2 * d.rank; dst[0] = d.cand[0]; dst[1] = d.cand[1]; }
     const bool ok = px_barrier(d, epoch);
-    if (lane == 0) { st->xchg_epoch = epoch; if (!ok) st->halt = kErrPeerTimeout; }
+    if (lane == 0) { st->xchg_epoch = epoch; if (!ok) st->halt = kErrPeerTimeout; st->xchg_cycles[0] += (unsigned long long)(clock64() - c0); }
 }
 // every step: this rank's touched (symbol, delta) lists + ZZ / M go to every rank; replaces the all_reduce over 2 * vmax + 2 values
 __global__ void __launch_bounds__(1024) k_xchg_delta(TrainDev d) {
@@ -855,6 +861,7 @@ __global__ void __launch_bounds__(1024) k_xchg_delta(TrainDev d) {
     if (st->halt || !st->cur_valid) return;
     const uint32_t nl = st->n_touch_l, nr = st->n_touch_r, epoch = st->xchg_epoch + 1, parity = epoch & 1u;
     long long *L = d.delta, *R = d.delta + d.vmax;
+    const long long c0 = clock64();
     for (uint32_t p = 0; p < d.world; ++p) {
         uint64_t *dst = px_delta(d.px.base[p], parity, d.rank, d.px.stride);
         for (uint32_t i = threadIdx.x; i < nl + nr; i += blockDim.x) {
@@ -867,12 +874,21 @@ __global__ void __launch_bounds__(1024) k_xchg_delta(TrainDev d) {
     __syncthreads();                                                // every read of L / R happened
     for (uint32_t i = threadIdx.x; i < nl + nr; i += blockDim.x) { if (i < nl) L[d.touch_l[i]] = 0; else R[d.touch_r[i - nl]] = 0; }
     if (threadIdx.x == 0) { d.delta[2 * (uint64_t)d.vmax] = 0; d.delta[2 * (uint64_t)d.vmax + 1] = 0; }
-    __threadfence_system();
+    // the CTA barrier orders every thread's pushes before the release stores of the flags (cumulativity): no system-scope fence per
+    // thread (1024 MEMBAR.SYS behind a kernel that has just written the word table were the most expensive part of this kernel)
     __syncthreads();
     if (threadIdx.x < 32) {
         const bool ok = px_barrier(d, epoch);
-        if (threadIdx.x == 0) { st->xchg_epoch = epoch; if (!ok) st->halt = kErrPeerTimeout; }
+        if (threadIdx.x == 0) { st->xchg_epoch = epoch; if (!ok) st->halt = kErrPeerTimeout; st->xchg_cycles[1] += (unsigned long long)(clock64() - c0); }
     }
+}
+// barrier only (swt_bpe_train_exchange_probe: measures what one cross-GPU barrier costs on this box)
+__global__ void __launch_bounds__(32) k_xchg_probe(TrainDev d) {
+    TrainState *st = d.st;
+    const uint32_t epoch = st->xchg_epoch + 1;
+    __threadfence_system();
+    const bool ok = px_barrier(d, epoch);
+    if (threadIdx.x == 0) { st->xchg_epoch = epoch; if (!ok) st->halt = kErrPeerTimeout; }
 }
 // update from the inboxes: the lists of all ranks are folded into this rank's replica of the pair table (integer adds commute, so every
 // replica ends up identical)
@@ -883,6 +899,7 @@ __global__ void __launch_bounds__(256) k_update_peer(TrainDev d) {
     const uint32_t parity = st->xchg_epoch & 1u;                    // the generation the barrier of this step closed
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     long long zz = 0, m = 0;
+    const long long c0 = clock64();
     for (uint32_t r = 0; r < d.world; ++r) {
         const uint64_t *src = px_delta(d.px.base[d.rank], parity, r, d.px.stride);
         const uint32_t nl = (uint32_t)src[0], nr = (uint32_t)src[1];
@@ -898,6 +915,7 @@ __global__ void __launch_bounds__(256) k_update_peer(TrainDev d) {
         if (zz) { table_add(d.table, cap, (b << 32) | a, -zz, st, d.dl()); table_add(d.table, cap, (z << 32) | z, zz, st, d.dl()); }
         if (m) table_add(d.table, cap, (a << 32) | b, -m, st, d.dl());
         if (d.mode == 1) { d.sfreq[a] -= m; d.sfreq[b] -= m; d.sfreq[z] += m; }
+        st->xchg_cycles[2] += (unsigned long long)(clock64() - c0);
     }
 }
 
@@ -1185,6 +1203,12 @@ SWT_API int swt_bpe_train_exchange_deltas(swt_bpe_trainer *t, void *stream) {
     SWT_CUDA_OK(cudaGetLastError());
     return SWT_OK;
 }
+SWT_API int swt_bpe_train_exchange_probe(swt_bpe_trainer *t, uint32_t n_rounds, void *stream) {
+    SWT_REQUIRE(t != nullptr && t->dev.px.enabled, "peer exchange is not set up");
+    for (uint32_t k = 0; k < n_rounds; ++k) k_xchg_probe<<<1, 32, 0, (cudaStream_t)stream>>>(t->dev);
+    SWT_CUDA_OK(cudaGetLastError());
+    return SWT_OK;
+}
 SWT_API size_t swt_bpe_train_peer_bytes(const swt_bpe_train_config *cfg) { return cfg ? px_bytes(vmax_of(cfg)) : 0; }
 SWT_API int swt_bpe_train_set_peers(swt_bpe_trainer *t, void *const *peer_buffers, uint32_t n_peers) {
     SWT_REQUIRE(t && peer_buffers, "NULL argument");
@@ -1211,7 +1235,8 @@ SWT_API int swt_bpe_train_steps(swt_bpe_trainer *t, uint32_t n_steps, void *stre
     cudaStream_t st = (cudaStream_t)stream;
     // The step is launch-bound on small corpora (9 short kernels), so kStepsPerGraph steps are captured into one CUDA
     // graph and replayed; every kernel is self-gating on the halt flag, so replaying past the end is harmless.
-    if (!t->step_graph && n_steps >= kStepsPerGraph && st != nullptr && !t->timing) {
+    static const bool no_graph = getenv("SWT_TRAIN_NO_GRAPH") != nullptr;        // experiments: eager launches
+    if (!t->step_graph && n_steps >= kStepsPerGraph && st != nullptr && !t->timing && !no_graph) {
         cudaGraph_t g = nullptr;
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             int rc = SWT_OK;
@@ -1221,8 +1246,9 @@ SWT_API int swt_bpe_train_steps(swt_bpe_trainer *t, uint32_t n_steps, void *stre
                 if (cudaGraphInstantiate(&t->step_graph, g, 0) != cudaSuccess) t->step_graph = nullptr;
             }
             if (g) cudaGraphDestroy(g);
+            if (!t->step_graph) fprintf(stderr, "[swt] trainer: CUDA graph capture of the step failed (%s); falling back to eager launches\n", cudaGetErrorString(e));
             (void)cudaGetLastError();
-        } else (void)cudaGetLastError();
+        } else { fprintf(stderr, "[swt] trainer: stream capture unavailable; eager launches\n"); (void)cudaGetLastError(); }
     }
     uint32_t done = 0;
     if (t->step_graph) {
@@ -1252,6 +1278,8 @@ SWT_API int swt_bpe_train_read(swt_bpe_trainer *t, uint32_t *h_left, uint32_t *h
     state->halt = hs.halt; state->n_recorded = n; state->n_merges_total = hs.n_merges_total; state->vocab_size = hs.vocab_size;
     state->n_symbols = hs.n_symbols; state->n_table_entries = hs.n_entries; state->table_cap = hs.table_cap; state->n_live_slots = hs.n_live;
     state->n_tie_steps = hs.n_tie_steps; state->n_tie_listed = hs.n_tie_listed;
+    state->n_peer_barriers = hs.xchg_epoch; state->peer_wait_cycles = hs.xchg_wait_cycles;
+    for (int k = 0; k < 3; ++k) state->peer_kernel_cycles[k] = hs.xchg_cycles[k];
     return SWT_OK;
 }
 
