@@ -353,3 +353,60 @@ def test_small_call_path_equals_the_batch_path(hf_tokenizer, tmp_path):
             big = enc._encode_text_resident(t)
             if small is not None:
                 assert np.array_equal(small, big), (cls.__name__, t[:30], len(data))
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE configs[4]: --compare at 50 K
+def _token_sequence_equivalence(tok1, tok2, sentences):
+    """The metric of the reference's --compare (source/benchmarks.py:113-184), restated for the test: positional matches, unordered
+    overlap and per-word shared-subword rate between two tokenizers."""
+    from collections import Counter
+    strip = lambda toks: [t[2:] if t.startswith("##") else t for t in toks]         # noqa: E731
+    pos = n_pos = unordered = n_words = word_matches = 0
+    for s in sentences:
+        t1, t2 = strip(tok1.tokenize(s)), strip(tok2.tokenize(s))
+        n = min(len(t1), len(t2))
+        pos += sum(1 for i in range(n) if t1[i] == t2[i]); n_pos += n
+        f1, f2 = Counter(t1), Counter(t2)
+        unordered += sum(min(f1[t], f2[t]) for t in (f1.keys() & f2.keys()))
+        words = s.split()
+        n_words += len(words)
+        for w in words:
+            if set(strip(tok1.tokenize(w))) & set(strip(tok2.tokenize(w))):
+                word_matches += 1
+    return [pos, n_pos, (pos / n_pos * 100) if n_pos else 0.0, unordered, (unordered / n_pos * 100) if n_pos else 0.0,
+            word_matches, n_words, (word_matches / n_words * 100) if n_words else 0.0]
+
+
+def test_config5_compare_equivalence_at_50k_vocab(hf_tokenizer, tmp_path):
+    """BASELINE configs[4]: the four drop-in classes with 50 K models (trained by the GPU trainers on synthetic types, oracle-checked
+    prefix: tests/golden/make_config5_models.py) on adversarial long-word / heavy-tail input.  Their token lists and the three
+    --compare tuples must equal what the UNMODIFIED reference produced with the same models (tests/golden/make_config5_fixture.py)."""
+    import bench_data as BD
+    from subword_tokenizers_b200 import FastBPE, FastWP, NaiveBPE, NaiveWP
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from config5_inputs import config5_sentences
+    fixture = load_golden("config5_fixture.json.gz")
+    merges, vocab = load_golden("config5_bpe_merges.json.gz"), load_golden("config5_wp_vocab.json.gz")
+    assert len(vocab) == 50_000 and len(merges) > 49_000
+    mat, lens = BD.synth_type_table(300_000, 9)
+    arena, off = BD.table_to_utf8(mat, lens)
+    types = [arena[int(off[k]):int(off[k + 1])].tobytes().decode() for k in range(2000)]
+    sentences = config5_sentences(types, set(vocab))
+    assert len(sentences) == fixture["n_sentences"]
+    for d, payload, name in (("bpe", merges, "merges.json"), ("wp", vocab, "vocab.json")):
+        os.makedirs(tmp_path / d, exist_ok=True)
+        with open(tmp_path / d / name, "w", encoding="utf-8") as f:
+            json.dump(payload, f, ensure_ascii=False)
+    toks = {}
+    for cls, d in ((NaiveBPE, "bpe"), (FastBPE, "bpe"), (NaiveWP, "wp"), (FastWP, "wp")):
+        t = cls(hf_tokenizer)
+        t.load_resources(str(tmp_path / d))
+        toks[cls.__name__] = t
+        lists = [t.tokenize(s) for s in sentences]
+        assert sum(len(x) for x in lists) == fixture["n_tokens"][cls.__name__], cls.__name__
+        assert hashlib.sha256(json.dumps(lists, ensure_ascii=False).encode()).hexdigest() == fixture["token_sha256"][cls.__name__], cls.__name__
+        assert t.tokenize_batch(sentences) == lists, cls.__name__
+    for pair, want in fixture["equivalence"].items():
+        a, b = pair.split("/")
+        got = _token_sequence_equivalence(toks[a], toks[b], sentences)
+        assert got == want, (pair, got, want)
