@@ -165,6 +165,38 @@ def oracle_encode(kind, tab, arena, off, threads):
     return np.concatenate(parts) if parts else np.zeros(0, np.uint32), sec
 
 
+def python_reference_rate(vocab, arena, off, max_bytes=3_000_000):
+    """The UNMODIFIED Python reference (baseline/_ref/source, vendored by __graft_entry__.build()) on ONE host core: FastWP.tokenize over
+    the text form of a prefix of the stream.  -> dict or None when the reference is not vendored."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref_root, "source", "wordpiece.py")):
+        return None
+    try:
+        sys.path.insert(0, ref_root)
+        from source.wordpiece import FastWP as RefFastWP            # type: ignore
+        from source.utils import WPTrie_E2E as RefTrie             # type: ignore
+        from subword_tokenizers_b200.hf_shim import make_hf_tokenizer
+        n = int(np.searchsorted(off, max_bytes))
+        words = [arena[int(off[k]):int(off[k + 1])].tobytes().decode("utf-8", "surrogatepass") for k in range(n)]
+        text = " ".join(words)
+        tok = RefFastWP(make_hf_tokenizer())
+        tok.vocab = set(vocab)
+        tok.vocab_trie = RefTrie(tok.vocab)
+        tok.tokenize(text[:2000])
+        tic = time.perf_counter()
+        out = tok.tokenize(text)
+        sec = time.perf_counter() - tic
+        nbytes = int(off[n])
+        return {"value": nbytes / sec / 1e6, "unit": "MB/s", "cores": 1, "kind": "reference",
+                "sample": "reference FastWP.tokenize (pure Python, source/wordpiece.py:233-316) on the first %d words (%.1f MB) of the stream, "
+                          "%.1f s, %d tokens" % (n, nbytes / 1e6, sec, len(out))}
+    except Exception as e:                                          # noqa: BLE001
+        return {"error": repr(e)}
+    finally:
+        if ref_root in sys.path:
+            sys.path.remove(ref_root)
+
+
 def check_prefix(kind, tab, host_prefix, d_ids, d_tok, threads):
     """Compares the GPU ids of the stream's first words with the oracle. -> (n_words_checked, equal, oracle_seconds, bytes)."""
     h_arena, h_off = host_prefix
@@ -468,6 +500,7 @@ def main():
     ap.add_argument("--many-types", type=int, default=2_000_000)
     ap.add_argument("--many-bytes", type=int, default=500_000_000)
     ap.add_argument("--check-words", type=int, default=4_000_000, help="words of the stream prefix compared with the oracle at N > 1")
+    ap.add_argument("--e2e-batch-mb", type=int, default=32, help="batch size of the host-buffer pipeline (MiB of input per batch)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -572,13 +605,14 @@ def main():
     h_text = torch.empty(d_text.numel(), dtype=torch.uint8).pin_memory(); h_text.copy_(d_text)
     del d_text
     h_ids16.zero_()
-    enc.tokenize_host(h_text, n_text, h_ids16, has_sigma=False)
+    e2e_batch = args.e2e_batch_mb << 20
+    enc.tokenize_host(h_text, n_text, h_ids16, has_sigma=False, batch_bytes=e2e_batch)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     tic = time.perf_counter()
     for _ in range(e2e_steps):
-        nt_text, nw_text, _ = enc.tokenize_host(h_text, n_text, h_ids16, has_sigma=False)
+        nt_text, nw_text, _ = enc.tokenize_host(h_text, n_text, h_ids16, has_sigma=False, batch_bytes=e2e_batch)
     torch.cuda.synchronize()
     t3 = torch.tensor([time.perf_counter() - tic], dtype=torch.float64, device=dev)
     if world > 1:
@@ -595,7 +629,7 @@ def main():
     e2e32_ok = bool(torch.equal(h_ids[:n_tokens], ref_ids))
     del h_ids, h_tok, h_arena, h_off, ref_ids
     # the same copies without kernels: the PCIe ceiling of the headline e2e number (all ranks concurrently)
-    ceil_sec = copy_ceiling(dev, n_text, 2 * n_tokens, 64 << 20, e2e_steps, dist, world)
+    ceil_sec = copy_ceiling(dev, n_text, 2 * n_tokens, e2e_batch, e2e_steps, dist, world)
 
     line = None
     if rank == 0:
@@ -608,14 +642,14 @@ def main():
             "parity": {"checked_against": "oracle (C port of reference wordpiece.py:233-316) on the first words of each rank's stream",
                        "parity_checked_words": parity_words, "ok": parity_all},
             "e2e": {"value": e2e_text_value, "unit": "MB/s", "h2d_bytes_per_step": n_text,
-                    "d2h_bytes_per_step": 2 * n_tokens + 64 * ((n_text >> 26) + 1), "steps": e2e_steps,
+                    "d2h_bytes_per_step": 2 * n_tokens + 64 * (n_text // e2e_batch + 1), "steps": e2e_steps, "batch_mib": args.e2e_batch_mb,
                     "call": "swt_tokenize_text_host",
                     "what": "raw UTF-8 text (the stream's words joined by single spaces) in a pinned host buffer -> H2D -> lower-casing + "
                             "whitespace split on the device (swt_pretok_*) -> FastWP encode -> 16-bit flat token ids (the list "
                             "tokenize() returns) D2H into a pinned host buffer; MB = word bytes, as in `value`",
                     "matches_resident_run": e2e_text_ok,
                     "copy_ceiling": {"seconds_per_step": ceil_sec, "value": job_bytes / ceil_sec / 1e6, "unit": "MB/s",
-                                     "what": "the same H2D + D2H byte counts through five streams in 64 MiB batches, no kernels, "
+                                     "what": "the same H2D + D2H byte counts through five streams in %d MiB batches, no kernels, " % args.e2e_batch_mb +
                                              "all %d rank(s) concurrently (max over ranks)" % world},
                     "frac_of_copy_ceiling": ceil_sec / e2e_text_sec,
                     "packed_words_in_16bit_ids": {"value": e2e_value, "unit": "MB/s", "call": "swt_encode_host16",
@@ -633,6 +667,9 @@ def main():
             line["cpu_baseline"] = {"value": pre_bytes / oracle_sec / 1e6, "unit": "MB/s", "cores": threads, "kind": "port",
                                     "sample": "first %d words (%.1f MB) of the stream, %.2f s; its ids are the ones the GPU output "
                                               "was compared with" % (npre, pre_bytes / 1e6, oracle_sec)}
+            pyref = python_reference_rate(vocab, prefix[0], prefix[1])
+            if pyref is not None:
+                line["cpu_baseline"]["python_reference_one_core"] = pyref
     del d_ids
     also = {}
     if not args.no_also:
