@@ -632,8 +632,12 @@ __global__ void __launch_bounds__(256) encode_long_count_kernel(Enc enc, const u
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t n_bm = (ws.n_tiles + 31) >> 5;
     uint32_t h6 = 0;
-    for (uint32_t bw = warp_global; bw < n_bm; bw += n_warps) {
-        uint32_t bits = ws.long_tiles[bw];                                          // warp-uniform
+    // the bitmap is read 32 words per warp step (one per lane); nearly all of it is zero
+    for (uint32_t bw0 = warp_global * 32u; bw0 < n_bm; bw0 += n_warps * 32u) {
+      const uint32_t my_bits = bw0 + lane < n_bm ? ws.long_tiles[bw0 + lane] : 0u;
+      for (uint32_t nz = __ballot_sync(0xffffffffu, my_bits != 0); nz; nz &= nz - 1) {
+        const uint32_t src = __ffs(nz) - 1, bw = bw0 + src;
+        uint32_t bits = __shfl_sync(0xffffffffu, my_bits, src);                     // warp-uniform
         while (bits) {
             const uint32_t tile = (bw << 5) + (__ffs(bits) - 1); bits &= bits - 1;
             const uint32_t w_tile = tile * kTileWords, tile_words = min((uint32_t)kTileWords, n_words - w_tile);
@@ -683,6 +687,7 @@ __global__ void __launch_bounds__(256) encode_long_count_kernel(Enc enc, const u
             }
             if (lane == 0 && added) atomicAdd(&ws.tile_total[tile], added);
         }
+      }
     }
     if (h6) atomicAdd(&status[kStatusH6], h6);
 }
@@ -704,8 +709,11 @@ __global__ void __launch_bounds__(256) encode_long_emit_kernel(Enc enc, const ui
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t n_bm = (ws.n_tiles + 31) >> 5;
-    for (uint32_t bw = warp_global; bw < n_bm; bw += n_warps) {
-        uint32_t bits = ws.long_tiles[bw];
+    for (uint32_t bw0 = warp_global * 32u; bw0 < n_bm; bw0 += n_warps * 32u) {
+      const uint32_t my_bits = bw0 + lane < n_bm ? ws.long_tiles[bw0 + lane] : 0u;
+      for (uint32_t nz = __ballot_sync(0xffffffffu, my_bits != 0); nz; nz &= nz - 1) {
+        const uint32_t src = __ffs(nz) - 1, bw = bw0 + src;
+        uint32_t bits = __shfl_sync(0xffffffffu, my_bits, src);
         while (bits) {
             const uint32_t tile = (bw << 5) + (__ffs(bits) - 1); bits &= bits - 1;
             const uint32_t w_tile = tile * kTileWords, tile_words = min((uint32_t)kTileWords, n_words - w_tile);
@@ -750,6 +758,7 @@ __global__ void __launch_bounds__(256) encode_long_emit_kernel(Enc enc, const ui
                 }
             }
         }
+      }
     }
 }
 
