@@ -327,7 +327,7 @@ typedef struct swt_bpe_train_state {
     uint64_t n_tie_listed;     /* ... of which the tied pairs were few enough to be listed (filtered scan, no table probes) */
     uint64_t n_peer_barriers;  /* peer exchange: cross-GPU barriers passed ... */
     uint64_t peer_wait_cycles; /* ... and SM cycles one lane waited in them (rank skew + NVLink latency) */
-    uint64_t peer_kernel_cycles[3]; /* diagnostic: SM cycles inside the candidate exchange, the delta exchange, CTA 0 of the peer update */
+    uint64_t peer_kernel_cycles[3]; /* diagnostic: SM cycles inside the candidate exchange, the delta exchange, thread 0 of the inbox accumulation */
 } swt_bpe_train_state;
 
 size_t swt_bpe_train_workspace_bytes(const swt_bpe_train_config *cfg);

@@ -66,7 +66,7 @@ struct TrainState {                 // device resident, mutable
     uint64_t tie_keys[32];
     uint32_t xchg_epoch, pad_xchg;                  // peer exchange: number of cross-GPU barriers passed so far
     unsigned long long xchg_wait_cycles;            // ... and the SM cycles spent waiting in them (skew between the ranks + NVLink latency)
-    unsigned long long xchg_cycles[3];              // diagnostic: SM cycles inside k_xchg_cand / k_xchg_delta / CTA 0 of k_update_peer
+    unsigned long long xchg_cycles[3];              // diagnostic: SM cycles inside k_xchg_cand / k_xchg_delta / thread 0 of k_accum_peer
 };
 constexpr uint32_t kTieKeys = 32;
 
@@ -284,7 +284,7 @@ __global__ void k_build_filter(TrainDev d) {
 // single rank: the delta vectors of the previous step are cleared through its touched-symbol lists (k_update reads every delta from
 // two threads, so it cannot clear them itself); called by every thread of the select kernel before the lists are reset
 __device__ __forceinline__ void clear_touched_deltas(const TrainDev &d, const TrainState *st) {
-    if (d.world != 1) return;
+    if (d.world != 1 && !d.px.enabled) return;          // (NCCL exchange: k_update clears the dense vectors itself)
     long long *L = d.delta, *R = d.delta + d.vmax;
     const uint32_t nl = st->n_touch_l, nr = st->n_touch_r;
     for (uint32_t i = threadIdx.x; i < nl; i += blockDim.x) L[d.touch_l[i]] = 0;
@@ -790,8 +790,9 @@ __global__ void __launch_bounds__(256) k_update(TrainDev d) {
     const uint64_t cap = st->table_cap;
     long long *L = d.delta, *R = d.delta + d.vmax;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    if (d.world == 1) {
-        // single rank: only the symbols whose delta became non-zero (listed by k_apply) have to be visited
+    if (d.world == 1 || d.px.enabled) {
+        // single rank, or peer exchange (k_accum_peer rebuilt the lists from all ranks): only the symbols whose delta became non-zero
+        // have to be visited
         // one table update per thread (the -delta and the +delta of an entry are independent chains of random accesses);
         // L / R are cleared by k_clear_deltas afterwards
         const uint32_t nl = st->n_touch_l, nr = st->n_touch_r;
@@ -879,7 +880,10 @@ __global__ void __launch_bounds__(1024) k_xchg_delta(TrainDev d) {
     __syncthreads();
     if (threadIdx.x < 32) {
         const bool ok = px_barrier(d, epoch);
-        if (threadIdx.x == 0) { st->xchg_epoch = epoch; if (!ok) st->halt = kErrPeerTimeout; st->xchg_cycles[1] += (unsigned long long)(clock64() - c0); }
+        if (threadIdx.x == 0) {
+            st->xchg_epoch = epoch; if (!ok) st->halt = kErrPeerTimeout; st->xchg_cycles[1] += (unsigned long long)(clock64() - c0);
+            st->n_touch_l = 0; st->n_touch_r = 0;                   // the lists are rebuilt from the inboxes of all ranks (k_accum_peer)
+        }
     }
 }
 // barrier only (swt_bpe_train_exchange_probe: measures what one cross-GPU barrier costs on this box)
@@ -890,31 +894,31 @@ __global__ void __launch_bounds__(32) k_xchg_probe(TrainDev d) {
     const bool ok = px_barrier(d, epoch);
     if (threadIdx.x == 0) { st->xchg_epoch = epoch; if (!ok) st->halt = kErrPeerTimeout; }
 }
-// update from the inboxes: the lists of all ranks are folded into this rank's replica of the pair table (integer adds commute, so every
-// replica ends up identical)
-__global__ void __launch_bounds__(256) k_update_peer(TrainDev d) {
+// after the barrier: the lists of ALL ranks (own inbox) are summed into the dense delta vectors and the lists of touched symbols are
+// rebuilt, so that k_update folds every symbol into the pair table ONCE (applying each rank's list separately cost world_size times
+// the table updates: 8 GPUs were slower than the NCCL all-reduce of round 1).  Deltas are sums of positive frequencies, so "the old
+// value was zero" identifies the first contribution to a symbol exactly as in k_apply.
+__global__ void __launch_bounds__(256) k_accum_peer(TrainDev d) {
     TrainState *st = d.st;
     if (st->halt || !st->cur_valid) return;
-    const uint64_t a = st->cur_a, b = st->cur_b, z = st->cur_z, cap = st->table_cap;
     const uint32_t parity = st->xchg_epoch & 1u;                    // the generation the barrier of this step closed
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    long long *L = d.delta, *R = d.delta + d.vmax;
     long long zz = 0, m = 0;
     const long long c0 = clock64();
     for (uint32_t r = 0; r < d.world; ++r) {
         const uint64_t *src = px_delta(d.px.base[d.rank], parity, r, d.px.stride);
         const uint32_t nl = (uint32_t)src[0], nr = (uint32_t)src[1];
         zz += (long long)src[2]; m += (long long)src[3];
-        for (uint32_t i = gtid; i < 2 * (nl + nr); i += gsz) {      // one table update per thread: the - and the + of an entry are independent
-            const uint32_t e = i >> 1; const bool plus = i & 1u;
-            const uint64_t x = src[4 + 2 * (uint64_t)e]; const long long v = (long long)src[5 + 2 * (uint64_t)e];
-            if (e < nl) table_add(d.table, cap, (x << 32) | (plus ? z : a), plus ? v : -v, st, d.dl());
-            else table_add(d.table, cap, ((plus ? z : b) << 32) | x, plus ? v : -v, st, d.dl());
+        for (uint32_t i = gtid; i < nl + nr; i += gsz) {
+            const uint32_t sym = (uint32_t)src[4 + 2 * (uint64_t)i];
+            const unsigned long long v = src[5 + 2 * (uint64_t)i];
+            if (i < nl) { if (atomicAdd((unsigned long long *)&L[sym], v) == 0ull) d.touch_l[atomicAdd(&st->n_touch_l, 1u)] = sym; }
+            else if (atomicAdd((unsigned long long *)&R[sym], v) == 0ull) d.touch_r[atomicAdd(&st->n_touch_r, 1u)] = sym;
         }
     }
     if (gtid == 0) {
-        if (zz) { table_add(d.table, cap, (b << 32) | a, -zz, st, d.dl()); table_add(d.table, cap, (z << 32) | z, zz, st, d.dl()); }
-        if (m) table_add(d.table, cap, (a << 32) | b, -m, st, d.dl());
-        if (d.mode == 1) { d.sfreq[a] -= m; d.sfreq[b] -= m; d.sfreq[z] += m; }
+        d.delta[2 * (uint64_t)d.vmax] = zz; d.delta[2 * (uint64_t)d.vmax + 1] = m;      // (zeroed by k_xchg_delta after the push)
         st->xchg_cycles[2] += (unsigned long long)(clock64() - c0);
     }
 }
@@ -1180,11 +1184,9 @@ SWT_API int swt_bpe_train_merge(swt_bpe_trainer *t, void *stream) {
 SWT_API int swt_bpe_train_update(swt_bpe_trainer *t, void *stream) {
     SWT_REQUIRE(t != nullptr, "NULL trainer");
     cudaStream_t st = (cudaStream_t)stream;
-    if (t->dev.px.enabled) TRAIN_LAUNCH("update_peer", k_update_peer<<<32, 256, 0, st>>>(t->dev));
-    else {
-        const int blocks = t->cfg.world_size == 1 ? 32 : (int)std::min<uint64_t>((t->dev.vmax + 255) / 256, 4096);
-        TRAIN_LAUNCH("update", k_update<<<blocks, 256, 0, st>>>(t->dev));
-    }
+    if (t->dev.px.enabled) TRAIN_LAUNCH("accum_peer", k_accum_peer<<<32, 256, 0, st>>>(t->dev));
+    const int blocks = (t->cfg.world_size == 1 || t->dev.px.enabled) ? 32 : (int)std::min<uint64_t>((t->dev.vmax + 255) / 256, 4096);
+    TRAIN_LAUNCH("update", k_update<<<blocks, 256, 0, st>>>(t->dev));
     SWT_CUDA_OK(cudaGetLastError());
     return SWT_OK;
 }
