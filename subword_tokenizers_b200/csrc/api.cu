@@ -33,6 +33,7 @@ size_t encode_workspace_layout(uint32_t n_words, uint64_t long_bytes, void *base
     ws->tok32 = cv.take<uint32_t>((size_t)ws->tok32_cap + 1);
     ws->packed = cv.take<uint32_t>((size_t)n_words + 2);
     ws->tile_total = cv.take<uint32_t>((size_t)n_tiles + 1);
+    ws->tile_pend = cv.take<uint2>((size_t)n_tiles + 1);
     ws->group_base = cv.take<unsigned long long>((size_t)n_tiles / 1024 + 2);
     ws->long_tiles = cv.take<uint32_t>((size_t)n_tiles / 32 + 2);
     // long words: a 16-word header + per-byte scratch each, allocated in 16-word granules.  BPE: two symbol buffers (2 words per
@@ -66,6 +67,9 @@ SWT_API int swt_tune(const char *name, int value) {
     else if (n == "timing") g_tune.timing = value;
     else if (n == "warp_words") g_tune.warp_words = value;
     else if (n == "bpe_queue") g_tune.bpe_queue = value;
+    else if (n == "split_count") g_tune.split_count = value;
+    else if (n == "split_chunks") g_tune.split_chunks = value;
+    else if (n == "split_warm_tiles") g_tune.split_warm_tiles = value;
     else if (n == "train_timing") g_train_timing = value;
     else { set_error("swt_tune: unknown knob " + n); return SWT_ERR_ARG; }
     return SWT_OK;

@@ -246,6 +246,7 @@ struct BpeEncT {
     static constexpr bool kBatchSlowPath = kQueue;
     static constexpr bool kWarpShort = true;
     static constexpr bool kWarpLong = false;
+    static constexpr bool kSplitCount = true;     // count pass = warm-up + leaf count kernel + resolve kernel (encode.cuh)
     __device__ __forceinline__ void stage_init(Stage &s) const {
         const uint4 *src = reinterpret_cast<const uint4 *>(t.stage);
         uint4 *dst = reinterpret_cast<uint4 *>(&s);

@@ -53,7 +53,13 @@ constexpr int kMemoTokens = 44;        // >= kShortBytes: every word of up to 32
 constexpr int kMemoProbes = 8;
 
 // status words written by the encode kernels
-enum { kStatusCode = 0, kStatusTokens = 1, kStatusH6 = 2, kStatusTokensHi = 3, kStatusMemoTypes = 4, kStatusSlowWords = 5 };
+enum { kStatusCode = 0, kStatusTokens = 1, kStatusH6 = 2, kStatusTokensHi = 3, kStatusMemoTypes = 4, kStatusSlowWords = 5,
+       kStatusWarmSlow = 6 };   // slow-path words of the last warm-up tiles: gates the split count pass (see launch_encode_tiles)
+// split count pass: the stream has MANY word types when more than 1/8 of the words of the last warm-up tiles took the slow path
+// (counted over the LAST QUARTER of the warm-up tiles only: the first waves of tiles miss whatever the stream, nothing is published yet)
+__device__ __forceinline__ bool many_types_stream(const uint32_t *status, uint32_t warm_tiles) {
+    return (uint64_t)status[kStatusWarmSlow] * 8u > (uint64_t)(warm_tiles / 4u) * 64u;
+}
 
 // Word-type memo, structure of arrays (one slot index addresses all three):
 //   keys[slot]   16 B  the CAS key: word bytes 0..7 | bytes 8..14, bits 56-59 = length (0 for words > 15 bytes), bits 60-63 = "pub":
@@ -90,6 +96,7 @@ struct EncodeWorkspace {
     uint32_t *tok32; uint32_t tok32_cap;
     uint32_t *packed;                // n_words: per-word record handed from the count pass to the emit pass
     uint32_t *tile_total;            // n_tiles: tokens per tile, then (after the scan) the in-group exclusive prefix
+    uint2 *tile_pend;                // n_tiles: per row, the words the leaf count kernel left to the resolve kernel (bit = lane)
     unsigned long long *group_base;  // n_groups: tokens per group of 1024 tiles, then the group's global token offset
     uint32_t *long_tiles;            // bitmap over the tiles: the tile holds a word longer than kShortBytes (rare; cleared per call)
     uint32_t *long_scratch;          // BPE: symbol ping-pong buffers of long words; WP: segment records of long chunks
@@ -106,6 +113,9 @@ struct Tuning {                     // process-wide knobs for experiments (swt_t
     int timing = 0;                 // per-kernel CUDA-event times of every encode call on stderr (synchronises)
     int warp_words = 3;             // FastBPE: up to this many missed words are encoded by the whole warp, one after the other
     int bpe_queue = 1;              // FastBPE: memo misses go through the warp's pending queue (0: resolved inside their tile)
+    int split_count = 1;            // count pass = warm-up + chunks of (leaf count kernel, resolve kernel); 0: one kernel with the slow path inside
+    int split_chunks = 2;           // ... number of chunks
+    int split_warm_tiles = 16384;   // ... tiles of the warm-up (1 M words); the split form is used for calls of more than 4x as many tiles
 };
 extern Tuning g_tune;
 
@@ -488,7 +498,11 @@ __device__ __forceinline__ uint32_t key_diff(const uint4 &e, const uint4 &k) {
 template <class Enc>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words,
-                    EncodeWorkspace ws, uint32_t *status, uint32_t warp_words) {
+                    EncodeWorkspace ws, uint32_t *status, uint32_t warp_words, uint32_t tile_begin, uint32_t tile_end, uint32_t mode,
+                    uint32_t warm_tiles) {
+    // mode 0: plain.  1: the warm-up of the split count pass (its slow-path words are also counted in kStatusWarmSlow).  2: the rest of a
+    // stream with many word types (runs only when the warm-up found one; otherwise the leaf / resolve kernels do the work).
+    if (mode == 2 && !many_types_stream(status, warm_tiles)) return;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * kThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kThreads) >> 5;
     const uint32_t arena_end = word_off[n_words];
@@ -506,6 +520,7 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
     uint32_t *pend = s_pend[threadIdx.x >> 5];
     uint32_t n_pend = 0;
     uint32_t n_slow_words = 0;                                                      // diagnostic (status word 5), warp-uniform
+    uint32_t n_gate_words = 0;                                                      // warm-up: slow-path words of its last quarter
     auto flush_pending = [&](uint32_t first, uint32_t count) {
         h6 += flush_pending_words(enc, sg, ws, arena, word_off, arena_end, status, pend + first, count, warp_words, pend + 96);
         n_slow_words += count;
@@ -520,10 +535,10 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
     };
     // The tile loop holds no calls: when 32 words are pending the warp leaves it, resolves them (flush_pending_words, out of line) and
     // enters it again, so that nothing of the loop's state (the prefetched offsets) has to survive a call.
-    uint32_t tile = warp_global;
-    while (tile < ws.n_tiles) {
+    uint32_t tile = tile_begin + warp_global;
+    while (tile < tile_end) {
     if (tile < n_full) load_offsets(tile);
-    for (; tile < ws.n_tiles && n_pend < 32; tile += n_warps) {
+    for (; tile < tile_end && n_pend < 32; tile += n_warps) {
         const uint32_t w_tile = tile * kTileWords;
         uint32_t rec[kWordsPerThread] = {0u, 0u}, ntok[kWordsPerThread] = {0u, 0u};
         bool slow[kWordsPerThread] = {false, false}, is_long[kWordsPerThread] = {false, false};
@@ -584,6 +599,7 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
         for (int j = 0; j < kWordsPerThread; ++j) {
             const uint32_t m = __ballot_sync(0xffffffffu, slow[j]);
             if (m == 0) continue;                                                   // warp-uniform, the common case
+            if (mode == 1 && tile >= tile_end - tile_end / 4u) n_gate_words += __popc(m);
             if constexpr (Enc::kBatchSlowPath) {
                 if (slow[j]) pend[n_pend + __popc(m & ((1u << lane) - 1u))] = w_tile + 32u * j + lane;
                 n_pend += __popc(m);
@@ -615,6 +631,135 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
     while (n_pend >= 32) { n_pend -= 32; flush_pending(n_pend, 32); }
     }
     if (n_pend) flush_pending(0, n_pend);
+    if (h6) atomicAdd(&status[kStatusH6], h6);
+    if (lane == 0 && n_slow_words) atomicAdd(&status[kStatusSlowWords], n_slow_words);
+    if (lane == 0 && n_gate_words) atomicAdd(&status[kStatusWarmSlow], n_gate_words);
+}
+
+// ---- pass 1, split form: leaf count kernel + resolve kernel ------------------------------------------------------------------------
+// The kernel above carries the slow path (calls, a stack frame, the encoder's tables): the FastBPE instantiations want 98 registers,
+// get 64 and spill inside the tile loop (count pass 1.40 ms per GB against 0.90 ms for FastWP, same fast path).  Once the memo is warm
+// almost every word is served by the first probe, so for the encoders with Enc::kSplitCount the bulk of the stream goes through a
+// LEAF kernel that only probes -- no encoder, no calls, no stack, 39 registers, 6 CTAs per SM -- and leaves the words it cannot serve
+// as one bit per word in tile_pend[]; encode_resolve_kernel then walks those bits and resolves the words 32 at a time with the same
+// flush_pending_words as above.  The stream is cut into chunks (count, resolve, count, resolve) so that a type first seen in one chunk
+// is published before the next chunk is counted.  Measured per GB: FastBPE 1.40 -> 1.15 (1 chunk) / 1.21 ms (2 chunks); FastWP
+// 0.90 -> 0.94 / 0.97 ms (the resolve kernels are exposed latency, which the single kernel hides behind other warps' tiles), so
+// FastWP keeps the single kernel.
+constexpr int kLeafCtasPerSm = 6;
+static __global__ void __launch_bounds__(kThreads, kLeafCtasPerSm)
+encode_count_leaf_kernel(const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words, EncodeWorkspace ws,
+                         const uint32_t *status, uint32_t tile_begin, uint32_t tile_end, uint32_t warm_tiles) {
+    if (many_types_stream(status, warm_tiles)) return;              // such streams stay with the kernel that resolves its misses itself
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * kThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kThreads) >> 5;
+    const uint32_t arena_end = word_off[n_words];
+    const uint8_t *arena_al = reinterpret_cast<const uint8_t *>((uintptr_t)arena & ~(uintptr_t)7);
+    const uint32_t aphase = (uint32_t)((uintptr_t)arena & 7);
+    const uint32_t n_full = n_words / kTileWords;
+    uint32_t po[4] = {0, 0, 0, 0};
+    auto load_offsets = [&](uint32_t t) {
+        const uint32_t *q = word_off + (size_t)t * kTileWords + lane;
+        po[0] = __ldg(q); po[1] = __ldg(q + 1); po[2] = __ldg(q + 32); po[3] = __ldg(q + 33);
+    };
+    uint32_t tile = tile_begin + warp_global;
+    if (tile < tile_end && tile < n_full) load_offsets(tile);
+    for (; tile < tile_end; tile += n_warps) {
+        const uint32_t w_tile = tile * kTileWords;
+        uint32_t rec[kWordsPerThread] = {0u, 0u}, ntok[kWordsPerThread] = {0u, 0u};
+        bool slow[kWordsPerThread] = {false, false}, is_long[kWordsPerThread] = {false, false};
+        const uint32_t o[4] = {po[0], po[1], po[2], po[3]};
+        if (tile + n_warps < tile_end && tile + n_warps < n_full) load_offsets(tile + n_warps);
+        const uint32_t last_start = __shfl_sync(0xffffffffu, o[2], 31);
+        if (tile < n_full && (uint64_t)last_start + 40 <= arena_end) {
+            RowLoads ld[kWordsPerThread];
+            uint32_t nb[kWordsPerThread], pos[kWordsPerThread], slot[kWordsPerThread];
+            uint4 kw[kWordsPerThread], ew[kWordsPerThread];
+#pragma unroll
+            for (int j = 0; j < kWordsPerThread; ++j) { nb[j] = o[2 * j + 1] - o[2 * j]; pos[j] = o[2 * j] + aphase; ld[j] = row_load(arena_al, pos[j]); }
+#pragma unroll
+            for (int j = 0; j < kWordsPerThread; ++j) {
+                kw[j] = row_key(ld[j], pos[j], nb[j]);
+                slot[j] = memo_hash4(kw[j].x, kw[j].y, kw[j].z, kw[j].w) & ws.memo_mask;
+                ew[j] = ld_ca_u32x4(ws.keys + slot[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < kWordsPerThread; ++j) {
+                uint32_t d = key_diff(ew[j], kw[j]);
+                if (d != 0 && (ew[j].x | ew[j].y | ew[j].z | ew[j].w) != 0) {       // another word lives here: try the neighbouring slot
+                    slot[j] = (slot[j] + 1) & ws.memo_mask;
+                    ew[j] = ld_ca_u32x4(ws.keys + slot[j]);
+                    d = key_diff(ew[j], kw[j]);
+                }
+                const uint32_t pub = ew[j].w >> 28;
+                const bool hit = d == 0 && pub - 1u < kPubWide - 1u && nb[j] - 1u < 15u;
+                ntok[j] = hit ? pub : 0u;
+                is_long[j] = nb[j] > (uint32_t)kShortBytes;
+                slow[j] = !hit && !is_long[j];
+                rec[j] = hit ? (kWordHit16 << 29) | (pub << 23) | slot[j] : is_long[j] ? kWordLong << 29 : 0u;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kWordsPerThread; ++j) {
+                const uint32_t w = w_tile + 32u * j + lane;
+                if (w < n_words) {
+                    const uint32_t nbj = __ldg(word_off + w + 1) - __ldg(word_off + w);
+                    is_long[j] = nbj > (uint32_t)kShortBytes;
+                    slow[j] = !is_long[j];
+                    rec[j] = is_long[j] ? kWordLong << 29 : 0u;
+                }
+            }
+        }
+        const uint32_t m0 = __ballot_sync(0xffffffffu, slow[0]), m1 = __ballot_sync(0xffffffffu, slow[1]);
+        if ((m0 | m1) != 0 && lane == 0) ws.tile_pend[tile] = make_uint2(m0, m1);   // (the array was zeroed by the launcher)
+        if (__any_sync(0xffffffffu, is_long[0] || is_long[1])) { if (lane == 0) atomicOr(&ws.long_tiles[tile >> 5], 1u << (tile & 31u)); }
+#pragma unroll
+        for (int j = 0; j < kWordsPerThread; ++j) {
+            const uint32_t w = w_tile + 32u * j + lane;
+            if (w < n_words && !slow[j]) ws.packed[w] = rec[j];
+        }
+        const uint32_t total = __reduce_add_sync(0xffffffffu, ntok[0] + ntok[1]);
+        if (lane == 0) ws.tile_total[tile] = total;
+    }
+}
+
+// resolves the words the leaf kernel left behind: a warp reads the pending masks of 32 tiles at a time, queues the words and flushes
+// the queue 32 words at a time (records and token counts are written by the flush)
+template <class Enc>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+encode_resolve_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words, EncodeWorkspace ws,
+                      uint32_t *status, uint32_t warp_words, uint32_t tile_begin, uint32_t tile_end, uint32_t warm_tiles) {
+    if (many_types_stream(status, warm_tiles)) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * kThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kThreads) >> 5;
+    const uint32_t arena_end = word_off[n_words];
+    __shared__ typename Enc::Stage s_stage;
+    enc.stage_init(s_stage);
+    const typename Enc::Stage *sg = &s_stage;
+    __shared__ uint32_t s_pend[kWarps][96 + 32];
+    uint32_t *pend = s_pend[threadIdx.x >> 5];
+    uint32_t n_pend = 0, n_slow_words = 0, h6 = 0;
+    for (uint32_t tb = tile_begin + warp_global * 32u; tb < tile_end; tb += n_warps * 32u) {
+        const uint32_t my_tile = tb + lane;
+        const uint2 pm = my_tile < tile_end ? ws.tile_pend[my_tile] : make_uint2(0u, 0u);
+        for (uint32_t nz = __ballot_sync(0xffffffffu, (pm.x | pm.y) != 0); nz; nz &= nz - 1) {
+            const uint32_t src = __ffs(nz) - 1, w_tile = (tb + src) * kTileWords;
+#pragma unroll
+            for (int j = 0; j < kWordsPerThread; ++j) {
+                const uint32_t m = __shfl_sync(0xffffffffu, j == 0 ? pm.x : pm.y, src);
+                if (m == 0) continue;                                               // warp-uniform
+                if ((m >> lane) & 1u) pend[n_pend + __popc(m & ((1u << lane) - 1u))] = w_tile + 32u * j + lane;
+                n_pend += __popc(m);
+                __syncwarp();
+                while (n_pend >= 32) {
+                    n_pend -= 32;
+                    h6 += flush_pending_words(enc, sg, ws, arena, word_off, arena_end, status, pend + n_pend, 32, warp_words, pend + 96);
+                    n_slow_words += 32;
+                }
+            }
+        }
+    }
+    if (n_pend) { h6 += flush_pending_words(enc, sg, ws, arena, word_off, arena_end, status, pend, n_pend, warp_words, pend + 96); n_slow_words += n_pend; }
     if (h6) atomicAdd(&status[kStatusH6], h6);
     if (lane == 0 && n_slow_words) atomicAdd(&status[kStatusSlowWords], n_slow_words);
 }
@@ -1140,8 +1285,38 @@ int launch_encode_tiles(const Enc &enc, const uint8_t *d_arena, const uint32_t *
     SWT_CUDA_OK(cudaMemsetAsync(ws.long_tiles, 0, ((size_t)(ws.n_tiles + 31) / 32) * 4, st));
     memo_clear_kernel<<<kNumSMs * 8, 256, 0, st>>>(ws.keys, ws.memo_mask ? ws.memo_mask + 1 : 0u, ws.long_cursor);
     if (timing) cudaEventRecord(ev[1], st);
-    encode_count_kernel<Enc><<<(int)std::min<uint32_t>((uint32_t)grid1, n_ctas), kThreads, 0, st>>>(enc, d_arena, d_word_off, n_words, ws, d_status,
-                                                                                                    (uint32_t)std::max(g_tune.warp_words, 0));
+    const uint32_t warp_words = (uint32_t)std::max(g_tune.warp_words, 0);
+    // warm-up: the first tiles go through the kernel that resolves its misses itself (the memo fills with the frequent types) ...
+    const uint32_t kWarmTiles = (uint32_t)std::max(1, g_tune.split_warm_tiles);     // default 1 M words
+    const bool split = Enc::kSplitCount && g_tune.split_count && ws.memo_mask != 0 && ws.n_tiles > 4 * kWarmTiles;
+    const uint32_t warm_end = split ? kWarmTiles : ws.n_tiles;
+    encode_count_kernel<Enc><<<(int)std::min<uint32_t>((uint32_t)grid1, (warm_end + kWarps - 1) / kWarps), kThreads, 0, st>>>(
+        enc, d_arena, d_word_off, n_words, ws, d_status, warp_words, 0u, warm_end, split ? 1u : 0u, kWarmTiles);
+    if (split) {
+        // ... the rest in chunks: leaf count kernel (probe only), then the resolve kernel for the words it left behind.  A stream whose
+        // warm-up sent more than 1/8 of its words to the slow path has MANY word types: deferring its first occurrences to the end of
+        // a chunk would send every repetition inside the chunk to the slow path too (measured: 2 M types, 5.4 M -> 11.9 M slow words,
+        // 91 -> 76 GB/s),
+        // so the leaf / resolve kernels return at once (device-side gate, no host synchronisation) and the kernel that resolves its
+        // misses itself takes the rest of the stream.
+        static int grid_leaf = 0, grid_res = 0;
+        if (!grid_leaf) {
+            grid_leaf = encode_grid((const void *)encode_count_leaf_kernel, kThreads, 0);
+            grid_res = encode_grid((const void *)encode_resolve_kernel<Enc>, kThreads, 0);
+        }
+        SWT_CUDA_OK(cudaMemsetAsync(ws.tile_pend, 0, (size_t)ws.n_tiles * sizeof(uint2), st));
+        const uint32_t kChunks = (uint32_t)std::max(1, g_tune.split_chunks);
+        const uint32_t per = ((ws.n_tiles - warm_end + kChunks - 1) / kChunks + 31u) & ~31u;
+        for (uint32_t t0 = warm_end; t0 < ws.n_tiles; t0 += per) {
+            const uint32_t t1 = std::min(ws.n_tiles, t0 + per), nt = t1 - t0;
+            encode_count_leaf_kernel<<<(int)std::min<uint32_t>((uint32_t)grid_leaf, (nt + kWarps - 1) / kWarps), kThreads, 0, st>>>(
+                d_arena, d_word_off, n_words, ws, d_status, t0, t1, kWarmTiles);
+            encode_resolve_kernel<Enc><<<(int)std::min<uint32_t>((uint32_t)grid_res, (nt / 32 + kWarps) / kWarps), kThreads, 0, st>>>(
+                enc, d_arena, d_word_off, n_words, ws, d_status, warp_words, t0, t1, kWarmTiles);
+        }
+        encode_count_kernel<Enc><<<(int)std::min<uint32_t>((uint32_t)grid1, (ws.n_tiles - warm_end + kWarps - 1) / kWarps), kThreads, 0, st>>>(
+            enc, d_arena, d_word_off, n_words, ws, d_status, warp_words, warm_end, ws.n_tiles, 2u, kWarmTiles);
+    }
     const int long_grid = (int)std::min<uint32_t>(kNumSMs * 2, ((ws.n_tiles + 31) / 32 + 7) / 8);      // one warp per 32 tiles of the bitmap
     encode_long_count_kernel<Enc><<<long_grid, 256, 0, st>>>(enc, d_arena, d_word_off, n_words, ws, d_status);
     if (timing) cudaEventRecord(ev[2], st);

@@ -281,6 +281,7 @@ struct NaiveWpEnc {
     static constexpr bool kBatchSlowPath = true;
     static constexpr bool kWarpShort = false;
     static constexpr bool kWarpLong = false;
+    static constexpr bool kSplitCount = false;
     __device__ __forceinline__ void stage_init(Stage &) const {}
     __device__ static __forceinline__ bool narrow16(uint32_t id, uint32_t k, uint32_t &v16) { (void)k; v16 = id; return id < 65536u; }
     __device__ static __forceinline__ uint32_t expand16(uint32_t v16, uint32_t k) { (void)k; return v16; }
@@ -310,6 +311,7 @@ struct WpEnc {
     static constexpr bool kBatchSlowPath = true;
     static constexpr bool kWarpShort = false;
     static constexpr bool kWarpLong = true;
+    static constexpr bool kSplitCount = false;    // the single count kernel is faster for this encoder (encode.cuh)
     __device__ __forceinline__ void stage_init(Stage &) const {}
     __device__ static __forceinline__ bool narrow16(uint32_t id, uint32_t k, uint32_t &v16) { (void)k; v16 = id; return id < 65536u; }
     __device__ static __forceinline__ uint32_t expand16(uint32_t v16, uint32_t k) { (void)k; return v16; }

@@ -81,6 +81,45 @@ def test_more_than_2_20_distinct_word_types(P, dev):
         dev.tune("memo_max_log2", 22)
 
 
+def test_split_count_pass_leaf_and_resolve_kernels(P, dev):
+    """FastBPE / NaiveBPE with the split count pass (warm-up kernel, then leaf count + resolve kernels per chunk) forced onto a small
+    stream: many first occurrences after the warm-up, words of 16..32 and more than 32 bytes, empty words, a partial last tile."""
+    import oracle
+    import bench_data as BD
+    mat, lens = BD.synth_type_table(120_000, 3)
+    t_arena, t_off = BD.table_to_utf8(mat, lens)
+    rng = np.random.default_rng(29)
+    draw = np.concatenate([rng.integers(0, 500, size=150_000), np.arange(120_000), rng.integers(0, 120_000, size=100_000)])
+    rng.shuffle(draw)
+    # a prefix of few types: the warm-up (64 tiles here) sees almost no slow-path words, so the split form is taken; without the
+    # prefix (second pass below) the warm-up meets mostly first occurrences and the device-side gate hands the stream to the single kernel
+    draw = np.concatenate([rng.integers(0, 20, size=6000), draw])
+    words = [t_arena[int(t_off[i]):int(t_off[i + 1])].tobytes().decode() for i in draw[:60_000]]
+    words += ["", "x" * 40, "wielkopolskiego" + "ab", "a" * 33, "zażółćgęśląjaźńzażółć"] * 50
+    extra_arena, extra_off = P.pack_words(words)
+    tl = np.diff(t_off)
+    off = np.zeros(len(draw) + 1, dtype=np.int64)
+    np.cumsum(tl[draw], out=off[1:])
+    idx = np.repeat(t_off[:-1][draw] - off[:-1], tl[draw]) + np.arange(off[-1])
+    arena = np.concatenate([t_arena[idx], extra_arena])
+    off = np.concatenate([off, off[-1] + extra_off[1:].astype(np.int64)])
+    merges = [tuple(p) for p in load_golden("pretrained_bpe_merges.json.gz")]
+    btab = P.BpeTables(merges)
+    dev.tune("split_warm_tiles", 64); dev.tune("split_chunks", 3)
+    try:
+        for naive in (False, True):
+            tab = btab if not naive else P.BpeTables(merges[:4000])
+            enc = dev.BpeEncoder(tab, naive=naive)
+            o_ids, o_off = oracle.bpe_encode(tab, arena, off.astype(np.uint64), naive=naive)
+            for skip in (0, 6000):                                      # with / without the prefix of few types
+                a0, t0 = int(off[skip]), int(o_off[skip])
+                ids, tok_off, _ = enc.encode_packed(arena[a0:], (off[skip:] - off[skip]).astype(np.uint32))
+                assert np.array_equal(tok_off.astype(np.uint64), o_off[skip:] - o_off[skip]) and np.array_equal(ids, o_ids[t0:]), (naive, skip)
+            enc.close()
+    finally:
+        dev.tune("split_warm_tiles", 16384); dev.tune("split_chunks", 2)
+
+
 def test_memo_contention_stress(P, dev):
     """The memo protocol under contention (compute-sanitizer is closed on this pool, so the check is a stress test): a handful of
     16..32-byte types that share their 15-byte key prefix, hot short types, and thousands of first occurrences, on every SM at once,
