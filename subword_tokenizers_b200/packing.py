@@ -252,6 +252,10 @@ class BpeTables:
             lut[0::2] = self.id_to_str
             lut[1::2] = ["##" + x for x in self.id_to_str]
             self._str_lut = lut
+        try:                                   # the common case in one call (per-line tokenize() is a few microseconds of Python in total)
+            return lut[toks].tolist()
+        except IndexError:                     # ids outside the table: characters no merge mentions (0x40000000 | cp), the empty word
+            pass
         known = toks < len(lut)
         if known.all():
             return lut[toks].tolist()
