@@ -243,7 +243,8 @@ int swt_tokenize_text_host(swt_pipeline *p, const swt_pretok *pretok, int which,
  * scratch and a stream; a call copies the text into the pinned buffer, launches ONE single-CTA kernel (pre-tokenizer +
  * encoder; no memo, no batching) and synchronises once.  Nothing is allocated per call.  Texts of up to
  * swt_small_max_bytes() bytes; *ids points into the object's output buffer (u32 ids) and stays valid until the next call.
- * which / table / pretok as in swt_tokenize_text_host.  n_words / h6_events may be NULL. */
+ * which / table / pretok as in swt_tokenize_text_host.  n_words / h6_events may be NULL.  One call at a time per swt_small object
+ * (the reference's classes are single-threaded); use one object per host thread otherwise. */
 typedef struct swt_small swt_small;
 int swt_small_create(int device, swt_small **out);
 void swt_small_destroy(swt_small *s);
