@@ -200,3 +200,25 @@ def test_token_id_to_string_tables():
     wt = P.WpTables(["b", "##a", "a"])
     assert wt.tokens_to_strs(np.array([0, 1, 2, 3, 4], dtype=np.uint32)) == ["##a", "a", "b", "['UNK']", "[UNK]"]
     assert wt.tokens_to_strs([]) == []
+
+
+def test_config5_fixture_and_inputs_are_consistent():
+    """The config-5 fixture (tests/golden/make_config5_fixture.py, unmodified reference) belongs to the committed 50 K models and to
+    the deterministic adversarial inputs of tests/golden/config5_inputs.py."""
+    import os
+    import sys
+    import bench_data as BD
+    from conftest import ROOT, load_golden
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from config5_inputs import config5_sentences
+    fixture = load_golden("config5_fixture.json.gz")
+    merges, vocab = load_golden("config5_bpe_merges.json.gz"), load_golden("config5_wp_vocab.json.gz")
+    assert len(vocab) == 50_000 and len(set(vocab)) == 50_000 and 49_000 < len(merges) <= 50_000
+    mat, lens = BD.synth_type_table(300_000, 9)
+    arena, off = BD.table_to_utf8(mat, lens)
+    types = [arena[int(off[k]):int(off[k + 1])].tobytes().decode() for k in range(2000)]
+    s1, s2 = config5_sentences(types, set(vocab)), config5_sentences(types, set(vocab))
+    assert s1 == s2 and len(s1) == fixture["n_sentences"]
+    assert set(fixture["equivalence"]) == {"NaiveBPE/FastBPE", "NaiveWP/FastWP", "FastBPE/FastWP"}
+    assert fixture["equivalence"]["NaiveBPE/FastBPE"][2] == 100.0          # the trained merge list is in training order: Naive == Fast
+    assert fixture["n_tokens"]["NaiveBPE"] == fixture["n_tokens"]["FastBPE"] and fixture["n_tokens"]["NaiveWP"] == fixture["n_tokens"]["FastWP"]
