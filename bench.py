@@ -690,6 +690,26 @@ def main():
         benc.close()
         if world == 1:
             also["fastwp_pretokenize"] = pretok_numbers(dev, d_arena, d_off, n_words, n_bytes)
+            # direct-path rates: the word-type memo disabled, every word is encoded (trie walk / merge loop) -- first 200 MB of the stream
+            try:
+                nw_d = int(torch.searchsorted(d_off[: n_words + 1].long(), 200_000_000).item())
+                nb_d = int(d_off[nw_d].item())
+                device.tune("memo_off", 1)
+                for name, e_d, kind, t_d in (("fastwp_direct", enc, "wp", tab), ("fastbpe_direct", None, "bpe", None)):
+                    if e_d is None:
+                        e_d, t_d = device.BpeEncoder(btab), btab
+                    rd = time_encode(e_d, d_arena[:nb_d + 64], d_off[: nw_d + 1], nw_d, 3, 2, dist, 1)
+                    dn, dok, _, _ = check_prefix(kind, t_d, (prefix[0][: int(prefix[1][200_000])], prefix[1][:200_001]), rd["d_ids"], rd["d_tok"], threads)
+                    also[name] = {"value": nb_d * len(rd["step_ms"]) / (rd["total_ms"] / 1e3) / 1e6, "unit": "MB/s", "ms_per_step": float(np.mean(rd["step_ms"])),
+                                  "bytes": nb_d, "parity_checked_words": dn, "parity_ok": dok,
+                                  "what": "swt_tune(\"memo_off\", 1): no word-type memo, every word goes through the batched direct path"}
+                    del rd
+                    if kind == "bpe":
+                        e_d.close()
+            except Exception as e:                              # noqa: BLE001
+                also["direct_error"] = repr(e)
+            finally:
+                device.tune("memo_off", 0)
     del d_arena, d_off
     enc.close()
     torch.cuda.empty_cache()
