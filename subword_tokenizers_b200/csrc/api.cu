@@ -40,7 +40,7 @@ size_t encode_workspace_layout(uint32_t n_words, uint64_t long_bytes, void *base
     // byte); WP: a 4-word segment record per boundary position of a long chunk (at most one per byte)
     ws->long_scratch_elems = long_bytes ? 4 * long_bytes + 32 * (long_bytes / 33 + 1) : 0;
     ws->long_scratch = cv.take<uint32_t>(ws->long_scratch_elems + 1);
-    ws->flags = g_tune.bulk_store ? kFlagBulkStore : 0u;
+    ws->flags = 0u;
     return cv.used();
 }
 

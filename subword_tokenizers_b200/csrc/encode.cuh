@@ -1,20 +1,27 @@
 // encode.cuh -- the tile kernels shared by all encoders (HP-1 FastBPE, HP-2 FastWP, and the NaiveBPE / NaiveWP encoders).
 //
 // Data flow of one encode call (north-star subsystem 1: packed word-offset/byte arena).  Tile = 64 consecutive words per
-// WARP (2 per lane), tiles assigned round-robin to a persistent grid; warps never synchronise with each other.
+// WARP, two rows of 32 (word w_tile + 32 j + lane on lane `lane`); tiles assigned round-robin to a persistent grid; warps never
+// synchronise with each other.
 //
-//   pass 1  encode_count_kernel   per word: look the word up in the word-type memo; on a miss encode it (rank table /
-//                                 trie walk) and publish the ids.  Writes one packed u32 record per word (kind, token
-//                                 count, memo slot) and the tile's token total.
+//   pass 1  encode_count_kernel   per word: look the word up in the word-type memo (one scattered 16-byte load); rare cases -- first
+//                                 occurrences, words of 16..32 bytes, 14+ tokens -- go to the warp's pending queue and are resolved
+//                                 32 at a time (probe at L2, encode through the rank table / trie, publish).  Writes one packed
+//                                 u32 record per word (kind, token count, memo slot) and the tile's token total.
+//           split form            (Enc::kSplitCount, FastBPE): warm-up by the kernel above, then encode_count_leaf_kernel (probe
+//                                 only, no encoder / calls / stack) + encode_resolve_kernel per chunk of the stream
+//           encode_long_count     words longer than 32 bytes, one warp per flagged tile
 //   scan    two tiny kernels      exclusive scan of the tile totals (in-group prefixes + group bases)
-//   pass 2  encode_emit_kernel    per word: copy the ids memo entry -> the warp's shared-memory buffer at their tile-local
-//                                 position; the tile's ids leave shared memory as ONE bulk copy (cp.async.bulk shared::cta ->
-//                                 global, issued by one lane: no LSU wavefronts) at their final position, u32 token offsets as
-//                                 8-byte stores.
+//   pass 2  encode_emit_kernel    per word: one scattered load of ids16[slot], ids expanded into the warp's shared-memory buffer at
+//                                 their tile-local position; the tile's ids leave shared memory as ONE bulk copy (cp.async.bulk
+//                                 shared::cta -> global, issued by one lane: no LSU wavefronts) at their final position, u32 token
+//                                 offsets as coalesced stores.  encode_long_emit: the ids of long words.
+//   small   tokenize_small_kernel one CTA pre-tokenizes and encodes one short text (the per-line tokenize() call)
 //
-// An earlier single-pass version (decoupled look-back over tile states) was measured slower: with warp-sized tiles
-// the look-back walked hundreds of in-flight predecessors, with CTA-sized tiles the CTA barriers serialised the L2
-// latencies.  The two passes cost 8 extra bytes of HBM traffic per word and have no inter-tile dependency at all.
+// Why two passes: a single pass needs every tile's global token base while the tile is in flight.  With warp-sized tiles a decoupled
+// look-back walked hundreds of in-flight predecessors; with CTA-sized tiles every tile waits for ALL earlier tiles, and a tile that
+// holds a first occurrence (a 10-25 us trie walk) stalls every successor -- head-of-line blocking.  The two passes cost 8 extra bytes
+// of HBM traffic per word and a second scattered load per word, and have no inter-tile dependency at all.
 //
 // Word-type memo: encode_word is a pure function of the word and word streams are
 // Zipf-distributed, so every launch keeps a hash table  word bytes -> token ids  in its workspace.  The first
@@ -102,14 +109,13 @@ struct EncodeWorkspace {
     uint32_t *long_scratch;          // BPE: symbol ping-pong buffers of long words; WP: segment records of long chunks
     uint64_t long_scratch_elems;
     uint32_t n_tiles;
-    uint32_t flags;                  // kFlag*
+    uint32_t flags;                  // (unused)
 };
-enum : uint32_t { kFlagBulkStore = 1u };   // emit pass: tile copy-out with cp.async.bulk (shared::cta -> global)
 
 struct Tuning {                     // process-wide knobs for experiments (swt_tune); defaults are the measured best
     int memo_max_log2 = 22;         // cap of the memo size (10..23)
     int memo_off = 0;               // 1: no memo -- every word takes the direct path (reported as *_direct rates)
-    int bulk_store = 1;             // emit pass copy-out through cp.async.bulk
+    int bulk_store = 1;             // (kept for old experiment scripts: the copy-out is always cp.async.bulk now)
     int timing = 0;                 // per-kernel CUDA-event times of every encode call on stderr (synchronises)
     int warp_words = 3;             // FastBPE: up to this many missed words are encoded by the whole warp, one after the other
     int bpe_queue = 1;              // FastBPE: memo misses go through the warp's pending queue (0: resolved inside their tile)
@@ -958,7 +964,7 @@ static __global__ void __launch_bounds__(1024) encode_scan_top_kernel(EncodeWork
 }
 
 // ---- pass 2: emit ------------------------------------------------------------------------------------------------------
-// Bulk copy-out (kFlagBulkStore): the 16-byte aligned middle of a tile's ids goes shared -> global as one cp.async.bulk issued by
+// Bulk copy-out: the 16-byte aligned middle of a tile's ids goes shared -> global as one cp.async.bulk issued by
 // lane 0 (TMA engine; no LDS/STG wavefronts on the LSU pipe that bounds this kernel), the at most three ids in front of / behind it
 // as scalar stores.  The buffer is reused by the next tile after cp.async.bulk.wait_group.read.
 __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
