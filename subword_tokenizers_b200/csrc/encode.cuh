@@ -642,6 +642,42 @@ encode_count_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *
     if (lane == 0 && n_gate_words) atomicAdd(&status[kStatusWarmSlow], n_gate_words);
 }
 
+// ---- pass 1 without memo (swt_tune("memo_off", 1): the direct-path rates): every lane encodes its own words, no queue ----------------
+template <class Enc>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+encode_count_direct_kernel(Enc enc, const uint8_t *__restrict__ arena, const uint32_t *__restrict__ word_off, uint32_t n_words, EncodeWorkspace ws,
+                           uint32_t *status) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * kThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kThreads) >> 5;
+    __shared__ typename Enc::Stage s_stage;
+    enc.stage_init(s_stage);
+    const typename Enc::Stage *sg = &s_stage;
+    uint32_t h6 = 0;
+    for (uint32_t tile = warp_global; tile < ws.n_tiles; tile += n_warps) {
+        uint32_t total = 0; bool any_long = false;
+#pragma unroll
+        for (int j = 0; j < kWordsPerThread; ++j) {
+            const uint32_t w = tile * kTileWords + 32u * j + lane;
+            uint32_t ntok = 0;
+            if (w < n_words) {
+                const uint32_t b0 = __ldg(word_off + w), nb = __ldg(word_off + w + 1) - b0;
+                if (nb > (uint32_t)kShortBytes) { any_long = true; ws.packed[w] = kWordLong << 29; }
+                else {
+                    uint32_t buf[kShortBytes];
+                    ntok = enc.encode_short(sg, arena + b0, nb, buf, h6);
+                    ws.packed[w] = (kWordRecompute << 29) | (ntok << 23);
+                }
+            }
+            total += ntok;
+        }
+        if (__any_sync(0xffffffffu, any_long)) { if (lane == 0) atomicOr(&ws.long_tiles[tile >> 5], 1u << (tile & 31u)); }
+        total = __reduce_add_sync(0xffffffffu, total);
+        if (lane == 0) ws.tile_total[tile] = total;
+    }
+    if (h6) atomicAdd(&status[kStatusH6], h6);
+    if (lane == 0 && warp_global == 0) atomicAdd(&status[kStatusSlowWords], n_words);
+}
+
 // ---- pass 1, split form: leaf count kernel + resolve kernel ------------------------------------------------------------------------
 // The kernel above carries the slow path (calls, a stack frame, the encoder's tables): the FastBPE instantiations want 98 registers,
 // get 64 and spill inside the tile loop (count pass 1.40 ms per GB against 0.90 ms for FastWP, same fast path).  Once the memo is warm
@@ -1292,6 +1328,11 @@ int launch_encode_tiles(const Enc &enc, const uint8_t *d_arena, const uint32_t *
     memo_clear_kernel<<<kNumSMs * 8, 256, 0, st>>>(ws.keys, ws.memo_mask ? ws.memo_mask + 1 : 0u, ws.long_cursor);
     if (timing) cudaEventRecord(ev[1], st);
     const uint32_t warp_words = (uint32_t)std::max(g_tune.warp_words, 0);
+    if (ws.memo_mask == 0) {                           // memo disabled: the direct path, one lane per word, no queue
+        static int grid_direct = 0;
+        if (!grid_direct) grid_direct = encode_grid((const void *)encode_count_direct_kernel<Enc>, kThreads, 0);
+        encode_count_direct_kernel<Enc><<<(int)std::min<uint32_t>((uint32_t)grid_direct, n_ctas), kThreads, 0, st>>>(enc, d_arena, d_word_off, n_words, ws, d_status);
+    } else {
     // warm-up: the first tiles go through the kernel that resolves its misses itself (the memo fills with the frequent types) ...
     const uint32_t kWarmTiles = (uint32_t)std::max(1, g_tune.split_warm_tiles);     // default 1 M words
     const bool split = Enc::kSplitCount && g_tune.split_count && ws.memo_mask != 0 && ws.n_tiles > 4 * kWarmTiles;
@@ -1322,6 +1363,7 @@ int launch_encode_tiles(const Enc &enc, const uint8_t *d_arena, const uint32_t *
         }
         encode_count_kernel<Enc><<<(int)std::min<uint32_t>((uint32_t)grid1, (ws.n_tiles - warm_end + kWarps - 1) / kWarps), kThreads, 0, st>>>(
             enc, d_arena, d_word_off, n_words, ws, d_status, warp_words, warm_end, ws.n_tiles, 2u, kWarmTiles);
+    }
     }
     const int long_grid = (int)std::min<uint32_t>(kNumSMs * 2, ((ws.n_tiles + 31) / 32 + 7) / 8);      // one warp per 32 tiles of the bitmap
     encode_long_count_kernel<Enc><<<long_grid, 256, 0, st>>>(enc, d_arena, d_word_off, n_words, ws, d_status);

@@ -449,3 +449,35 @@ def test_config5_compare_equivalence_at_50k_vocab(hf_tokenizer, tmp_path):
         a, b = pair.split("/")
         got = _token_sequence_equivalence(toks[a], toks[b], sentences)
         assert got == want, (pair, got, want)
+
+
+def test_direct_path_without_memo_equals_oracle(P, dev):
+    """swt_tune("memo_off", 1): no word-type memo, every word is encoded by its own lane in the count pass and again in the emit pass
+    (the direct-path rates of bench.py).  All four encoders against the oracle, with empty, 16..32-byte and long words."""
+    import oracle
+    from subword_tokenizers_b200.utils import naive_wp_encode_ids
+    rng = np.random.default_rng(37)
+    alphabet = list("abcdeiknorstwyzłóżę") + list(".,-'")
+    words = ["".join(rng.choice(alphabet, size=int(rng.integers(1, 24)))) for _ in range(40_000)]
+    words += ["", "x" * 33, "a" * 200, "wielkopolskiegoab", "zażółćgęśląjaźń"] * 20
+    arena, off = P.pack_words(words)
+    merges = [tuple(p) for p in load_golden("pretrained_bpe_merges.json.gz")]
+    vocab = load_golden("pretrained_wp_vocab.json.gz")
+    alnum, space = P.unicode_class_bitmaps()
+    dev.tune("memo_off", 1)
+    try:
+        for naive in (False, True):
+            btab = P.BpeTables(merges if not naive else merges[:3000])
+            benc = dev.BpeEncoder(btab, naive=naive)
+            ids, tok_off, _ = benc.encode_packed(arena, off.astype(np.uint32))
+            o_ids, o_off = oracle.bpe_encode(btab, arena, off, naive=naive)
+            assert np.array_equal(tok_off.astype(np.uint64), o_off) and np.array_equal(ids, o_ids), ("bpe", naive)
+            benc.close()
+        wtab = P.WpTables(vocab)
+        wenc = dev.WpEncoder(wtab, naive_wp_encode_ids("##", wtab))
+        ids, tok_off, h6 = wenc.encode_packed(arena, off.astype(np.uint32))
+        o_ids, o_off, o_h6 = oracle.WpTrie(wtab, alnum).encode(arena, off, space)
+        assert np.array_equal(tok_off.astype(np.uint64), o_off) and np.array_equal(ids, o_ids) and h6 == o_h6
+        wenc.close()
+    finally:
+        dev.tune("memo_off", 0)
