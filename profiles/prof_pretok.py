@@ -9,7 +9,7 @@ from subword_tokenizers_b200.utils import naive_wp_encode_ids
 
 nbytes = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000_000
 dev = torch.device("cuda", 0)
-stream = bench.ZipfStream(0)
+stream = bench.ZipfStream.train5k(0)
 d_arena, d_off, n_words, off32 = stream.device_stream(nbytes, dev)
 d_text, n_text = bench.device_text(d_arena, d_off, n_words)
 tab = P.WpTables(bench.load_golden("ref_wp_train5k_v8000_vocab.json.gz"))
